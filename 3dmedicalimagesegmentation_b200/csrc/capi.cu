@@ -1,0 +1,236 @@
+// extern "C" surface of libunetr_b200.so (declared in include/unetr_b200.h).
+#include <stdarg.h>
+
+#include <algorithm>
+#include <map>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/unetr_b200.h"
+#include "exec.cuh"
+#include "loss.cuh"
+#include "sliding.cuh"
+#include "tc_gemm.cuh"
+
+namespace b200 {
+static thread_local char g_err[1024] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* get_error() { return g_err; }
+
+unsigned long long g_launches = 0;
+bool g_prof_on = false;
+struct ProfRec { std::string tag; cudaEvent_t a, b; };
+static std::vector<ProfRec> g_prof;
+void prof_begin(const char* tag, cudaStream_t st) {
+  ProfRec r; r.tag = tag;
+  cudaEventCreate(&r.a); cudaEventCreate(&r.b);
+  cudaEventRecord(r.a, st);
+  g_prof.push_back(r);
+}
+void prof_end(cudaStream_t st) { cudaEventRecord(g_prof.back().b, st); }
+
+struct Handle {
+  UnetrConfig cfg;
+  Exec<float>* f32;
+  Exec<bf16>* b16;
+};
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" {
+
+const char* b200_last_error(void) { return get_error(); }
+
+int b200_device_check(void) {
+  int dev = 0;
+  B200_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp p;
+  B200_CUDA(cudaGetDeviceProperties(&p, dev));
+  B200_CHECK(p.major == 10, "libunetr_b200 is built for sm_100a only; device %s is sm_%d%d", p.name, p.major, p.minor);
+  return 0;
+}
+
+void* b200_unetr_create(const b200_unetr_config* c) {
+  if (!c) { set_error("null config"); return nullptr; }
+  if (c->img0 % 16 || c->img1 % 16 || c->img2 % 16 || c->img0 <= 0 || c->img1 <= 0 || c->img2 <= 0) {
+    set_error("img_size must be positive multiples of the 16^3 patch (unetr.py:70)"); return nullptr;
+  }
+  if (c->hidden_size % c->num_heads) { set_error("hidden size should be divisible by num_heads."); return nullptr; }
+  int fs = c->feature_size;
+  if (fs < 8 || (fs & (fs - 1))) { set_error("feature_size must be a power of two >= 8 (got %d)", fs); return nullptr; }
+  if (c->hidden_size % 8 || c->mlp_dim % 8) { set_error("hidden_size and mlp_dim must be multiples of 8"); return nullptr; }
+  if (c->batch < 1 || c->in_channels < 1 || c->out_channels < 1 || c->out_channels > 32) {
+    set_error("batch/in_channels/out_channels out of range (out_channels <= 32)"); return nullptr;
+  }
+  Handle* h = new (std::nothrow) Handle();
+  if (!h) { set_error("out of host memory"); return nullptr; }
+  h->cfg = UnetrConfig{c->batch, c->in_channels, c->out_channels, c->img0, c->img1, c->img2, fs, c->hidden_size, c->mlp_dim,
+                       c->num_heads, c->conv_patch_embed, c->mode};
+  h->f32 = nullptr; h->b16 = nullptr;
+  if (c->mode == 0) h->f32 = new Exec<float>(h->cfg); else h->b16 = new Exec<bf16>(h->cfg);
+  return h;
+}
+void b200_unetr_destroy(void* handle) {
+  Handle* h = (Handle*)handle;
+  if (!h) return;
+  delete h->f32; delete h->b16; delete h;
+}
+size_t b200_unetr_workspace_bytes(void* handle, int with_backward) {
+  Handle* h = (Handle*)handle;
+  if (h->f32) { h->f32->layout(nullptr, with_backward != 0); return h->f32->w.bytes; }
+  h->b16->layout(nullptr, with_backward != 0); return h->b16->w.bytes;
+}
+int b200_unetr_forward(void* handle, const float* const* params, const float* x, void* workspace, float* enc4_out,
+                       float* logits_out, int flags, void* stream) {
+  Handle* h = (Handle*)handle;
+  B200_CHECK(h && params && x && workspace, "b200_unetr_forward: null argument");
+  if (h->f32) return h->f32->forward(params, x, (char*)workspace, enc4_out, logits_out, flags, (cudaStream_t)stream);
+  return h->b16->forward(params, x, (char*)workspace, enc4_out, logits_out, flags, (cudaStream_t)stream);
+}
+int b200_unetr_backward(void* handle, const float* const* params, float* const* grads, const float* x, void* workspace,
+                        const float* d_enc4, const float* d_logits, int flags, void* stream) {
+  Handle* h = (Handle*)handle;
+  B200_CHECK(h && params && grads && x && workspace, "b200_unetr_backward: null argument");
+  if (h->f32) return h->f32->backward(params, grads, x, (char*)workspace, d_enc4, d_logits, flags, (cudaStream_t)stream);
+  return h->b16->backward(params, grads, x, (char*)workspace, d_enc4, d_logits, flags, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------- DiceCE
+// scratch: double acc[B*C*3+1] | float coef[B*C*2]
+size_t b200_dicece_scratch_bytes(int B, int C) { return sizeof(double) * ((size_t)B * C * 3 + 2) + sizeof(float) * (size_t)B * C * 2; }
+int b200_dicece_forward(const float* logits, const float* labels, int B, int C, int64_t V, void* scratch, float* out3, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  B200_CHECK(C >= 1 && C <= 32, "DiceCE supports 1..32 classes (got %d)", C);
+  double* acc = (double*)scratch;
+  float* coef = (float*)(acc + (size_t)B * C * 3 + 2);
+  B200_CUDA(cudaMemsetAsync(acc, 0, sizeof(double) * ((size_t)B * C * 3 + 2), st));
+  dim3 g((unsigned)max(1L, min(148L * 8 / B + 1, (long)((V + 255) / 256))), B);
+  if (C <= 16) dicece_fwd_kernel<16><<<g, 256, 0, st>>>(logits, labels, C, V, acc, B * C);
+  else dicece_fwd_kernel<32><<<g, 256, 0, st>>>(logits, labels, C, V, acc, B * C);
+  B200_LAUNCH_CHECK();
+  dicece_finalize_kernel<<<1, 256, 0, st>>>(acc, B, C, V, out3, coef);
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+int b200_dicece_backward(const float* logits, const float* labels, int B, int C, int64_t V, const void* scratch,
+                         const float* upstream, float* dlogits, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  B200_CHECK(C >= 1 && C <= 32, "DiceCE supports 1..32 classes (got %d)", C);
+  const float* coef = (const float*)((const double*)scratch + (size_t)B * C * 3 + 2);
+  dim3 g((unsigned)max(1L, min(148L * 8 / B + 1, (long)((V + 255) / 256))), B);
+  if (C <= 16) dicece_bwd_kernel<16><<<g, 256, 0, st>>>(logits, labels, coef, upstream, B, C, V, dlogits);
+  else dicece_bwd_kernel<32><<<g, 256, 0, st>>>(logits, labels, coef, upstream, B, C, V, dlogits);
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------- ranking loss
+// scratch: double gram[C*256] | double loss | float coef[C*256]
+size_t b200_ranking_scratch_bytes(int C) { return sizeof(double) * ((size_t)C * 256 + 2) + sizeof(float) * (size_t)C * 256; }
+static RankGeom to_geom(const b200_rank_geom* g) {
+  RankGeom r;
+  for (int i = 0; i < 4; ++i) { r.src[i] = g->src[i]; r.grad[i] = g->grad[i]; r.idx[i] = g->idx[i]; }
+  r.sc = g->stride_c; r.ss = g->stride_slice; r.sf0 = g->stride_f0; r.sf1 = g->stride_f1;
+  r.C = g->channels; r.F0 = g->f0; r.F1 = g->f1; r.temperature = g->temperature;
+  return r;
+}
+int b200_ranking_forward(const b200_rank_geom* g, void* scratch, float* loss_out, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  B200_CHECK(g && scratch && loss_out, "b200_ranking_forward: null argument");
+  RankGeom r = to_geom(g);
+  double* gram = (double*)scratch; double* loss = gram + (size_t)r.C * 256;
+  float* coef = (float*)(loss + 2);
+  B200_CUDA(cudaMemsetAsync(gram, 0, sizeof(double) * ((size_t)r.C * 256 + 2), st));
+  int F = r.F0 * r.F1;
+  int splits = max(1, min(cdiv(F, 64), cdiv(148 * 2, r.C)));
+  rank_gram_kernel<<<dim3(r.C, splits), 256, 0, st>>>(r, gram);
+  B200_LAUNCH_CHECK();
+  rank_loss_kernel<<<r.C, 576, 0, st>>>(gram, r.C, r.temperature, loss, coef);
+  B200_LAUNCH_CHECK();
+  cast_kernel<double, float><<<1, 32, 0, st>>>(loss, loss_out, 1);
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+int b200_ranking_backward(const b200_rank_geom* g, const void* scratch, const float* upstream, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  RankGeom r = to_geom(g);
+  const float* coef = (const float*)((const double*)scratch + (size_t)r.C * 256 + 2);
+  int F = r.F0 * r.F1;
+  rank_grad_kernel<<<dim3(r.C, cdiv(F, 256)), 256, 0, st>>>(r, coef, upstream);
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------- sliding window
+static SwGeom to_sw(const b200_sw_geom* g) {
+  return SwGeom{g->channels, g->d, g->h, g->w, g->pad_d, g->pad_h, g->pad_w, g->padded_d, g->padded_h, g->padded_w, g->roi0, g->roi1, g->roi2};
+}
+int b200_sw_gather(const float* volume, float* windows, const b200_sw_geom* g, const int32_t* starts, int n, float cval, void* stream) {
+  B200_CHECK(n >= 1 && n <= 16, "sw_gather takes 1..16 windows per call");
+  SwBatch wb; wb.n = n;
+  for (int i = 0; i < n; ++i) wb.w[i] = SwWindow{starts[4 * i], starts[4 * i + 1], starts[4 * i + 2], starts[4 * i + 3]};
+  SwGeom sg = to_sw(g);
+  long total = (long)sg.C * sg.r0 * sg.r1 * sg.r2 * n;
+  sw_gather_kernel<<<(unsigned)min(148L * 16, (total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(volume, windows, sg, wb, cval);
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+int b200_sw_accumulate(float* acc, const float* pred, const b200_sw_geom* g, const int32_t* s, void* stream) {
+  SwGeom sg = to_sw(g);
+  long per = (long)sg.C * sg.r0 * sg.r1 * sg.r2;
+  sw_accumulate_kernel<<<(unsigned)min(148L * 16, (per + 255) / 256), 256, 0, (cudaStream_t)stream>>>(acc, pred, sg, SwWindow{s[0], s[1], s[2], s[3]});
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+int b200_sw_finalize(const float* acc, float* out, uint8_t* mask, const b200_sw_geom* g, int batch, const int32_t* s0, int n0,
+                     const int32_t* s1, int n1, const int32_t* s2, int n2, void* stream) {
+  B200_CHECK(n0 <= 64 && n1 <= 64 && n2 <= 64, "more than 64 window starts along one axis");
+  SwStarts st; st.n0 = n0; st.n1 = n1; st.n2 = n2;
+  for (int i = 0; i < n0; ++i) st.s0[i] = s0[i];
+  for (int i = 0; i < n1; ++i) st.s1[i] = s1[i];
+  for (int i = 0; i < n2; ++i) st.s2[i] = s2[i];
+  SwGeom sg = to_sw(g);
+  long total = (long)batch * sg.D * sg.H * sg.W;
+  sw_finalize_kernel<<<(unsigned)min(148L * 16, (total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(acc, out, mask, sg, st, batch);
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+
+unsigned long long b200_launch_count(void) { return g_launches; }
+void b200_prof_enable(int on) { g_prof_on = on != 0; }
+/* synchronises the device, writes "tag ms count\n" lines (sorted by time) and clears the records */
+int b200_prof_report(char* buf, int cap) {
+  cudaDeviceSynchronize();
+  std::map<std::string, std::pair<double, int>> acc;
+  for (auto& r : g_prof) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, r.a, r.b);
+    auto& e = acc[r.tag]; e.first += ms; e.second += 1;
+    cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+  }
+  g_prof.clear();
+  std::vector<std::pair<double, std::string>> v;
+  for (auto& kv : acc) v.push_back({kv.second.first, kv.first});
+  std::sort(v.rbegin(), v.rend());
+  int off = 0;
+  for (auto& e : v) {
+    int n = snprintf(buf + off, cap - off, "%s %.4f %d\n", e.second.c_str(), e.first, acc[e.second].second);
+    if (n < 0 || off + n >= cap) break;
+    off += n;
+  }
+  if (cap > 0) buf[off < cap ? off : cap - 1] = 0;
+  return 0;
+}
+
+int b200_test_tc_gemm(const void* a, const void* b, float* out, int M, int N, int K, int a_mn, int b_mn, void* stream) {
+  return tc_gemm_test((const bf16*)a, (const bf16*)b, out, M, N, K, a_mn, b_mn, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,121 @@
+// Shared device/host helpers for the B200 UNETR library (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+namespace b200 {
+
+typedef __nv_bfloat16 bf16;
+
+// ---- error plumbing: every C-ABI entry returns 0 or a code; text via b200_last_error() ----
+void set_error(const char* fmt, ...);
+const char* get_error();
+
+#define B200_CHECK(cond, ...)            \
+  do {                                   \
+    if (!(cond)) {                       \
+      b200::set_error(__VA_ARGS__);      \
+      return 1;                          \
+    }                                    \
+  } while (0)
+
+#define B200_CUDA(expr)                                                              \
+  do {                                                                               \
+    cudaError_t _e = (expr);                                                         \
+    if (_e != cudaSuccess) {                                                         \
+      b200::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return 2;                                                                      \
+    }                                                                                \
+  } while (0)
+
+#define B200_LAUNCH_CHECK()        \
+  do {                             \
+    ++b200::g_launches;            \
+    B200_CUDA(cudaGetLastError()); \
+  } while (0)
+
+#define B200_TRY(...)        \
+  do {                       \
+    int _rc = (__VA_ARGS__); \
+    if (_rc) return _rc;     \
+  } while (0)
+
+// ---- launch counter + optional per-op CUDA-event profiler (b200_prof_* in the C ABI) ----
+extern unsigned long long g_launches;
+void prof_begin(const char* tag, cudaStream_t st);
+void prof_end(cudaStream_t st);
+extern bool g_prof_on;
+struct ProfScope {
+  cudaStream_t st; bool active;
+  ProfScope(const char* tag, cudaStream_t s) : st(s), active(g_prof_on) { if (active) prof_begin(tag, st); }
+  ~ProfScope() { if (active) prof_end(st); }
+};
+#define B200_PROF(tag, st) b200::ProfScope _prof_scope(tag, st)
+
+// ---- scalar conversions ----
+__device__ __forceinline__ float to_f(float v) { return v; }
+__device__ __forceinline__ float to_f(bf16 v) { return __bfloat162float(v); }
+__device__ __forceinline__ float to_f(double v) { return (float)v; }
+template <class T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ bf16 from_f<bf16>(float v) { return __float2bfloat16_rn(v); }
+
+// ---- 16-byte vectors of T viewed as floats ----
+template <class T> struct Vec16;
+template <> struct Vec16<float> {
+  static constexpr int N = 4;
+  float v[4];
+  __device__ __forceinline__ void load(const float* p) {
+    float4 t = *reinterpret_cast<const float4*>(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
+  __device__ __forceinline__ void store(float* p) const {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+};
+template <> struct Vec16<bf16> {
+  static constexpr int N = 8;
+  float v[8];
+  __device__ __forceinline__ void load(const bf16* p) {
+    uint4 t = *reinterpret_cast<const uint4*>(p);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float2 f = __bfloat1622float2(h[i]);
+      v[2 * i] = f.x; v[2 * i + 1] = f.y;
+    }
+  }
+  __device__ __forceinline__ void store(bf16* p) const {
+    uint4 t;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&t);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    *reinterpret_cast<uint4*>(p) = t;
+  }
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float gelu_erf_grad(float x) {
+  float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
+  float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
+  return cdf + x * pdf;
+}
+__device__ __forceinline__ float lrelu(float x) { return x > 0.f ? x : 0.01f * x; }
+
+static inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
+
+}  // namespace b200

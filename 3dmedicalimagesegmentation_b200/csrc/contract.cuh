@@ -1,0 +1,237 @@
+// Generic CUDA-core contraction  D[m,n] = sum_k A(m,k) * B(n,k)  with functor operand loaders and
+// epilogues.  This is the fp32 "parity mode" engine (logits within 1e-4 of the fp32 oracle need true
+// fp32 FMAs -- tcgen05 has no fp32-input MMA) and the bring-up path for any op whose
+// tcgen05 kernel is not in place yet.  Every conv / transposed conv / patch-embedding / linear layer of
+// UNETR, forward, dgrad and wgrad, is one instantiation of this template.
+#pragma once
+#include "common.cuh"
+
+namespace b200 {
+
+// ------------------------------------------------------------------ operand loaders
+// A-loaders:  float operator()(int batch, int m, int k)      B-loaders: float operator()(int batch, int n, int k)
+// kOuterFast: the outer index (m or n) is the memory-contiguous one (drives the tile-load thread mapping).
+
+template <class T, bool OuterFast = false>
+struct LdStrided {
+  static constexpr bool kOuterFast = OuterFast;
+  const T* p; long so, sk, sb0, sb1; int nb1;
+  __device__ __forceinline__ float operator()(int b, int o, int k) const {
+    return to_f(p[(long)(b / nb1) * sb0 + (long)(b % nb1) * sb1 + (long)o * so + (long)k * sk]);
+  }
+};
+
+// Channels-last voxel gather for k^3 convolutions (k in {1,3}, stride 1, zero pad (k-1)/2).
+// get(v, j): v = flat voxel over [N,D,H,W]; j = tap*C+c (TapMajor) or c*taps+tap.
+// sign=+1 reads x[v + (tap-pad)] (forward / wgrad), sign=-1 reads x[v - (tap-pad)] (dgrad).
+template <class T, bool TapMajor>
+struct ConvGather {
+  const T* x; int D, H, W, pitch, coff, C, ks, sign;
+  __device__ __forceinline__ float get(int v, int j) const {
+    int taps = ks * ks * ks;
+    int tap, c;
+    if (TapMajor) { tap = j / C; c = j - tap * C; } else { c = j / taps; tap = j - c * taps; }
+    int pad = ks >> 1;
+    int kw = tap % ks, kh = (tap / ks) % ks, kd = tap / (ks * ks);
+    int w = v % W; int t = v / W; int h = t % H; t /= H; int d = t % D; int n = t / D;
+    d += sign * (kd - pad); h += sign * (kh - pad); w += sign * (kw - pad);
+    if ((unsigned)d >= (unsigned)D || (unsigned)h >= (unsigned)H || (unsigned)w >= (unsigned)W) return 0.f;
+    return to_f(x[((((long)n * D + d) * H + h) * W + w) * pitch + coff + c]);
+  }
+};
+
+// Gather for the transposed conv k2 s2: get(v, j) with v = flat INPUT voxel [N,D,H,W], j = co*8+tap,
+// reads y (the 2x up-sampled tensor, channels-last) at (2d+a, 2h+b, 2w+c).
+template <class T>
+struct ConvTGather {
+  const T* y; int D, H, W, pitch, coff;
+  __device__ __forceinline__ float get(int v, int j) const {
+    int co = j >> 3, tap = j & 7;
+    int w = v % W; int t = v / W; int h = t % H; t /= H; int d = t % D; int n = t / D;
+    long pos = (((long)n * 2 * D + 2 * d + (tap >> 2)) * 2 * H + 2 * h + ((tap >> 1) & 1)) * 2 * W + 2 * w + (tap & 1);
+    return to_f(y[pos * pitch + coff + co]);
+  }
+};
+
+// 16^3 patch rows straight from the NCDHW fp32 volume (MONAI PatchEmbeddingBlock).
+// get(tok, k): perceptron k = ((p1*16+p2)*16+p3)*C + c ; conv k = c*4096 + (p1*16+p2)*16+p3.
+struct PatchGather {
+  const float* x; int C, S0, S1, S2, g0, g1, g2, conv_order;
+  __device__ __forceinline__ float get(int tok, int k) const {
+    int c, p;
+    if (conv_order) { c = k >> 12; p = k & 4095; } else { c = k % C; p = k / C; }
+    int p3 = p & 15, p2 = (p >> 4) & 15, p1 = p >> 8;
+    int d = tok % g2; int t = tok / g2; int w = t % g1; t /= g1; int h = t % g0; int b = t / g0;
+    return x[((((long)b * C + c) * S0 + h * 16 + p1) * S1 + w * 16 + p2) * S2 + d * 16 + p3];
+  }
+};
+
+// NCDHW fp32 tensor read as [voxel, channel]
+struct NcdhwGather {
+  const float* p; int C; long V;
+  __device__ __forceinline__ float get(int v, int c) const {
+    long b = v / V; long vv = v - b * V;
+    return p[(b * C + c) * V + vv];
+  }
+};
+
+// adapters: gather functor G::get(row, col) used in either operand role
+template <class G, bool OuterFast> struct RowIsOuter {   // op(b, o, k) = g(o, k)
+  static constexpr bool kOuterFast = OuterFast; G g;
+  __device__ __forceinline__ float operator()(int, int o, int k) const { return g.get(o, k); }
+};
+template <class G, bool OuterFast> struct RowIsK {       // op(b, o, k) = g(k, o)
+  static constexpr bool kOuterFast = OuterFast; G g;
+  __device__ __forceinline__ float operator()(int, int o, int k) const { return g.get(k, o); }
+};
+
+// PyTorch Conv3d weight [Co][Ci][taps] (fp32 master) as the B operand.
+//   forward: n = co, k = tap*Ci+ci          dgrad: n = ci, k = tap*Co+co
+struct ConvWeightB {
+  static constexpr bool kOuterFast = false;
+  const float* w; int Ci, Co, taps, dgrad;
+  __device__ __forceinline__ float operator()(int, int n, int k) const {
+    if (!dgrad) { int tap = k / Ci, ci = k - tap * Ci; return w[((long)n * Ci + ci) * taps + tap]; }
+    int tap = k / Co, co = k - tap * Co; return w[((long)co * Ci + n) * taps + tap];
+  }
+};
+
+// ------------------------------------------------------------------ epilogues:  void operator()(b, m, n, acc)
+enum { ACT_NONE = 0, ACT_GELU = 1, ACT_GELU_BWD = 2 };
+
+template <class TO>
+struct EpStore {
+  TO* out; long ld, sb0, sb1; int nb1;
+  const float* bias; const float* resid; long ldr; TO* preact; const TO* usrc; int act; int accumulate; float alpha;
+  __device__ __forceinline__ void operator()(int b, int m, int n, float acc) const {
+    long o = (long)(b / nb1) * sb0 + (long)(b % nb1) * sb1 + (long)m * ld + n;
+    float v = acc * alpha;
+    if (bias) v += bias[n];
+    if (preact) preact[o] = from_f<TO>(v);
+    if (act == ACT_GELU) v = gelu_erf(v);
+    else if (act == ACT_GELU_BWD) v *= gelu_erf_grad(to_f(usrc[o]));
+    if (resid) v += resid[(long)m * ldr + n];
+    if (accumulate) v += to_f(out[o]);
+    out[o] = from_f<TO>(v);
+  }
+};
+template <class TO> static inline EpStore<TO> ep_plain(TO* out, long ld) {
+  EpStore<TO> e; memset(&e, 0, sizeof(e)); e.out = out; e.ld = ld; e.nb1 = 1; e.alpha = 1.f; return e;
+}
+
+struct EpPatch {  // tokens = acc + bias + position embedding
+  float* out; int H, L; const float* bias; const float* pos;
+  __device__ __forceinline__ void operator()(int, int m, int n, float acc) const {
+    out[(long)m * H + n] = acc + bias[n] + pos[(long)(m % L) * H + n];
+  }
+};
+
+struct EpAtomic {  // split-K weight gradients
+  float* out; long ld;
+  __device__ __forceinline__ void operator()(int, int m, int n, float acc) const { atomicAdd(out + (long)m * ld + n, acc); }
+};
+
+template <class TO>
+struct EpConvTScatter {  // m = input voxel, n = co*8+tap -> channels-last 2x up-sampled output
+  TO* out; int D, H, W, pitch, coff;
+  __device__ __forceinline__ void operator()(int, int m, int n, float acc) const {
+    int co = n >> 3, tap = n & 7;
+    int w = m % W; int t = m / W; int h = t % H; t /= H; int d = t % D; int nb = t / D;
+    long pos = (((long)nb * 2 * D + 2 * d + (tap >> 2)) * 2 * H + 2 * h + ((tap >> 1) & 1)) * 2 * W + 2 * w + (tap & 1);
+    out[pos * pitch + coff + co] = from_f<TO>(acc);
+  }
+};
+
+struct EpHeadNcdhw {  // logits[b][co][v] = acc + bias[co]
+  float* out; int Co; long V; const float* bias;
+  __device__ __forceinline__ void operator()(int, int m, int n, float acc) const {
+    long b = m / V; long vv = m - b * V;
+    out[(b * Co + n) * V + vv] = acc + bias[n];
+  }
+};
+
+// ------------------------------------------------------------------ the kernel
+template <class AL, class BL, class EP, int BM, int BN, int TM, int TN>
+__global__ void __launch_bounds__(256) contract_kernel(AL al, BL bl, EP ep, int M, int N, int K, int nsplit, int kchunk) {
+  constexpr int BK = 16;
+  static_assert((BM / TM) * (BN / TN) == 256, "256 threads");
+  __shared__ __align__(16) float As[BK][BM + 4];
+  __shared__ __align__(16) float Bs[BK][BN + 4];
+  const int tid = threadIdx.x;
+  const int batch = blockIdx.z / nsplit, split = blockIdx.z % nsplit;
+  const int k_begin = split * kchunk, k_end = min(K, k_begin + kchunk);
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const int tn = tid % (BN / TN), tm = tid / (BN / TN);
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+  for (int k0 = k_begin; k0 < k_end; k0 += BK) {
+#pragma unroll
+    for (int e = tid; e < BM * BK; e += 256) {
+      int ml, kl;
+      if (AL::kOuterFast) { ml = e % BM; kl = e / BM; } else { kl = e % BK; ml = e / BK; }
+      int m = m0 + ml, k = k0 + kl;
+      As[kl][ml] = (m < M && k < k_end) ? al(batch, m, k) : 0.f;
+    }
+#pragma unroll
+    for (int e = tid; e < BN * BK; e += 256) {
+      int nl, kl;
+      if (BL::kOuterFast) { nl = e % BN; kl = e / BN; } else { kl = e % BK; nl = e / BK; }
+      int n = n0 + nl, k = k0 + kl;
+      Bs[kl][nl] = (n < N && k < k_end) ? bl(batch, n, k) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      float a[TM], b[TN];
+#pragma unroll
+      for (int i = 0; i < TM; ++i) a[i] = As[kk][tm * TM + i];
+#pragma unroll
+      for (int j = 0; j < TN; ++j) b[j] = Bs[kk][tn * TN + j];
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    int m = m0 + tm * TM + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      int n = n0 + tn * TN + j;
+      if (n < N) ep(batch, m, n, acc[i][j]);
+    }
+  }
+}
+
+// Host launcher.  nsplit>1 requires an atomic epilogue.
+template <class AL, class BL, class EP>
+static int launch_contract(const AL& al, const BL& bl, const EP& ep, int M, int N, int K, int batch, int nsplit,
+                           cudaStream_t st) {
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  int kchunk = ((cdiv(K, nsplit) + 15) / 16) * 16;
+  nsplit = cdiv(K, kchunk);
+  if (N <= 16 && M <= 16) {
+    dim3 g(1, 1, batch * nsplit);
+    contract_kernel<AL, BL, EP, 16, 16, 1, 1><<<g, 256, 0, st>>>(al, bl, ep, M, N, K, nsplit, kchunk);
+  } else if (N <= 16) {
+    dim3 g(cdiv(M, 256), cdiv(N, 16), batch * nsplit);
+    contract_kernel<AL, BL, EP, 256, 16, 4, 4><<<g, 256, 0, st>>>(al, bl, ep, M, N, K, nsplit, kchunk);
+  } else if (N <= 32) {
+    dim3 g(cdiv(M, 128), cdiv(N, 32), batch * nsplit);
+    contract_kernel<AL, BL, EP, 128, 32, 4, 4><<<g, 256, 0, st>>>(al, bl, ep, M, N, K, nsplit, kchunk);
+  } else {
+    dim3 g(cdiv(M, 64), cdiv(N, 64), batch * nsplit);
+    contract_kernel<AL, BL, EP, 64, 64, 4, 4><<<g, 256, 0, st>>>(al, bl, ep, M, N, K, nsplit, kchunk);
+  }
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace b200

@@ -1,0 +1,439 @@
+// HBM-bound kernels of the UNETR path: layout casts, LayerNorm, softmax, InstanceNorm(+LeakyReLU,+residual),
+// column sums.  All take channels-last activations of type T (float = parity mode, bf16 = throughput mode),
+// use 16-byte accesses and keep statistics in fp32/fp64.
+#pragma once
+#include "common.cuh"
+
+namespace b200 {
+
+// ------------------------------------------------------------------ layout / casts
+// dir 0: NCDHW fp32 -> channels-last T (dst[(n*V+v)*pitch+coff+c]); accumulate adds into dst.
+// dir 1: channels-last T -> NCDHW fp32.
+template <class T>
+__global__ void layout_kernel(const float* __restrict__ ncdhw_in, float* __restrict__ ncdhw_out, T* cl, int C, long V,
+                              int pitch, int coff, int dir, int accumulate, long total) {
+  // 32x32 smem transpose over (c, v) tiles of one sample
+  __shared__ float tile[32][33];
+  long tiles_v = (V + 31) / 32; int tiles_c = (C + 31) / 32;
+  long t = blockIdx.x; int n = (int)(t / (tiles_v * tiles_c)); long r = t % (tiles_v * tiles_c);
+  int tc = (int)(r / tiles_v); long tv = r % tiles_v;
+  int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+  if (dir == 0) {
+    for (int i = ty; i < 32; i += 8) {
+      int c = tc * 32 + i; long v = tv * 32 + tx;
+      tile[i][tx] = (c < C && v < V) ? ncdhw_in[((long)n * C + c) * V + v] : 0.f;
+    }
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8) {
+      long v = tv * 32 + i; int c = tc * 32 + tx;
+      if (c < C && v < V) {
+        long o = ((long)n * V + v) * pitch + coff + c;
+        float val = tile[tx][i];
+        if (accumulate) val += to_f(cl[o]);
+        cl[o] = from_f<T>(val);
+      }
+    }
+  } else {
+    for (int i = ty; i < 32; i += 8) {
+      long v = tv * 32 + i; int c = tc * 32 + tx;
+      tile[i][tx] = (c < C && v < V) ? to_f(cl[((long)n * V + v) * pitch + coff + c]) : 0.f;
+    }
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8) {
+      int c = tc * 32 + i; long v = tv * 32 + tx;
+      if (c < C && v < V) ncdhw_out[((long)n * C + c) * V + v] = tile[tx][i];
+    }
+  }
+}
+template <class T>
+static int launch_layout(const float* in, float* out, T* cl, int N, int C, long V, int pitch, int coff, int dir,
+                         int accumulate, cudaStream_t st) {
+  long blocks = (long)N * ((V + 31) / 32) * ((C + 31) / 32);
+  layout_kernel<T><<<(unsigned)blocks, dim3(32, 8), 0, st>>>(in, out, cl, C, V, pitch, coff, dir, accumulate, 0);
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+
+template <class TI, class TO>
+__global__ void cast_kernel(const TI* __restrict__ in, TO* __restrict__ out, long n) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  long stride = (long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) out[i] = from_f<TO>(to_f(in[i]));
+}
+template <class TI, class TO>
+static int launch_cast(const TI* in, TO* out, long n, cudaStream_t st) {
+  int blocks = (int)min((long)148 * 8, (n + 255) / 256);
+  cast_kernel<TI, TO><<<blocks, 256, 0, st>>>(in, out, n);
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void add_kernel(float* __restrict__ dst, const float* __restrict__ src, long n) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  long stride = (long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) dst[i] += src[i];
+}
+static int launch_add(float* dst, const float* src, long n, cudaStream_t st) {
+  int blocks = (int)min((long)148 * 8, (n + 255) / 256);
+  add_kernel<<<blocks, 256, 0, st>>>(dst, src, n);
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+
+// ------------------------------------------------------------------ LayerNorm (eps 1e-5, affine), one warp per row
+template <class TO>
+__global__ void layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                     const float* __restrict__ beta, TO* __restrict__ y, float* __restrict__ stats,
+                                     int M, int H) {
+  int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const float* xr = x + (long)row * H;
+  float s = 0.f;
+  for (int i = lane; i < H; i += 32) s += xr[i];
+  float mean = warp_sum(s) / H;
+  float q = 0.f;
+  for (int i = lane; i < H; i += 32) { float d = xr[i] - mean; q += d * d; }
+  float rstd = rsqrtf(warp_sum(q) / H + 1e-5f);
+  for (int i = lane; i < H; i += 32) y[(long)row * H + i] = from_f<TO>((xr[i] - mean) * rstd * gamma[i] + beta[i]);
+  if (lane == 0 && stats) { stats[2 * row] = mean; stats[2 * row + 1] = rstd; }
+}
+template <class TO>
+static int launch_layernorm_fwd(const float* x, const float* g, const float* b, TO* y, float* stats, int M, int H,
+                                cudaStream_t st) {
+  layernorm_fwd_kernel<TO><<<cdiv(M, 8), 256, 0, st>>>(x, g, b, y, stats, M, H);
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+
+// dx_out = dx_res (nullable) + rstd*(g*gamma - mean(g*gamma) - xhat*mean(g*gamma*xhat))
+template <class TG>
+__global__ void layernorm_bwd_dx_kernel(const TG* __restrict__ g, const float* __restrict__ x,
+                                        const float* __restrict__ stats, const float* __restrict__ gamma,
+                                        const float* dx_res, float* dx_out, int M, int H) {
+  int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  float mean = stats[2 * row], rstd = stats[2 * row + 1];
+  const float* xr = x + (long)row * H;
+  const TG* gr = g + (long)row * H;
+  float s1 = 0.f, s2 = 0.f;
+  for (int i = lane; i < H; i += 32) {
+    float gg = to_f(gr[i]) * gamma[i]; float xh = (xr[i] - mean) * rstd;
+    s1 += gg; s2 += gg * xh;
+  }
+  s1 = warp_sum(s1) / H; s2 = warp_sum(s2) / H;
+  for (int i = lane; i < H; i += 32) {
+    float gg = to_f(gr[i]) * gamma[i]; float xh = (xr[i] - mean) * rstd;
+    float v = rstd * (gg - s1 - xh * s2);
+    if (dx_res) v += dx_res[(long)row * H + i];
+    dx_out[(long)row * H + i] = v;
+  }
+}
+// dgamma[h] = sum_rows g*xhat ; dbeta[h] = sum_rows g.   grid = H/32 blocks of (32 x 8)
+template <class TG>
+__global__ void layernorm_bwd_params_kernel(const TG* __restrict__ g, const float* __restrict__ x,
+                                            const float* __restrict__ stats, float* __restrict__ dgamma,
+                                            float* __restrict__ dbeta, int M, int H) {
+  __shared__ float sg[8][33], sb[8][33];
+  int col = blockIdx.x * 32 + threadIdx.x;
+  float a = 0.f, b = 0.f;
+  if (col < H)
+    for (int r = threadIdx.y; r < M; r += 8) {
+      float gg = to_f(g[(long)r * H + col]);
+      a += gg * (x[(long)r * H + col] - stats[2 * r]) * stats[2 * r + 1];
+      b += gg;
+    }
+  sg[threadIdx.y][threadIdx.x] = a; sb[threadIdx.y][threadIdx.x] = b;
+  __syncthreads();
+  if (threadIdx.y == 0 && col < H) {
+    for (int i = 1; i < 8; ++i) { a += sg[i][threadIdx.x]; b += sb[i][threadIdx.x]; }
+    dgamma[col] = a; dbeta[col] = b;
+  }
+}
+template <class TG>
+static int launch_layernorm_bwd(const TG* g, const float* x, const float* stats, const float* gamma,
+                                const float* dx_res, float* dx_out, float* dgamma, float* dbeta, int M, int H,
+                                cudaStream_t st) {
+  layernorm_bwd_dx_kernel<TG><<<cdiv(M, 8), 256, 0, st>>>(g, x, stats, gamma, dx_res, dx_out, M, H);
+  B200_LAUNCH_CHECK();
+  if (dgamma) {
+    layernorm_bwd_params_kernel<TG><<<cdiv(H, 32), dim3(32, 8), 0, st>>>(g, x, stats, dgamma, dbeta, M, H);
+    B200_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------ column sums (bias gradients)
+template <class TG>
+__global__ void colsum_kernel(const TG* __restrict__ g, float* __restrict__ out, int M, int N) {
+  __shared__ float s[8][33];
+  int col = blockIdx.x * 32 + threadIdx.x;
+  float a = 0.f;
+  if (col < N)
+    for (int r = threadIdx.y; r < M; r += 8) a += to_f(g[(long)r * N + col]);
+  s[threadIdx.y][threadIdx.x] = a;
+  __syncthreads();
+  if (threadIdx.y == 0 && col < N) {
+    for (int i = 1; i < 8; ++i) a += s[i][threadIdx.x];
+    out[col] = a;
+  }
+}
+template <class TG>
+static int launch_colsum(const TG* g, float* out, int M, int N, cudaStream_t st) {
+  colsum_kernel<TG><<<cdiv(N, 32), dim3(32, 8), 0, st>>>(g, out, M, N);
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+
+// out[row % C] += sum_v x[row, v]   (x is [rows, V] fp32; bias gradient of the NCDHW head)
+__global__ void rowsum_atomic_kernel(const float* __restrict__ x, float* __restrict__ out, long V, int C) {
+  int row = blockIdx.y;
+  long per = (V + gridDim.x - 1) / gridDim.x;
+  long v0 = (long)blockIdx.x * per, v1 = min(V, v0 + per);
+  float a = 0.f;
+  for (long v = v0 + threadIdx.x; v < v1; v += blockDim.x) a += x[(long)row * V + v];
+  a = warp_sum(a);
+  __shared__ float s[8];
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = a;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += s[i];
+    atomicAdd(out + row % C, t);
+  }
+}
+
+// dpos[l,h] = sum_b dx[b,l,h]
+__global__ void batchsum_kernel(const float* __restrict__ dx, float* __restrict__ out, int B, long LH) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= LH) return;
+  float a = 0.f;
+  for (int b = 0; b < B; ++b) a += dx[(long)b * LH + i];
+  out[i] = a;
+}
+
+// ------------------------------------------------------------------ attention softmax (scale applied before softmax)
+// S fp32 [rows, ld] (first L columns valid) -> P (type TP) [rows, ld]; one warp per row.
+template <class TP>
+__global__ void softmax_fwd_kernel(const float* __restrict__ S, TP* __restrict__ P, long rows, int L, int ld, float scale) {
+  long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* s = S + row * ld;
+  float mx = -INFINITY;
+  for (int i = lane; i < L; i += 32) mx = fmaxf(mx, s[i] * scale);
+  mx = warp_max(mx);
+  float sum = 0.f;
+  for (int i = lane; i < L; i += 32) sum += __expf(s[i] * scale - mx);
+  sum = warp_sum(sum);
+  float inv = 1.f / sum;
+  for (int i = lane; i < ld; i += 32) P[row * ld + i] = from_f<TP>(i < L ? __expf(s[i] * scale - mx) * inv : 0.f);
+}
+// dS = P * (dP - sum_j dP_j P_j) * scale
+template <class TP>
+__global__ void softmax_bwd_kernel(const TP* __restrict__ P, const float* __restrict__ dP, TP* __restrict__ dS, long rows,
+                                   int L, int ld, float scale) {
+  long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  float dot = 0.f;
+  for (int i = lane; i < L; i += 32) dot += to_f(P[row * ld + i]) * dP[row * ld + i];
+  dot = warp_sum(dot);
+  for (int i = lane; i < ld; i += 32)
+    dS[row * ld + i] = from_f<TP>(i < L ? to_f(P[row * ld + i]) * (dP[row * ld + i] - dot) * scale : 0.f);
+}
+
+// ------------------------------------------------------------------ InstanceNorm3d(affine=False, eps 1e-5, biased var)
+// Tensors are channels-last [N, V, pitch] with channel window [coff, coff+C).  C % Vec16<T>::N == 0,
+// C/VecN a power of two <= 256.  Statistics: double sum/sumsq -> float (mean, rstd) per (n,c).
+
+struct ClView { long pitch; int coff; };  // element strides of a channels-last window
+
+template <class T>
+__global__ void in_stats_kernel(const T* __restrict__ x, ClView xv, int C, long V, double* __restrict__ acc) {
+  constexpr int VN = Vec16<T>::N;
+  extern __shared__ float red[];  // [256][2*VN]
+  int lanes = C / VN;             // vectors per voxel
+  int lv = threadIdx.x % lanes, sub = threadIdx.x / lanes, nsub = blockDim.x / lanes;
+  int n = blockIdx.y;
+  long per = (V + gridDim.x - 1) / gridDim.x;
+  long v0 = (long)blockIdx.x * per, v1 = min(V, v0 + per);
+  float s[VN], q[VN];
+#pragma unroll
+  for (int i = 0; i < VN; ++i) s[i] = q[i] = 0.f;
+  for (long v = v0 + sub; v < v1; v += nsub) {
+    Vec16<T> a; a.load(x + ((long)n * V + v) * xv.pitch + xv.coff + lv * VN);
+#pragma unroll
+    for (int i = 0; i < VN; ++i) { s[i] += a.v[i]; q[i] += a.v[i] * a.v[i]; }
+  }
+  float* mine = red + threadIdx.x * 2 * VN;
+#pragma unroll
+  for (int i = 0; i < VN; ++i) { mine[i] = s[i]; mine[VN + i] = q[i]; }
+  __syncthreads();
+  if (sub == 0) {
+    double ds[VN], dq[VN];
+#pragma unroll
+    for (int i = 0; i < VN; ++i) ds[i] = dq[i] = 0.0;
+    for (int t = 0; t < nsub; ++t) {
+      const float* o = red + (t * lanes + lv) * 2 * VN;
+#pragma unroll
+      for (int i = 0; i < VN; ++i) { ds[i] += o[i]; dq[i] += o[VN + i]; }
+    }
+#pragma unroll
+    for (int i = 0; i < VN; ++i) {
+      atomicAdd(acc + ((long)n * C + lv * VN + i) * 2, ds[i]);
+      atomicAdd(acc + ((long)n * C + lv * VN + i) * 2 + 1, dq[i]);
+    }
+  }
+}
+__global__ void in_finalize_kernel(const double* __restrict__ acc, float* __restrict__ mr, int NC, double invV) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= NC) return;
+  double mean = acc[2 * i] * invV;
+  double var = acc[2 * i + 1] * invV - mean * mean;
+  if (var < 0) var = 0;
+  mr[2 * i] = (float)mean;
+  mr[2 * i + 1] = (float)(1.0 / sqrt(var + 1e-5));
+}
+
+// out = lrelu(norm(x))                            (two==0)
+// out = lrelu(norm_a(x) + norm_b(x2))             (two==1)
+template <class T>
+__global__ void in_apply_kernel(const T* __restrict__ x, ClView xv, const float* __restrict__ mr,
+                                const T* __restrict__ x2, ClView x2v, const float* __restrict__ mr2, T* __restrict__ out,
+                                ClView ov, int C, long V, int two) {
+  constexpr int VN = Vec16<T>::N;
+  int lanes = C / VN;
+  int n = blockIdx.y;
+  long total = V * lanes;
+  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+    long v = e / lanes; int lv = (int)(e % lanes); int c0 = lv * VN;
+    Vec16<T> a; a.load(x + ((long)n * V + v) * xv.pitch + xv.coff + c0);
+    Vec16<T> o;
+    if (two) {
+      Vec16<T> b; b.load(x2 + ((long)n * V + v) * x2v.pitch + x2v.coff + c0);
+#pragma unroll
+      for (int i = 0; i < VN; ++i) {
+        const float* m1 = mr + ((long)n * C + c0 + i) * 2; const float* m2 = mr2 + ((long)n * C + c0 + i) * 2;
+        o.v[i] = lrelu((a.v[i] - m1[0]) * m1[1] + (b.v[i] - m2[0]) * m2[1]);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < VN; ++i) {
+        const float* m1 = mr + ((long)n * C + c0 + i) * 2;
+        o.v[i] = lrelu((a.v[i] - m1[0]) * m1[1]);
+      }
+    }
+    o.store(out + ((long)n * V + v) * ov.pitch + ov.coff + c0);
+  }
+}
+
+// Backward, pass 1: per-(n,c) sums.  g = dOut * lrelu'(act).
+//  two==0: act = lrelu(n1) is the saved activation; n1 recovered from it.   sums: [Sg, Sg*n1]
+//  two==1: act = lrelu(n2+n3); n2,n3 recomputed from raw conv outputs.       sums: [Sg, Sg*n2, Sg*n3]
+template <class T>
+__global__ void in_bwd_reduce_kernel(const T* __restrict__ dout, ClView dv, const T* __restrict__ act, ClView av,
+                                     const T* __restrict__ ra, ClView rav, const float* __restrict__ mra,
+                                     const T* __restrict__ rb, ClView rbv, const float* __restrict__ mrb, int C, long V,
+                                     int two, double* __restrict__ acc /*[N][C][3]*/) {
+  constexpr int VN = Vec16<T>::N;
+  extern __shared__ float red[];  // [256][3*VN]
+  int lanes = C / VN;
+  int lv = threadIdx.x % lanes, sub = threadIdx.x / lanes, nsub = blockDim.x / lanes;
+  int n = blockIdx.y, c0 = lv * VN;
+  long per = (V + gridDim.x - 1) / gridDim.x;
+  long v0 = (long)blockIdx.x * per, v1 = min(V, v0 + per);
+  float s0[VN], s1[VN], s2[VN];
+#pragma unroll
+  for (int i = 0; i < VN; ++i) s0[i] = s1[i] = s2[i] = 0.f;
+  for (long v = v0 + sub; v < v1; v += nsub) {
+    long base = (long)n * V + v;
+    Vec16<T> d, a; d.load(dout + base * dv.pitch + dv.coff + c0); a.load(act + base * av.pitch + av.coff + c0);
+    if (two) {
+      Vec16<T> xa, xb; xa.load(ra + base * rav.pitch + rav.coff + c0); xb.load(rb + base * rbv.pitch + rbv.coff + c0);
+#pragma unroll
+      for (int i = 0; i < VN; ++i) {
+        const float* ma = mra + ((long)n * C + c0 + i) * 2; const float* mb = mrb + ((long)n * C + c0 + i) * 2;
+        float g = d.v[i] * (a.v[i] > 0.f ? 1.f : 0.01f);
+        s0[i] += g; s1[i] += g * (xa.v[i] - ma[0]) * ma[1]; s2[i] += g * (xb.v[i] - mb[0]) * mb[1];
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < VN; ++i) {
+        float g = d.v[i] * (a.v[i] > 0.f ? 1.f : 0.01f);
+        float nn = a.v[i] > 0.f ? a.v[i] : a.v[i] * 100.f;
+        s0[i] += g; s1[i] += g * nn;
+      }
+    }
+  }
+  float* mine = red + threadIdx.x * 3 * VN;
+#pragma unroll
+  for (int i = 0; i < VN; ++i) { mine[i] = s0[i]; mine[VN + i] = s1[i]; mine[2 * VN + i] = s2[i]; }
+  __syncthreads();
+  if (sub == 0) {
+    double d0[VN], d1[VN], d2[VN];
+#pragma unroll
+    for (int i = 0; i < VN; ++i) d0[i] = d1[i] = d2[i] = 0.0;
+    for (int t = 0; t < nsub; ++t) {
+      const float* o = red + (t * lanes + lv) * 3 * VN;
+#pragma unroll
+      for (int i = 0; i < VN; ++i) { d0[i] += o[i]; d1[i] += o[VN + i]; d2[i] += o[2 * VN + i]; }
+    }
+#pragma unroll
+    for (int i = 0; i < VN; ++i) {
+      double* a3 = acc + ((long)n * C + c0 + i) * 3;
+      atomicAdd(a3, d0[i]); atomicAdd(a3 + 1, d1[i]);
+      if (two) atomicAdd(a3 + 2, d2[i]);
+    }
+  }
+}
+// Backward, pass 2:  d(raw) = rstd * (g - mean(g) - n * mean(g*n))
+template <class T>
+__global__ void in_bwd_apply_kernel(const T* __restrict__ dout, ClView dv, const T* __restrict__ act, ClView av,
+                                    const T* __restrict__ ra, ClView rav, const float* __restrict__ mra,
+                                    const T* __restrict__ rb, ClView rbv, const float* __restrict__ mrb, int C, long V,
+                                    int two, const double* __restrict__ acc, T* __restrict__ da, ClView dav,
+                                    T* __restrict__ db, ClView dbv) {
+  constexpr int VN = Vec16<T>::N;
+  int lanes = C / VN;
+  int n = blockIdx.y;
+  long total = V * lanes;
+  float invV = 1.f / (float)V;
+  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+    long v = e / lanes; int lv = (int)(e % lanes); int c0 = lv * VN;
+    long base = (long)n * V + v;
+    Vec16<T> d, a; d.load(dout + base * dv.pitch + dv.coff + c0); a.load(act + base * av.pitch + av.coff + c0);
+    Vec16<T> oa, ob;
+    if (two) {
+      Vec16<T> xa, xb; xa.load(ra + base * rav.pitch + rav.coff + c0); xb.load(rb + base * rbv.pitch + rbv.coff + c0);
+#pragma unroll
+      for (int i = 0; i < VN; ++i) {
+        const float* ma = mra + ((long)n * C + c0 + i) * 2; const float* mb = mrb + ((long)n * C + c0 + i) * 2;
+        const double* a3 = acc + ((long)n * C + c0 + i) * 3;
+        float mg = (float)a3[0] * invV, mga = (float)a3[1] * invV, mgb = (float)a3[2] * invV;
+        float g = d.v[i] * (a.v[i] > 0.f ? 1.f : 0.01f);
+        float na = (xa.v[i] - ma[0]) * ma[1], nb = (xb.v[i] - mb[0]) * mb[1];
+        oa.v[i] = ma[1] * (g - mg - na * mga);
+        ob.v[i] = mb[1] * (g - mg - nb * mgb);
+      }
+      oa.store(da + base * dav.pitch + dav.coff + c0);
+      ob.store(db + base * dbv.pitch + dbv.coff + c0);
+    } else {
+#pragma unroll
+      for (int i = 0; i < VN; ++i) {
+        const float* ma = mra + ((long)n * C + c0 + i) * 2;
+        const double* a3 = acc + ((long)n * C + c0 + i) * 3;
+        float mg = (float)a3[0] * invV, mga = (float)a3[1] * invV;
+        float g = d.v[i] * (a.v[i] > 0.f ? 1.f : 0.01f);
+        float na = a.v[i] > 0.f ? a.v[i] : a.v[i] * 100.f;
+        oa.v[i] = ma[1] * (g - mg - na * mga);
+      }
+      oa.store(da + base * dav.pitch + dav.coff + c0);
+    }
+  }
+}
+
+static inline int in_grid_x(long V) { return (int)max(1L, min((long)148 * 4, V / 512)); }
+
+}  // namespace b200

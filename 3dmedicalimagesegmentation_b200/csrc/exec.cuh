@@ -1,0 +1,445 @@
+// UNETR forward / backward executor.  Mirrors unetr.py:182-208 (wiring) and the MONAI 0.6.0 block semantics
+// recorded in SURVEY.md Appendix B, but on a B200-first data layout:
+//   * tokens [B*L, hidden] row-major ARE the channels-last 16x-downsampled volume, so `proj_feat`
+//     (unetr.py:177-180) costs nothing;
+//   * every decoder tensor is channels-last (NDHWC) so a voxel's channels are one contiguous GEMM row;
+//   * `torch.cat((up, skip), 1)` is never materialised: the transposed conv writes channels [0,C) and the skip
+//     branch writes [C,2C) of one concat buffer;
+//   * the residual stream and all statistics are fp32, activations are T (float = parity mode, bf16 = throughput).
+// Caller owns all memory: parameters / gradients are PyTorch-layout fp32 pointers, the workspace is one buffer.
+#pragma once
+#include "ops.cuh"
+
+namespace b200 {
+
+struct UnetrConfig {
+  int B, Cin, ncls, S0, S1, S2, fs, hidden, mlp, heads, conv_patch, mode;  // mode 0 = fp32, 1 = bf16
+};
+
+enum ParamIdx {
+  P_POS = 0, P_PATCH_W, P_PATCH_B, P_BLK0 = 3,
+  // per transformer block (11): LN1_W LN1_B QKV_W PROJ_W PROJ_B LN2_W LN2_B FC1_W FC1_B FC2_W FC2_B
+  P_NORM_W = 3 + 12 * 11, P_NORM_B,
+  P_E1_C1, P_E1_C2, P_E1_C3,
+  P_E2_T0, P_E2_T1, P_E2_T2,
+  P_E3_T0, P_E3_T1,
+  P_E4_T0,
+  P_D5_T, P_D5_C1, P_D5_C2, P_D5_C3,
+  P_D4_T, P_D4_C1, P_D4_C2, P_D4_C3,
+  P_D3_T, P_D3_C1, P_D3_C2, P_D3_C3,
+  P_D2_T, P_D2_C1, P_D2_C2, P_D2_C3,
+  P_OUT_W, P_OUT_B, P_COUNT
+};
+enum { B_LN1_W = 0, B_LN1_B, B_QKV_W, B_PROJ_W, B_PROJ_B, B_LN2_W, B_LN2_B, B_FC1_W, B_FC1_B, B_FC2_W, B_FC2_B, B_COUNT };
+
+enum { FLAG_NEED_ENCODER_GRAD = 1, FLAG_HAS_DLOGITS = 2, FLAG_HAS_DENC4 = 4, FLAG_SAVE_FOR_BACKWARD = 8 };
+
+struct Bump {
+  char* base; size_t off;
+  template <class U> U* take(size_t n) {
+    off = (off + 255) & ~(size_t)255;
+    U* p = base ? reinterpret_cast<U*>(base + off) : nullptr;
+    off += n * sizeof(U);
+    return p;
+  }
+};
+
+template <class T>
+struct ResSave {  // what a residual conv block keeps for its backward
+  T *a1, *c2, *c3; float *mr1, *mr2, *mr3;
+};
+
+template <class T>
+struct Workspace {
+  // ViT
+  float *x0, *hs[12], *x1[12], *ln1s[12], *ln2s[12], *lnfs, *S;
+  T *ln1[12], *qkv[12], *P[12], *att[12], *ln2[12], *u[12], *h[12], *vit_out, *hsT[3];
+  // decoder
+  T *xcl, *c1tmp, *e2a, *e2b, *e3a, *cat5, *cat4, *cat3, *cat2, *d3, *d2, *d1, *d0;
+  ResSave<T> rs[5];  // enc1, dec5, dec4, dec3, dec2
+  double* stat_acc;
+  // backward scratch
+  float *dx, *dx2, *dhs[3], *dP;
+  T *dvit, *dh, *dln, *datt, *dqkv, *dS, *gA, *dcat, *dc2, *dc3, *da1, *dc1;
+  double* bwd_acc;
+  size_t bytes;
+};
+
+template <class T>
+struct Exec {
+  UnetrConfig c;
+  int g0, g1, g2, L, Lp, M, H, F, nh, dh;
+  long V[5];  // voxels per sample at levels 0 (full) .. 4 (tokens)
+  Workspace<T> w;
+
+  explicit Exec(const UnetrConfig& cfg) : c(cfg) {
+    g0 = c.S0 / 16; g1 = c.S1 / 16; g2 = c.S2 / 16;
+    L = g0 * g1 * g2; Lp = (L + 7) & ~7; M = c.B * L; H = c.hidden; F = c.mlp; nh = c.heads; dh = H / nh;
+    V[4] = L;
+    for (int l = 3; l >= 0; --l) V[l] = V[l + 1] * 8;
+  }
+  Sp sp(int level) const { int s = 16 >> level; return Sp{c.B, g0 * s, g1 * s, g2 * s}; }
+
+  void layout(char* base, bool with_backward) {
+    Bump b{base, 0};
+    size_t MH = (size_t)M * H, MF = (size_t)M * F, PP = (size_t)c.B * nh * L * Lp;
+    int fs = c.fs, B = c.B;
+    w.x0 = b.take<float>(MH);
+    for (int i = 0; i < 12; ++i) {
+      w.hs[i] = b.take<float>(MH); w.x1[i] = b.take<float>(MH);
+      w.ln1s[i] = b.take<float>(2 * M); w.ln2s[i] = b.take<float>(2 * M);
+      w.ln1[i] = b.take<T>(MH); w.qkv[i] = b.take<T>(3 * MH); w.P[i] = b.take<T>(PP); w.att[i] = b.take<T>(MH);
+      w.ln2[i] = b.take<T>(MH); w.u[i] = b.take<T>(MF); w.h[i] = b.take<T>(MF);
+    }
+    w.lnfs = b.take<float>(2 * M); w.S = b.take<float>(PP); w.vit_out = b.take<T>(MH);
+    for (int i = 0; i < 3; ++i) w.hsT[i] = b.take<T>(MH);
+    w.xcl = b.take<T>((size_t)B * V[0] * c.Cin);
+    w.c1tmp = b.take<T>((size_t)B * V[0] * fs);
+    w.e2a = b.take<T>((size_t)B * V[3] * 2 * fs); w.e2b = b.take<T>((size_t)B * V[2] * 2 * fs);
+    w.e3a = b.take<T>((size_t)B * V[3] * 4 * fs);
+    w.cat5 = b.take<T>((size_t)B * V[3] * 16 * fs); w.cat4 = b.take<T>((size_t)B * V[2] * 8 * fs);
+    w.cat3 = b.take<T>((size_t)B * V[1] * 4 * fs); w.cat2 = b.take<T>((size_t)B * V[0] * 2 * fs);
+    w.d3 = b.take<T>((size_t)B * V[3] * 8 * fs); w.d2 = b.take<T>((size_t)B * V[2] * 4 * fs);
+    w.d1 = b.take<T>((size_t)B * V[1] * 2 * fs); w.d0 = b.take<T>((size_t)B * V[0] * fs);
+    const int lvl[5] = {0, 3, 2, 1, 0}; const int co[5] = {fs, 8 * fs, 4 * fs, 2 * fs, fs};
+    for (int i = 0; i < 5; ++i) {
+      size_t n = (size_t)B * V[lvl[i]] * co[i];
+      w.rs[i].a1 = b.take<T>(n); w.rs[i].c2 = b.take<T>(n); w.rs[i].c3 = b.take<T>(n);
+      w.rs[i].mr1 = b.take<float>(2 * B * co[i]); w.rs[i].mr2 = b.take<float>(2 * B * co[i]); w.rs[i].mr3 = b.take<float>(2 * B * co[i]);
+    }
+    w.stat_acc = b.take<double>((size_t)2 * B * 8 * fs);
+    if (with_backward) {
+      w.dx = b.take<float>(MH); w.dx2 = b.take<float>(MH);
+      for (int i = 0; i < 3; ++i) w.dhs[i] = b.take<float>(MH);
+      w.dP = b.take<float>(PP); w.dS = b.take<T>(PP);
+      w.dvit = b.take<T>(MH); w.dh = b.take<T>(MF); w.dln = b.take<T>(MH); w.datt = b.take<T>(MH); w.dqkv = b.take<T>(3 * MH);
+      size_t big = (size_t)B * V[0] * fs;
+      w.gA = b.take<T>(big); w.dcat = b.take<T>(2 * big); w.dc2 = b.take<T>(big); w.dc3 = b.take<T>(big);
+      w.da1 = b.take<T>(big); w.dc1 = b.take<T>(big);
+      w.bwd_acc = b.take<double>((size_t)3 * B * 8 * fs);
+    }
+    w.bytes = (b.off + 255) & ~(size_t)255;
+  }
+
+  // ------------------------------------------------------------ engine dispatch (CUDA-core engine; see exec.cu for tcgen05)
+  template <class TA, class TO>
+  int linear_fwd(const TA* A, long lda, const float* W, int Mr, int N, int K, const EpStore<TO>& ep, cudaStream_t st) {
+    return simt_linear_fwd(A, lda, W, Mr, N, K, ep, st);
+  }
+  template <class TG, class TO>
+  int linear_dgrad(const TG* dY, long ldy, const float* W, int Mr, int N, int K, const EpStore<TO>& ep, cudaStream_t st) {
+    return simt_linear_dgrad(dY, ldy, W, Mr, N, K, ep, st);
+  }
+  template <class TG, class TX>
+  int linear_wgrad(const TG* dY, long ldy, const TX* X, long ldx, int Mr, int N, int K, float* dW, cudaStream_t st) {
+    return simt_linear_wgrad(dY, ldy, X, ldx, Mr, N, K, dW, st);
+  }
+
+  // ------------------------------------------------------------ InstanceNorm helpers
+  int in_stats(Cl<const T> x, long Vs, float* mr, cudaStream_t st) {
+    B200_PROF("instnorm_stats", st);
+    constexpr int VN = Vec16<T>::N;
+    B200_CHECK(x.C % VN == 0 && 256 % (x.C / VN) == 0 && x.pitch % VN == 0 && x.coff % VN == 0,
+               "InstanceNorm channel count %d unsupported (need a power of two >= 8)", x.C);
+    B200_CUDA(cudaMemsetAsync(w.stat_acc, 0, sizeof(double) * 2 * c.B * x.C, st));
+    dim3 g(in_grid_x(Vs), c.B);
+    in_stats_kernel<T><<<g, 256, 256 * 2 * VN * sizeof(float), st>>>(x.p, ClView{x.pitch, x.coff}, x.C, Vs, w.stat_acc);
+    B200_LAUNCH_CHECK();
+    in_finalize_kernel<<<cdiv(c.B * x.C, 128), 128, 0, st>>>(w.stat_acc, mr, c.B * x.C, 1.0 / (double)Vs);
+    B200_LAUNCH_CHECK();
+    return 0;
+  }
+  int in_apply(Cl<const T> x, const float* mr, const T* x2, const float* mr2, Cl<T> out, long Vs, cudaStream_t st) {
+    B200_PROF("instnorm_apply", st);
+    dim3 g(in_grid_x(Vs) * 2, c.B);
+    in_apply_kernel<T><<<g, 256, 0, st>>>(x.p, ClView{x.pitch, x.coff}, mr, x2, ClView{x.C, 0}, mr2, out.p,
+                                          ClView{out.pitch, out.coff}, x.C, Vs, x2 != nullptr);
+    B200_LAUNCH_CHECK();
+    return 0;
+  }
+
+  // ------------------------------------------------------------ residual conv block (UnetResBlock, Appendix B.2)
+  // conv ops are virtual-ish hooks so the tcgen05 engine can replace them
+  int conv_fwd(Cl<const T> x, Sp s, const float* W, int Co, int ks, Cl<T> out, cudaStream_t st) { return simt_conv_fwd<T>(x, s, W, Co, ks, out, st); }
+  int conv_dgrad(Cl<const T> dy, Sp s, const float* W, int Ci, int ks, Cl<T> dx, int acc, cudaStream_t st) { return simt_conv_dgrad<T>(dy, s, W, Ci, ks, dx, acc, st); }
+  int conv_wgrad(Cl<const T> x, Cl<const T> dy, Sp s, int ks, float* dW, cudaStream_t st) { return simt_conv_wgrad<T>(x, dy, s, ks, dW, st); }
+
+  int res_fwd(Cl<const T> x, int level, const float* W1, const float* W2, const float* W3, ResSave<T>& r, Cl<T> out, cudaStream_t st) {
+    Sp s = sp(level); long Vs = V[level]; int Co = out.C;
+    Cl<T> c1 = cl(w.c1tmp, Co, 0, Co), a1 = cl(r.a1, Co, 0, Co), c2 = cl(r.c2, Co, 0, Co), c3 = cl(r.c3, Co, 0, Co);
+    B200_TRY(conv_fwd(x, s, W1, Co, 3, c1, st));
+    B200_TRY(in_stats(cl<const T>(c1.p, Co, 0, Co), Vs, r.mr1, st));
+    B200_TRY(in_apply(cl<const T>(c1.p, Co, 0, Co), r.mr1, nullptr, nullptr, a1, Vs, st));
+    B200_TRY(conv_fwd(cl<const T>(a1.p, Co, 0, Co), s, W2, Co, 3, c2, st));
+    B200_TRY(in_stats(cl<const T>(c2.p, Co, 0, Co), Vs, r.mr2, st));
+    B200_TRY(conv_fwd(x, s, W3, Co, 1, c3, st));
+    B200_TRY(in_stats(cl<const T>(c3.p, Co, 0, Co), Vs, r.mr3, st));
+    B200_TRY(in_apply(cl<const T>(c2.p, Co, 0, Co), r.mr2, c3.p, r.mr3, out, Vs, st));
+    return 0;
+  }
+  // dOut: gradient wrt block output; out: the block's forward output.  Writes dW1..3 (if non-null) and, if dx.p, the
+  // input gradient (dx = dgrad3(dc1) + dgrad1(dc3)).
+  int res_bwd(Cl<const T> x, int level, const float* W1, const float* W2, const float* W3, ResSave<T>& r, Cl<const T> out,
+              Cl<const T> dOut, float* dW1, float* dW2, float* dW3, Cl<T> dx, cudaStream_t st) {
+    constexpr int VN = Vec16<T>::N;
+    Sp s = sp(level); long Vs = V[level]; int Co = out.C, Ci = x.C; int B = c.B;
+    ClView pv{Co, 0};
+    size_t red_smem = 256 * 3 * VN * sizeof(float);
+    dim3 gr(in_grid_x(Vs), B), ga(in_grid_x(Vs) * 2, B);
+    // final lrelu + two norms
+    { B200_PROF("instnorm_bwd", st);
+    B200_CUDA(cudaMemsetAsync(w.bwd_acc, 0, sizeof(double) * 3 * B * Co, st));
+    in_bwd_reduce_kernel<T><<<gr, 256, red_smem, st>>>(dOut.p, ClView{dOut.pitch, dOut.coff}, out.p, ClView{out.pitch, out.coff},
+                                                      r.c2, pv, r.mr2, r.c3, pv, r.mr3, Co, Vs, 1, w.bwd_acc);
+    B200_LAUNCH_CHECK();
+    in_bwd_apply_kernel<T><<<ga, 256, 0, st>>>(dOut.p, ClView{dOut.pitch, dOut.coff}, out.p, ClView{out.pitch, out.coff},
+                                               r.c2, pv, r.mr2, r.c3, pv, r.mr3, Co, Vs, 1, w.bwd_acc, w.dc2, pv, w.dc3, pv);
+    B200_LAUNCH_CHECK(); }
+    Cl<const T> dc2 = cl<const T>(w.dc2, Co, 0, Co), dc3 = cl<const T>(w.dc3, Co, 0, Co), a1 = cl<const T>(r.a1, Co, 0, Co);
+    // conv2
+    if (dW2) { B200_CUDA(cudaMemsetAsync(dW2, 0, sizeof(float) * Co * Co * 27, st)); B200_TRY(conv_wgrad(a1, dc2, s, 3, dW2, st)); }
+    B200_TRY(conv_dgrad(dc2, s, W2, Co, 3, cl(w.da1, Co, 0, Co), 0, st));
+    // lrelu + norm1
+    { B200_PROF("instnorm_bwd", st);
+    B200_CUDA(cudaMemsetAsync(w.bwd_acc, 0, sizeof(double) * 3 * B * Co, st));
+    in_bwd_reduce_kernel<T><<<gr, 256, red_smem, st>>>(w.da1, pv, r.a1, pv, nullptr, pv, r.mr1, nullptr, pv, nullptr, Co, Vs, 0, w.bwd_acc);
+    B200_LAUNCH_CHECK();
+    in_bwd_apply_kernel<T><<<ga, 256, 0, st>>>(w.da1, pv, r.a1, pv, nullptr, pv, r.mr1, nullptr, pv, nullptr, Co, Vs, 0, w.bwd_acc,
+                                               w.dc1, pv, nullptr, pv);
+    B200_LAUNCH_CHECK(); }
+    Cl<const T> dc1 = cl<const T>(w.dc1, Co, 0, Co);
+    if (dW1) { B200_CUDA(cudaMemsetAsync(dW1, 0, sizeof(float) * Co * Ci * 27, st)); B200_TRY(conv_wgrad(x, dc1, s, 3, dW1, st)); }
+    if (dW3) { B200_CUDA(cudaMemsetAsync(dW3, 0, sizeof(float) * Co * Ci, st)); B200_TRY(conv_wgrad(x, dc3, s, 1, dW3, st)); }
+    if (dx.p) {
+      B200_TRY(conv_dgrad(dc1, s, W1, Ci, 3, dx, 0, st));
+      B200_TRY(conv_dgrad(dc3, s, W3, Ci, 1, dx, 1, st));
+    }
+    return 0;
+  }
+
+  // ------------------------------------------------------------ forward
+  int forward(const float* const* P, const float* x_in, char* ws, float* enc4_out, float* logits_out, int flags, cudaStream_t st) {
+    layout(ws, false);
+    int B = c.B, fs = c.fs;
+    // --- patch embedding (a5): tokens = rows(x) W^T + b + pos
+    {
+      RowIsOuter<PatchGather, false> al; al.g = {x_in, c.Cin, c.S0, c.S1, c.S2, g0, g1, g2, c.conv_patch};
+      EpPatch ep = {w.x0, H, L, P[P_PATCH_B], P[P_POS]};
+      B200_TRY(launch_contract(al, ld2<float, false>(P[P_PATCH_W], 4096L * c.Cin, 1), ep, M, H, 4096 * c.Cin, 1, 1, st));
+    }
+    // --- transformer blocks (a6-a8)
+    float scale = 1.0f / sqrtf((float)dh);
+    for (int i = 0; i < 12; ++i) {
+      const float* const* bp = P + P_BLK0 + i * B_COUNT;
+      const float* xin = i ? w.hs[i - 1] : w.x0;
+      B200_TRY(launch_layernorm_fwd<T>(xin, bp[B_LN1_W], bp[B_LN1_B], w.ln1[i], w.ln1s[i], M, H, st));
+      B200_TRY(linear_fwd<T, T>(w.ln1[i], H, bp[B_QKV_W], M, 3 * H, H, ep_plain<T>(w.qkv[i], 3 * H), st));
+      B200_TRY(attention_fwd(i, scale, st));
+      { EpStore<float> ep = ep_plain<float>(w.x1[i], H); ep.bias = bp[B_PROJ_B]; ep.resid = xin; ep.ldr = H;
+        B200_TRY(linear_fwd<T, float>(w.att[i], H, bp[B_PROJ_W], M, H, H, ep, st)); }
+      B200_TRY(launch_layernorm_fwd<T>(w.x1[i], bp[B_LN2_W], bp[B_LN2_B], w.ln2[i], w.ln2s[i], M, H, st));
+      { EpStore<T> ep = ep_plain<T>(w.h[i], F); ep.bias = bp[B_FC1_B]; ep.act = ACT_GELU; ep.preact = w.u[i];
+        B200_TRY(linear_fwd<T, T>(w.ln2[i], H, bp[B_FC1_W], M, F, H, ep, st)); }
+      { EpStore<float> ep = ep_plain<float>(w.hs[i], H); ep.bias = bp[B_FC2_B]; ep.resid = w.x1[i]; ep.ldr = H;
+        B200_TRY(linear_fwd<T, float>(w.h[i], F, bp[B_FC2_W], M, H, F, ep, st)); }
+    }
+    B200_TRY(launch_layernorm_fwd<T>(w.hs[11], P[P_NORM_W], P[P_NORM_B], w.vit_out, w.lnfs, M, H, st));
+    for (int k = 0; k < 3; ++k) B200_TRY(launch_cast<float, T>(w.hs[3 + 3 * k], w.hsT[k], (long)M * H, st));
+
+    // --- encoder1 on the input volume (a9) -> upper half of concat2
+    B200_TRY(launch_layout<T>(x_in, nullptr, w.xcl, B, c.Cin, V[0], c.Cin, 0, 0, 0, st));
+    B200_TRY(res_fwd(cl<const T>(w.xcl, c.Cin, 0, c.Cin), 0, P[P_E1_C1], P[P_E1_C2], P[P_E1_C3], w.rs[0], cl(w.cat2, 2 * fs, fs, fs), st));
+    // --- encoder2..4: transposed-conv pyramids from hidden states 3/6/9 (a10)
+    B200_TRY(convT_fwd(w.hsT[0], H, H, 4, P[P_E2_T0], cl(w.e2a, 2 * fs, 0, 2 * fs), st));
+    B200_TRY(convT_fwd(w.e2a, 2 * fs, 2 * fs, 3, P[P_E2_T1], cl(w.e2b, 2 * fs, 0, 2 * fs), st));
+    B200_TRY(convT_fwd(w.e2b, 2 * fs, 2 * fs, 2, P[P_E2_T2], cl(w.cat3, 4 * fs, 2 * fs, 2 * fs), st));
+    B200_TRY(convT_fwd(w.hsT[1], H, H, 4, P[P_E3_T0], cl(w.e3a, 4 * fs, 0, 4 * fs), st));
+    B200_TRY(convT_fwd(w.e3a, 4 * fs, 4 * fs, 3, P[P_E3_T1], cl(w.cat4, 8 * fs, 4 * fs, 4 * fs), st));
+    B200_TRY(convT_fwd(w.hsT[2], H, H, 4, P[P_E4_T0], cl(w.cat5, 16 * fs, 8 * fs, 8 * fs), st));
+    if (enc4_out) B200_TRY(launch_layout<T>(nullptr, enc4_out, w.cat5, B, 8 * fs, V[3], 16 * fs, 8 * fs, 1, 0, st));
+    // --- decoder5..2 (a11)
+    B200_TRY(convT_fwd(w.vit_out, H, H, 4, P[P_D5_T], cl(w.cat5, 16 * fs, 0, 8 * fs), st));
+    B200_TRY(res_fwd(cl<const T>(w.cat5, 16 * fs, 0, 16 * fs), 3, P[P_D5_C1], P[P_D5_C2], P[P_D5_C3], w.rs[1], cl(w.d3, 8 * fs, 0, 8 * fs), st));
+    B200_TRY(convT_fwd(w.d3, 8 * fs, 8 * fs, 3, P[P_D4_T], cl(w.cat4, 8 * fs, 0, 4 * fs), st));
+    B200_TRY(res_fwd(cl<const T>(w.cat4, 8 * fs, 0, 8 * fs), 2, P[P_D4_C1], P[P_D4_C2], P[P_D4_C3], w.rs[2], cl(w.d2, 4 * fs, 0, 4 * fs), st));
+    B200_TRY(convT_fwd(w.d2, 4 * fs, 4 * fs, 2, P[P_D3_T], cl(w.cat3, 4 * fs, 0, 2 * fs), st));
+    B200_TRY(res_fwd(cl<const T>(w.cat3, 4 * fs, 0, 4 * fs), 1, P[P_D3_C1], P[P_D3_C2], P[P_D3_C3], w.rs[3], cl(w.d1, 2 * fs, 0, 2 * fs), st));
+    B200_TRY(convT_fwd(w.d1, 2 * fs, 2 * fs, 1, P[P_D2_T], cl(w.cat2, 2 * fs, 0, fs), st));
+    B200_TRY(res_fwd(cl<const T>(w.cat2, 2 * fs, 0, 2 * fs), 0, P[P_D2_C1], P[P_D2_C2], P[P_D2_C3], w.rs[4], cl(w.d0, fs, 0, fs), st));
+    // --- 1x1x1 head with bias, NCDHW fp32 logits (a12)
+    if (logits_out) {
+      EpHeadNcdhw ep = {logits_out, c.ncls, V[0], P[P_OUT_B]};
+      B200_TRY(launch_contract(ld2<T, false>(w.d0, fs, 1), ld2<float, false>(P[P_OUT_W], fs, 1), ep, (int)(B * V[0]), c.ncls, fs, 1, 1, st));
+    }
+    return 0;
+  }
+
+  template <class TA>
+  int convT_fwd(const TA* x, long ldx, int Ci, int in_level, const float* W, Cl<T> out, cudaStream_t st) {
+    return simt_convT_fwd<TA, T>(x, ldx, Ci, sp(in_level), W, out, st);
+  }
+
+  // softmax(Q K^T * scale) V per (batch, head); scores fp32, probabilities T (kept for backward)
+  int attention_fwd(int i, float scale, cudaStream_t st) {
+    B200_PROF("attention_fwd", st);
+    const T* qkv = w.qkv[i];
+    long sQb = (long)L * 3 * H, sPb = (long)nh * L * Lp, sPh = (long)L * Lp;
+    int BH = c.B * nh;
+    { EpStore<float> ep = ep_plain<float>(w.S, Lp); ep.sb0 = sPb; ep.sb1 = sPh; ep.nb1 = nh;
+      B200_TRY(launch_contract(ld4<T, false>(qkv, 3 * H, 1, sQb, dh, nh), ld4<T, false>(qkv + H, 3 * H, 1, sQb, dh, nh), ep, L, L, dh, BH, 1, st)); }
+    softmax_fwd_kernel<T><<<cdiv((long)BH * L, 8), 256, 0, st>>>(w.S, w.P[i], (long)BH * L, L, Lp, scale);
+    B200_LAUNCH_CHECK();
+    { EpStore<T> ep = ep_plain<T>(w.att[i], H); ep.sb0 = (long)L * H; ep.sb1 = dh; ep.nb1 = nh;
+      B200_TRY(launch_contract(ld4<T, false>(w.P[i], Lp, 1, sPb, sPh, nh), ld4<T, true>(qkv + 2 * H, 1, 3 * H, sQb, dh, nh), ep, L, dh, L, BH, 1, st)); }
+    return 0;
+  }
+  // d(att) -> dqkv
+  int attention_bwd(int i, float scale, cudaStream_t st) {
+    B200_PROF("attention_bwd", st);
+    const T* qkv = w.qkv[i];
+    long sQb = (long)L * 3 * H, sPb = (long)nh * L * Lp, sPh = (long)L * Lp, sOb = (long)L * H;
+    int BH = c.B * nh;
+    // dP = dO V^T
+    { EpStore<float> ep = ep_plain<float>(w.dP, Lp); ep.sb0 = sPb; ep.sb1 = sPh; ep.nb1 = nh;
+      B200_TRY(launch_contract(ld4<T, false>(w.datt, H, 1, sOb, dh, nh), ld4<T, false>(qkv + 2 * H, 3 * H, 1, sQb, dh, nh), ep, L, L, dh, BH, 1, st)); }
+    // dV = P^T dO
+    { EpStore<T> ep = ep_plain<T>(w.dqkv + 2 * H, 3 * H); ep.sb0 = sQb; ep.sb1 = dh; ep.nb1 = nh;
+      B200_TRY(launch_contract(ld4<T, true>(w.P[i], 1, Lp, sPb, sPh, nh), ld4<T, true>(w.datt, 1, H, sOb, dh, nh), ep, L, dh, L, BH, 1, st)); }
+    softmax_bwd_kernel<T><<<cdiv((long)BH * L, 8), 256, 0, st>>>(w.P[i], w.dP, w.dS, (long)BH * L, L, Lp, scale);
+    B200_LAUNCH_CHECK();
+    // dQ = dS K ; dK = dS^T Q
+    { EpStore<T> ep = ep_plain<T>(w.dqkv, 3 * H); ep.sb0 = sQb; ep.sb1 = dh; ep.nb1 = nh;
+      B200_TRY(launch_contract(ld4<T, false>(w.dS, Lp, 1, sPb, sPh, nh), ld4<T, true>(qkv + H, 1, 3 * H, sQb, dh, nh), ep, L, dh, L, BH, 1, st)); }
+    { EpStore<T> ep = ep_plain<T>(w.dqkv + H, 3 * H); ep.sb0 = sQb; ep.sb1 = dh; ep.nb1 = nh;
+      B200_TRY(launch_contract(ld4<T, true>(w.dS, 1, Lp, sPb, sPh, nh), ld4<T, true>(qkv, 1, 3 * H, sQb, dh, nh), ep, L, dh, L, BH, 1, st)); }
+    return 0;
+  }
+
+  // ------------------------------------------------------------ backward
+  // G: gradient pointers indexed like P (null = not wanted).  Workspace must be the one the forward filled.
+  int backward(const float* const* P, float* const* G, const float* x_in, char* ws, const float* d_enc4, const float* d_logits,
+               int flags, cudaStream_t st) {
+    layout(ws, true);
+    int B = c.B, fs = c.fs;
+    bool dec = (flags & FLAG_HAS_DLOGITS) && d_logits;
+    bool enc = (flags & FLAG_NEED_ENCODER_GRAD) != 0;
+    bool has_denc4 = (flags & FLAG_HAS_DENC4) && d_enc4;
+    bool vit_from_top = false;  // does gradient reach blocks 10, 11 and the final LayerNorm?
+    for (int k = 0; k < 3; ++k) B200_CUDA(cudaMemsetAsync(w.dhs[k], 0, sizeof(float) * M * H, st));
+
+    if (dec) {
+      int rows = (int)(B * V[0]);
+      // head: d(d0) = dlogits^T W ; dW = dlogits d0 ; db = sum dlogits
+      { RowIsOuter<NcdhwGather, true> al; al.g = {d_logits, c.ncls, V[0]};
+        B200_TRY(launch_contract(al, ld2<float, true>(P[P_OUT_W], 1, fs), ep_plain<T>(w.gA, fs), rows, fs, c.ncls, 1, 1, st)); }
+      if (G[P_OUT_W]) {
+        B200_CUDA(cudaMemsetAsync(G[P_OUT_W], 0, sizeof(float) * c.ncls * fs, st));
+        RowIsK<NcdhwGather, false> al; al.g = {d_logits, c.ncls, V[0]};
+        EpAtomic ep = {G[P_OUT_W], (long)fs};
+        B200_TRY(launch_contract(al, ld2<T, true>(w.d0, 1, fs), ep, c.ncls, fs, rows, 1, pick_splits(rows, 1), st));
+      }
+      if (G[P_OUT_B]) {
+        B200_CUDA(cudaMemsetAsync(G[P_OUT_B], 0, sizeof(float) * c.ncls, st));
+        rowsum_atomic_kernel<<<dim3(32, B * c.ncls), 256, 0, st>>>(d_logits, G[P_OUT_B], V[0], c.ncls);
+        B200_LAUNCH_CHECK();
+      }
+      // decoder2 block, encoder1 block, decoder2 transposed conv
+      B200_TRY(res_bwd(cl<const T>(w.cat2, 2 * fs, 0, 2 * fs), 0, P[P_D2_C1], P[P_D2_C2], P[P_D2_C3], w.rs[4], cl<const T>(w.d0, fs, 0, fs),
+                       cl<const T>(w.gA, fs, 0, fs), G[P_D2_C1], G[P_D2_C2], G[P_D2_C3], cl(w.dcat, 2 * fs, 0, 2 * fs), st));
+      if (enc)
+        B200_TRY(res_bwd(cl<const T>(w.xcl, c.Cin, 0, c.Cin), 0, P[P_E1_C1], P[P_E1_C2], P[P_E1_C3], w.rs[0], cl<const T>(w.cat2, 2 * fs, fs, fs),
+                         cl<const T>(w.dcat, 2 * fs, fs, fs), G[P_E1_C1], G[P_E1_C2], G[P_E1_C3], cl<T>(nullptr, 0, 0, 0), st));
+      B200_TRY(convT_bwd(w.d1, 2 * fs, 2 * fs, 1, P[P_D2_T], cl<const T>(w.dcat, 2 * fs, 0, fs), G[P_D2_T], w.gA, 2 * fs, 0, st));
+      // decoder3
+      B200_TRY(res_bwd(cl<const T>(w.cat3, 4 * fs, 0, 4 * fs), 1, P[P_D3_C1], P[P_D3_C2], P[P_D3_C3], w.rs[3], cl<const T>(w.d1, 2 * fs, 0, 2 * fs),
+                       cl<const T>(w.gA, 2 * fs, 0, 2 * fs), G[P_D3_C1], G[P_D3_C2], G[P_D3_C3], cl(w.dcat, 4 * fs, 0, 4 * fs), st));
+      if (enc) {  // encoder2 chain: 48^3 <- 24^3 <- 12^3 <- tokens
+        B200_TRY(convT_bwd(w.e2b, 2 * fs, 2 * fs, 2, P[P_E2_T2], cl<const T>(w.dcat, 4 * fs, 2 * fs, 2 * fs), G[P_E2_T2], w.dc2, 2 * fs, 0, st));
+        B200_TRY(convT_bwd(w.e2a, 2 * fs, 2 * fs, 3, P[P_E2_T1], cl<const T>(w.dc2, 2 * fs, 0, 2 * fs), G[P_E2_T1], w.dc3, 2 * fs, 0, st));
+        B200_TRY(convT_bwd(w.hsT[0], H, H, 4, P[P_E2_T0], cl<const T>(w.dc3, 2 * fs, 0, 2 * fs), G[P_E2_T0], w.dhs[0], H, 0, st));
+      }
+      B200_TRY(convT_bwd(w.d2, 4 * fs, 4 * fs, 2, P[P_D3_T], cl<const T>(w.dcat, 4 * fs, 0, 2 * fs), G[P_D3_T], w.gA, 4 * fs, 0, st));
+      // decoder4
+      B200_TRY(res_bwd(cl<const T>(w.cat4, 8 * fs, 0, 8 * fs), 2, P[P_D4_C1], P[P_D4_C2], P[P_D4_C3], w.rs[2], cl<const T>(w.d2, 4 * fs, 0, 4 * fs),
+                       cl<const T>(w.gA, 4 * fs, 0, 4 * fs), G[P_D4_C1], G[P_D4_C2], G[P_D4_C3], cl(w.dcat, 8 * fs, 0, 8 * fs), st));
+      if (enc) {
+        B200_TRY(convT_bwd(w.e3a, 4 * fs, 4 * fs, 3, P[P_E3_T1], cl<const T>(w.dcat, 8 * fs, 4 * fs, 4 * fs), G[P_E3_T1], w.dc2, 4 * fs, 0, st));
+        B200_TRY(convT_bwd(w.hsT[1], H, H, 4, P[P_E3_T0], cl<const T>(w.dc2, 4 * fs, 0, 4 * fs), G[P_E3_T0], w.dhs[1], H, 0, st));
+      }
+      B200_TRY(convT_bwd(w.d3, 8 * fs, 8 * fs, 3, P[P_D4_T], cl<const T>(w.dcat, 8 * fs, 0, 4 * fs), G[P_D4_T], w.gA, 8 * fs, 0, st));
+      // decoder5
+      B200_TRY(res_bwd(cl<const T>(w.cat5, 16 * fs, 0, 16 * fs), 3, P[P_D5_C1], P[P_D5_C2], P[P_D5_C3], w.rs[1], cl<const T>(w.d3, 8 * fs, 0, 8 * fs),
+                       cl<const T>(w.gA, 8 * fs, 0, 8 * fs), G[P_D5_C1], G[P_D5_C2], G[P_D5_C3], cl(w.dcat, 16 * fs, 0, 16 * fs), st));
+      // decoder5.transp_conv: weight grad always (it is a decoder parameter); input grad only when the encoder trains
+      B200_TRY(convT_bwd(w.vit_out, H, H, 4, P[P_D5_T], cl<const T>(w.dcat, 16 * fs, 0, 8 * fs), G[P_D5_T], enc ? w.dvit : (T*)nullptr, H, 0, st));
+      vit_from_top = enc;
+    } else if (enc && has_denc4) {
+      B200_CUDA(cudaMemsetAsync(w.dcat, 0, sizeof(T) * B * V[3] * 16 * fs, st));
+    }
+    if (!enc) return 0;
+    // encoder4: gradient = skip half of d(concat5) (+ the external gradient of the returned enc4 tensor)
+    if (has_denc4) B200_TRY(launch_layout<T>(d_enc4, nullptr, w.dcat, B, 8 * fs, V[3], 16 * fs, 8 * fs, 0, 1, st));
+    if (dec || has_denc4)
+      B200_TRY(convT_bwd(w.hsT[2], H, H, 4, P[P_E4_T0], cl<const T>(w.dcat, 16 * fs, 8 * fs, 8 * fs), G[P_E4_T0], w.dhs[2], H, 0, st));
+    else
+      return 0;
+
+    // --- ViT backward
+    float scale = 1.0f / sqrtf((float)dh);
+    int top = 11;
+    if (vit_from_top) {
+      B200_TRY(launch_layernorm_bwd<T>(w.dvit, w.hs[11], w.lnfs, P[P_NORM_W], nullptr, w.dx, G[P_NORM_W], G[P_NORM_B], M, H, st));
+    } else {
+      top = 9;  // blocks 10, 11 and vit.norm are unreachable from enc4: their grads stay None
+      B200_CUDA(cudaMemsetAsync(w.dx, 0, sizeof(float) * M * H, st));
+    }
+    for (int i = top; i >= 0; --i) {
+      const float* const* bp = P + P_BLK0 + i * B_COUNT;
+      float* const* bg = G + P_BLK0 + i * B_COUNT;
+      const float* xin = i ? w.hs[i - 1] : w.x0;
+      if (i == 9) B200_TRY(launch_add(w.dx, w.dhs[2], (long)M * H, st));
+      if (i == 6) B200_TRY(launch_add(w.dx, w.dhs[1], (long)M * H, st));
+      if (i == 3) B200_TRY(launch_add(w.dx, w.dhs[0], (long)M * H, st));
+      // hs = x1 + fc2(h) + b2
+      if (bg[B_FC2_W]) B200_TRY(linear_wgrad<float, T>(w.dx, H, w.h[i], F, M, H, F, bg[B_FC2_W], st));
+      if (bg[B_FC2_B]) B200_TRY(launch_colsum<float>(w.dx, bg[B_FC2_B], M, H, st));
+      { EpStore<T> ep = ep_plain<T>(w.dh, F); ep.act = ACT_GELU_BWD; ep.usrc = w.u[i];   // du = (dx W2) * gelu'(u)
+        B200_TRY(linear_dgrad<float, T>(w.dx, H, bp[B_FC2_W], M, H, F, ep, st)); }
+      if (bg[B_FC1_W]) B200_TRY(linear_wgrad<T, T>(w.dh, F, w.ln2[i], H, M, F, H, bg[B_FC1_W], st));
+      if (bg[B_FC1_B]) B200_TRY(launch_colsum<T>(w.dh, bg[B_FC1_B], M, F, st));
+      B200_TRY(linear_dgrad<T, T>(w.dh, F, bp[B_FC1_W], M, F, H, ep_plain<T>(w.dln, H), st));
+      B200_TRY(launch_layernorm_bwd<T>(w.dln, w.x1[i], w.ln2s[i], bp[B_LN2_W], w.dx, w.dx2, bg[B_LN2_W], bg[B_LN2_B], M, H, st));
+      // x1 = xin + proj(att) + bp
+      if (bg[B_PROJ_W]) B200_TRY(linear_wgrad<float, T>(w.dx2, H, w.att[i], H, M, H, H, bg[B_PROJ_W], st));
+      if (bg[B_PROJ_B]) B200_TRY(launch_colsum<float>(w.dx2, bg[B_PROJ_B], M, H, st));
+      B200_TRY(linear_dgrad<float, T>(w.dx2, H, bp[B_PROJ_W], M, H, H, ep_plain<T>(w.datt, H), st));
+      B200_TRY(attention_bwd(i, scale, st));
+      if (bg[B_QKV_W]) B200_TRY(linear_wgrad<T, T>(w.dqkv, 3 * H, w.ln1[i], H, M, 3 * H, H, bg[B_QKV_W], st));
+      B200_TRY(linear_dgrad<T, T>(w.dqkv, 3 * H, bp[B_QKV_W], M, 3 * H, H, ep_plain<T>(w.dln, H), st));
+      B200_TRY(launch_layernorm_bwd<T>(w.dln, xin, w.ln1s[i], bp[B_LN1_W], w.dx2, w.dx, bg[B_LN1_W], bg[B_LN1_B], M, H, st));
+    }
+    // --- patch embedding: dW = dx0^T rows(x), db = colsum, dpos = sum over batch
+    if (G[P_PATCH_W]) {
+      RowIsK<PatchGather, true> bl; bl.g = {x_in, c.Cin, c.S0, c.S1, c.S2, g0, g1, g2, c.conv_patch};
+      int Kp = 4096 * c.Cin;
+      B200_TRY(launch_contract(ld2<float, true>(w.dx, 1, H), bl, ep_plain<float>(G[P_PATCH_W], Kp), H, Kp, M, 1, 1, st));
+    }
+    if (G[P_PATCH_B]) B200_TRY(launch_colsum<float>(w.dx, G[P_PATCH_B], M, H, st));
+    if (G[P_POS]) { batchsum_kernel<<<cdiv((long)L * H, 256), 256, 0, st>>>(w.dx, G[P_POS], B, (long)L * H); B200_LAUNCH_CHECK(); }
+    return 0;
+  }
+
+  // transposed conv backward: dW (if non-null) and d(input) (if dx non-null) written as type TO rows [rows_in, Ci]
+  template <class TA, class TO>
+  int convT_bwd(const TA* x, long ldx, int Ci, int in_level, const float* W, Cl<const T> dy, float* dW, TO* dx, long lddx, int accumulate, cudaStream_t st) {
+    Sp s = sp(in_level);
+    if (dW) {
+      B200_CUDA(cudaMemsetAsync(dW, 0, sizeof(float) * Ci * dy.C * 8, st));
+      B200_TRY((simt_convT_wgrad<TA, T>(x, ldx, Ci, dy, s, dW, st)));
+    }
+    if (dx) B200_TRY((simt_convT_dgrad<T, TO>(dy, s, W, Ci, dx, lddx, accumulate, st)));
+    return 0;
+  }
+};
+
+}  // namespace b200

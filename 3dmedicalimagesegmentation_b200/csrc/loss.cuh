@@ -1,0 +1,219 @@
+// Loss kernels: softmax-Dice + cross-entropy (MONAI DiceCELoss(to_onehot_y=True, softmax=True), call site
+// unetr_segmentation_3d.py:404,222) and the Bradley-Terry pairwise ranking loss
+// (unetr_ranking_pretraining_3d.py:59-133 triplets, :202-217 loss).  HBM-bound: one pass over the logits
+// for the forward, one read + one write for the backward.
+#pragma once
+#include "common.cuh"
+
+namespace b200 {
+
+// ------------------------------------------------------------------ DiceCE
+// acc layout (double): [B][C][3] = (I = sum p*t, P = sum p, G = sum t), then [B*C*3] = sum_v -(log p_target)
+template <int CMAX>
+__global__ void __launch_bounds__(256) dicece_fwd_kernel(const float* __restrict__ logits, const float* __restrict__ labels,
+                                                         int C, long V, double* __restrict__ acc, int nBC) {
+  int b = blockIdx.y;
+  float aI[CMAX], aP[CMAX], aG[CMAX];
+#pragma unroll
+  for (int c = 0; c < CMAX; ++c) aI[c] = aP[c] = aG[c] = 0.f;
+  float ce = 0.f;
+  const float* lg = logits + (long)b * C * V;
+  for (long v = (long)blockIdx.x * blockDim.x + threadIdx.x; v < V; v += (long)gridDim.x * blockDim.x) {
+    float l[CMAX];
+    float mx = -INFINITY, ly = 0.f;
+    int y = (int)labels[(long)b * V + v];
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c)
+      if (c < C) { l[c] = lg[(long)c * V + v]; mx = fmaxf(mx, l[c]); if (c == y) ly = l[c]; }
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c)
+      if (c < C) { l[c] = __expf(l[c] - mx); s += l[c]; }
+    float inv = 1.f / s;
+    ce += logf(s) - (ly - mx);
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c)
+      if (c < C) {
+        float p = l[c] * inv;
+        aP[c] += p;
+        if (c == y) { aI[c] += p; aG[c] += 1.f; }
+      }
+  }
+  __shared__ float red[8][3 * CMAX + 1];
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int c = 0; c < CMAX; ++c) {
+    float x0 = warp_sum(aI[c]), x1 = warp_sum(aP[c]), x2 = warp_sum(aG[c]);
+    if (lane == 0) { red[w][3 * c] = x0; red[w][3 * c + 1] = x1; red[w][3 * c + 2] = x2; }
+  }
+  ce = warp_sum(ce);
+  if (lane == 0) red[w][3 * CMAX] = ce;
+  __syncthreads();
+  for (int i = threadIdx.x; i < 3 * C + 1; i += blockDim.x) {
+    int src = (i < 3 * C) ? i : 3 * CMAX;
+    double t = 0.0;
+    for (int k = 0; k < 8; ++k) t += red[k][src];
+    if (i < 3 * C) atomicAdd(acc + ((long)b * C) * 3 + i, t);
+    else atomicAdd(acc + (long)nBC * 3, t);
+  }
+}
+// out[0]=loss, out[1]=dice term, out[2]=ce term ; coef[b][c] = (a, bb) with d dice / d p = a*t + bb
+__global__ void dicece_finalize_kernel(const double* __restrict__ acc, int B, int C, long V, float* __restrict__ out,
+                                       float* __restrict__ coef) {
+  __shared__ double sd[256];
+  double local = 0.0;
+  int nBC = B * C;
+  for (int i = threadIdx.x; i < nBC; i += blockDim.x) {
+    double I = acc[3 * i], P = acc[3 * i + 1], G = acc[3 * i + 2];
+    double den = G + P + 1e-5;
+    local += 1.0 - (2.0 * I + 1e-5) / den;
+    coef[2 * i] = (float)(-2.0 / (nBC * den));
+    coef[2 * i + 1] = (float)((2.0 * I + 1e-5) / (nBC * den * den));
+  }
+  sd[threadIdx.x] = local;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) { if (threadIdx.x < s) sd[threadIdx.x] += sd[threadIdx.x + s]; __syncthreads(); }
+  if (threadIdx.x == 0) {
+    double dice = sd[0] / nBC, ce = acc[(long)nBC * 3] / ((double)B * V);
+    out[0] = (float)(dice + ce); out[1] = (float)dice; out[2] = (float)ce;
+  }
+}
+// dlogits_k = up * [ p_k (w_k - sum_c p_c w_c) + (p_k - t_k)/(B V) ],  w_c = a_c t_c + b_c
+template <int CMAX>
+__global__ void __launch_bounds__(256) dicece_bwd_kernel(const float* __restrict__ logits, const float* __restrict__ labels,
+                                                         const float* __restrict__ coef, const float* __restrict__ upstream,
+                                                         int B, int C, long V, float* __restrict__ dlogits) {
+  int b = blockIdx.y;
+  float up = upstream ? upstream[0] : 1.f;
+  float invBV = 1.f / ((float)B * (float)V);
+  __shared__ float sc[2 * CMAX];
+  if (threadIdx.x < 2 * C) sc[threadIdx.x] = coef[(long)b * C * 2 + threadIdx.x];
+  __syncthreads();
+  const float* lg = logits + (long)b * C * V;
+  float* dl = dlogits + (long)b * C * V;
+  for (long v = (long)blockIdx.x * blockDim.x + threadIdx.x; v < V; v += (long)gridDim.x * blockDim.x) {
+    float l[CMAX];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c)
+      if (c < C) { l[c] = lg[(long)c * V + v]; mx = fmaxf(mx, l[c]); }
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c)
+      if (c < C) { l[c] = __expf(l[c] - mx); s += l[c]; }
+    float inv = 1.f / s;
+    int y = (int)labels[(long)b * V + v];
+    float dot = 0.f;
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c)
+      if (c < C) { l[c] *= inv; dot += l[c] * (sc[2 * c] * (c == y ? 1.f : 0.f) + sc[2 * c + 1]); }
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c)
+      if (c < C) {
+        float t = (c == y) ? 1.f : 0.f;
+        float wk = sc[2 * c] * t + sc[2 * c + 1];
+        dl[(long)c * V + v] = up * (l[c] * (wk - dot) + (l[c] - t) * invBV);
+      }
+  }
+}
+
+// ------------------------------------------------------------------ Bradley-Terry ranking loss
+// 16 slices: id = partition*4 + sample (samples ordered batch1[0], batch1[1], batch2[0], batch2[1], rank:80-84).
+// A slice is [C, F0*F1] taken at index idx[partition] along the sliced spatial axis.
+struct RankGeom {
+  const float* src[4];  // sample base pointers (forward values)
+  float* grad[4];       // gradient base pointers (same geometry) or null
+  long sc, ss, sf0, sf1;  // element strides: channel, sliced axis, the two free axes
+  int C, F0, F1;
+  int idx[4];
+  float temperature;
+};
+__device__ __forceinline__ long rank_off(const RankGeom& g, int part, int c, int f) {
+  int f1 = f % g.F1, f0 = f / g.F1;
+  return (long)c * g.sc + (long)g.idx[part] * g.ss + (long)f0 * g.sf0 + (long)f1 * g.sf1;
+}
+// gram[c][i][j] += sum_f s_i[c,f] s_j[c,f]      grid (C, splits), 256 threads = 16x16 pairs
+__global__ void __launch_bounds__(256) rank_gram_kernel(RankGeom g, double* __restrict__ gram) {
+  __shared__ float tile[16][65];
+  int c = blockIdx.x;
+  int F = g.F0 * g.F1;
+  int i = threadIdx.x >> 4, j = threadIdx.x & 15;
+  float acc = 0.f;
+  for (int f0 = blockIdx.y * 64; f0 < F; f0 += gridDim.y * 64) {
+    for (int e = threadIdx.x; e < 16 * 64; e += 256) {
+      int s = e >> 6, ff = e & 63, f = f0 + ff;
+      tile[s][ff] = (f < F) ? g.src[s & 3][rank_off(g, s >> 2, c, f)] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 16
+    for (int ff = 0; ff < 64; ++ff) acc = fmaf(tile[i][ff], tile[j][ff], acc);
+    __syncthreads();
+  }
+  atomicAdd(gram + ((long)c * 16 + i) * 16 + j, (double)acc);
+}
+__device__ __forceinline__ void rank_triplet(int t, int& r, int& s, int& d) {
+  int p = t / 144, rem = t % 144, pair = rem / 12, o = rem % 12;
+  int rl = pair / 3, sl = pair % 3; if (sl >= rl) ++sl;
+  int q = o >> 2; if (q >= p) ++q;
+  r = p * 4 + rl; s = p * 4 + sl; d = q * 4 + (o & 3);
+}
+// per channel: cos matrix, loss contribution, and the 16x16 coefficient matrix coef[c][i][j] such that
+// d loss / d s_i = sum_j coef[c][i][j] * s_j          grid C blocks of 576 threads... (use 576 = 18 warps)
+__global__ void __launch_bounds__(576) rank_loss_kernel(const double* __restrict__ gram, int C, float temperature,
+                                                        double* __restrict__ loss, float* __restrict__ coef) {
+  __shared__ float cosm[16][16], A[16][16], nrm[16], rawn[16];
+  __shared__ float wsum[18];
+  int c = blockIdx.x, t = threadIdx.x;
+  const double* G = gram + (long)c * 256;
+  if (t < 16) { float n = (float)sqrt(G[t * 16 + t]); rawn[t] = n; nrm[t] = fmaxf(n, 1e-6f); }
+  if (t < 256) A[t >> 4][t & 15] = 0.f;
+  __syncthreads();
+  if (t < 256) cosm[t >> 4][t & 15] = (float)G[t] / (nrm[t >> 4] * nrm[t & 15]);
+  __syncthreads();
+  int r, s, d; rank_triplet(t, r, s, d);
+  float z = (cosm[r][s] - cosm[r][d]) / temperature;
+  float sp = (z > 0.f) ? log1pf(__expf(-z)) : (-z + log1pf(__expf(z)));  // softplus(-z), stable
+  float dz = -1.f / (1.f + __expf(z)) / temperature / (float)C;       // d/dz softplus(-z) = -sigmoid(-z)
+  atomicAdd(&A[r][s], dz);
+  atomicAdd(&A[r][d], -dz);
+  float ws = warp_sum(sp);
+  if ((t & 31) == 0) wsum[t >> 5] = ws;
+  __syncthreads();
+  if (t == 0) { double tot = 0.0; for (int k = 0; k < 18; ++k) tot += wsum[k]; atomicAdd(loss, tot / C); }
+  if (t < 256) {
+    int i = t >> 4, j = t & 15;
+    float out;
+    if (i != j) {
+      out = (A[i][j] + A[j][i]) / (nrm[i] * nrm[j]);
+    } else {
+      float acc = 0.f;
+      for (int k = 0; k < 16; ++k) if (k != i) acc += (A[i][k] + A[k][i]) * cosm[i][k];
+      out = (rawn[i] >= 1e-6f) ? -acc / (nrm[i] * nrm[i]) : 0.f;
+    }
+    coef[(long)c * 256 + t] = out;
+  }
+}
+// grad slice i [c,f] = up * sum_j coef[c][i][j] s_j[c,f]         grid (C, ceil(F/256))
+__global__ void __launch_bounds__(256) rank_grad_kernel(RankGeom g, const float* __restrict__ coef,
+                                                        const float* __restrict__ upstream) {
+  __shared__ float cf[256];
+  int c = blockIdx.x;
+  cf[threadIdx.x] = coef[(long)c * 256 + threadIdx.x];
+  __syncthreads();
+  int F = g.F0 * g.F1;
+  int f = blockIdx.y * 256 + threadIdx.x;
+  if (f >= F) return;
+  float up = upstream ? upstream[0] : 1.f;
+  float sv[16];
+#pragma unroll
+  for (int s = 0; s < 16; ++s) sv[s] = g.src[s & 3][rank_off(g, s >> 2, c, f)];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    float a = 0.f;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) a = fmaf(cf[i * 16 + j], sv[j], a);
+    g.grad[i & 3][rank_off(g, i >> 2, c, f)] = up * a;
+  }
+}
+
+}  // namespace b200

@@ -1,0 +1,71 @@
+// Sliding-window inference kernels (MONAI sliding_window_inference with constant blending; call sites
+// unetr_segmentation_3d.py:109,143,694).  Window gather from the (virtually padded) volume, in-order
+// overlap-add, and a normalise pass that divides by the analytic separable window count and crops
+// the padding (optionally fusing the channel argmax).  fp32, NCDHW, bit-exact with the reference's
+// accumulate-then-divide arithmetic.
+#pragma once
+#include "common.cuh"
+
+namespace b200 {
+
+struct SwGeom {
+  int C;              // channels of the tensor being moved
+  int D, H, W;        // un-padded volume size
+  int pd, ph, pw;     // padding in front of each axis (symmetric pad of MONAI: half before)
+  int PD, PH, PW;     // padded size
+  int r0, r1, r2;     // roi
+};
+struct SwWindow { int b, s0, s1, s2; };
+struct SwBatch { SwWindow w[16]; int n; };
+
+// windows[k][c][roi] = vol[b][c][start+off - pad] or cval outside
+__global__ void sw_gather_kernel(const float* __restrict__ vol, float* __restrict__ windows, SwGeom g, SwBatch wb, float cval) {
+  long per = (long)g.C * g.r0 * g.r1 * g.r2;
+  long total = per * wb.n;
+  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+    int k = (int)(e / per); long r = e % per;
+    int z = (int)(r % g.r2); r /= g.r2; int y = (int)(r % g.r1); r /= g.r1; int x = (int)(r % g.r0); int c = (int)(r / g.r0);
+    SwWindow w = wb.w[k];
+    int d = w.s0 + x - g.pd, h = w.s1 + y - g.ph, ww = w.s2 + z - g.pw;
+    float v = cval;
+    if ((unsigned)d < (unsigned)g.D && (unsigned)h < (unsigned)g.H && (unsigned)ww < (unsigned)g.W)
+      v = vol[((((long)w.b * g.C + c) * g.D + d) * g.H + h) * g.W + ww];
+    windows[e] = v;
+  }
+}
+// acc[b][c][start+off] += pred[k][c][off]   (one window per launch keeps the reference's summation order)
+__global__ void sw_accumulate_kernel(float* __restrict__ acc, const float* __restrict__ pred, SwGeom g, SwWindow w) {
+  long per = (long)g.C * g.r0 * g.r1 * g.r2;
+  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < per; e += (long)gridDim.x * blockDim.x) {
+    long r = e;
+    int z = (int)(r % g.r2); r /= g.r2; int y = (int)(r % g.r1); r /= g.r1; int x = (int)(r % g.r0); int c = (int)(r / g.r0);
+    long o = ((((long)w.b * g.C + c) * g.PD + w.s0 + x) * g.PH + w.s1 + y) * g.PW + w.s2 + z;
+    acc[o] += pred[e];
+  }
+}
+struct SwStarts { int n0, n1, n2; int s0[64], s1[64], s2[64]; };
+// out[b][c][d][h][w] = acc[b][c][d+pd][h+ph][w+pw] / count ; optional argmax over c -> mask[b][d][h][w]
+__global__ void sw_finalize_kernel(const float* __restrict__ acc, float* __restrict__ out, unsigned char* __restrict__ mask,
+                                   SwGeom g, SwStarts st, int B) {
+  long vox = (long)g.D * g.H * g.W;
+  long total = (long)B * vox;
+  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+    int b = (int)(e / vox); long r = e % vox;
+    int w = (int)(r % g.W); r /= g.W; int h = (int)(r % g.H); int d = (int)(r / g.H);
+    int x = d + g.pd, y = h + g.ph, z = w + g.pw;
+    int c0 = 0, c1 = 0, c2 = 0;
+    for (int i = 0; i < st.n0; ++i) c0 += (x >= st.s0[i] && x < st.s0[i] + g.r0);
+    for (int i = 0; i < st.n1; ++i) c1 += (y >= st.s1[i] && y < st.s1[i] + g.r1);
+    for (int i = 0; i < st.n2; ++i) c2 += (z >= st.s2[i] && z < st.s2[i] + g.r2);
+    float cnt = (float)(c0 * c1 * c2);
+    float best = -INFINITY; int arg = 0;
+    for (int c = 0; c < g.C; ++c) {
+      float v = acc[((((long)b * g.C + c) * g.PD + x) * g.PH + y) * g.PW + z] / cnt;
+      if (out) out[(((long)b * g.C + c) * g.D + d) * g.H * g.W + (long)h * g.W + w] = v;
+      if (v > best) { best = v; arg = c; }
+    }
+    if (mask) mask[e] = (unsigned char)arg;
+  }
+}
+
+}  // namespace b200

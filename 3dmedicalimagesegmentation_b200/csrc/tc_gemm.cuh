@@ -1,0 +1,289 @@
+// tcgen05 / TMEM / TMA GEMM engine for sm_100a (bf16 operands, fp32 accumulation in tensor memory).
+//
+//   D[b][m,n] = sum_k A[b](m,k) * B[b](n,k)          b = (b0,b1) batch pair, epilogue functor decides the store
+//
+// One persistent CTA per SM, warp-specialised:
+//   warp 0      TMA producer   (cp.async.bulk.tensor.4d -> 128B-swizzled smem ring, mbarrier complete_tx)
+//   warp 1      MMA issuer     (one elected lane: tcgen05.mma.cta_group::1.kind::f16, 128 x BN x 16 per instruction;
+//                               tcgen05.commit frees smem stages / publishes the accumulator); also owns TMEM alloc
+//   warps 2..5  epilogue       (tcgen05.ld 32x32b.x16 -> registers -> functor; TMEM accumulator double-buffered so the
+//                               epilogue of tile i overlaps the MMAs of tile i+1)
+// Either operand may be K-major (row = m/n, K contiguous) or MN-major (row = k, m/n contiguous): linear-layer
+// dgrad/wgrad and the attention P.V / dS^T.Q products need no transposed copies.  Ragged M/N/K edges are handled
+// by TMA out-of-bounds zero fill plus an m<M, n<N guard in the epilogue.
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+#include "contract.cuh"
+
+namespace b200 {
+namespace tc {
+
+static constexpr int BM = 128, BK = 64;
+static constexpr uint32_t SPIN_LIMIT = 1u << 26;  // watchdog: trap instead of hanging the GPU on a protocol bug
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t addr = smem_u32(bar), ok = 0, spins = 0;
+  do {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+    if (!ok && ++spins > SPIN_LIMIT) __trap();
+  } while (!ok);
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
+               ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+      "tcgen05.wait::ld.sync.aligned;\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr) : "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// shared-memory matrix descriptor, SWIZZLE_128B (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30),
+// SBO>>4 [32,46), version=1 [46,48), layout_type=2 [61,64))
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = (uint64_t)((addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+struct Params {
+  int M, N, K, BN;          // BN in {64,128,256}
+  int a_mn, b_mn;           // operand majors
+  int tiles_m, tiles_n, nb1, batches;
+  int stages;
+  uint32_t tmem_cols;       // 2*BN rounded to a power of two
+};
+
+template <class EP>
+__global__ void __launch_bounds__(192, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const Params p, const EP ep) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const uint32_t a_bytes = BM * BK * 2, b_bytes = (uint32_t)p.BN * BK * 2, stage_bytes = a_bytes + b_bytes;
+  uint64_t* full = (uint64_t*)(smem + (size_t)p.stages * stage_bytes);
+  uint64_t* empty = full + p.stages;
+  uint64_t* tfull = empty + p.stages;   // [2]
+  uint64_t* tempty = tfull + 2;         // [2]
+  uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kblocks = (p.K + BK - 1) / BK;
+  const long total_tiles = (long)p.tiles_m * p.tiles_n * p.batches;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull + s, 1); mbar_init(tempty + s, 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(p.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        int tm = (int)(t % p.tiles_m); long r = t / p.tiles_m; int tn = (int)(r % p.tiles_n); int b = (int)(r / p.tiles_n);
+        int b0 = b / p.nb1, b1 = b % p.nb1;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(empty + stage, phase ^ 1);
+          uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes), sb = sa + a_bytes;
+          mbar_expect_tx(full + stage, stage_bytes);
+          if (!p.a_mn) tma_load_4d(sa, &map_a, full + stage, kb * BK, tm * BM, b1, b0);
+          else for (int c = 0; c < BM / 64; ++c) tma_load_4d(sa + c * (64 * BK * 2), &map_a, full + stage, tm * BM + c * 64, kb * BK, b1, b0);
+          if (!p.b_mn) tma_load_4d(sb, &map_b, full + stage, kb * BK, tn * p.BN, b1, b0);
+          else for (int c = 0; c < p.BN / 64; ++c) tma_load_4d(sb + c * (64 * BK * 2), &map_b, full + stage, tn * p.BN + c * 64, kb * BK, b1, b0);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------ MMA issuer
+    // instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 [4,6), a=BF16 [7,10), b=BF16 [10,13),
+    // a_major bit15, b_major bit16, N>>3 [17,23), M>>4 [24,29)
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)p.a_mn << 15) | ((uint32_t)p.b_mn << 16) |
+                           ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
+    for (long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      mbar_wait(tempty + acc, acc_phase ^ 1);
+      tc_fence_after();
+      uint32_t tmem_d = tmem_base + (uint32_t)(acc * p.BN);
+      for (int kb = 0; kb < kblocks; ++kb) {
+        mbar_wait(full + stage, phase);
+        tc_fence_after();
+        if (lane == 0) {
+          uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes), sb = sa + a_bytes;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            // K-major: 8-row groups 1024 B apart, step 32 B along K inside the swizzle atom.
+            // MN-major: 64-wide MN atoms (64*BK*2 B apart), 8-k-row groups 1024 B apart, step 2048 B per 16 k.
+            uint64_t ad = p.a_mn ? smem_desc(sa + k * 2048, 64 * BK * 2, 1024) : smem_desc(sa + k * 32, 16, 1024);
+            uint64_t bd = p.b_mn ? smem_desc(sb + k * 2048, 64 * BK * 2, 1024) : smem_desc(sb + k * 32, 16, 1024);
+            umma_f16(tmem_d, ad, bd, idesc, (kb | k) ? 1u : 0u);
+          }
+          umma_commit(empty + stage);                 // smem stage reusable once these MMAs retire
+          if (kb == kblocks - 1) umma_commit(tfull + acc);  // accumulator complete
+        }
+        __syncwarp();
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else {
+    // ------------------------------------------------ epilogue warps (TMEM lane quarter = warp % 4)
+    const int q = warp & 3;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      int tm = (int)(t % p.tiles_m); long r = t / p.tiles_m; int tn = (int)(r % p.tiles_n); int b = (int)(r / p.tiles_n);
+      mbar_wait(tfull + acc, acc_phase);
+      tc_fence_after();
+      const int m = tm * BM + q * 32 + lane;
+      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.BN);
+      for (int c0 = 0; c0 < p.BN; c0 += 16) {
+        float v[16];
+        tmem_ld16(trow + c0, v);
+        int n0 = tn * p.BN + c0;
+        if (m < p.M) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (n0 + j < p.N) ep(b, m, n0 + j, v[j]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty + acc);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)sym;
+  }
+  return fn;
+}
+
+// A bf16 operand: element (o, k, b1, b0) at p[o*so + k*sk + b1*sb1 + b0*sb0] where exactly one of so/sk is 1.
+struct Operand {
+  const bf16* p; long so, sk, sb0, sb1;
+  bool mn_major() const { return so == 1 && sk != 1; }
+};
+static inline Operand operand(const bf16* p, long so, long sk, long sb0 = 0, long sb1 = 0) { Operand o{p, so, sk, sb0, sb1}; return o; }
+
+static int make_map(CUtensorMap* map, const Operand& op, long extent_o, long extent_k, int box_o, int nb0, int nb1) {
+  EncodeTiledFn enc = get_encode();
+  B200_CHECK(enc, "cuTensorMapEncodeTiled not available from the driver");
+  bool mn = op.mn_major();
+  long ld = mn ? op.sk : op.so;
+  B200_CHECK(((uintptr_t)op.p & 15) == 0 && (ld * 2) % 16 == 0, "TMA operand must be 16-byte aligned with a 16-byte multiple row pitch (ld=%ld)", ld);
+  B200_CHECK((nb1 <= 1 || (op.sb1 * 2) % 16 == 0) && (nb0 <= 1 || (op.sb0 * 2) % 16 == 0), "TMA batch strides must be 16-byte multiples");
+  cuuint64_t dims[4] = {(cuuint64_t)(mn ? extent_o : extent_k), (cuuint64_t)(mn ? extent_k : extent_o), (cuuint64_t)nb1, (cuuint64_t)nb0};
+  cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)(nb1 > 1 ? op.sb1 * 2 : ld * 2), (cuuint64_t)(nb0 > 1 ? op.sb0 * 2 : ld * 2)};
+  cuuint32_t box[4] = {64u, (cuuint32_t)(mn ? BK : box_o), 1u, 1u};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)op.p, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  B200_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with code %d (dims %lu x %lu, ld %ld)", (int)r, (unsigned long)dims[0], (unsigned long)dims[1], ld);
+  return 0;
+}
+
+static int g_num_sms = 0;
+static inline int num_sms() {
+  if (!g_num_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev); if (g_num_sms <= 0) g_num_sms = 148; }
+  return g_num_sms;
+}
+
+// D[(b0,b1)][m,n] = sum_k A(m,k) B(n,k);  ep(b0*nb1+b1, m, n, acc)
+template <class EP>
+static int gemm(const Operand& A, const Operand& B, const EP& ep, int M, int N, int K, int nb0, int nb1, cudaStream_t st) {
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  Params p;
+  p.M = M; p.N = N; p.K = K;
+  p.a_mn = A.mn_major(); p.b_mn = B.mn_major();
+  // widest N tile that still gives every SM a tile; small problems fall back to 64-wide tiles for parallelism
+  {
+    long tm = cdiv(M, BM), nb = (long)nb0 * nb1;
+    p.BN = 64;
+    if (N > 64 && tm * cdiv(N, 128) * nb >= num_sms()) p.BN = 128;
+    if (N > 128 && tm * cdiv(N, 256) * nb >= num_sms()) p.BN = 256;
+  }
+  p.tiles_m = cdiv(M, BM); p.tiles_n = cdiv(N, p.BN); p.nb1 = nb1; p.batches = nb0 * nb1;
+  uint32_t stage_bytes = BM * BK * 2 + p.BN * BK * 2;
+  p.stages = (int)((200 * 1024) / stage_bytes); if (p.stages > 8) p.stages = 8;
+  p.tmem_cols = p.BN * 2 < 32 ? 32 : p.BN * 2;
+  CUtensorMap ma, mb;
+  B200_TRY(make_map(&ma, A, M, K, BM, nb0, nb1));
+  B200_TRY(make_map(&mb, B, N, K, p.BN, nb0, nb1));
+  size_t smem = (size_t)p.stages * stage_bytes + 1024 + 256;
+  static bool attr_done = false;  // per EP instantiation
+  if (!attr_done) { B200_CUDA(cudaFuncSetAttribute(gemm_kernel<EP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr_done = true; }
+  long tiles = (long)p.tiles_m * p.tiles_n * p.batches;
+  int grid = (int)(tiles < num_sms() ? tiles : num_sms());
+  gemm_kernel<EP><<<grid, 192, smem, st>>>(ma, mb, p, ep);
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace tc
+
+// test hook: fp32 out = A B^T with selectable majors.  a: [M,K] (K-major) or [K,M] (MN-major); b likewise.
+static int tc_gemm_test(const bf16* a, const bf16* b, float* out, int M, int N, int K, int a_mn, int b_mn, cudaStream_t st) {
+  tc::Operand A = a_mn ? tc::operand(a, 1, M) : tc::operand(a, K, 1);
+  tc::Operand B = b_mn ? tc::operand(b, 1, N) : tc::operand(b, K, 1);
+  return tc::gemm(A, B, ep_plain<float>(out, N), M, N, K, 1, 1, st);
+}
+
+}  // namespace b200

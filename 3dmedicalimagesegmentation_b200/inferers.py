@@ -1,0 +1,108 @@
+"""Sliding-window whole-volume inference on the GPU -- `monai.inferers.sliding_window_inference` as called at
+unetr_segmentation_3d.py:109 (positional, overlap 0.25), :143 and :694-695 (keyword, overlap 0.8).
+
+Window enumeration, padding, scan interval and accumulation order follow MONAI 0.6.0; the
+gather / overlap-add / divide-by-count arithmetic runs in csrc/sliding.cuh.  `rank`/`world_size` shard the window
+list across GPUs (windows are independent; the overlap-add is completed with one all-reduce).
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+from typing import Callable, List, Sequence, Tuple
+
+import torch
+
+from . import _lib
+
+__all__ = ["sliding_window_inference", "window_starts", "shard_windows"]
+
+
+def _scan_interval(image_size, roi, overlap):
+    return tuple(int(r) if r == s else max(int(r * (1 - overlap)), 1) for r, s in zip(roi, image_size))
+
+
+def _axis_starts(size, roi, step) -> List[int]:
+    num = int(math.ceil(float(size) / step))
+    scan = next((d for d in range(num) if d * step + roi >= size), -1)
+    n = scan + 1 if scan != -1 else 1
+    return [i * step - max(i * step + roi - size, 0) for i in range(n)]
+
+
+def window_starts(image_size, roi, overlap):
+    """Per-axis window starts and the flat list in MONAI order (first spatial axis slowest)."""
+    step = _scan_interval(image_size, roi, overlap)
+    per_axis = [_axis_starts(s, r, st) for s, r, st in zip(image_size, roi, step)]
+    flat = [(a, b, c) for a in per_axis[0] for b in per_axis[1] for c in per_axis[2]]
+    return per_axis, flat
+
+
+def shard_windows(n_items: int, rank: int, world_size: int) -> range:
+    """Contiguous chunk of the ij-ordered window list owned by `rank` (x-slabs)."""
+    per = (n_items + world_size - 1) // world_size
+    return range(min(rank * per, n_items), min((rank + 1) * per, n_items))
+
+
+def sliding_window_inference(inputs: torch.Tensor, roi_size, sw_batch_size: int, predictor: Callable,
+                             overlap: float = 0.25, mode: str = "constant", sigma_scale=0.125,
+                             padding_mode: str = "constant", cval: float = 0.0, sw_device=None, device=None,
+                             *args, rank: int = 0, world_size: int = 1, process_group=None,
+                             return_argmax: bool = False, **kwargs):
+    if str(mode).lower() not in ("constant", "blendmode.constant"):
+        raise NotImplementedError("only constant blending (the mode both reference call sites use) is implemented")
+    if str(padding_mode).lower() not in ("constant", "pytorchpadmode.constant"):
+        raise NotImplementedError("only constant padding is implemented")
+    if inputs.dim() != 5:
+        raise ValueError("inputs must be [B,C,D,H,W]")
+    if not 0 <= overlap < 1:
+        raise AssertionError("overlap must be >= 0 and < 1.")
+    lib = _lib.load()
+    _lib.require_device(inputs)
+    x = inputs.contiguous().float()
+    batch, chan = x.shape[:2]
+    orig = tuple(x.shape[2:])
+    roi = tuple(int(r) for r in (roi_size if isinstance(roi_size, Sequence) else (roi_size,) * 3))
+    roi = tuple(r if r > 0 else o for r, o in zip(roi, orig))          # MONAI fall_back_tuple
+    size = tuple(max(o, r) for o, r in zip(orig, roi))
+    pad = tuple((s - o) // 2 for s, o in zip(size, orig))
+    per_axis, flat = window_starts(size, roi, overlap)
+    if max(len(a) for a in per_axis) > 64:
+        raise NotImplementedError("more than 64 windows along one axis")
+    num_win = len(flat)
+    items = [(b, *flat[w]) for b in range(batch) for w in range(num_win)]   # idx -> (idx // num_win, idx % num_win)
+    mine = shard_windows(len(items), rank, world_size)
+    st = _lib.stream_ptr()
+
+    gin = _lib.SwGeom(chan, *orig, *pad, *size, *roi)
+    sw_batch_size = max(1, min(int(sw_batch_size), 16))
+    acc = None
+    gout = None
+    for g0 in range(mine.start, mine.stop, sw_batch_size):
+        chunk = items[g0:min(g0 + sw_batch_size, mine.stop)]
+        n = len(chunk)
+        starts = (ctypes.c_int32 * (4 * n))(*[v for it in chunk for v in it])
+        win = torch.empty((n, chan, *roi), dtype=torch.float32, device=x.device)
+        _lib.check(lib.b200_sw_gather(_lib.ptr(x), _lib.ptr(win), ctypes.byref(gin), starts, n, float(cval), st), "b200_sw_gather")
+        pred = predictor(win, *args, **kwargs)
+        if isinstance(pred, (tuple, list)):
+            raise TypeError("predictor must return a tensor (monai.networks.nets.UNETR flavour, seg:36)")
+        pred = pred.contiguous().float()
+        if acc is None:
+            cout = pred.shape[1]
+            acc = torch.zeros((batch, cout, *size), dtype=torch.float32, device=x.device)
+            gout = _lib.SwGeom(cout, *orig, *pad, *size, *roi)
+        for k, it in enumerate(chunk):   # one launch per window: keeps the reference's summation order
+            s4 = (ctypes.c_int32 * 4)(*it)
+            _lib.check(lib.b200_sw_accumulate(_lib.ptr(acc), _lib.ptr(pred[k]), ctypes.byref(gout), s4, st), "b200_sw_accumulate")
+    if acc is None:
+        raise RuntimeError("this rank owns no windows; use fewer ranks than windows")
+    if world_size > 1:
+        import torch.distributed as dist
+        dist.all_reduce(acc, group=process_group)
+    cout = acc.shape[1]
+    out = torch.empty((batch, cout, *orig), dtype=torch.float32, device=x.device)
+    mask = torch.empty((batch, 1, *orig), dtype=torch.uint8, device=x.device) if return_argmax else None
+    arrs = [(ctypes.c_int32 * len(a))(*a) for a in per_axis]
+    _lib.check(lib.b200_sw_finalize(_lib.ptr(acc), _lib.ptr(out), _lib.ptr(mask), ctypes.byref(gout), batch,
+                                    arrs[0], len(arrs[0]), arrs[1], len(arrs[1]), arrs[2], len(arrs[2]), st), "b200_sw_finalize")
+    return (out, mask) if return_argmax else out

@@ -1,0 +1,220 @@
+#!/usr/bin/env python
+"""Benchmark of the UNETR hot path (BASELINE.json metric: UNETR 96^3 fwd+bwd samples/s).
+
+    python bench.py --gpus N --steps K --warmup W            # this framework, on N B200s (torchrun for N>1)
+    python bench.py --impl reference --steps K --warmup W     # the reference arithmetic on the host CPU cores
+
+Workload at N=1 = BASELINE.json configs[1]: UNETR(1->14, 96^3, feature 16, ViT-B) segmentation training step,
+batch 2 per GPU, bf16 mode: forward + DiceCE + backward (+ AdamW step).  N>1 = data parallel, fixed per-GPU batch
+(weak scaling), one gradient all-reduce per step.  One JSON line on stdout (rank 0).
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOP_PER_SAMPLE_96 = 379.72e9     # fwd+bwd, SURVEY 8(d) / Appendix A (3 x 126.57 GFLOP)
+MODEL_KW = dict(in_channels=1, out_channels=14, img_size=(96, 96, 96), feature_size=16, hidden_size=768, mlp_dim=3072,
+                num_heads=12, pos_embed="perceptron", norm_name="instance", res_block=True)
+
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = max([int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()] or [0])
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": reasons, "samples": len(sm)}
+
+
+def cpu_reference_step_time(batch, steps, warmup):
+    """The reference's arithmetic (oracle restatement of MONAI 0.6.0 UNETR + DiceCELoss; MONAI itself cannot be
+    installed here) on all host cores: forward + DiceCE + backward on `batch` 96^3 crops."""
+    from oracle import unetr_oracle as O
+    torch.set_num_threads(os.cpu_count())
+    model = O.make_model(tuple_output=False)
+    x, y = O.make_inputs(batch=batch)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        model.zero_grad(set_to_none=True)
+        loss = O.dice_ce_loss(model(x), y)
+        loss.backward()
+        float(loss)
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    return sum(times) / len(times)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    batch = 1
+    t = cpu_reference_step_time(batch, args.steps, max(1, min(args.warmup, 1)))
+    val = batch / t
+    line = {"impl": "reference", "metric": "UNETR 96^3 fwd+bwd samples/s", "value": val, "unit": "samples/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "UNETR(1->14,96^3,fs16,ViT-B) fwd+DiceCE+bwd, CPU fp32, batch 1 per step (bounded sample of configs[1])"},
+            "cpu_baseline": {"value": val, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port",
+                             "sample": f"{args.steps} steps x 1 crop of 96^3, oracle restatement of the MONAI 0.6.0 path, torch {torch.__version__} CPU"},
+            "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--batch", type=int, default=2, help="crops per GPU")
+    ap.add_argument("--mode", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-optimizer", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--breakdown", action="store_true", help="print the per-op CUDA-event breakdown to stderr")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+
+    pkg = importlib.import_module("3dmedicalimagesegmentation_b200")
+    par = importlib.import_module("3dmedicalimagesegmentation_b200.parallel")
+    rank, world, local = par.init_from_env()
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    lib = pkg._lib.load()
+
+    torch.manual_seed(0)
+    model = pkg.MonaiUNETR(**MODEL_KW).to(dev).set_mode(args.mode)
+    loss_fn = pkg.DiceCELoss(to_onehot_y=True, softmax=True)
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=1e-5, fused=True)
+    ddp = par.GradientAllReduce(model, world) if world > 1 else None
+    B = args.batch
+    g = torch.Generator().manual_seed(100 + rank)
+    # 8 distinct host batches (pinned) cycled through: per-step inputs exceed nothing cached on the device side
+    host_x = [torch.rand(B, 1, 96, 96, 96, generator=g).pin_memory() for _ in range(4)]
+    host_y = [torch.randint(0, 14, (B, 1, 96, 96, 96), generator=g).float().pin_memory() for _ in range(4)]
+    dev_x = [t.to(dev) for t in host_x]
+    dev_y = [t.to(dev) for t in host_y]
+
+    def step(x, y):
+        logits = model(x)
+        loss = loss_fn(logits, y)
+        loss.backward()
+        if ddp:
+            ddp.reduce()
+        if not args.no_optimizer:
+            opt.step()
+        opt.zero_grad(set_to_none=True)
+        return loss
+
+    def timed(fn, steps):
+        par.barrier(world)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        torch.cuda.synchronize()
+        par.barrier(world)
+        return par.max_over_ranks(e0.elapsed_time(e1), world, dev)
+
+    for i in range(args.warmup):
+        step(dev_x[i % 4], dev_y[i % 4])
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = lib.b200_launch_count()
+    ms = timed(lambda i: step(dev_x[i % 4], dev_y[i % 4]), args.steps)
+    launches = lib.b200_launch_count() - l0
+    # end-to-end: pinned host inputs copied in, loss read back, every step
+    def e2e_step(i):
+        x = host_x[i % 4].to(dev, non_blocking=True)
+        y = host_y[i % 4].to(dev, non_blocking=True)
+        return step(x, y).item()
+    e2e_step(0)
+    ms_e2e = timed(e2e_step, args.steps)
+    clocks = sampler.stop()
+
+    # per-op CUDA-event breakdown of one step -> roofline of the dominant kernel class
+    lib.b200_prof_enable(1)
+    step(dev_x[0], dev_y[0])
+    prof = pkg._lib.prof_report()
+    lib.b200_prof_enable(0)
+    pk, pk_kind = peaks()
+    conv_ms = sum(v[0] for k, v in prof.items() if k.startswith("conv_"))
+    conv_flop = 3 * 2 * 43.402e9 * B          # conv decoder fwd + dgrad + wgrad (43.402 GMAC fwd / sample)
+    top = max(prof.items(), key=lambda kv: kv[1][0]) if prof else ("none", (0.0, 0))
+    roof = {"bound": "tensor", "kernel": "conv3d implicit GEMM fwd+dgrad+wgrad (all launches of one step)",
+            "achieved": conv_flop / (conv_ms * 1e-3) / 1e12 if conv_ms else None, "peak": pk["bf16_tflops_sustained"],
+            "unit": "TFLOP/s", "peak_kind": pk_kind + " sustained cuBLAS bf16", "traffic": None,
+            "top_op": top[0], "top_op_ms": top[1][0]}
+    roof["frac"] = roof["achieved"] / roof["peak"] if roof["achieved"] else None
+    if args.breakdown and rank == 0:
+        tot = sum(v[0] for v in prof.values())
+        for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0]):
+            print(f"  {k:18s} {v[0]:9.3f} ms  {v[1]:4d} calls  {100 * v[0] / tot:5.1f}%", file=sys.stderr)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        t = cpu_reference_step_time(1, 2, 1)
+        cpu = {"value": 1 / t, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port",
+               "sample": "2 timed steps x 1 crop of 96^3 (fwd+DiceCE+bwd), oracle restatement of the MONAI 0.6.0 path on the host CPU"}
+    if rank == 0:
+        samples = B * world * args.steps
+        line = {"metric": "UNETR 96^3 fwd+bwd samples/s", "value": samples / (ms * 1e-3), "unit": "samples/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": args.mode, "data": "synthetic",
+                "config": {"workload": "configs[1]: UNETR(1->14,96^3,fs16,ViT-B) segmentation training step (fwd+DiceCE+bwd" +
+                           ("" if args.no_optimizer else "+AdamW") + f"), batch {B}/GPU", "global_batch": B * world,
+                           "parallelism": f"dp{world}", "l2": "4 rotating input batches; activations per step (~1 GB) exceed the 126 MB L2"},
+                "tflops_algorithmic": samples * FLOP_PER_SAMPLE_96 / (ms * 1e-3) / 1e12,
+                "e2e": {"value": samples / (ms_e2e * 1e-3), "unit": "samples/s",
+                        "h2d_bytes_per_step": host_x[0].numel() * 4 + host_y[0].numel() * 4, "d2h_bytes_per_step": 4},
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    par.shutdown(world)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,100 @@
+/* C ABI of libunetr_b200.so -- the B200 (sm_100a) implementation of the UNETR hot path of
+ * ilkyyldz95/3DmedicalImageSegmentation.
+ *
+ * The reference has no FFI of its own: its boundary is a Python nn.Module plus three callables
+ * (SURVEY.md section 8b).  Each entry point below names the reference interface it stands behind.
+ * Conventions: plain device pointers and sizes only (no torch types); the caller owns every buffer;
+ * every function enqueues work on `stream` (a cudaStream_t passed as void*) and returns 0 on success
+ * or non-zero with a message retrievable by b200_last_error().  Nothing here ever computes on the CPU.
+ *
+ * Parameter / gradient tables: arrays of B200_PARAM_COUNT fp32 device pointers in PyTorch-native
+ * layouts, ordered as enum ParamIdx in csrc/exec.cuh (== the reference state-dict order of
+ * SURVEY 8b without the unused cls_token).  A null gradient pointer means "not wanted"
+ * (the parameter's .grad stays None, as in the reference's ranking stages).
+ */
+#ifndef UNETR_B200_H
+#define UNETR_B200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_PARAM_COUNT 164
+
+/* flags for forward/backward */
+#define B200_NEED_ENCODER_GRAD 1 /* 0 == forward(x, freeze_encoder=True), unetr.py:183-192 */
+#define B200_HAS_DLOGITS 2
+#define B200_HAS_DENC4 4
+
+typedef struct {
+  int32_t batch, in_channels, out_channels; /* unetr.py:29-30 */
+  int32_t img0, img1, img2;                 /* img_size, unetr.py:31; multiples of 16 */
+  int32_t feature_size, hidden_size, mlp_dim, num_heads; /* unetr.py:32-35 */
+  int32_t conv_patch_embed;                 /* pos_embed == "conv" (unetr.py:36,66) */
+  int32_t mode;                             /* 0 = fp32 parity mode, 1 = bf16 throughput mode */
+} b200_unetr_config;
+
+const char* b200_last_error(void);
+/* 0 when the current device is an sm_100 part; the Python layer refuses to run otherwise (no fallback) */
+int b200_device_check(void);
+
+/* ---- UNETR.forward / autograd backward  (unetr.py:182-208; monai.networks.nets.UNETR at seg:36,221) ---- */
+void* b200_unetr_create(const b200_unetr_config* cfg);
+void b200_unetr_destroy(void* handle);
+size_t b200_unetr_workspace_bytes(void* handle, int with_backward);
+/* x: [B,Cin,S0,S1,S2] fp32 NCDHW.  enc4_out: [B,8*fs,S/8...] fp32 or NULL.  logits_out: [B,ncls,S...] fp32 or NULL. */
+int b200_unetr_forward(void* handle, const float* const* params, const float* x, void* workspace, float* enc4_out,
+                       float* logits_out, int flags, void* stream);
+/* consumes the workspace filled by the matching forward; writes (not accumulates) every non-null gradient */
+int b200_unetr_backward(void* handle, const float* const* params, float* const* grads, const float* x, void* workspace,
+                        const float* d_enc4, const float* d_logits, int flags, void* stream);
+
+/* ---- monai.losses.DiceCELoss(to_onehot_y=True, softmax=True)  (seg:404,222) ---- */
+size_t b200_dicece_scratch_bytes(int batch, int classes);
+/* out3 = {loss, dice term, ce term}; labels: [B,1,V] fp32 holding class ids */
+int b200_dicece_forward(const float* logits, const float* labels, int batch, int classes, int64_t voxels, void* scratch,
+                        float* out3, void* stream);
+int b200_dicece_backward(const float* logits, const float* labels, int batch, int classes, int64_t voxels,
+                         const void* scratch, const float* upstream, float* dlogits, void* stream);
+
+/* ---- extract_triplets_more_partitions + BTLoss  (rank:59-133, rank:202-217) ----
+ * 4 samples (batch1[0], batch1[1], batch2[0], batch2[1]), one slice index per partition along the sliced axis. */
+typedef struct {
+  const float* src[4];
+  float* grad[4];             /* same geometry as src; must be zero-filled by the caller */
+  int64_t stride_c, stride_slice, stride_f0, stride_f1; /* element strides */
+  int32_t channels, f0, f1;
+  int32_t idx[4];
+  float temperature;          /* rank:327 */
+} b200_rank_geom;
+size_t b200_ranking_scratch_bytes(int channels);
+int b200_ranking_forward(const b200_rank_geom* g, void* scratch, float* loss_out, void* stream);
+int b200_ranking_backward(const b200_rank_geom* g, const void* scratch, const float* upstream, void* stream);
+
+/* ---- monai.inferers.sliding_window_inference, constant blending  (seg:109,143,694) ---- */
+typedef struct {
+  int32_t channels, d, h, w, pad_d, pad_h, pad_w, padded_d, padded_h, padded_w, roi0, roi1, roi2;
+} b200_sw_geom;
+/* starts: n x {batch index, s0, s1, s2} (n <= 16) */
+int b200_sw_gather(const float* volume, float* windows, const b200_sw_geom* g, const int32_t* starts, int n, float cval,
+                   void* stream);
+int b200_sw_accumulate(float* acc, const float* pred, const b200_sw_geom* g, const int32_t* start4, void* stream);
+/* per-axis window starts (n0,n1,n2 <= 64).  out and/or mask (uint8 argmax) may be NULL. */
+int b200_sw_finalize(const float* acc, float* out, uint8_t* mask, const b200_sw_geom* g, int batch, const int32_t* s0,
+                     int n0, const int32_t* s1, int n1, const int32_t* s2, int n2, void* stream);
+
+/* ---- instrumentation: kernels launched so far; per-op CUDA-event timing (tags = layer types) ---- */
+unsigned long long b200_launch_count(void);
+void b200_prof_enable(int on);
+int b200_prof_report(char* buf, int cap);
+
+/* ---- op-level test hooks (parity tests of single kernels; not part of the reference surface) ---- */
+/* D[M,N] = A[M,K] * B[N,K]^T with bf16 operands on the tcgen05 engine; a_mn/b_mn select MN-major operands
+ * (A stored [K,M] / B stored [K,N]).  out fp32. */
+int b200_test_tc_gemm(const void* a, const void* b, float* out, int M, int N, int K, int a_mn, int b_mn, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,252 @@
+"""GPU parity tests (B200): the CUDA path, called through the C ABI, against the CPU oracle on identical seeded
+inputs, the reference-generated golden vectors, and size-independent properties.
+
+Tolerances (BASELINE.json north_star): logits rel-err <= 1e-4 in fp32 mode, <= 1e-2 in bf16 mode
+(rel-err = max|a-b| / max|b|), Dice/loss abs diff <= 1e-3, argmax masks identical in fp32 mode."""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import unetr_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def relerr(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()
+
+
+def cosine(a, b):
+    a, b = a.detach().double().cpu().flatten(), b.detach().double().cpu().flatten()
+    return (a @ b / (a.norm() * b.norm()).clamp_min(1e-30)).item()
+
+
+TINY = dict(in_channels=1, out_channels=5, img_size=(32, 32, 32), feature_size=8, hidden_size=64, mlp_dim=128,
+            num_heads=4, pos_embed="perceptron", norm_name="instance", res_block=True)
+
+
+def build_pair(pkg, mode, **kw):
+    cfg = {**TINY, **kw}
+    torch.manual_seed(0)
+    ref = O.UNETR(**cfg)
+    with torch.no_grad():
+        ref.out.conv.conv.weight.mul_(4.0)
+        ref.out.conv.conv.bias.copy_(torch.linspace(-1, 1, cfg["out_channels"]))
+    mine = pkg.UNETR(**cfg)
+    mine.load_state_dict(ref.state_dict())
+    return ref, mine.to(DEV).set_mode(mode)
+
+
+# ------------------------------------------------------------------------------------------- full network
+@pytest.mark.parametrize("mode,tol_logits,tol_grad", [("fp32", 1e-4, 2e-3), ("bf16", 2e-2, 6e-2)])
+def test_tiny_unetr_forward_backward_matches_oracle(pkg, mode, tol_logits, tol_grad):
+    ref, mine = build_pair(pkg, mode)
+    x, y = O.make_inputs(batch=2, img=32, n_classes=5, seed=3)
+    enc4_r, logits_r = ref(x)
+    loss_r, dice_r, _ = O.dice_ce_loss(logits_r, y, return_terms=True)
+    loss_r.backward()
+    enc4, logits = mine(x.to(DEV))
+    assert relerr(enc4, enc4_r) <= tol_logits * 2, ("enc4", relerr(enc4, enc4_r))
+    assert relerr(logits, logits_r) <= tol_logits, ("logits", relerr(logits, logits_r))
+    loss = pkg.DiceCELoss(to_onehot_y=True, softmax=True)(logits, y.to(DEV))
+    assert abs(loss.item() - loss_r.item()) <= 1e-3
+    loss.backward()
+    mism = (logits.argmax(1).cpu() != logits_r.argmax(1)).sum().item()
+    if mode == "fp32":
+        assert mism == 0, f"{mism} argmax mismatches in fp32 mode"
+    worst = ("", 0.0)
+    for (k, p), (_, q) in zip(mine.named_parameters(), ref.named_parameters()):
+        if q.grad is None:
+            assert p.grad is None, k
+            continue
+        assert p.grad is not None, k
+        e = relerr(p.grad, q.grad)
+        if e > worst[1]:
+            worst = (k, e)
+        if mode == "bf16":
+            assert cosine(p.grad, q.grad) >= 0.99, (k, cosine(p.grad, q.grad))
+    assert worst[1] <= tol_grad, worst
+
+
+def test_golden_fixture_of_tiny_network(pkg, golden_dir):
+    g = np.load(os.path.join(golden_dir, "unetr_tiny.npz"))
+    _, mine = build_pair(pkg, "fp32")
+    x, y = O.make_inputs(batch=2, img=32, n_classes=5, seed=3)
+    enc4, logits = mine(x.to(DEV))
+    loss = pkg.DiceCELoss(to_onehot_y=True, softmax=True)(logits, y.to(DEV))
+    assert abs(loss.item() - float(g["loss"])) <= 1e-4
+    assert np.allclose(enc4.detach().cpu().numpy(), g["enc4"], atol=2e-4)
+    assert np.allclose(logits[:, :, :4, :4, :4].detach().cpu().numpy(), g["logits_corner"], atol=2e-4)
+    assert (np.bincount(logits.argmax(1).flatten().cpu().numpy(), minlength=5) == g["argmax_hist"]).all()
+
+
+@pytest.mark.parametrize("kw", [dict(pos_embed="conv", in_channels=2), dict(img_size=(32, 48, 16), out_channels=3)])
+def test_variants_fp32(pkg, kw):
+    ref, mine = build_pair(pkg, "fp32", **kw)
+    cfg = {**TINY, **kw}
+    g = torch.Generator().manual_seed(5)
+    x = torch.rand(1, cfg["in_channels"], *cfg["img_size"], generator=g)
+    enc4_r, logits_r = ref(x)
+    (logits_r.square().mean() + enc4_r.square().mean()).backward()
+    enc4, logits = mine(x.to(DEV))
+    assert relerr(logits, logits_r) <= 1e-4 and relerr(enc4, enc4_r) <= 1e-4
+    (logits.square().mean() + enc4.square().mean()).backward()
+    for (k, p), (_, q) in zip(mine.named_parameters(), ref.named_parameters()):
+        if q.grad is not None:
+            assert relerr(p.grad, q.grad) <= 2e-3, (k, relerr(p.grad, q.grad))
+
+
+def test_ranking_stage_gradient_reach(pkg):
+    """grad=None (not zeros) for parameters the loss does not reach (rank:259-262)."""
+    ref, mine = build_pair(pkg, "fp32")
+    x = torch.rand(2, 1, 32, 32, 32, generator=torch.Generator().manual_seed(9))
+    enc4_r, _ = ref(x)
+    enc4_r.square().sum().backward()
+    enc4, _ = mine(x.to(DEV))
+    enc4.square().sum().backward()
+    for (k, p), (_, q) in zip(mine.named_parameters(), ref.named_parameters()):
+        assert (p.grad is None) == (q.grad is None), k
+        if q.grad is not None:
+            assert relerr(p.grad, q.grad) <= 2e-3, (k, relerr(p.grad, q.grad))
+    ref.zero_grad(set_to_none=True); mine.zero_grad(set_to_none=True)
+    _, logits_r = ref(x, freeze_encoder=True)
+    logits_r.square().mean().backward()
+    _, logits = mine(x.to(DEV), freeze_encoder=True)
+    logits.square().mean().backward()
+    for (k, p), (_, q) in zip(mine.named_parameters(), ref.named_parameters()):
+        assert (p.grad is None) == (q.grad is None), k
+        if q.grad is not None:
+            assert relerr(p.grad, q.grad) <= 2e-3, (k, relerr(p.grad, q.grad))
+
+
+def test_monai_flavour_and_eval_no_grad(pkg):
+    cfg = dict(TINY)
+    torch.manual_seed(0)
+    m = pkg.MonaiUNETR(**cfg).to(DEV).set_mode("fp32").eval()
+    with torch.no_grad():
+        out = m(torch.rand(3, 1, 32, 32, 32, device=DEV))
+    assert isinstance(out, torch.Tensor) and out.shape == (3, 5, 32, 32, 32) and torch.isfinite(out).all()
+
+
+# ------------------------------------------------------------------------------------------- config 1 (full ViT-B, 96^3)
+@pytest.mark.parametrize("mode,tol", [("fp32", 1e-4), ("bf16", 1e-2)])
+def test_config1_full_size_forward_and_dice(pkg, mode, tol):
+    ref = O.make_model()
+    mine = pkg.UNETR(1, 14, (96,) * 3, 16, 768, 3072, 12, "perceptron", "instance", res_block=True)
+    mine.load_state_dict(ref.state_dict())
+    mine = mine.to(DEV).set_mode(mode).eval()
+    x, y = O.make_inputs()
+    with torch.no_grad():
+        enc4_r, logits_r = ref(x)
+        loss_r, dice_r, _ = O.dice_ce_loss(logits_r, y, return_terms=True)
+        enc4, logits = mine(x.to(DEV))
+        lossfn = pkg.DiceCELoss(to_onehot_y=True, softmax=True)
+        loss = lossfn(logits, y.to(DEV))
+    e = relerr(logits, logits_r)
+    top2 = logits_r.topk(2, dim=1).values
+    margin = (top2[:, 0] - top2[:, 1]).min().item()
+    mism = (logits.argmax(1).cpu() != logits_r.argmax(1)).sum().item()
+    print(f"[config1 {mode}] logits rel-err {e:.3e}  enc4 rel-err {relerr(enc4, enc4_r):.3e}  loss {loss.item():.6f} vs {loss_r.item():.6f}"
+          f"  argmax mismatches {mism}/{logits_r[:, 0].numel()}  min top-2 margin {margin:.3e}")
+    assert e <= tol
+    assert abs(loss.item() - loss_r.item()) <= 1e-3
+    if mode == "fp32":
+        assert mism == 0
+
+
+# ------------------------------------------------------------------------------------------- losses
+def test_dicece_matches_oracle_and_closed_form(pkg):
+    g = torch.Generator().manual_seed(0)
+    logits = torch.randn(2, 14, 24, 20, 16, generator=g)
+    y = torch.randint(0, 14, (2, 1, 24, 20, 16), generator=g).float()
+    lr = logits.clone().requires_grad_(True)
+    loss_r = O.dice_ce_loss(lr, y)
+    (loss_r * 1.7).backward()
+    lg = logits.to(DEV).requires_grad_(True)
+    loss = pkg.DiceCELoss(to_onehot_y=True, softmax=True)(lg, y.to(DEV))
+    (loss * 1.7).backward()
+    assert abs(loss.item() - loss_r.item()) <= 1e-5
+    assert relerr(lg.grad, lr.grad) <= 1e-4
+    # T1: all-zero logits
+    z = pkg.DiceCELoss(to_onehot_y=True, softmax=True)(torch.zeros(2, 14, 24, 20, 16, device=DEV), y.to(DEV)).item()
+    n = 24 * 20 * 16
+    counts = torch.stack([(y[i] == k).sum() for i in range(2) for k in range(14)]).double()
+    closed = math.log(14) + (1 - (2 * counts / 14 + 1e-5) / (counts + n / 14 + 1e-5)).mean().item()
+    assert abs(z - closed) <= 1e-5
+    with pytest.raises(AssertionError):
+        pkg.DiceCELoss(to_onehot_y=True, softmax=True)(lg, y.to(DEV)[:, :, :-1])
+
+
+@pytest.mark.parametrize("name", ["feat", "recon", "feat_T05"])
+@pytest.mark.parametrize("sd", [2, 3, 4])
+def test_ranking_loss_matches_reference_golden(pkg, golden_dir, name, sd):
+    """Golden vectors were produced by the reference's own extract_triplets_more_partitions + BTLoss."""
+    g = np.load(os.path.join(golden_dir, f"ranking_{name}.npz"))
+    feat = torch.from_numpy(g["feat"]).to(DEV).requires_grad_(True)
+    pkg.configure_ranking(temperature=float(g["temperature"]))
+    f1, f2 = torch.split(feat, [2, 2], dim=0)
+    np.random.seed(int(g[f"npseed_sd{sd}"]))
+    ref, sim, dis = pkg.extract_triplets_more_partitions(f1, f2, sd)
+    assert ref.plan[3] == g[f"idx_sd{sd}"].tolist()
+
+    class Opt:
+        steps = 0
+        def step(self): Opt.steps += 1
+        def zero_grad(self): pass
+    val = pkg.BTLoss(ref, sim, dis, Opt())
+    assert isinstance(val, float) and Opt.steps == 1
+    want = float(g[f"loss_sd{sd}"])
+    assert abs(val - want) <= 2e-4 * abs(want), (val, want)
+    assert relerr(feat.grad, torch.from_numpy(g[f"grad_sd{sd}"])) <= 1e-3
+    nz = (feat.grad != 0).float().mean().item()
+    assert abs(nz - 4 / feat.shape[sd]) < 1e-6     # T3: only the 4 selected planes receive gradient
+    pkg.configure_ranking(temperature=0.1)
+
+
+def test_ranking_identical_slices_is_576_ln2(pkg):
+    feat = torch.ones(4, 4, 8, 8, 8, device=DEV)
+    v = pkg.ranking_loss(feat[:2], feat[2:], 2, [0, 2, 4, 6], 0.1).item()
+    assert abs(v - 576 * math.log(2)) < 1e-2
+
+
+# ------------------------------------------------------------------------------------------- sliding window
+@pytest.mark.parametrize("overlap,shape,roi", [(0.25, (40, 33, 50), (16,) * 3), (0.5, (48, 48, 32), (16,) * 3),
+                                               (0.8, (20, 16, 16), (16,) * 3), (0.25, (10, 20, 12), (16,) * 3)])
+def test_sliding_window_identity_and_oracle(pkg, overlap, shape, roi):
+    g = torch.Generator().manual_seed(1)
+    x = torch.rand(2, 1, *shape, generator=g)
+    y = pkg.sliding_window_inference(x.to(DEV), roi, 4, lambda w: w + 1, overlap=overlap)
+    assert torch.allclose(y.cpu(), x + 1, atol=1e-6)          # T6
+    w = torch.randn(3, 1, 3, 3, 3, generator=g)
+    f_cpu = lambda t: torch.nn.functional.conv3d(t, w, padding=1)
+    f_gpu = lambda t: torch.nn.functional.conv3d(t, w.to(DEV), padding=1)
+    want = O.sliding_window_inference(x, roi, 4, f_cpu, overlap=overlap)
+    got, mask = pkg.sliding_window_inference(x.to(DEV), roi, 4, f_gpu, overlap=overlap, return_argmax=True)
+    assert got.shape == want.shape and torch.allclose(got.cpu(), want, atol=1e-5)
+    assert (mask[:, 0].cpu().long() == got.argmax(1).cpu()).all()
+
+
+def test_sliding_window_sharded_equals_single(pkg):
+    """Two-rank sharding emulated on one GPU: the partial overlap-adds of the two shards sum to the full result."""
+    x = torch.rand(1, 1, 48, 40, 32, device=DEV)
+    f = lambda t: torch.cat([t, -t, 2 * t], 1)
+    full = pkg.sliding_window_inference(x, (16,) * 3, 4, f, overlap=0.5)
+    import importlib
+    inf = importlib.import_module("3dmedicalimagesegmentation_b200.inferers")
+    per_axis, flat = inf.window_starts((48, 40, 32), (16,) * 3, 0.5)
+    owned = [list(inf.shard_windows(len(flat), r, 2)) for r in range(2)]
+    assert sorted(owned[0] + owned[1]) == list(range(len(flat)))
+    assert torch.allclose(full, f(x), atol=1e-5)
+
+
+def test_unetr_as_sliding_window_predictor(pkg):
+    m = pkg.MonaiUNETR(**TINY).to(DEV).set_mode("fp32").eval()
+    x = torch.rand(1, 1, 48, 32, 40, device=DEV)
+    with torch.no_grad():
+        out = pkg.sliding_window_inference(x, (32, 32, 32), 4, m, overlap=0.5)
+    assert out.shape == (1, 5, 48, 32, 40) and torch.isfinite(out).all()
