@@ -68,6 +68,24 @@ static int launch_cast(const TI* in, TO* out, long n, cudaStream_t st) {
   return 0;
 }
 
+struct CastJob { const float* src; bf16* dst; long n; };
+struct CastJobs { CastJob j[64]; int count; };
+// fp32 -> bf16 for up to 64 tensors in one launch: grid (blocks per tensor, tensor)
+__global__ void multi_cast_kernel(const CastJobs jobs) {
+  const CastJob jb = jobs.j[blockIdx.y];
+  long n4 = jb.n >> 2;
+  const float4* s4 = reinterpret_cast<const float4*>(jb.src);
+  uint2* d2 = reinterpret_cast<uint2*>(jb.dst);
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
+    float4 v = s4[i];
+    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    uint2 o; o.x = *reinterpret_cast<uint32_t*>(&a); o.y = *reinterpret_cast<uint32_t*>(&b);
+    d2[i] = o;
+  }
+  for (long i = (n4 << 2) + (long)blockIdx.x * blockDim.x + threadIdx.x; i < jb.n; i += (long)gridDim.x * blockDim.x)
+    jb.dst[i] = __float2bfloat16_rn(jb.src[i]);
+}
+
 __global__ void add_kernel(float* __restrict__ dst, const float* __restrict__ src, long n) {
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   long stride = (long)gridDim.x * blockDim.x;
@@ -110,7 +128,7 @@ static int launch_layernorm_fwd(const float* x, const float* g, const float* b, 
 template <class TG>
 __global__ void layernorm_bwd_dx_kernel(const TG* __restrict__ g, const float* __restrict__ x,
                                         const float* __restrict__ stats, const float* __restrict__ gamma,
-                                        const float* dx_res, float* dx_out, int M, int H) {
+                                        const float* dx_res, float* dx_out, TG* dx_out_cast, int M, int H) {
   int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   int lane = threadIdx.x & 31;
   if (row >= M) return;
@@ -128,6 +146,7 @@ __global__ void layernorm_bwd_dx_kernel(const TG* __restrict__ g, const float* _
     float v = rstd * (gg - s1 - xh * s2);
     if (dx_res) v += dx_res[(long)row * H + i];
     dx_out[(long)row * H + i] = v;
+    if (dx_out_cast) dx_out_cast[(long)row * H + i] = from_f<TG>(v);
   }
 }
 // dgamma[h] = sum_rows g*xhat ; dbeta[h] = sum_rows g.   grid = H/32 blocks of (32 x 8)
@@ -153,9 +172,9 @@ __global__ void layernorm_bwd_params_kernel(const TG* __restrict__ g, const floa
 }
 template <class TG>
 static int launch_layernorm_bwd(const TG* g, const float* x, const float* stats, const float* gamma,
-                                const float* dx_res, float* dx_out, float* dgamma, float* dbeta, int M, int H,
+                                const float* dx_res, float* dx_out, TG* dx_out_cast, float* dgamma, float* dbeta, int M, int H,
                                 cudaStream_t st) {
-  layernorm_bwd_dx_kernel<TG><<<cdiv(M, 8), 256, 0, st>>>(g, x, stats, gamma, dx_res, dx_out, M, H);
+  layernorm_bwd_dx_kernel<TG><<<cdiv(M, 8), 256, 0, st>>>(g, x, stats, gamma, dx_res, dx_out, dx_out_cast, M, H);
   B200_LAUNCH_CHECK();
   if (dgamma) {
     layernorm_bwd_params_kernel<TG><<<cdiv(H, 32), dim3(32, 8), 0, st>>>(g, x, stats, dgamma, dbeta, M, H);

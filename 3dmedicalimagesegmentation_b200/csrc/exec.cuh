@@ -8,7 +8,10 @@
 //   * the residual stream and all statistics are fp32, activations are T (float = parity mode, bf16 = throughput).
 // Caller owns all memory: parameters / gradients are PyTorch-layout fp32 pointers, the workspace is one buffer.
 #pragma once
+#include <type_traits>
+
 #include "ops.cuh"
+#include "tc_gemm.cuh"
 
 namespace b200 {
 
@@ -58,8 +61,11 @@ struct Workspace {
   T *xcl, *c1tmp, *e2a, *e2b, *e3a, *cat5, *cat4, *cat3, *cat2, *d3, *d2, *d1, *d0;
   ResSave<T> rs[5];  // enc1, dec5, dec4, dec3, dec2
   double* stat_acc;
+  // bf16 mode only: packed bf16 copies of the GEMM weights (refreshed every forward), same layouts as the fp32 masters
+  bf16 *wqkv[12], *wproj[12], *wfc1[12], *wfc2[12], *wT[10];
   // backward scratch
   float *dx, *dx2, *dhs[3], *dP;
+  T *dxb, *dx2b;  // bf16 mode: operand copies of the fp32 residual-stream gradients
   T *dvit, *dh, *dln, *datt, *dqkv, *dS, *gA, *dcat, *dc2, *dc3, *da1, *dc1;
   double* bwd_acc;
   size_t bytes;
@@ -71,6 +77,21 @@ struct Exec {
   int g0, g1, g2, L, Lp, M, H, F, nh, dh;
   long V[5];  // voxels per sample at levels 0 (full) .. 4 (tokens)
   Workspace<T> w;
+  static constexpr bool kTC = std::is_same<T, bf16>::value;  // tcgen05 engine for the dense contractions
+
+  // the 10 transposed convs in table order: (param index, Ci, Co)
+  void convT_desc(int i, int& pidx, int& Ci, int& Co) const {
+    const int fs = c.fs, Hh = c.hidden;
+    const int tab[10][3] = {{P_E2_T0, Hh, 2 * fs}, {P_E2_T1, 2 * fs, 2 * fs}, {P_E2_T2, 2 * fs, 2 * fs}, {P_E3_T0, Hh, 4 * fs},
+                            {P_E3_T1, 4 * fs, 4 * fs}, {P_E4_T0, Hh, 8 * fs}, {P_D5_T, Hh, 8 * fs}, {P_D4_T, 8 * fs, 4 * fs},
+                            {P_D3_T, 4 * fs, 2 * fs}, {P_D2_T, 2 * fs, fs}};
+    pidx = tab[i][0]; Ci = tab[i][1]; Co = tab[i][2];
+  }
+  size_t convT_elems(int i) const { int p, ci, co; convT_desc(i, p, ci, co); return (size_t)ci * co * 8; }
+  const bf16* convT_packed(const float* const* P, const float* W) const {
+    for (int i = 0; i < 10; ++i) { int p, ci, co; convT_desc(i, p, ci, co); if (P[p] == W) return w.wT[i]; }
+    return nullptr;
+  }
 
   explicit Exec(const UnetrConfig& cfg) : c(cfg) {
     g0 = c.S0 / 16; g1 = c.S1 / 16; g2 = c.S2 / 16;
@@ -108,8 +129,16 @@ struct Exec {
       w.rs[i].mr1 = b.take<float>(2 * B * co[i]); w.rs[i].mr2 = b.take<float>(2 * B * co[i]); w.rs[i].mr3 = b.take<float>(2 * B * co[i]);
     }
     w.stat_acc = b.take<double>((size_t)2 * B * 8 * fs);
+    if (kTC) {
+      for (int i = 0; i < 12; ++i) {
+        w.wqkv[i] = b.take<bf16>((size_t)3 * H * H); w.wproj[i] = b.take<bf16>((size_t)H * H);
+        w.wfc1[i] = b.take<bf16>((size_t)F * H); w.wfc2[i] = b.take<bf16>((size_t)H * F);
+      }
+      for (int i = 0; i < 10; ++i) w.wT[i] = b.take<bf16>(convT_elems(i));
+    }
     if (with_backward) {
       w.dx = b.take<float>(MH); w.dx2 = b.take<float>(MH);
+      w.dxb = b.take<T>(MH); w.dx2b = b.take<T>(MH);
       for (int i = 0; i < 3; ++i) w.dhs[i] = b.take<float>(MH);
       w.dP = b.take<float>(PP); w.dS = b.take<T>(PP);
       w.dvit = b.take<T>(MH); w.dh = b.take<T>(MF); w.dln = b.take<T>(MH); w.datt = b.take<T>(MH); w.dqkv = b.take<T>(3 * MH);
@@ -122,17 +151,51 @@ struct Exec {
   }
 
   // ------------------------------------------------------------ engine dispatch (CUDA-core engine; see exec.cu for tcgen05)
-  template <class TA, class TO>
-  int linear_fwd(const TA* A, long lda, const float* W, int Mr, int N, int K, const EpStore<TO>& ep, cudaStream_t st) {
-    return simt_linear_fwd(A, lda, W, Mr, N, K, ep, st);
+  // Wb = packed bf16 copy of W (bf16 mode) -- operands of the tcgen05 engine; fp32 mode runs the CUDA-core engine.
+  template <class TO>
+  int linear_fwd(const T* A, long lda, const float* W, const bf16* Wb, int Mr, int N, int K, const EpStore<TO>& ep, cudaStream_t st) {
+    if constexpr (kTC) {
+      B200_PROF("linear_fwd", st);
+      return tc::gemm(tc::operand(A, lda, 1), tc::operand(Wb, K, 1), ep, Mr, N, K, 1, 1, st);
+    } else {
+      return simt_linear_fwd(A, lda, W, Mr, N, K, ep, st);
+    }
   }
-  template <class TG, class TO>
-  int linear_dgrad(const TG* dY, long ldy, const float* W, int Mr, int N, int K, const EpStore<TO>& ep, cudaStream_t st) {
-    return simt_linear_dgrad(dY, ldy, W, Mr, N, K, ep, st);
+  template <class TO>  // dX[M,K] = dY[M,N] W[N,K]   (W is the MN-major B operand: no transposed copy)
+  int linear_dgrad(const T* dY, long ldy, const float* W, const bf16* Wb, int Mr, int N, int K, const EpStore<TO>& ep, cudaStream_t st) {
+    if constexpr (kTC) {
+      B200_PROF("linear_dgrad", st);
+      return tc::gemm(tc::operand(dY, ldy, 1), tc::operand(Wb, 1, K), ep, Mr, K, N, 1, 1, st);
+    } else {
+      return simt_linear_dgrad(dY, ldy, W, Mr, N, K, ep, st);
+    }
   }
-  template <class TG, class TX>
-  int linear_wgrad(const TG* dY, long ldy, const TX* X, long ldx, int Mr, int N, int K, float* dW, cudaStream_t st) {
-    return simt_linear_wgrad(dY, ldy, X, ldx, Mr, N, K, dW, st);
+  // dW[N,K] = dY^T X   (both operands MN-major)
+  int linear_wgrad(const T* dY, long ldy, const T* X, long ldx, int Mr, int N, int K, float* dW, cudaStream_t st) {
+    if constexpr (kTC) {
+      B200_PROF("linear_wgrad", st);
+      return tc::gemm(tc::operand(dY, 1, ldy), tc::operand(X, 1, ldx), ep_plain<float>(dW, K), N, K, Mr, 1, 1, st);
+    } else {
+      return simt_linear_wgrad(dY, ldy, X, ldx, Mr, N, K, dW, st);
+    }
+  }
+  // bf16 mode: refresh the packed weight copies (one launch for all ViT + transposed-conv weights)
+  int pack_weights(const float* const* P, cudaStream_t st) {
+    if constexpr (kTC) {
+      B200_PROF("pack_weights", st);
+      CastJobs jobs; int n = 0;
+      auto add = [&](const float* src, bf16* dst, size_t cnt) { jobs.j[n].src = src; jobs.j[n].dst = dst; jobs.j[n].n = (long)cnt; ++n; };
+      for (int i = 0; i < 12; ++i) {
+        const float* const* bp = P + P_BLK0 + i * B_COUNT;
+        add(bp[B_QKV_W], w.wqkv[i], (size_t)3 * H * H); add(bp[B_PROJ_W], w.wproj[i], (size_t)H * H);
+        add(bp[B_FC1_W], w.wfc1[i], (size_t)F * H); add(bp[B_FC2_W], w.wfc2[i], (size_t)H * F);
+      }
+      for (int i = 0; i < 10; ++i) { int p, ci, co; convT_desc(i, p, ci, co); add(P[p], w.wT[i], convT_elems(i)); }
+      jobs.count = n;
+      multi_cast_kernel<<<dim3(64, n), 256, 0, st>>>(jobs);
+      B200_LAUNCH_CHECK();
+    }
+    return 0;
   }
 
   // ------------------------------------------------------------ InstanceNorm helpers
@@ -221,6 +284,8 @@ struct Exec {
   int forward(const float* const* P, const float* x_in, char* ws, float* enc4_out, float* logits_out, int flags, cudaStream_t st) {
     layout(ws, false);
     int B = c.B, fs = c.fs;
+    B200_TRY(pack_weights(P, st));
+    cur_params = P;
     // --- patch embedding (a5): tokens = rows(x) W^T + b + pos
     {
       RowIsOuter<PatchGather, false> al; al.g = {x_in, c.Cin, c.S0, c.S1, c.S2, g0, g1, g2, c.conv_patch};
@@ -233,15 +298,15 @@ struct Exec {
       const float* const* bp = P + P_BLK0 + i * B_COUNT;
       const float* xin = i ? w.hs[i - 1] : w.x0;
       B200_TRY(launch_layernorm_fwd<T>(xin, bp[B_LN1_W], bp[B_LN1_B], w.ln1[i], w.ln1s[i], M, H, st));
-      B200_TRY(linear_fwd<T, T>(w.ln1[i], H, bp[B_QKV_W], M, 3 * H, H, ep_plain<T>(w.qkv[i], 3 * H), st));
+      B200_TRY(linear_fwd<T>(w.ln1[i], H, bp[B_QKV_W], w.wqkv[i], M, 3 * H, H, ep_plain<T>(w.qkv[i], 3 * H), st));
       B200_TRY(attention_fwd(i, scale, st));
       { EpStore<float> ep = ep_plain<float>(w.x1[i], H); ep.bias = bp[B_PROJ_B]; ep.resid = xin; ep.ldr = H;
-        B200_TRY(linear_fwd<T, float>(w.att[i], H, bp[B_PROJ_W], M, H, H, ep, st)); }
+        B200_TRY(linear_fwd<float>(w.att[i], H, bp[B_PROJ_W], w.wproj[i], M, H, H, ep, st)); }
       B200_TRY(launch_layernorm_fwd<T>(w.x1[i], bp[B_LN2_W], bp[B_LN2_B], w.ln2[i], w.ln2s[i], M, H, st));
       { EpStore<T> ep = ep_plain<T>(w.h[i], F); ep.bias = bp[B_FC1_B]; ep.act = ACT_GELU; ep.preact = w.u[i];
-        B200_TRY(linear_fwd<T, T>(w.ln2[i], H, bp[B_FC1_W], M, F, H, ep, st)); }
+        B200_TRY(linear_fwd<T>(w.ln2[i], H, bp[B_FC1_W], w.wfc1[i], M, F, H, ep, st)); }
       { EpStore<float> ep = ep_plain<float>(w.hs[i], H); ep.bias = bp[B_FC2_B]; ep.resid = w.x1[i]; ep.ldr = H;
-        B200_TRY(linear_fwd<T, float>(w.h[i], F, bp[B_FC2_W], M, H, F, ep, st)); }
+        B200_TRY(linear_fwd<float>(w.h[i], F, bp[B_FC2_W], w.wfc2[i], M, H, F, ep, st)); }
     }
     B200_TRY(launch_layernorm_fwd<T>(w.hs[11], P[P_NORM_W], P[P_NORM_B], w.vit_out, w.lnfs, M, H, st));
     for (int k = 0; k < 3; ++k) B200_TRY(launch_cast<float, T>(w.hs[3 + 3 * k], w.hsT[k], (long)M * H, st));
@@ -274,10 +339,21 @@ struct Exec {
     return 0;
   }
 
-  template <class TA>
-  int convT_fwd(const TA* x, long ldx, int Ci, int in_level, const float* W, Cl<T> out, cudaStream_t st) {
-    return simt_convT_fwd<TA, T>(x, ldx, Ci, sp(in_level), W, out, st);
+  int convT_fwd(const T* x, long ldx, int Ci, int in_level, const float* W, Cl<T> out, cudaStream_t st) {
+    if constexpr (kTC) {
+      if (cur_params) {
+        const bf16* Wb = convT_packed(cur_params, W);
+        if (Wb) {   // [rows, Ci] x W[Ci][Co*8] (MN-major B), scatter epilogue writes straight into the concat buffer
+          B200_PROF("convT_fwd", st);
+          Sp s = sp(in_level);
+          EpConvTScatter<T> ep = {out.p, s.D, s.H, s.W, out.pitch, out.coff};
+          return tc::gemm(tc::operand(x, ldx, 1), tc::operand(Wb, 1, (long)out.C * 8), ep, (int)s.rows(), out.C * 8, Ci, 1, 1, st);
+        }
+      }
+    }
+    return simt_convT_fwd<T, T>(x, ldx, Ci, sp(in_level), W, out, st);
   }
+  const float* const* cur_params = nullptr;
 
   // softmax(Q K^T * scale) V per (batch, head); scores fp32, probabilities T (kept for backward)
   int attention_fwd(int i, float scale, cudaStream_t st) {
@@ -286,11 +362,13 @@ struct Exec {
     long sQb = (long)L * 3 * H, sPb = (long)nh * L * Lp, sPh = (long)L * Lp;
     int BH = c.B * nh;
     { EpStore<float> ep = ep_plain<float>(w.S, Lp); ep.sb0 = sPb; ep.sb1 = sPh; ep.nb1 = nh;
-      B200_TRY(launch_contract(ld4<T, false>(qkv, 3 * H, 1, sQb, dh, nh), ld4<T, false>(qkv + H, 3 * H, 1, sQb, dh, nh), ep, L, L, dh, BH, 1, st)); }
+      if constexpr (kTC) B200_TRY(tc::gemm(tc::operand(qkv, 3 * H, 1, sQb, dh), tc::operand(qkv + H, 3 * H, 1, sQb, dh), ep, L, L, dh, c.B, nh, st));
+      else B200_TRY(launch_contract(ld4<T, false>(qkv, 3 * H, 1, sQb, dh, nh), ld4<T, false>(qkv + H, 3 * H, 1, sQb, dh, nh), ep, L, L, dh, BH, 1, st)); }
     softmax_fwd_kernel<T><<<cdiv((long)BH * L, 8), 256, 0, st>>>(w.S, w.P[i], (long)BH * L, L, Lp, scale);
     B200_LAUNCH_CHECK();
     { EpStore<T> ep = ep_plain<T>(w.att[i], H); ep.sb0 = (long)L * H; ep.sb1 = dh; ep.nb1 = nh;
-      B200_TRY(launch_contract(ld4<T, false>(w.P[i], Lp, 1, sPb, sPh, nh), ld4<T, true>(qkv + 2 * H, 1, 3 * H, sQb, dh, nh), ep, L, dh, L, BH, 1, st)); }
+      if constexpr (kTC) B200_TRY(tc::gemm(tc::operand(w.P[i], Lp, 1, sPb, sPh), tc::operand(qkv + 2 * H, 1, 3 * H, sQb, dh), ep, L, dh, L, c.B, nh, st));
+      else B200_TRY(launch_contract(ld4<T, false>(w.P[i], Lp, 1, sPb, sPh, nh), ld4<T, true>(qkv + 2 * H, 1, 3 * H, sQb, dh, nh), ep, L, dh, L, BH, 1, st)); }
     return 0;
   }
   // d(att) -> dqkv
@@ -301,17 +379,21 @@ struct Exec {
     int BH = c.B * nh;
     // dP = dO V^T
     { EpStore<float> ep = ep_plain<float>(w.dP, Lp); ep.sb0 = sPb; ep.sb1 = sPh; ep.nb1 = nh;
-      B200_TRY(launch_contract(ld4<T, false>(w.datt, H, 1, sOb, dh, nh), ld4<T, false>(qkv + 2 * H, 3 * H, 1, sQb, dh, nh), ep, L, L, dh, BH, 1, st)); }
+      if constexpr (kTC) B200_TRY(tc::gemm(tc::operand(w.datt, H, 1, sOb, dh), tc::operand(qkv + 2 * H, 3 * H, 1, sQb, dh), ep, L, L, dh, c.B, nh, st));
+      else B200_TRY(launch_contract(ld4<T, false>(w.datt, H, 1, sOb, dh, nh), ld4<T, false>(qkv + 2 * H, 3 * H, 1, sQb, dh, nh), ep, L, L, dh, BH, 1, st)); }
     // dV = P^T dO
     { EpStore<T> ep = ep_plain<T>(w.dqkv + 2 * H, 3 * H); ep.sb0 = sQb; ep.sb1 = dh; ep.nb1 = nh;
-      B200_TRY(launch_contract(ld4<T, true>(w.P[i], 1, Lp, sPb, sPh, nh), ld4<T, true>(w.datt, 1, H, sOb, dh, nh), ep, L, dh, L, BH, 1, st)); }
+      if constexpr (kTC) B200_TRY(tc::gemm(tc::operand(w.P[i], 1, Lp, sPb, sPh), tc::operand(w.datt, 1, H, sOb, dh), ep, L, dh, L, c.B, nh, st));
+      else B200_TRY(launch_contract(ld4<T, true>(w.P[i], 1, Lp, sPb, sPh, nh), ld4<T, true>(w.datt, 1, H, sOb, dh, nh), ep, L, dh, L, BH, 1, st)); }
     softmax_bwd_kernel<T><<<cdiv((long)BH * L, 8), 256, 0, st>>>(w.P[i], w.dP, w.dS, (long)BH * L, L, Lp, scale);
     B200_LAUNCH_CHECK();
     // dQ = dS K ; dK = dS^T Q
     { EpStore<T> ep = ep_plain<T>(w.dqkv, 3 * H); ep.sb0 = sQb; ep.sb1 = dh; ep.nb1 = nh;
-      B200_TRY(launch_contract(ld4<T, false>(w.dS, Lp, 1, sPb, sPh, nh), ld4<T, true>(qkv + H, 1, 3 * H, sQb, dh, nh), ep, L, dh, L, BH, 1, st)); }
+      if constexpr (kTC) B200_TRY(tc::gemm(tc::operand(w.dS, Lp, 1, sPb, sPh), tc::operand(qkv + H, 1, 3 * H, sQb, dh), ep, L, dh, L, c.B, nh, st));
+      else B200_TRY(launch_contract(ld4<T, false>(w.dS, Lp, 1, sPb, sPh, nh), ld4<T, true>(qkv + H, 1, 3 * H, sQb, dh, nh), ep, L, dh, L, BH, 1, st)); }
     { EpStore<T> ep = ep_plain<T>(w.dqkv + H, 3 * H); ep.sb0 = sQb; ep.sb1 = dh; ep.nb1 = nh;
-      B200_TRY(launch_contract(ld4<T, true>(w.dS, 1, Lp, sPb, sPh, nh), ld4<T, true>(qkv, 1, 3 * H, sQb, dh, nh), ep, L, dh, L, BH, 1, st)); }
+      if constexpr (kTC) B200_TRY(tc::gemm(tc::operand(w.dS, 1, Lp, sPb, sPh), tc::operand(qkv, 1, 3 * H, sQb, dh), ep, L, dh, L, c.B, nh, st));
+      else B200_TRY(launch_contract(ld4<T, true>(w.dS, 1, Lp, sPb, sPh, nh), ld4<T, true>(qkv, 1, 3 * H, sQb, dh, nh), ep, L, dh, L, BH, 1, st)); }
     return 0;
   }
 
@@ -388,35 +470,37 @@ struct Exec {
     float scale = 1.0f / sqrtf((float)dh);
     int top = 11;
     if (vit_from_top) {
-      B200_TRY(launch_layernorm_bwd<T>(w.dvit, w.hs[11], w.lnfs, P[P_NORM_W], nullptr, w.dx, G[P_NORM_W], G[P_NORM_B], M, H, st));
+      B200_TRY(launch_layernorm_bwd<T>(w.dvit, w.hs[11], w.lnfs, P[P_NORM_W], nullptr, w.dx, w.dxb, G[P_NORM_W], G[P_NORM_B], M, H, st));
     } else {
       top = 9;  // blocks 10, 11 and vit.norm are unreachable from enc4: their grads stay None
       B200_CUDA(cudaMemsetAsync(w.dx, 0, sizeof(float) * M * H, st));
+      B200_CUDA(cudaMemsetAsync(w.dxb, 0, sizeof(T) * M * H, st));
     }
     for (int i = top; i >= 0; --i) {
       const float* const* bp = P + P_BLK0 + i * B_COUNT;
       float* const* bg = G + P_BLK0 + i * B_COUNT;
       const float* xin = i ? w.hs[i - 1] : w.x0;
-      if (i == 9) B200_TRY(launch_add(w.dx, w.dhs[2], (long)M * H, st));
-      if (i == 6) B200_TRY(launch_add(w.dx, w.dhs[1], (long)M * H, st));
-      if (i == 3) B200_TRY(launch_add(w.dx, w.dhs[0], (long)M * H, st));
+      if (i == 9 || i == 6 || i == 3) {
+        B200_TRY(launch_add(w.dx, w.dhs[(i - 3) / 3], (long)M * H, st));
+        B200_TRY(launch_cast<float, T>(w.dx, w.dxb, (long)M * H, st));
+      }
       // hs = x1 + fc2(h) + b2
-      if (bg[B_FC2_W]) B200_TRY(linear_wgrad<float, T>(w.dx, H, w.h[i], F, M, H, F, bg[B_FC2_W], st));
+      if (bg[B_FC2_W]) B200_TRY(linear_wgrad(w.dxb, H, w.h[i], F, M, H, F, bg[B_FC2_W], st));
       if (bg[B_FC2_B]) B200_TRY(launch_colsum<float>(w.dx, bg[B_FC2_B], M, H, st));
       { EpStore<T> ep = ep_plain<T>(w.dh, F); ep.act = ACT_GELU_BWD; ep.usrc = w.u[i];   // du = (dx W2) * gelu'(u)
-        B200_TRY(linear_dgrad<float, T>(w.dx, H, bp[B_FC2_W], M, H, F, ep, st)); }
-      if (bg[B_FC1_W]) B200_TRY(linear_wgrad<T, T>(w.dh, F, w.ln2[i], H, M, F, H, bg[B_FC1_W], st));
+        B200_TRY(linear_dgrad<T>(w.dxb, H, bp[B_FC2_W], w.wfc2[i], M, H, F, ep, st)); }
+      if (bg[B_FC1_W]) B200_TRY(linear_wgrad(w.dh, F, w.ln2[i], H, M, F, H, bg[B_FC1_W], st));
       if (bg[B_FC1_B]) B200_TRY(launch_colsum<T>(w.dh, bg[B_FC1_B], M, F, st));
-      B200_TRY(linear_dgrad<T, T>(w.dh, F, bp[B_FC1_W], M, F, H, ep_plain<T>(w.dln, H), st));
-      B200_TRY(launch_layernorm_bwd<T>(w.dln, w.x1[i], w.ln2s[i], bp[B_LN2_W], w.dx, w.dx2, bg[B_LN2_W], bg[B_LN2_B], M, H, st));
+      B200_TRY(linear_dgrad<T>(w.dh, F, bp[B_FC1_W], w.wfc1[i], M, F, H, ep_plain<T>(w.dln, H), st));
+      B200_TRY(launch_layernorm_bwd<T>(w.dln, w.x1[i], w.ln2s[i], bp[B_LN2_W], w.dx, w.dx2, w.dx2b, bg[B_LN2_W], bg[B_LN2_B], M, H, st));
       // x1 = xin + proj(att) + bp
-      if (bg[B_PROJ_W]) B200_TRY(linear_wgrad<float, T>(w.dx2, H, w.att[i], H, M, H, H, bg[B_PROJ_W], st));
+      if (bg[B_PROJ_W]) B200_TRY(linear_wgrad(w.dx2b, H, w.att[i], H, M, H, H, bg[B_PROJ_W], st));
       if (bg[B_PROJ_B]) B200_TRY(launch_colsum<float>(w.dx2, bg[B_PROJ_B], M, H, st));
-      B200_TRY(linear_dgrad<float, T>(w.dx2, H, bp[B_PROJ_W], M, H, H, ep_plain<T>(w.datt, H), st));
+      B200_TRY(linear_dgrad<T>(w.dx2b, H, bp[B_PROJ_W], w.wproj[i], M, H, H, ep_plain<T>(w.datt, H), st));
       B200_TRY(attention_bwd(i, scale, st));
-      if (bg[B_QKV_W]) B200_TRY(linear_wgrad<T, T>(w.dqkv, 3 * H, w.ln1[i], H, M, 3 * H, H, bg[B_QKV_W], st));
-      B200_TRY(linear_dgrad<T, T>(w.dqkv, 3 * H, bp[B_QKV_W], M, 3 * H, H, ep_plain<T>(w.dln, H), st));
-      B200_TRY(launch_layernorm_bwd<T>(w.dln, xin, w.ln1s[i], bp[B_LN1_W], w.dx2, w.dx, bg[B_LN1_W], bg[B_LN1_B], M, H, st));
+      if (bg[B_QKV_W]) B200_TRY(linear_wgrad(w.dqkv, 3 * H, w.ln1[i], H, M, 3 * H, H, bg[B_QKV_W], st));
+      B200_TRY(linear_dgrad<T>(w.dqkv, 3 * H, bp[B_QKV_W], w.wqkv[i], M, 3 * H, H, ep_plain<T>(w.dln, H), st));
+      B200_TRY(launch_layernorm_bwd<T>(w.dln, xin, w.ln1s[i], bp[B_LN1_W], w.dx2, w.dx, w.dxb, bg[B_LN1_W], bg[B_LN1_B], M, H, st));
     }
     // --- patch embedding: dW = dx0^T rows(x), db = colsum, dpos = sum over batch
     if (G[P_PATCH_W]) {
@@ -430,12 +514,12 @@ struct Exec {
   }
 
   // transposed conv backward: dW (if non-null) and d(input) (if dx non-null) written as type TO rows [rows_in, Ci]
-  template <class TA, class TO>
-  int convT_bwd(const TA* x, long ldx, int Ci, int in_level, const float* W, Cl<const T> dy, float* dW, TO* dx, long lddx, int accumulate, cudaStream_t st) {
+  template <class TO>
+  int convT_bwd(const T* x, long ldx, int Ci, int in_level, const float* W, Cl<const T> dy, float* dW, TO* dx, long lddx, int accumulate, cudaStream_t st) {
     Sp s = sp(in_level);
     if (dW) {
       B200_CUDA(cudaMemsetAsync(dW, 0, sizeof(float) * Ci * dy.C * 8, st));
-      B200_TRY((simt_convT_wgrad<TA, T>(x, ldx, Ci, dy, s, dW, st)));
+      B200_TRY((simt_convT_wgrad<T, T>(x, ldx, Ci, dy, s, dW, st)));
     }
     if (dx) B200_TRY((simt_convT_dgrad<T, TO>(dy, s, W, Ci, dx, lddx, accumulate, st)));
     return 0;

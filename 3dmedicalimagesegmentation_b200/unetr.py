@@ -92,13 +92,12 @@ def _vit(in_channels, img_size, hidden, mlp_dim, heads, pos_embed) -> nn.Module:
 # ------------------------------------------------------------------------------------------------
 class _UnetrFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, module: "UNETR", x: torch.Tensor, freeze_encoder: bool, *params: torch.Tensor):
+    def forward(ctx, module: "UNETR", x: torch.Tensor, freeze_encoder: bool, needs_grad: bool, *params: torch.Tensor):
         lib = _lib.load()
         _lib.require_device(x)
         x = x.contiguous().float()
         batch = x.shape[0]
         handle = module._handle(batch)
-        needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
         ws = torch.empty(lib.b200_unetr_workspace_bytes(handle, 1 if needs_grad else 0), dtype=torch.uint8, device=x.device)
         fs, s = module.feature_size, module.img_size
         enc4 = torch.empty((batch, 8 * fs, s[0] // 8, s[1] // 8, s[2] // 8), dtype=torch.float32, device=x.device)
@@ -125,7 +124,7 @@ class _UnetrFunction(torch.autograd.Function):
         has_dl, has_de = d_logits is not None, d_enc4 is not None
         n = len(params)
         if not (has_dl or has_de):
-            return (None, None, None) + (None,) * n
+            return (None, None, None, None) + (None,) * n
         flags = (_lib.FLAG_NEED_ENCODER_GRAD if enc else 0) | (_lib.FLAG_HAS_DLOGITS if has_dl else 0) | \
                 (_lib.FLAG_HAS_DENC4 if has_de else 0)
         reach = module._grad_reach(has_dl, enc, has_dl or has_de)
@@ -150,7 +149,7 @@ class _UnetrFunction(torch.autograd.Function):
         _lib.check(lib.b200_unetr_backward(ctx.handle, module._param_table(params), gtab, _lib.ptr(x), _lib.ptr(ws),
                                            _lib.ptr(d_enc4), _lib.ptr(d_logits), flags, _lib.stream_ptr()),
                    "b200_unetr_backward")
-        return (None, None, None) + tuple(grads)
+        return (None, None, None, None) + tuple(grads)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -301,7 +300,10 @@ class UNETR(nn.Module):
     def forward(self, x_in, freeze_encoder=False):
         if x_in.dim() != 5 or tuple(x_in.shape[1:]) != (self.in_channels, *self.img_size):
             raise ValueError(f"expected input [B,{self.in_channels},{self.img_size}], got {tuple(x_in.shape)}")
-        enc4, logits = _UnetrFunction.apply(self, x_in, bool(freeze_encoder), *self._ordered_params())
+        params = self._ordered_params()
+        # grad mode is off inside Function.forward, so decide here whether the backward workspace is needed
+        needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        enc4, logits = _UnetrFunction.apply(self, x_in, bool(freeze_encoder), needs_grad, *params)
         return (enc4, logits) if self.tuple_output else logits
 
 
