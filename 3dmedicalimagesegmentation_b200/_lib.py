@@ -52,9 +52,12 @@ SIGNATURES = {
     "b200_sw_accumulate": (c_int, [c_void_p, c_void_p, POINTER(SwGeom), POINTER(c_int32), c_void_p]),
     "b200_sw_finalize": (c_int, [c_void_p, c_void_p, c_void_p, POINTER(SwGeom), c_int, POINTER(c_int32), c_int,
                                  POINTER(c_int32), c_int, POINTER(c_int32), c_int, c_void_p]),
+    "b200_unetr_peek": (c_int, [c_void_p, c_char_p, c_void_p, c_size_t]),
     "b200_launch_count": (ctypes.c_ulonglong, []),
     "b200_prof_enable": (None, [c_int]),
     "b200_prof_report": (c_int, [ctypes.c_char_p, c_int]),
+    "b200_test_tc_conv": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int,
+                                  c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "b200_test_tc_gemm": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
 }
 

@@ -203,6 +203,15 @@ int b200_sw_finalize(const float* acc, float* out, uint8_t* mask, const b200_sw_
   return 0;
 }
 
+int b200_unetr_peek(void* handle, const char* name, void* dst, size_t cap) {
+  Handle* h = (Handle*)handle;
+  size_t bytes = 0;
+  const void* src = h->f32 ? h->f32->peek(name, &bytes) : h->b16->peek(name, &bytes);
+  B200_CHECK(src, "no workspace buffer named %s", name);
+  if (bytes > cap) bytes = cap;
+  B200_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToDevice));
+  return 0;
+}
 unsigned long long b200_launch_count(void) { return g_launches; }
 void b200_prof_enable(int on) { g_prof_on = on != 0; }
 /* synchronises the device, writes "tag ms count\n" lines (sorted by time) and clears the records */
@@ -227,6 +236,24 @@ int b200_prof_report(char* buf, int cap) {
   }
   if (cap > 0) buf[off < cap ? off : cap - 1] = 0;
   return 0;
+}
+
+/* x: bf16 channels-last [N,D,H,W,in_pitch] window (in_coff, Ci); w: fp32 [Co][Ci][ks^3]; out bf16 [N,D,H,W,out_pitch];
+ * dgrad!=0 runs the transposed/flipped packing (input has Co channels, output Ci); stats: double[N*Cout*2] or null;
+ * scratch: 2*Co*Ci*ks^3 bf16 */
+int b200_test_tc_conv(const void* x, int in_pitch, int in_coff, int Ci, int N, int D, int H, int W, const float* w, int Co, int ks,
+                      void* out, int out_pitch, int out_coff, int accumulate, int dgrad, double* stats, void* scratch, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  int taps = ks * ks * ks;
+  bf16* wf = (bf16*)scratch; bf16* wd = wf + (size_t)Co * Ci * taps;
+  pack_conv_weights_kernel<<<64, 256, 0, st>>>(w, wf, wd, Co, Ci, taps);
+  B200_LAUNCH_CHECK();
+  if (!dgrad) {
+    B200_CHECK(tc::conv_supported(Ci, Co, in_pitch, in_coff, out_pitch, out_coff), "shape unsupported by the tcgen05 conv");
+    return tc::conv((const bf16*)x, in_pitch, in_coff, Ci, N, D, H, W, wf, Co, ks, (bf16*)out, out_pitch, out_coff, accumulate, stats, st);
+  }
+  B200_CHECK(tc::conv_supported(Co, Ci, in_pitch, in_coff, out_pitch, out_coff), "shape unsupported by the tcgen05 conv");
+  return tc::conv((const bf16*)x, in_pitch, in_coff, Co, N, D, H, W, wd, Ci, ks, (bf16*)out, out_pitch, out_coff, accumulate, stats, st);
 }
 
 int b200_test_tc_gemm(const void* a, const void* b, float* out, int M, int N, int K, int a_mn, int b_mn, void* stream) {

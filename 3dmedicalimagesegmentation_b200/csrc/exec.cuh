@@ -12,6 +12,7 @@
 
 #include "ops.cuh"
 #include "tc_gemm.cuh"
+#include "tc_conv.cuh"
 
 namespace b200 {
 
@@ -63,6 +64,7 @@ struct Workspace {
   double* stat_acc;
   // bf16 mode only: packed bf16 copies of the GEMM weights (refreshed every forward), same layouts as the fp32 masters
   bf16 *wqkv[12], *wproj[12], *wfc1[12], *wfc2[12], *wT[10];
+  bf16 *wcf[15], *wcd[15];  // conv weights packed [tap][co][ci] (forward) and [tap'][ci][co] (dgrad, taps flipped)
   // backward scratch
   float *dx, *dx2, *dhs[3], *dP;
   T *dxb, *dx2b;  // bf16 mode: operand copies of the fp32 residual-stream gradients
@@ -86,6 +88,19 @@ struct Exec {
                             {P_E3_T1, 4 * fs, 4 * fs}, {P_E4_T0, Hh, 8 * fs}, {P_D5_T, Hh, 8 * fs}, {P_D4_T, 8 * fs, 4 * fs},
                             {P_D3_T, 4 * fs, 2 * fs}, {P_D2_T, 2 * fs, fs}};
     pidx = tab[i][0]; Ci = tab[i][1]; Co = tab[i][2];
+  }
+  // the 15 convolutions in table order: (param index, Ci, Co, kernel)
+  void conv_desc(int i, int& pidx, int& Ci, int& Co, int& ks) const {
+    const int fs = c.fs;
+    const int base[5] = {P_E1_C1, P_D5_C1, P_D4_C1, P_D3_C1, P_D2_C1};
+    const int cin[5] = {c.Cin, 16 * fs, 8 * fs, 4 * fs, 2 * fs}, cout[5] = {fs, 8 * fs, 4 * fs, 2 * fs, fs};
+    int blk = i / 3, which = i % 3;
+    pidx = base[blk] + which; Co = cout[blk]; Ci = which == 1 ? cout[blk] : cin[blk]; ks = which == 2 ? 1 : 3;
+  }
+  int conv_index(const float* W) const {
+    if (!cur_params) return -1;
+    for (int i = 0; i < 15; ++i) { int p, ci, co, ks; conv_desc(i, p, ci, co, ks); if (cur_params[p] == W) return i; }
+    return -1;
   }
   size_t convT_elems(int i) const { int p, ci, co; convT_desc(i, p, ci, co); return (size_t)ci * co * 8; }
   const bf16* convT_packed(const float* const* P, const float* W) const {
@@ -135,6 +150,7 @@ struct Exec {
         w.wfc1[i] = b.take<bf16>((size_t)F * H); w.wfc2[i] = b.take<bf16>((size_t)H * F);
       }
       for (int i = 0; i < 10; ++i) w.wT[i] = b.take<bf16>(convT_elems(i));
+      for (int i = 0; i < 15; ++i) { int p, ci, co, ks; conv_desc(i, p, ci, co, ks); size_t n = (size_t)ci * co * ks * ks * ks; w.wcf[i] = b.take<bf16>(n); w.wcd[i] = b.take<bf16>(n); }
     }
     if (with_backward) {
       w.dx = b.take<float>(MH); w.dx2 = b.take<float>(MH);
@@ -194,13 +210,25 @@ struct Exec {
       jobs.count = n;
       multi_cast_kernel<<<dim3(64, n), 256, 0, st>>>(jobs);
       B200_LAUNCH_CHECK();
+      for (int i = 0; i < 15; ++i) {
+        int p, ci, co, ks; conv_desc(i, p, ci, co, ks);
+        if (ci % 16 || co % 16) continue;   // those layers stay on the CUDA-core engine
+        long tot = (long)ci * co * ks * ks * ks;
+        pack_conv_weights_kernel<<<(unsigned)min(64L, (tot + 255) / 256), 256, 0, st>>>(P[p], w.wcf[i], w.wcd[i], co, ci, ks * ks * ks);
+        B200_LAUNCH_CHECK();
+      }
     }
     return 0;
   }
 
   // ------------------------------------------------------------ InstanceNorm helpers
-  int in_stats(Cl<const T> x, long Vs, float* mr, cudaStream_t st) {
+  int in_stats(Cl<const T> x, long Vs, float* mr, cudaStream_t st, bool have_sums = false) {
     B200_PROF("instnorm_stats", st);
+    if (have_sums) {  // sums already accumulated by the conv epilogue
+      in_finalize_kernel<<<cdiv(c.B * x.C, 128), 128, 0, st>>>(w.stat_acc, mr, c.B * x.C, 1.0 / (double)Vs);
+      B200_LAUNCH_CHECK();
+      return 0;
+    }
     constexpr int VN = Vec16<T>::N;
     B200_CHECK(x.C % VN == 0 && 256 % (x.C / VN) == 0 && x.pitch % VN == 0 && x.coff % VN == 0,
                "InstanceNorm channel count %d unsupported (need a power of two >= 8)", x.C);
@@ -223,20 +251,42 @@ struct Exec {
 
   // ------------------------------------------------------------ residual conv block (UnetResBlock, Appendix B.2)
   // conv ops are virtual-ish hooks so the tcgen05 engine can replace them
-  int conv_fwd(Cl<const T> x, Sp s, const float* W, int Co, int ks, Cl<T> out, cudaStream_t st) { return simt_conv_fwd<T>(x, s, W, Co, ks, out, st); }
-  int conv_dgrad(Cl<const T> dy, Sp s, const float* W, int Ci, int ks, Cl<T> dx, int acc, cudaStream_t st) { return simt_conv_dgrad<T>(dy, s, W, Ci, ks, dx, acc, st); }
+  // stats != null asks for the InstanceNorm sums of the output; *stats_done tells whether the conv epilogue produced them
+  int conv_fwd(Cl<const T> x, Sp s, const float* W, int Co, int ks, Cl<T> out, double* stats, bool* stats_done, cudaStream_t st) {
+    if (stats_done) *stats_done = false;
+    if constexpr (kTC) {
+      int ci = conv_index(W);
+      if (ci >= 0 && tc::conv_supported(x.C, Co, x.pitch, x.coff, out.pitch, out.coff)) {
+        B200_PROF("conv_fwd", st);
+        if (stats) { B200_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * c.B * Co, st)); if (stats_done) *stats_done = true; }
+        return tc::conv(x.p, x.pitch, x.coff, x.C, s.N, s.D, s.H, s.W, w.wcf[ci], Co, ks, out.p, out.pitch, out.coff, 0, stats, st);
+      }
+    }
+    return simt_conv_fwd<T>(x, s, W, Co, ks, out, st);
+  }
+  int conv_dgrad(Cl<const T> dy, Sp s, const float* W, int Ci, int ks, Cl<T> dx, int acc, cudaStream_t st) {
+    if constexpr (kTC) {
+      int ci = conv_index(W);
+      if (ci >= 0 && tc::conv_supported(dy.C, Ci, dy.pitch, dy.coff, dx.pitch, dx.coff)) {
+        B200_PROF("conv_dgrad", st);
+        return tc::conv(dy.p, dy.pitch, dy.coff, dy.C, s.N, s.D, s.H, s.W, w.wcd[ci], Ci, ks, dx.p, dx.pitch, dx.coff, acc, nullptr, st);
+      }
+    }
+    return simt_conv_dgrad<T>(dy, s, W, Ci, ks, dx, acc, st);
+  }
   int conv_wgrad(Cl<const T> x, Cl<const T> dy, Sp s, int ks, float* dW, cudaStream_t st) { return simt_conv_wgrad<T>(x, dy, s, ks, dW, st); }
 
   int res_fwd(Cl<const T> x, int level, const float* W1, const float* W2, const float* W3, ResSave<T>& r, Cl<T> out, cudaStream_t st) {
     Sp s = sp(level); long Vs = V[level]; int Co = out.C;
     Cl<T> c1 = cl(w.c1tmp, Co, 0, Co), a1 = cl(r.a1, Co, 0, Co), c2 = cl(r.c2, Co, 0, Co), c3 = cl(r.c3, Co, 0, Co);
-    B200_TRY(conv_fwd(x, s, W1, Co, 3, c1, st));
-    B200_TRY(in_stats(cl<const T>(c1.p, Co, 0, Co), Vs, r.mr1, st));
+    bool done = false;
+    B200_TRY(conv_fwd(x, s, W1, Co, 3, c1, w.stat_acc, &done, st));
+    B200_TRY(in_stats(cl<const T>(c1.p, Co, 0, Co), Vs, r.mr1, st, done));
     B200_TRY(in_apply(cl<const T>(c1.p, Co, 0, Co), r.mr1, nullptr, nullptr, a1, Vs, st));
-    B200_TRY(conv_fwd(cl<const T>(a1.p, Co, 0, Co), s, W2, Co, 3, c2, st));
-    B200_TRY(in_stats(cl<const T>(c2.p, Co, 0, Co), Vs, r.mr2, st));
-    B200_TRY(conv_fwd(x, s, W3, Co, 1, c3, st));
-    B200_TRY(in_stats(cl<const T>(c3.p, Co, 0, Co), Vs, r.mr3, st));
+    B200_TRY(conv_fwd(cl<const T>(a1.p, Co, 0, Co), s, W2, Co, 3, c2, w.stat_acc, &done, st));
+    B200_TRY(in_stats(cl<const T>(c2.p, Co, 0, Co), Vs, r.mr2, st, done));
+    B200_TRY(conv_fwd(x, s, W3, Co, 1, c3, w.stat_acc, &done, st));
+    B200_TRY(in_stats(cl<const T>(c3.p, Co, 0, Co), Vs, r.mr3, st, done));
     B200_TRY(in_apply(cl<const T>(c2.p, Co, 0, Co), r.mr2, c3.p, r.mr3, out, Vs, st));
     return 0;
   }
@@ -402,6 +452,7 @@ struct Exec {
   int backward(const float* const* P, float* const* G, const float* x_in, char* ws, const float* d_enc4, const float* d_logits,
                int flags, cudaStream_t st) {
     layout(ws, true);
+    cur_params = P;
     int B = c.B, fs = c.fs;
     bool dec = (flags & FLAG_HAS_DLOGITS) && d_logits;
     bool enc = (flags & FLAG_NEED_ENCODER_GRAD) != 0;
@@ -440,6 +491,7 @@ struct Exec {
         B200_TRY(convT_bwd(w.e2a, 2 * fs, 2 * fs, 3, P[P_E2_T1], cl<const T>(w.dc2, 2 * fs, 0, 2 * fs), G[P_E2_T1], w.dc3, 2 * fs, 0, st));
         B200_TRY(convT_bwd(w.hsT[0], H, H, 4, P[P_E2_T0], cl<const T>(w.dc3, 2 * fs, 0, 2 * fs), G[P_E2_T0], w.dhs[0], H, 0, st));
       }
+      if (flags & 16) return 0;  // debug: stop right after the decoder3 block (b200_unetr_peek then reads its scratch)
       B200_TRY(convT_bwd(w.d2, 4 * fs, 4 * fs, 2, P[P_D3_T], cl<const T>(w.dcat, 4 * fs, 0, 2 * fs), G[P_D3_T], w.gA, 4 * fs, 0, st));
       // decoder4
       B200_TRY(res_bwd(cl<const T>(w.cat4, 8 * fs, 0, 8 * fs), 2, P[P_D4_C1], P[P_D4_C2], P[P_D4_C3], w.rs[2], cl<const T>(w.d2, 4 * fs, 0, 4 * fs),
@@ -511,6 +563,20 @@ struct Exec {
     if (G[P_PATCH_B]) B200_TRY(launch_colsum<float>(w.dx, G[P_PATCH_B], M, H, st));
     if (G[P_POS]) { batchsum_kernel<<<cdiv((long)L * H, 256), 256, 0, st>>>(w.dx, G[P_POS], B, (long)L * H); B200_LAUNCH_CHECK(); }
     return 0;
+  }
+
+  // debug: device pointer + element count of a named workspace buffer (valid after forward/backward laid it out)
+  const void* peek(const char* name, size_t* bytes) const {
+    struct { const char* n; const void* p; size_t b; } tab[] = {
+      {"dc1", w.dc1, sizeof(T) * c.B * V[0] * c.fs}, {"da1", w.da1, sizeof(T) * c.B * V[0] * c.fs},
+      {"dc2", w.dc2, sizeof(T) * c.B * V[0] * c.fs}, {"dc3", w.dc3, sizeof(T) * c.B * V[0] * c.fs},
+      {"gA", w.gA, sizeof(T) * c.B * V[0] * c.fs}, {"dcat", w.dcat, sizeof(T) * c.B * V[0] * 2 * c.fs},
+      {"a1_dec3", w.rs[3].a1, sizeof(T) * c.B * V[1] * 2 * c.fs}, {"c2_dec3", w.rs[3].c2, sizeof(T) * c.B * V[1] * 2 * c.fs},
+      {"mr1_dec3", w.rs[3].mr1, sizeof(float) * 2 * c.B * 2 * c.fs}, {"cat3", w.cat3, sizeof(T) * c.B * V[1] * 4 * c.fs},
+      {"bwd_acc", w.bwd_acc, sizeof(double) * 3 * c.B * 8 * c.fs}, {"d1", w.d1, sizeof(T) * c.B * V[1] * 2 * c.fs},
+    };
+    for (auto& e : tab) if (!strcmp(e.n, name)) { *bytes = e.b; return e.p; }
+    return nullptr;
   }
 
   // transposed conv backward: dW (if non-null) and d(input) (if dx non-null) written as type TO rows [rows_in, Ci]

@@ -1,0 +1,258 @@
+// tcgen05 implicit-GEMM 3-D convolution (k in {1,3}, stride 1, "same" zero padding, bias-free) on channels-last bf16.
+//
+//   out[v, co] = sum_{tap, ci} x[v + tap - pad, ci] * Wp[tap][co][ci]
+//
+// GEMM view: M = 128 voxels (a 4x4x8 brick of the volume), N = Co, K = taps * Ci.  No im2col buffer exists anywhere:
+// for every tap the TMA engine fetches the brick shifted by (kd-1,kh-1,kw-1) straight from the 5-D tensor
+// (C, W, H, D, N) into a K-major swizzled smem tile; out-of-volume voxels are zero-filled by TMA, which *is* the
+// padding.  The same kernel computes dgrad (input = dy, weights packed flipped/transposed by pack_conv_weights).
+// Warp roles as in tc_gemm.cuh.  Epilogue: TMEM -> registers -> bf16 channels-last rows (16-byte stores), optionally
+// accumulating into the destination (dx = dgrad3x3 + dgrad1x1) and emitting per-(n,c) sum / sum-of-squares of the
+// fp32 accumulators for the InstanceNorm that follows (K10 -> K12 fusion of SURVEY 2.1).
+#pragma once
+#include "tc_gemm.cuh"
+
+namespace b200 {
+namespace tc {
+
+static constexpr int TD = 4, TH = 4, TW = 8;  // voxel brick = 128 GEMM rows (w fastest: matches the TMA box order)
+
+struct ConvParams {
+  int N, D, H, W, Ci, Co, ks;
+  int kc, row_bytes;          // channels per k-block and its smem row size (32/64/128 B -> swizzle mode)
+  int nchunk, kblocks;        // Ci/kc ; taps*nchunk
+  int group;                  // k-blocks per pipeline stage
+  int tiles_w, tiles_h, tiles_d; long total_tiles;
+  int a_bytes, b_bytes;       // per k-block, b rounded up to 1024
+  int stages; uint32_t tmem_cols;
+  // epilogue
+  bf16* out; int pitch, coff, accumulate; double* stats;
+};
+
+__device__ __forceinline__ uint64_t smem_desc_k(uint32_t addr, int row_bytes) {
+  // K-major canonical layout, 8-row groups `8*row_bytes` apart; layout_type: 128B=2, 64B=4, 32B=6
+  uint64_t lt = row_bytes == 128 ? 2 : (row_bytes == 64 ? 4 : 6);
+  uint64_t d = (uint64_t)((addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(((uint32_t)(8 * row_bytes) >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= lt << 61;
+  return d;
+}
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+
+__global__ void __launch_bounds__(192, 1)
+conv_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const ConvParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const uint32_t kb_bytes = p.a_bytes + p.b_bytes, stage_bytes = kb_bytes * p.group;
+  uint64_t* full = (uint64_t*)(smem + (size_t)p.stages * stage_bytes);
+  uint64_t* empty = full + p.stages;
+  uint64_t* tfull = empty + p.stages;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
+  float* red = (float*)(tmem_slot + 4);  // [4 warps][2*Co] partial statistics
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nstage_per_tile = (p.kblocks + p.group - 1) / p.group;
+  const int pad = p.ks >> 1;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull + s, 1); mbar_init(tempty + s, 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(p.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        int tw = (int)(t % p.tiles_w); long r = t / p.tiles_w; int th = (int)(r % p.tiles_h); r /= p.tiles_h;
+        int td = (int)(r % p.tiles_d); int n = (int)(r / p.tiles_d);
+        for (int s = 0; s < nstage_per_tile; ++s) {
+          int kb0 = s * p.group, cnt = min(p.group, p.kblocks - kb0);
+          mbar_wait(empty + stage, phase ^ 1);
+          mbar_expect_tx(full + stage, (uint32_t)cnt * kb_bytes);
+          uint32_t base = smem_u32(smem + (size_t)stage * stage_bytes);
+          for (int i = 0; i < cnt; ++i) {
+            int kb = kb0 + i, tap = kb / p.nchunk, ch = kb - tap * p.nchunk;
+            int kw = tap % p.ks, kh = (tap / p.ks) % p.ks, kd = tap / (p.ks * p.ks);
+            uint32_t sa = base + i * kb_bytes, sb = sa + p.a_bytes;
+            tma_load_5d(sa, &map_x, full + stage, ch * p.kc, tw * TW + kw - pad, th * TH + kh - pad, td * TD + kd - pad, n);
+            tma_load_2d(sb, &map_w, full + stage, ch * p.kc, tap * p.Co);
+          }
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.Co >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
+    const int ksteps = p.kc / 16;
+    for (long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      mbar_wait(tempty + acc, acc_phase ^ 1);
+      tc_fence_after();
+      uint32_t tmem_d = tmem_base + (uint32_t)(acc * p.Co);
+      for (int s = 0; s < nstage_per_tile; ++s) {
+        int kb0 = s * p.group, cnt = min(p.group, p.kblocks - kb0);
+        mbar_wait(full + stage, phase);
+        tc_fence_after();
+        if (lane == 0) {
+          uint32_t base = smem_u32(smem + (size_t)stage * stage_bytes);
+          for (int i = 0; i < cnt; ++i) {
+            uint32_t sa = base + i * kb_bytes, sb = sa + p.a_bytes;
+            for (int k = 0; k < ksteps; ++k)
+              umma_f16(tmem_d, smem_desc_k(sa + k * 32, p.row_bytes), smem_desc_k(sb + k * 32, p.row_bytes), idesc, (s | i | k) ? 1u : 0u);
+          }
+          umma_commit(empty + stage);
+          if (s == nstage_per_tile - 1) umma_commit(tfull + acc);
+        }
+        __syncwarp();
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else {
+    const int q = warp & 3, ew = warp - 2;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      int tw = (int)(t % p.tiles_w); long r = t / p.tiles_w; int th = (int)(r % p.tiles_h); r /= p.tiles_h;
+      int td = (int)(r % p.tiles_d); int n = (int)(r / p.tiles_d);
+      const int row = q * 32 + lane;
+      const int w = tw * TW + (row & 7), h = th * TH + ((row >> 3) & 3), d = td * TD + (row >> 5);
+      const bool valid = (w < p.W) && (h < p.H) && (d < p.D);
+      bf16* dst = p.out + ((((long)n * p.D + d) * p.H + h) * p.W + w) * p.pitch + p.coff;
+      mbar_wait(tfull + acc, acc_phase);
+      tc_fence_after();
+      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.Co);
+      for (int c0 = 0; c0 < p.Co; c0 += 16) {
+        float v[16];
+        tmem_ld16(trow + c0, v);
+        if (p.stats) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float x = valid ? v[j] : 0.f;
+            float s1 = warp_sum(x), s2 = warp_sum(x * x);
+            if (lane == 0) { red[ew * 2 * p.Co + c0 + j] = s1; red[ew * 2 * p.Co + p.Co + c0 + j] = s2; }
+          }
+        }
+        if (valid) {
+          if (p.accumulate) {
+            Vec16<bf16> a, b; a.load(dst + c0); b.load(dst + c0 + 8);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { v[j] += a.v[j]; v[8 + j] += b.v[j]; }
+          }
+          Vec16<bf16> o0, o1;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { o0.v[j] = v[j]; o1.v[j] = v[8 + j]; }
+          o0.store(dst + c0); o1.store(dst + c0 + 8);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty + acc);
+      if (p.stats) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        int e = (warp - 2) * 32 + lane;  // 0..127
+        for (int i = e; i < 2 * p.Co; i += 128) {
+          float tot = red[i] + red[2 * p.Co + i] + red[4 * p.Co + i] + red[6 * p.Co + i];
+          int c = i % p.Co, which = i / p.Co;
+          atomicAdd(p.stats + ((long)n * p.Co + c) * 2 + which, (double)tot);
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+  }
+}
+
+static inline bool conv_supported(int Ci, int Co, int in_pitch, int in_coff, int out_pitch, int out_coff) {
+  return Ci % 16 == 0 && Co % 16 == 0 && Co <= 256 && in_pitch % 8 == 0 && in_coff % 8 == 0 && out_pitch % 8 == 0 && out_coff % 8 == 0;
+}
+
+// x: channels-last window (p + coff, pitch) with Ci channels; wp: packed bf16 [taps][Co][Ci]
+static int conv(const bf16* x, int in_pitch, int in_coff, int Ci, int N, int D, int H, int W, const bf16* wp, int Co, int ks,
+                bf16* out, int out_pitch, int out_coff, int accumulate, double* stats, cudaStream_t st) {
+  EncodeTiledFn enc = get_encode();
+  B200_CHECK(enc, "cuTensorMapEncodeTiled not available from the driver");
+  ConvParams p;
+  p.N = N; p.D = D; p.H = H; p.W = W; p.Ci = Ci; p.Co = Co; p.ks = ks;
+  p.kc = Ci % 64 == 0 ? 64 : (Ci % 32 == 0 ? 32 : 16);
+  p.row_bytes = p.kc * 2;
+  p.nchunk = Ci / p.kc; p.kblocks = ks * ks * ks * p.nchunk;
+  p.a_bytes = 128 * p.row_bytes; p.b_bytes = ((Co * p.row_bytes + 1023) / 1024) * 1024;
+  int kb_bytes = p.a_bytes + p.b_bytes;
+  p.group = 32 * 1024 / kb_bytes; if (p.group < 1) p.group = 1; if (p.group > 9) p.group = 9; if (p.group > p.kblocks) p.group = p.kblocks;
+  p.stages = (int)((196 * 1024) / (kb_bytes * p.group)); if (p.stages > 8) p.stages = 8; if (p.stages < 2) p.stages = 2;
+  p.tiles_w = cdiv(W, TW); p.tiles_h = cdiv(H, TH); p.tiles_d = cdiv(D, TD);
+  p.total_tiles = (long)N * p.tiles_d * p.tiles_h * p.tiles_w;
+  uint32_t cols = 2 * Co, pw = 32; while (pw < cols) pw <<= 1; p.tmem_cols = pw;
+  p.out = out; p.pitch = out_pitch; p.coff = out_coff; p.accumulate = accumulate; p.stats = stats;
+
+  CUtensorMapSwizzle sw = p.row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (p.row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  CUtensorMap mx, mw;
+  {
+    cuuint64_t dims[5] = {(cuuint64_t)Ci, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
+    cuuint64_t strides[4] = {(cuuint64_t)in_pitch * 2, (cuuint64_t)W * in_pitch * 2, (cuuint64_t)H * W * in_pitch * 2, (cuuint64_t)D * H * W * in_pitch * 2};
+    cuuint32_t box[5] = {(cuuint32_t)p.kc, TW, TH, TD, 1};
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(&mx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (void*)(x + in_coff), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    B200_CHECK(r == CUDA_SUCCESS, "conv input tensor map failed (%d): C=%d pitch=%d dims %dx%dx%d", (int)r, Ci, in_pitch, D, H, W);
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)Ci, (cuuint64_t)ks * ks * ks * Co};
+    cuuint64_t strides[1] = {(cuuint64_t)Ci * 2};
+    cuuint32_t box[2] = {(cuuint32_t)p.kc, (cuuint32_t)Co};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(&mw, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)wp, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    B200_CHECK(r == CUDA_SUCCESS, "conv weight tensor map failed (%d)", (int)r);
+  }
+  size_t smem = (size_t)p.stages * kb_bytes * p.group + 1024 + 256 + 8 * Co * sizeof(float) + 64;
+  B200_CHECK(smem <= 227 * 1024, "conv smem budget exceeded (%zu)", smem);
+  static bool attr_done = false;
+  if (!attr_done) { B200_CUDA(cudaFuncSetAttribute(conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr_done = true; }
+  int grid = (int)(p.total_tiles < num_sms() ? p.total_tiles : num_sms());
+  conv_kernel<<<grid, 192, smem, st>>>(mx, mw, p);
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace tc
+
+// W fp32 [Co][Ci][taps] -> fwd[tap][co][ci] and dgr[taps-1-tap][ci][co] (bf16)
+__global__ void pack_conv_weights_kernel(const float* __restrict__ W, bf16* __restrict__ fwd, bf16* __restrict__ dgr, int Co, int Ci, int taps) {
+  long total = (long)Co * Ci * taps;
+  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+    int tap = (int)(e % taps); long r = e / taps; int ci = (int)(r % Ci); int co = (int)(r / Ci);
+    bf16 v = __float2bfloat16_rn(W[e]);
+    fwd[((long)tap * Co + co) * Ci + ci] = v;
+    dgr[((long)(taps - 1 - tap) * Ci + ci) * Co + co] = v;
+  }
+}
+
+}  // namespace b200

@@ -84,6 +84,9 @@ int b200_sw_accumulate(float* acc, const float* pred, const b200_sw_geom* g, con
 int b200_sw_finalize(const float* acc, float* out, uint8_t* mask, const b200_sw_geom* g, int batch, const int32_t* s0,
                      int n0, const int32_t* s1, int n1, const int32_t* s2, int n2, void* stream);
 
+/* debug: copy a named workspace buffer of the last forward/backward (device to device, synchronous) */
+int b200_unetr_peek(void* handle, const char* name, void* dst, size_t cap);
+
 /* ---- instrumentation: kernels launched so far; per-op CUDA-event timing (tags = layer types) ---- */
 unsigned long long b200_launch_count(void);
 void b200_prof_enable(int on);
@@ -92,6 +95,9 @@ int b200_prof_report(char* buf, int cap);
 /* ---- op-level test hooks (parity tests of single kernels; not part of the reference surface) ---- */
 /* D[M,N] = A[M,K] * B[N,K]^T with bf16 operands on the tcgen05 engine; a_mn/b_mn select MN-major operands
  * (A stored [K,M] / B stored [K,N]).  out fp32. */
+/* tcgen05 implicit-GEMM conv3d (k=1|3, same padding) on channels-last bf16; see csrc/capi.cu for the argument layout */
+int b200_test_tc_conv(const void* x, int in_pitch, int in_coff, int Ci, int N, int D, int H, int W, const float* w, int Co, int ks,
+                      void* out, int out_pitch, int out_coff, int accumulate, int dgrad, double* stats, void* scratch, void* stream);
 int b200_test_tc_gemm(const void* a, const void* b, float* out, int M, int N, int K, int a_mn, int b_mn, void* stream);
 
 #ifdef __cplusplus

@@ -30,18 +30,25 @@ TINY = dict(in_channels=1, out_channels=5, img_size=(32, 32, 32), feature_size=8
             num_heads=4, pos_embed="perceptron", norm_name="instance", res_block=True)
 
 
+def l2err(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
 def grad_check(mine, ref, ref64, floor, cos_min=None):
-    """Gradients against the fp64 oracle; the fp32 CPU oracle's own distance to fp64 sets the scale of what fp32
-    arithmetic can deliver on this (ill-conditioned: InstanceNorm over few voxels) problem."""
+    """Gradients against the fp64 oracle in relative L2 norm.  (Max-norm is not meaningful here: a voxel whose
+    pre-activation sits within fp32 rounding of the LeakyReLU kink flips its slope 1 <-> 0.01 between any two fp32
+    implementations -- observed: 1 element of 65 536 -- and that single voxel dominates a max-norm.)  The fp32 CPU
+    oracle's own distance to fp64 sets the scale."""
     worst = ("", 0.0, 0.0)
     for (k, p), (_, q), (_, q64) in zip(mine.named_parameters(), ref.named_parameters(), ref64.named_parameters()):
         assert (p.grad is None) == (q.grad is None), k
         if q.grad is None:
             continue
-        e_mine, e_ref = relerr(p.grad, q64.grad), relerr(q.grad, q64.grad)
+        e_mine, e_ref = l2err(p.grad, q64.grad), l2err(q.grad, q64.grad)
         if cos_min is not None:
             assert cosine(p.grad, q64.grad) >= cos_min, (k, cosine(p.grad, q64.grad))
-        if e_mine - 8 * e_ref > worst[1] - 8 * worst[2]:
+        if e_mine > worst[1]:
             worst = (k, e_mine, e_ref)
         assert e_mine <= max(floor, 8 * e_ref), (k, e_mine, e_ref)
     return worst
@@ -65,7 +72,7 @@ def build_pair(pkg, mode, **kw):
 
 
 # ------------------------------------------------------------------------------------------- full network
-@pytest.mark.parametrize("mode,tol_logits,tol_grad,cos_min", [("fp32", 1e-4, 2e-3, 0.9999), ("bf16", 2e-2, 0.25, 0.97)])
+@pytest.mark.parametrize("mode,tol_logits,tol_grad,cos_min", [("fp32", 1e-4, 2e-3, 0.9999), ("bf16", 2e-2, 0.2, 0.97)])
 def test_tiny_unetr_forward_backward_matches_oracle(pkg, mode, tol_logits, tol_grad, cos_min):
     ref, mine = build_pair(pkg, mode)
     ref64 = to64(ref)

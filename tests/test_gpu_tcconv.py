@@ -1,0 +1,60 @@
+"""tcgen05 implicit-GEMM conv3d (forward and dgrad) against torch conv3d on the same bf16-rounded operands.
+Floating-point kernel: torch fp32 is the reference; tolerance 2^-8 relative (bf16 output rounding) of max|ref|."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def run_conv(pkg, x_cl, in_coff, Ci, w, Co, ks, out_cl, out_coff, accumulate, dgrad, stats):
+    lib = pkg._lib.load()
+    N, D, H, W, in_pitch = x_cl.shape
+    scratch = torch.empty(2 * w.numel(), dtype=torch.bfloat16, device=DEV)
+    pkg._lib.check(lib.b200_test_tc_conv(pkg._lib.ptr(x_cl), in_pitch, in_coff, Ci, N, D, H, W, pkg._lib.ptr(w), Co, ks,
+                                          pkg._lib.ptr(out_cl), out_cl.shape[-1], out_coff, accumulate, dgrad,
+                                          pkg._lib.ptr(stats), pkg._lib.ptr(scratch), pkg._lib.stream_ptr()), "tc_conv")
+    torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("Ci,Co", [(16, 16), (32, 16), (64, 32), (128, 64), (256, 128), (16, 32)])
+@pytest.mark.parametrize("ks", [3, 1])
+@pytest.mark.parametrize("dims", [(12, 12, 12), (8, 20, 24)])
+def test_conv_forward_with_stats(pkg, Ci, Co, ks, dims):
+    g = torch.Generator().manual_seed(Ci * 7 + Co + ks)
+    N = 2
+    x = torch.randn(N, Ci, *dims, generator=g).to(torch.bfloat16)
+    w = (torch.randn(Co, Ci, ks, ks, ks, generator=g) / (Ci * ks ** 3) ** 0.5)
+    want = F.conv3d(x.float(), w.to(torch.bfloat16).float(), padding=ks // 2)
+    pitch_in, coff_in = Ci + 16, 8          # exercise channel windows (concat buffers)
+    x_cl = torch.zeros(N, *dims, pitch_in, dtype=torch.bfloat16)
+    x_cl[..., coff_in:coff_in + Ci] = x.permute(0, 2, 3, 4, 1)
+    out = torch.full((N, *dims, Co + 8), 7.0, dtype=torch.bfloat16, device=DEV)
+    stats = torch.zeros(N, Co, 2, dtype=torch.float64, device=DEV)
+    run_conv(pkg, x_cl.to(DEV), coff_in, Ci, w.to(DEV), Co, ks, out, 8, 0, 0, stats)
+    got = out[..., 8:].float().permute(0, 4, 1, 2, 3).cpu()
+    err = ((got - want).abs().max() / want.abs().max()).item()
+    assert err <= 2 ** -7, err
+    assert (out[..., :8] == 7.0).all()      # untouched channels of the destination
+    s = stats.cpu()
+    assert torch.allclose(s[..., 0], want.double().sum((2, 3, 4)), rtol=1e-3, atol=1e-2 * want.abs().max().item())
+    assert torch.allclose(s[..., 1], want.double().square().sum((2, 3, 4)), rtol=1e-3)
+
+
+@pytest.mark.parametrize("Ci,Co", [(32, 16), (16, 16), (256, 128)])
+@pytest.mark.parametrize("ks", [3, 1])
+def test_conv_dgrad_and_accumulate(pkg, Ci, Co, ks):
+    g = torch.Generator().manual_seed(Ci + Co * 3 + ks)
+    dims = (8, 12, 16)
+    dy = torch.randn(1, Co, *dims, generator=g).to(torch.bfloat16)
+    w = torch.randn(Co, Ci, ks, ks, ks, generator=g) / (Co * ks ** 3) ** 0.5
+    want = F.conv_transpose3d(dy.float(), w.to(torch.bfloat16).float(), padding=ks // 2)
+    dy_cl = dy.permute(0, 2, 3, 4, 1).contiguous().to(DEV)
+    base = torch.randn(1, *dims, Ci, generator=g).to(torch.bfloat16)
+    out = base.clone().to(DEV)
+    run_conv(pkg, dy_cl, 0, Ci, w.to(DEV), Co, ks, out, 0, 1, 1, None)
+    got = out.float().permute(0, 4, 1, 2, 3).cpu()
+    want_acc = want + base.float().permute(0, 4, 1, 2, 3)
+    err = ((got - want_acc).abs().max() / want_acc.abs().max()).item()
+    assert err <= 2 ** -7, err
