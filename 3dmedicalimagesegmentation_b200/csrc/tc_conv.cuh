@@ -89,7 +89,7 @@ conv_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ C
         for (int s = 0; s < nstage_per_tile; ++s) {
           int kb0 = s * p.group, cnt = min(p.group, p.kblocks - kb0);
           mbar_wait(empty + stage, phase ^ 1);
-          mbar_expect_tx(full + stage, (uint32_t)cnt * kb_bytes);
+          mbar_expect_tx(full + stage, (uint32_t)cnt * (uint32_t)(p.a_bytes + p.Co * p.row_bytes));  // bytes TMA really delivers
           uint32_t base = smem_u32(smem + (size_t)stage * stage_bytes);
           for (int i = 0; i < cnt; ++i) {
             int kb = kb0 + i, tap = kb / p.nchunk, ch = kb - tap * p.nchunk;

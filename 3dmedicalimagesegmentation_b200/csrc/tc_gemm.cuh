@@ -21,7 +21,7 @@ namespace b200 {
 namespace tc {
 
 static constexpr int BM = 128, BK = 64;
-static constexpr uint32_t SPIN_LIMIT = 1u << 26;  // watchdog: trap instead of hanging the GPU on a protocol bug
+static constexpr long long WATCHDOG_CYCLES = 2000000000LL;  // ~1 s: trap instead of hanging the GPU on a protocol bug
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -34,11 +34,16 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t addr = smem_u32(bar), ok = 0, spins = 0;
+  uint32_t addr = smem_u32(bar), ok = 0;
+  long long t0 = 0;
   do {
     asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
                  : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
-    if (!ok && ++spins > SPIN_LIMIT) __trap();
+    if (!ok) {
+      long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > WATCHDOG_CYCLES) __trap();
+    }
   } while (!ok);
 }
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
