@@ -58,3 +58,26 @@ def test_conv_dgrad_and_accumulate(pkg, Ci, Co, ks):
     want_acc = want + base.float().permute(0, 4, 1, 2, 3)
     err = ((got - want_acc).abs().max() / want_acc.abs().max()).item()
     assert err <= 2 ** -7, err
+
+
+@pytest.mark.parametrize("Ci,Co", [(16, 16), (32, 16), (32, 32), (64, 32), (64, 64), (128, 64), (128, 128), (256, 128)])
+@pytest.mark.parametrize("ks", [3, 1])
+@pytest.mark.parametrize("dims", [(12, 12, 12), (8, 20, 24)])
+def test_conv_wgrad(pkg, Ci, Co, ks, dims):
+    """tcgen05 weight gradient (voxels as the reduction dim, MN-major operands) vs torch.nn.grad.conv3d_weight."""
+    lib = pkg._lib.load()
+    g = torch.Generator().manual_seed(Ci * 5 + Co + ks)
+    N = 2
+    x = torch.randn(N, Ci, *dims, generator=g).to(torch.bfloat16)
+    dy = torch.randn(N, Co, *dims, generator=g).to(torch.bfloat16)
+    want = torch.nn.grad.conv3d_weight(x.float(), (Co, Ci, ks, ks, ks), dy.float(), padding=ks // 2)
+    xp, xo, dp, do = Ci + 8, 8, Co + 16, 16
+    x_cl = torch.zeros(N, *dims, xp, dtype=torch.bfloat16); x_cl[..., xo:] = x.permute(0, 2, 3, 4, 1)
+    dy_cl = torch.zeros(N, *dims, dp, dtype=torch.bfloat16); dy_cl[..., do:] = dy.permute(0, 2, 3, 4, 1)
+    x_cl, dy_cl = x_cl.to(DEV), dy_cl.to(DEV)
+    dW = torch.full((Co, Ci, ks, ks, ks), float("nan"), device=DEV)
+    pkg._lib.check(lib.b200_test_tc_wgrad(pkg._lib.ptr(x_cl), xp, xo, Ci, pkg._lib.ptr(dy_cl), dp, do, Co, N, *dims, ks,
+                                           pkg._lib.ptr(dW), pkg._lib.stream_ptr()), "tc_wgrad")
+    torch.cuda.synchronize()
+    err = ((dW.cpu() - want).abs().max() / want.abs().max()).item()
+    assert err <= 1e-3, err
