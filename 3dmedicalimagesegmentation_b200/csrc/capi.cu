@@ -256,6 +256,15 @@ int b200_test_tc_conv(const void* x, int in_pitch, int in_coff, int Ci, int N, i
   return tc::conv((const bf16*)x, in_pitch, in_coff, Co, N, D, H, W, wd, Ci, ks, (bf16*)out, out_pitch, out_coff, accumulate, stats, st);
 }
 
+/* dW fp32 [Co][Ci][ks^3] = sum_v dy[v,co] x[v+tap,ci]; x, dy channels-last bf16 windows */
+int b200_test_tc_wgrad(const void* x, int x_pitch, int x_coff, int Ci, const void* dy, int dy_pitch, int dy_coff, int Co, int N, int D, int H,
+                       int W, int ks, float* dW, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  B200_CHECK(tc::wgrad_supported(Ci, Co, x_pitch, x_coff, dy_pitch, dy_coff), "shape unsupported by the tcgen05 wgrad");
+  B200_CUDA(cudaMemsetAsync(dW, 0, sizeof(float) * Co * Ci * ks * ks * ks, st));
+  return tc::conv_wgrad((const bf16*)x, x_pitch, x_coff, Ci, (const bf16*)dy, dy_pitch, dy_coff, Co, N, D, H, W, ks, dW, st);
+}
+
 int b200_test_tc_gemm(const void* a, const void* b, float* out, int M, int N, int K, int a_mn, int b_mn, void* stream) {
   return tc_gemm_test((const bf16*)a, (const bf16*)b, out, M, N, K, a_mn, b_mn, (cudaStream_t)stream);
 }

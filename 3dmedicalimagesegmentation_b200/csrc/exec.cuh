@@ -13,6 +13,7 @@
 #include "ops.cuh"
 #include "tc_gemm.cuh"
 #include "tc_conv.cuh"
+#include "tc_wgrad.cuh"
 
 namespace b200 {
 
@@ -274,7 +275,15 @@ struct Exec {
     }
     return simt_conv_dgrad<T>(dy, s, W, Ci, ks, dx, acc, st);
   }
-  int conv_wgrad(Cl<const T> x, Cl<const T> dy, Sp s, int ks, float* dW, cudaStream_t st) { return simt_conv_wgrad<T>(x, dy, s, ks, dW, st); }
+  int conv_wgrad(Cl<const T> x, Cl<const T> dy, Sp s, int ks, float* dW, cudaStream_t st) {
+    if constexpr (kTC) {
+      if (tc::wgrad_supported(x.C, dy.C, x.pitch, x.coff, dy.pitch, dy.coff)) {
+        B200_PROF("conv_wgrad", st);
+        return tc::conv_wgrad(x.p, x.pitch, x.coff, x.C, dy.p, dy.pitch, dy.coff, dy.C, s.N, s.D, s.H, s.W, ks, dW, st);
+      }
+    }
+    return simt_conv_wgrad<T>(x, dy, s, ks, dW, st);
+  }
 
   int res_fwd(Cl<const T> x, int level, const float* W1, const float* W2, const float* W3, ResSave<T>& r, Cl<T> out, cudaStream_t st) {
     Sp s = sp(level); long Vs = V[level]; int Co = out.C;

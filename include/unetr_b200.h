@@ -98,6 +98,8 @@ int b200_prof_report(char* buf, int cap);
 /* tcgen05 implicit-GEMM conv3d (k=1|3, same padding) on channels-last bf16; see csrc/capi.cu for the argument layout */
 int b200_test_tc_conv(const void* x, int in_pitch, int in_coff, int Ci, int N, int D, int H, int W, const float* w, int Co, int ks,
                       void* out, int out_pitch, int out_coff, int accumulate, int dgrad, double* stats, void* scratch, void* stream);
+int b200_test_tc_wgrad(const void* x, int x_pitch, int x_coff, int Ci, const void* dy, int dy_pitch, int dy_coff, int Co, int N, int D, int H,
+                       int W, int ks, float* dW, void* stream);
 int b200_test_tc_gemm(const void* a, const void* b, float* out, int M, int N, int K, int a_mn, int b_mn, void* stream);
 
 #ifdef __cplusplus
