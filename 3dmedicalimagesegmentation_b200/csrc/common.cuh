@@ -54,6 +54,11 @@ struct ProfScope {
   ~ProfScope() { if (active) prof_end(st); }
 };
 #define B200_PROF(tag, st) b200::ProfScope _prof_scope(tag, st)
+// detailed variant: printf-style tag, formatted only when profiling is on
+#define B200_PROFD(st, ...)                                   \
+  char _prof_tag[96];                                         \
+  if (b200::g_prof_on) snprintf(_prof_tag, sizeof(_prof_tag), __VA_ARGS__); \
+  b200::ProfScope _prof_scope(_prof_tag, st)
 
 // ---- scalar conversions ----
 __device__ __forceinline__ float to_f(float v) { return v; }

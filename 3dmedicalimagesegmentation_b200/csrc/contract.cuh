@@ -131,6 +131,14 @@ struct EpAtomic {  // split-K weight gradients
   __device__ __forceinline__ void operator()(int, int m, int n, float acc) const { atomicAdd(out + (long)m * ld + n, acc); }
 };
 
+struct EpAtomicTapRemap {  // GEMM column n = tap*Co+co -> PyTorch ConvTranspose3d weight column co*8+tap, atomic (split-K)
+  float* out; int Co;
+  __device__ __forceinline__ void operator()(int, int m, int n, float acc) const {
+    int tap = n / Co, co = n - tap * Co;
+    atomicAdd(out + (long)m * Co * 8 + co * 8 + tap, acc);
+  }
+};
+
 template <class TO>
 struct EpConvTScatter {  // m = input voxel, n = co*8+tap -> channels-last 2x up-sampled output
   TO* out; int D, H, W, pitch, coff;

@@ -6,6 +6,8 @@
 
 namespace b200 {
 
+struct ClView { long pitch; int coff; };  // element strides of a channels-last window
+
 // ------------------------------------------------------------------ layout / casts
 // dir 0: NCDHW fp32 -> channels-last T (dst[(n*V+v)*pitch+coff+c]); accumulate adds into dst.
 // dir 1: channels-last T -> NCDHW fp32.
@@ -48,6 +50,7 @@ __global__ void layout_kernel(const float* __restrict__ ncdhw_in, float* __restr
 template <class T>
 static int launch_layout(const float* in, float* out, T* cl, int N, int C, long V, int pitch, int coff, int dir,
                          int accumulate, cudaStream_t st) {
+  B200_PROF("layout", st);
   long blocks = (long)N * ((V + 31) / 32) * ((C + 31) / 32);
   layout_kernel<T><<<(unsigned)blocks, dim3(32, 8), 0, st>>>(in, out, cl, C, V, pitch, coff, dir, accumulate, 0);
   B200_LAUNCH_CHECK();
@@ -62,6 +65,7 @@ __global__ void cast_kernel(const TI* __restrict__ in, TO* __restrict__ out, lon
 }
 template <class TI, class TO>
 static int launch_cast(const TI* in, TO* out, long n, cudaStream_t st) {
+  B200_PROF("cast", st);
   int blocks = (int)min((long)148 * 8, (n + 255) / 256);
   cast_kernel<TI, TO><<<blocks, 256, 0, st>>>(in, out, n);
   B200_LAUNCH_CHECK();
@@ -92,6 +96,7 @@ __global__ void add_kernel(float* __restrict__ dst, const float* __restrict__ sr
   for (; i < n; i += stride) dst[i] += src[i];
 }
 static int launch_add(float* dst, const float* src, long n, cudaStream_t st) {
+  B200_PROF("add", st);
   int blocks = (int)min((long)148 * 8, (n + 255) / 256);
   add_kernel<<<blocks, 256, 0, st>>>(dst, src, n);
   B200_LAUNCH_CHECK();
@@ -119,6 +124,7 @@ __global__ void layernorm_fwd_kernel(const float* __restrict__ x, const float* _
 template <class TO>
 static int launch_layernorm_fwd(const float* x, const float* g, const float* b, TO* y, float* stats, int M, int H,
                                 cudaStream_t st) {
+  B200_PROF("layernorm_fwd", st);
   layernorm_fwd_kernel<TO><<<cdiv(M, 8), 256, 0, st>>>(x, g, b, y, stats, M, H);
   B200_LAUNCH_CHECK();
   return 0;
@@ -158,7 +164,7 @@ __global__ void layernorm_bwd_params_kernel(const TG* __restrict__ g, const floa
   int col = blockIdx.x * 32 + threadIdx.x;
   float a = 0.f, b = 0.f;
   if (col < H)
-    for (int r = threadIdx.y; r < M; r += 8) {
+    for (int r = blockIdx.y * 8 + threadIdx.y; r < M; r += 8 * gridDim.y) {
       float gg = to_f(g[(long)r * H + col]);
       a += gg * (x[(long)r * H + col] - stats[2 * r]) * stats[2 * r + 1];
       b += gg;
@@ -167,17 +173,19 @@ __global__ void layernorm_bwd_params_kernel(const TG* __restrict__ g, const floa
   __syncthreads();
   if (threadIdx.y == 0 && col < H) {
     for (int i = 1; i < 8; ++i) { a += sg[i][threadIdx.x]; b += sb[i][threadIdx.x]; }
-    dgamma[col] = a; dbeta[col] = b;
+    atomicAdd(dgamma + col, a); atomicAdd(dbeta + col, b);   // outputs zeroed by the launcher
   }
 }
 template <class TG>
 static int launch_layernorm_bwd(const TG* g, const float* x, const float* stats, const float* gamma,
                                 const float* dx_res, float* dx_out, TG* dx_out_cast, float* dgamma, float* dbeta, int M, int H,
                                 cudaStream_t st) {
+  B200_PROF("layernorm_bwd", st);
   layernorm_bwd_dx_kernel<TG><<<cdiv(M, 8), 256, 0, st>>>(g, x, stats, gamma, dx_res, dx_out, dx_out_cast, M, H);
   B200_LAUNCH_CHECK();
   if (dgamma) {
-    layernorm_bwd_params_kernel<TG><<<cdiv(H, 32), dim3(32, 8), 0, st>>>(g, x, stats, dgamma, dbeta, M, H);
+    cudaMemsetAsync(dgamma, 0, sizeof(float) * H, st); cudaMemsetAsync(dbeta, 0, sizeof(float) * H, st);
+    layernorm_bwd_params_kernel<TG><<<dim3(cdiv(H, 32), 12), dim3(32, 8), 0, st>>>(g, x, stats, dgamma, dbeta, M, H);
     B200_LAUNCH_CHECK();
   }
   return 0;
@@ -190,17 +198,19 @@ __global__ void colsum_kernel(const TG* __restrict__ g, float* __restrict__ out,
   int col = blockIdx.x * 32 + threadIdx.x;
   float a = 0.f;
   if (col < N)
-    for (int r = threadIdx.y; r < M; r += 8) a += to_f(g[(long)r * N + col]);
+    for (int r = blockIdx.y * 8 + threadIdx.y; r < M; r += 8 * gridDim.y) a += to_f(g[(long)r * N + col]);
   s[threadIdx.y][threadIdx.x] = a;
   __syncthreads();
   if (threadIdx.y == 0 && col < N) {
     for (int i = 1; i < 8; ++i) a += s[i][threadIdx.x];
-    out[col] = a;
+    atomicAdd(out + col, a);   // out zeroed by the launcher
   }
 }
 template <class TG>
 static int launch_colsum(const TG* g, float* out, int M, int N, cudaStream_t st) {
-  colsum_kernel<TG><<<cdiv(N, 32), dim3(32, 8), 0, st>>>(g, out, M, N);
+  B200_PROF("colsum", st);
+  cudaMemsetAsync(out, 0, sizeof(float) * N, st);
+  colsum_kernel<TG><<<dim3(cdiv(N, 32), N >= 2048 ? 4 : 12), dim3(32, 8), 0, st>>>(g, out, M, N);
   B200_LAUNCH_CHECK();
   return 0;
 }
@@ -220,6 +230,42 @@ __global__ void rowsum_atomic_kernel(const float* __restrict__ x, float* __restr
     float t = 0.f;
     for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += s[i];
     atomicAdd(out + row % C, t);
+  }
+}
+
+// Pixel-unshuffle of the 2x up-sampled channels-last tensor y (window coff..coff+Co of pitch) into the GEMM operand
+// U[v_in][tap*Co + co]  (tap = (a*2+b)*2+c of the k2s2 transposed conv).  16-byte moves both ways.
+template <class T>
+__global__ void unshuffle_kernel(const T* __restrict__ y, ClView yv, int Co, int N, int D, int H, int W, T* __restrict__ U) {
+  constexpr int VN = Vec16<T>::N;
+  int lanes = Co / VN;
+  long total = (long)N * D * H * W * 8 * lanes;
+  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+    int lv = (int)(e % lanes); long r = e / lanes; int tap = (int)(r & 7); long v = r >> 3;
+    int w = (int)(v % W); long t = v / W; int h = (int)(t % H); t /= H; int d = (int)(t % D); long n = t / D;
+    long pos = ((n * 2 * D + 2 * d + (tap >> 2)) * 2 * H + 2 * h + ((tap >> 1) & 1)) * 2 * W + 2 * w + (tap & 1);
+    Vec16<T> a; a.load(y + pos * yv.pitch + yv.coff + lv * VN);
+    a.store(U + v * 8 * Co + tap * Co + lv * VN);
+  }
+}
+// fp32 [Ci][Co][8] -> bf16 [Ci][8][Co]  (tap-major copy of a transposed-conv weight)
+__global__ void pack_convT_tapmajor_kernel(const float* __restrict__ W, bf16* __restrict__ out, int Ci, int Co) {
+  long total = (long)Ci * Co * 8;
+  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+    int tap = (int)(e & 7); long r = e >> 3; int co = (int)(r % Co); long ci = r / Co;
+    out[(ci * 8 + tap) * Co + co] = __float2bfloat16_rn(W[e]);
+  }
+}
+// bf16 patch rows A[tok][k] from the NCDHW fp32 volume (same k order as the weight: perceptron or conv)
+__global__ void patch_gather_kernel(const float* __restrict__ x, bf16* __restrict__ A, int C, int S0, int S1, int S2, int g0, int g1, int g2,
+                                    int conv_order, long total) {
+  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+    int Kp = 4096 * C; int k = (int)(e % Kp); int tok = (int)(e / Kp);
+    int c, p;
+    if (conv_order) { c = k >> 12; p = k & 4095; } else { c = k % C; p = k / C; }
+    int p3 = p & 15, p2 = (p >> 4) & 15, p1 = p >> 8;
+    int d = tok % g2; int t = tok / g2; int w = t % g1; t /= g1; int h = t % g0; int b = t / g0;
+    A[e] = __float2bfloat16_rn(x[((((long)b * C + c) * S0 + h * 16 + p1) * S1 + w * 16 + p2) * S2 + d * 16 + p3]);
   }
 }
 
@@ -267,7 +313,6 @@ __global__ void softmax_bwd_kernel(const TP* __restrict__ P, const float* __rest
 // Tensors are channels-last [N, V, pitch] with channel window [coff, coff+C).  C % Vec16<T>::N == 0,
 // C/VecN a power of two <= 256.  Statistics: double sum/sumsq -> float (mean, rstd) per (n,c).
 
-struct ClView { long pitch; int coff; };  // element strides of a channels-last window
 
 template <class T>
 __global__ void in_stats_kernel(const T* __restrict__ x, ClView xv, int C, long V, double* __restrict__ acc) {

@@ -65,10 +65,11 @@ struct Workspace {
   double* stat_acc;
   // bf16 mode only: packed bf16 copies of the GEMM weights (refreshed every forward), same layouts as the fp32 masters
   bf16 *wqkv[12], *wproj[12], *wfc1[12], *wfc2[12], *wT[10];
-  bf16 *wcf[15], *wcd[15];  // conv weights packed [tap][co][ci] (forward) and [tap'][ci][co] (dgrad, taps flipped)
+  bf16 *wcf[15], *wcd[15];
+  bf16 *wTt[10], *wpatch, *apatch;  // tap-major transposed-conv weights; patch weight; gathered bf16 patch rows [M, 4096*Cin]  // conv weights packed [tap][co][ci] (forward) and [tap'][ci][co] (dgrad, taps flipped)
   // backward scratch
   float *dx, *dx2, *dhs[3], *dP;
-  T *dxb, *dx2b;  // bf16 mode: operand copies of the fp32 residual-stream gradients
+  T *dxb, *dx2b, *unsh;  // unsh: pixel-unshuffled dOut of a transposed conv [rows_in, 8*Co]  // bf16 mode: operand copies of the fp32 residual-stream gradients
   T *dvit, *dh, *dln, *datt, *dqkv, *dS, *gA, *dcat, *dc2, *dc3, *da1, *dc1;
   double* bwd_acc;
   size_t bytes;
@@ -104,8 +105,8 @@ struct Exec {
     return -1;
   }
   size_t convT_elems(int i) const { int p, ci, co; convT_desc(i, p, ci, co); return (size_t)ci * co * 8; }
-  const bf16* convT_packed(const float* const* P, const float* W) const {
-    for (int i = 0; i < 10; ++i) { int p, ci, co; convT_desc(i, p, ci, co); if (P[p] == W) return w.wT[i]; }
+  const bf16* convT_packed(const float* const* P, const float* W, bool tap_major = false) const {
+    for (int i = 0; i < 10; ++i) { int p, ci, co; convT_desc(i, p, ci, co); if (P[p] == W) return tap_major ? w.wTt[i] : w.wT[i]; }
     return nullptr;
   }
 
@@ -150,7 +151,8 @@ struct Exec {
         w.wqkv[i] = b.take<bf16>((size_t)3 * H * H); w.wproj[i] = b.take<bf16>((size_t)H * H);
         w.wfc1[i] = b.take<bf16>((size_t)F * H); w.wfc2[i] = b.take<bf16>((size_t)H * F);
       }
-      for (int i = 0; i < 10; ++i) w.wT[i] = b.take<bf16>(convT_elems(i));
+      for (int i = 0; i < 10; ++i) { w.wT[i] = b.take<bf16>(convT_elems(i)); w.wTt[i] = b.take<bf16>(convT_elems(i)); }
+      w.wpatch = b.take<bf16>((size_t)H * 4096 * c.Cin); w.apatch = b.take<bf16>((size_t)M * 4096 * c.Cin);
       for (int i = 0; i < 15; ++i) { int p, ci, co, ks; conv_desc(i, p, ci, co, ks); size_t n = (size_t)ci * co * ks * ks * ks; w.wcf[i] = b.take<bf16>(n); w.wcd[i] = b.take<bf16>(n); }
     }
     if (with_backward) {
@@ -161,7 +163,7 @@ struct Exec {
       w.dvit = b.take<T>(MH); w.dh = b.take<T>(MF); w.dln = b.take<T>(MH); w.datt = b.take<T>(MH); w.dqkv = b.take<T>(3 * MH);
       size_t big = (size_t)B * V[0] * fs;
       w.gA = b.take<T>(big); w.dcat = b.take<T>(2 * big); w.dc2 = b.take<T>(big); w.dc3 = b.take<T>(big);
-      w.da1 = b.take<T>(big); w.dc1 = b.take<T>(big);
+      w.da1 = b.take<T>(big); w.dc1 = b.take<T>(big); w.unsh = b.take<T>(big);
       w.bwd_acc = b.take<double>((size_t)3 * B * 8 * fs);
     }
     w.bytes = (b.off + 255) & ~(size_t)255;
@@ -172,7 +174,7 @@ struct Exec {
   template <class TO>
   int linear_fwd(const T* A, long lda, const float* W, const bf16* Wb, int Mr, int N, int K, const EpStore<TO>& ep, cudaStream_t st) {
     if constexpr (kTC) {
-      B200_PROF("linear_fwd", st);
+      B200_PROFD(st, "linear_fwd %dx%dx%d", Mr, N, K);
       return tc::gemm(tc::operand(A, lda, 1), tc::operand(Wb, K, 1), ep, Mr, N, K, 1, 1, st);
     } else {
       return simt_linear_fwd(A, lda, W, Mr, N, K, ep, st);
@@ -181,7 +183,7 @@ struct Exec {
   template <class TO>  // dX[M,K] = dY[M,N] W[N,K]   (W is the MN-major B operand: no transposed copy)
   int linear_dgrad(const T* dY, long ldy, const float* W, const bf16* Wb, int Mr, int N, int K, const EpStore<TO>& ep, cudaStream_t st) {
     if constexpr (kTC) {
-      B200_PROF("linear_dgrad", st);
+      B200_PROFD(st, "linear_dgrad %dx%dx%d", Mr, K, N);
       return tc::gemm(tc::operand(dY, ldy, 1), tc::operand(Wb, 1, K), ep, Mr, K, N, 1, 1, st);
     } else {
       return simt_linear_dgrad(dY, ldy, W, Mr, N, K, ep, st);
@@ -190,7 +192,7 @@ struct Exec {
   // dW[N,K] = dY^T X   (both operands MN-major)
   int linear_wgrad(const T* dY, long ldy, const T* X, long ldx, int Mr, int N, int K, float* dW, cudaStream_t st) {
     if constexpr (kTC) {
-      B200_PROF("linear_wgrad", st);
+      B200_PROFD(st, "linear_wgrad %dx%dx%d", N, K, Mr);
       return tc::gemm(tc::operand(dY, 1, ldy), tc::operand(X, 1, ldx), ep_plain<float>(dW, K), N, K, Mr, 1, 1, st);
     } else {
       return simt_linear_wgrad(dY, ldy, X, ldx, Mr, N, K, dW, st);
@@ -208,9 +210,15 @@ struct Exec {
         add(bp[B_FC1_W], w.wfc1[i], (size_t)F * H); add(bp[B_FC2_W], w.wfc2[i], (size_t)H * F);
       }
       for (int i = 0; i < 10; ++i) { int p, ci, co; convT_desc(i, p, ci, co); add(P[p], w.wT[i], convT_elems(i)); }
+      add(P[P_PATCH_W], w.wpatch, (size_t)H * 4096 * c.Cin);
       jobs.count = n;
       multi_cast_kernel<<<dim3(64, n), 256, 0, st>>>(jobs);
       B200_LAUNCH_CHECK();
+      for (int i = 0; i < 10; ++i) {
+        int p, ci, co; convT_desc(i, p, ci, co);
+        pack_convT_tapmajor_kernel<<<(unsigned)min(64L, (long)(convT_elems(i) + 255) / 256), 256, 0, st>>>(P[p], w.wTt[i], ci, co);
+        B200_LAUNCH_CHECK();
+      }
       for (int i = 0; i < 15; ++i) {
         int p, ci, co, ks; conv_desc(i, p, ci, co, ks);
         if (ci % 16 || co % 16) continue;   // those layers stay on the CUDA-core engine
@@ -258,7 +266,7 @@ struct Exec {
     if constexpr (kTC) {
       int ci = conv_index(W);
       if (ci >= 0 && tc::conv_supported(x.C, Co, x.pitch, x.coff, out.pitch, out.coff)) {
-        B200_PROF("conv_fwd", st);
+        B200_PROFD(st, "conv_fwd k%d %d->%d @%d", ks, x.C, Co, s.D);
         if (stats) { B200_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * c.B * Co, st)); if (stats_done) *stats_done = true; }
         return tc::conv(x.p, x.pitch, x.coff, x.C, s.N, s.D, s.H, s.W, w.wcf[ci], Co, ks, out.p, out.pitch, out.coff, 0, stats, st);
       }
@@ -269,7 +277,7 @@ struct Exec {
     if constexpr (kTC) {
       int ci = conv_index(W);
       if (ci >= 0 && tc::conv_supported(dy.C, Ci, dy.pitch, dy.coff, dx.pitch, dx.coff)) {
-        B200_PROF("conv_dgrad", st);
+        B200_PROFD(st, "conv_dgrad k%d %d->%d @%d", ks, dy.C, Ci, s.D);
         return tc::conv(dy.p, dy.pitch, dy.coff, dy.C, s.N, s.D, s.H, s.W, w.wcd[ci], Ci, ks, dx.p, dx.pitch, dx.coff, acc, nullptr, st);
       }
     }
@@ -278,7 +286,7 @@ struct Exec {
   int conv_wgrad(Cl<const T> x, Cl<const T> dy, Sp s, int ks, float* dW, cudaStream_t st) {
     if constexpr (kTC) {
       if (tc::wgrad_supported(x.C, dy.C, x.pitch, x.coff, dy.pitch, dy.coff)) {
-        B200_PROF("conv_wgrad", st);
+        B200_PROFD(st, "conv_wgrad k%d %dx%d @%d", ks, x.C, dy.C, s.D);
         return tc::conv_wgrad(x.p, x.pitch, x.coff, x.C, dy.p, dy.pitch, dy.coff, dy.C, s.N, s.D, s.H, s.W, ks, dW, st);
       }
     }
@@ -347,9 +355,17 @@ struct Exec {
     cur_params = P;
     // --- patch embedding (a5): tokens = rows(x) W^T + b + pos
     {
-      RowIsOuter<PatchGather, false> al; al.g = {x_in, c.Cin, c.S0, c.S1, c.S2, g0, g1, g2, c.conv_patch};
+      B200_PROF("patch_fwd", st);
       EpPatch ep = {w.x0, H, L, P[P_PATCH_B], P[P_POS]};
-      B200_TRY(launch_contract(al, ld2<float, false>(P[P_PATCH_W], 4096L * c.Cin, 1), ep, M, H, 4096 * c.Cin, 1, 1, st));
+      if constexpr (kTC) {
+        long tot = (long)M * 4096 * c.Cin;
+        patch_gather_kernel<<<(unsigned)min(148L * 8, (tot + 255) / 256), 256, 0, st>>>(x_in, w.apatch, c.Cin, c.S0, c.S1, c.S2, g0, g1, g2, c.conv_patch, tot);
+        B200_LAUNCH_CHECK();
+        B200_TRY(tc::gemm(tc::operand(w.apatch, 4096L * c.Cin, 1), tc::operand(w.wpatch, 4096L * c.Cin, 1), ep, M, H, 4096 * c.Cin, 1, 1, st));
+      } else {
+        RowIsOuter<PatchGather, false> al; al.g = {x_in, c.Cin, c.S0, c.S1, c.S2, g0, g1, g2, c.conv_patch};
+        B200_TRY(launch_contract(al, ld2<float, false>(P[P_PATCH_W], 4096L * c.Cin, 1), ep, M, H, 4096 * c.Cin, 1, 1, st));
+      }
     }
     // --- transformer blocks (a6-a8)
     float scale = 1.0f / sqrtf((float)dh);
@@ -392,6 +408,7 @@ struct Exec {
     B200_TRY(res_fwd(cl<const T>(w.cat2, 2 * fs, 0, 2 * fs), 0, P[P_D2_C1], P[P_D2_C2], P[P_D2_C3], w.rs[4], cl(w.d0, fs, 0, fs), st));
     // --- 1x1x1 head with bias, NCDHW fp32 logits (a12)
     if (logits_out) {
+      B200_PROF("head_fwd", st);
       EpHeadNcdhw ep = {logits_out, c.ncls, V[0], P[P_OUT_B]};
       B200_TRY(launch_contract(ld2<T, false>(w.d0, fs, 1), ld2<float, false>(P[P_OUT_W], fs, 1), ep, (int)(B * V[0]), c.ncls, fs, 1, 1, st));
     }
@@ -403,7 +420,7 @@ struct Exec {
       if (cur_params) {
         const bf16* Wb = convT_packed(cur_params, W);
         if (Wb) {   // [rows, Ci] x W[Ci][Co*8] (MN-major B), scatter epilogue writes straight into the concat buffer
-          B200_PROF("convT_fwd", st);
+          B200_PROFD(st, "convT_fwd %d->%d @%d", Ci, out.C, sp(in_level).D);
           Sp s = sp(in_level);
           EpConvTScatter<T> ep = {out.p, s.D, s.H, s.W, out.pitch, out.coff};
           return tc::gemm(tc::operand(x, ldx, 1), tc::operand(Wb, 1, (long)out.C * 8), ep, (int)s.rows(), out.C * 8, Ci, 1, 1, st);
@@ -472,6 +489,7 @@ struct Exec {
     if (dec) {
       int rows = (int)(B * V[0]);
       // head: d(d0) = dlogits^T W ; dW = dlogits d0 ; db = sum dlogits
+      { B200_PROF("head_bwd", st);
       { RowIsOuter<NcdhwGather, true> al; al.g = {d_logits, c.ncls, V[0]};
         B200_TRY(launch_contract(al, ld2<float, true>(P[P_OUT_W], 1, fs), ep_plain<T>(w.gA, fs), rows, fs, c.ncls, 1, 1, st)); }
       if (G[P_OUT_W]) {
@@ -484,6 +502,7 @@ struct Exec {
         B200_CUDA(cudaMemsetAsync(G[P_OUT_B], 0, sizeof(float) * c.ncls, st));
         rowsum_atomic_kernel<<<dim3(32, B * c.ncls), 256, 0, st>>>(d_logits, G[P_OUT_B], V[0], c.ncls);
         B200_LAUNCH_CHECK();
+      }
       }
       // decoder2 block, encoder1 block, decoder2 transposed conv
       B200_TRY(res_bwd(cl<const T>(w.cat2, 2 * fs, 0, 2 * fs), 0, P[P_D2_C1], P[P_D2_C2], P[P_D2_C3], w.rs[4], cl<const T>(w.d0, fs, 0, fs),
@@ -565,9 +584,14 @@ struct Exec {
     }
     // --- patch embedding: dW = dx0^T rows(x), db = colsum, dpos = sum over batch
     if (G[P_PATCH_W]) {
-      RowIsK<PatchGather, true> bl; bl.g = {x_in, c.Cin, c.S0, c.S1, c.S2, g0, g1, g2, c.conv_patch};
+      B200_PROF("patch_wgrad", st);
       int Kp = 4096 * c.Cin;
-      B200_TRY(launch_contract(ld2<float, true>(w.dx, 1, H), bl, ep_plain<float>(G[P_PATCH_W], Kp), H, Kp, M, 1, 1, st));
+      if constexpr (kTC) {
+        B200_TRY(tc::gemm(tc::operand(w.dxb, 1, H), tc::operand(w.apatch, 1, Kp), ep_plain<float>(G[P_PATCH_W], Kp), H, Kp, M, 1, 1, st));
+      } else {
+        RowIsK<PatchGather, true> bl; bl.g = {x_in, c.Cin, c.S0, c.S1, c.S2, g0, g1, g2, c.conv_patch};
+        B200_TRY(launch_contract(ld2<float, true>(w.dx, 1, H), bl, ep_plain<float>(G[P_PATCH_W], Kp), H, Kp, M, 1, 1, st));
+      }
     }
     if (G[P_PATCH_B]) B200_TRY(launch_colsum<float>(w.dx, G[P_PATCH_B], M, H, st));
     if (G[P_POS]) { batchsum_kernel<<<cdiv((long)L * H, 256), 256, 0, st>>>(w.dx, G[P_POS], B, (long)L * H); B200_LAUNCH_CHECK(); }
@@ -592,6 +616,29 @@ struct Exec {
   template <class TO>
   int convT_bwd(const T* x, long ldx, int Ci, int in_level, const float* W, Cl<const T> dy, float* dW, TO* dx, long lddx, int accumulate, cudaStream_t st) {
     Sp s = sp(in_level);
+    if constexpr (kTC) {
+      const bf16* Wt = cur_params ? convT_packed(cur_params, W, true) : nullptr;
+      constexpr int VN = Vec16<T>::N;
+      if (Wt && dy.C % VN == 0 && dy.pitch % VN == 0 && dy.coff % VN == 0 && (ldx * 2) % 16 == 0) {
+        int Co = dy.C, rows = (int)s.rows(), K8 = 8 * Co;
+        { B200_PROFD(st, "convT_unshuffle %d @%d", Co, s.D);
+          long tot = (long)rows * 8 * (Co / VN);
+          unshuffle_kernel<T><<<(unsigned)min(148L * 16, (tot + 255) / 256), 256, 0, st>>>(dy.p, ClView{dy.pitch, dy.coff}, Co, s.N, s.D, s.H, s.W, w.unsh);
+          B200_LAUNCH_CHECK(); }
+        if (dW) {   // dW[ci][co*8+tap] = sum_v x[v,ci] U[v, tap*Co+co]   (voxels = reduction, split-K + atomics)
+          B200_PROFD(st, "convT_wgrad %dx%d @%d", Ci, Co, s.D);
+          B200_CUDA(cudaMemsetAsync(dW, 0, sizeof(float) * Ci * K8, st));
+          EpAtomicTapRemap ep = {dW, Co};
+          B200_TRY(tc::gemm(tc::operand(x, 1, ldx), tc::operand(w.unsh, 1, K8), ep, Ci, K8, rows, 1, 1, st, true));
+        }
+        if (dx) {   // dx[v,ci] = sum_j U[v,j] Wt[ci][j]
+          B200_PROFD(st, "convT_dgrad %d<-%d @%d", Ci, Co, s.D);
+          EpStore<TO> ep = ep_plain<TO>(dx, lddx); ep.accumulate = accumulate;
+          B200_TRY(tc::gemm(tc::operand(w.unsh, K8, 1), tc::operand(Wt, K8, 1), ep, rows, Ci, K8, 1, 1, st));
+        }
+        return 0;
+      }
+    }
     if (dW) {
       B200_CUDA(cudaMemsetAsync(dW, 0, sizeof(float) * Ci * dy.C * 8, st));
       B200_TRY((simt_convT_wgrad<T, T>(x, ldx, Ci, dy, s, dW, st)));

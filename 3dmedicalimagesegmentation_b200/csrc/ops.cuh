@@ -39,7 +39,7 @@ static int simt_linear_wgrad(const TG* dY, long ldy, const TX* X, long ldx, int 
 // ---- k^3 convolution, stride 1, same padding, bias-free (W fp32 [Co][Ci][k^3]) ----
 template <class T>
 static int simt_conv_fwd(Cl<const T> x, Sp sp, const float* W, int Co, int ks, Cl<T> out, cudaStream_t st) {
-  B200_PROF("conv_fwd", st);
+  B200_PROFD(st, "simt conv_fwd k%d %d->%d @%d", ks, x.C, Co, sp.D);
   int taps = ks * ks * ks;
   RowIsOuter<ConvGather<T, true>, false> al; al.g = {x.p, sp.D, sp.H, sp.W, x.pitch, x.coff, x.C, ks, 1};
   ConvWeightB bl = {W, x.C, Co, taps, 0};
@@ -48,7 +48,7 @@ static int simt_conv_fwd(Cl<const T> x, Sp sp, const float* W, int Co, int ks, C
 }
 template <class T>
 static int simt_conv_dgrad(Cl<const T> dy, Sp sp, const float* W, int Ci, int ks, Cl<T> dx, int accumulate, cudaStream_t st) {
-  B200_PROF("conv_dgrad", st);
+  B200_PROFD(st, "simt conv_dgrad k%d %d->%d @%d", ks, dy.C, Ci, sp.D);
   int taps = ks * ks * ks;
   RowIsOuter<ConvGather<T, true>, false> al; al.g = {dy.p, sp.D, sp.H, sp.W, dy.pitch, dy.coff, dy.C, ks, -1};
   ConvWeightB bl = {W, Ci, dy.C, taps, 1};
@@ -67,7 +67,7 @@ static inline int pick_splits(long K, long tiles) {
 }
 template <class T>  // dW[co][ci][tap] = sum_v dy[v,co] x[v+tap,ci]   (dW must be zero on entry)
 static int simt_conv_wgrad(Cl<const T> x, Cl<const T> dy, Sp sp, int ks, float* dW, cudaStream_t st) {
-  B200_PROF("conv_wgrad", st);
+  B200_PROFD(st, "simt conv_wgrad k%d %dx%d @%d", ks, x.C, dy.C, sp.D);
   int taps = ks * ks * ks;
   int Mr = x.C * taps, Nr = dy.C;
   RowIsK<ConvGather<T, false>, false> al; al.g = {x.p, sp.D, sp.H, sp.W, x.pitch, x.coff, x.C, ks, 1};
@@ -86,14 +86,14 @@ static int simt_convT_fwd(const TA* x, long ldx, int Ci, Sp sp, const float* W, 
 }
 template <class T, class TO>
 static int simt_convT_dgrad(Cl<const T> dy, Sp sp, const float* W, int Ci, TO* dx, long lddx, int accumulate, cudaStream_t st) {
-  B200_PROF("convT_dgrad", st);
+  B200_PROFD(st, "simt convT_dgrad %d<-%d @%d", Ci, dy.C, sp.D);
   RowIsOuter<ConvTGather<T>, false> al; al.g = {dy.p, sp.D, sp.H, sp.W, dy.pitch, dy.coff};
   EpStore<TO> ep = ep_plain<TO>(dx, lddx); ep.accumulate = accumulate;
   return launch_contract(al, ld2<float, false>(W, (long)dy.C * 8, 1), ep, (int)sp.rows(), Ci, dy.C * 8, 1, 1, st);
 }
 template <class TA, class T>  // dW[ci][co*8+tap] (dW zero on entry)
 static int simt_convT_wgrad(const TA* x, long ldx, int Ci, Cl<const T> dy, Sp sp, float* dW, cudaStream_t st) {
-  B200_PROF("convT_wgrad", st);
+  B200_PROFD(st, "simt convT_wgrad %dx%d @%d", Ci, dy.C, sp.D);
   RowIsK<ConvTGather<T>, true> bl; bl.g = {dy.p, sp.D, sp.H, sp.W, dy.pitch, dy.coff};
   int Nr = dy.C * 8;
   EpAtomic ep = {dW, (long)Nr};

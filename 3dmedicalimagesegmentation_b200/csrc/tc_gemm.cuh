@@ -89,6 +89,7 @@ struct Params {
   int tiles_m, tiles_n, nb1, batches;
   int stages;
   uint32_t tmem_cols;       // 2*BN rounded to a power of two
+  int ksplit, kb_per_split; // split-K: work item = (tile, split); epilogue functor must accumulate atomically
 };
 
 template <class EP>
@@ -104,8 +105,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
   uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int kblocks = (p.K + BK - 1) / BK;
-  const long total_tiles = (long)p.tiles_m * p.tiles_n * p.batches;
+  const int kblocks_all = (p.K + BK - 1) / BK;
+  const long total_tiles = (long)p.tiles_m * p.tiles_n * p.batches * p.ksplit;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
@@ -126,9 +127,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       for (long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        int tm = (int)(t % p.tiles_m); long r = t / p.tiles_m; int tn = (int)(r % p.tiles_n); int b = (int)(r / p.tiles_n);
+        int sp = (int)(t % p.ksplit); long r = t / p.ksplit;
+        int tm = (int)(r % p.tiles_m); r /= p.tiles_m; int tn = (int)(r % p.tiles_n); int b = (int)(r / p.tiles_n);
         int b0 = b / p.nb1, b1 = b % p.nb1;
-        for (int kb = 0; kb < kblocks; ++kb) {
+        const int kb_begin = sp * p.kb_per_split, kb_end = min(kblocks_all, kb_begin + p.kb_per_split);
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
           mbar_wait(empty + stage, phase ^ 1);
           uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes), sb = sa + a_bytes;
           mbar_expect_tx(full + stage, stage_bytes);
@@ -148,6 +151,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                            ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
     int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
     for (long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int sp = (int)(t % p.ksplit);
+      const int kblocks = min(kblocks_all, (sp + 1) * p.kb_per_split) - sp * p.kb_per_split;
       mbar_wait(tempty + acc, acc_phase ^ 1);
       tc_fence_after();
       uint32_t tmem_d = tmem_base + (uint32_t)(acc * p.BN);
@@ -177,7 +182,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     const int q = warp & 3;
     int acc = 0; uint32_t acc_phase = 0;
     for (long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-      int tm = (int)(t % p.tiles_m); long r = t / p.tiles_m; int tn = (int)(r % p.tiles_n); int b = (int)(r / p.tiles_n);
+      long r = t / p.ksplit;
+      int tm = (int)(r % p.tiles_m); r /= p.tiles_m; int tn = (int)(r % p.tiles_n); int b = (int)(r / p.tiles_n);
       mbar_wait(tfull + acc, acc_phase);
       tc_fence_after();
       const int m = tm * BM + q * 32 + lane;
@@ -253,7 +259,7 @@ static inline int num_sms() {
 
 // D[(b0,b1)][m,n] = sum_k A(m,k) B(n,k);  ep(b0*nb1+b1, m, n, acc)
 template <class EP>
-static int gemm(const Operand& A, const Operand& B, const EP& ep, int M, int N, int K, int nb0, int nb1, cudaStream_t st) {
+static int gemm(const Operand& A, const Operand& B, const EP& ep, int M, int N, int K, int nb0, int nb1, cudaStream_t st, bool allow_splitk = false) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   Params p;
   p.M = M; p.N = N; p.K = K;
@@ -275,7 +281,13 @@ static int gemm(const Operand& A, const Operand& B, const EP& ep, int M, int N, 
   size_t smem = (size_t)p.stages * stage_bytes + 1024 + 256;
   static bool attr_done = false;  // per EP instantiation
   if (!attr_done) { B200_CUDA(cudaFuncSetAttribute(gemm_kernel<EP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr_done = true; }
-  long tiles = (long)p.tiles_m * p.tiles_n * p.batches;
+  p.ksplit = 1; p.kb_per_split = cdiv(K, BK);
+  if (allow_splitk) {
+    long base_tiles = (long)p.tiles_m * p.tiles_n * p.batches; int kbs = cdiv(K, BK);
+    long want = num_sms() / base_tiles; if (want > kbs / 4) want = kbs / 4; if (want < 1) want = 1;
+    p.kb_per_split = cdiv(kbs, (int)want); p.ksplit = cdiv(kbs, p.kb_per_split);
+  }
+  long tiles = (long)p.tiles_m * p.tiles_n * p.batches * p.ksplit;
   int grid = (int)(tiles < num_sms() ? tiles : num_sms());
   gemm_kernel<EP><<<grid, 192, smem, st>>>(ma, mb, p, ep);
   B200_LAUNCH_CHECK();

@@ -182,7 +182,7 @@ def main():
     prof = pkg._lib.prof_report()
     lib.b200_prof_enable(0)
     pk, pk_kind = peaks()
-    conv_ms = sum(v[0] for k, v in prof.items() if k.startswith("conv_"))
+    conv_ms = sum(v[0] for k, v in prof.items() if "conv_" in k and "convT" not in k)
     conv_flop = 3 * 2 * 43.402e9 * B          # conv decoder fwd + dgrad + wgrad (43.402 GMAC fwd / sample)
     top = max(prof.items(), key=lambda kv: kv[1][0]) if prof else ("none", (0.0, 0))
     roof = {"bound": "tensor", "kernel": "conv3d implicit GEMM fwd+dgrad+wgrad (all launches of one step)",
@@ -192,8 +192,9 @@ def main():
     roof["frac"] = roof["achieved"] / roof["peak"] if roof["achieved"] else None
     if args.breakdown and rank == 0:
         tot = sum(v[0] for v in prof.values())
+        print(f"  profiled total {tot:.3f} ms", file=sys.stderr)
         for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0]):
-            print(f"  {k:18s} {v[0]:9.3f} ms  {v[1]:4d} calls  {100 * v[0] / tot:5.1f}%", file=sys.stderr)
+            print(f"  {k:34s} {v[0]:9.3f} ms  {v[1]:4d} calls  {100 * v[0] / tot:5.1f}%", file=sys.stderr)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
