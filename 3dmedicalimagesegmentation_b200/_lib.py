@@ -60,6 +60,7 @@ SIGNATURES = {
                                   c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "b200_test_tc_wgrad": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                    c_void_p, c_void_p]),
+    "b200_test_set_debug_buffer": (None, [c_void_p]),
     "b200_test_tc_gemm": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
 }
 

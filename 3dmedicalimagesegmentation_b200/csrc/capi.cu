@@ -265,6 +265,8 @@ int b200_test_tc_wgrad(const void* x, int x_pitch, int x_coff, int Ci, const voi
   return tc::conv_wgrad((const bf16*)x, x_pitch, x_coff, Ci, (const bf16*)dy, dy_pitch, dy_coff, Co, N, D, H, W, ks, dW, st);
 }
 
+void b200_test_set_debug_buffer(void* dev_ptr) { tc::g_dbg = (long long*)dev_ptr; }
+
 int b200_test_tc_gemm(const void* a, const void* b, float* out, int M, int N, int K, int a_mn, int b_mn, void* stream) {
   return tc_gemm_test((const bf16*)a, (const bf16*)b, out, M, N, K, a_mn, b_mn, (cudaStream_t)stream);
 }

@@ -114,6 +114,48 @@ struct EpStore {
     if (accumulate) v += to_f(out[o]);
     out[o] = from_f<TO>(v);
   }
+  // 16 consecutive columns of row m (tcgen05 epilogue): 16-byte loads/stores when the segment is full and aligned
+  __device__ __forceinline__ void seg16(int b, int m, int n0, const float* acc, int nvalid) const {
+    long o = (long)(b / nb1) * sb0 + (long)(b % nb1) * sb1 + (long)m * ld + n0;
+    bool fast = nvalid == 16 && ((reinterpret_cast<uintptr_t>(out + o) & 15) == 0) && (!preact || (reinterpret_cast<uintptr_t>(preact + o) & 15) == 0) &&
+                (!usrc || (reinterpret_cast<uintptr_t>(usrc + o) & 15) == 0) && (!resid || (reinterpret_cast<uintptr_t>(resid + (long)m * ldr + n0) & 15) == 0) &&
+                (!bias || (reinterpret_cast<uintptr_t>(bias + n0) & 15) == 0);
+    if (!fast) {
+#pragma unroll 1
+      for (int j = 0; j < nvalid; ++j) (*this)(b, m, n0 + j, acc[j]);
+      return;
+    }
+    constexpr int VN = Vec16<TO>::N;
+    float v[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = acc[j] * alpha;
+    if (bias) {
+#pragma unroll
+      for (int j = 0; j < 16; j += 4) { float4 t = *reinterpret_cast<const float4*>(bias + n0 + j); v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w; }
+    }
+    if (preact) {
+#pragma unroll
+      for (int j = 0; j < 16; j += VN) { Vec16<TO> t; for (int i = 0; i < VN; ++i) t.v[i] = v[j + i]; t.store(preact + o + j); }
+    }
+    if (act == ACT_GELU) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = gelu_erf(v[j]);
+    } else if (act == ACT_GELU_BWD) {
+#pragma unroll
+      for (int j = 0; j < 16; j += VN) { Vec16<TO> t; t.load(usrc + o + j); for (int i = 0; i < VN; ++i) v[j + i] *= gelu_erf_grad(t.v[i]); }
+    }
+    if (resid) {
+      const float* r = resid + (long)m * ldr + n0;
+#pragma unroll
+      for (int j = 0; j < 16; j += 4) { float4 t = *reinterpret_cast<const float4*>(r + j); v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w; }
+    }
+    if (accumulate) {
+#pragma unroll
+      for (int j = 0; j < 16; j += VN) { Vec16<TO> t; t.load(out + o + j); for (int i = 0; i < VN; ++i) v[j + i] += t.v[i]; }
+    }
+#pragma unroll
+    for (int j = 0; j < 16; j += VN) { Vec16<TO> t; for (int i = 0; i < VN; ++i) t.v[i] = v[j + i]; t.store(out + o + j); }
+  }
 };
 template <class TO> static inline EpStore<TO> ep_plain(TO* out, long ld) {
   EpStore<TO> e; memset(&e, 0, sizeof(e)); e.out = out; e.ld = ld; e.nb1 = 1; e.alpha = 1.f; return e;
@@ -123,6 +165,18 @@ struct EpPatch {  // tokens = acc + bias + position embedding
   float* out; int H, L; const float* bias; const float* pos;
   __device__ __forceinline__ void operator()(int, int m, int n, float acc) const {
     out[(long)m * H + n] = acc + bias[n] + pos[(long)(m % L) * H + n];
+  }
+  __device__ __forceinline__ void seg16(int, int m, int n0, const float* acc, int nvalid) const {
+    const float* pr = pos + (long)(m % L) * H + n0; float* o = out + (long)m * H + n0;
+    if (nvalid == 16 && (H & 3) == 0) {
+#pragma unroll
+      for (int j = 0; j < 16; j += 4) {
+        float4 bb = *reinterpret_cast<const float4*>(bias + n0 + j), pp = *reinterpret_cast<const float4*>(pr + j);
+        *reinterpret_cast<float4*>(o + j) = make_float4(acc[j] + bb.x + pp.x, acc[j + 1] + bb.y + pp.y, acc[j + 2] + bb.z + pp.z, acc[j + 3] + bb.w + pp.w);
+      }
+    } else {
+      for (int j = 0; j < nvalid; ++j) o[j] = acc[j] + bias[n0 + j] + pr[j];
+    }
   }
 };
 

@@ -81,45 +81,58 @@ conv_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ C
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      for (long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-        int tw = (int)(t % p.tiles_w); long r = t / p.tiles_w; int th = (int)(r % p.tiles_h); r /= p.tiles_h;
-        int td = (int)(r % p.tiles_d); int n = (int)(r / p.tiles_d);
-        for (int s = 0; s < nstage_per_tile; ++s) {
-          int kb0 = s * p.group, cnt = min(p.group, p.kblocks - kb0);
-          mbar_wait(empty + stage, phase ^ 1);
-          mbar_expect_tx(full + stage, (uint32_t)cnt * (uint32_t)(p.a_bytes + p.Co * p.row_bytes));  // bytes TMA really delivers
-          uint32_t base = smem_u32(smem + (size_t)stage * stage_bytes);
-          for (int i = 0; i < cnt; ++i) {
-            int kb = kb0 + i, tap = kb / p.nchunk, ch = kb - tap * p.nchunk;
-            int kw = tap % p.ks, kh = (tap / p.ks) % p.ks, kd = tap / (p.ks * p.ks);
-            uint32_t sa = base + i * kb_bytes, sb = sa + p.a_bytes;
-            tma_load_5d(sa, &map_x, full + stage, ch * p.kc, tw * TW + kw - pad, th * TH + kh - pad, td * TD + kd - pad, n);
-            tma_load_2d(sb, &map_w, full + stage, ch * p.kc, tap * p.Co);
+    // ---- TMA producer: warp-uniform loop, one elected lane issues
+    int stage = 0; uint32_t phase = 0;
+    const uint32_t smem_base_u = smem_u32(smem);
+    const uint32_t kb_tx = (uint32_t)(p.a_bytes + p.Co * p.row_bytes);   // bytes TMA really delivers per k-block
+    for (long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      int tw = (int)(t % p.tiles_w); long r = t / p.tiles_w; int th = (int)(r % p.tiles_h); r /= p.tiles_h;
+      int td = (int)(r % p.tiles_d); int n = (int)(r / p.tiles_d);
+      const int w0 = tw * TW - pad, h0 = th * TH - pad, d0 = td * TD - pad;
+      int kw = 0, kh = 0, kd = 0, ch = 0, wrow = 0;   // running tap / chunk state (kb = tap*nchunk + ch)
+      for (int s = 0; s < nstage_per_tile; ++s) {
+        const int cnt = min(p.group, p.kblocks - s * p.group);
+        mbar_wait(empty + stage, phase ^ 1);
+        const uint32_t base = smem_base_u + (uint32_t)stage * stage_bytes;
+        const bool leader = elect_one();
+        if (leader) mbar_expect_tx(full + stage, (uint32_t)cnt * kb_tx);
+        for (int i = 0; i < cnt; ++i) {
+          if (leader) {
+            const uint32_t sa = base + i * kb_bytes;
+            tma_load_5d(sa, &map_x, full + stage, ch * p.kc, w0 + kw, h0 + kh, d0 + kd, n);
+            tma_load_2d(sa + p.a_bytes, &map_w, full + stage, ch * p.kc, wrow);
           }
-          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          if (++ch == p.nchunk) { ch = 0; wrow += p.Co; if (++kw == p.ks) { kw = 0; if (++kh == p.ks) { kh = 0; ++kd; } } }
         }
+        __syncwarp();
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
+    // ---- MMA issuer
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.Co >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint32_t layout = p.row_bytes == 128 ? 2u : (p.row_bytes == 64 ? 4u : 6u);
+    const uint32_t hi = desc_hi(8 * p.row_bytes, layout);
+    const uint32_t smem_base_u = smem_u32(smem);
+    const uint32_t a_lo0 = desc_lo(smem_base_u, 16), b_lo0 = desc_lo(smem_base_u + p.a_bytes, 16);
+    const uint32_t stage_units = stage_bytes >> 4, kb_units = kb_bytes >> 4;
     int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
     const int ksteps = p.kc / 16;
     for (long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
       mbar_wait(tempty + acc, acc_phase ^ 1);
       tc_fence_after();
-      uint32_t tmem_d = tmem_base + (uint32_t)(acc * p.Co);
+      const uint32_t tmem_d = tmem_base + (uint32_t)(acc * p.Co);
       for (int s = 0; s < nstage_per_tile; ++s) {
-        int kb0 = s * p.group, cnt = min(p.group, p.kblocks - kb0);
+        const int cnt = min(p.group, p.kblocks - s * p.group);
         mbar_wait(full + stage, phase);
         tc_fence_after();
-        if (lane == 0) {
-          uint32_t base = smem_u32(smem + (size_t)stage * stage_bytes);
+        const uint32_t a_st = a_lo0 + (uint32_t)stage * stage_units, b_st = b_lo0 + (uint32_t)stage * stage_units;
+        if (elect_one()) {
+          uint32_t a_lo = a_st, b_lo = b_st;
           for (int i = 0; i < cnt; ++i) {
-            uint32_t sa = base + i * kb_bytes, sb = sa + p.a_bytes;
             for (int k = 0; k < ksteps; ++k)
-              umma_f16(tmem_d, smem_desc_k(sa + k * 32, p.row_bytes), smem_desc_k(sb + k * 32, p.row_bytes), idesc, (s | i | k) ? 1u : 0u);
+              umma_f16(tmem_d, desc64(a_lo + 2 * k, hi), desc64(b_lo + 2 * k, hi), idesc, (s | i | k) ? 1u : 0u);
+            a_lo += kb_units; b_lo += kb_units;
           }
           umma_commit(empty + stage);
           if (s == nstage_per_tile - 1) umma_commit(tfull + acc);

@@ -13,6 +13,7 @@
 // by TMA out-of-bounds zero fill plus an m<M, n<N guard in the epilogue.
 #pragma once
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "contract.cuh"
@@ -21,7 +22,6 @@ namespace b200 {
 namespace tc {
 
 static constexpr int BM = 128, BK = 64;
-static constexpr long long WATCHDOG_CYCLES = 2000000000LL;  // ~1 s: trap instead of hanging the GPU on a protocol bug
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -33,24 +33,39 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// Straight-line asm (internal retry loop) so the compiler keeps the surrounding loops warp-uniform.
+// Watchdog: ~4M failed probes (each probe suspends in hardware for a while) -> trap instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t addr = smem_u32(bar), ok = 0;
-  long long t0 = 0;
-  do {
-    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
-                 : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
-    if (!ok) {
-      long long now = clock64();
-      if (t0 == 0) t0 = now;
-      else if (now - t0 > WATCHDOG_CYCLES) __trap();
-    }
-  } while (!ok);
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .u32 n;\n"
+      "mov.u32 n, 0;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "add.u32 n, n, 1;\n"
+      "setp.gt.u32 p, n, 4194304;\n"
+      "@p trap;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
   asm volatile(
       "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
       ::"r"(dst), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
+// one elected lane of a converged warp (keeps the surrounding loop warp-uniform so operands stay in uniform registers)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n .reg .pred p;\n elect.sync _|p, 0xffffffff;\n selp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ uint64_t desc64(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
+// descriptor halves: lo = start>>4 | (LBO>>4)<<16 ; hi = SBO>>4 | version(1)<<14 | layout<<29
+__device__ __forceinline__ uint32_t desc_hi(uint32_t sbo_bytes, uint32_t layout) { return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (layout << 29); }
+__device__ __forceinline__ uint32_t desc_lo(uint32_t addr, uint32_t lbo_bytes) { return ((addr & 0x3FFFFu) >> 4) | (((lbo_bytes >> 4) & 0x3FFFu) << 16); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -83,6 +98,17 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes,
   return d;
 }
 
+// 16 consecutive output columns of one row: functors with a vectorised `seg16` use it, others get a rolled scalar loop
+template <class EP>
+__device__ __forceinline__ auto ep_seg16(const EP& ep, int b, int m, int n0, const float* v, int nvalid) -> decltype(ep.seg16(b, m, n0, v, nvalid), void()) {
+  ep.seg16(b, m, n0, v, nvalid);
+}
+template <class EP, class... Dummy>
+__device__ __forceinline__ void ep_seg16(const EP& ep, int b, int m, int n0, const float* v, int nvalid, Dummy...) {
+#pragma unroll 1
+  for (int j = 0; j < nvalid; ++j) ep(b, m, n0 + j, v[j]);
+}
+
 struct Params {
   int M, N, K, BN;          // BN in {64,128,256}
   int a_mn, b_mn;           // operand majors
@@ -90,9 +116,10 @@ struct Params {
   int stages;
   uint32_t tmem_cols;       // 2*BN rounded to a power of two
   int ksplit, kb_per_split; // split-K: work item = (tile, split); epilogue functor must accumulate atomically
+  long long* dbg;           // optional: CTA 0 phase timestamps (clock64) for tuning
 };
 
-template <class EP>
+template <class EP, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(192, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const Params p, const EP ep) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -105,6 +132,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
   uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool dbg = p.dbg && blockIdx.x == 0;
+  if (dbg && threadIdx.x == 0) p.dbg[0] = clock64();
   const int kblocks_all = (p.K + BK - 1) / BK;
   const long total_tiles = (long)p.tiles_m * p.tiles_n * p.batches * p.ksplit;
 
@@ -121,62 +150,75 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (dbg && threadIdx.x == 0) p.dbg[1] = clock64();
 
   if (warp == 0) {
-    // ------------------------------------------------ TMA producer
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      for (long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        int sp = (int)(t % p.ksplit); long r = t / p.ksplit;
-        int tm = (int)(r % p.tiles_m); r /= p.tiles_m; int tn = (int)(r % p.tiles_n); int b = (int)(r / p.tiles_n);
-        int b0 = b / p.nb1, b1 = b % p.nb1;
-        const int kb_begin = sp * p.kb_per_split, kb_end = min(kblocks_all, kb_begin + p.kb_per_split);
-        for (int kb = kb_begin; kb < kb_end; ++kb) {
-          mbar_wait(empty + stage, phase ^ 1);
-          uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes), sb = sa + a_bytes;
+    // ------------------------------------------------ TMA producer (warp-uniform loop, one elected lane issues)
+    int stage = 0; uint32_t phase = 0;
+    const uint32_t smem_base_u = smem_u32(smem);
+    for (long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      int sp = (int)(t % p.ksplit); long r = t / p.ksplit;
+      int tm = (int)(r % p.tiles_m); r /= p.tiles_m; int tn = (int)(r % p.tiles_n); int b = (int)(r / p.tiles_n);
+      int b0 = b / p.nb1, b1 = b % p.nb1;
+      const int kb_begin = sp * p.kb_per_split, kb_end = min(kblocks_all, kb_begin + p.kb_per_split);
+      const int m0 = tm * BM, n0 = tn * p.BN;
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        mbar_wait(empty + stage, phase ^ 1);
+        if (elect_one()) {
+          const uint32_t sa = smem_base_u + (uint32_t)stage * stage_bytes, sb = sa + a_bytes;
+          const int k0 = kb * BK;
           mbar_expect_tx(full + stage, stage_bytes);
-          if (!p.a_mn) tma_load_4d(sa, &map_a, full + stage, kb * BK, tm * BM, b1, b0);
-          else for (int c = 0; c < BM / 64; ++c) tma_load_4d(sa + c * (64 * BK * 2), &map_a, full + stage, tm * BM + c * 64, kb * BK, b1, b0);
-          if (!p.b_mn) tma_load_4d(sb, &map_b, full + stage, kb * BK, tn * p.BN, b1, b0);
-          else for (int c = 0; c < p.BN / 64; ++c) tma_load_4d(sb + c * (64 * BK * 2), &map_b, full + stage, tn * p.BN + c * 64, kb * BK, b1, b0);
-          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          if (!A_MN) tma_load_4d(sa, &map_a, full + stage, k0, m0, b1, b0);
+          else { tma_load_4d(sa, &map_a, full + stage, m0, k0, b1, b0); tma_load_4d(sa + 64 * BK * 2, &map_a, full + stage, m0 + 64, k0, b1, b0); }
+          if (!B_MN) tma_load_4d(sb, &map_b, full + stage, k0, n0, b1, b0);
+          else for (int c = 0; c < p.BN / 64; ++c) tma_load_4d(sb + c * (64 * BK * 2), &map_b, full + stage, n0 + c * 64, k0, b1, b0);
+          if (dbg && kb < 4 && t == blockIdx.x) p.dbg[16 + kb] = clock64();
         }
+        __syncwarp();
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
     }
+    if (dbg && lane == 0) p.dbg[2] = clock64();   // producer done issuing
   } else if (warp == 1) {
-    // ------------------------------------------------ MMA issuer
+    // ------------------------------------------------ MMA issuer (warp-uniform loop, one elected lane issues)
     // instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 [4,6), a=BF16 [7,10), b=BF16 [10,13),
     // a_major bit15, b_major bit16, N>>3 [17,23), M>>4 [24,29)
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)p.a_mn << 15) | ((uint32_t)p.b_mn << 16) |
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)A_MN << 15) | ((uint32_t)B_MN << 16) |
                            ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    // K-major: 8-row groups 1024 B apart, +32 B per 16-wide K step inside the swizzle atom.
+    // MN-major: 64-wide MN atoms 64*BK*2 B apart (LBO), 8-k-row groups 1024 B apart (SBO), +2048 B per K step.
+    const uint32_t hi = desc_hi(1024, 2);
+    const uint32_t smem_base_u = smem_u32(smem);
+    const uint32_t a_lo0 = desc_lo(smem_base_u, A_MN ? 64 * BK * 2 : 16), b_lo0 = desc_lo(smem_base_u + a_bytes, B_MN ? 64 * BK * 2 : 16);
+    const uint32_t a_step = A_MN ? (2048u >> 4) : (32u >> 4), b_step = B_MN ? (2048u >> 4) : (32u >> 4);
+    const uint32_t stage_units = stage_bytes >> 4;
     int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
     for (long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int sp = (int)(t % p.ksplit);
       const int kblocks = min(kblocks_all, (sp + 1) * p.kb_per_split) - sp * p.kb_per_split;
       mbar_wait(tempty + acc, acc_phase ^ 1);
       tc_fence_after();
-      uint32_t tmem_d = tmem_base + (uint32_t)(acc * p.BN);
+      const uint32_t tmem_d = tmem_base + (uint32_t)(acc * p.BN);
       for (int kb = 0; kb < kblocks; ++kb) {
         mbar_wait(full + stage, phase);
         tc_fence_after();
-        if (lane == 0) {
-          uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes), sb = sa + a_bytes;
-#pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            // K-major: 8-row groups 1024 B apart, step 32 B along K inside the swizzle atom.
-            // MN-major: 64-wide MN atoms (64*BK*2 B apart), 8-k-row groups 1024 B apart, step 2048 B per 16 k.
-            uint64_t ad = p.a_mn ? smem_desc(sa + k * 2048, 64 * BK * 2, 1024) : smem_desc(sa + k * 32, 16, 1024);
-            uint64_t bd = p.b_mn ? smem_desc(sb + k * 2048, 64 * BK * 2, 1024) : smem_desc(sb + k * 32, 16, 1024);
-            umma_f16(tmem_d, ad, bd, idesc, (kb | k) ? 1u : 0u);
-          }
+        if (dbg && lane == 0 && kb < 4 && t == blockIdx.x) p.dbg[8 + kb] = clock64();   // arrival of the first k-blocks
+        const uint32_t a_lo = a_lo0 + (uint32_t)stage * stage_units, b_lo = b_lo0 + (uint32_t)stage * stage_units;
+        if (elect_one()) {
+          umma_f16(tmem_d, desc64(a_lo, hi), desc64(b_lo, hi), idesc, kb ? 1u : 0u);
+          umma_f16(tmem_d, desc64(a_lo + a_step, hi), desc64(b_lo + b_step, hi), idesc, 1u);
+          umma_f16(tmem_d, desc64(a_lo + 2 * a_step, hi), desc64(b_lo + 2 * b_step, hi), idesc, 1u);
+          umma_f16(tmem_d, desc64(a_lo + 3 * a_step, hi), desc64(b_lo + 3 * b_step, hi), idesc, 1u);
           umma_commit(empty + stage);                 // smem stage reusable once these MMAs retire
           if (kb == kblocks - 1) umma_commit(tfull + acc);  // accumulator complete
+          if (dbg && kb < 4 && t == blockIdx.x) p.dbg[12 + kb] = clock64();   // MMAs of this k-block issued
         }
         __syncwarp();
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (dbg && lane == 0) p.dbg[3] = clock64();   // MMA issue done
   } else {
     // ------------------------------------------------ epilogue warps (TMEM lane quarter = warp % 4)
     const int q = warp & 3;
@@ -186,17 +228,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
       int tm = (int)(r % p.tiles_m); r /= p.tiles_m; int tn = (int)(r % p.tiles_n); int b = (int)(r / p.tiles_n);
       mbar_wait(tfull + acc, acc_phase);
       tc_fence_after();
+      if (dbg && warp == 2 && lane == 0 && t == blockIdx.x) p.dbg[4] = clock64();   // first accumulator ready
       const int m = tm * BM + q * 32 + lane;
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.BN);
       for (int c0 = 0; c0 < p.BN; c0 += 16) {
         float v[16];
         tmem_ld16(trow + c0, v);
         int n0 = tn * p.BN + c0;
-        if (m < p.M) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (n0 + j < p.N) ep(b, m, n0 + j, v[j]);
-        }
+        if (m < p.M && n0 < p.N) ep_seg16(ep, b, m, n0, v, min(16, p.N - n0));
       }
       tc_fence_before();
       __syncwarp();
@@ -206,6 +245,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
   }
   tc_fence_before();
   __syncthreads();
+  if (dbg && threadIdx.x == 0) p.dbg[5] = clock64();
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
@@ -251,6 +291,7 @@ static int make_map(CUtensorMap* map, const Operand& op, long extent_o, long ext
   return 0;
 }
 
+static long long* g_dbg = nullptr;   // set by b200_test_set_debug_buffer
 static int g_num_sms = 0;
 static inline int num_sms() {
   if (!g_num_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev); if (g_num_sms <= 0) g_num_sms = 148; }
@@ -278,18 +319,28 @@ static int gemm(const Operand& A, const Operand& B, const EP& ep, int M, int N, 
   CUtensorMap ma, mb;
   B200_TRY(make_map(&ma, A, M, K, BM, nb0, nb1));
   B200_TRY(make_map(&mb, B, N, K, p.BN, nb0, nb1));
-  size_t smem = (size_t)p.stages * stage_bytes + 1024 + 256;
   static bool attr_done = false;  // per EP instantiation
-  if (!attr_done) { B200_CUDA(cudaFuncSetAttribute(gemm_kernel<EP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr_done = true; }
+  if (!attr_done) {
+    B200_CUDA(cudaFuncSetAttribute(gemm_kernel<EP, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    B200_CUDA(cudaFuncSetAttribute(gemm_kernel<EP, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    B200_CUDA(cudaFuncSetAttribute(gemm_kernel<EP, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    B200_CUDA(cudaFuncSetAttribute(gemm_kernel<EP, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_done = true;
+  }
+  p.dbg = g_dbg;
+  if (const char* e = getenv("B200_GEMM_BN")) { int v = atoi(e); if (v == 64 || v == 128 || v == 256) { p.BN = v; p.tiles_n = cdiv(N, p.BN); stage_bytes = BM * BK * 2 + p.BN * BK * 2; p.stages = (int)((200 * 1024) / stage_bytes); if (p.stages > 8) p.stages = 8; p.tmem_cols = p.BN * 2; } }
+  if (const char* e = getenv("B200_GEMM_STAGES")) { int v = atoi(e); if (v >= 1 && v <= p.stages) p.stages = v; }
   p.ksplit = 1; p.kb_per_split = cdiv(K, BK);
   if (allow_splitk) {
     long base_tiles = (long)p.tiles_m * p.tiles_n * p.batches; int kbs = cdiv(K, BK);
     long want = num_sms() / base_tiles; if (want > kbs / 4) want = kbs / 4; if (want < 1) want = 1;
     p.kb_per_split = cdiv(kbs, (int)want); p.ksplit = cdiv(kbs, p.kb_per_split);
   }
+  size_t smem = (size_t)p.stages * stage_bytes + 1024 + 256;
   long tiles = (long)p.tiles_m * p.tiles_n * p.batches * p.ksplit;
   int grid = (int)(tiles < num_sms() ? tiles : num_sms());
-  gemm_kernel<EP><<<grid, 192, smem, st>>>(ma, mb, p, ep);
+  if (p.a_mn) { if (p.b_mn) gemm_kernel<EP, true, true><<<grid, 192, smem, st>>>(ma, mb, p, ep); else gemm_kernel<EP, true, false><<<grid, 192, smem, st>>>(ma, mb, p, ep); }
+  else { if (p.b_mn) gemm_kernel<EP, false, true><<<grid, 192, smem, st>>>(ma, mb, p, ep); else gemm_kernel<EP, false, false><<<grid, 192, smem, st>>>(ma, mb, p, ep); }
   B200_LAUNCH_CHECK();
   return 0;
 }

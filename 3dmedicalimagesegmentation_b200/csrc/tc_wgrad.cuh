@@ -72,59 +72,72 @@ wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ 
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0; int bb = 0; uint32_t bphase = 0;
-      for (long t = vs; t < p.total_tiles; t += p.vsplit) {
-        int tw = (int)(t % p.tiles_w); long r = t / p.tiles_w; int th = (int)(r % p.tiles_h); r /= p.tiles_h;
-        int td = (int)(r % p.tiles_d); int n = (int)(r / p.tiles_d);
-        mbar_wait(bempty + bb, bphase ^ 1);
+    // ---- TMA producer: warp-uniform loop, one elected lane issues
+    int stage = 0; uint32_t phase = 0; int bb = 0; uint32_t bphase = 0;
+    const uint32_t smem_a_u = smem_u32(smem), smem_b_u = smem_u32(smem_b);
+    for (long t = vs; t < p.total_tiles; t += p.vsplit) {
+      int tw = (int)(t % p.tiles_w); long r = t / p.tiles_w; int th = (int)(r % p.tiles_h); r /= p.tiles_h;
+      int td = (int)(r % p.tiles_d); int n = (int)(r / p.tiles_d);
+      const int w0 = tw * TW, h0 = th * TH, d0 = td * TD;
+      mbar_wait(bempty + bb, bphase ^ 1);
+      if (elect_one()) {
         mbar_expect_tx(bfull + bb, b_bytes);
         for (int c = 0; c < p.b_chunks; ++c)
-          tma_load_5d(smem_u32(smem_b + (size_t)bb * b_bytes + (size_t)c * p.b_chunk_bytes), &map_dy, bfull + bb, c * p.b_ch, tw * TW, th * TH, td * TD, n);
-        if (++bb == 2) { bb = 0; bphase ^= 1; }
-        for (int mt = mt0; mt < mt1; ++mt) {
-          int a0 = mt * p.atoms_per_tile, cnt = min(p.atoms_per_tile, p.total_atoms - a0);
-          mbar_wait(aempty + stage, phase ^ 1);
-          mbar_expect_tx(afull + stage, (uint32_t)cnt * p.a_atom_bytes);
-          uint32_t base = smem_u32(smem + (size_t)stage * a_stage_bytes);
-          for (int i = 0; i < cnt; ++i) {
-            int a = a0 + i, tap = a / p.atoms_per_tap, ch = a - tap * p.atoms_per_tap;
-            int kw = tap % p.ks, kh = (tap / p.ks) % p.ks, kd = tap / (p.ks * p.ks);
-            tma_load_5d(base + i * p.a_atom_bytes, &map_x, afull + stage, ch * p.atom_ch, tw * TW + kw - pad, th * TH + kh - pad, td * TD + kd - pad, n);
-          }
-          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          tma_load_5d(smem_b_u + (uint32_t)bb * b_bytes + (uint32_t)c * p.b_chunk_bytes, &map_dy, bfull + bb, c * p.b_ch, w0, h0, d0, n);
+      }
+      __syncwarp();
+      if (++bb == 2) { bb = 0; bphase ^= 1; }
+      // running atom state: atom a = tap*atoms_per_tap + ch, starting at the first atom of this CTA's M-tiles
+      int a = mt0 * p.atoms_per_tile;
+      int tap = a / p.atoms_per_tap, ch = a - tap * p.atoms_per_tap;
+      int kw = tap % p.ks, kh = (tap / p.ks) % p.ks, kd = tap / (p.ks * p.ks);
+      for (int mt = mt0; mt < mt1; ++mt) {
+        const int cnt = min(p.atoms_per_tile, p.total_atoms - mt * p.atoms_per_tile);
+        mbar_wait(aempty + stage, phase ^ 1);
+        const uint32_t base = smem_a_u + (uint32_t)stage * a_stage_bytes;
+        const bool leader = elect_one();
+        if (leader) mbar_expect_tx(afull + stage, (uint32_t)cnt * p.a_atom_bytes);
+        for (int i = 0; i < cnt; ++i) {
+          if (leader) tma_load_5d(base + i * p.a_atom_bytes, &map_x, afull + stage, ch * p.atom_ch, w0 + kw - pad, h0 + kh - pad, d0 + kd - pad, n);
+          if (++ch == p.atoms_per_tap) { ch = 0; if (++kw == p.ks) { kw = 0; if (++kh == p.ks) { kh = 0; ++kd; } } }
         }
+        __syncwarp();
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
-    // both operands MN-major (bits 15, 16)
+    // ---- MMA issuer; both operands MN-major (bits 15, 16)
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(p.Co >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-    int stage = 0; uint32_t phase = 0; int bb = 0; uint32_t bphase = 0; bool first = true;
+    auto layout_of = [](int rb) { return rb == 128 ? 2u : (rb == 64 ? 4u : 6u); };
+    const uint32_t a_hi = desc_hi(8 * p.a_row_bytes, layout_of(p.a_row_bytes)), b_hi = desc_hi(8 * p.b_row_bytes, layout_of(p.b_row_bytes));
+    const uint32_t a_lo0 = desc_lo(smem_u32(smem), p.a_atom_bytes), b_lo0 = desc_lo(smem_u32(smem_b), p.b_chunk_bytes);
+    const uint32_t a_kstep = (16u * p.a_row_bytes) >> 4, b_kstep = (16u * p.b_row_bytes) >> 4;   // 16 voxels per MMA
+    const uint32_t a_stage_units = a_stage_bytes >> 4, b_units = b_bytes >> 4;
+    int stage = 0; uint32_t phase = 0; int bb = 0; uint32_t bphase = 0; uint32_t accum = 0;
     for (long t = vs; t < p.total_tiles; t += p.vsplit) {
       mbar_wait(bfull + bb, bphase);
       tc_fence_after();
-      uint32_t sb = smem_u32(smem_b + (size_t)bb * b_bytes);
+      const uint32_t b_lo = b_lo0 + (uint32_t)bb * b_units;
       for (int mt = mt0; mt < mt1; ++mt) {
         mbar_wait(afull + stage, phase);
         tc_fence_after();
-        if (lane == 0) {
-          uint32_t sa = smem_u32(smem + (size_t)stage * a_stage_bytes);
-          uint32_t tmem_d = tmem_base + (uint32_t)((mt - mt0) * p.Co);
+        const uint32_t a_lo = a_lo0 + (uint32_t)stage * a_stage_units;
+        const uint32_t tmem_d = tmem_base + (uint32_t)((mt - mt0) * p.Co);
+        if (elect_one()) {
 #pragma unroll
           for (int j = 0; j < 8; ++j)   // 8 x 16 voxels = one brick
-            umma_f16(tmem_d, smem_desc_mn(sa + j * 16 * p.a_row_bytes, p.a_atom_bytes, p.a_row_bytes),
-                     smem_desc_mn(sb + j * 16 * p.b_row_bytes, p.b_chunk_bytes, p.b_row_bytes), idesc, (first && j == 0) ? 0u : 1u);
+            umma_f16(tmem_d, desc64(a_lo + j * a_kstep, a_hi), desc64(b_lo + j * b_kstep, b_hi), idesc, (j == 0) ? accum : 1u);
           umma_commit(aempty + stage);
         }
         __syncwarp();
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
-      if (lane == 0) umma_commit(bempty + bb);
+      if (elect_one()) umma_commit(bempty + bb);
       __syncwarp();
       if (++bb == 2) { bb = 0; bphase ^= 1; }
-      first = false;
+      accum = 1u;
     }
-    if (lane == 0) umma_commit(done);
+    if (elect_one()) umma_commit(done);
     __syncwarp();
   } else {
     const int q = warp & 3;

@@ -100,6 +100,8 @@ int b200_test_tc_conv(const void* x, int in_pitch, int in_coff, int Ci, int N, i
                       void* out, int out_pitch, int out_coff, int accumulate, int dgrad, double* stats, void* scratch, void* stream);
 int b200_test_tc_wgrad(const void* x, int x_pitch, int x_coff, int Ci, const void* dy, int dy_pitch, int dy_coff, int Co, int N, int D, int H,
                        int W, int ks, float* dW, void* stream);
+/* tuning aid: 16 x int64 device buffer receiving CTA-0 clock64 phase stamps of the next tcgen05 GEMM launches (NULL = off) */
+void b200_test_set_debug_buffer(void* dev_ptr);
 int b200_test_tc_gemm(const void* a, const void* b, float* out, int M, int N, int K, int a_mn, int b_mn, void* stream);
 
 #ifdef __cplusplus
