@@ -1,0 +1,252 @@
+// Kernels for the two "edge" layers whose channel counts are too small for tensor cores:
+//   * encoder1's convolutions on the raw input volume (C_in = 1..4; unetr.py:90-98): conv1 3x3x3 and the conv3 1x1x1
+//     residual projection computed together, straight from the NCDHW fp32 input (no bf16 rounding of the image),
+//     with the InstanceNorm sums fused; and their weight gradients;
+//   * the segmentation head (UnetOutBlock 1x1x1 + bias, unetr.py:175) fused with the last InstanceNorm/LeakyReLU/residual
+//     pass, so logits are formed from fp32 activations, and its backward.
+// All HBM-bound; one thread per voxel, coalesced along W, 16-byte channel-row accesses.
+#pragma once
+#include "elementwise.cuh"
+
+namespace b200 {
+
+// ---------------------------------------------------------------------------------------------- encoder1 forward
+// c1[v,co] = sum_{ci,tap} x[ci, v+tap-1] W1[co][ci][tap] ; c3[v,co] = sum_ci x[ci,v] W3[co][ci]
+// stats1/stats3: double [N][CO][2] (sum, sumsq), zeroed by the caller.
+template <class T, int CO>
+__global__ void __launch_bounds__(256) conv_in_fwd_kernel(const float* __restrict__ x, const float* __restrict__ W1, const float* __restrict__ W3,
+                                                          int Cin, int D, int H, int W, T* __restrict__ c1, T* __restrict__ c3,
+                                                          double* __restrict__ stats1, double* __restrict__ stats3) {
+  extern __shared__ float sw[];   // W1 as [ci][tap][CO], then W3 as [ci][CO]
+  __shared__ float red[8][4 * CO];
+  const long V = (long)D * H * W;
+  const int n = blockIdx.y;
+  for (int i = threadIdx.x; i < Cin * 27 * CO; i += 256) { int co = i % CO, r = i / CO, tap = r % 27, ci = r / 27; sw[i] = W1[((long)co * Cin + ci) * 27 + tap]; }
+  for (int i = threadIdx.x; i < Cin * CO; i += 256) { int co = i % CO, ci = i / CO; sw[Cin * 27 * CO + i] = W3[(long)co * Cin + ci]; }
+  __syncthreads();
+  const float* w3 = sw + Cin * 27 * CO;
+  float s1[CO], q1[CO], s3[CO], q3[CO];
+#pragma unroll
+  for (int c = 0; c < CO; ++c) s1[c] = q1[c] = s3[c] = q3[c] = 0.f;
+  for (long v = (long)blockIdx.x * 256 + threadIdx.x; v < V; v += (long)gridDim.x * 256) {
+    int w = (int)(v % W); long t = v / W; int h = (int)(t % H); int d = (int)(t / H);
+    float a1[CO], a3[CO];
+#pragma unroll
+    for (int c = 0; c < CO; ++c) a1[c] = a3[c] = 0.f;
+    for (int ci = 0; ci < Cin; ++ci) {
+      const float* xc = x + ((long)n * Cin + ci) * V;
+      const float* wc = sw + ci * 27 * CO;
+#pragma unroll
+      for (int kd = 0; kd < 3; ++kd) {
+        int dd = d + kd - 1;
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh) {
+          int hh = h + kh - 1;
+          bool ok = (unsigned)dd < (unsigned)D && (unsigned)hh < (unsigned)H;
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw) {
+            int ww = w + kw - 1;
+            float xv = (ok && (unsigned)ww < (unsigned)W) ? xc[((long)dd * H + hh) * W + ww] : 0.f;
+            const float* wt = wc + ((kd * 3 + kh) * 3 + kw) * CO;
+#pragma unroll
+            for (int c = 0; c < CO; ++c) a1[c] = fmaf(xv, wt[c], a1[c]);
+            if (kd == 1 && kh == 1 && kw == 1) {
+#pragma unroll
+              for (int c = 0; c < CO; ++c) a3[c] = fmaf(xv, w3[ci * CO + c], a3[c]);
+            }
+          }
+        }
+      }
+    }
+    constexpr int VN = Vec16<T>::N;
+    T* o1 = c1 + ((long)n * V + v) * CO; T* o3 = c3 + ((long)n * V + v) * CO;
+#pragma unroll
+    for (int c0 = 0; c0 < CO; c0 += VN) {
+      Vec16<T> p, r;
+#pragma unroll
+      for (int i = 0; i < VN; ++i) { p.v[i] = a1[c0 + i]; r.v[i] = a3[c0 + i]; }
+      p.store(o1 + c0); r.store(o3 + c0);
+    }
+#pragma unroll
+    for (int c = 0; c < CO; ++c) { s1[c] += a1[c]; q1[c] += a1[c] * a1[c]; s3[c] += a3[c]; q3[c] += a3[c] * a3[c]; }
+  }
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+#pragma unroll
+  for (int c = 0; c < CO; ++c) {
+    float a = warp_sum(s1[c]), b = warp_sum(q1[c]), e = warp_sum(s3[c]), f = warp_sum(q3[c]);
+    if (lane == 0) { red[wp][c] = a; red[wp][CO + c] = b; red[wp][2 * CO + c] = e; red[wp][3 * CO + c] = f; }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 4 * CO; i += 256) {
+    double tot = 0.0;
+    for (int k = 0; k < 8; ++k) tot += red[k][i];
+    int which = i / CO, c = i % CO;
+    double* dst = (which < 2 ? stats1 : stats3) + ((long)n * CO + c) * 2 + (which & 1);
+    atomicAdd(dst, tot);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- encoder1 weight gradients
+// dW1[co][ci][tap] += sum_v dc1[v,co] x[ci,v+tap-1] ; dW3[co][ci] += sum_v dc3[v,co] x[ci,v]     (outputs zeroed by the caller)
+// grid (voxel chunks, N, Cin); 8 warps, warp w owns taps {w, w+8, w+16, w+24<27}; warp 7's 4th slot does the 1x1 conv3.
+template <class T, int CO>
+__global__ void __launch_bounds__(256) conv_in_wgrad_kernel(const float* __restrict__ x, const T* __restrict__ dc1, const T* __restrict__ dc3,
+                                                            int Cin, int D, int H, int W, long chunk, float* __restrict__ dW1, float* __restrict__ dW3) {
+  const long V = (long)D * H * W;
+  const int n = blockIdx.y, ci = blockIdx.z;
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+  const float* xc = x + ((long)n * Cin + ci) * V;
+  float acc[4][CO];
+#pragma unroll
+  for (int s = 0; s < 4; ++s)
+#pragma unroll
+    for (int c = 0; c < CO; ++c) acc[s][c] = 0.f;
+  const long v0 = (long)blockIdx.x * chunk, v1 = min(V, v0 + chunk);
+  constexpr int VN = Vec16<T>::N;
+  for (long v = v0 + lane; v < v1; v += 32) {
+    int w = (int)(v % W); long t = v / W; int h = (int)(t % H); int d = (int)(t / H);
+    float g[CO], g3[CO];
+    const T* r1 = dc1 + ((long)n * V + v) * CO;
+#pragma unroll
+    for (int c0 = 0; c0 < CO; c0 += VN) { Vec16<T> p; p.load(r1 + c0);
+#pragma unroll
+      for (int i = 0; i < VN; ++i) g[c0 + i] = p.v[i]; }
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      int tap = wp + 8 * s;
+      if (tap < 27) {
+        int kw = tap % 3, kh = (tap / 3) % 3, kd = tap / 9;
+        int dd = d + kd - 1, hh = h + kh - 1, ww = w + kw - 1;
+        float xv = ((unsigned)dd < (unsigned)D && (unsigned)hh < (unsigned)H && (unsigned)ww < (unsigned)W) ? xc[((long)dd * H + hh) * W + ww] : 0.f;
+#pragma unroll
+        for (int c = 0; c < CO; ++c) acc[s][c] = fmaf(xv, g[c], acc[s][c]);
+      } else if (wp == 7 && s == 3) {   // tap slot 31 is free: use it for conv3 (1x1x1)
+        const T* r3 = dc3 + ((long)n * V + v) * CO;
+#pragma unroll
+        for (int c0 = 0; c0 < CO; c0 += VN) { Vec16<T> p; p.load(r3 + c0);
+#pragma unroll
+          for (int i = 0; i < VN; ++i) g3[c0 + i] = p.v[i]; }
+        float xv = xc[v];
+#pragma unroll
+        for (int c = 0; c < CO; ++c) acc[s][c] = fmaf(xv, g3[c], acc[s][c]);
+      }
+    }
+  }
+#pragma unroll
+  for (int s = 0; s < 4; ++s) {
+    int tap = wp + 8 * s;
+    bool is3 = (wp == 7 && s == 3);
+    if (tap >= 27 && !is3) continue;
+#pragma unroll
+    for (int c = 0; c < CO; ++c) {
+      float tot = warp_sum(acc[s][c]);
+      if (lane == 0) {
+        if (is3) atomicAdd(dW3 + (long)c * Cin + ci, tot);
+        else atomicAdd(dW1 + ((long)c * Cin + ci) * 27 + tap, tot);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- fused last norm pass + head
+// d0[v,c] = lrelu(norm(c2)[v,c] + norm(c3)[v,c]) (stored as T for the backward), logits[n][k][v] = sum_c d0_fp32[c] Wh[k][c] + bh[k]
+template <class T, int CO>
+__global__ void __launch_bounds__(256) in_apply_head_kernel(const T* __restrict__ c2, const float* __restrict__ mr2, const T* __restrict__ c3,
+                                                            const float* __restrict__ mr3, T* __restrict__ d0, const float* __restrict__ Wh,
+                                                            const float* __restrict__ bh, int ncls, long V, float* __restrict__ logits) {
+  __shared__ float sW[32 * CO], sb[32], sm[4 * CO];
+  const int n = blockIdx.y;
+  for (int i = threadIdx.x; i < ncls * CO; i += 256) sW[i] = Wh[i];
+  if (threadIdx.x < ncls) sb[threadIdx.x] = bh[threadIdx.x];
+  for (int i = threadIdx.x; i < 2 * CO; i += 256) { sm[i] = mr2[(long)n * CO * 2 + i]; sm[2 * CO + i] = mr3[(long)n * CO * 2 + i]; }
+  __syncthreads();
+  constexpr int VN = Vec16<T>::N;
+  for (long v = (long)blockIdx.x * 256 + threadIdx.x; v < V; v += (long)gridDim.x * 256) {
+    const long row = ((long)n * V + v) * CO;
+    float o[CO];
+#pragma unroll
+    for (int c0 = 0; c0 < CO; c0 += VN) {
+      Vec16<T> a, b, r; a.load(c2 + row + c0); b.load(c3 + row + c0);
+#pragma unroll
+      for (int i = 0; i < VN; ++i) {
+        int c = c0 + i;
+        float val = lrelu((a.v[i] - sm[2 * c]) * sm[2 * c + 1] + (b.v[i] - sm[2 * CO + 2 * c]) * sm[2 * CO + 2 * c + 1]);
+        o[c] = val; r.v[i] = val;
+      }
+      r.store(d0 + row + c0);
+    }
+    for (int k = 0; k < ncls; ++k) {
+      float acc = sb[k];
+#pragma unroll
+      for (int c = 0; c < CO; ++c) acc = fmaf(o[c], sW[k * CO + c], acc);
+      logits[((long)n * ncls + k) * V + v] = acc;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- head backward
+// g[v,c] = sum_k dlogits[n][k][v] Wh[k][c] (stored T, channels-last); dWh[k][c] += sum_v dlogits d0 ; dbh[k] += sum_v dlogits
+// block = 256 threads over 256 voxels per iteration; (k,c) pairs are owned by threads for the outer-product sums.
+template <class T, int CO>
+__global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__ dlogits, const T* __restrict__ d0, const float* __restrict__ Wh,
+                                                       int ncls, long V, long chunk, T* __restrict__ g, float* __restrict__ dWh, float* __restrict__ dbh) {
+  extern __shared__ float hsm[];
+  float* sW = hsm;                                            // [ncls][CO]
+  float (*sdl)[257] = reinterpret_cast<float (*)[257]>(hsm + ncls * CO);          // [k][voxel]
+  float (*sd0)[CO + 1] = reinterpret_cast<float (*)[CO + 1]>(hsm + ncls * CO + ncls * 257);  // [voxel][c]
+  const int n = blockIdx.y;
+  for (int i = threadIdx.x; i < ncls * CO; i += 256) sW[i] = Wh[i];
+  __syncthreads();
+  const int pairs = ncls * CO;
+  float accw[4] = {0.f, 0.f, 0.f, 0.f};   // up to 1024 (k,c) pairs: four per thread
+  float accb = 0.f;
+  constexpr int VN = Vec16<T>::N;
+  const long v0 = (long)blockIdx.x * chunk, v1 = min(V, v0 + chunk);
+  for (long vb = v0; vb < v1; vb += 256) {
+    long v = vb + threadIdx.x;
+    bool ok = v < v1;
+    float dl[32];
+    for (int k = 0; k < ncls; ++k) { dl[k] = ok ? dlogits[((long)n * ncls + k) * V + v] : 0.f; sdl[k][threadIdx.x] = dl[k]; }
+    if (ok) {
+      const long row = ((long)n * V + v) * CO;
+#pragma unroll
+      for (int c0 = 0; c0 < CO; c0 += VN) {
+        Vec16<T> a, o; a.load(d0 + row + c0);
+#pragma unroll
+        for (int i = 0; i < VN; ++i) {
+          sd0[threadIdx.x][c0 + i] = a.v[i];
+          float s = 0.f;
+          for (int k = 0; k < ncls; ++k) s = fmaf(dl[k], sW[k * CO + c0 + i], s);
+          o.v[i] = s;
+        }
+        o.store(g + row + c0);
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < CO; ++c) sd0[threadIdx.x][c] = 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      int pi = threadIdx.x + 256 * s;
+      if (pi < pairs) {
+        int k = pi / CO, c = pi % CO;
+        float a = 0.f;
+#pragma unroll 8
+        for (int j = 0; j < 256; ++j) a = fmaf(sdl[k][j], sd0[j][c], a);
+        accw[s] += a;
+      }
+    }
+    if (threadIdx.x < ncls) { float a = 0.f; for (int j = 0; j < 256; ++j) a += sdl[threadIdx.x][j]; accb += a; }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int s = 0; s < 4; ++s) { int pi = threadIdx.x + 256 * s; if (pi < pairs && dWh) atomicAdd(dWh + pi, accw[s]); }
+  if (threadIdx.x < ncls && dbh) atomicAdd(dbh + threadIdx.x, accb);
+}
+
+}  // namespace b200
+
+namespace b200 {
+static inline size_t head_bwd_smem(int ncls, int CO) { return sizeof(float) * ((size_t)ncls * CO + (size_t)ncls * 257 + 256 * (size_t)(CO + 1)); }
+}

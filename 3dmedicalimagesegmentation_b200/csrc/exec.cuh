@@ -11,6 +11,7 @@
 #include <type_traits>
 
 #include "ops.cuh"
+#include "edge_kernels.cuh"
 #include "tc_gemm.cuh"
 #include "tc_conv.cuh"
 #include "tc_wgrad.cuh"
@@ -145,7 +146,7 @@ struct Exec {
       w.rs[i].a1 = b.take<T>(n); w.rs[i].c2 = b.take<T>(n); w.rs[i].c3 = b.take<T>(n);
       w.rs[i].mr1 = b.take<float>(2 * B * co[i]); w.rs[i].mr2 = b.take<float>(2 * B * co[i]); w.rs[i].mr3 = b.take<float>(2 * B * co[i]);
     }
-    w.stat_acc = b.take<double>((size_t)2 * B * 8 * fs);
+    w.stat_acc = b.take<double>((size_t)4 * B * 8 * fs);   // two (sum, sumsq) accumulators
     if (kTC) {
       for (int i = 0; i < 12; ++i) {
         w.wqkv[i] = b.take<bf16>((size_t)3 * H * H); w.wproj[i] = b.take<bf16>((size_t)H * H);
@@ -293,10 +294,35 @@ struct Exec {
     return simt_conv_wgrad<T>(x, dy, s, ks, dW, st);
   }
 
-  int res_fwd(Cl<const T> x, int level, const float* W1, const float* W2, const float* W3, ResSave<T>& r, Cl<T> out, cudaStream_t st) {
+  struct HeadArgs { const float* Wh; const float* bh; float* logits; };
+  static bool edge_co_ok(int co) { return co == 8 || co == 16 || co == 32; }
+
+  // raw != null: the block input is the NCDHW fp32 network input (encoder1) and conv1/conv3 run in the dedicated kernel.
+  // head != null: the last normalise pass also emits the 1x1x1 head's logits (decoder2).
+  int res_fwd(Cl<const T> x, int level, const float* W1, const float* W2, const float* W3, ResSave<T>& r, Cl<T> out, cudaStream_t st,
+              const float* raw = nullptr, const HeadArgs* head = nullptr) {
     Sp s = sp(level); long Vs = V[level]; int Co = out.C;
     Cl<T> c1 = cl(w.c1tmp, Co, 0, Co), a1 = cl(r.a1, Co, 0, Co), c2 = cl(r.c2, Co, 0, Co), c3 = cl(r.c3, Co, 0, Co);
     bool done = false;
+    if (raw) {
+      double* st3 = w.stat_acc + (size_t)2 * c.B * 8 * c.fs;
+      { B200_PROF("enc1_conv_fwd", st);
+        B200_CUDA(cudaMemsetAsync(w.stat_acc, 0, sizeof(double) * 4 * c.B * 8 * c.fs, st));
+        dim3 g((unsigned)min(148L * 4, (Vs + 255) / 256), c.B);
+        size_t sm = sizeof(float) * ((size_t)c.Cin * 27 * Co + (size_t)c.Cin * Co);
+        if (Co == 8) conv_in_fwd_kernel<T, 8><<<g, 256, sm, st>>>(raw, W1, W3, c.Cin, s.D, s.H, s.W, c1.p, c3.p, w.stat_acc, st3);
+        else if (Co == 16) conv_in_fwd_kernel<T, 16><<<g, 256, sm, st>>>(raw, W1, W3, c.Cin, s.D, s.H, s.W, c1.p, c3.p, w.stat_acc, st3);
+        else conv_in_fwd_kernel<T, 32><<<g, 256, sm, st>>>(raw, W1, W3, c.Cin, s.D, s.H, s.W, c1.p, c3.p, w.stat_acc, st3);
+        B200_LAUNCH_CHECK();
+        in_finalize_kernel<<<cdiv(c.B * Co, 128), 128, 0, st>>>(w.stat_acc, r.mr1, c.B * Co, 1.0 / (double)Vs); B200_LAUNCH_CHECK();
+        in_finalize_kernel<<<cdiv(c.B * Co, 128), 128, 0, st>>>(st3, r.mr3, c.B * Co, 1.0 / (double)Vs); B200_LAUNCH_CHECK();
+      }
+      B200_TRY(in_apply(cl<const T>(c1.p, Co, 0, Co), r.mr1, nullptr, nullptr, a1, Vs, st));
+      B200_TRY(conv_fwd(cl<const T>(a1.p, Co, 0, Co), s, W2, Co, 3, c2, w.stat_acc, &done, st));
+      B200_TRY(in_stats(cl<const T>(c2.p, Co, 0, Co), Vs, r.mr2, st, done));
+      B200_TRY(in_apply(cl<const T>(c2.p, Co, 0, Co), r.mr2, c3.p, r.mr3, out, Vs, st));
+      return 0;
+    }
     B200_TRY(conv_fwd(x, s, W1, Co, 3, c1, w.stat_acc, &done, st));
     B200_TRY(in_stats(cl<const T>(c1.p, Co, 0, Co), Vs, r.mr1, st, done));
     B200_TRY(in_apply(cl<const T>(c1.p, Co, 0, Co), r.mr1, nullptr, nullptr, a1, Vs, st));
@@ -304,13 +330,22 @@ struct Exec {
     B200_TRY(in_stats(cl<const T>(c2.p, Co, 0, Co), Vs, r.mr2, st, done));
     B200_TRY(conv_fwd(x, s, W3, Co, 1, c3, w.stat_acc, &done, st));
     B200_TRY(in_stats(cl<const T>(c3.p, Co, 0, Co), Vs, r.mr3, st, done));
+    if (head && out.pitch == Co && out.coff == 0) {
+      B200_PROF("norm_head_fwd", st);
+      dim3 g((unsigned)min(148L * 4, (Vs + 255) / 256), c.B);
+      if (Co == 8) in_apply_head_kernel<T, 8><<<g, 256, 0, st>>>(c2.p, r.mr2, c3.p, r.mr3, out.p, head->Wh, head->bh, c.ncls, Vs, head->logits);
+      else if (Co == 16) in_apply_head_kernel<T, 16><<<g, 256, 0, st>>>(c2.p, r.mr2, c3.p, r.mr3, out.p, head->Wh, head->bh, c.ncls, Vs, head->logits);
+      else in_apply_head_kernel<T, 32><<<g, 256, 0, st>>>(c2.p, r.mr2, c3.p, r.mr3, out.p, head->Wh, head->bh, c.ncls, Vs, head->logits);
+      B200_LAUNCH_CHECK();
+      return 0;
+    }
     B200_TRY(in_apply(cl<const T>(c2.p, Co, 0, Co), r.mr2, c3.p, r.mr3, out, Vs, st));
     return 0;
   }
   // dOut: gradient wrt block output; out: the block's forward output.  Writes dW1..3 (if non-null) and, if dx.p, the
   // input gradient (dx = dgrad3(dc1) + dgrad1(dc3)).
   int res_bwd(Cl<const T> x, int level, const float* W1, const float* W2, const float* W3, ResSave<T>& r, Cl<const T> out,
-              Cl<const T> dOut, float* dW1, float* dW2, float* dW3, Cl<T> dx, cudaStream_t st) {
+              Cl<const T> dOut, float* dW1, float* dW2, float* dW3, Cl<T> dx, cudaStream_t st, const float* raw = nullptr) {
     constexpr int VN = Vec16<T>::N;
     Sp s = sp(level); long Vs = V[level]; int Co = out.C, Ci = x.C; int B = c.B;
     ClView pv{Co, 0};
@@ -338,6 +373,19 @@ struct Exec {
                                                w.dc1, pv, nullptr, pv);
     B200_LAUNCH_CHECK(); }
     Cl<const T> dc1 = cl<const T>(w.dc1, Co, 0, Co);
+    if (raw) {   // encoder1: both weight gradients from the raw fp32 input in one dedicated kernel
+      B200_PROF("enc1_conv_wgrad", st);
+      B200_CHECK(dW1 && dW3, "encoder1 weight gradients are produced together");
+      B200_CUDA(cudaMemsetAsync(dW1, 0, sizeof(float) * Co * Ci * 27, st));
+      B200_CUDA(cudaMemsetAsync(dW3, 0, sizeof(float) * Co * Ci, st));
+      long chunk = 4096;
+      dim3 g((unsigned)((Vs + chunk - 1) / chunk), B, Ci);
+      if (Co == 8) conv_in_wgrad_kernel<T, 8><<<g, 256, 0, st>>>(raw, w.dc1, w.dc3, Ci, s.D, s.H, s.W, chunk, dW1, dW3);
+      else if (Co == 16) conv_in_wgrad_kernel<T, 16><<<g, 256, 0, st>>>(raw, w.dc1, w.dc3, Ci, s.D, s.H, s.W, chunk, dW1, dW3);
+      else conv_in_wgrad_kernel<T, 32><<<g, 256, 0, st>>>(raw, w.dc1, w.dc3, Ci, s.D, s.H, s.W, chunk, dW1, dW3);
+      B200_LAUNCH_CHECK();
+      return 0;
+    }
     if (dW1) { B200_CUDA(cudaMemsetAsync(dW1, 0, sizeof(float) * Co * Ci * 27, st)); B200_TRY(conv_wgrad(x, dc1, s, 3, dW1, st)); }
     if (dW3) { B200_CUDA(cudaMemsetAsync(dW3, 0, sizeof(float) * Co * Ci, st)); B200_TRY(conv_wgrad(x, dc3, s, 1, dW3, st)); }
     if (dx.p) {
@@ -387,8 +435,10 @@ struct Exec {
     for (int k = 0; k < 3; ++k) B200_TRY(launch_cast<float, T>(w.hs[3 + 3 * k], w.hsT[k], (long)M * H, st));
 
     // --- encoder1 on the input volume (a9) -> upper half of concat2
-    B200_TRY(launch_layout<T>(x_in, nullptr, w.xcl, B, c.Cin, V[0], c.Cin, 0, 0, 0, st));
-    B200_TRY(res_fwd(cl<const T>(w.xcl, c.Cin, 0, c.Cin), 0, P[P_E1_C1], P[P_E1_C2], P[P_E1_C3], w.rs[0], cl(w.cat2, 2 * fs, fs, fs), st));
+    const bool edge = edge_co_ok(fs);   // dedicated small-channel kernels (fp32 input, fused head) available for this feature_size
+    if (!edge) B200_TRY(launch_layout<T>(x_in, nullptr, w.xcl, B, c.Cin, V[0], c.Cin, 0, 0, 0, st));
+    B200_TRY(res_fwd(cl<const T>(w.xcl, c.Cin, 0, c.Cin), 0, P[P_E1_C1], P[P_E1_C2], P[P_E1_C3], w.rs[0], cl(w.cat2, 2 * fs, fs, fs), st,
+                     edge ? x_in : nullptr));
     // --- encoder2..4: transposed-conv pyramids from hidden states 3/6/9 (a10)
     B200_TRY(convT_fwd(w.hsT[0], H, H, 4, P[P_E2_T0], cl(w.e2a, 2 * fs, 0, 2 * fs), st));
     B200_TRY(convT_fwd(w.e2a, 2 * fs, 2 * fs, 3, P[P_E2_T1], cl(w.e2b, 2 * fs, 0, 2 * fs), st));
@@ -405,9 +455,12 @@ struct Exec {
     B200_TRY(convT_fwd(w.d2, 4 * fs, 4 * fs, 2, P[P_D3_T], cl(w.cat3, 4 * fs, 0, 2 * fs), st));
     B200_TRY(res_fwd(cl<const T>(w.cat3, 4 * fs, 0, 4 * fs), 1, P[P_D3_C1], P[P_D3_C2], P[P_D3_C3], w.rs[3], cl(w.d1, 2 * fs, 0, 2 * fs), st));
     B200_TRY(convT_fwd(w.d1, 2 * fs, 2 * fs, 1, P[P_D2_T], cl(w.cat2, 2 * fs, 0, fs), st));
-    B200_TRY(res_fwd(cl<const T>(w.cat2, 2 * fs, 0, 2 * fs), 0, P[P_D2_C1], P[P_D2_C2], P[P_D2_C3], w.rs[4], cl(w.d0, fs, 0, fs), st));
-    // --- 1x1x1 head with bias, NCDHW fp32 logits (a12)
-    if (logits_out) {
+    HeadArgs head = {P[P_OUT_W], P[P_OUT_B], logits_out};
+    const bool fused_head = edge && logits_out;
+    B200_TRY(res_fwd(cl<const T>(w.cat2, 2 * fs, 0, 2 * fs), 0, P[P_D2_C1], P[P_D2_C2], P[P_D2_C3], w.rs[4], cl(w.d0, fs, 0, fs), st, nullptr,
+                     fused_head ? &head : nullptr));
+    // --- 1x1x1 head with bias, NCDHW fp32 logits (a12) -- normally fused into the pass above
+    if (logits_out && !fused_head) {
       B200_PROF("head_fwd", st);
       EpHeadNcdhw ep = {logits_out, c.ncls, V[0], P[P_OUT_B]};
       B200_TRY(launch_contract(ld2<T, false>(w.d0, fs, 1), ld2<float, false>(P[P_OUT_W], fs, 1), ep, (int)(B * V[0]), c.ncls, fs, 1, 1, st));
@@ -489,7 +542,25 @@ struct Exec {
     if (dec) {
       int rows = (int)(B * V[0]);
       // head: d(d0) = dlogits^T W ; dW = dlogits d0 ; db = sum dlogits
-      { B200_PROF("head_bwd", st);
+      if (edge_co_ok(fs)) {
+        B200_PROF("head_bwd", st);
+        if (G[P_OUT_W]) B200_CUDA(cudaMemsetAsync(G[P_OUT_W], 0, sizeof(float) * c.ncls * fs, st));
+        if (G[P_OUT_B]) B200_CUDA(cudaMemsetAsync(G[P_OUT_B], 0, sizeof(float) * c.ncls, st));
+        long chunk = 2048;
+        dim3 g((unsigned)((V[0] + chunk - 1) / chunk), B);
+        size_t sm = head_bwd_smem(c.ncls, fs);
+        static bool attr = false;
+        if (!attr) {
+          B200_CUDA(cudaFuncSetAttribute(head_bwd_kernel<T, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+          B200_CUDA(cudaFuncSetAttribute(head_bwd_kernel<T, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+          B200_CUDA(cudaFuncSetAttribute(head_bwd_kernel<T, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+          attr = true;
+        }
+        if (fs == 8) head_bwd_kernel<T, 8><<<g, 256, sm, st>>>(d_logits, w.d0, P[P_OUT_W], c.ncls, V[0], chunk, w.gA, G[P_OUT_W], G[P_OUT_B]);
+        else if (fs == 16) head_bwd_kernel<T, 16><<<g, 256, sm, st>>>(d_logits, w.d0, P[P_OUT_W], c.ncls, V[0], chunk, w.gA, G[P_OUT_W], G[P_OUT_B]);
+        else head_bwd_kernel<T, 32><<<g, 256, sm, st>>>(d_logits, w.d0, P[P_OUT_W], c.ncls, V[0], chunk, w.gA, G[P_OUT_W], G[P_OUT_B]);
+        B200_LAUNCH_CHECK();
+      } else { B200_PROF("head_bwd", st);
       { RowIsOuter<NcdhwGather, true> al; al.g = {d_logits, c.ncls, V[0]};
         B200_TRY(launch_contract(al, ld2<float, true>(P[P_OUT_W], 1, fs), ep_plain<T>(w.gA, fs), rows, fs, c.ncls, 1, 1, st)); }
       if (G[P_OUT_W]) {
@@ -509,7 +580,8 @@ struct Exec {
                        cl<const T>(w.gA, fs, 0, fs), G[P_D2_C1], G[P_D2_C2], G[P_D2_C3], cl(w.dcat, 2 * fs, 0, 2 * fs), st));
       if (enc)
         B200_TRY(res_bwd(cl<const T>(w.xcl, c.Cin, 0, c.Cin), 0, P[P_E1_C1], P[P_E1_C2], P[P_E1_C3], w.rs[0], cl<const T>(w.cat2, 2 * fs, fs, fs),
-                         cl<const T>(w.dcat, 2 * fs, fs, fs), G[P_E1_C1], G[P_E1_C2], G[P_E1_C3], cl<T>(nullptr, 0, 0, 0), st));
+                         cl<const T>(w.dcat, 2 * fs, fs, fs), G[P_E1_C1], G[P_E1_C2], G[P_E1_C3], cl<T>(nullptr, 0, 0, 0), st,
+                         (edge_co_ok(fs) && G[P_E1_C1] && G[P_E1_C3]) ? x_in : nullptr));
       B200_TRY(convT_bwd(w.d1, 2 * fs, 2 * fs, 1, P[P_D2_T], cl<const T>(w.dcat, 2 * fs, 0, fs), G[P_D2_T], w.gA, 2 * fs, 0, st));
       // decoder3
       B200_TRY(res_bwd(cl<const T>(w.cat3, 4 * fs, 0, 4 * fs), 1, P[P_D3_C1], P[P_D3_C2], P[P_D3_C3], w.rs[3], cl<const T>(w.d1, 2 * fs, 0, 2 * fs),
