@@ -12,6 +12,7 @@
 #include "loss.cuh"
 #include "sliding.cuh"
 #include "tc_gemm.cuh"
+#include "tc_conv_halo.cuh"
 
 namespace b200 {
 static thread_local char g_err[1024] = "";
@@ -250,9 +251,13 @@ int b200_test_tc_conv(const void* x, int in_pitch, int in_coff, int Ci, int N, i
   B200_LAUNCH_CHECK();
   if (!dgrad) {
     B200_CHECK(tc::conv_supported(Ci, Co, in_pitch, in_coff, out_pitch, out_coff), "shape unsupported by the tcgen05 conv");
+    if (ks == 3 && !getenv("B200_TEST_NO_HALO") && tc::conv_halo_supported(Ci, Co))
+      return tc::conv_halo((const bf16*)x, in_pitch, in_coff, Ci, N, D, H, W, wf, Co, (bf16*)out, out_pitch, out_coff, accumulate, stats, st);
     return tc::conv((const bf16*)x, in_pitch, in_coff, Ci, N, D, H, W, wf, Co, ks, (bf16*)out, out_pitch, out_coff, accumulate, stats, st);
   }
   B200_CHECK(tc::conv_supported(Co, Ci, in_pitch, in_coff, out_pitch, out_coff), "shape unsupported by the tcgen05 conv");
+  if (ks == 3 && !getenv("B200_TEST_NO_HALO") && tc::conv_halo_supported(Co, Ci))
+    return tc::conv_halo((const bf16*)x, in_pitch, in_coff, Co, N, D, H, W, wd, Ci, (bf16*)out, out_pitch, out_coff, accumulate, stats, st);
   return tc::conv((const bf16*)x, in_pitch, in_coff, Co, N, D, H, W, wd, Ci, ks, (bf16*)out, out_pitch, out_coff, accumulate, stats, st);
 }
 

@@ -326,6 +326,7 @@ __global__ void in_stats_kernel(const T* __restrict__ x, ClView xv, int C, long 
   float s[VN], q[VN];
 #pragma unroll
   for (int i = 0; i < VN; ++i) s[i] = q[i] = 0.f;
+#pragma unroll 4
   for (long v = v0 + sub; v < v1; v += nsub) {
     Vec16<T> a; a.load(x + ((long)n * V + v) * xv.pitch + xv.coff + lv * VN);
 #pragma unroll
@@ -371,6 +372,7 @@ __global__ void in_apply_kernel(const T* __restrict__ x, ClView xv, const float*
   int lanes = C / VN;
   int n = blockIdx.y;
   long total = V * lanes;
+#pragma unroll 4
   for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
     long v = e / lanes; int lv = (int)(e % lanes); int c0 = lv * VN;
     Vec16<T> a; a.load(x + ((long)n * V + v) * xv.pitch + xv.coff + c0);
@@ -411,6 +413,7 @@ __global__ void in_bwd_reduce_kernel(const T* __restrict__ dout, ClView dv, cons
   float s0[VN], s1[VN], s2[VN];
 #pragma unroll
   for (int i = 0; i < VN; ++i) s0[i] = s1[i] = s2[i] = 0.f;
+#pragma unroll 4
   for (long v = v0 + sub; v < v1; v += nsub) {
     long base = (long)n * V + v;
     Vec16<T> d, a; d.load(dout + base * dv.pitch + dv.coff + c0); a.load(act + base * av.pitch + av.coff + c0);
@@ -464,6 +467,7 @@ __global__ void in_bwd_apply_kernel(const T* __restrict__ dout, ClView dv, const
   int n = blockIdx.y;
   long total = V * lanes;
   float invV = 1.f / (float)V;
+#pragma unroll 4
   for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
     long v = e / lanes; int lv = (int)(e % lanes); int c0 = lv * VN;
     long base = (long)n * V + v;

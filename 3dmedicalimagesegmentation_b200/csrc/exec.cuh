@@ -14,6 +14,7 @@
 #include "edge_kernels.cuh"
 #include "tc_gemm.cuh"
 #include "tc_conv.cuh"
+#include "tc_conv_halo.cuh"
 #include "tc_wgrad.cuh"
 
 namespace b200 {
@@ -269,6 +270,8 @@ struct Exec {
       if (ci >= 0 && tc::conv_supported(x.C, Co, x.pitch, x.coff, out.pitch, out.coff)) {
         B200_PROFD(st, "conv_fwd k%d %d->%d @%d", ks, x.C, Co, s.D);
         if (stats) { B200_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * c.B * Co, st)); if (stats_done) *stats_done = true; }
+        if (ks == 3 && tc::conv_halo_supported(x.C, Co))
+          return tc::conv_halo(x.p, x.pitch, x.coff, x.C, s.N, s.D, s.H, s.W, w.wcf[ci], Co, out.p, out.pitch, out.coff, 0, stats, st);
         return tc::conv(x.p, x.pitch, x.coff, x.C, s.N, s.D, s.H, s.W, w.wcf[ci], Co, ks, out.p, out.pitch, out.coff, 0, stats, st);
       }
     }
@@ -279,6 +282,8 @@ struct Exec {
       int ci = conv_index(W);
       if (ci >= 0 && tc::conv_supported(dy.C, Ci, dy.pitch, dy.coff, dx.pitch, dx.coff)) {
         B200_PROFD(st, "conv_dgrad k%d %d->%d @%d", ks, dy.C, Ci, s.D);
+        if (ks == 3 && tc::conv_halo_supported(dy.C, Ci))
+          return tc::conv_halo(dy.p, dy.pitch, dy.coff, dy.C, s.N, s.D, s.H, s.W, w.wcd[ci], Ci, dx.p, dx.pitch, dx.coff, acc, nullptr, st);
         return tc::conv(dy.p, dy.pitch, dy.coff, dy.C, s.N, s.D, s.H, s.W, w.wcd[ci], Ci, ks, dx.p, dx.pitch, dx.coff, acc, nullptr, st);
       }
     }
