@@ -2,11 +2,18 @@
 //
 // tc_conv.cuh fetches the voxel brick once per tap: every input voxel crosses L2->SM 27 times and the kernel is bound by
 // L2 request bandwidth (measured 16-35 B/clk/SM).  Here the output tile is ONE d-plane of 16(h) x 8(w) voxels and, per
-// kd, one TMA box brings the (16+2) x (8+2) halo plane [18][10][C] into swizzled smem.  All nine (kh,kw) taps of that kd
+// kd, one halo plane of (16+2) x (8+2) voxels [18][10][C] sits in swizzled smem.  All nine (kh,kw) taps of that kd
 // are then just *descriptor views* of the same tile:
 //       start = tile + (kh*10 + kw) * row_bytes ,   SBO (next 8-row group = next h) = 10 * row_bytes
 // which is legal because UMMA (like TMA) applies the 32/64/128-byte swizzle XOR to absolute smem address bits (the same
-// property the +32 B K-advance inside a swizzle atom relies on).  3 TMA loads and zero copies per tile instead of 27.
+// property the +32 B K-advance inside a swizzle atom relies on).  When the packed weights fit in smem next to the ring,
+// ONE TMA box of depth 3 brings all three halo planes of a tile (1 TMA load and 27*kc/16 MMAs per pipeline stage).
+//
+// Measured on B200 (ncu, 16->16 @96^3): the tensor pipe is busy 32 cycles per 128x16x16 MMA (A-operand smem read), so the
+// single issuing thread must spend well under that per MMA.  The issue loop is therefore a template on kc/16 with every
+// tap offset a compile-time constant: 2 uniform adds + 1 UTCHMMA per MMA, all operands in uniform registers.
+// InstanceNorm statistics of 16/32-channel outputs are accumulated in registers across a CTA's tiles and flushed with one
+// warp reduction per sample instead of 2*Co shuffled reductions per tile.
 #pragma once
 #include "tc_conv.cuh"
 
@@ -18,14 +25,38 @@ static constexpr int HTH = 16, HTW = 8, HALO_H = HTH + 2, HALO_W = HTW + 2;
 struct HaloParams {
   int N, D, H, W, Ci, Co;
   int kc, row_bytes, nchunk;     // channels per chunk (<= 64), smem row size, Ci/kc
-  int tiles_w, tiles_h; long total_tiles;
-  int halo_bytes;                // HALO_H*HALO_W*row_bytes rounded up to 1024
+  int tiles_w, tiles_h, tiles_per_n, total_tiles;
+  int planes;                    // halo planes per pipeline stage: 3 (one box of depth 3) or 1
+  int plane_bytes;               // HALO_H*HALO_W*row_bytes
+  int halo_bytes;                // planes*plane_bytes rounded up to 1024 (weight tiles of a non-resident stage follow)
   int b_bytes;                   // one (tap, chunk) weight tile, rounded to 1024
   int resident;                  // all 27*nchunk weight tiles stay in smem
   int stage_bytes, stages; uint32_t tmem_cols;
   bf16* out; int pitch, coff, accumulate; double* stats;
+  int dbg_mode; long long* dbg;  // tuning aids: bit0 skip TMA, bit1 skip MMA, bit2 skip epilogue stores; CTA-0 clock stamps
 };
 
+// all 9 (kh,kw) taps x KSTEPS k-steps of one halo plane: a_pl/b_pl are descriptor low words (16-byte units)
+template <int KSTEPS>
+__device__ __forceinline__ void issue_plane(uint32_t tmem_d, uint32_t a_pl, uint32_t a_hi, uint32_t b_pl, uint32_t b_hi, uint32_t b_tap,
+                                            uint32_t idesc, uint32_t first) {
+  constexpr uint32_t ROW_UNITS = 2 * KSTEPS;   // row_bytes / 16
+#pragma unroll
+  for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+    for (int kw = 0; kw < 3; ++kw) {
+      const uint32_t a_lo = a_pl + (uint32_t)(kh * HALO_W + kw) * ROW_UNITS;
+      const uint32_t b_lo = b_pl + (uint32_t)(kh * 3 + kw) * b_tap;
+#pragma unroll
+      for (int k = 0; k < KSTEPS; ++k) {
+        if (kh == 0 && kw == 0 && k == 0) umma_f16(tmem_d, desc64(a_lo, a_hi), desc64(b_lo, b_hi), idesc, first ? 0u : 1u);
+        else umma_f16(tmem_d, desc64(a_lo + 2 * k, a_hi), desc64(b_lo + 2 * k, b_hi), idesc, 1u);
+      }
+    }
+}
+
+// KSTEPS = kc/16; CO_T = 16 / 32: output channels known at compile time (register-resident statistics), 0 = generic
+template <int KSTEPS, int CO_T>
 __global__ void __launch_bounds__(192, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const HaloParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -41,7 +72,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
   float* red = (float*)(tmem_slot + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nstage_per_tile = 3 * p.nchunk;   // (kd, chunk)
+  const bool dbg = p.dbg && blockIdx.x == 0;
+  if (dbg && threadIdx.x == 0) p.dbg[0] = clock64();
+  const int kd_groups = 3 / p.planes;                       // stages along kd per chunk
+  const int nstage_per_tile = kd_groups * p.nchunk;         // (kd group, chunk)
   const uint32_t w_tx = (uint32_t)(p.Co * p.row_bytes);
 
   if (threadIdx.x == 0) {
@@ -66,63 +100,68 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ---- TMA producer: one halo plane (+ its 9 weight tiles when not resident) per (kd, chunk)
+    // ---- TMA producer: per (kd group, chunk) one halo box (+ its 9*planes weight tiles when not resident)
     int stage = 0; uint32_t phase = 0;
     const uint32_t ring_u = smem_u32(ring);
-    const uint32_t tx = (uint32_t)(HALO_H * HALO_W * p.row_bytes) + (p.resident ? 0u : 9u * w_tx);
-    for (long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-      int tw = (int)(t % p.tiles_w); long r = t / p.tiles_w; int th = (int)(r % p.tiles_h); r /= p.tiles_h;
-      int d = (int)(r % p.D); int n = (int)(r / p.D);
-      for (int kd = 0; kd < 3; ++kd)
+    const uint32_t tx = (uint32_t)(p.planes * p.plane_bytes) + (p.resident ? 0u : 9u * (uint32_t)p.planes * w_tx);
+    int t = blockIdx.x;
+    int n = t / p.tiles_per_n, r = t - n * p.tiles_per_n;
+    for (; t < p.total_tiles; t += gridDim.x) {
+      const int tw = r % p.tiles_w, q = r / p.tiles_w, th = q % p.tiles_h, d = q / p.tiles_h;
+      for (int kg = 0; kg < kd_groups; ++kg)
         for (int ch = 0; ch < p.nchunk; ++ch) {
           mbar_wait(empty + stage, phase ^ 1);
           if (elect_one()) {
             const uint32_t base = ring_u + (uint32_t)stage * p.stage_bytes;
-            mbar_expect_tx(full + stage, tx);
-            tma_load_5d(base, &map_x, full + stage, ch * p.kc, tw * HTW - 1, th * HTH - 1, d + kd - 1, n);
-            if (!p.resident)
-              for (int j = 0; j < 9; ++j)
-                tma_load_2d(base + p.halo_bytes + j * p.b_bytes, &map_w, full + stage, ch * p.kc, (kd * 9 + j) * p.Co);
+            if (p.dbg_mode & 1) mbar_arrive(full + stage);
+            else {
+              mbar_expect_tx(full + stage, tx);
+              tma_load_5d(base, &map_x, full + stage, ch * p.kc, tw * HTW - 1, th * HTH - 1, d + kg * p.planes - 1, n);
+              if (!p.resident)
+                for (int j = 0; j < 9 * p.planes; ++j)
+                  tma_load_2d(base + p.halo_bytes + j * p.b_bytes, &map_w, full + stage, ch * p.kc, (kg * p.planes * 9 + j) * p.Co);
+            }
           }
           __syncwarp();
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
+      r += gridDim.x;
+      while (r >= p.tiles_per_n) { r -= p.tiles_per_n; ++n; }
     }
   } else if (warp == 1) {
     // ---- MMA issuer
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.Co >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-    const uint32_t layout = p.row_bytes == 128 ? 2u : (p.row_bytes == 64 ? 4u : 6u);
-    const uint32_t a_hi = desc_hi((uint32_t)(HALO_W * p.row_bytes), layout);   // next 8-row group = next h line of the halo
-    const uint32_t b_hi = desc_hi(8 * p.row_bytes, layout);
+    const uint32_t layout = KSTEPS == 4 ? 2u : (KSTEPS == 2 ? 4u : 6u);
+    constexpr uint32_t ROW_BYTES = 32 * KSTEPS;
+    const uint32_t a_hi = desc_hi((uint32_t)(HALO_W * ROW_BYTES), layout);   // next 8-row group = next h line of the halo
+    const uint32_t b_hi = desc_hi(8 * ROW_BYTES, layout);
     const uint32_t ring_u = smem_u32(ring);
     const uint32_t a_lo0 = desc_lo(ring_u, 16);
     const uint32_t b_lo0 = p.resident ? desc_lo(smem_u32(smem), 16) : desc_lo(ring_u + p.halo_bytes, 16);
-    const uint32_t stage_units = (uint32_t)p.stage_bytes >> 4, b_units = (uint32_t)p.b_bytes >> 4, row_units = (uint32_t)p.row_bytes >> 4;
-    const int ksteps = p.kc / 16;
+    const uint32_t stage_units = (uint32_t)p.stage_bytes >> 4, b_units = (uint32_t)p.b_bytes >> 4, plane_units = (uint32_t)p.plane_bytes >> 4;
+    const uint32_t b_tap = p.resident ? (uint32_t)p.nchunk * b_units : b_units;   // distance between consecutive taps' weight tiles
+    const uint32_t b_plane = 9 * b_tap;                                           // ... and between consecutive kd planes
     int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
-    for (long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+    if (p.resident) { mbar_wait(wfull, 0); tc_fence_after(); }
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
       mbar_wait(tempty + acc, acc_phase ^ 1);
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + (uint32_t)(acc * p.Co);
       int s = 0;
-      for (int kd = 0; kd < 3; ++kd)
+      for (int kg = 0; kg < kd_groups; ++kg)
         for (int ch = 0; ch < p.nchunk; ++ch, ++s) {
           mbar_wait(full + stage, phase);
           tc_fence_after();
           const uint32_t a_st = a_lo0 + (uint32_t)stage * stage_units;
-          const uint32_t b_st = p.resident ? b_lo0 + (uint32_t)((kd * 9) * p.nchunk + ch) * b_units : b_lo0 + (uint32_t)stage * stage_units;
-          const uint32_t b_tap = p.resident ? (uint32_t)p.nchunk * b_units : b_units;   // distance between consecutive taps' weight tiles
+          const uint32_t b_st = p.resident ? b_lo0 + (uint32_t)(kg * p.planes) * b_plane + (uint32_t)ch * b_units : b_lo0 + (uint32_t)stage * stage_units;
           if (elect_one()) {
-            uint32_t b_lo = b_st;
-#pragma unroll
-            for (int kh = 0; kh < 3; ++kh)
-#pragma unroll
-              for (int kw = 0; kw < 3; ++kw) {
-                const uint32_t a_lo = a_st + (uint32_t)(kh * HALO_W + kw) * row_units;
-                for (int k = 0; k < ksteps; ++k)
-                  umma_f16(tmem_d, desc64(a_lo + 2 * k, a_hi), desc64(b_lo + 2 * k, b_hi), idesc, (s | kh | kw | k) ? 1u : 0u);
-                b_lo += b_tap;
+            if (!(p.dbg_mode & 2)) {
+              issue_plane<KSTEPS>(tmem_d, a_st, a_hi, b_st, b_hi, b_tap, idesc, s == 0 ? 1u : 0u);
+              if (p.planes == 3) {
+                issue_plane<KSTEPS>(tmem_d, a_st + plane_units, a_hi, b_st + b_plane, b_hi, b_tap, idesc, 0u);
+                issue_plane<KSTEPS>(tmem_d, a_st + 2 * plane_units, a_hi, b_st + 2 * b_plane, b_hi, b_tap, idesc, 0u);
               }
+            }
             umma_commit(empty + stage);
             if (s == nstage_per_tile - 1) umma_commit(tfull + acc);
           }
@@ -133,72 +172,155 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     }
   } else {
     // ---- epilogue (TMEM lane quarter = warp % 4); row r -> (h = r/8, w = r%8) of the d-plane tile
-    const int q = warp & 3, ew = warp - 2;
+    const int q4 = warp & 3, ew = warp - 2;
+    const int row = q4 * 32 + lane;
     int acc = 0; uint32_t acc_phase = 0;
-    for (long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-      int tw = (int)(t % p.tiles_w); long r = t / p.tiles_w; int th = (int)(r % p.tiles_h); r /= p.tiles_h;
-      int d = (int)(r % p.D); int n = (int)(r / p.D);
-      const int row = q * 32 + lane;
+    int t = blockIdx.x;
+    int n = t / p.tiles_per_n, r = t - n * p.tiles_per_n;
+    constexpr int NR = CO_T ? CO_T : 1;
+    float rs1[NR], rs2[NR];          // register-resident statistics (CO_T != 0)
+#pragma unroll
+    for (int j = 0; j < NR; ++j) { rs1[j] = 0.f; rs2[j] = 0.f; }
+    int n_acc = n;
+    auto flush = [&](int nn) {       // all 128 epilogue threads
+      if (CO_T && p.stats) {
+#pragma unroll
+        for (int j = 0; j < NR; ++j) {
+          float s1 = warp_sum(rs1[j]), s2 = warp_sum(rs2[j]);
+          if (lane == 0) { red[ew * 2 * CO_T + j] = s1; red[ew * 2 * CO_T + CO_T + j] = s2; }
+          rs1[j] = 0.f; rs2[j] = 0.f;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const int e = ew * 32 + lane;
+        if (e < 2 * CO_T) {
+          float tot = red[e] + red[2 * CO_T + e] + red[4 * CO_T + e] + red[6 * CO_T + e];
+          int c = e % NR, which = e / NR;
+          atomicAdd(p.stats + ((long)nn * CO_T + c) * 2 + which, (double)tot);
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+    };
+    for (; t < p.total_tiles; t += gridDim.x) {
+      const int tw = r % p.tiles_w, qq = r / p.tiles_w, th = qq % p.tiles_h, d = qq / p.tiles_h;
+      if (n != n_acc) { flush(n_acc); n_acc = n; }
       const int w = tw * HTW + (row & 7), h = th * HTH + (row >> 3);
       const bool valid = (w < p.W) && (h < p.H);
       bf16* dst = p.out + ((((long)n * p.D + d) * p.H + h) * p.W + w) * p.pitch + p.coff;
       mbar_wait(tfull + acc, acc_phase);
       tc_fence_after();
-      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.Co);
-      for (int c0 = 0; c0 < p.Co; c0 += 16) {
-        float v[16];
-        tmem_ld16(trow + c0, v);
+      const uint32_t trow = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(acc * p.Co);
+      if (CO_T) {
+#pragma unroll
+        for (int c0 = 0; c0 < NR; c0 += 16) {
+          float v[16];
+          tmem_ld16(trow + c0, v);
+          if (p.dbg_mode & 4) continue;
+          if (valid) {
+            if (p.stats) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) { rs1[(c0 + j) % NR] += v[j]; rs2[(c0 + j) % NR] = fmaf(v[j], v[j], rs2[(c0 + j) % NR]); }
+            }
+            if (p.accumulate) {
+              Vec16<bf16> a, b; a.load(dst + c0); b.load(dst + c0 + 8);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) { v[j] += a.v[j]; v[8 + j] += b.v[j]; }
+            }
+            Vec16<bf16> o0, o1;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { o0.v[j] = v[j]; o1.v[j] = v[8 + j]; }
+            o0.store(dst + c0); o1.store(dst + c0 + 8);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty + acc);
+      } else {
+        for (int c0 = 0; c0 < p.Co; c0 += 16) {
+          float v[16];
+          tmem_ld16(trow + c0, v);
+          if (p.dbg_mode & 4) continue;
+          if (p.stats) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              float x = valid ? v[j] : 0.f;
+              float s1 = warp_sum(x), s2 = warp_sum(x * x);
+              if (lane == 0) { red[ew * 2 * p.Co + c0 + j] = s1; red[ew * 2 * p.Co + p.Co + c0 + j] = s2; }
+            }
+          }
+          if (valid) {
+            if (p.accumulate) {
+              Vec16<bf16> a, b; a.load(dst + c0); b.load(dst + c0 + 8);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) { v[j] += a.v[j]; v[8 + j] += b.v[j]; }
+            }
+            Vec16<bf16> o0, o1;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { o0.v[j] = v[j]; o1.v[j] = v[8 + j]; }
+            o0.store(dst + c0); o1.store(dst + c0 + 8);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty + acc);
         if (p.stats) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            float x = valid ? v[j] : 0.f;
-            float s1 = warp_sum(x), s2 = warp_sum(x * x);
-            if (lane == 0) { red[ew * 2 * p.Co + c0 + j] = s1; red[ew * 2 * p.Co + p.Co + c0 + j] = s2; }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          int e = ew * 32 + lane;
+          for (int i = e; i < 2 * p.Co; i += 128) {
+            float tot = red[i] + red[2 * p.Co + i] + red[4 * p.Co + i] + red[6 * p.Co + i];
+            int c = i % p.Co, which = i / p.Co;
+            atomicAdd(p.stats + ((long)n * p.Co + c) * 2 + which, (double)tot);
           }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
         }
-        if (valid) {
-          if (p.accumulate) {
-            Vec16<bf16> a, b; a.load(dst + c0); b.load(dst + c0 + 8);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) { v[j] += a.v[j]; v[8 + j] += b.v[j]; }
-          }
-          Vec16<bf16> o0, o1;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) { o0.v[j] = v[j]; o1.v[j] = v[8 + j]; }
-          o0.store(dst + c0); o1.store(dst + c0 + 8);
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty + acc);
-      if (p.stats) {
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        int e = (warp - 2) * 32 + lane;
-        for (int i = e; i < 2 * p.Co; i += 128) {
-          float tot = red[i] + red[2 * p.Co + i] + red[4 * p.Co + i] + red[6 * p.Co + i];
-          int c = i % p.Co, which = i / p.Co;
-          atomicAdd(p.stats + ((long)n * p.Co + c) * 2 + which, (double)tot);
-        }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      r += gridDim.x;
+      while (r >= p.tiles_per_n) { r -= p.tiles_per_n; ++n; }
     }
+    flush(n_acc);
   }
   tc_fence_before();
   __syncthreads();
+  if (dbg && threadIdx.x == 0) p.dbg[48] = clock64();
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
   }
 }
 
-// does the (kd, chunk) stage (halo plane + 9 weight tiles unless all weights are resident) fit at least twice?
+// smem plan shared by the support test and the launcher
+struct HaloPlan { int kc, rb, nchunk, plane_bytes, b_bytes, resident, planes, halo_bytes, stage_bytes, stages; };
+static inline HaloPlan halo_plan(int Ci, int Co) {
+  HaloPlan h;
+  h.kc = Ci % 64 == 0 ? 64 : (Ci % 32 == 0 ? 32 : 16); h.rb = h.kc * 2; h.nchunk = Ci / h.kc;
+  h.plane_bytes = HALO_H * HALO_W * h.rb;
+  h.b_bytes = ((Co * h.rb + 1023) / 1024) * 1024;
+  const int budget_all = 200 * 1024;
+  h.resident = ((long)27 * h.nchunk * h.b_bytes <= 112 * 1024) ? 1 : 0;
+  int budget = budget_all - (h.resident ? 27 * h.nchunk * h.b_bytes : 0);
+  h.planes = 3;
+  h.halo_bytes = ((3 * h.plane_bytes + 1023) / 1024) * 1024;
+  h.stage_bytes = h.halo_bytes + (h.resident ? 0 : 27 * h.b_bytes);
+  if (budget / h.stage_bytes < 3) {   // one plane per stage
+    h.planes = 1;
+    h.halo_bytes = ((h.plane_bytes + 1023) / 1024) * 1024;
+    h.stage_bytes = h.halo_bytes + (h.resident ? 0 : 9 * h.b_bytes);
+  }
+  h.stages = budget / h.stage_bytes; if (h.stages > 8) h.stages = 8;
+  return h;
+}
 static inline bool conv_halo_supported(int Ci, int Co) {
-  int kc = Ci % 64 == 0 ? 64 : (Ci % 32 == 0 ? 32 : 16), rb = kc * 2, nchunk = Ci / kc;
-  int halo = ((HALO_H * HALO_W * rb + 1023) / 1024) * 1024, b = ((Co * rb + 1023) / 1024) * 1024;
-  bool resident = (long)27 * nchunk * b <= 112 * 1024;
-  int stage = halo + (resident ? 0 : 9 * b), budget = 200 * 1024 - (resident ? 27 * nchunk * b : 0);
-  return Ci % 16 == 0 && Co % 16 == 0 && Co <= 256 && budget / stage >= 2;
+  if (!(Ci % 16 == 0 && Co % 16 == 0 && Co <= 256)) return false;
+  return halo_plan(Ci, Co).stages >= 2;
+}
+
+template <int KSTEPS, int CO_T>
+static int conv_halo_launch(const CUtensorMap& mx, const CUtensorMap& mw, const HaloParams& p, int grid, size_t smem, cudaStream_t st) {
+  static bool attr_done = false;
+  if (!attr_done) { B200_CUDA(cudaFuncSetAttribute(conv_halo_kernel<KSTEPS, CO_T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr_done = true; }
+  conv_halo_kernel<KSTEPS, CO_T><<<grid, 192, smem, st>>>(mx, mw, p);
+  B200_LAUNCH_CHECK();
+  return 0;
 }
 
 // 3x3x3 only.  wp: packed bf16 [27][Co][Ci] (same packing as tc::conv).
@@ -206,28 +328,30 @@ static int conv_halo(const bf16* x, int in_pitch, int in_coff, int Ci, int N, in
                      bf16* out, int out_pitch, int out_coff, int accumulate, double* stats, cudaStream_t st) {
   EncodeTiledFn enc = get_encode();
   B200_CHECK(enc, "cuTensorMapEncodeTiled not available from the driver");
+  HaloPlan h = halo_plan(Ci, Co);
   HaloParams p;
   p.N = N; p.D = D; p.H = H; p.W = W; p.Ci = Ci; p.Co = Co;
-  p.kc = Ci % 64 == 0 ? 64 : (Ci % 32 == 0 ? 32 : 16);
-  p.row_bytes = p.kc * 2; p.nchunk = Ci / p.kc;
+  p.kc = h.kc; p.row_bytes = h.rb; p.nchunk = h.nchunk;
   p.tiles_w = cdiv(W, HTW); p.tiles_h = cdiv(H, HTH);
-  p.total_tiles = (long)N * D * p.tiles_h * p.tiles_w;
-  p.halo_bytes = ((HALO_H * HALO_W * p.row_bytes + 1023) / 1024) * 1024;
-  p.b_bytes = ((Co * p.row_bytes + 1023) / 1024) * 1024;
-  p.resident = ((long)27 * p.nchunk * p.b_bytes <= 112 * 1024) ? 1 : 0;
-  p.stage_bytes = p.halo_bytes + (p.resident ? 0 : 9 * p.b_bytes);
-  int budget = 200 * 1024 - (p.resident ? 27 * p.nchunk * p.b_bytes : 0);
-  p.stages = budget / p.stage_bytes; if (p.stages > 8) p.stages = 8;
+  p.tiles_per_n = D * p.tiles_h * p.tiles_w;
+  long total = (long)N * p.tiles_per_n;
+  B200_CHECK(total < (1L << 30), "halo conv: too many tiles");
+  p.total_tiles = (int)total;
+  p.planes = h.planes; p.plane_bytes = h.plane_bytes; p.halo_bytes = h.halo_bytes; p.b_bytes = h.b_bytes; p.resident = h.resident;
+  p.stage_bytes = h.stage_bytes; p.stages = h.stages;
   B200_CHECK(p.stages >= 2, "halo conv smem budget exceeded (Ci=%d Co=%d)", Ci, Co);
   uint32_t cols = 2 * Co, pw = 32; while (pw < cols) pw <<= 1; p.tmem_cols = pw;
   p.out = out; p.pitch = out_pitch; p.coff = out_coff; p.accumulate = accumulate; p.stats = stats;
+  p.dbg = g_dbg; p.dbg_mode = 0;
+  if (const char* e = getenv("B200_HALO_DBG")) p.dbg_mode = atoi(e);
+  if (const char* e = getenv("B200_HALO_STAGES")) { int v = atoi(e); if (v >= 2 && v <= p.stages) p.stages = v; }
 
   CUtensorMapSwizzle sw = p.row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (p.row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
   CUtensorMap mx, mw;
   {
     cuuint64_t dims[5] = {(cuuint64_t)Ci, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
     cuuint64_t strides[4] = {(cuuint64_t)in_pitch * 2, (cuuint64_t)W * in_pitch * 2, (cuuint64_t)H * W * in_pitch * 2, (cuuint64_t)D * H * W * in_pitch * 2};
-    cuuint32_t box[5] = {(cuuint32_t)p.kc, HALO_W, HALO_H, 1, 1};
+    cuuint32_t box[5] = {(cuuint32_t)p.kc, HALO_W, HALO_H, (cuuint32_t)p.planes, 1};
     cuuint32_t es[5] = {1, 1, 1, 1, 1};
     CUresult r = enc(&mx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (void*)(x + in_coff), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -244,12 +368,14 @@ static int conv_halo(const bf16* x, int in_pitch, int in_coff, int Ci, int N, in
   }
   size_t smem = (size_t)p.stages * p.stage_bytes + (p.resident ? (size_t)27 * p.nchunk * p.b_bytes : 0) + 1024 + 256 + 8 * Co * sizeof(float) + 64;
   B200_CHECK(smem <= 227 * 1024, "halo conv smem budget exceeded (%zu)", smem);
-  static bool attr_done = false;
-  if (!attr_done) { B200_CUDA(cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr_done = true; }
   int grid = (int)(p.total_tiles < num_sms() ? p.total_tiles : num_sms());
-  conv_halo_kernel<<<grid, 192, smem, st>>>(mx, mw, p);
-  B200_LAUNCH_CHECK();
-  return 0;
+  const int ks = p.kc / 16;
+#define B200_HALO_CASE(KS, CO) if (ks == KS && ((CO) ? Co == (CO) : (Co != 16 && Co != 32))) return conv_halo_launch<KS, CO>(mx, mw, p, grid, smem, st)
+  B200_HALO_CASE(1, 16); B200_HALO_CASE(1, 32); B200_HALO_CASE(1, 0);
+  B200_HALO_CASE(2, 16); B200_HALO_CASE(2, 32); B200_HALO_CASE(2, 0);
+  B200_HALO_CASE(4, 16); B200_HALO_CASE(4, 32); B200_HALO_CASE(4, 0);
+#undef B200_HALO_CASE
+  B200_CHECK(false, "halo conv: no kernel for kc=%d Co=%d", p.kc, Co);
 }
 
 }  // namespace tc

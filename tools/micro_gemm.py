@@ -25,6 +25,8 @@ def run(M, N, K, a_mn=0, b_mn=0, iters=20, cold=False):
     d = dbg.cpu().tolist(); t0 = d[0]
     rel = lambda i: (d[i] - t0) if d[i] else -1
     print(f"gemm {M}x{N}x{K} mn={a_mn}{b_mn} {'cold' if cold else 'hot '}: {us:7.1f} us {2*M*N*K/us/1e6:7.1f} TF | cyc: setup {rel(1)} prod_done {rel(2)} kb0..3 {[rel(8+i) for i in range(4)]} mma_done {rel(3)} acc_ready {rel(4)} end {rel(5)} | mma_issued {[rel(12+i) for i in range(4)]} prod_issued {[rel(16+i) for i in range(4)]}")
+for bn in ("", "64", "128", "256"):
+    if bn: os.environ["B200_GEMM_BN"] = bn
+    print("BN override:", bn or "auto")
+    run(432, 3072, 768); run(432, 768, 3072); run(432, 2304, 768); run(432, 768, 768)
 run(128, 64, 768)
-run(128, 256, 3072)
-run(432, 768, 768, cold=True)
