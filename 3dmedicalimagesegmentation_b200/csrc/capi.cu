@@ -13,6 +13,7 @@
 #include "sliding.cuh"
 #include "tc_gemm.cuh"
 #include "tc_conv_halo.cuh"
+#include "tc_wgrad_halo.cuh"
 
 namespace b200 {
 static thread_local char g_err[1024] = "";
@@ -267,6 +268,8 @@ int b200_test_tc_wgrad(const void* x, int x_pitch, int x_coff, int Ci, const voi
   cudaStream_t st = (cudaStream_t)stream;
   B200_CHECK(tc::wgrad_supported(Ci, Co, x_pitch, x_coff, dy_pitch, dy_coff), "shape unsupported by the tcgen05 wgrad");
   B200_CUDA(cudaMemsetAsync(dW, 0, sizeof(float) * Co * Ci * ks * ks * ks, st));
+  if (tc::wgrad_halo_supported(Ci, Co, ks))
+    return tc::conv_wgrad_halo((const bf16*)x, x_pitch, x_coff, Ci, (const bf16*)dy, dy_pitch, dy_coff, Co, N, D, H, W, dW, st);
   return tc::conv_wgrad((const bf16*)x, x_pitch, x_coff, Ci, (const bf16*)dy, dy_pitch, dy_coff, Co, N, D, H, W, ks, dW, st);
 }
 

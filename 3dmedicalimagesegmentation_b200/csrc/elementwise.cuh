@@ -104,6 +104,87 @@ static int launch_add(float* dst, const float* src, long n, cudaStream_t st) {
 }
 
 // ------------------------------------------------------------------ LayerNorm (eps 1e-5, affine), one warp per row
+
+// 4 consecutive elements of T <-> floats (16-byte / 8-byte accesses)
+__device__ __forceinline__ void load4(const float* p, float* o) { float4 t = *reinterpret_cast<const float4*>(p); o[0] = t.x; o[1] = t.y; o[2] = t.z; o[3] = t.w; }
+__device__ __forceinline__ void load4(const bf16* p, float* o) {
+  uint2 t = *reinterpret_cast<const uint2*>(p);
+  float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.x)), b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.y));
+  o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y;
+}
+__device__ __forceinline__ void store4(float* p, const float* v) { *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]); }
+__device__ __forceinline__ void store4(bf16* p, const float* v) {
+  uint2 t; __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+  t.x = *reinterpret_cast<uint32_t*>(&a); t.y = *reinterpret_cast<uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(p) = t;
+}
+
+// Register-resident variants for H = NV4*128 (ViT-B: 768 -> NV4 = 6): every load of a row is issued before the first
+// use, one pass over memory (the generic kernels below are latency-bound: 2-3 dependent passes of 24 scalar loads).
+template <class TO, int NV4>
+__global__ void layernorm_fwd_reg_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                         TO* __restrict__ y, float* __restrict__ stats, int M) {
+  constexpr int H = NV4 * 128;
+  int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const float* xr = x + (long)row * H;
+  float v[NV4][4];
+#pragma unroll
+  for (int i = 0; i < NV4; ++i) load4(xr + (i * 32 + lane) * 4, v[i]);
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV4; ++i) s += (v[i][0] + v[i][1]) + (v[i][2] + v[i][3]);
+  float mean = warp_sum(s) * (1.f / H);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { float d = v[i][j] - mean; q = fmaf(d, d, q); }
+  float rstd = rsqrtf(warp_sum(q) * (1.f / H) + 1e-5f);
+#pragma unroll
+  for (int i = 0; i < NV4; ++i) {
+    float g[4], b[4], o[4];
+    load4(gamma + (i * 32 + lane) * 4, g); load4(beta + (i * 32 + lane) * 4, b);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[j] = (v[i][j] - mean) * rstd * g[j] + b[j];
+    store4(y + (long)row * H + (i * 32 + lane) * 4, o);
+  }
+  if (lane == 0 && stats) { stats[2 * row] = mean; stats[2 * row + 1] = rstd; }
+}
+template <class TG, int NV4>
+__global__ void layernorm_bwd_dx_reg_kernel(const TG* __restrict__ g, const float* __restrict__ x, const float* __restrict__ stats,
+                                            const float* __restrict__ gamma, const float* dx_res, float* dx_out, TG* dx_out_cast, int M) {
+  constexpr int H = NV4 * 128;
+  int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const float mean = stats[2 * row], rstd = stats[2 * row + 1];
+  float gg[NV4][4], xh[NV4][4], rs[NV4][4];
+#pragma unroll
+  for (int i = 0; i < NV4; ++i) {
+    const long o = (long)row * H + (i * 32 + lane) * 4;
+    float gm[4];
+    load4(g + o, gg[i]); load4(x + o, xh[i]); load4(gamma + (i * 32 + lane) * 4, gm);
+    if (dx_res) load4(dx_res + o, rs[i]);
+    else { rs[i][0] = rs[i][1] = rs[i][2] = rs[i][3] = 0.f; }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { gg[i][j] *= gm[j]; xh[i][j] = (xh[i][j] - mean) * rstd; }
+  }
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { s1 += gg[i][j]; s2 = fmaf(gg[i][j], xh[i][j], s2); }
+  s1 = warp_sum(s1) * (1.f / H); s2 = warp_sum(s2) * (1.f / H);
+#pragma unroll
+  for (int i = 0; i < NV4; ++i) {
+    const long o = (long)row * H + (i * 32 + lane) * 4;
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = rstd * (gg[i][j] - s1 - xh[i][j] * s2) + rs[i][j];
+    store4(dx_out + o, v);
+    if (dx_out_cast) store4(dx_out_cast + o, v);
+  }
+}
 template <class TO>
 __global__ void layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                      const float* __restrict__ beta, TO* __restrict__ y, float* __restrict__ stats,
@@ -125,7 +206,8 @@ template <class TO>
 static int launch_layernorm_fwd(const float* x, const float* g, const float* b, TO* y, float* stats, int M, int H,
                                 cudaStream_t st) {
   B200_PROF("layernorm_fwd", st);
-  layernorm_fwd_kernel<TO><<<cdiv(M, 8), 256, 0, st>>>(x, g, b, y, stats, M, H);
+  if (H == 768) layernorm_fwd_reg_kernel<TO, 6><<<cdiv(M, 4), 128, 0, st>>>(x, g, b, y, stats, M);
+  else layernorm_fwd_kernel<TO><<<cdiv(M, 8), 256, 0, st>>>(x, g, b, y, stats, M, H);
   B200_LAUNCH_CHECK();
   return 0;
 }
@@ -181,7 +263,8 @@ static int launch_layernorm_bwd(const TG* g, const float* x, const float* stats,
                                 const float* dx_res, float* dx_out, TG* dx_out_cast, float* dgamma, float* dbeta, int M, int H,
                                 cudaStream_t st) {
   B200_PROF("layernorm_bwd", st);
-  layernorm_bwd_dx_kernel<TG><<<cdiv(M, 8), 256, 0, st>>>(g, x, stats, gamma, dx_res, dx_out, dx_out_cast, M, H);
+  if (H == 768) layernorm_bwd_dx_reg_kernel<TG, 6><<<cdiv(M, 4), 128, 0, st>>>(g, x, stats, gamma, dx_res, dx_out, dx_out_cast, M);
+  else layernorm_bwd_dx_kernel<TG><<<cdiv(M, 8), 256, 0, st>>>(g, x, stats, gamma, dx_res, dx_out, dx_out_cast, M, H);
   B200_LAUNCH_CHECK();
   if (dgamma) {
     cudaMemsetAsync(dgamma, 0, sizeof(float) * H, st); cudaMemsetAsync(dbeta, 0, sizeof(float) * H, st);
@@ -314,6 +397,24 @@ __global__ void softmax_bwd_kernel(const TP* __restrict__ P, const float* __rest
 // C/VecN a power of two <= 256.  Statistics: double sum/sumsq -> float (mean, rstd) per (n,c).
 
 
+
+// Block reduction of NVAL per-thread floats over all threads that share (threadIdx.x % lanes): xor-shuffles inside the warp,
+// then one smem row per (warp, lane<lanes); returns through `red` ([warps][lanes][NVAL]) after a __syncthreads().
+// (The previous tail -- `lanes` threads serially adding 128 x NVAL smem values in double -- cost ~45 us per block.)
+template <int NVAL>
+__device__ __forceinline__ void block_reduce_groups(float* vals, int lanes, float* red) {
+  for (int o = lanes; o < 32; o <<= 1) {
+#pragma unroll
+    for (int i = 0; i < NVAL; ++i) vals[i] += __shfl_xor_sync(0xffffffffu, vals[i], o);
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane < lanes) {
+#pragma unroll
+    for (int i = 0; i < NVAL; ++i) red[((warp * lanes) + lane) * NVAL + i] = vals[i];
+  }
+  __syncthreads();
+}
+
 template <class T>
 __global__ void in_stats_kernel(const T* __restrict__ x, ClView xv, int C, long V, double* __restrict__ acc) {
   constexpr int VN = Vec16<T>::N;
@@ -332,23 +433,24 @@ __global__ void in_stats_kernel(const T* __restrict__ x, ClView xv, int C, long 
 #pragma unroll
     for (int i = 0; i < VN; ++i) { s[i] += a.v[i]; q[i] += a.v[i] * a.v[i]; }
   }
-  float* mine = red + threadIdx.x * 2 * VN;
+  float vals[2 * VN];
 #pragma unroll
-  for (int i = 0; i < VN; ++i) { mine[i] = s[i]; mine[VN + i] = q[i]; }
-  __syncthreads();
-  if (sub == 0) {
-    double ds[VN], dq[VN];
-#pragma unroll
-    for (int i = 0; i < VN; ++i) ds[i] = dq[i] = 0.0;
-    for (int t = 0; t < nsub; ++t) {
-      const float* o = red + (t * lanes + lv) * 2 * VN;
-#pragma unroll
-      for (int i = 0; i < VN; ++i) { ds[i] += o[i]; dq[i] += o[VN + i]; }
+  for (int i = 0; i < VN; ++i) { vals[i] = s[i]; vals[VN + i] = q[i]; }
+  const int lanes_eff = lanes < 32 ? lanes : 32;   // lanes > 32: a warp covers only part of the channels
+  if (lanes <= 32) {
+    block_reduce_groups<2 * VN>(vals, lanes, red);
+    const int nwarp = blockDim.x >> 5;
+    for (int e = threadIdx.x; e < lanes_eff * 2 * VN; e += blockDim.x) {
+      int l = e / (2 * VN), i = e % (2 * VN);
+      double tot = 0.0;
+      for (int wv = 0; wv < nwarp; ++wv) tot += red[(wv * lanes + l) * 2 * VN + i];
+      atomicAdd(acc + ((long)n * C + l * VN + i % VN) * 2 + i / VN, tot);
     }
+  } else {
 #pragma unroll
     for (int i = 0; i < VN; ++i) {
-      atomicAdd(acc + ((long)n * C + lv * VN + i) * 2, ds[i]);
-      atomicAdd(acc + ((long)n * C + lv * VN + i) * 2 + 1, dq[i]);
+      atomicAdd(acc + ((long)n * C + lv * VN + i) * 2, (double)s[i]);
+      atomicAdd(acc + ((long)n * C + lv * VN + i) * 2 + 1, (double)q[i]);
     }
   }
 }
@@ -372,24 +474,27 @@ __global__ void in_apply_kernel(const T* __restrict__ x, ClView xv, const float*
   int lanes = C / VN;
   int n = blockIdx.y;
   long total = V * lanes;
+  // lanes is a power of two dividing the grid stride, so this thread always owns the same VN channels: constants live in registers
+  const long e0 = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lv = (int)(e0 % lanes), c0 = lv * VN;
+  float m1[VN], r1[VN], m2[VN], r2[VN];
+#pragma unroll
+  for (int i = 0; i < VN; ++i) {
+    m1[i] = mr[((long)n * C + c0 + i) * 2]; r1[i] = mr[((long)n * C + c0 + i) * 2 + 1];
+    m2[i] = two ? mr2[((long)n * C + c0 + i) * 2] : 0.f; r2[i] = two ? mr2[((long)n * C + c0 + i) * 2 + 1] : 0.f;
+  }
 #pragma unroll 4
-  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
-    long v = e / lanes; int lv = (int)(e % lanes); int c0 = lv * VN;
+  for (long e = e0; e < total; e += (long)gridDim.x * blockDim.x) {
+    long v = e / lanes;
     Vec16<T> a; a.load(x + ((long)n * V + v) * xv.pitch + xv.coff + c0);
     Vec16<T> o;
     if (two) {
       Vec16<T> b; b.load(x2 + ((long)n * V + v) * x2v.pitch + x2v.coff + c0);
 #pragma unroll
-      for (int i = 0; i < VN; ++i) {
-        const float* m1 = mr + ((long)n * C + c0 + i) * 2; const float* m2 = mr2 + ((long)n * C + c0 + i) * 2;
-        o.v[i] = lrelu((a.v[i] - m1[0]) * m1[1] + (b.v[i] - m2[0]) * m2[1]);
-      }
+      for (int i = 0; i < VN; ++i) o.v[i] = lrelu((a.v[i] - m1[i]) * r1[i] + (b.v[i] - m2[i]) * r2[i]);
     } else {
 #pragma unroll
-      for (int i = 0; i < VN; ++i) {
-        const float* m1 = mr + ((long)n * C + c0 + i) * 2;
-        o.v[i] = lrelu((a.v[i] - m1[0]) * m1[1]);
-      }
+      for (int i = 0; i < VN; ++i) o.v[i] = lrelu((a.v[i] - m1[i]) * r1[i]);
     }
     o.store(out + ((long)n * V + v) * ov.pitch + ov.coff + c0);
   }
@@ -411,8 +516,13 @@ __global__ void in_bwd_reduce_kernel(const T* __restrict__ dout, ClView dv, cons
   long per = (V + gridDim.x - 1) / gridDim.x;
   long v0 = (long)blockIdx.x * per, v1 = min(V, v0 + per);
   float s0[VN], s1[VN], s2[VN];
+  float ma0[VN], ma1[VN], mb0[VN], mb1[VN];   // per-channel (mean, rstd) of the two raw inputs, hoisted out of the voxel loop
 #pragma unroll
-  for (int i = 0; i < VN; ++i) s0[i] = s1[i] = s2[i] = 0.f;
+  for (int i = 0; i < VN; ++i) {
+    s0[i] = s1[i] = s2[i] = 0.f;
+    ma0[i] = two ? mra[((long)n * C + c0 + i) * 2] : 0.f; ma1[i] = two ? mra[((long)n * C + c0 + i) * 2 + 1] : 0.f;
+    mb0[i] = two ? mrb[((long)n * C + c0 + i) * 2] : 0.f; mb1[i] = two ? mrb[((long)n * C + c0 + i) * 2 + 1] : 0.f;
+  }
 #pragma unroll 4
   for (long v = v0 + sub; v < v1; v += nsub) {
     long base = (long)n * V + v;
@@ -421,9 +531,8 @@ __global__ void in_bwd_reduce_kernel(const T* __restrict__ dout, ClView dv, cons
       Vec16<T> xa, xb; xa.load(ra + base * rav.pitch + rav.coff + c0); xb.load(rb + base * rbv.pitch + rbv.coff + c0);
 #pragma unroll
       for (int i = 0; i < VN; ++i) {
-        const float* ma = mra + ((long)n * C + c0 + i) * 2; const float* mb = mrb + ((long)n * C + c0 + i) * 2;
         float g = d.v[i] * (a.v[i] > 0.f ? 1.f : 0.01f);
-        s0[i] += g; s1[i] += g * (xa.v[i] - ma[0]) * ma[1]; s2[i] += g * (xb.v[i] - mb[0]) * mb[1];
+        s0[i] += g; s1[i] += g * (xa.v[i] - ma0[i]) * ma1[i]; s2[i] += g * (xb.v[i] - mb0[i]) * mb1[i];
       }
     } else {
 #pragma unroll
@@ -434,24 +543,25 @@ __global__ void in_bwd_reduce_kernel(const T* __restrict__ dout, ClView dv, cons
       }
     }
   }
-  float* mine = red + threadIdx.x * 3 * VN;
+  float vals[3 * VN];
 #pragma unroll
-  for (int i = 0; i < VN; ++i) { mine[i] = s0[i]; mine[VN + i] = s1[i]; mine[2 * VN + i] = s2[i]; }
-  __syncthreads();
-  if (sub == 0) {
-    double d0[VN], d1[VN], d2[VN];
-#pragma unroll
-    for (int i = 0; i < VN; ++i) d0[i] = d1[i] = d2[i] = 0.0;
-    for (int t = 0; t < nsub; ++t) {
-      const float* o = red + (t * lanes + lv) * 3 * VN;
-#pragma unroll
-      for (int i = 0; i < VN; ++i) { d0[i] += o[i]; d1[i] += o[VN + i]; d2[i] += o[2 * VN + i]; }
+  for (int i = 0; i < VN; ++i) { vals[i] = s0[i]; vals[VN + i] = s1[i]; vals[2 * VN + i] = s2[i]; }
+  if (lanes <= 32) {
+    block_reduce_groups<3 * VN>(vals, lanes, red);
+    const int nwarp = blockDim.x >> 5;
+    for (int e = threadIdx.x; e < lanes * 3 * VN; e += blockDim.x) {
+      int l = e / (3 * VN), i = e % (3 * VN);
+      if (!two && i >= 2 * VN) continue;
+      double tot = 0.0;
+      for (int wv = 0; wv < nwarp; ++wv) tot += red[(wv * lanes + l) * 3 * VN + i];
+      atomicAdd(acc + ((long)n * C + l * VN + i % VN) * 3 + i / VN, tot);
     }
+  } else {
 #pragma unroll
     for (int i = 0; i < VN; ++i) {
       double* a3 = acc + ((long)n * C + c0 + i) * 3;
-      atomicAdd(a3, d0[i]); atomicAdd(a3 + 1, d1[i]);
-      if (two) atomicAdd(a3 + 2, d2[i]);
+      atomicAdd(a3, (double)s0[i]); atomicAdd(a3 + 1, (double)s1[i]);
+      if (two) atomicAdd(a3 + 2, (double)s2[i]);
     }
   }
 }
@@ -467,9 +577,19 @@ __global__ void in_bwd_apply_kernel(const T* __restrict__ dout, ClView dv, const
   int n = blockIdx.y;
   long total = V * lanes;
   float invV = 1.f / (float)V;
+  const long e0 = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lv = (int)(e0 % lanes), c0 = lv * VN;   // fixed per thread (lanes divides the grid stride)
+  float ma0[VN], ma1[VN], mb0[VN], mb1[VN], mg[VN], mga[VN], mgb[VN];
+#pragma unroll
+  for (int i = 0; i < VN; ++i) {
+    const double* a3 = acc + ((long)n * C + c0 + i) * 3;
+    mg[i] = (float)a3[0] * invV; mga[i] = (float)a3[1] * invV; mgb[i] = two ? (float)a3[2] * invV : 0.f;
+    ma0[i] = mra[((long)n * C + c0 + i) * 2]; ma1[i] = mra[((long)n * C + c0 + i) * 2 + 1];
+    mb0[i] = two ? mrb[((long)n * C + c0 + i) * 2] : 0.f; mb1[i] = two ? mrb[((long)n * C + c0 + i) * 2 + 1] : 0.f;
+  }
 #pragma unroll 4
-  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
-    long v = e / lanes; int lv = (int)(e % lanes); int c0 = lv * VN;
+  for (long e = e0; e < total; e += (long)gridDim.x * blockDim.x) {
+    long v = e / lanes;
     long base = (long)n * V + v;
     Vec16<T> d, a; d.load(dout + base * dv.pitch + dv.coff + c0); a.load(act + base * av.pitch + av.coff + c0);
     Vec16<T> oa, ob;
@@ -477,25 +597,19 @@ __global__ void in_bwd_apply_kernel(const T* __restrict__ dout, ClView dv, const
       Vec16<T> xa, xb; xa.load(ra + base * rav.pitch + rav.coff + c0); xb.load(rb + base * rbv.pitch + rbv.coff + c0);
 #pragma unroll
       for (int i = 0; i < VN; ++i) {
-        const float* ma = mra + ((long)n * C + c0 + i) * 2; const float* mb = mrb + ((long)n * C + c0 + i) * 2;
-        const double* a3 = acc + ((long)n * C + c0 + i) * 3;
-        float mg = (float)a3[0] * invV, mga = (float)a3[1] * invV, mgb = (float)a3[2] * invV;
         float g = d.v[i] * (a.v[i] > 0.f ? 1.f : 0.01f);
-        float na = (xa.v[i] - ma[0]) * ma[1], nb = (xb.v[i] - mb[0]) * mb[1];
-        oa.v[i] = ma[1] * (g - mg - na * mga);
-        ob.v[i] = mb[1] * (g - mg - nb * mgb);
+        float na = (xa.v[i] - ma0[i]) * ma1[i], nb = (xb.v[i] - mb0[i]) * mb1[i];
+        oa.v[i] = ma1[i] * (g - mg[i] - na * mga[i]);
+        ob.v[i] = mb1[i] * (g - mg[i] - nb * mgb[i]);
       }
       oa.store(da + base * dav.pitch + dav.coff + c0);
       ob.store(db + base * dbv.pitch + dbv.coff + c0);
     } else {
 #pragma unroll
       for (int i = 0; i < VN; ++i) {
-        const float* ma = mra + ((long)n * C + c0 + i) * 2;
-        const double* a3 = acc + ((long)n * C + c0 + i) * 3;
-        float mg = (float)a3[0] * invV, mga = (float)a3[1] * invV;
         float g = d.v[i] * (a.v[i] > 0.f ? 1.f : 0.01f);
         float na = a.v[i] > 0.f ? a.v[i] : a.v[i] * 100.f;
-        oa.v[i] = ma[1] * (g - mg - na * mga);
+        oa.v[i] = ma1[i] * (g - mg[i] - na * mga[i]);
       }
       oa.store(da + base * dav.pitch + dav.coff + c0);
     }

@@ -15,6 +15,7 @@
 #include "tc_gemm.cuh"
 #include "tc_conv.cuh"
 #include "tc_conv_halo.cuh"
+#include "tc_wgrad_halo.cuh"
 #include "tc_wgrad.cuh"
 
 namespace b200 {
@@ -293,6 +294,8 @@ struct Exec {
     if constexpr (kTC) {
       if (tc::wgrad_supported(x.C, dy.C, x.pitch, x.coff, dy.pitch, dy.coff)) {
         B200_PROFD(st, "conv_wgrad k%d %dx%d @%d", ks, x.C, dy.C, s.D);
+        if (tc::wgrad_halo_supported(x.C, dy.C, ks))
+          return tc::conv_wgrad_halo(x.p, x.pitch, x.coff, x.C, dy.p, dy.pitch, dy.coff, dy.C, s.N, s.D, s.H, s.W, dW, st);
         return tc::conv_wgrad(x.p, x.pitch, x.coff, x.C, dy.p, dy.pitch, dy.coff, dy.C, s.N, s.D, s.H, s.W, ks, dW, st);
       }
     }
