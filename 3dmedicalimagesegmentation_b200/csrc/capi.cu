@@ -8,7 +8,8 @@
 #include <vector>
 
 #include "../../include/unetr_b200.h"
-#include "exec.cuh"
+#include "exec_iface.h"
+#include "elementwise.cuh"
 #include "loss.cuh"
 #include "sliding.cuh"
 #include "tc_gemm.cuh"
@@ -39,8 +40,7 @@ void prof_end(cudaStream_t st) { cudaEventRecord(g_prof.back().b, st); }
 
 struct Handle {
   UnetrConfig cfg;
-  Exec<float>* f32;
-  Exec<bf16>* b16;
+  ExecIface* ex;
 };
 }  // namespace b200
 
@@ -75,33 +75,29 @@ void* b200_unetr_create(const b200_unetr_config* c) {
   if (!h) { set_error("out of host memory"); return nullptr; }
   h->cfg = UnetrConfig{c->batch, c->in_channels, c->out_channels, c->img0, c->img1, c->img2, fs, c->hidden_size, c->mlp_dim,
                        c->num_heads, c->conv_patch_embed, c->mode};
-  h->f32 = nullptr; h->b16 = nullptr;
-  if (c->mode == 0) h->f32 = new Exec<float>(h->cfg); else h->b16 = new Exec<bf16>(h->cfg);
+  h->ex = c->mode == 0 ? make_exec_f32(h->cfg) : make_exec_bf16(h->cfg);
   return h;
 }
 void b200_unetr_destroy(void* handle) {
   Handle* h = (Handle*)handle;
   if (!h) return;
-  delete h->f32; delete h->b16; delete h;
+  delete h->ex; delete h;
 }
 size_t b200_unetr_workspace_bytes(void* handle, int with_backward) {
   Handle* h = (Handle*)handle;
-  if (h->f32) { h->f32->layout(nullptr, with_backward != 0); return h->f32->w.bytes; }
-  h->b16->layout(nullptr, with_backward != 0); return h->b16->w.bytes;
+  return h->ex->workspace_bytes(with_backward != 0);
 }
 int b200_unetr_forward(void* handle, const float* const* params, const float* x, void* workspace, float* enc4_out,
                        float* logits_out, int flags, void* stream) {
   Handle* h = (Handle*)handle;
   B200_CHECK(h && params && x && workspace, "b200_unetr_forward: null argument");
-  if (h->f32) return h->f32->forward(params, x, (char*)workspace, enc4_out, logits_out, flags, (cudaStream_t)stream);
-  return h->b16->forward(params, x, (char*)workspace, enc4_out, logits_out, flags, (cudaStream_t)stream);
+  return h->ex->forward(params, x, (char*)workspace, enc4_out, logits_out, flags, (cudaStream_t)stream);
 }
 int b200_unetr_backward(void* handle, const float* const* params, float* const* grads, const float* x, void* workspace,
                         const float* d_enc4, const float* d_logits, int flags, void* stream) {
   Handle* h = (Handle*)handle;
   B200_CHECK(h && params && grads && x && workspace, "b200_unetr_backward: null argument");
-  if (h->f32) return h->f32->backward(params, grads, x, (char*)workspace, d_enc4, d_logits, flags, (cudaStream_t)stream);
-  return h->b16->backward(params, grads, x, (char*)workspace, d_enc4, d_logits, flags, (cudaStream_t)stream);
+  return h->ex->backward(params, grads, x, (char*)workspace, d_enc4, d_logits, flags, (cudaStream_t)stream);
 }
 
 // ---------------------------------------------------------------- DiceCE
@@ -208,7 +204,7 @@ int b200_sw_finalize(const float* acc, float* out, uint8_t* mask, const b200_sw_
 int b200_unetr_peek(void* handle, const char* name, void* dst, size_t cap) {
   Handle* h = (Handle*)handle;
   size_t bytes = 0;
-  const void* src = h->f32 ? h->f32->peek(name, &bytes) : h->b16->peek(name, &bytes);
+  const void* src = h->ex->peek(name, &bytes);
   B200_CHECK(src, "no workspace buffer named %s", name);
   if (bytes > cap) bytes = cap;
   B200_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToDevice));

@@ -204,6 +204,31 @@ struct EpConvTScatter {  // m = input voxel, n = co*8+tap -> channels-last 2x up
   }
 };
 
+template <class TO>
+struct EpConvTScatterTap {  // m = input voxel, n = tap*Co + co (tap-major packed weight, Co % 16 == 0): 16 channels per 32-byte store
+  TO* out; int D, H, W, pitch, coff, Co;
+  __device__ __forceinline__ long pos_of(int m, int tap) const {
+    int w = m % W; int t = m / W; int h = t % H; t /= H; int d = t % D; int nb = t / D;
+    return (((long)nb * 2 * D + 2 * d + (tap >> 2)) * 2 * H + 2 * h + ((tap >> 1) & 1)) * 2 * W + 2 * w + (tap & 1);
+  }
+  __device__ __forceinline__ void operator()(int, int m, int n, float acc) const {
+    int tap = n / Co, co = n - tap * Co;
+    out[pos_of(m, tap) * pitch + coff + co] = from_f<TO>(acc);
+  }
+  __device__ __forceinline__ void seg16(int, int m, int n0, const float* acc, int nvalid) const {
+    int tap = n0 / Co, co = n0 - tap * Co;
+    TO* dst = out + pos_of(m, tap) * pitch + coff + co;
+    constexpr int VN = Vec16<TO>::N;
+#pragma unroll
+    for (int q = 0; q < 16 / VN; ++q) {
+      Vec16<TO> o;
+#pragma unroll
+      for (int j = 0; j < VN; ++j) o.v[j] = acc[q * VN + j];
+      o.store(dst + q * VN);
+    }
+  }
+};
+
 struct EpHeadNcdhw {  // logits[b][co][v] = acc + bias[co]
   float* out; int Co; long V; const float* bias;
   __device__ __forceinline__ void operator()(int, int m, int n, float acc) const {

@@ -75,7 +75,7 @@ static int launch_cast(const TI* in, TO* out, long n, cudaStream_t st) {
 struct CastJob { const float* src; bf16* dst; long n; };
 struct CastJobs { CastJob j[64]; int count; };
 // fp32 -> bf16 for up to 64 tensors in one launch: grid (blocks per tensor, tensor)
-__global__ void multi_cast_kernel(const CastJobs jobs) {
+static __global__ void multi_cast_kernel(const CastJobs jobs) {
   const CastJob jb = jobs.j[blockIdx.y];
   long n4 = jb.n >> 2;
   const float4* s4 = reinterpret_cast<const float4*>(jb.src);
@@ -90,7 +90,31 @@ __global__ void multi_cast_kernel(const CastJobs jobs) {
     jb.dst[i] = __float2bfloat16_rn(jb.src[i]);
 }
 
-__global__ void add_kernel(float* __restrict__ dst, const float* __restrict__ src, long n) {
+// Re-layout jobs of the bf16 engine in ONE launch (was one launch per conv layer):
+//  kind 0: transposed conv  fp32 [Ci][Co][8] -> bf16 [Ci][8][Co]
+//  kind 1: conv             fp32 [Co][Ci][taps] -> fwd bf16 [tap][co][ci] and dgrad bf16 [taps-1-tap][ci][co]
+struct PackJob { const float* src; bf16* d0; bf16* d1; int a, b, taps, kind; };
+struct PackJobs { PackJob j[32]; int count; };
+static __global__ void multi_pack_kernel(const PackJobs jobs) {
+  const PackJob jb = jobs.j[blockIdx.y];
+  if (jb.kind == 0) {
+    const int Co = jb.b; const long total = (long)jb.a * Co * 8;
+    for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+      int tap = (int)(e & 7); long r = e >> 3; int co = (int)(r % Co); long ci = r / Co;
+      jb.d0[(ci * 8 + tap) * Co + co] = __float2bfloat16_rn(jb.src[e]);
+    }
+  } else {
+    const int Co = jb.a, Ci = jb.b, taps = jb.taps; const long total = (long)Co * Ci * taps;
+    for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+      int tap = (int)(e % taps); long r = e / taps; int ci = (int)(r % Ci); int co = (int)(r / Ci);
+      bf16 v = __float2bfloat16_rn(jb.src[e]);
+      jb.d0[((long)tap * Co + co) * Ci + ci] = v;
+      jb.d1[((long)(taps - 1 - tap) * Ci + ci) * Co + co] = v;
+    }
+  }
+}
+
+static __global__ void add_kernel(float* __restrict__ dst, const float* __restrict__ src, long n) {
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   long stride = (long)gridDim.x * blockDim.x;
   for (; i < n; i += stride) dst[i] += src[i];
@@ -242,20 +266,23 @@ template <class TG>
 __global__ void layernorm_bwd_params_kernel(const TG* __restrict__ g, const float* __restrict__ x,
                                             const float* __restrict__ stats, float* __restrict__ dgamma,
                                             float* __restrict__ dbeta, int M, int H) {
-  __shared__ float sg[8][33], sb[8][33];
+  __shared__ float sg[32][33], sb[32][33];
   int col = blockIdx.x * 32 + threadIdx.x;
   float a = 0.f, b = 0.f;
-  if (col < H)
-    for (int r = blockIdx.y * 8 + threadIdx.y; r < M; r += 8 * gridDim.y) {
+  if (col < H) {
+#pragma unroll 4
+    for (int r = threadIdx.y; r < M; r += 32) {
       float gg = to_f(g[(long)r * H + col]);
       a += gg * (x[(long)r * H + col] - stats[2 * r]) * stats[2 * r + 1];
       b += gg;
     }
+  }
   sg[threadIdx.y][threadIdx.x] = a; sb[threadIdx.y][threadIdx.x] = b;
   __syncthreads();
   if (threadIdx.y == 0 && col < H) {
-    for (int i = 1; i < 8; ++i) { a += sg[i][threadIdx.x]; b += sb[i][threadIdx.x]; }
-    atomicAdd(dgamma + col, a); atomicAdd(dbeta + col, b);   // outputs zeroed by the launcher
+#pragma unroll
+    for (int i = 1; i < 32; ++i) { a += sg[i][threadIdx.x]; b += sb[i][threadIdx.x]; }
+    dgamma[col] = a; dbeta[col] = b;
   }
 }
 template <class TG>
@@ -267,8 +294,7 @@ static int launch_layernorm_bwd(const TG* g, const float* x, const float* stats,
   else layernorm_bwd_dx_kernel<TG><<<cdiv(M, 8), 256, 0, st>>>(g, x, stats, gamma, dx_res, dx_out, dx_out_cast, M, H);
   B200_LAUNCH_CHECK();
   if (dgamma) {
-    cudaMemsetAsync(dgamma, 0, sizeof(float) * H, st); cudaMemsetAsync(dbeta, 0, sizeof(float) * H, st);
-    layernorm_bwd_params_kernel<TG><<<dim3(cdiv(H, 32), 12), dim3(32, 8), 0, st>>>(g, x, stats, dgamma, dbeta, M, H);
+    layernorm_bwd_params_kernel<TG><<<cdiv(H, 32), dim3(32, 32), 0, st>>>(g, x, stats, dgamma, dbeta, M, H);
     B200_LAUNCH_CHECK();
   }
   return 0;
@@ -277,29 +303,31 @@ static int launch_layernorm_bwd(const TG* g, const float* x, const float* stats,
 // ------------------------------------------------------------------ column sums (bias gradients)
 template <class TG>
 __global__ void colsum_kernel(const TG* __restrict__ g, float* __restrict__ out, int M, int N) {
-  __shared__ float s[8][33];
+  __shared__ float s[32][33];
   int col = blockIdx.x * 32 + threadIdx.x;
   float a = 0.f;
-  if (col < N)
-    for (int r = blockIdx.y * 8 + threadIdx.y; r < M; r += 8 * gridDim.y) a += to_f(g[(long)r * N + col]);
+  if (col < N) {
+#pragma unroll 4
+    for (int r = threadIdx.y; r < M; r += 32) a += to_f(g[(long)r * N + col]);
+  }
   s[threadIdx.y][threadIdx.x] = a;
   __syncthreads();
   if (threadIdx.y == 0 && col < N) {
-    for (int i = 1; i < 8; ++i) a += s[i][threadIdx.x];
-    atomicAdd(out + col, a);   // out zeroed by the launcher
+#pragma unroll
+    for (int i = 1; i < 32; ++i) a += s[i][threadIdx.x];
+    out[col] = a;
   }
 }
 template <class TG>
 static int launch_colsum(const TG* g, float* out, int M, int N, cudaStream_t st) {
   B200_PROF("colsum", st);
-  cudaMemsetAsync(out, 0, sizeof(float) * N, st);
-  colsum_kernel<TG><<<dim3(cdiv(N, 32), N >= 2048 ? 4 : 12), dim3(32, 8), 0, st>>>(g, out, M, N);
+  colsum_kernel<TG><<<cdiv(N, 32), dim3(32, 32), 0, st>>>(g, out, M, N);
   B200_LAUNCH_CHECK();
   return 0;
 }
 
 // out[row % C] += sum_v x[row, v]   (x is [rows, V] fp32; bias gradient of the NCDHW head)
-__global__ void rowsum_atomic_kernel(const float* __restrict__ x, float* __restrict__ out, long V, int C) {
+static __global__ void rowsum_atomic_kernel(const float* __restrict__ x, float* __restrict__ out, long V, int C) {
   int row = blockIdx.y;
   long per = (V + gridDim.x - 1) / gridDim.x;
   long v0 = (long)blockIdx.x * per, v1 = min(V, v0 + per);
@@ -332,7 +360,7 @@ __global__ void unshuffle_kernel(const T* __restrict__ y, ClView yv, int Co, int
   }
 }
 // fp32 [Ci][Co][8] -> bf16 [Ci][8][Co]  (tap-major copy of a transposed-conv weight)
-__global__ void pack_convT_tapmajor_kernel(const float* __restrict__ W, bf16* __restrict__ out, int Ci, int Co) {
+static __global__ void pack_convT_tapmajor_kernel(const float* __restrict__ W, bf16* __restrict__ out, int Ci, int Co) {
   long total = (long)Ci * Co * 8;
   for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
     int tap = (int)(e & 7); long r = e >> 3; int co = (int)(r % Co); long ci = r / Co;
@@ -340,7 +368,7 @@ __global__ void pack_convT_tapmajor_kernel(const float* __restrict__ W, bf16* __
   }
 }
 // bf16 patch rows A[tok][k] from the NCDHW fp32 volume (same k order as the weight: perceptron or conv)
-__global__ void patch_gather_kernel(const float* __restrict__ x, bf16* __restrict__ A, int C, int S0, int S1, int S2, int g0, int g1, int g2,
+static __global__ void patch_gather_kernel(const float* __restrict__ x, bf16* __restrict__ A, int C, int S0, int S1, int S2, int g0, int g1, int g2,
                                     int conv_order, long total) {
   for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
     int Kp = 4096 * C; int k = (int)(e % Kp); int tok = (int)(e / Kp);
@@ -353,7 +381,7 @@ __global__ void patch_gather_kernel(const float* __restrict__ x, bf16* __restric
 }
 
 // dpos[l,h] = sum_b dx[b,l,h]
-__global__ void batchsum_kernel(const float* __restrict__ dx, float* __restrict__ out, int B, long LH) {
+static __global__ void batchsum_kernel(const float* __restrict__ dx, float* __restrict__ out, int B, long LH) {
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= LH) return;
   float a = 0.f;
@@ -454,7 +482,7 @@ __global__ void in_stats_kernel(const T* __restrict__ x, ClView xv, int C, long 
     }
   }
 }
-__global__ void in_finalize_kernel(const double* __restrict__ acc, float* __restrict__ mr, int NC, double invV) {
+static __global__ void in_finalize_kernel(const double* __restrict__ acc, float* __restrict__ mr, int NC, double invV) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= NC) return;
   double mean = acc[2 * i] * invV;

@@ -18,11 +18,10 @@
 #include "tc_wgrad_halo.cuh"
 #include "tc_wgrad.cuh"
 
+#include "exec_iface.h"
+
 namespace b200 {
 
-struct UnetrConfig {
-  int B, Cin, ncls, S0, S1, S2, fs, hidden, mlp, heads, conv_patch, mode;  // mode 0 = fp32, 1 = bf16
-};
 
 enum ParamIdx {
   P_POS = 0, P_PATCH_W, P_PATCH_B, P_BLK0 = 3,
@@ -217,18 +216,19 @@ struct Exec {
       jobs.count = n;
       multi_cast_kernel<<<dim3(64, n), 256, 0, st>>>(jobs);
       B200_LAUNCH_CHECK();
+      PackJobs pj; int m = 0;
       for (int i = 0; i < 10; ++i) {
         int p, ci, co; convT_desc(i, p, ci, co);
-        pack_convT_tapmajor_kernel<<<(unsigned)min(64L, (long)(convT_elems(i) + 255) / 256), 256, 0, st>>>(P[p], w.wTt[i], ci, co);
-        B200_LAUNCH_CHECK();
+        pj.j[m++] = PackJob{P[p], w.wTt[i], nullptr, ci, co, 8, 0};
       }
       for (int i = 0; i < 15; ++i) {
         int p, ci, co, ks; conv_desc(i, p, ci, co, ks);
         if (ci % 16 || co % 16) continue;   // those layers stay on the CUDA-core engine
-        long tot = (long)ci * co * ks * ks * ks;
-        pack_conv_weights_kernel<<<(unsigned)min(64L, (tot + 255) / 256), 256, 0, st>>>(P[p], w.wcf[i], w.wcd[i], co, ci, ks * ks * ks);
-        B200_LAUNCH_CHECK();
+        pj.j[m++] = PackJob{P[p], w.wcf[i], w.wcd[i], co, ci, ks * ks * ks, 1};
       }
+      pj.count = m;
+      multi_pack_kernel<<<dim3(32, m), 256, 0, st>>>(pj);
+      B200_LAUNCH_CHECK();
     }
     return 0;
   }
@@ -479,7 +479,14 @@ struct Exec {
   int convT_fwd(const T* x, long ldx, int Ci, int in_level, const float* W, Cl<T> out, cudaStream_t st) {
     if constexpr (kTC) {
       if (cur_params) {
-        const bf16* Wb = convT_packed(cur_params, W);
+        const bool tapm = out.C % 16 == 0 && out.pitch % 8 == 0 && out.coff % 8 == 0;
+        const bf16* Wb = convT_packed(cur_params, W, tapm);
+        if (Wb && tapm) {   // tap-major weight: 16 consecutive GEMM columns = 16 channels of one output voxel (32-byte stores)
+          B200_PROFD(st, "convT_fwd %d->%d @%d", Ci, out.C, sp(in_level).D);
+          Sp s = sp(in_level);
+          EpConvTScatterTap<T> ep = {out.p, s.D, s.H, s.W, out.pitch, out.coff, out.C};
+          return tc::gemm(tc::operand(x, ldx, 1), tc::operand(Wb, 1, (long)out.C * 8), ep, (int)s.rows(), out.C * 8, Ci, 1, 1, st);
+        }
         if (Wb) {   // [rows, Ci] x W[Ci][Co*8] (MN-major B), scatter epilogue writes straight into the concat buffer
           B200_PROFD(st, "convT_fwd %d->%d @%d", Ci, out.C, sp(in_level).D);
           Sp s = sp(in_level);

@@ -1,0 +1,23 @@
+// Type-erased handle on Exec<T> so the fp32 and bf16 executors compile in separate translation units (parallel build).
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+
+namespace b200 {
+
+struct UnetrConfig {
+  int B, Cin, ncls, S0, S1, S2, fs, hidden, mlp, heads, conv_patch, mode;  // mode 0 = fp32, 1 = bf16
+};
+
+struct ExecIface {
+  virtual ~ExecIface() {}
+  virtual size_t workspace_bytes(bool with_backward) = 0;
+  virtual int forward(const float* const* P, const float* x, char* ws, float* enc4_out, float* logits_out, int flags, cudaStream_t st) = 0;
+  virtual int backward(const float* const* P, float* const* G, const float* x, char* ws, const float* d_enc4, const float* d_logits, int flags,
+                       cudaStream_t st) = 0;
+  virtual const void* peek(const char* name, size_t* bytes) = 0;
+};
+ExecIface* make_exec_f32(const UnetrConfig& c);
+ExecIface* make_exec_bf16(const UnetrConfig& c);
+
+}  // namespace b200

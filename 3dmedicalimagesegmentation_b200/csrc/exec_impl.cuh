@@ -1,0 +1,20 @@
+// ExecIface adaptor over Exec<T>; included by exec_f32.cu / exec_bf16.cu only.
+#pragma once
+#include "exec.cuh"
+
+namespace b200 {
+template <class T>
+struct ExecImpl : ExecIface {
+  Exec<T> e;
+  explicit ExecImpl(const UnetrConfig& c) : e(c) {}
+  size_t workspace_bytes(bool with_backward) override { e.layout(nullptr, with_backward); return e.w.bytes; }
+  int forward(const float* const* P, const float* x, char* ws, float* enc4_out, float* logits_out, int flags, cudaStream_t st) override {
+    return e.forward(P, x, ws, enc4_out, logits_out, flags, st);
+  }
+  int backward(const float* const* P, float* const* G, const float* x, char* ws, const float* d_enc4, const float* d_logits, int flags,
+               cudaStream_t st) override {
+    return e.backward(P, G, x, ws, d_enc4, d_logits, flags, st);
+  }
+  const void* peek(const char* name, size_t* bytes) override { return e.peek(name, bytes); }
+};
+}  // namespace b200

@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(256) dicece_fwd_kernel(const float* __restrict
   }
 }
 // out[0]=loss, out[1]=dice term, out[2]=ce term ; coef[b][c] = (a, bb) with d dice / d p = a*t + bb
-__global__ void dicece_finalize_kernel(const double* __restrict__ acc, int B, int C, long V, float* __restrict__ out,
+static __global__ void dicece_finalize_kernel(const double* __restrict__ acc, int B, int C, long V, float* __restrict__ out,
                                        float* __restrict__ coef) {
   __shared__ double sd[256];
   double local = 0.0;
@@ -133,7 +133,7 @@ __device__ __forceinline__ long rank_off(const RankGeom& g, int part, int c, int
   return (long)c * g.sc + (long)g.idx[part] * g.ss + (long)f0 * g.sf0 + (long)f1 * g.sf1;
 }
 // gram[c][i][j] += sum_f s_i[c,f] s_j[c,f]      grid (C, splits), 256 threads = 16x16 pairs
-__global__ void __launch_bounds__(256) rank_gram_kernel(RankGeom g, double* __restrict__ gram) {
+static __global__ void __launch_bounds__(256) rank_gram_kernel(RankGeom g, double* __restrict__ gram) {
   __shared__ float tile[16][65];
   int c = blockIdx.x;
   int F = g.F0 * g.F1;
@@ -159,7 +159,7 @@ __device__ __forceinline__ void rank_triplet(int t, int& r, int& s, int& d) {
 }
 // per channel: cos matrix, loss contribution, and the 16x16 coefficient matrix coef[c][i][j] such that
 // d loss / d s_i = sum_j coef[c][i][j] * s_j          grid C blocks of 576 threads... (use 576 = 18 warps)
-__global__ void __launch_bounds__(576) rank_loss_kernel(const double* __restrict__ gram, int C, float temperature,
+static __global__ void __launch_bounds__(576) rank_loss_kernel(const double* __restrict__ gram, int C, float temperature,
                                                         double* __restrict__ loss, float* __restrict__ coef) {
   __shared__ float cosm[16][16], A[16][16], nrm[16], rawn[16];
   __shared__ float wsum[18];
@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(576) rank_loss_kernel(const double* __restrict
   }
 }
 // grad slice i [c,f] = up * sum_j coef[c][i][j] s_j[c,f]         grid (C, ceil(F/256))
-__global__ void __launch_bounds__(256) rank_grad_kernel(RankGeom g, const float* __restrict__ coef,
+static __global__ void __launch_bounds__(256) rank_grad_kernel(RankGeom g, const float* __restrict__ coef,
                                                         const float* __restrict__ upstream) {
   __shared__ float cf[256];
   int c = blockIdx.x;

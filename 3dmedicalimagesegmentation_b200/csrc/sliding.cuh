@@ -19,7 +19,7 @@ struct SwWindow { int b, s0, s1, s2; };
 struct SwBatch { SwWindow w[16]; int n; };
 
 // windows[k][c][roi] = vol[b][c][start+off - pad] or cval outside
-__global__ void sw_gather_kernel(const float* __restrict__ vol, float* __restrict__ windows, SwGeom g, SwBatch wb, float cval) {
+static __global__ void sw_gather_kernel(const float* __restrict__ vol, float* __restrict__ windows, SwGeom g, SwBatch wb, float cval) {
   long per = (long)g.C * g.r0 * g.r1 * g.r2;
   long total = per * wb.n;
   for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
@@ -34,7 +34,7 @@ __global__ void sw_gather_kernel(const float* __restrict__ vol, float* __restric
   }
 }
 // acc[b][c][start+off] += pred[k][c][off]   (one window per launch keeps the reference's summation order)
-__global__ void sw_accumulate_kernel(float* __restrict__ acc, const float* __restrict__ pred, SwGeom g, SwWindow w) {
+static __global__ void sw_accumulate_kernel(float* __restrict__ acc, const float* __restrict__ pred, SwGeom g, SwWindow w) {
   long per = (long)g.C * g.r0 * g.r1 * g.r2;
   for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < per; e += (long)gridDim.x * blockDim.x) {
     long r = e;
@@ -45,7 +45,7 @@ __global__ void sw_accumulate_kernel(float* __restrict__ acc, const float* __res
 }
 struct SwStarts { int n0, n1, n2; int s0[64], s1[64], s2[64]; };
 // out[b][c][d][h][w] = acc[b][c][d+pd][h+ph][w+pw] / count ; optional argmax over c -> mask[b][d][h][w]
-__global__ void sw_finalize_kernel(const float* __restrict__ acc, float* __restrict__ out, unsigned char* __restrict__ mask,
+static __global__ void sw_finalize_kernel(const float* __restrict__ acc, float* __restrict__ out, unsigned char* __restrict__ mask,
                                    SwGeom g, SwStarts st, int B) {
   long vox = (long)g.D * g.H * g.W;
   long total = (long)B * vox;

@@ -59,7 +59,7 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
 
-__global__ void __launch_bounds__(CONV_THREADS, 1)
+static __global__ void __launch_bounds__(CONV_THREADS, 1)
 conv_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const ConvParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -364,7 +364,7 @@ static int conv(const bf16* x, int in_pitch, int in_coff, int Ci, int N, int D, 
 }  // namespace tc
 
 // W fp32 [Co][Ci][taps] -> fwd[tap][co][ci] and dgr[taps-1-tap][ci][co] (bf16)
-__global__ void pack_conv_weights_kernel(const float* __restrict__ W, bf16* __restrict__ fwd, bf16* __restrict__ dgr, int Co, int Ci, int taps) {
+static __global__ void pack_conv_weights_kernel(const float* __restrict__ W, bf16* __restrict__ fwd, bf16* __restrict__ dgr, int Co, int Ci, int taps) {
   long total = (long)Co * Ci * taps;
   for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
     int tap = (int)(e % taps); long r = e / taps; int ci = (int)(r % Ci); int co = (int)(r / Ci);

@@ -134,6 +134,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool dbg = p.dbg && blockIdx.x == 0;
   if (dbg && threadIdx.x == 0) p.dbg[0] = clock64();
+  if (p.dbg && threadIdx.x == 0) { long long g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g)); p.dbg[64 + 2 * blockIdx.x] = g; }
   const int kblocks_all = (p.K + BK - 1) / BK;
   const long total_tiles = (long)p.tiles_m * p.tiles_n * p.batches * p.ksplit;
 
@@ -246,6 +247,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
   tc_fence_before();
   __syncthreads();
   if (dbg && threadIdx.x == 0) p.dbg[5] = clock64();
+  if (p.dbg && threadIdx.x == 0) { long long g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g)); p.dbg[65 + 2 * blockIdx.x] = g; }
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");

@@ -37,7 +37,7 @@ __device__ __forceinline__ uint64_t smem_desc_mn(uint32_t addr, uint32_t lbo_byt
   return d;
 }
 
-__global__ void __launch_bounds__(192, 1)
+static __global__ void __launch_bounds__(192, 1)
 wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_dy, const WgradParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);

@@ -3,7 +3,7 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 pkg = importlib.import_module("3dmedicalimagesegmentation_b200")
 L = pkg._lib; lib = L.load(); dev = "cuda:0"
-dbg = torch.zeros(32, dtype=torch.int64, device=dev)
+dbg = torch.zeros(512, dtype=torch.int64, device=dev)
 def run(M, N, K, a_mn=0, b_mn=0, iters=20, cold=False):
     a = torch.randn(M, K, device=dev).bfloat16(); b = torch.randn(N, K, device=dev).bfloat16()
     if a_mn: a = a.t().contiguous()
@@ -24,9 +24,11 @@ def run(M, N, K, a_mn=0, b_mn=0, iters=20, cold=False):
     f(); torch.cuda.synchronize(); lib.b200_test_set_debug_buffer(None)
     d = dbg.cpu().tolist(); t0 = d[0]
     rel = lambda i: (d[i] - t0) if d[i] else -1
+    import numpy as np
+    g = np.array(d[64:64 + 2 * 148]).reshape(148, 2); g = g[g[:, 0] > 0]
+    if len(g):
+        t00 = g[:, 0].min(); dur = g[:, 1] - g[:, 0]
+        print(f"   globaltimer: {len(g)} CTAs, start spread {g[:,0].max()-t00} ns, kernel span {g[:,1].max()-t00} ns, per-CTA duration min/med/max {dur.min()}/{int(np.median(dur))}/{dur.max()} ns")
     print(f"gemm {M}x{N}x{K} mn={a_mn}{b_mn} {'cold' if cold else 'hot '}: {us:7.1f} us {2*M*N*K/us/1e6:7.1f} TF | cyc: setup {rel(1)} prod_done {rel(2)} kb0..3 {[rel(8+i) for i in range(4)]} mma_done {rel(3)} acc_ready {rel(4)} end {rel(5)} | mma_issued {[rel(12+i) for i in range(4)]} prod_issued {[rel(16+i) for i in range(4)]}")
-for bn in ("", "64", "128", "256"):
-    if bn: os.environ["B200_GEMM_BN"] = bn
-    print("BN override:", bn or "auto")
-    run(432, 3072, 768); run(432, 768, 3072); run(432, 2304, 768); run(432, 768, 768)
-run(128, 64, 768)
+run(432, 3072, 768); run(432, 3072, 768, cold=True); run(432, 768, 3072); run(432, 768, 3072, cold=True); run(432, 2304, 768); run(432, 768, 768); run(432, 768, 768, cold=True)
+run(3072, 768, 432, a_mn=1, b_mn=1); run(768, 3072, 432, a_mn=1, b_mn=1)
