@@ -28,6 +28,7 @@ const char* get_error() { return g_err; }
 
 unsigned long long g_launches = 0;
 bool g_prof_on = false;
+bool g_prof_coarse = false;
 struct ProfRec { std::string tag; cudaEvent_t a, b; };
 static std::vector<ProfRec> g_prof;
 void prof_begin(const char* tag, cudaStream_t st) {
@@ -211,14 +212,14 @@ int b200_unetr_peek(void* handle, const char* name, void* dst, size_t cap) {
   return 0;
 }
 unsigned long long b200_launch_count(void) { return g_launches; }
-void b200_prof_enable(int on) { g_prof_on = on != 0; }
+void b200_prof_enable(int on) { g_prof_on = on == 1; g_prof_coarse = on == 2; }
 /* synchronises the device, writes "tag ms count\n" lines (sorted by time) and clears the records */
 int b200_prof_report(char* buf, int cap) {
   cudaDeviceSynchronize();
   std::map<std::string, std::pair<double, int>> acc;
   for (auto& r : g_prof) {
     float ms = 0.f;
-    cudaEventElapsedTime(&ms, r.a, r.b);
+    if (cudaEventElapsedTime(&ms, r.a, r.b) != cudaSuccess) { cudaGetLastError(); ms = 0.f; }
     auto& e = acc[r.tag]; e.first += ms; e.second += 1;
     cudaEventDestroy(r.a); cudaEventDestroy(r.b);
   }

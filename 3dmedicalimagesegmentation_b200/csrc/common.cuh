@@ -48,11 +48,14 @@ extern unsigned long long g_launches;
 void prof_begin(const char* tag, cudaStream_t st);
 void prof_end(cudaStream_t st);
 extern bool g_prof_on;
+extern bool g_prof_coarse;   // phase-level regions only (no per-op events: their ~8 us floor hides small kernels)
 struct ProfScope {
   cudaStream_t st; bool active;
   ProfScope(const char* tag, cudaStream_t s) : st(s), active(g_prof_on) { if (active) prof_begin(tag, st); }
   ~ProfScope() { if (active) prof_end(st); }
 };
+#define B200_PROFC_BEGIN(tag, st) do { if (b200::g_prof_coarse) b200::prof_begin(tag, st); } while (0)
+#define B200_PROFC_END(st) do { if (b200::g_prof_coarse) b200::prof_end(st); } while (0)
 #define B200_PROF(tag, st) b200::ProfScope _prof_scope(tag, st)
 // detailed variant: printf-style tag, formatted only when profiling is on
 #define B200_PROFD(st, ...)                                   \

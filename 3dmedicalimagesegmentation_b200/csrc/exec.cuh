@@ -331,13 +331,31 @@ struct Exec {
       B200_TRY(in_apply(cl<const T>(c2.p, Co, 0, Co), r.mr2, c3.p, r.mr3, out, Vs, st));
       return 0;
     }
-    B200_TRY(conv_fwd(x, s, W1, Co, 3, c1, w.stat_acc, &done, st));
-    B200_TRY(in_stats(cl<const T>(c1.p, Co, 0, Co), Vs, r.mr1, st, done));
+    bool fused13 = false;   // conv1 (3^3) and conv3 (1^3) read the same x: one kernel, two accumulators, two stat sets
+    if constexpr (kTC) {
+      int i1 = conv_index(W1), i3 = conv_index(W3);
+      if (i1 >= 0 && i3 >= 0 && tc::conv_supported(x.C, Co, x.pitch, x.coff, Co, 0) && tc::conv_halo_fused_supported(x.C, Co, 1)) {
+        B200_PROFD(st, "conv_fwd k3+k1 %d->%d @%d", x.C, Co, s.D);
+        double* st3 = w.stat_acc + (size_t)2 * c.B * 8 * c.fs;
+        B200_CUDA(cudaMemsetAsync(w.stat_acc, 0, sizeof(double) * 4 * c.B * 8 * c.fs, st));
+        tc::HaloFused fu = {1, w.wcf[i3], c3.p, Co, 0, st3, nullptr, 0, 0};
+        B200_TRY(tc::conv_halo(x.p, x.pitch, x.coff, x.C, s.N, s.D, s.H, s.W, w.wcf[i1], Co, c1.p, Co, 0, 0, w.stat_acc, st, &fu));
+        in_finalize_kernel<<<cdiv(c.B * Co, 128), 128, 0, st>>>(w.stat_acc, r.mr1, c.B * Co, 1.0 / (double)Vs); B200_LAUNCH_CHECK();
+        in_finalize_kernel<<<cdiv(c.B * Co, 128), 128, 0, st>>>(st3, r.mr3, c.B * Co, 1.0 / (double)Vs); B200_LAUNCH_CHECK();
+        fused13 = true;
+      }
+    }
+    if (!fused13) {
+      B200_TRY(conv_fwd(x, s, W1, Co, 3, c1, w.stat_acc, &done, st));
+      B200_TRY(in_stats(cl<const T>(c1.p, Co, 0, Co), Vs, r.mr1, st, done));
+    }
     B200_TRY(in_apply(cl<const T>(c1.p, Co, 0, Co), r.mr1, nullptr, nullptr, a1, Vs, st));
     B200_TRY(conv_fwd(cl<const T>(a1.p, Co, 0, Co), s, W2, Co, 3, c2, w.stat_acc, &done, st));
     B200_TRY(in_stats(cl<const T>(c2.p, Co, 0, Co), Vs, r.mr2, st, done));
-    B200_TRY(conv_fwd(x, s, W3, Co, 1, c3, w.stat_acc, &done, st));
-    B200_TRY(in_stats(cl<const T>(c3.p, Co, 0, Co), Vs, r.mr3, st, done));
+    if (!fused13) {
+      B200_TRY(conv_fwd(x, s, W3, Co, 1, c3, w.stat_acc, &done, st));
+      B200_TRY(in_stats(cl<const T>(c3.p, Co, 0, Co), Vs, r.mr3, st, done));
+    }
     if (head && out.pitch == Co && out.coff == 0) {
       B200_PROF("norm_head_fwd", st);
       dim3 g((unsigned)min(148L * 4, (Vs + 255) / 256), c.B);
@@ -397,6 +415,14 @@ struct Exec {
     if (dW1) { B200_CUDA(cudaMemsetAsync(dW1, 0, sizeof(float) * Co * Ci * 27, st)); B200_TRY(conv_wgrad(x, dc1, s, 3, dW1, st)); }
     if (dW3) { B200_CUDA(cudaMemsetAsync(dW3, 0, sizeof(float) * Co * Ci, st)); B200_TRY(conv_wgrad(x, dc3, s, 1, dW3, st)); }
     if (dx.p) {
+      if constexpr (kTC) {   // dx = dgrad3x3(dc1) + dgrad1x1(dc3) in one kernel (second input tile, same accumulator)
+        int i1 = conv_index(W1), i3 = conv_index(W3);
+        if (i1 >= 0 && i3 >= 0 && tc::conv_supported(Co, Ci, Co, 0, dx.pitch, dx.coff) && tc::conv_halo_fused_supported(Co, Ci, 2)) {
+          B200_PROFD(st, "conv_dgrad k3+k1 %d->%d @%d", Co, Ci, s.D);
+          tc::HaloFused fu = {2, w.wcd[i3], nullptr, 0, 0, nullptr, dc3.p, dc3.pitch, dc3.coff};
+          return tc::conv_halo(dc1.p, dc1.pitch, dc1.coff, Co, s.N, s.D, s.H, s.W, w.wcd[i1], Ci, dx.p, dx.pitch, dx.coff, 0, nullptr, st, &fu);
+        }
+      }
       B200_TRY(conv_dgrad(dc1, s, W1, Ci, 3, dx, 0, st));
       B200_TRY(conv_dgrad(dc3, s, W3, Ci, 1, dx, 1, st));
     }
@@ -406,6 +432,7 @@ struct Exec {
   // ------------------------------------------------------------ forward
   int forward(const float* const* P, const float* x_in, char* ws, float* enc4_out, float* logits_out, int flags, cudaStream_t st) {
     layout(ws, false);
+    B200_PROFC_BEGIN("F1 pack+patch", st);
     int B = c.B, fs = c.fs;
     B200_TRY(pack_weights(P, st));
     cur_params = P;
@@ -423,6 +450,7 @@ struct Exec {
         B200_TRY(launch_contract(al, ld2<float, false>(P[P_PATCH_W], 4096L * c.Cin, 1), ep, M, H, 4096 * c.Cin, 1, 1, st));
       }
     }
+    B200_PROFC_END(st); B200_PROFC_BEGIN("F2 vit", st);
     // --- transformer blocks (a6-a8)
     float scale = 1.0f / sqrtf((float)dh);
     for (int i = 0; i < 12; ++i) {
@@ -442,6 +470,7 @@ struct Exec {
     B200_TRY(launch_layernorm_fwd<T>(w.hs[11], P[P_NORM_W], P[P_NORM_B], w.vit_out, w.lnfs, M, H, st));
     for (int k = 0; k < 3; ++k) B200_TRY(launch_cast<float, T>(w.hs[3 + 3 * k], w.hsT[k], (long)M * H, st));
 
+    B200_PROFC_END(st); B200_PROFC_BEGIN("F3 encoders", st);
     // --- encoder1 on the input volume (a9) -> upper half of concat2
     const bool edge = edge_co_ok(fs);   // dedicated small-channel kernels (fp32 input, fused head) available for this feature_size
     if (!edge) B200_TRY(launch_layout<T>(x_in, nullptr, w.xcl, B, c.Cin, V[0], c.Cin, 0, 0, 0, st));
@@ -455,6 +484,7 @@ struct Exec {
     B200_TRY(convT_fwd(w.e3a, 4 * fs, 4 * fs, 3, P[P_E3_T1], cl(w.cat4, 8 * fs, 4 * fs, 4 * fs), st));
     B200_TRY(convT_fwd(w.hsT[2], H, H, 4, P[P_E4_T0], cl(w.cat5, 16 * fs, 8 * fs, 8 * fs), st));
     if (enc4_out) B200_TRY(launch_layout<T>(nullptr, enc4_out, w.cat5, B, 8 * fs, V[3], 16 * fs, 8 * fs, 1, 0, st));
+    B200_PROFC_END(st); B200_PROFC_BEGIN("F4 decoders+head", st);
     // --- decoder5..2 (a11)
     B200_TRY(convT_fwd(w.vit_out, H, H, 4, P[P_D5_T], cl(w.cat5, 16 * fs, 0, 8 * fs), st));
     B200_TRY(res_fwd(cl<const T>(w.cat5, 16 * fs, 0, 16 * fs), 3, P[P_D5_C1], P[P_D5_C2], P[P_D5_C3], w.rs[1], cl(w.d3, 8 * fs, 0, 8 * fs), st));
@@ -473,6 +503,7 @@ struct Exec {
       EpHeadNcdhw ep = {logits_out, c.ncls, V[0], P[P_OUT_B]};
       B200_TRY(launch_contract(ld2<T, false>(w.d0, fs, 1), ld2<float, false>(P[P_OUT_W], fs, 1), ep, (int)(B * V[0]), c.ncls, fs, 1, 1, st));
     }
+    B200_PROFC_END(st);
     return 0;
   }
 
@@ -553,6 +584,7 @@ struct Exec {
     bool has_denc4 = (flags & FLAG_HAS_DENC4) && d_enc4;
     bool vit_from_top = false;  // does gradient reach blocks 10, 11 and the final LayerNorm?
     for (int k = 0; k < 3; ++k) B200_CUDA(cudaMemsetAsync(w.dhs[k], 0, sizeof(float) * M * H, st));
+    B200_PROFC_BEGIN("B1 head+decoders+encoders", st);
 
     if (dec) {
       int rows = (int)(B * V[0]);
@@ -634,6 +666,7 @@ struct Exec {
       return 0;
 
     // --- ViT backward
+    B200_PROFC_END(st); B200_PROFC_BEGIN("B2 vit+patch", st);
     float scale = 1.0f / sqrtf((float)dh);
     int top = 11;
     if (vit_from_top) {
@@ -682,6 +715,7 @@ struct Exec {
     }
     if (G[P_PATCH_B]) B200_TRY(launch_colsum<float>(w.dx, G[P_PATCH_B], M, H, st));
     if (G[P_POS]) { batchsum_kernel<<<cdiv((long)L * H, 256), 256, 0, st>>>(w.dx, G[P_POS], B, (long)L * H); B200_LAUNCH_CHECK(); }
+    B200_PROFC_END(st);
     return 0;
   }
 

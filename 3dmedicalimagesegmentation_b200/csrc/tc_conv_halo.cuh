@@ -33,6 +33,10 @@ struct HaloParams {
   int resident;                  // all 27*nchunk weight tiles stay in smem
   int stage_bytes, stages; uint32_t tmem_cols;
   bf16* out; int pitch, coff, accumulate; double* stats;
+  // fused 1x1x1 convolution of the residual block (weight tile index 27*nchunk + chunk, resident weights only):
+  //  mode2 == 1: second OUTPUT  out2 = conv1x1(x; W3)      (forward: conv1 and conv3 read the same x)
+  //  mode2 == 2: second INPUT   out += conv1x1(x2; W3^T)   (dgrad: dx = dgrad3x3(dc1) + dgrad1x1(dc3))
+  int mode2; bf16* out2; int pitch2, coff2; double* stats2; int x2_off;
   int dbg_mode; long long* dbg;  // tuning aids: bit0 skip TMA, bit1 skip MMA, bit2 skip epilogue stores; CTA-0 clock stamps
 };
 
@@ -58,10 +62,12 @@ __device__ __forceinline__ void issue_plane(uint32_t tmem_d, uint32_t a_pl, uint
 // KSTEPS = kc/16; CO_T = 16 / 32: output channels known at compile time (register-resident statistics), 0 = generic
 template <int KSTEPS, int CO_T>
 __global__ void __launch_bounds__(192, 1)
-conv_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const HaloParams p) {
+conv_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x2,
+                 const __grid_constant__ CUtensorMap map_w2, const HaloParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  const uint32_t wres_bytes = p.resident ? (uint32_t)(27 * p.nchunk) * p.b_bytes : 0;
+  const int wtiles = (27 + (p.mode2 ? 1 : 0)) * p.nchunk;
+  const uint32_t wres_bytes = p.resident ? (uint32_t)wtiles * p.b_bytes : 0;
   uint8_t* ring = smem + wres_bytes;
   uint64_t* full = (uint64_t*)(ring + (size_t)p.stages * p.stage_bytes);
   uint64_t* empty = full + p.stages;
@@ -84,10 +90,13 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     mbar_init(wfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     if (p.resident) {   // weight tile index = (tap * nchunk + chunk), tap = (kd*3+kh)*3+kw
-      mbar_expect_tx(wfull, (uint32_t)(27 * p.nchunk) * w_tx);
+      mbar_expect_tx(wfull, (uint32_t)wtiles * w_tx);
       for (int tap = 0; tap < 27; ++tap)
         for (int ch = 0; ch < p.nchunk; ++ch)
           tma_load_2d(smem_u32(smem) + (uint32_t)(tap * p.nchunk + ch) * p.b_bytes, &map_w, wfull, ch * p.kc, tap * p.Co);
+      if (p.mode2)
+        for (int ch = 0; ch < p.nchunk; ++ch)
+          tma_load_2d(smem_u32(smem) + (uint32_t)(27 * p.nchunk + ch) * p.b_bytes, &map_w2, wfull, ch * p.kc, 0);
     }
   }
   if (warp == 1) {
@@ -115,8 +124,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
             const uint32_t base = ring_u + (uint32_t)stage * p.stage_bytes;
             if (p.dbg_mode & 1) mbar_arrive(full + stage);
             else {
-              mbar_expect_tx(full + stage, tx);
+              const bool second = p.mode2 == 2 && (p.planes == 3 || kg == 1);   // the stage that holds the centre plane
+              mbar_expect_tx(full + stage, tx + (second ? (uint32_t)(128 * p.row_bytes) : 0u));
               tma_load_5d(base, &map_x, full + stage, ch * p.kc, tw * HTW - 1, th * HTH - 1, d + kg * p.planes - 1, n);
+              if (second) tma_load_5d(base + p.x2_off, &map_x2, full + stage, ch * p.kc, tw * HTW, th * HTH, d, n);
               if (!p.resident)
                 for (int j = 0; j < 9 * p.planes; ++j)
                   tma_load_2d(base + p.halo_bytes + j * p.b_bytes, &map_w, full + stage, ch * p.kc, (kg * p.planes * 9 + j) * p.Co);
@@ -161,6 +172,21 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
                 issue_plane<KSTEPS>(tmem_d, a_st + plane_units, a_hi, b_st + b_plane, b_hi, b_tap, idesc, 0u);
                 issue_plane<KSTEPS>(tmem_d, a_st + 2 * plane_units, a_hi, b_st + 2 * b_plane, b_hi, b_tap, idesc, 0u);
               }
+              if (p.mode2 && (p.planes == 3 || kg == 1)) {   // fused 1x1x1 conv on the centre plane's stage
+                const uint32_t b_k1 = b_lo0 + (uint32_t)(27 * p.nchunk + ch) * b_units;
+                if (p.mode2 == 1) {       // same input (centre tap view), second accumulator
+                  const uint32_t a_c = a_st + (p.planes == 3 ? plane_units : 0u) + (uint32_t)(HALO_W + 1) * (2 * KSTEPS);
+                  const uint32_t tmem_d2 = tmem_base + (uint32_t)((2 + acc) * p.Co);
+#pragma unroll
+                  for (int k = 0; k < KSTEPS; ++k)
+                    umma_f16(tmem_d2, desc64(a_c + 2 * k, a_hi), desc64(b_k1 + 2 * k, b_hi), idesc, (ch | k) ? 1u : 0u);
+                } else {                  // second input tile (no halo), same accumulator
+                  const uint32_t a_2 = a_st + ((uint32_t)p.x2_off >> 4);
+#pragma unroll
+                  for (int k = 0; k < KSTEPS; ++k)
+                    umma_f16(tmem_d, desc64(a_2 + 2 * k, b_hi), desc64(b_k1 + 2 * k, b_hi), idesc, 1u);
+                }
+              }
             }
             umma_commit(empty + stage);
             if (s == nstage_per_tile - 1) umma_commit(tfull + acc);
@@ -174,30 +200,36 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     // ---- epilogue (TMEM lane quarter = warp % 4); row r -> (h = r/8, w = r%8) of the d-plane tile
     const int q4 = warp & 3, ew = warp - 2;
     const int row = q4 * 32 + lane;
+    const int npass = p.mode2 == 1 ? 2 : 1;      // pass 1 = the fused 1x1x1 output (second accumulator pair)
     int acc = 0; uint32_t acc_phase = 0;
     int t = blockIdx.x;
     int n = t / p.tiles_per_n, r = t - n * p.tiles_per_n;
     constexpr int NR = CO_T ? CO_T : 1;
-    float rs1[NR], rs2[NR];          // register-resident statistics (CO_T != 0)
+    float rs1[2][NR], rs2[2][NR];    // register-resident statistics (CO_T != 0), per pass
 #pragma unroll
-    for (int j = 0; j < NR; ++j) { rs1[j] = 0.f; rs2[j] = 0.f; }
+    for (int j = 0; j < NR; ++j) { rs1[0][j] = rs2[0][j] = rs1[1][j] = rs2[1][j] = 0.f; }
     int n_acc = n;
     auto flush = [&](int nn) {       // all 128 epilogue threads
-      if (CO_T && p.stats) {
+      if (CO_T) {
 #pragma unroll
-        for (int j = 0; j < NR; ++j) {
-          float s1 = warp_sum(rs1[j]), s2 = warp_sum(rs2[j]);
-          if (lane == 0) { red[ew * 2 * CO_T + j] = s1; red[ew * 2 * CO_T + CO_T + j] = s2; }
-          rs1[j] = 0.f; rs2[j] = 0.f;
+        for (int ps = 0; ps < 2; ++ps) {
+          double* sp = ps ? p.stats2 : p.stats;
+          if (ps >= npass || !sp) continue;
+#pragma unroll
+          for (int j = 0; j < NR; ++j) {
+            float s1 = warp_sum(rs1[ps][j]), s2 = warp_sum(rs2[ps][j]);
+            if (lane == 0) { red[ew * 2 * CO_T + j] = s1; red[ew * 2 * CO_T + CO_T + j] = s2; }
+            rs1[ps][j] = 0.f; rs2[ps][j] = 0.f;
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          const int e = ew * 32 + lane;
+          if (e < 2 * CO_T) {
+            float tot = red[e] + red[2 * CO_T + e] + red[4 * CO_T + e] + red[6 * CO_T + e];
+            int c = e % NR, which = e / NR;
+            atomicAdd(sp + ((long)nn * CO_T + c) * 2 + which, (double)tot);
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        const int e = ew * 32 + lane;
-        if (e < 2 * CO_T) {
-          float tot = red[e] + red[2 * CO_T + e] + red[4 * CO_T + e] + red[6 * CO_T + e];
-          int c = e % NR, which = e / NR;
-          atomicAdd(p.stats + ((long)nn * CO_T + c) * 2 + which, (double)tot);
-        }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
       }
     };
     for (; t < p.total_tiles; t += gridDim.x) {
@@ -205,74 +237,77 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
       if (n != n_acc) { flush(n_acc); n_acc = n; }
       const int w = tw * HTW + (row & 7), h = th * HTH + (row >> 3);
       const bool valid = (w < p.W) && (h < p.H);
-      bf16* dst = p.out + ((((long)n * p.D + d) * p.H + h) * p.W + w) * p.pitch + p.coff;
+      const long vox = (((long)n * p.D + d) * p.H + h) * p.W + w;
       mbar_wait(tfull + acc, acc_phase);
       tc_fence_after();
-      const uint32_t trow = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(acc * p.Co);
-      if (CO_T) {
 #pragma unroll
-        for (int c0 = 0; c0 < NR; c0 += 16) {
-          float v[16];
-          tmem_ld16(trow + c0, v);
-          if (p.dbg_mode & 4) continue;
-          if (valid) {
-            if (p.stats) {
+      for (int ps = 0; ps < 2; ++ps) {
+        if (ps >= npass) continue;
+        bf16* dst = ps ? p.out2 + vox * p.pitch2 + p.coff2 : p.out + vox * p.pitch + p.coff;
+        double* sp = ps ? p.stats2 : p.stats;
+        const uint32_t trow = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)((2 * ps + acc) * p.Co);
+        if (CO_T) {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) { rs1[(c0 + j) % NR] += v[j]; rs2[(c0 + j) % NR] = fmaf(v[j], v[j], rs2[(c0 + j) % NR]); }
-            }
-            if (p.accumulate) {
-              Vec16<bf16> a, b; a.load(dst + c0); b.load(dst + c0 + 8);
+          for (int c0 = 0; c0 < NR; c0 += 16) {
+            float v[16];
+            tmem_ld16(trow + c0, v);
+            if (p.dbg_mode & 4) continue;
+            if (valid) {
+              if (sp) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) { v[j] += a.v[j]; v[8 + j] += b.v[j]; }
-            }
-            Vec16<bf16> o0, o1;
+                for (int j = 0; j < 16; ++j) { rs1[ps][(c0 + j) % NR] += v[j]; rs2[ps][(c0 + j) % NR] = fmaf(v[j], v[j], rs2[ps][(c0 + j) % NR]); }
+              }
+              if (p.accumulate && ps == 0) {
+                Vec16<bf16> a, b; a.load(dst + c0); b.load(dst + c0 + 8);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) { o0.v[j] = v[j]; o1.v[j] = v[8 + j]; }
-            o0.store(dst + c0); o1.store(dst + c0 + 8);
-          }
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(tempty + acc);
-      } else {
-        for (int c0 = 0; c0 < p.Co; c0 += 16) {
-          float v[16];
-          tmem_ld16(trow + c0, v);
-          if (p.dbg_mode & 4) continue;
-          if (p.stats) {
+                for (int j = 0; j < 8; ++j) { v[j] += a.v[j]; v[8 + j] += b.v[j]; }
+              }
+              Vec16<bf16> o0, o1;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              float x = valid ? v[j] : 0.f;
-              float s1 = warp_sum(x), s2 = warp_sum(x * x);
-              if (lane == 0) { red[ew * 2 * p.Co + c0 + j] = s1; red[ew * 2 * p.Co + p.Co + c0 + j] = s2; }
+              for (int j = 0; j < 8; ++j) { o0.v[j] = v[j]; o1.v[j] = v[8 + j]; }
+              o0.store(dst + c0); o1.store(dst + c0 + 8);
             }
           }
-          if (valid) {
-            if (p.accumulate) {
-              Vec16<bf16> a, b; a.load(dst + c0); b.load(dst + c0 + 8);
+        } else {
+          for (int c0 = 0; c0 < p.Co; c0 += 16) {
+            float v[16];
+            tmem_ld16(trow + c0, v);
+            if (p.dbg_mode & 4) continue;
+            if (sp) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) { v[j] += a.v[j]; v[8 + j] += b.v[j]; }
+              for (int j = 0; j < 16; ++j) {
+                float x = valid ? v[j] : 0.f;
+                float s1 = warp_sum(x), s2 = warp_sum(x * x);
+                if (lane == 0) { red[ew * 2 * p.Co + c0 + j] = s1; red[ew * 2 * p.Co + p.Co + c0 + j] = s2; }
+              }
             }
-            Vec16<bf16> o0, o1;
+            if (valid) {
+              if (p.accumulate && ps == 0) {
+                Vec16<bf16> a, b; a.load(dst + c0); b.load(dst + c0 + 8);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) { o0.v[j] = v[j]; o1.v[j] = v[8 + j]; }
-            o0.store(dst + c0); o1.store(dst + c0 + 8);
+                for (int j = 0; j < 8; ++j) { v[j] += a.v[j]; v[8 + j] += b.v[j]; }
+              }
+              Vec16<bf16> o0, o1;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) { o0.v[j] = v[j]; o1.v[j] = v[8 + j]; }
+              o0.store(dst + c0); o1.store(dst + c0 + 8);
+            }
           }
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(tempty + acc);
-        if (p.stats) {
-          asm volatile("bar.sync 1, 128;" ::: "memory");
-          int e = ew * 32 + lane;
-          for (int i = e; i < 2 * p.Co; i += 128) {
-            float tot = red[i] + red[2 * p.Co + i] + red[4 * p.Co + i] + red[6 * p.Co + i];
-            int c = i % p.Co, which = i / p.Co;
-            atomicAdd(p.stats + ((long)n * p.Co + c) * 2 + which, (double)tot);
+          if (sp) {
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            int e = ew * 32 + lane;
+            for (int i = e; i < 2 * p.Co; i += 128) {
+              float tot = red[i] + red[2 * p.Co + i] + red[4 * p.Co + i] + red[6 * p.Co + i];
+              int c = i % p.Co, which = i / p.Co;
+              atomicAdd(sp + ((long)n * p.Co + c) * 2 + which, (double)tot);
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
           }
-          asm volatile("bar.sync 1, 128;" ::: "memory");
         }
       }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty + acc);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       r += gridDim.x;
       while (r >= p.tiles_per_n) { r -= p.tiles_per_n; ++n; }
@@ -290,21 +325,23 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
 
 // smem plan shared by the support test and the launcher
 struct HaloPlan { int kc, rb, nchunk, plane_bytes, b_bytes, resident, planes, halo_bytes, stage_bytes, stages; };
-static inline HaloPlan halo_plan(int Ci, int Co) {
+static inline HaloPlan halo_plan(int Ci, int Co, int mode2 = 0) {
   HaloPlan h;
   h.kc = Ci % 64 == 0 ? 64 : (Ci % 32 == 0 ? 32 : 16); h.rb = h.kc * 2; h.nchunk = Ci / h.kc;
   h.plane_bytes = HALO_H * HALO_W * h.rb;
   h.b_bytes = ((Co * h.rb + 1023) / 1024) * 1024;
   const int budget_all = 200 * 1024;
-  h.resident = ((long)27 * h.nchunk * h.b_bytes <= 112 * 1024) ? 1 : 0;
-  int budget = budget_all - (h.resident ? 27 * h.nchunk * h.b_bytes : 0);
+  const int wtiles = (27 + (mode2 ? 1 : 0)) * h.nchunk;
+  h.resident = ((long)wtiles * h.b_bytes <= 112 * 1024) ? 1 : 0;
+  int budget = budget_all - (h.resident ? wtiles * h.b_bytes : 0);
+  const int x2 = mode2 == 2 ? ((128 * h.rb + 1023) / 1024) * 1024 : 0;   // second input tile of the fused 1x1x1 dgrad
   h.planes = 3;
   h.halo_bytes = ((3 * h.plane_bytes + 1023) / 1024) * 1024;
-  h.stage_bytes = h.halo_bytes + (h.resident ? 0 : 27 * h.b_bytes);
+  h.stage_bytes = h.halo_bytes + x2 + (h.resident ? 0 : 27 * h.b_bytes);
   if (budget / h.stage_bytes < 3) {   // one plane per stage
     h.planes = 1;
     h.halo_bytes = ((h.plane_bytes + 1023) / 1024) * 1024;
-    h.stage_bytes = h.halo_bytes + (h.resident ? 0 : 9 * h.b_bytes);
+    h.stage_bytes = h.halo_bytes + x2 + (h.resident ? 0 : 9 * h.b_bytes);
   }
   h.stages = budget / h.stage_bytes; if (h.stages > 8) h.stages = 8;
   return h;
@@ -313,22 +350,37 @@ static inline bool conv_halo_supported(int Ci, int Co) {
   if (!(Ci % 16 == 0 && Co % 16 == 0 && Co <= 256)) return false;
   return halo_plan(Ci, Co).stages >= 2;
 }
+// fused 3x3x3 + 1x1x1 (mode2 1: two outputs of one input, 2: two inputs of one output): resident weights, 4*Co TMEM columns
+static inline bool conv_halo_fused_supported(int Ci, int Co, int mode2) {
+  if (!(Ci % 16 == 0 && Co % 16 == 0) || getenv("B200_NO_FUSED_K1")) return false;
+  if (mode2 == 1 && 4 * Co > 512) return false;
+  HaloPlan h = halo_plan(Ci, Co, mode2);
+  return h.resident && h.stages >= 2;
+}
 
 template <int KSTEPS, int CO_T>
-static int conv_halo_launch(const CUtensorMap& mx, const CUtensorMap& mw, const HaloParams& p, int grid, size_t smem, cudaStream_t st) {
+static int conv_halo_launch(const CUtensorMap& mx, const CUtensorMap& mw, const CUtensorMap& mx2, const CUtensorMap& mw2, const HaloParams& p, int grid,
+                            size_t smem, cudaStream_t st) {
   static bool attr_done = false;
   if (!attr_done) { B200_CUDA(cudaFuncSetAttribute(conv_halo_kernel<KSTEPS, CO_T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr_done = true; }
-  conv_halo_kernel<KSTEPS, CO_T><<<grid, 192, smem, st>>>(mx, mw, p);
+  conv_halo_kernel<KSTEPS, CO_T><<<grid, 192, smem, st>>>(mx, mw, mx2, mw2, p);
   B200_LAUNCH_CHECK();
   return 0;
 }
 
 // 3x3x3 only.  wp: packed bf16 [27][Co][Ci] (same packing as tc::conv).
+struct HaloFused {   // optional fused 1x1x1 conv (see HaloParams::mode2); wp2: packed bf16 [Co][Ci]
+  int mode2; const bf16* wp2;
+  bf16* out2; int pitch2, coff2; double* stats2;          // mode2 == 1
+  const bf16* x2; int x2_pitch, x2_coff;                   // mode2 == 2 (same channel count Ci as x)
+};
 static int conv_halo(const bf16* x, int in_pitch, int in_coff, int Ci, int N, int D, int H, int W, const bf16* wp, int Co,
-                     bf16* out, int out_pitch, int out_coff, int accumulate, double* stats, cudaStream_t st) {
+                     bf16* out, int out_pitch, int out_coff, int accumulate, double* stats, cudaStream_t st, const HaloFused* fu = nullptr) {
   EncodeTiledFn enc = get_encode();
   B200_CHECK(enc, "cuTensorMapEncodeTiled not available from the driver");
-  HaloPlan h = halo_plan(Ci, Co);
+  const int mode2 = fu ? fu->mode2 : 0;
+  HaloPlan h = halo_plan(Ci, Co, mode2);
+  B200_CHECK(!mode2 || h.resident, "fused 1x1x1 conv needs resident weights (Ci=%d Co=%d)", Ci, Co);
   HaloParams p;
   p.N = N; p.D = D; p.H = H; p.W = W; p.Ci = Ci; p.Co = Co;
   p.kc = h.kc; p.row_bytes = h.rb; p.nchunk = h.nchunk;
@@ -340,14 +392,37 @@ static int conv_halo(const bf16* x, int in_pitch, int in_coff, int Ci, int N, in
   p.planes = h.planes; p.plane_bytes = h.plane_bytes; p.halo_bytes = h.halo_bytes; p.b_bytes = h.b_bytes; p.resident = h.resident;
   p.stage_bytes = h.stage_bytes; p.stages = h.stages;
   B200_CHECK(p.stages >= 2, "halo conv smem budget exceeded (Ci=%d Co=%d)", Ci, Co);
-  uint32_t cols = 2 * Co, pw = 32; while (pw < cols) pw <<= 1; p.tmem_cols = pw;
+  uint32_t cols = (mode2 == 1 ? 4 : 2) * Co, pw = 32; while (pw < cols) pw <<= 1; p.tmem_cols = pw;
+  B200_CHECK(p.tmem_cols <= 512, "halo conv TMEM budget exceeded");
   p.out = out; p.pitch = out_pitch; p.coff = out_coff; p.accumulate = accumulate; p.stats = stats;
+  p.mode2 = mode2; p.out2 = nullptr; p.pitch2 = p.coff2 = 0; p.stats2 = nullptr; p.x2_off = h.halo_bytes;
+  if (mode2 == 1) { p.out2 = fu->out2; p.pitch2 = fu->pitch2; p.coff2 = fu->coff2; p.stats2 = fu->stats2; }
   p.dbg = g_dbg; p.dbg_mode = 0;
   if (const char* e = getenv("B200_HALO_DBG")) p.dbg_mode = atoi(e);
   if (const char* e = getenv("B200_HALO_STAGES")) { int v = atoi(e); if (v >= 2 && v <= p.stages) p.stages = v; }
 
   CUtensorMapSwizzle sw = p.row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (p.row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
-  CUtensorMap mx, mw;
+  CUtensorMap mx, mw, mx2, mw2;
+  memset(&mx2, 0, sizeof(mx2)); memset(&mw2, 0, sizeof(mw2));
+  if (mode2 == 2) {
+    cuuint64_t dims[5] = {(cuuint64_t)Ci, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
+    const int pt = fu->x2_pitch;
+    cuuint64_t strides[4] = {(cuuint64_t)pt * 2, (cuuint64_t)W * pt * 2, (cuuint64_t)H * W * pt * 2, (cuuint64_t)D * H * W * pt * 2};
+    cuuint32_t box[5] = {(cuuint32_t)p.kc, HTW, HTH, 1, 1};
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(&mx2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (void*)(fu->x2 + fu->x2_coff), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    B200_CHECK(r == CUDA_SUCCESS, "halo conv second-input tensor map failed (%d)", (int)r);
+  }
+  if (mode2) {
+    cuuint64_t dims[2] = {(cuuint64_t)Ci, (cuuint64_t)Co};
+    cuuint64_t strides[1] = {(cuuint64_t)Ci * 2};
+    cuuint32_t box[2] = {(cuuint32_t)p.kc, (cuuint32_t)Co};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(&mw2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)fu->wp2, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    B200_CHECK(r == CUDA_SUCCESS, "halo conv 1x1x1 weight tensor map failed (%d)", (int)r);
+  }
   {
     cuuint64_t dims[5] = {(cuuint64_t)Ci, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
     cuuint64_t strides[4] = {(cuuint64_t)in_pitch * 2, (cuuint64_t)W * in_pitch * 2, (cuuint64_t)H * W * in_pitch * 2, (cuuint64_t)D * H * W * in_pitch * 2};
@@ -366,11 +441,11 @@ static int conv_halo(const bf16* x, int in_pitch, int in_coff, int Ci, int N, in
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     B200_CHECK(r == CUDA_SUCCESS, "halo conv weight tensor map failed (%d)", (int)r);
   }
-  size_t smem = (size_t)p.stages * p.stage_bytes + (p.resident ? (size_t)27 * p.nchunk * p.b_bytes : 0) + 1024 + 256 + 8 * Co * sizeof(float) + 64;
+  size_t smem = (size_t)p.stages * p.stage_bytes + (p.resident ? (size_t)(27 + (mode2 ? 1 : 0)) * p.nchunk * p.b_bytes : 0) + 1024 + 256 + 8 * Co * sizeof(float) + 64;
   B200_CHECK(smem <= 227 * 1024, "halo conv smem budget exceeded (%zu)", smem);
   int grid = (int)(p.total_tiles < num_sms() ? p.total_tiles : num_sms());
   const int ks = p.kc / 16;
-#define B200_HALO_CASE(KS, CO) if (ks == KS && ((CO) ? Co == (CO) : (Co != 16 && Co != 32))) return conv_halo_launch<KS, CO>(mx, mw, p, grid, smem, st)
+#define B200_HALO_CASE(KS, CO) if (ks == KS && ((CO) ? Co == (CO) : (Co != 16 && Co != 32))) return conv_halo_launch<KS, CO>(mx, mw, mx2, mw2, p, grid, smem, st)
   B200_HALO_CASE(1, 16); B200_HALO_CASE(1, 32); B200_HALO_CASE(1, 0);
   B200_HALO_CASE(2, 16); B200_HALO_CASE(2, 32); B200_HALO_CASE(2, 0);
   B200_HALO_CASE(4, 16); B200_HALO_CASE(4, 32); B200_HALO_CASE(4, 0);

@@ -199,6 +199,13 @@ def main():
             "algorithmic": "sum over launches of 2*B*D^3*Cin*Cout*k^3", "top_op": top[0], "top_op_ms": top[1][0]}
     roof["frac"] = roof["achieved"] / roof["peak"] if roof["achieved"] else None
     if args.breakdown and rank == 0:
+        lib.b200_prof_enable(2)            # phase-level regions only (per-op events have a ~8 us floor each)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); step(dev_x[1], dev_y[1]); e1.record()
+        phases = pkg._lib.prof_report()
+        lib.b200_prof_enable(0)
+        print(f"  phases of one step ({e0.elapsed_time(e1):.3f} ms incl. loss + AdamW): " +
+              "  ".join(f"{k} {v[0]:.3f}" for k, v in sorted(phases.items())), file=sys.stderr)
         tot = sum(v[0] for v in prof.values())
         print(f"  profiled total {tot:.3f} ms", file=sys.stderr)
         for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0]):
