@@ -29,6 +29,13 @@ const char* get_error() { return g_err; }
 unsigned long long g_launches = 0;
 bool g_prof_on = false;
 bool g_prof_coarse = false;
+long long* g_trace = nullptr;
+int g_trace_n = 0, g_trace_cap = 0;
+static std::vector<std::string> g_trace_tags;
+void trace_tag(const char* fmt, ...) {
+  char b[96]; va_list ap; va_start(ap, fmt); vsnprintf(b, sizeof(b), fmt, ap); va_end(ap);
+  g_trace_tags.push_back(b);
+}
 struct ProfRec { std::string tag; cudaEvent_t a, b; };
 static std::vector<ProfRec> g_prof;
 void prof_begin(const char* tag, cudaStream_t st) {
@@ -111,7 +118,10 @@ int b200_dicece_forward(const float* logits, const float* labels, int B, int C, 
   float* coef = (float*)(acc + (size_t)B * C * 3 + 2);
   B200_CUDA(cudaMemsetAsync(acc, 0, sizeof(double) * ((size_t)B * C * 3 + 2), st));
   dim3 g((unsigned)max(1L, min(148L * 8 / B + 1, (long)((V + 255) / 256))), B);
-  if (C <= 16) dicece_fwd_kernel<16><<<g, 256, 0, st>>>(logits, labels, C, V, acc, B * C);
+  const bool v4 = V % 4 == 0 && C <= 16 && (((uintptr_t)logits | (uintptr_t)labels) & 15) == 0;
+  dim3 g4((unsigned)max(1L, min(148L * 4 / B + 1, (long)((V / 4 + 255) / 256))), B);
+  if (v4) dicece_fwd4_kernel<16><<<g4, 256, 0, st>>>(logits, labels, C, V, acc, B * C);
+  else if (C <= 16) dicece_fwd_kernel<16><<<g, 256, 0, st>>>(logits, labels, C, V, acc, B * C);
   else dicece_fwd_kernel<32><<<g, 256, 0, st>>>(logits, labels, C, V, acc, B * C);
   B200_LAUNCH_CHECK();
   dicece_finalize_kernel<<<1, 256, 0, st>>>(acc, B, C, V, out3, coef);
@@ -124,7 +134,10 @@ int b200_dicece_backward(const float* logits, const float* labels, int B, int C,
   B200_CHECK(C >= 1 && C <= 32, "DiceCE supports 1..32 classes (got %d)", C);
   const float* coef = (const float*)((const double*)scratch + (size_t)B * C * 3 + 2);
   dim3 g((unsigned)max(1L, min(148L * 8 / B + 1, (long)((V + 255) / 256))), B);
-  if (C <= 16) dicece_bwd_kernel<16><<<g, 256, 0, st>>>(logits, labels, coef, upstream, B, C, V, dlogits);
+  const bool v4 = V % 4 == 0 && C <= 16 && (((uintptr_t)logits | (uintptr_t)labels | (uintptr_t)dlogits) & 15) == 0;
+  dim3 g4((unsigned)max(1L, min(148L * 4 / B + 1, (long)((V / 4 + 255) / 256))), B);
+  if (v4) dicece_bwd4_kernel<16><<<g4, 256, 0, st>>>(logits, labels, coef, upstream, B, C, V, dlogits);
+  else if (C <= 16) dicece_bwd_kernel<16><<<g, 256, 0, st>>>(logits, labels, coef, upstream, B, C, V, dlogits);
   else dicece_bwd_kernel<32><<<g, 256, 0, st>>>(logits, labels, coef, upstream, B, C, V, dlogits);
   B200_LAUNCH_CHECK();
   return 0;
@@ -268,6 +281,16 @@ int b200_test_tc_wgrad(const void* x, int x_pitch, int x_coff, int Ci, const voi
   if (tc::wgrad_halo_supported(Ci, Co, ks))
     return tc::conv_wgrad_halo((const bf16*)x, x_pitch, x_coff, Ci, (const bf16*)dy, dy_pitch, dy_coff, Co, N, D, H, W, dW, st);
   return tc::conv_wgrad((const bf16*)x, x_pitch, x_coff, Ci, (const bf16*)dy, dy_pitch, dy_coff, Co, N, D, H, W, ks, dW, st);
+}
+
+/* in-situ trace of the tcgen05 launches: buf = device int64[2*cap] pre-filled with (INT64_MAX, 0) pairs; null stops tracing */
+void b200_trace_begin(void* buf, int cap) { g_trace = (long long*)buf; g_trace_cap = cap; g_trace_n = 0; g_trace_tags.clear(); }
+int b200_trace_count(void) { return g_trace_n; }
+int b200_trace_tags(char* out, int cap) {
+  int off = 0;
+  for (auto& t : g_trace_tags) { int n = snprintf(out + off, cap - off, "%s\n", t.c_str()); if (n < 0 || off + n >= cap) break; off += n; }
+  if (cap > 0) out[off < cap ? off : cap - 1] = 0;
+  return 0;
 }
 
 void b200_test_set_debug_buffer(void* dev_ptr) { tc::g_dbg = (long long*)dev_ptr; }

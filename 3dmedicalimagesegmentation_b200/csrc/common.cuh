@@ -63,6 +63,19 @@ struct ProfScope {
   if (b200::g_prof_on) snprintf(_prof_tag, sizeof(_prof_tag), __VA_ARGS__); \
   b200::ProfScope _prof_scope(_prof_tag, st)
 
+// ---- in-situ kernel trace (b200_trace_* in the C ABI): every tcgen05 launch gets a slot; CTAs record min start / max end of
+// %globaltimer, so durations and gaps are measured inside a real step without per-op events
+extern long long* g_trace;     // device buffer of (start, end) pairs, or null
+extern int g_trace_n, g_trace_cap;
+void trace_tag(const char* fmt, ...);
+static inline long long* trace_slot() { return (g_trace && g_trace_n < g_trace_cap) ? g_trace + 2 * (g_trace_n++) : nullptr; }
+__device__ __forceinline__ void trace_start(long long* slot) {
+  if (slot && threadIdx.x == 0) { long long g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g)); atomicMin(slot, g); }
+}
+__device__ __forceinline__ void trace_end(long long* slot) {
+  if (slot && threadIdx.x == 0) { long long g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g)); atomicMax(slot + 1, g); }
+}
+
 // ---- scalar conversions ----
 __device__ __forceinline__ float to_f(float v) { return v; }
 __device__ __forceinline__ float to_f(bf16 v) { return __bfloat162float(v); }

@@ -103,7 +103,19 @@ template <class TO>
 struct EpStore {
   TO* out; long ld, sb0, sb1; int nb1;
   const float* bias; const float* resid; long ldr; TO* preact; const TO* usrc; int act; int accumulate; float alpha;
+  int splitk_nbat;   // > 0: split-K launch -- b carries split*nbat + batch; out (fp32, pre-zeroed) is accumulated atomically and only
+                     // split 0 adds bias / residual (no activation, no pre-activation copy)
+  __device__ __forceinline__ void split_store(int b, int m, int n0, const float* acc, int nvalid) const {
+    const int sp = b / splitk_nbat; b -= sp * splitk_nbat;
+    long o = (long)(b / nb1) * sb0 + (long)(b % nb1) * sb1 + (long)m * ld + n0;
+    for (int j = 0; j < nvalid; ++j) {
+      float v = acc[j] * alpha;
+      if (sp == 0) { if (bias) v += bias[n0 + j]; if (resid) v += resid[(long)m * ldr + n0 + j]; }
+      atomicAdd(reinterpret_cast<float*>(out + o + j), v);
+    }
+  }
   __device__ __forceinline__ void operator()(int b, int m, int n, float acc) const {
+    if (splitk_nbat) { split_store(b, m, n, &acc, 1); return; }
     long o = (long)(b / nb1) * sb0 + (long)(b % nb1) * sb1 + (long)m * ld + n;
     float v = acc * alpha;
     if (bias) v += bias[n];
@@ -116,6 +128,7 @@ struct EpStore {
   }
   // 16 consecutive columns of row m (tcgen05 epilogue): 16-byte loads/stores when the segment is full and aligned
   __device__ __forceinline__ void seg16(int b, int m, int n0, const float* acc, int nvalid) const {
+    if (splitk_nbat) { split_store(b, m, n0, acc, nvalid); return; }
     long o = (long)(b / nb1) * sb0 + (long)(b % nb1) * sb1 + (long)m * ld + n0;
     bool fast = nvalid == 16 && ((reinterpret_cast<uintptr_t>(out + o) & 15) == 0) && (!preact || (reinterpret_cast<uintptr_t>(preact + o) & 15) == 0) &&
                 (!usrc || (reinterpret_cast<uintptr_t>(usrc + o) & 15) == 0) && (!resid || (reinterpret_cast<uintptr_t>(resid + (long)m * ldr + n0) & 15) == 0) &&

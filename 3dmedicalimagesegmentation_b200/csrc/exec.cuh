@@ -177,6 +177,14 @@ struct Exec {
   int linear_fwd(const T* A, long lda, const float* W, const bf16* Wb, int Mr, int N, int K, const EpStore<TO>& ep, cudaStream_t st) {
     if constexpr (kTC) {
       B200_PROFD(st, "linear_fwd %dx%dx%d", Mr, N, K);
+      if constexpr (std::is_same<TO, float>::value) {   // few output tiles + long K: split K across SMs, fp32 atomics into a zeroed output
+        int ks = (ep.act == ACT_NONE && !ep.preact && !ep.accumulate && ep.sb0 == 0 && ep.sb1 == 0 && ep.ld == N) ? tc::plan_splitk(Mr, N, K, 1) : 1;
+        if (ks > 1) {
+          B200_CUDA(cudaMemsetAsync(ep.out, 0, sizeof(float) * (size_t)Mr * N, st));
+          EpStore<TO> e2 = ep; e2.splitk_nbat = 1;
+          return tc::gemm(tc::operand(A, lda, 1), tc::operand(Wb, K, 1), e2, Mr, N, K, 1, 1, st, false, ks);
+        }
+      }
       return tc::gemm(tc::operand(A, lda, 1), tc::operand(Wb, K, 1), ep, Mr, N, K, 1, 1, st);
     } else {
       return simt_linear_fwd(A, lda, W, Mr, N, K, ep, st);
@@ -601,9 +609,16 @@ struct Exec {
           B200_CUDA(cudaFuncSetAttribute(head_bwd_kernel<T, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
           B200_CUDA(cudaFuncSetAttribute(head_bwd_kernel<T, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
           B200_CUDA(cudaFuncSetAttribute(head_bwd_kernel<T, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+          B200_CUDA(cudaFuncSetAttribute(head_bwd2_kernel<T, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
           attr = true;
         }
-        if (fs == 8) head_bwd_kernel<T, 8><<<g, 256, sm, st>>>(d_logits, w.d0, P[P_OUT_W], c.ncls, V[0], chunk, w.gA, G[P_OUT_W], G[P_OUT_B]);
+        if (c.ncls <= 16 && !getenv("B200_HEAD_BWD_V1")) {
+          size_t sm2 = head_bwd2_smem(fs);
+          if (fs == 8) head_bwd2_kernel<T, 8><<<g, 256, sm2, st>>>(d_logits, w.d0, P[P_OUT_W], c.ncls, V[0], chunk, w.gA, G[P_OUT_W], G[P_OUT_B]);
+          else if (fs == 16) head_bwd2_kernel<T, 16><<<g, 256, sm2, st>>>(d_logits, w.d0, P[P_OUT_W], c.ncls, V[0], chunk, w.gA, G[P_OUT_W], G[P_OUT_B]);
+          else head_bwd2_kernel<T, 32><<<g, 256, sm2, st>>>(d_logits, w.d0, P[P_OUT_W], c.ncls, V[0], chunk, w.gA, G[P_OUT_W], G[P_OUT_B]);
+        }
+        else if (fs == 8) head_bwd_kernel<T, 8><<<g, 256, sm, st>>>(d_logits, w.d0, P[P_OUT_W], c.ncls, V[0], chunk, w.gA, G[P_OUT_W], G[P_OUT_B]);
         else if (fs == 16) head_bwd_kernel<T, 16><<<g, 256, sm, st>>>(d_logits, w.d0, P[P_OUT_W], c.ncls, V[0], chunk, w.gA, G[P_OUT_W], G[P_OUT_B]);
         else head_bwd_kernel<T, 32><<<g, 256, sm, st>>>(d_logits, w.d0, P[P_OUT_W], c.ncls, V[0], chunk, w.gA, G[P_OUT_W], G[P_OUT_B]);
         B200_LAUNCH_CHECK();

@@ -117,6 +117,116 @@ __global__ void __launch_bounds__(256) dicece_bwd_kernel(const float* __restrict
   }
 }
 
+
+// ---- 4 voxels per thread (16-byte loads per class plane; V % 4 == 0): 4x the bytes in flight of the scalar kernels above
+template <int CMAX>
+__global__ void __launch_bounds__(256) dicece_fwd4_kernel(const float* __restrict__ logits, const float* __restrict__ labels,
+                                                          int C, long V, double* __restrict__ acc, int nBC) {
+  int b = blockIdx.y;
+  float aI[CMAX], aP[CMAX], aG[CMAX];
+#pragma unroll
+  for (int c = 0; c < CMAX; ++c) aI[c] = aP[c] = aG[c] = 0.f;
+  float ce = 0.f;
+  const float* lg = logits + (long)b * C * V;
+  const long V4 = V >> 2;
+  for (long q = (long)blockIdx.x * blockDim.x + threadIdx.x; q < V4; q += (long)gridDim.x * blockDim.x) {
+    float4 l[CMAX];
+    const float4 yl = *reinterpret_cast<const float4*>(labels + (long)b * V + 4 * q);
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c)
+      if (c < C) l[c] = *reinterpret_cast<const float4*>(lg + (long)c * V + 4 * q);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int y = (int)(e == 0 ? yl.x : e == 1 ? yl.y : e == 2 ? yl.z : yl.w);
+      float x[CMAX];
+      float mx = -INFINITY, ly = 0.f;
+#pragma unroll
+      for (int c = 0; c < CMAX; ++c)
+        if (c < C) { x[c] = e == 0 ? l[c].x : e == 1 ? l[c].y : e == 2 ? l[c].z : l[c].w; mx = fmaxf(mx, x[c]); if (c == y) ly = x[c]; }
+      float s = 0.f;
+#pragma unroll
+      for (int c = 0; c < CMAX; ++c)
+        if (c < C) { x[c] = __expf(x[c] - mx); s += x[c]; }
+      const float inv = 1.f / s;
+      ce += logf(s) - (ly - mx);
+#pragma unroll
+      for (int c = 0; c < CMAX; ++c)
+        if (c < C) {
+          float p = x[c] * inv;
+          aP[c] += p;
+          if (c == y) { aI[c] += p; aG[c] += 1.f; }
+        }
+    }
+  }
+  __shared__ float red[8][3 * CMAX + 1];
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int c = 0; c < CMAX; ++c) {
+    float x0 = warp_sum(aI[c]), x1 = warp_sum(aP[c]), x2 = warp_sum(aG[c]);
+    if (lane == 0) { red[w][3 * c] = x0; red[w][3 * c + 1] = x1; red[w][3 * c + 2] = x2; }
+  }
+  ce = warp_sum(ce);
+  if (lane == 0) red[w][3 * CMAX] = ce;
+  __syncthreads();
+  for (int i = threadIdx.x; i < 3 * C + 1; i += blockDim.x) {
+    int src = (i < 3 * C) ? i : 3 * CMAX;
+    double t = 0.0;
+    for (int k = 0; k < 8; ++k) t += red[k][src];
+    if (i < 3 * C) atomicAdd(acc + ((long)b * C) * 3 + i, t);
+    else atomicAdd(acc + (long)nBC * 3, t);
+  }
+}
+template <int CMAX>
+__global__ void __launch_bounds__(256) dicece_bwd4_kernel(const float* __restrict__ logits, const float* __restrict__ labels,
+                                                          const float* __restrict__ coef, const float* __restrict__ upstream,
+                                                          int B, int C, long V, float* __restrict__ dlogits) {
+  int b = blockIdx.y;
+  float up = upstream ? upstream[0] : 1.f;
+  float invBV = 1.f / ((float)B * (float)V);
+  __shared__ float sc[2 * CMAX];
+  if (threadIdx.x < 2 * C) sc[threadIdx.x] = coef[(long)b * C * 2 + threadIdx.x];
+  __syncthreads();
+  const float* lg = logits + (long)b * C * V;
+  float* dl = dlogits + (long)b * C * V;
+  const long V4 = V >> 2;
+  for (long q = (long)blockIdx.x * blockDim.x + threadIdx.x; q < V4; q += (long)gridDim.x * blockDim.x) {
+    float4 l[CMAX];
+    const float4 yl = *reinterpret_cast<const float4*>(labels + (long)b * V + 4 * q);
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c)
+      if (c < C) l[c] = *reinterpret_cast<const float4*>(lg + (long)c * V + 4 * q);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int y = (int)(e == 0 ? yl.x : e == 1 ? yl.y : e == 2 ? yl.z : yl.w);
+      float x[CMAX];
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < CMAX; ++c)
+        if (c < C) { x[c] = e == 0 ? l[c].x : e == 1 ? l[c].y : e == 2 ? l[c].z : l[c].w; mx = fmaxf(mx, x[c]); }
+      float s = 0.f;
+#pragma unroll
+      for (int c = 0; c < CMAX; ++c)
+        if (c < C) { x[c] = __expf(x[c] - mx); s += x[c]; }
+      const float inv = 1.f / s;
+      float dot = 0.f;
+#pragma unroll
+      for (int c = 0; c < CMAX; ++c)
+        if (c < C) { x[c] *= inv; dot += x[c] * (sc[2 * c] * (c == y ? 1.f : 0.f) + sc[2 * c + 1]); }
+#pragma unroll
+      for (int c = 0; c < CMAX; ++c)
+        if (c < C) {
+          float t = (c == y) ? 1.f : 0.f;
+          float wk = sc[2 * c] * t + sc[2 * c + 1];
+          float g = up * (x[c] * (wk - dot) + (x[c] - t) * invBV);
+          if (e == 0) l[c].x = g; else if (e == 1) l[c].y = g; else if (e == 2) l[c].z = g; else l[c].w = g;
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c)
+      if (c < C) *reinterpret_cast<float4*>(dl + (long)c * V + 4 * q) = l[c];
+  }
+}
+
 // ------------------------------------------------------------------ Bradley-Terry ranking loss
 // 16 slices: id = partition*4 + sample (samples ordered batch1[0], batch1[1], batch2[0], batch2[1], rank:80-84).
 // A slice is [C, F0*F1] taken at index idx[partition] along the sliced spatial axis.

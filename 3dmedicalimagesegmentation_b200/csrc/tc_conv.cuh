@@ -31,6 +31,7 @@ struct ConvParams {
   // epilogue
   bf16* out; int pitch, coff, accumulate; double* stats;
   long long* dbg;   // optional CTA-0 clock64 stamps (tuning aid)
+  long long* trace;
   int resident;     // all packed weights (kblocks x b_bytes) stay in smem for the CTA's lifetime; stages hold A bricks only
   // Software A loader (row_bytes <= 64): TMA needs ~2 cycles per 32-byte box row, so the 27 shifted bricks are instead
   // fetched with coalesced 16-byte ld.global (the 27x overlap hits L1), written to smem in the hardware swizzle pattern,
@@ -76,6 +77,7 @@ conv_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ C
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool dbg = p.dbg && blockIdx.x == 0;
+  trace_start(p.trace);
   if (dbg && threadIdx.x == 0) p.dbg[0] = clock64();
   const int nstage_per_tile = (p.kblocks + p.group - 1) / p.group;
   const int pad = p.ks >> 1;
@@ -292,6 +294,7 @@ conv_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ C
   }
   tc_fence_before();
   __syncthreads();
+  trace_end(p.trace);
   if (dbg && threadIdx.x == 0) p.dbg[48] = clock64();
   if (warp == 1) {
     tc_fence_after();
@@ -329,6 +332,7 @@ static int conv(const bf16* x, int in_pitch, int in_coff, int Ci, int N, int D, 
   p.total_tiles = (long)N * p.tiles_d * p.tiles_h * p.tiles_w;
   uint32_t cols = 2 * Co, pw = 32; while (pw < cols) pw <<= 1; p.tmem_cols = pw;
   p.dbg = g_dbg;
+  p.trace = trace_slot(); if (p.trace) trace_tag("conv k%d %d->%d @%d", ks, Ci, Co, D);
   p.out = out; p.pitch = out_pitch; p.coff = out_coff; p.accumulate = accumulate; p.stats = stats;
 
   CUtensorMapSwizzle sw = p.row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (p.row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);

@@ -37,6 +37,7 @@ struct HaloParams {
   //  mode2 == 1: second OUTPUT  out2 = conv1x1(x; W3)      (forward: conv1 and conv3 read the same x)
   //  mode2 == 2: second INPUT   out += conv1x1(x2; W3^T)   (dgrad: dx = dgrad3x3(dc1) + dgrad1x1(dc3))
   int mode2; bf16* out2; int pitch2, coff2; double* stats2; int x2_off;
+  long long* trace;
   int dbg_mode; long long* dbg;  // tuning aids: bit0 skip TMA, bit1 skip MMA, bit2 skip epilogue stores; CTA-0 clock stamps
 };
 
@@ -79,6 +80,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool dbg = p.dbg && blockIdx.x == 0;
+  trace_start(p.trace);
   if (dbg && threadIdx.x == 0) p.dbg[0] = clock64();
   const int kd_groups = 3 / p.planes;                       // stages along kd per chunk
   const int nstage_per_tile = kd_groups * p.nchunk;         // (kd group, chunk)
@@ -316,6 +318,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
   }
   tc_fence_before();
   __syncthreads();
+  trace_end(p.trace);
   if (dbg && threadIdx.x == 0) p.dbg[48] = clock64();
   if (warp == 1) {
     tc_fence_after();
@@ -398,6 +401,7 @@ static int conv_halo(const bf16* x, int in_pitch, int in_coff, int Ci, int N, in
   p.mode2 = mode2; p.out2 = nullptr; p.pitch2 = p.coff2 = 0; p.stats2 = nullptr; p.x2_off = h.halo_bytes;
   if (mode2 == 1) { p.out2 = fu->out2; p.pitch2 = fu->pitch2; p.coff2 = fu->coff2; p.stats2 = fu->stats2; }
   p.dbg = g_dbg; p.dbg_mode = 0;
+  p.trace = trace_slot(); if (p.trace) trace_tag("conv_halo %d->%d @%d mode2=%d", Ci, Co, D, mode2);
   if (const char* e = getenv("B200_HALO_DBG")) p.dbg_mode = atoi(e);
   if (const char* e = getenv("B200_HALO_STAGES")) { int v = atoi(e); if (v >= 2 && v <= p.stages) p.stages = v; }
 

@@ -14,6 +14,7 @@
 #pragma once
 #include <cuda.h>
 #include <stdlib.h>
+#include <utility>
 
 #include "common.cuh"
 #include "contract.cuh"
@@ -87,6 +88,21 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// Programmatic dependent launch: the kernel may start while its predecessor in the stream drains; everything before
+// pdl_wait() (barrier init, TMEM allocation, descriptor prefetch) overlaps the predecessor's tail, nothing after it does.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) { asm volatile("prefetch.tensormap [%0];" ::"l"(m) : "memory"); }
+template <class... KArgs, class... Args>
+static cudaError_t launch_pdl(void (*kern)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
+  static const bool off = getenv("B200_NO_PDL") != nullptr;
+  cfg.attrs = at; cfg.numAttrs = off ? 0 : 1;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
+
 // shared-memory matrix descriptor, SWIZZLE_128B (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30),
 // SBO>>4 [32,46), version=1 [46,48), layout_type=2 [61,64))
 __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -117,6 +133,7 @@ struct Params {
   uint32_t tmem_cols;       // 2*BN rounded to a power of two
   int ksplit, kb_per_split; // split-K: work item = (tile, split); epilogue functor must accumulate atomically
   long long* dbg;           // optional: CTA 0 phase timestamps (clock64) for tuning
+  long long* trace;         // optional in-situ (start, end) slot
 };
 
 template <class EP, bool A_MN, bool B_MN>
@@ -139,6 +156,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
   const long total_tiles = (long)p.tiles_m * p.tiles_n * p.batches * p.ksplit;
 
   if (threadIdx.x == 0) {
+    prefetch_tmap(&map_a); prefetch_tmap(&map_b);
     for (int s = 0; s < p.stages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(tfull + s, 1); mbar_init(tempty + s, 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -151,6 +169,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();   // predecessor's global writes are visible from here on
+  trace_start(p.trace);
   if (dbg && threadIdx.x == 0) p.dbg[1] = clock64();
 
   if (warp == 0) {
@@ -227,6 +247,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     for (long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       long r = t / p.ksplit;
       int tm = (int)(r % p.tiles_m); r /= p.tiles_m; int tn = (int)(r % p.tiles_n); int b = (int)(r / p.tiles_n);
+      if (p.ksplit > 1) b += (int)(t % p.ksplit) * p.batches;   // split-K functors decode (split, batch) = (b / batches, b % batches)
       mbar_wait(tfull + acc, acc_phase);
       tc_fence_after();
       if (dbg && warp == 2 && lane == 0 && t == blockIdx.x) p.dbg[4] = clock64();   // first accumulator ready
@@ -246,6 +267,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
   }
   tc_fence_before();
   __syncthreads();
+  trace_end(p.trace);
   if (dbg && threadIdx.x == 0) p.dbg[5] = clock64();
   if (p.dbg && threadIdx.x == 0) { long long g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g)); p.dbg[65 + 2 * blockIdx.x] = g; }
   if (warp == 1) {
@@ -300,24 +322,47 @@ static inline int num_sms() {
   return g_num_sms;
 }
 
+// split-K factor worth using for a fp32-atomic epilogue: few output tiles, long K
+static inline int plan_splitk(int M, int N, int K, int nb) {
+  // measured: 16 scattered fp32 atomics per row segment make the epilogue slower than the K loop it saves (proj 10.6 -> 17.6 us);
+  // off unless asked for, until the partial sums are reduced by the consumer kernel instead
+  static const bool on = getenv("B200_SPLITK") != nullptr;
+  if (!on) return 1;
+  const long tiles = (long)cdiv(M, BM) * cdiv(N, 64) * nb; const int kbs = cdiv(K, BK);
+  if (tiles * 2 > num_sms() || kbs < 8) return 1;
+  long s = num_sms() / tiles; if (s > kbs / 4) s = kbs / 4;
+  return s < 2 ? 1 : (int)s;
+}
+
 // D[(b0,b1)][m,n] = sum_k A(m,k) B(n,k);  ep(b0*nb1+b1, m, n, acc)
 template <class EP>
-static int gemm(const Operand& A, const Operand& B, const EP& ep, int M, int N, int K, int nb0, int nb1, cudaStream_t st, bool allow_splitk = false) {
+static int gemm(const Operand& A, const Operand& B, const EP& ep, int M, int N, int K, int nb0, int nb1, cudaStream_t st, bool allow_splitk = false,
+                int ksplit_req = 0) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   Params p;
   p.M = M; p.N = N; p.K = K;
   p.a_mn = A.mn_major(); p.b_mn = B.mn_major();
-  // widest N tile that still gives every SM a tile; small problems fall back to 64-wide tiles for parallelism
+  // N-tile: minimise (waves) x (per-tile cost); per-tile cost ~ k-blocks x rows fetched (L2->SM bound, measured ~2.2 ns per
+  // row of 128 B per k-block in situ) + a fixed pipeline fill + the epilogue.  MN-major B is fetched in 64-column boxes.
   {
-    long tm = cdiv(M, BM), nb = (long)nb0 * nb1;
-    p.BN = 64;
-    if (N > 64 && tm * cdiv(N, 128) * nb >= num_sms()) p.BN = 128;
-    if (N > 128 && tm * cdiv(N, 256) * nb >= num_sms()) p.BN = 256;
+    static const int cand_k[] = {32, 48, 64, 80, 96, 112, 128, 160, 192, 224, 256}, cand_mn[] = {64, 128, 192, 256};
+    const int* cand = p.b_mn ? cand_mn : cand_k; const int nc = p.b_mn ? 4 : 11;
+    const long tm = cdiv(M, BM), nb = (long)nb0 * nb1; const int kbs = cdiv(K, BK);
+    double best = 1e30; p.BN = 64;
+    for (int i = 0; i < nc; ++i) {
+      const int bn = cand[i];
+      if (bn > 64 && bn - 16 >= N) continue;
+      const long tiles = tm * cdiv(N, bn) * nb * (ksplit_req > 1 ? ksplit_req : 1);
+      const long waves = (tiles + num_sms() - 1) / num_sms();
+      const int kb = ksplit_req > 1 ? cdiv(kbs, ksplit_req) : kbs;
+      const double cost = waves * (kb * (128.0 + bn) * 2.2e-3 + 0.6 + bn * 6e-3);
+      if (cost < best - 1e-9) { best = cost; p.BN = bn; }
+    }
   }
   p.tiles_m = cdiv(M, BM); p.tiles_n = cdiv(N, p.BN); p.nb1 = nb1; p.batches = nb0 * nb1;
   uint32_t stage_bytes = BM * BK * 2 + p.BN * BK * 2;
   p.stages = (int)((200 * 1024) / stage_bytes); if (p.stages > 8) p.stages = 8;
-  p.tmem_cols = p.BN * 2 < 32 ? 32 : p.BN * 2;
+  { uint32_t c = 32; while (c < (uint32_t)p.BN * 2) c <<= 1; p.tmem_cols = c; }
   CUtensorMap ma, mb;
   B200_TRY(make_map(&ma, A, M, K, BM, nb0, nb1));
   B200_TRY(make_map(&mb, B, N, K, p.BN, nb0, nb1));
@@ -330,10 +375,12 @@ static int gemm(const Operand& A, const Operand& B, const EP& ep, int M, int N, 
     attr_done = true;
   }
   p.dbg = g_dbg;
+  p.trace = trace_slot(); if (p.trace) trace_tag("gemm %dx%dx%d b%d %s%s", M, N, K, nb0 * nb1, A.mn_major() ? "m" : "k", B.mn_major() ? "m" : "k");
   if (const char* e = getenv("B200_GEMM_BN")) { int v = atoi(e); if (v == 64 || v == 128 || v == 256) { p.BN = v; p.tiles_n = cdiv(N, p.BN); stage_bytes = BM * BK * 2 + p.BN * BK * 2; p.stages = (int)((200 * 1024) / stage_bytes); if (p.stages > 8) p.stages = 8; p.tmem_cols = p.BN * 2; } }
   if (const char* e = getenv("B200_GEMM_STAGES")) { int v = atoi(e); if (v >= 1 && v <= p.stages) p.stages = v; }
   p.ksplit = 1; p.kb_per_split = cdiv(K, BK);
-  if (allow_splitk) {
+  if (ksplit_req > 1) { int kbs = cdiv(K, BK); p.kb_per_split = cdiv(kbs, ksplit_req); p.ksplit = cdiv(kbs, p.kb_per_split); }
+  else if (allow_splitk) {
     long base_tiles = (long)p.tiles_m * p.tiles_n * p.batches; int kbs = cdiv(K, BK);
     long want = num_sms() / base_tiles; if (want > kbs / 4) want = kbs / 4; if (want < 1) want = 1;
     p.kb_per_split = cdiv(kbs, (int)want); p.ksplit = cdiv(kbs, p.kb_per_split);
@@ -341,8 +388,10 @@ static int gemm(const Operand& A, const Operand& B, const EP& ep, int M, int N, 
   size_t smem = (size_t)p.stages * stage_bytes + 1024 + 256;
   long tiles = (long)p.tiles_m * p.tiles_n * p.batches * p.ksplit;
   int grid = (int)(tiles < num_sms() ? tiles : num_sms());
-  if (p.a_mn) { if (p.b_mn) gemm_kernel<EP, true, true><<<grid, 192, smem, st>>>(ma, mb, p, ep); else gemm_kernel<EP, true, false><<<grid, 192, smem, st>>>(ma, mb, p, ep); }
-  else { if (p.b_mn) gemm_kernel<EP, false, true><<<grid, 192, smem, st>>>(ma, mb, p, ep); else gemm_kernel<EP, false, false><<<grid, 192, smem, st>>>(ma, mb, p, ep); }
+  cudaError_t le;
+  if (p.a_mn) { if (p.b_mn) le = launch_pdl(gemm_kernel<EP, true, true>, grid, 192, smem, st, ma, mb, p, ep); else le = launch_pdl(gemm_kernel<EP, true, false>, grid, 192, smem, st, ma, mb, p, ep); }
+  else { if (p.b_mn) le = launch_pdl(gemm_kernel<EP, false, true>, grid, 192, smem, st, ma, mb, p, ep); else le = launch_pdl(gemm_kernel<EP, false, false>, grid, 192, smem, st, ma, mb, p, ep); }
+  B200_CUDA(le);
   B200_LAUNCH_CHECK();
   return 0;
 }

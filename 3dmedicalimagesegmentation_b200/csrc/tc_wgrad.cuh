@@ -24,6 +24,7 @@ struct WgradParams {
   int tiles_w, tiles_h, tiles_d; long total_tiles;
   int stages; uint32_t tmem_cols;
   float* dW;
+  long long* trace;
 };
 
 __device__ __forceinline__ uint64_t smem_desc_mn(uint32_t addr, uint32_t lbo_bytes, int row_bytes) {
@@ -55,6 +56,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ 
   const int grp = blockIdx.x % p.n_groups, vs = blockIdx.x / p.n_groups;
   const int mt0 = grp * p.mt_per_cta, mt1 = min(p.n_mtiles, mt0 + p.mt_per_cta);
   const int pad = p.ks >> 1;
+  trace_start(p.trace);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(afull + s, 1); mbar_init(aempty + s, 1); }
@@ -164,6 +166,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ 
   }
   tc_fence_before();
   __syncthreads();
+  trace_end(p.trace);
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
@@ -212,6 +215,7 @@ static int conv_wgrad(const bf16* x, int x_pitch, int x_coff, int Ci, const bf16
   p.stages = (int)((200 * 1024 - 2 * b_bytes) / a_stage); if (p.stages > 6) p.stages = 6;
   B200_CHECK(p.stages >= 2, "wgrad smem budget exceeded");
   p.dW = dW;
+  p.trace = trace_slot(); if (p.trace) trace_tag("wgrad k%d %dx%d @%d", ks, Ci, Co, D);
   CUtensorMap mx, mdy;
   B200_TRY(make_brick_map(&mx, x + x_coff, x_pitch, Ci, p.atom_ch, N, D, H, W));
   B200_TRY(make_brick_map(&mdy, dy + dy_coff, dy_pitch, Co, p.b_ch, N, D, H, W));

@@ -24,6 +24,7 @@ struct WgradHaloParams {
   int tiles_w, tiles_h, tiles_per_n, total_tiles;
   int plane_bytes, x_bytes, dy_bytes, stage_bytes, stages; uint32_t tmem_cols;
   float* dW;
+  long long* trace;
 };
 
 template <int CI>   // 16 or 32
@@ -37,6 +38,7 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
   uint64_t* done = empty + p.stages;
   uint32_t* tmem_slot = (uint32_t*)(done + 1);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  trace_start(p.trace);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
@@ -134,6 +136,7 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
   }
   tc_fence_before();
   __syncthreads();
+  trace_end(p.trace);
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
@@ -175,6 +178,7 @@ static int conv_wgrad_halo(const bf16* x, int x_pitch, int x_coff, int Ci, const
   uint32_t cols = 9 * Co, pw = 32; while (pw < cols) pw <<= 1; p.tmem_cols = pw;
   B200_CHECK(p.tmem_cols <= 512, "wgrad halo TMEM budget exceeded");
   p.dW = dW;
+  p.trace = trace_slot(); if (p.trace) trace_tag("wgrad_halo %dx%d @%d", Ci, Co, D);
   CUtensorMap mx, mdy;
   {
     CUtensorMapSwizzle sw = rb == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;

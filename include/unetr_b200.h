@@ -102,6 +102,11 @@ int b200_test_tc_wgrad(const void* x, int x_pitch, int x_coff, int Ci, const voi
                        int W, int ks, float* dW, void* stream);
 /* tuning aid: 16 x int64 device buffer receiving CTA-0 clock64 phase stamps of the next tcgen05 GEMM launches (NULL = off) */
 void b200_test_set_debug_buffer(void* dev_ptr);
+/* in-situ trace of the tcgen05 launches of the following calls: buf = device int64[2*cap] pre-filled with (INT64_MAX, 0)
+ * pairs receives (min CTA start, max CTA end) of %globaltimer per launch; b200_trace_tags lists one "kind dims" line per slot */
+void b200_trace_begin(void* buf, int cap);
+int b200_trace_count(void);
+int b200_trace_tags(char* out, int cap);
 int b200_test_tc_gemm(const void* a, const void* b, float* out, int M, int N, int K, int a_mn, int b_mn, void* stream);
 
 #ifdef __cplusplus
