@@ -529,45 +529,40 @@ __global__ void in_apply_kernel(const T* __restrict__ x, ClView xv, const float*
 }
 
 // Backward, pass 1: per-(n,c) sums.  g = dOut * lrelu'(act).
-//  two==0: act = lrelu(n1) is the saved activation; n1 recovered from it.   sums: [Sg, Sg*n1]
-//  two==1: act = lrelu(n2+n3); n2,n3 recomputed from raw conv outputs.       sums: [Sg, Sg*n2, Sg*n3]
-template <class T>
-__global__ void in_bwd_reduce_kernel(const T* __restrict__ dout, ClView dv, const T* __restrict__ act, ClView av,
-                                     const T* __restrict__ ra, ClView rav, const float* __restrict__ mra,
-                                     const T* __restrict__ rb, ClView rbv, const float* __restrict__ mrb, int C, long V,
-                                     int two, double* __restrict__ acc /*[N][C][3]*/) {
+//  TWO == false: act = lrelu(n1) is the saved activation; n1 recovered from it.   sums: [Sg, Sg*n1]
+//  TWO == true : act = lrelu(n2+n3); RAW moments [Sg, S g*c2, S g*c3] of the raw conv outputs are accumulated (no per-channel
+//                constants in the loop) and converted to [Sg, Sg*n2, Sg*n3] by in_bwd_fixup_kernel: Sg*n = rstd*(S g*c - mean*Sg)
+template <class T, bool TWO>
+__global__ void __launch_bounds__(256, 3) in_bwd_reduce_kernel(const T* __restrict__ dout, ClView dv, const T* __restrict__ act, ClView av,
+                                     const T* __restrict__ ra, ClView rav, const T* __restrict__ rb, ClView rbv, int C, long V,
+                                     double* __restrict__ acc /*[N][C][3]*/) {
   constexpr int VN = Vec16<T>::N;
-  extern __shared__ float red[];  // [256][3*VN]
+  extern __shared__ float red[];  // [warps][lanes][3*VN]
   int lanes = C / VN;
   int lv = threadIdx.x % lanes, sub = threadIdx.x / lanes, nsub = blockDim.x / lanes;
   int n = blockIdx.y, c0 = lv * VN;
   long per = (V + gridDim.x - 1) / gridDim.x;
   long v0 = (long)blockIdx.x * per, v1 = min(V, v0 + per);
   float s0[VN], s1[VN], s2[VN];
-  float ma0[VN], ma1[VN], mb0[VN], mb1[VN];   // per-channel (mean, rstd) of the two raw inputs, hoisted out of the voxel loop
 #pragma unroll
-  for (int i = 0; i < VN; ++i) {
-    s0[i] = s1[i] = s2[i] = 0.f;
-    ma0[i] = two ? mra[((long)n * C + c0 + i) * 2] : 0.f; ma1[i] = two ? mra[((long)n * C + c0 + i) * 2 + 1] : 0.f;
-    mb0[i] = two ? mrb[((long)n * C + c0 + i) * 2] : 0.f; mb1[i] = two ? mrb[((long)n * C + c0 + i) * 2 + 1] : 0.f;
-  }
+  for (int i = 0; i < VN; ++i) s0[i] = s1[i] = s2[i] = 0.f;
 #pragma unroll 4
   for (long v = v0 + sub; v < v1; v += nsub) {
     long base = (long)n * V + v;
     Vec16<T> d, a; d.load(dout + base * dv.pitch + dv.coff + c0); a.load(act + base * av.pitch + av.coff + c0);
-    if (two) {
+    if (TWO) {
       Vec16<T> xa, xb; xa.load(ra + base * rav.pitch + rav.coff + c0); xb.load(rb + base * rbv.pitch + rbv.coff + c0);
 #pragma unroll
       for (int i = 0; i < VN; ++i) {
         float g = d.v[i] * (a.v[i] > 0.f ? 1.f : 0.01f);
-        s0[i] += g; s1[i] += g * (xa.v[i] - ma0[i]) * ma1[i]; s2[i] += g * (xb.v[i] - mb0[i]) * mb1[i];
+        s0[i] += g; s1[i] = fmaf(g, xa.v[i], s1[i]); s2[i] = fmaf(g, xb.v[i], s2[i]);
       }
     } else {
 #pragma unroll
       for (int i = 0; i < VN; ++i) {
         float g = d.v[i] * (a.v[i] > 0.f ? 1.f : 0.01f);
         float nn = a.v[i] > 0.f ? a.v[i] : a.v[i] * 100.f;
-        s0[i] += g; s1[i] += g * nn;
+        s0[i] += g; s1[i] = fmaf(g, nn, s1[i]);
       }
     }
   }
@@ -579,7 +574,7 @@ __global__ void in_bwd_reduce_kernel(const T* __restrict__ dout, ClView dv, cons
     const int nwarp = blockDim.x >> 5;
     for (int e = threadIdx.x; e < lanes * 3 * VN; e += blockDim.x) {
       int l = e / (3 * VN), i = e % (3 * VN);
-      if (!two && i >= 2 * VN) continue;
+      if (!TWO && i >= 2 * VN) continue;
       double tot = 0.0;
       for (int wv = 0; wv < nwarp; ++wv) tot += red[(wv * lanes + l) * 3 * VN + i];
       atomicAdd(acc + ((long)n * C + l * VN + i % VN) * 3 + i / VN, tot);
@@ -589,61 +584,91 @@ __global__ void in_bwd_reduce_kernel(const T* __restrict__ dout, ClView dv, cons
     for (int i = 0; i < VN; ++i) {
       double* a3 = acc + ((long)n * C + c0 + i) * 3;
       atomicAdd(a3, (double)s0[i]); atomicAdd(a3 + 1, (double)s1[i]);
-      if (two) atomicAdd(a3 + 2, (double)s2[i]);
+      if (TWO) atomicAdd(a3 + 2, (double)s2[i]);
     }
   }
 }
-// Backward, pass 2:  d(raw) = rstd * (g - mean(g) - n * mean(g*n))
-template <class T>
-__global__ void in_bwd_apply_kernel(const T* __restrict__ dout, ClView dv, const T* __restrict__ act, ClView av,
+// raw moments -> centred/normalised ones (TWO mode): acc[.][1] = rstd_a*(acc[1] - mean_a*acc[0]), same for [2] with (mean_b, rstd_b)
+static __global__ void in_bwd_fixup_kernel(double* __restrict__ acc, const float* __restrict__ mra, const float* __restrict__ mrb, int NC) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= NC) return;
+  double sg = acc[3 * i];
+  acc[3 * i + 1] = (double)mra[2 * i + 1] * (acc[3 * i + 1] - (double)mra[2 * i] * sg);
+  acc[3 * i + 2] = (double)mrb[2 * i + 1] * (acc[3 * i + 2] - (double)mrb[2 * i] * sg);
+}
+// Backward, pass 2:  d(raw) = rstd * (g - mean(g) - n * mean(g*n))  =  A1*g + A2*raw + A3  with per-(n,c) constants staged in smem
+//   A1 = rstd, A2 = -rstd^2 * mean(g n), A3 = rstd^2 * mean(g n) * mean - rstd * mean(g)      (TWO: one triple per raw input)
+//   !TWO: n is recovered from the saved activation: d = rstd * (g - mg - n*mgn)
+template <class T, bool TWO>
+__global__ void __launch_bounds__(256, 3) in_bwd_apply_kernel(const T* __restrict__ dout, ClView dv, const T* __restrict__ act, ClView av,
                                     const T* __restrict__ ra, ClView rav, const float* __restrict__ mra,
                                     const T* __restrict__ rb, ClView rbv, const float* __restrict__ mrb, int C, long V,
-                                    int two, const double* __restrict__ acc, T* __restrict__ da, ClView dav,
+                                    const double* __restrict__ acc, T* __restrict__ da, ClView dav,
                                     T* __restrict__ db, ClView dbv) {
   constexpr int VN = Vec16<T>::N;
+  extern __shared__ __align__(16) float cst[];   // [6][C]
   int lanes = C / VN;
   int n = blockIdx.y;
   long total = V * lanes;
   float invV = 1.f / (float)V;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const double* a3 = acc + ((long)n * C + c) * 3;
+    float mg = (float)a3[0] * invV, mga = (float)a3[1] * invV;
+    float m = mra[((long)n * C + c) * 2], r = mra[((long)n * C + c) * 2 + 1];
+    if (TWO) {
+      float mgb = (float)a3[2] * invV;
+      float m2 = mrb[((long)n * C + c) * 2], r2 = mrb[((long)n * C + c) * 2 + 1];
+      cst[c] = r; cst[C + c] = -r * r * mga; cst[2 * C + c] = r * r * mga * m - r * mg;
+      cst[3 * C + c] = r2; cst[4 * C + c] = -r2 * r2 * mgb; cst[5 * C + c] = r2 * r2 * mgb * m2 - r2 * mg;
+    } else {
+      cst[c] = r; cst[C + c] = -r * mga; cst[2 * C + c] = -r * mg;   // d = r*g + (-r*mga)*n + (-r*mg)
+    }
+  }
+  __syncthreads();
   const long e0 = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const int lv = (int)(e0 % lanes), c0 = lv * VN;   // fixed per thread (lanes divides the grid stride)
-  float ma0[VN], ma1[VN], mb0[VN], mb1[VN], mg[VN], mga[VN], mgb[VN];
-#pragma unroll
-  for (int i = 0; i < VN; ++i) {
-    const double* a3 = acc + ((long)n * C + c0 + i) * 3;
-    mg[i] = (float)a3[0] * invV; mga[i] = (float)a3[1] * invV; mgb[i] = two ? (float)a3[2] * invV : 0.f;
-    ma0[i] = mra[((long)n * C + c0 + i) * 2]; ma1[i] = mra[((long)n * C + c0 + i) * 2 + 1];
-    mb0[i] = two ? mrb[((long)n * C + c0 + i) * 2] : 0.f; mb1[i] = two ? mrb[((long)n * C + c0 + i) * 2 + 1] : 0.f;
-  }
-#pragma unroll 4
+#pragma unroll 2
   for (long e = e0; e < total; e += (long)gridDim.x * blockDim.x) {
     long v = e / lanes;
     long base = (long)n * V + v;
     Vec16<T> d, a; d.load(dout + base * dv.pitch + dv.coff + c0); a.load(act + base * av.pitch + av.coff + c0);
     Vec16<T> oa, ob;
-    if (two) {
+    if (TWO) {
       Vec16<T> xa, xb; xa.load(ra + base * rav.pitch + rav.coff + c0); xb.load(rb + base * rbv.pitch + rbv.coff + c0);
 #pragma unroll
-      for (int i = 0; i < VN; ++i) {
-        float g = d.v[i] * (a.v[i] > 0.f ? 1.f : 0.01f);
-        float na = (xa.v[i] - ma0[i]) * ma1[i], nb = (xb.v[i] - mb0[i]) * mb1[i];
-        oa.v[i] = ma1[i] * (g - mg[i] - na * mga[i]);
-        ob.v[i] = mb1[i] * (g - mg[i] - nb * mgb[i]);
+      for (int i = 0; i < VN; i += 4) {
+        float4 A1 = *reinterpret_cast<const float4*>(cst + c0 + i), A2 = *reinterpret_cast<const float4*>(cst + C + c0 + i), A3 = *reinterpret_cast<const float4*>(cst + 2 * C + c0 + i);
+        float4 B1 = *reinterpret_cast<const float4*>(cst + 3 * C + c0 + i), B2 = *reinterpret_cast<const float4*>(cst + 4 * C + c0 + i), B3 = *reinterpret_cast<const float4*>(cst + 5 * C + c0 + i);
+        const float a1[4] = {A1.x, A1.y, A1.z, A1.w}, a2[4] = {A2.x, A2.y, A2.z, A2.w}, a3c[4] = {A3.x, A3.y, A3.z, A3.w};
+        const float b1[4] = {B1.x, B1.y, B1.z, B1.w}, b2[4] = {B2.x, B2.y, B2.z, B2.w}, b3[4] = {B3.x, B3.y, B3.z, B3.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float g = d.v[i + q] * (a.v[i + q] > 0.f ? 1.f : 0.01f);
+          oa.v[i + q] = fmaf(a1[q], g, fmaf(a2[q], xa.v[i + q], a3c[q]));
+          ob.v[i + q] = fmaf(b1[q], g, fmaf(b2[q], xb.v[i + q], b3[q]));
+        }
       }
       oa.store(da + base * dav.pitch + dav.coff + c0);
       ob.store(db + base * dbv.pitch + dbv.coff + c0);
     } else {
 #pragma unroll
-      for (int i = 0; i < VN; ++i) {
-        float g = d.v[i] * (a.v[i] > 0.f ? 1.f : 0.01f);
-        float na = a.v[i] > 0.f ? a.v[i] : a.v[i] * 100.f;
-        oa.v[i] = ma1[i] * (g - mg[i] - na * mga[i]);
+      for (int i = 0; i < VN; i += 4) {
+        float4 A1 = *reinterpret_cast<const float4*>(cst + c0 + i), A2 = *reinterpret_cast<const float4*>(cst + C + c0 + i), A3 = *reinterpret_cast<const float4*>(cst + 2 * C + c0 + i);
+        const float a1[4] = {A1.x, A1.y, A1.z, A1.w}, a2[4] = {A2.x, A2.y, A2.z, A2.w}, a3c[4] = {A3.x, A3.y, A3.z, A3.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float g = d.v[i + q] * (a.v[i + q] > 0.f ? 1.f : 0.01f);
+          float na = a.v[i + q] > 0.f ? a.v[i + q] : a.v[i + q] * 100.f;
+          oa.v[i + q] = fmaf(a1[q], g, fmaf(a2[q], na, a3c[q]));
+        }
       }
       oa.store(da + base * dav.pitch + dav.coff + c0);
     }
   }
 }
 
-static inline int in_grid_x(long V) { return (int)max(1L, min((long)148 * 4, V / 512)); }
+// ~4 16-byte vectors per thread, at most 8 blocks per SM; `lanes` = vectors per voxel (C / VecN).  (V/512 left the 24^3 and 12^3
+// levels with 27-54 blocks: 15-25 us of pure latency for a few MB.)
+static inline int in_grid_x(long V, int lanes = 2) { return (int)max(1L, min((long)148 * 4, V * lanes / 1024)); }
 
 }  // namespace b200

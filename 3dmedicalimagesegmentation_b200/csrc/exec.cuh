@@ -253,7 +253,7 @@ struct Exec {
     B200_CHECK(x.C % VN == 0 && 256 % (x.C / VN) == 0 && x.pitch % VN == 0 && x.coff % VN == 0,
                "InstanceNorm channel count %d unsupported (need a power of two >= 8)", x.C);
     B200_CUDA(cudaMemsetAsync(w.stat_acc, 0, sizeof(double) * 2 * c.B * x.C, st));
-    dim3 g(in_grid_x(Vs), c.B);
+    dim3 g(in_grid_x(Vs, x.C / VN), c.B);
     in_stats_kernel<T><<<g, 256, 256 * 2 * VN * sizeof(float), st>>>(x.p, ClView{x.pitch, x.coff}, x.C, Vs, w.stat_acc);
     B200_LAUNCH_CHECK();
     in_finalize_kernel<<<cdiv(c.B * x.C, 128), 128, 0, st>>>(w.stat_acc, mr, c.B * x.C, 1.0 / (double)Vs);
@@ -262,7 +262,7 @@ struct Exec {
   }
   int in_apply(Cl<const T> x, const float* mr, const T* x2, const float* mr2, Cl<T> out, long Vs, cudaStream_t st) {
     B200_PROF("instnorm_apply", st);
-    dim3 g(in_grid_x(Vs) * 2, c.B);
+    dim3 g(in_grid_x(Vs, x.C / Vec16<T>::N) * 2, c.B);
     in_apply_kernel<T><<<g, 256, 0, st>>>(x.p, ClView{x.pitch, x.coff}, mr, x2, ClView{x.C, 0}, mr2, out.p,
                                           ClView{out.pitch, out.coff}, x.C, Vs, x2 != nullptr);
     B200_LAUNCH_CHECK();
@@ -383,16 +383,18 @@ struct Exec {
     constexpr int VN = Vec16<T>::N;
     Sp s = sp(level); long Vs = V[level]; int Co = out.C, Ci = x.C; int B = c.B;
     ClView pv{Co, 0};
-    size_t red_smem = 256 * 3 * VN * sizeof(float);
-    dim3 gr(in_grid_x(Vs), B), ga(in_grid_x(Vs) * 2, B);
+    size_t red_smem = 256 * 3 * VN * sizeof(float), cst_smem = 6 * (size_t)Co * sizeof(float);
+    dim3 gr(in_grid_x(Vs, Co / VN), B), ga(in_grid_x(Vs, Co / VN) * 2, B);
     // final lrelu + two norms
     { B200_PROF("instnorm_bwd", st);
     B200_CUDA(cudaMemsetAsync(w.bwd_acc, 0, sizeof(double) * 3 * B * Co, st));
-    in_bwd_reduce_kernel<T><<<gr, 256, red_smem, st>>>(dOut.p, ClView{dOut.pitch, dOut.coff}, out.p, ClView{out.pitch, out.coff},
-                                                      r.c2, pv, r.mr2, r.c3, pv, r.mr3, Co, Vs, 1, w.bwd_acc);
+    in_bwd_reduce_kernel<T, true><<<gr, 256, red_smem, st>>>(dOut.p, ClView{dOut.pitch, dOut.coff}, out.p, ClView{out.pitch, out.coff},
+                                                      r.c2, pv, r.c3, pv, Co, Vs, w.bwd_acc);
     B200_LAUNCH_CHECK();
-    in_bwd_apply_kernel<T><<<ga, 256, 0, st>>>(dOut.p, ClView{dOut.pitch, dOut.coff}, out.p, ClView{out.pitch, out.coff},
-                                               r.c2, pv, r.mr2, r.c3, pv, r.mr3, Co, Vs, 1, w.bwd_acc, w.dc2, pv, w.dc3, pv);
+    in_bwd_fixup_kernel<<<cdiv(B * Co, 128), 128, 0, st>>>(w.bwd_acc, r.mr2, r.mr3, B * Co);
+    B200_LAUNCH_CHECK();
+    in_bwd_apply_kernel<T, true><<<ga, 256, cst_smem, st>>>(dOut.p, ClView{dOut.pitch, dOut.coff}, out.p, ClView{out.pitch, out.coff},
+                                               r.c2, pv, r.mr2, r.c3, pv, r.mr3, Co, Vs, w.bwd_acc, w.dc2, pv, w.dc3, pv);
     B200_LAUNCH_CHECK(); }
     Cl<const T> dc2 = cl<const T>(w.dc2, Co, 0, Co), dc3 = cl<const T>(w.dc3, Co, 0, Co), a1 = cl<const T>(r.a1, Co, 0, Co);
     // conv2
@@ -401,9 +403,9 @@ struct Exec {
     // lrelu + norm1
     { B200_PROF("instnorm_bwd", st);
     B200_CUDA(cudaMemsetAsync(w.bwd_acc, 0, sizeof(double) * 3 * B * Co, st));
-    in_bwd_reduce_kernel<T><<<gr, 256, red_smem, st>>>(w.da1, pv, r.a1, pv, nullptr, pv, r.mr1, nullptr, pv, nullptr, Co, Vs, 0, w.bwd_acc);
+    in_bwd_reduce_kernel<T, false><<<gr, 256, red_smem, st>>>(w.da1, pv, r.a1, pv, nullptr, pv, nullptr, pv, Co, Vs, w.bwd_acc);
     B200_LAUNCH_CHECK();
-    in_bwd_apply_kernel<T><<<ga, 256, 0, st>>>(w.da1, pv, r.a1, pv, nullptr, pv, r.mr1, nullptr, pv, nullptr, Co, Vs, 0, w.bwd_acc,
+    in_bwd_apply_kernel<T, false><<<ga, 256, cst_smem, st>>>(w.da1, pv, r.a1, pv, nullptr, pv, r.mr1, nullptr, pv, nullptr, Co, Vs, w.bwd_acc,
                                                w.dc1, pv, nullptr, pv);
     B200_LAUNCH_CHECK(); }
     Cl<const T> dc1 = cl<const T>(w.dc1, Co, 0, Co);
