@@ -29,7 +29,7 @@ __global__ void __launch_bounds__(256) conv_in_fwd_kernel(const float* __restric
 #pragma unroll
   for (int c = 0; c < CO; ++c) s1[c] = q1[c] = s3[c] = q3[c] = 0.f;
   for (long v = (long)blockIdx.x * 256 + threadIdx.x; v < V; v += (long)gridDim.x * 256) {
-    int w = (int)(v % W); long t = v / W; int h = (int)(t % H); int d = (int)(t / H);
+    const int vi = (int)v; const int w = vi % W, t = vi / W, h = t % H, d = t / H;   // 32-bit: 64-bit div/mod is emulated (~100 instr each)
     float a1[CO], a3[CO];
 #pragma unroll
     for (int c = 0; c < CO; ++c) a1[c] = a3[c] = 0.f;
@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(256) conv_in_wgrad_kernel(const float* __restr
   const long v0 = (long)blockIdx.x * chunk, v1 = min(V, v0 + chunk);
   constexpr int VN = Vec16<T>::N;
   for (long v = v0 + lane; v < v1; v += 32) {
-    int w = (int)(v % W); long t = v / W; int h = (int)(t % H); int d = (int)(t / H);
+    const int vi = (int)v; const int w = vi % W, t = vi / W, h = t % H, d = t / H;   // 32-bit: 64-bit div/mod is emulated (~100 instr each)
     float g[CO], g3[CO];
     const T* r1 = dc1 + ((long)n * V + v) * CO;
 #pragma unroll

@@ -504,7 +504,8 @@ __global__ void in_apply_kernel(const T* __restrict__ x, ClView xv, const float*
   long total = V * lanes;
   // lanes is a power of two dividing the grid stride, so this thread always owns the same VN channels: constants live in registers
   const long e0 = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int lv = (int)(e0 % lanes), c0 = lv * VN;
+  const int lgl = 31 - __clz(lanes);   // lanes is a power of two
+  const int lv = (int)(e0 & (lanes - 1)), c0 = lv * VN;
   float m1[VN], r1[VN], m2[VN], r2[VN];
 #pragma unroll
   for (int i = 0; i < VN; ++i) {
@@ -513,7 +514,7 @@ __global__ void in_apply_kernel(const T* __restrict__ x, ClView xv, const float*
   }
 #pragma unroll 4
   for (long e = e0; e < total; e += (long)gridDim.x * blockDim.x) {
-    long v = e / lanes;
+    long v = e >> lgl;
     Vec16<T> a; a.load(x + ((long)n * V + v) * xv.pitch + xv.coff + c0);
     Vec16<T> o;
     if (two) {
@@ -626,10 +627,11 @@ __global__ void __launch_bounds__(256, 3) in_bwd_apply_kernel(const T* __restric
   }
   __syncthreads();
   const long e0 = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int lv = (int)(e0 % lanes), c0 = lv * VN;   // fixed per thread (lanes divides the grid stride)
+  const int lgl = 31 - __clz(lanes);   // lanes is a power of two
+  const int lv = (int)(e0 & (lanes - 1)), c0 = lv * VN;   // fixed per thread (lanes divides the grid stride)
 #pragma unroll 2
   for (long e = e0; e < total; e += (long)gridDim.x * blockDim.x) {
-    long v = e / lanes;
+    long v = e >> lgl;
     long base = (long)n * V + v;
     Vec16<T> d, a; d.load(dout + base * dv.pitch + dv.coff + c0); a.load(act + base * av.pitch + av.coff + c0);
     Vec16<T> oa, ob;

@@ -39,7 +39,8 @@ enum ParamIdx {
 };
 enum { B_LN1_W = 0, B_LN1_B, B_QKV_W, B_PROJ_W, B_PROJ_B, B_LN2_W, B_LN2_B, B_FC1_W, B_FC1_B, B_FC2_W, B_FC2_B, B_COUNT };
 
-enum { FLAG_NEED_ENCODER_GRAD = 1, FLAG_HAS_DLOGITS = 2, FLAG_HAS_DENC4 = 4, FLAG_SAVE_FOR_BACKWARD = 8 };
+enum { FLAG_NEED_ENCODER_GRAD = 1, FLAG_HAS_DLOGITS = 2, FLAG_HAS_DENC4 = 4, FLAG_SAVE_FOR_BACKWARD = 8,
+       FLAG_WEIGHTS_PACKED = 64 };   // the bf16 weight copies in this workspace are current (same workspace, unchanged parameters)
 
 struct Bump {
   char* base; size_t off;
@@ -444,7 +445,7 @@ struct Exec {
     layout(ws, false);
     B200_PROFC_BEGIN("F1 pack+patch", st);
     int B = c.B, fs = c.fs;
-    B200_TRY(pack_weights(P, st));
+    if (!(flags & FLAG_WEIGHTS_PACKED)) B200_TRY(pack_weights(P, st));
     cur_params = P;
     // --- patch embedding (a5): tokens = rows(x) W^T + b + pos
     {

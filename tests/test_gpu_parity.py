@@ -240,6 +240,28 @@ def test_config2_training_step_gradients(pkg, mode, cos_min, cos_med):
     assert min(r[0] for r in near_loss) >= (0.9999 if mode == "fp32" else 0.995), near_loss
 
 
+def test_inference_reuses_packed_weights_until_they_change(pkg):
+    """no_grad calls keep one workspace and skip the fp32->bf16 weight re-pack while (storage, version) of every parameter
+    is unchanged; an in-place update (optimizer step, load_state_dict) must invalidate the cache."""
+    cfg = dict(in_channels=1, out_channels=3, img_size=(32, 32, 32), feature_size=16, hidden_size=64, mlp_dim=128, num_heads=4,
+               pos_embed="perceptron", norm_name="instance", res_block=True)
+    torch.manual_seed(3)
+    net = pkg.MonaiUNETR(**cfg).to(DEV).set_mode("bf16").eval()
+    x = torch.rand(2, 1, 32, 32, 32, device=DEV)
+    with torch.no_grad():
+        a = net(x).clone()
+        b = net(x).clone()           # second call: packed weights reused
+        assert torch.equal(a, b)
+        for p in net.parameters():   # in-place change of every weight -> cache must be refreshed
+            p.mul_(1.5)
+        c = net(x).clone()
+        fresh = pkg.MonaiUNETR(**cfg).to(DEV).set_mode("bf16").eval()
+        fresh.load_state_dict(net.state_dict())
+        d = fresh(x)
+    assert not torch.equal(a, c)
+    assert torch.equal(c, d)
+
+
 # ------------------------------------------------------------------------------------------- losses
 def test_dicece_matches_oracle_and_closed_form(pkg):
     g = torch.Generator().manual_seed(0)
