@@ -77,7 +77,10 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     }
   } else if (warp == 1) {
     // ---- MMA issuer: both operands MN-major (bits 15, 16)
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(p.Co >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    // CI = 16: M = 64 (4 kw atoms, 3 useful) halves the A-operand smem read that bounds these N = 16 MMAs (ncu: tensor pipe 67 %
+    // busy at M = 128 with 5 junk atoms of 8); CI = 32: M = 128 = 4 atoms.
+    constexpr uint32_t MROWS = CI == 16 ? 64u : 128u;
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(p.Co >> 3) << 17) | ((MROWS >> 4) << 24);
     const uint32_t a_layout = CI == 32 ? 4u : 6u;                              // 64 B / 32 B swizzle
     const uint32_t b_row_bytes = (uint32_t)p.Co * 2, b_layout = b_row_bytes == 64 ? 4u : 6u;
     const uint32_t a_hi = desc_hi(HALO_W * ROW_BYTES, a_layout);               // SBO: next 8-k-row group = next h line
@@ -119,7 +122,8 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     if ((int)blockIdx.x < p.total_tiles) {
       mbar_wait(done, 0);
       tc_fence_after();
-      const int row = q * 32 + lane;
+      // M = 128: accumulator row = TMEM lane.  M = 64: rows 16q..16q+15 sit in lanes 32q..32q+15 (16 lanes per warp quarter).
+      const int row = CI == 16 ? (lane < 16 ? q * 16 + lane : 1 << 20) : q * 32 + lane;
       const int kw = row / CI, ci = row % CI;
       for (int a = 0; a < 9; ++a) {
         const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * p.Co);
