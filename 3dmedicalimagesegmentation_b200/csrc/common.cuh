@@ -1,6 +1,7 @@
 // Shared device/host helpers for the B200 UNETR library (sm_100a only).
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -80,7 +81,9 @@ __device__ __forceinline__ void trace_end(long long* slot) {
 __device__ __forceinline__ float to_f(float v) { return v; }
 __device__ __forceinline__ float to_f(bf16 v) { return __bfloat162float(v); }
 __device__ __forceinline__ float to_f(double v) { return (float)v; }
+__device__ __forceinline__ float to_f(__half v) { return __half2float(v); }
 template <class T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ __half from_f<__half>(float v) { return __float2half_rn(v); }
 template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
 template <> __device__ __forceinline__ bf16 from_f<bf16>(float v) { return __float2bfloat16_rn(v); }
 
@@ -117,6 +120,34 @@ template <> struct Vec16<bf16> {
     *reinterpret_cast<uint4*>(p) = t;
   }
 };
+
+template <> struct Vec16<__half> {
+  static constexpr int N = 8;
+  float v[8];
+  __device__ __forceinline__ void load(const __half* p) {
+    uint4 t = *reinterpret_cast<const uint4*>(p);
+    const __half2* h = reinterpret_cast<const __half2*>(&t);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float2 f = __half22float2(h[i]);
+      v[2 * i] = f.x; v[2 * i + 1] = f.y;
+    }
+  }
+  __device__ __forceinline__ void store(__half* p) const {
+    uint4 t;
+    __half2* h = reinterpret_cast<__half2*>(&t);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+    *reinterpret_cast<uint4*>(p) = t;
+  }
+};
+
+// Storage type of RAW convolution outputs (the tensors an InstanceNorm consumes).  In bf16 mode they are kept as fp16: same bytes,
+// 8x finer rounding.  Measured on the fp32 oracle (tests/test_oracle.py): bf16 rounding of these tensors alone costs 0.65e-2 of the
+// 1e-2 logits budget at configs[0] (the normalisation amplifies |mean|/std), fp16 makes that term vanish (total 0.98e-2 -> 0.70e-2).
+// Range is safe: pre-norm outputs of an InstanceNorm'd network are O(1..100) against fp16's 65504.
+template <class T> struct RawOf { typedef T type; };
+template <> struct RawOf<bf16> { typedef __half type; };
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -103,11 +103,23 @@ template <class TO>
 struct EpStore {
   TO* out; long ld, sb0, sb1; int nb1;
   const float* bias; const float* resid; long ldr; TO* preact; const TO* usrc; int act; int accumulate; float alpha;
-  int splitk_nbat;   // > 0: split-K launch -- b carries split*nbat + batch; out (fp32, pre-zeroed) is accumulated atomically and only
-                     // split 0 adds bias / residual (no activation, no pre-activation copy)
+  int splitk_nbat;   // > 0: split-K launch -- b carries split*nbat + batch.  split_stride > 0: each split stores its raw fp32 partial
+                     // tile at out + split*split_stride (the CONSUMER kernel sums the partials and adds bias / residual);
+                     // split_stride == 0: out (fp32, pre-zeroed) is accumulated atomically and split 0 adds bias / residual
+  long split_stride;
   __device__ __forceinline__ void split_store(int b, int m, int n0, const float* acc, int nvalid) const {
     const int sp = b / splitk_nbat; b -= sp * splitk_nbat;
     long o = (long)(b / nb1) * sb0 + (long)(b % nb1) * sb1 + (long)m * ld + n0;
+    if (split_stride) {
+      float* dst = reinterpret_cast<float*>(out) + sp * split_stride + o;
+      if (nvalid == 16 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(acc[j] * alpha, acc[j + 1] * alpha, acc[j + 2] * alpha, acc[j + 3] * alpha);
+      } else {
+        for (int j = 0; j < nvalid; ++j) dst[j] = acc[j] * alpha;
+      }
+      return;
+    }
     for (int j = 0; j < nvalid; ++j) {
       float v = acc[j] * alpha;
       if (sp == 0) { if (bias) v += bias[n0 + j]; if (resid) v += resid[(long)m * ldr + n0 + j]; }

@@ -15,8 +15,9 @@ namespace b200 {
 // stats1/stats3: double [N][CO][2] (sum, sumsq), zeroed by the caller.
 template <class T, int CO>
 __global__ void __launch_bounds__(256) conv_in_fwd_kernel(const float* __restrict__ x, const float* __restrict__ W1, const float* __restrict__ W3,
-                                                          int Cin, int D, int H, int W, T* __restrict__ c1, T* __restrict__ c3,
+                                                          int Cin, int D, int H, int W, typename RawOf<T>::type* __restrict__ c1, typename RawOf<T>::type* __restrict__ c3,
                                                           double* __restrict__ stats1, double* __restrict__ stats3) {
+  typedef typename RawOf<T>::type TR;   // raw conv outputs (see RawOf)
   extern __shared__ float sw[];   // W1 as [ci][tap][CO], then W3 as [ci][CO]
   __shared__ float red[8][4 * CO];
   const long V = (long)D * H * W;
@@ -58,11 +59,11 @@ __global__ void __launch_bounds__(256) conv_in_fwd_kernel(const float* __restric
         }
       }
     }
-    constexpr int VN = Vec16<T>::N;
-    T* o1 = c1 + ((long)n * V + v) * CO; T* o3 = c3 + ((long)n * V + v) * CO;
+    constexpr int VN = Vec16<TR>::N;
+    TR* o1 = c1 + ((long)n * V + v) * CO; TR* o3 = c3 + ((long)n * V + v) * CO;
 #pragma unroll
     for (int c0 = 0; c0 < CO; c0 += VN) {
-      Vec16<T> p, r;
+      Vec16<TR> p, r;
 #pragma unroll
       for (int i = 0; i < VN; ++i) { p.v[i] = a1[c0 + i]; r.v[i] = a3[c0 + i]; }
       p.store(o1 + c0); r.store(o3 + c0);
@@ -151,7 +152,7 @@ __global__ void __launch_bounds__(256) conv_in_wgrad_kernel(const float* __restr
 // ---------------------------------------------------------------------------------------------- fused last norm pass + head
 // d0[v,c] = lrelu(norm(c2)[v,c] + norm(c3)[v,c]) (stored as T for the backward), logits[n][k][v] = sum_c d0_fp32[c] Wh[k][c] + bh[k]
 template <class T, int CO>
-__global__ void __launch_bounds__(256) in_apply_head_kernel(const T* __restrict__ c2, const float* __restrict__ mr2, const T* __restrict__ c3,
+__global__ void __launch_bounds__(256) in_apply_head_kernel(const typename RawOf<T>::type* __restrict__ c2, const float* __restrict__ mr2, const typename RawOf<T>::type* __restrict__ c3,
                                                             const float* __restrict__ mr3, T* __restrict__ d0, const float* __restrict__ Wh,
                                                             const float* __restrict__ bh, int ncls, long V, float* __restrict__ logits) {
   __shared__ float sW[32 * CO], sb[32], sm[4 * CO];
@@ -166,7 +167,7 @@ __global__ void __launch_bounds__(256) in_apply_head_kernel(const T* __restrict_
     float o[CO];
 #pragma unroll
     for (int c0 = 0; c0 < CO; c0 += VN) {
-      Vec16<T> a, b, r; a.load(c2 + row + c0); b.load(c3 + row + c0);
+      Vec16<typename RawOf<T>::type> a, b; Vec16<T> r; a.load(c2 + row + c0); b.load(c3 + row + c0);
 #pragma unroll
       for (int i = 0; i < VN; ++i) {
         int c = c0 + i;

@@ -145,16 +145,36 @@ __device__ __forceinline__ void store4(bf16* p, const float* v) {
 
 // Register-resident variants for H = NV4*128 (ViT-B: 768 -> NV4 = 6): every load of a row is issued before the first
 // use, one pass over memory (the generic kernels below are latency-bound: 2-3 dependent passes of 24 scalar loads).
+// Split-K producer fused into its consumer: x[row] = resid[row] + bias + sum_s part[s][row] is formed here (and written to xsum,
+// the fp32 residual stream) instead of by atomics in the GEMM epilogue.
+struct SplitSum { const float* part; int nsplit; long stride; const float* bias; const float* resid; float* xsum; };
 template <class TO, int NV4>
 __global__ void layernorm_fwd_reg_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
-                                         TO* __restrict__ y, float* __restrict__ stats, int M) {
+                                         TO* __restrict__ y, float* __restrict__ stats, int M, const SplitSum ss) {
   constexpr int H = NV4 * 128;
   int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= M) return;
   const float* xr = x + (long)row * H;
   float v[NV4][4];
+  if (ss.nsplit) {
 #pragma unroll
-  for (int i = 0; i < NV4; ++i) load4(xr + (i * 32 + lane) * 4, v[i]);
+    for (int i = 0; i < NV4; ++i) {
+      const long o = (long)row * H + (i * 32 + lane) * 4;
+      float b4[4], p4[4];
+      load4(ss.resid + o, v[i]); load4(ss.bias + (i * 32 + lane) * 4, b4);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[i][j] += b4[j];
+      for (int sp = 0; sp < ss.nsplit; ++sp) {
+        load4(ss.part + sp * ss.stride + o, p4);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[i][j] += p4[j];
+      }
+      store4(ss.xsum + o, v[i]);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < NV4; ++i) load4(xr + (i * 32 + lane) * 4, v[i]);
+  }
   float s = 0.f;
 #pragma unroll
   for (int i = 0; i < NV4; ++i) s += (v[i][0] + v[i][1]) + (v[i][2] + v[i][3]);
@@ -175,9 +195,12 @@ __global__ void layernorm_fwd_reg_kernel(const float* __restrict__ x, const floa
   }
   if (lane == 0 && stats) { stats[2 * row] = mean; stats[2 * row + 1] = rstd; }
 }
+// ss.nsplit > 0: the incoming gradient g is the sum of the producer GEMM's split-K partials (fp32); it is also written back as TG to
+// ss_gout (the parameter-gradient kernel reads it)
 template <class TG, int NV4>
 __global__ void layernorm_bwd_dx_reg_kernel(const TG* __restrict__ g, const float* __restrict__ x, const float* __restrict__ stats,
-                                            const float* __restrict__ gamma, const float* dx_res, float* dx_out, TG* dx_out_cast, int M) {
+                                            const float* __restrict__ gamma, const float* dx_res, float* dx_out, TG* dx_out_cast, int M,
+                                            const SplitSum ss, TG* ss_gout) {
   constexpr int H = NV4 * 128;
   int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= M) return;
@@ -187,7 +210,19 @@ __global__ void layernorm_bwd_dx_reg_kernel(const TG* __restrict__ g, const floa
   for (int i = 0; i < NV4; ++i) {
     const long o = (long)row * H + (i * 32 + lane) * 4;
     float gm[4];
-    load4(g + o, gg[i]); load4(x + o, xh[i]); load4(gamma + (i * 32 + lane) * 4, gm);
+    if (ss.nsplit) {
+      float p4[4];
+      load4(ss.part + o, gg[i]);
+      for (int sp = 1; sp < ss.nsplit; ++sp) {
+        load4(ss.part + sp * ss.stride + o, p4);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) gg[i][j] += p4[j];
+      }
+      store4(ss_gout + o, gg[i]);
+    } else {
+      load4(g + o, gg[i]);
+    }
+    load4(x + o, xh[i]); load4(gamma + (i * 32 + lane) * 4, gm);
     if (dx_res) load4(dx_res + o, rs[i]);
     else { rs[i][0] = rs[i][1] = rs[i][2] = rs[i][3] = 0.f; }
 #pragma unroll
@@ -228,9 +263,11 @@ __global__ void layernorm_fwd_kernel(const float* __restrict__ x, const float* _
 }
 template <class TO>
 static int launch_layernorm_fwd(const float* x, const float* g, const float* b, TO* y, float* stats, int M, int H,
-                                cudaStream_t st) {
+                                cudaStream_t st, const SplitSum* ss = nullptr) {
   B200_PROF("layernorm_fwd", st);
-  if (H == 768) layernorm_fwd_reg_kernel<TO, 6><<<cdiv(M, 4), 128, 0, st>>>(x, g, b, y, stats, M);
+  SplitSum none; memset(&none, 0, sizeof(none));
+  B200_CHECK(!ss || H == 768, "fused split-K LayerNorm needs hidden size 768");
+  if (H == 768) layernorm_fwd_reg_kernel<TO, 6><<<cdiv(M, 4), 128, 0, st>>>(x, g, b, y, stats, M, ss ? *ss : none);
   else layernorm_fwd_kernel<TO><<<cdiv(M, 8), 256, 0, st>>>(x, g, b, y, stats, M, H);
   B200_LAUNCH_CHECK();
   return 0;
@@ -288,9 +325,11 @@ __global__ void layernorm_bwd_params_kernel(const TG* __restrict__ g, const floa
 template <class TG>
 static int launch_layernorm_bwd(const TG* g, const float* x, const float* stats, const float* gamma,
                                 const float* dx_res, float* dx_out, TG* dx_out_cast, float* dgamma, float* dbeta, int M, int H,
-                                cudaStream_t st) {
+                                cudaStream_t st, const SplitSum* ss = nullptr) {
   B200_PROF("layernorm_bwd", st);
-  if (H == 768) layernorm_bwd_dx_reg_kernel<TG, 6><<<cdiv(M, 4), 128, 0, st>>>(g, x, stats, gamma, dx_res, dx_out, dx_out_cast, M);
+  SplitSum none; memset(&none, 0, sizeof(none));
+  B200_CHECK(!ss || H == 768, "fused split-K LayerNorm needs hidden size 768");
+  if (H == 768) layernorm_bwd_dx_reg_kernel<TG, 6><<<cdiv(M, 4), 128, 0, st>>>(g, x, stats, gamma, dx_res, dx_out, dx_out_cast, M, ss ? *ss : none, const_cast<TG*>(g));
   else layernorm_bwd_dx_kernel<TG><<<cdiv(M, 8), 256, 0, st>>>(g, x, stats, gamma, dx_res, dx_out, dx_out_cast, M, H);
   B200_LAUNCH_CHECK();
   if (dgamma) {
@@ -444,7 +483,8 @@ __device__ __forceinline__ void block_reduce_groups(float* vals, int lanes, floa
 }
 
 template <class T>
-__global__ void in_stats_kernel(const T* __restrict__ x, ClView xv, int C, long V, double* __restrict__ acc) {
+__global__ void in_stats_kernel(const typename RawOf<T>::type* __restrict__ x, ClView xv, int C, long V, double* __restrict__ acc) {
+  typedef typename RawOf<T>::type TR;
   constexpr int VN = Vec16<T>::N;
   extern __shared__ float red[];  // [256][2*VN]
   int lanes = C / VN;             // vectors per voxel
@@ -457,7 +497,7 @@ __global__ void in_stats_kernel(const T* __restrict__ x, ClView xv, int C, long 
   for (int i = 0; i < VN; ++i) s[i] = q[i] = 0.f;
 #pragma unroll 4
   for (long v = v0 + sub; v < v1; v += nsub) {
-    Vec16<T> a; a.load(x + ((long)n * V + v) * xv.pitch + xv.coff + lv * VN);
+    Vec16<TR> a; a.load(x + ((long)n * V + v) * xv.pitch + xv.coff + lv * VN);
 #pragma unroll
     for (int i = 0; i < VN; ++i) { s[i] += a.v[i]; q[i] += a.v[i] * a.v[i]; }
   }
@@ -495,8 +535,8 @@ static __global__ void in_finalize_kernel(const double* __restrict__ acc, float*
 // out = lrelu(norm(x))                            (two==0)
 // out = lrelu(norm_a(x) + norm_b(x2))             (two==1)
 template <class T>
-__global__ void in_apply_kernel(const T* __restrict__ x, ClView xv, const float* __restrict__ mr,
-                                const T* __restrict__ x2, ClView x2v, const float* __restrict__ mr2, T* __restrict__ out,
+__global__ void in_apply_kernel(const typename RawOf<T>::type* __restrict__ x, ClView xv, const float* __restrict__ mr,
+                                const typename RawOf<T>::type* __restrict__ x2, ClView x2v, const float* __restrict__ mr2, T* __restrict__ out,
                                 ClView ov, int C, long V, int two) {
   constexpr int VN = Vec16<T>::N;
   int lanes = C / VN;
@@ -515,10 +555,10 @@ __global__ void in_apply_kernel(const T* __restrict__ x, ClView xv, const float*
 #pragma unroll 4
   for (long e = e0; e < total; e += (long)gridDim.x * blockDim.x) {
     long v = e >> lgl;
-    Vec16<T> a; a.load(x + ((long)n * V + v) * xv.pitch + xv.coff + c0);
+    Vec16<typename RawOf<T>::type> a; a.load(x + ((long)n * V + v) * xv.pitch + xv.coff + c0);
     Vec16<T> o;
     if (two) {
-      Vec16<T> b; b.load(x2 + ((long)n * V + v) * x2v.pitch + x2v.coff + c0);
+      Vec16<typename RawOf<T>::type> b; b.load(x2 + ((long)n * V + v) * x2v.pitch + x2v.coff + c0);
 #pragma unroll
       for (int i = 0; i < VN; ++i) o.v[i] = lrelu((a.v[i] - m1[i]) * r1[i] + (b.v[i] - m2[i]) * r2[i]);
     } else {
@@ -535,7 +575,7 @@ __global__ void in_apply_kernel(const T* __restrict__ x, ClView xv, const float*
 //                constants in the loop) and converted to [Sg, Sg*n2, Sg*n3] by in_bwd_fixup_kernel: Sg*n = rstd*(S g*c - mean*Sg)
 template <class T, bool TWO>
 __global__ void __launch_bounds__(256, 3) in_bwd_reduce_kernel(const T* __restrict__ dout, ClView dv, const T* __restrict__ act, ClView av,
-                                     const T* __restrict__ ra, ClView rav, const T* __restrict__ rb, ClView rbv, int C, long V,
+                                     const typename RawOf<T>::type* __restrict__ ra, ClView rav, const typename RawOf<T>::type* __restrict__ rb, ClView rbv, int C, long V,
                                      double* __restrict__ acc /*[N][C][3]*/) {
   constexpr int VN = Vec16<T>::N;
   extern __shared__ float red[];  // [warps][lanes][3*VN]
@@ -552,7 +592,7 @@ __global__ void __launch_bounds__(256, 3) in_bwd_reduce_kernel(const T* __restri
     long base = (long)n * V + v;
     Vec16<T> d, a; d.load(dout + base * dv.pitch + dv.coff + c0); a.load(act + base * av.pitch + av.coff + c0);
     if (TWO) {
-      Vec16<T> xa, xb; xa.load(ra + base * rav.pitch + rav.coff + c0); xb.load(rb + base * rbv.pitch + rbv.coff + c0);
+      Vec16<typename RawOf<T>::type> xa, xb; xa.load(ra + base * rav.pitch + rav.coff + c0); xb.load(rb + base * rbv.pitch + rbv.coff + c0);
 #pragma unroll
       for (int i = 0; i < VN; ++i) {
         float g = d.v[i] * (a.v[i] > 0.f ? 1.f : 0.01f);
@@ -602,8 +642,8 @@ static __global__ void in_bwd_fixup_kernel(double* __restrict__ acc, const float
 //   !TWO: n is recovered from the saved activation: d = rstd * (g - mg - n*mgn)
 template <class T, bool TWO>
 __global__ void __launch_bounds__(256, 3) in_bwd_apply_kernel(const T* __restrict__ dout, ClView dv, const T* __restrict__ act, ClView av,
-                                    const T* __restrict__ ra, ClView rav, const float* __restrict__ mra,
-                                    const T* __restrict__ rb, ClView rbv, const float* __restrict__ mrb, int C, long V,
+                                    const typename RawOf<T>::type* __restrict__ ra, ClView rav, const float* __restrict__ mra,
+                                    const typename RawOf<T>::type* __restrict__ rb, ClView rbv, const float* __restrict__ mrb, int C, long V,
                                     const double* __restrict__ acc, T* __restrict__ da, ClView dav,
                                     T* __restrict__ db, ClView dbv) {
   constexpr int VN = Vec16<T>::N;
@@ -636,7 +676,7 @@ __global__ void __launch_bounds__(256, 3) in_bwd_apply_kernel(const T* __restric
     Vec16<T> d, a; d.load(dout + base * dv.pitch + dv.coff + c0); a.load(act + base * av.pitch + av.coff + c0);
     Vec16<T> oa, ob;
     if (TWO) {
-      Vec16<T> xa, xb; xa.load(ra + base * rav.pitch + rav.coff + c0); xb.load(rb + base * rbv.pitch + rbv.coff + c0);
+      Vec16<typename RawOf<T>::type> xa, xb; xa.load(ra + base * rav.pitch + rav.coff + c0); xb.load(rb + base * rbv.pitch + rbv.coff + c0);
 #pragma unroll
       for (int i = 0; i < VN; i += 4) {
         float4 A1 = *reinterpret_cast<const float4*>(cst + c0 + i), A2 = *reinterpret_cast<const float4*>(cst + C + c0 + i), A3 = *reinterpret_cast<const float4*>(cst + 2 * C + c0 + i);

@@ -72,6 +72,7 @@ struct Workspace {
   bf16 *wTt[10], *wpatch, *apatch;  // tap-major transposed-conv weights; patch weight; gathered bf16 patch rows [M, 4096*Cin]  // conv weights packed [tap][co][ci] (forward) and [tap'][ci][co] (dgrad, taps flipped)
   // backward scratch
   float *dx, *dx2, *dhs[3], *dP;
+  float* part;   // split-K partial tiles [<=4][M][H] (summed by the LayerNorm kernel that consumes the GEMM)
   T *dxb, *dx2b, *unsh;  // unsh: pixel-unshuffled dOut of a transposed conv [rows_in, 8*Co]  // bf16 mode: operand copies of the fp32 residual-stream gradients
   T *dvit, *dh, *dln, *datt, *dqkv, *dS, *gA, *dcat, *dc2, *dc3, *da1, *dc1;
   double* bwd_acc;
@@ -80,6 +81,7 @@ struct Workspace {
 
 template <class T>
 struct Exec {
+  typedef typename RawOf<T>::type TR;   // storage type of raw conv outputs (c1, c2, c3 of every residual block)
   UnetrConfig c;
   int g0, g1, g2, L, Lp, M, H, F, nh, dh;
   long V[5];  // voxels per sample at levels 0 (full) .. 4 (tokens)
@@ -126,6 +128,7 @@ struct Exec {
     size_t MH = (size_t)M * H, MF = (size_t)M * F, PP = (size_t)c.B * nh * L * Lp;
     int fs = c.fs, B = c.B;
     w.x0 = b.take<float>(MH);
+    w.part = b.take<float>(4 * MH);
     for (int i = 0; i < 12; ++i) {
       w.hs[i] = b.take<float>(MH); w.x1[i] = b.take<float>(MH);
       w.ln1s[i] = b.take<float>(2 * M); w.ln2s[i] = b.take<float>(2 * M);
@@ -178,18 +181,34 @@ struct Exec {
   int linear_fwd(const T* A, long lda, const float* W, const bf16* Wb, int Mr, int N, int K, const EpStore<TO>& ep, cudaStream_t st) {
     if constexpr (kTC) {
       B200_PROFD(st, "linear_fwd %dx%dx%d", Mr, N, K);
-      if constexpr (std::is_same<TO, float>::value) {   // few output tiles + long K: split K across SMs, fp32 atomics into a zeroed output
-        int ks = (ep.act == ACT_NONE && !ep.preact && !ep.accumulate && ep.sb0 == 0 && ep.sb1 == 0 && ep.ld == N) ? tc::plan_splitk(Mr, N, K, 1) : 1;
-        if (ks > 1) {
-          B200_CUDA(cudaMemsetAsync(ep.out, 0, sizeof(float) * (size_t)Mr * N, st));
-          EpStore<TO> e2 = ep; e2.splitk_nbat = 1;
-          return tc::gemm(tc::operand(A, lda, 1), tc::operand(Wb, K, 1), e2, Mr, N, K, 1, 1, st, false, ks);
-        }
-      }
       return tc::gemm(tc::operand(A, lda, 1), tc::operand(Wb, K, 1), ep, Mr, N, K, 1, 1, st);
     } else {
       return simt_linear_fwd(A, lda, W, Mr, N, K, ep, st);
     }
+  }
+  // Split-K variants for the N = hidden GEMMs (48 output tiles on 148 SMs): the splits store raw fp32 partial tiles into w.part and
+  // the LayerNorm kernel that consumes the result sums them (+ bias + residual).  Returns the split count in *ss (0 = not split).
+  bool can_split(int Mr, int N, int K) const { return kTC && H == 768 && N == H && Mr == M && tc::plan_splitk(Mr, N, K, 1) > 1; }
+  int linear_fwd_split(const T* A, long lda, const bf16* Wb, int Mr, int N, int K, const float* bias, const float* resid, float* xsum,
+                       SplitSum* ss, cudaStream_t st) {
+    if constexpr (kTC) {
+      B200_PROFD(st, "linear_fwd %dx%dx%d", Mr, N, K);
+      const int ks = tc::plan_splitk(Mr, N, K, 1);
+      EpStore<float> e = ep_plain<float>(w.part, N); e.splitk_nbat = 1; e.split_stride = (long)Mr * N;
+      B200_TRY(tc::gemm(tc::operand(A, lda, 1), tc::operand(Wb, K, 1), e, Mr, N, K, 1, 1, st, false, ks));
+      *ss = SplitSum{w.part, ks, (long)Mr * N, bias, resid, xsum};
+    }
+    return 0;
+  }
+  int linear_dgrad_split(const T* dY, long ldy, const bf16* Wb, int Mr, int N, int K, SplitSum* ss, cudaStream_t st) {
+    if constexpr (kTC) {
+      B200_PROFD(st, "linear_dgrad %dx%dx%d", Mr, K, N);
+      const int ks = tc::plan_splitk(Mr, K, N, 1);
+      EpStore<float> e = ep_plain<float>(w.part, K); e.splitk_nbat = 1; e.split_stride = (long)Mr * K;
+      B200_TRY(tc::gemm(tc::operand(dY, ldy, 1), tc::operand(Wb, 1, K), e, Mr, K, N, 1, 1, st, false, ks));
+      *ss = SplitSum{w.part, ks, (long)Mr * K, nullptr, nullptr, nullptr};
+    }
+    return 0;
   }
   template <class TO>  // dX[M,K] = dY[M,N] W[N,K]   (W is the MN-major B operand: no transposed copy)
   int linear_dgrad(const T* dY, long ldy, const float* W, const bf16* Wb, int Mr, int N, int K, const EpStore<TO>& ep, cudaStream_t st) {
@@ -255,7 +274,7 @@ struct Exec {
                "InstanceNorm channel count %d unsupported (need a power of two >= 8)", x.C);
     B200_CUDA(cudaMemsetAsync(w.stat_acc, 0, sizeof(double) * 2 * c.B * x.C, st));
     dim3 g(in_grid_x(Vs, x.C / VN), c.B);
-    in_stats_kernel<T><<<g, 256, 256 * 2 * VN * sizeof(float), st>>>(x.p, ClView{x.pitch, x.coff}, x.C, Vs, w.stat_acc);
+    in_stats_kernel<T><<<g, 256, 256 * 2 * VN * sizeof(float), st>>>(reinterpret_cast<const TR*>(x.p), ClView{x.pitch, x.coff}, x.C, Vs, w.stat_acc);
     B200_LAUNCH_CHECK();
     in_finalize_kernel<<<cdiv(c.B * x.C, 128), 128, 0, st>>>(w.stat_acc, mr, c.B * x.C, 1.0 / (double)Vs);
     B200_LAUNCH_CHECK();
@@ -264,7 +283,7 @@ struct Exec {
   int in_apply(Cl<const T> x, const float* mr, const T* x2, const float* mr2, Cl<T> out, long Vs, cudaStream_t st) {
     B200_PROF("instnorm_apply", st);
     dim3 g(in_grid_x(Vs, x.C / Vec16<T>::N) * 2, c.B);
-    in_apply_kernel<T><<<g, 256, 0, st>>>(x.p, ClView{x.pitch, x.coff}, mr, x2, ClView{x.C, 0}, mr2, out.p,
+    in_apply_kernel<T><<<g, 256, 0, st>>>(reinterpret_cast<const TR*>(x.p), ClView{x.pitch, x.coff}, mr, reinterpret_cast<const TR*>(x2), ClView{x.C, 0}, mr2, out.p,
                                           ClView{out.pitch, out.coff}, x.C, Vs, x2 != nullptr);
     B200_LAUNCH_CHECK();
     return 0;
@@ -281,8 +300,8 @@ struct Exec {
         B200_PROFD(st, "conv_fwd k%d %d->%d @%d", ks, x.C, Co, s.D);
         if (stats) { B200_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * c.B * Co, st)); if (stats_done) *stats_done = true; }
         if (ks == 3 && tc::conv_halo_supported(x.C, Co))
-          return tc::conv_halo(x.p, x.pitch, x.coff, x.C, s.N, s.D, s.H, s.W, w.wcf[ci], Co, out.p, out.pitch, out.coff, 0, stats, st);
-        return tc::conv(x.p, x.pitch, x.coff, x.C, s.N, s.D, s.H, s.W, w.wcf[ci], Co, ks, out.p, out.pitch, out.coff, 0, stats, st);
+          return tc::conv_halo(x.p, x.pitch, x.coff, x.C, s.N, s.D, s.H, s.W, w.wcf[ci], Co, out.p, out.pitch, out.coff, 0, stats, st, nullptr, 1);
+        return tc::conv(x.p, x.pitch, x.coff, x.C, s.N, s.D, s.H, s.W, w.wcf[ci], Co, ks, out.p, out.pitch, out.coff, 0, stats, st, 1);
       }
     }
     return simt_conv_fwd<T>(x, s, W, Co, ks, out, st);
@@ -327,9 +346,9 @@ struct Exec {
         B200_CUDA(cudaMemsetAsync(w.stat_acc, 0, sizeof(double) * 4 * c.B * 8 * c.fs, st));
         dim3 g((unsigned)min(148L * 4, (Vs + 255) / 256), c.B);
         size_t sm = sizeof(float) * ((size_t)c.Cin * 27 * Co + (size_t)c.Cin * Co);
-        if (Co == 8) conv_in_fwd_kernel<T, 8><<<g, 256, sm, st>>>(raw, W1, W3, c.Cin, s.D, s.H, s.W, c1.p, c3.p, w.stat_acc, st3);
-        else if (Co == 16) conv_in_fwd_kernel<T, 16><<<g, 256, sm, st>>>(raw, W1, W3, c.Cin, s.D, s.H, s.W, c1.p, c3.p, w.stat_acc, st3);
-        else conv_in_fwd_kernel<T, 32><<<g, 256, sm, st>>>(raw, W1, W3, c.Cin, s.D, s.H, s.W, c1.p, c3.p, w.stat_acc, st3);
+        if (Co == 8) conv_in_fwd_kernel<T, 8><<<g, 256, sm, st>>>(raw, W1, W3, c.Cin, s.D, s.H, s.W, (TR*)c1.p, (TR*)c3.p, w.stat_acc, st3);
+        else if (Co == 16) conv_in_fwd_kernel<T, 16><<<g, 256, sm, st>>>(raw, W1, W3, c.Cin, s.D, s.H, s.W, (TR*)c1.p, (TR*)c3.p, w.stat_acc, st3);
+        else conv_in_fwd_kernel<T, 32><<<g, 256, sm, st>>>(raw, W1, W3, c.Cin, s.D, s.H, s.W, (TR*)c1.p, (TR*)c3.p, w.stat_acc, st3);
         B200_LAUNCH_CHECK();
         in_finalize_kernel<<<cdiv(c.B * Co, 128), 128, 0, st>>>(w.stat_acc, r.mr1, c.B * Co, 1.0 / (double)Vs); B200_LAUNCH_CHECK();
         in_finalize_kernel<<<cdiv(c.B * Co, 128), 128, 0, st>>>(st3, r.mr3, c.B * Co, 1.0 / (double)Vs); B200_LAUNCH_CHECK();
@@ -348,7 +367,7 @@ struct Exec {
         double* st3 = w.stat_acc + (size_t)2 * c.B * 8 * c.fs;
         B200_CUDA(cudaMemsetAsync(w.stat_acc, 0, sizeof(double) * 4 * c.B * 8 * c.fs, st));
         tc::HaloFused fu = {1, w.wcf[i3], c3.p, Co, 0, st3, nullptr, 0, 0};
-        B200_TRY(tc::conv_halo(x.p, x.pitch, x.coff, x.C, s.N, s.D, s.H, s.W, w.wcf[i1], Co, c1.p, Co, 0, 0, w.stat_acc, st, &fu));
+        B200_TRY(tc::conv_halo(x.p, x.pitch, x.coff, x.C, s.N, s.D, s.H, s.W, w.wcf[i1], Co, c1.p, Co, 0, 0, w.stat_acc, st, &fu, 1));
         in_finalize_kernel<<<cdiv(c.B * Co, 128), 128, 0, st>>>(w.stat_acc, r.mr1, c.B * Co, 1.0 / (double)Vs); B200_LAUNCH_CHECK();
         in_finalize_kernel<<<cdiv(c.B * Co, 128), 128, 0, st>>>(st3, r.mr3, c.B * Co, 1.0 / (double)Vs); B200_LAUNCH_CHECK();
         fused13 = true;
@@ -368,9 +387,9 @@ struct Exec {
     if (head && out.pitch == Co && out.coff == 0) {
       B200_PROF("norm_head_fwd", st);
       dim3 g((unsigned)min(148L * 4, (Vs + 255) / 256), c.B);
-      if (Co == 8) in_apply_head_kernel<T, 8><<<g, 256, 0, st>>>(c2.p, r.mr2, c3.p, r.mr3, out.p, head->Wh, head->bh, c.ncls, Vs, head->logits);
-      else if (Co == 16) in_apply_head_kernel<T, 16><<<g, 256, 0, st>>>(c2.p, r.mr2, c3.p, r.mr3, out.p, head->Wh, head->bh, c.ncls, Vs, head->logits);
-      else in_apply_head_kernel<T, 32><<<g, 256, 0, st>>>(c2.p, r.mr2, c3.p, r.mr3, out.p, head->Wh, head->bh, c.ncls, Vs, head->logits);
+      if (Co == 8) in_apply_head_kernel<T, 8><<<g, 256, 0, st>>>((const TR*)c2.p, r.mr2, (const TR*)c3.p, r.mr3, out.p, head->Wh, head->bh, c.ncls, Vs, head->logits);
+      else if (Co == 16) in_apply_head_kernel<T, 16><<<g, 256, 0, st>>>((const TR*)c2.p, r.mr2, (const TR*)c3.p, r.mr3, out.p, head->Wh, head->bh, c.ncls, Vs, head->logits);
+      else in_apply_head_kernel<T, 32><<<g, 256, 0, st>>>((const TR*)c2.p, r.mr2, (const TR*)c3.p, r.mr3, out.p, head->Wh, head->bh, c.ncls, Vs, head->logits);
       B200_LAUNCH_CHECK();
       return 0;
     }
@@ -390,12 +409,12 @@ struct Exec {
     { B200_PROF("instnorm_bwd", st);
     B200_CUDA(cudaMemsetAsync(w.bwd_acc, 0, sizeof(double) * 3 * B * Co, st));
     in_bwd_reduce_kernel<T, true><<<gr, 256, red_smem, st>>>(dOut.p, ClView{dOut.pitch, dOut.coff}, out.p, ClView{out.pitch, out.coff},
-                                                      r.c2, pv, r.c3, pv, Co, Vs, w.bwd_acc);
+                                                      (const TR*)r.c2, pv, (const TR*)r.c3, pv, Co, Vs, w.bwd_acc);
     B200_LAUNCH_CHECK();
     in_bwd_fixup_kernel<<<cdiv(B * Co, 128), 128, 0, st>>>(w.bwd_acc, r.mr2, r.mr3, B * Co);
     B200_LAUNCH_CHECK();
     in_bwd_apply_kernel<T, true><<<ga, 256, cst_smem, st>>>(dOut.p, ClView{dOut.pitch, dOut.coff}, out.p, ClView{out.pitch, out.coff},
-                                               r.c2, pv, r.mr2, r.c3, pv, r.mr3, Co, Vs, w.bwd_acc, w.dc2, pv, w.dc3, pv);
+                                               (const TR*)r.c2, pv, r.mr2, (const TR*)r.c3, pv, r.mr3, Co, Vs, w.bwd_acc, w.dc2, pv, w.dc3, pv);
     B200_LAUNCH_CHECK(); }
     Cl<const T> dc2 = cl<const T>(w.dc2, Co, 0, Co), dc3 = cl<const T>(w.dc3, Co, 0, Co), a1 = cl<const T>(r.a1, Co, 0, Co);
     // conv2
@@ -404,9 +423,9 @@ struct Exec {
     // lrelu + norm1
     { B200_PROF("instnorm_bwd", st);
     B200_CUDA(cudaMemsetAsync(w.bwd_acc, 0, sizeof(double) * 3 * B * Co, st));
-    in_bwd_reduce_kernel<T, false><<<gr, 256, red_smem, st>>>(w.da1, pv, r.a1, pv, nullptr, pv, nullptr, pv, Co, Vs, w.bwd_acc);
+    in_bwd_reduce_kernel<T, false><<<gr, 256, red_smem, st>>>(w.da1, pv, r.a1, pv, (const TR*)nullptr, pv, (const TR*)nullptr, pv, Co, Vs, w.bwd_acc);
     B200_LAUNCH_CHECK();
-    in_bwd_apply_kernel<T, false><<<ga, 256, cst_smem, st>>>(w.da1, pv, r.a1, pv, nullptr, pv, r.mr1, nullptr, pv, nullptr, Co, Vs, w.bwd_acc,
+    in_bwd_apply_kernel<T, false><<<ga, 256, cst_smem, st>>>(w.da1, pv, r.a1, pv, (const TR*)nullptr, pv, r.mr1, (const TR*)nullptr, pv, nullptr, Co, Vs, w.bwd_acc,
                                                w.dc1, pv, nullptr, pv);
     B200_LAUNCH_CHECK(); }
     Cl<const T> dc1 = cl<const T>(w.dc1, Co, 0, Co);
@@ -464,21 +483,32 @@ struct Exec {
     B200_PROFC_END(st); B200_PROFC_BEGIN("F2 vit", st);
     // --- transformer blocks (a6-a8)
     float scale = 1.0f / sqrtf((float)dh);
+    SplitSum pend; memset(&pend, 0, sizeof(pend));   // split-K partials of the previous N = hidden GEMM, consumed by the next LayerNorm
     for (int i = 0; i < 12; ++i) {
       const float* const* bp = P + P_BLK0 + i * B_COUNT;
       const float* xin = i ? w.hs[i - 1] : w.x0;
-      B200_TRY(launch_layernorm_fwd<T>(xin, bp[B_LN1_W], bp[B_LN1_B], w.ln1[i], w.ln1s[i], M, H, st));
+      B200_TRY(launch_layernorm_fwd<T>(xin, bp[B_LN1_W], bp[B_LN1_B], w.ln1[i], w.ln1s[i], M, H, st, pend.nsplit ? &pend : nullptr));
+      pend.nsplit = 0;
       B200_TRY(linear_fwd<T>(w.ln1[i], H, bp[B_QKV_W], w.wqkv[i], M, 3 * H, H, ep_plain<T>(w.qkv[i], 3 * H), st));
       B200_TRY(attention_fwd(i, scale, st));
-      { EpStore<float> ep = ep_plain<float>(w.x1[i], H); ep.bias = bp[B_PROJ_B]; ep.resid = xin; ep.ldr = H;
-        B200_TRY(linear_fwd<float>(w.att[i], H, bp[B_PROJ_W], w.wproj[i], M, H, H, ep, st)); }
-      B200_TRY(launch_layernorm_fwd<T>(w.x1[i], bp[B_LN2_W], bp[B_LN2_B], w.ln2[i], w.ln2s[i], M, H, st));
+      if (can_split(M, H, H)) {
+        B200_TRY(linear_fwd_split(w.att[i], H, w.wproj[i], M, H, H, bp[B_PROJ_B], xin, w.x1[i], &pend, st));
+      } else {
+        EpStore<float> ep = ep_plain<float>(w.x1[i], H); ep.bias = bp[B_PROJ_B]; ep.resid = xin; ep.ldr = H;
+        B200_TRY(linear_fwd<float>(w.att[i], H, bp[B_PROJ_W], w.wproj[i], M, H, H, ep, st));
+      }
+      B200_TRY(launch_layernorm_fwd<T>(w.x1[i], bp[B_LN2_W], bp[B_LN2_B], w.ln2[i], w.ln2s[i], M, H, st, pend.nsplit ? &pend : nullptr));
+      pend.nsplit = 0;
       { EpStore<T> ep = ep_plain<T>(w.h[i], F); ep.bias = bp[B_FC1_B]; ep.act = ACT_GELU; ep.preact = w.u[i];
         B200_TRY(linear_fwd<T>(w.ln2[i], H, bp[B_FC1_W], w.wfc1[i], M, F, H, ep, st)); }
-      { EpStore<float> ep = ep_plain<float>(w.hs[i], H); ep.bias = bp[B_FC2_B]; ep.resid = w.x1[i]; ep.ldr = H;
-        B200_TRY(linear_fwd<float>(w.h[i], F, bp[B_FC2_W], w.wfc2[i], M, H, F, ep, st)); }
+      if (can_split(M, H, F)) {
+        B200_TRY(linear_fwd_split(w.h[i], F, w.wfc2[i], M, H, F, bp[B_FC2_B], w.x1[i], w.hs[i], &pend, st));
+      } else {
+        EpStore<float> ep = ep_plain<float>(w.hs[i], H); ep.bias = bp[B_FC2_B]; ep.resid = w.x1[i]; ep.ldr = H;
+        B200_TRY(linear_fwd<float>(w.h[i], F, bp[B_FC2_W], w.wfc2[i], M, H, F, ep, st));
+      }
     }
-    B200_TRY(launch_layernorm_fwd<T>(w.hs[11], P[P_NORM_W], P[P_NORM_B], w.vit_out, w.lnfs, M, H, st));
+    B200_TRY(launch_layernorm_fwd<T>(w.hs[11], P[P_NORM_W], P[P_NORM_B], w.vit_out, w.lnfs, M, H, st, pend.nsplit ? &pend : nullptr));
     for (int k = 0; k < 3; ++k) B200_TRY(launch_cast<float, T>(w.hs[3 + 3 * k], w.hsT[k], (long)M * H, st));
 
     B200_PROFC_END(st); B200_PROFC_BEGIN("F3 encoders", st);
@@ -709,16 +739,20 @@ struct Exec {
         B200_TRY(linear_dgrad<T>(w.dxb, H, bp[B_FC2_W], w.wfc2[i], M, H, F, ep, st)); }
       if (bg[B_FC1_W]) B200_TRY(linear_wgrad(w.dh, F, w.ln2[i], H, M, F, H, bg[B_FC1_W], st));
       if (bg[B_FC1_B]) B200_TRY(launch_colsum<T>(w.dh, bg[B_FC1_B], M, F, st));
-      B200_TRY(linear_dgrad<T>(w.dh, F, bp[B_FC1_W], w.wfc1[i], M, F, H, ep_plain<T>(w.dln, H), st));
-      B200_TRY(launch_layernorm_bwd<T>(w.dln, w.x1[i], w.ln2s[i], bp[B_LN2_W], w.dx, w.dx2, w.dx2b, bg[B_LN2_W], bg[B_LN2_B], M, H, st));
+      { SplitSum ss; memset(&ss, 0, sizeof(ss));
+        if (can_split(M, H, F)) B200_TRY(linear_dgrad_split(w.dh, F, w.wfc1[i], M, F, H, &ss, st));
+        else B200_TRY(linear_dgrad<T>(w.dh, F, bp[B_FC1_W], w.wfc1[i], M, F, H, ep_plain<T>(w.dln, H), st));
+        B200_TRY(launch_layernorm_bwd<T>(w.dln, w.x1[i], w.ln2s[i], bp[B_LN2_W], w.dx, w.dx2, w.dx2b, bg[B_LN2_W], bg[B_LN2_B], M, H, st, ss.nsplit ? &ss : nullptr)); }
       // x1 = xin + proj(att) + bp
       if (bg[B_PROJ_W]) B200_TRY(linear_wgrad(w.dx2b, H, w.att[i], H, M, H, H, bg[B_PROJ_W], st));
       if (bg[B_PROJ_B]) B200_TRY(launch_colsum<float>(w.dx2, bg[B_PROJ_B], M, H, st));
       B200_TRY(linear_dgrad<T>(w.dx2b, H, bp[B_PROJ_W], w.wproj[i], M, H, H, ep_plain<T>(w.datt, H), st));
       B200_TRY(attention_bwd(i, scale, st));
       if (bg[B_QKV_W]) B200_TRY(linear_wgrad(w.dqkv, 3 * H, w.ln1[i], H, M, 3 * H, H, bg[B_QKV_W], st));
-      B200_TRY(linear_dgrad<T>(w.dqkv, 3 * H, bp[B_QKV_W], w.wqkv[i], M, 3 * H, H, ep_plain<T>(w.dln, H), st));
-      B200_TRY(launch_layernorm_bwd<T>(w.dln, xin, w.ln1s[i], bp[B_LN1_W], w.dx2, w.dx, w.dxb, bg[B_LN1_W], bg[B_LN1_B], M, H, st));
+      { SplitSum ss; memset(&ss, 0, sizeof(ss));
+        if (can_split(M, H, 3 * H)) B200_TRY(linear_dgrad_split(w.dqkv, 3 * H, w.wqkv[i], M, 3 * H, H, &ss, st));
+        else B200_TRY(linear_dgrad<T>(w.dqkv, 3 * H, bp[B_QKV_W], w.wqkv[i], M, 3 * H, H, ep_plain<T>(w.dln, H), st));
+        B200_TRY(launch_layernorm_bwd<T>(w.dln, xin, w.ln1s[i], bp[B_LN1_W], w.dx2, w.dx, w.dxb, bg[B_LN1_W], bg[B_LN1_B], M, H, st, ss.nsplit ? &ss : nullptr)); }
     }
     // --- patch embedding: dW = dx0^T rows(x), db = colsum, dpos = sum over batch
     if (G[P_PATCH_W]) {

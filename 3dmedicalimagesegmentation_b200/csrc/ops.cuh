@@ -37,13 +37,14 @@ static int simt_linear_wgrad(const TG* dY, long ldy, const TX* X, long ldx, int 
 }
 
 // ---- k^3 convolution, stride 1, same padding, bias-free (W fp32 [Co][Ci][k^3]) ----
-template <class T>
+template <class T>   // the output is a RAW conv output: stored as RawOf<T> (fp16 in bf16 mode)
 static int simt_conv_fwd(Cl<const T> x, Sp sp, const float* W, int Co, int ks, Cl<T> out, cudaStream_t st) {
   B200_PROFD(st, "simt conv_fwd k%d %d->%d @%d", ks, x.C, Co, sp.D);
+  typedef typename RawOf<T>::type TR;
   int taps = ks * ks * ks;
   RowIsOuter<ConvGather<T, true>, false> al; al.g = {x.p, sp.D, sp.H, sp.W, x.pitch, x.coff, x.C, ks, 1};
   ConvWeightB bl = {W, x.C, Co, taps, 0};
-  EpStore<T> ep = ep_plain<T>(out.p + out.coff, out.pitch);
+  EpStore<TR> ep = ep_plain<TR>(reinterpret_cast<TR*>(out.p) + out.coff, out.pitch);
   return launch_contract(al, bl, ep, (int)sp.rows(), Co, taps * x.C, 1, 1, st);
 }
 template <class T>

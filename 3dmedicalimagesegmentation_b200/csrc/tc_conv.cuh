@@ -29,7 +29,7 @@ struct ConvParams {
   int a_bytes, b_bytes;       // per k-block, b rounded up to 1024
   int stages; uint32_t tmem_cols;
   // epilogue
-  bf16* out; int pitch, coff, accumulate; double* stats;
+  bf16* out; int pitch, coff, accumulate; double* stats; int out_half;
   long long* dbg;   // optional CTA-0 clock64 stamps (tuning aid)
   long long* trace;
   int resident;     // all packed weights (kblocks x b_bytes) stay in smem for the CTA's lifetime; stages hold A bricks only
@@ -269,10 +269,17 @@ conv_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ C
 #pragma unroll
             for (int j = 0; j < 8; ++j) { v[j] += a.v[j]; v[8 + j] += b.v[j]; }
           }
-          Vec16<bf16> o0, o1;
+          if (p.out_half) {
+            Vec16<__half> o0, o1;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) { o0.v[j] = v[j]; o1.v[j] = v[8 + j]; }
-          o0.store(dst + c0); o1.store(dst + c0 + 8);
+            for (int j = 0; j < 8; ++j) { o0.v[j] = v[j]; o1.v[j] = v[8 + j]; }
+            o0.store(reinterpret_cast<__half*>(dst) + c0); o1.store(reinterpret_cast<__half*>(dst) + c0 + 8);
+          } else {
+            Vec16<bf16> o0, o1;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { o0.v[j] = v[j]; o1.v[j] = v[8 + j]; }
+            o0.store(dst + c0); o1.store(dst + c0 + 8);
+          }
         }
       }
       tc_fence_before();
@@ -308,7 +315,7 @@ static inline bool conv_supported(int Ci, int Co, int in_pitch, int in_coff, int
 
 // x: channels-last window (p + coff, pitch) with Ci channels; wp: packed bf16 [taps][Co][Ci]
 static int conv(const bf16* x, int in_pitch, int in_coff, int Ci, int N, int D, int H, int W, const bf16* wp, int Co, int ks,
-                bf16* out, int out_pitch, int out_coff, int accumulate, double* stats, cudaStream_t st) {
+                bf16* out, int out_pitch, int out_coff, int accumulate, double* stats, cudaStream_t st, int out_half = 0) {
   EncodeTiledFn enc = get_encode();
   B200_CHECK(enc, "cuTensorMapEncodeTiled not available from the driver");
   ConvParams p;
@@ -333,7 +340,7 @@ static int conv(const bf16* x, int in_pitch, int in_coff, int Ci, int N, int D, 
   uint32_t cols = 2 * Co, pw = 32; while (pw < cols) pw <<= 1; p.tmem_cols = pw;
   p.dbg = g_dbg;
   p.trace = trace_slot(); if (p.trace) trace_tag("conv k%d %d->%d @%d", ks, Ci, Co, D);
-  p.out = out; p.pitch = out_pitch; p.coff = out_coff; p.accumulate = accumulate; p.stats = stats;
+  p.out = out; p.pitch = out_pitch; p.coff = out_coff; p.accumulate = accumulate; p.stats = stats; p.out_half = out_half;
 
   CUtensorMapSwizzle sw = p.row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (p.row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
   CUtensorMap mx, mw;

@@ -36,6 +36,7 @@ struct HaloParams {
   // fused 1x1x1 convolution of the residual block (weight tile index 27*nchunk + chunk, resident weights only):
   //  mode2 == 1: second OUTPUT  out2 = conv1x1(x; W3)      (forward: conv1 and conv3 read the same x)
   //  mode2 == 2: second INPUT   out += conv1x1(x2; W3^T)   (dgrad: dx = dgrad3x3(dc1) + dgrad1x1(dc3))
+  int out_half;   // raw conv outputs (forward, feeding an InstanceNorm) are stored as fp16 (RawOf<bf16>)
   int mode2; bf16* out2; int pitch2, coff2; double* stats2; int x2_off;
   long long* trace;
   int dbg_mode; long long* dbg;  // tuning aids: bit0 skip TMA, bit1 skip MMA, bit2 skip epilogue stores; CTA-0 clock stamps
@@ -264,10 +265,17 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
 #pragma unroll
                 for (int j = 0; j < 8; ++j) { v[j] += a.v[j]; v[8 + j] += b.v[j]; }
               }
-              Vec16<bf16> o0, o1;
+              if (p.out_half) {
+                Vec16<__half> o0, o1;
 #pragma unroll
-              for (int j = 0; j < 8; ++j) { o0.v[j] = v[j]; o1.v[j] = v[8 + j]; }
-              o0.store(dst + c0); o1.store(dst + c0 + 8);
+                for (int j = 0; j < 8; ++j) { o0.v[j] = v[j]; o1.v[j] = v[8 + j]; }
+                o0.store(reinterpret_cast<__half*>(dst) + c0); o1.store(reinterpret_cast<__half*>(dst) + c0 + 8);
+              } else {
+                Vec16<bf16> o0, o1;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { o0.v[j] = v[j]; o1.v[j] = v[8 + j]; }
+                o0.store(dst + c0); o1.store(dst + c0 + 8);
+              }
             }
           }
         } else {
@@ -289,10 +297,17 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
 #pragma unroll
                 for (int j = 0; j < 8; ++j) { v[j] += a.v[j]; v[8 + j] += b.v[j]; }
               }
-              Vec16<bf16> o0, o1;
+              if (p.out_half) {
+                Vec16<__half> o0, o1;
 #pragma unroll
-              for (int j = 0; j < 8; ++j) { o0.v[j] = v[j]; o1.v[j] = v[8 + j]; }
-              o0.store(dst + c0); o1.store(dst + c0 + 8);
+                for (int j = 0; j < 8; ++j) { o0.v[j] = v[j]; o1.v[j] = v[8 + j]; }
+                o0.store(reinterpret_cast<__half*>(dst) + c0); o1.store(reinterpret_cast<__half*>(dst) + c0 + 8);
+              } else {
+                Vec16<bf16> o0, o1;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { o0.v[j] = v[j]; o1.v[j] = v[8 + j]; }
+                o0.store(dst + c0); o1.store(dst + c0 + 8);
+              }
             }
           }
           if (sp) {
@@ -378,7 +393,8 @@ struct HaloFused {   // optional fused 1x1x1 conv (see HaloParams::mode2); wp2: 
   const bf16* x2; int x2_pitch, x2_coff;                   // mode2 == 2 (same channel count Ci as x)
 };
 static int conv_halo(const bf16* x, int in_pitch, int in_coff, int Ci, int N, int D, int H, int W, const bf16* wp, int Co,
-                     bf16* out, int out_pitch, int out_coff, int accumulate, double* stats, cudaStream_t st, const HaloFused* fu = nullptr) {
+                     bf16* out, int out_pitch, int out_coff, int accumulate, double* stats, cudaStream_t st, const HaloFused* fu = nullptr,
+                     int out_half = 0) {
   EncodeTiledFn enc = get_encode();
   B200_CHECK(enc, "cuTensorMapEncodeTiled not available from the driver");
   const int mode2 = fu ? fu->mode2 : 0;
@@ -398,6 +414,7 @@ static int conv_halo(const bf16* x, int in_pitch, int in_coff, int Ci, int N, in
   uint32_t cols = (mode2 == 1 ? 4 : 2) * Co, pw = 32; while (pw < cols) pw <<= 1; p.tmem_cols = pw;
   B200_CHECK(p.tmem_cols <= 512, "halo conv TMEM budget exceeded");
   p.out = out; p.pitch = out_pitch; p.coff = out_coff; p.accumulate = accumulate; p.stats = stats;
+  p.out_half = out_half;
   p.mode2 = mode2; p.out2 = nullptr; p.pitch2 = p.coff2 = 0; p.stats2 = nullptr; p.x2_off = h.halo_bytes;
   if (mode2 == 1) { p.out2 = fu->out2; p.pitch2 = fu->pitch2; p.coff2 = fu->coff2; p.stats2 = fu->stats2; }
   p.dbg = g_dbg; p.dbg_mode = 0;

@@ -324,13 +324,13 @@ static inline int num_sms() {
 
 // split-K factor worth using for a fp32-atomic epilogue: few output tiles, long K
 static inline int plan_splitk(int M, int N, int K, int nb) {
-  // measured: 16 scattered fp32 atomics per row segment make the epilogue slower than the K loop it saves (proj 10.6 -> 17.6 us);
-  // off unless asked for, until the partial sums are reduced by the consumer kernel instead
-  static const bool on = getenv("B200_SPLITK") != nullptr;
-  if (!on) return 1;
+  // (fp32 atomics in the epilogue were measured slower than the K loop they save: proj 10.6 -> 17.6 us; the partial tiles are
+  // stored plainly and summed by the consumer kernel -- see SplitSum in elementwise.cuh)
+  static const bool off = getenv("B200_NO_SPLITK") != nullptr;
+  if (off) return 1;
   const long tiles = (long)cdiv(M, BM) * cdiv(N, 64) * nb; const int kbs = cdiv(K, BK);
   if (tiles * 2 > num_sms() || kbs < 8) return 1;
-  long s = num_sms() / tiles; if (s > kbs / 4) s = kbs / 4;
+  long s = num_sms() / tiles; if (s > kbs / 4) s = kbs / 4; if (s > 4) s = 4;
   return s < 2 ? 1 : (int)s;
 }
 

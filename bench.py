@@ -184,20 +184,49 @@ def main():
     lib.b200_prof_enable(0)
     pk, pk_kind = peaks()
     import re
-    conv_ms, conv_flop, conv_n = 0.0, 0.0, 0
-    for k, v in prof.items():      # tags: "conv_fwd k3 16->16 @96" / "conv_dgrad k3 16->32 @96"  (tc::conv_kernel launches)
-        m = re.match(r"conv_(fwd|dgrad) k(\d) (\d+)->(\d+) @(\d+)", k)
+    # kernel classes of the tcgen05 engine, algorithmic FLOPs from the op tags (2*M*N*K; 2*B*S^3*Cin*Cout*taps)
+    classes = {"tc::gemm_kernel (ViT linear layers: fwd, dgrad, wgrad)": [0.0, 0.0, 0],
+               "tc::conv_halo_kernel (conv3d 3^3 [+fused 1^3] implicit GEMM: fwd, dgrad)": [0.0, 0.0, 0],
+               "tc::wgrad_halo_kernel / tc::wgrad_kernel (conv3d weight gradients)": [0.0, 0.0, 0]}
+    names = list(classes)
+    for k, v in prof.items():
+        m = re.match(r"linear_(fwd|dgrad|wgrad) (\d+)x(\d+)x(\d+)", k)
         if m:
-            ks, ci, co, d = int(m.group(2)), int(m.group(3)), int(m.group(4)), int(m.group(5))
-            conv_ms += v[0]; conv_n += v[1]
-            conv_flop += v[1] * 2.0 * B * d ** 3 * ci * co * ks ** 3
+            c = classes[names[0]]; c[0] += v[0]; c[1] += v[1] * 2.0 * int(m.group(2)) * int(m.group(3)) * int(m.group(4)); c[2] += v[1]
+            continue
+        m = re.match(r"conv_(fwd|dgrad) k3(\+k1)? (\d+)->(\d+) @(\d+)", k)
+        if m:
+            taps = 28 if m.group(2) else 27
+            c = classes[names[1]]; c[0] += v[0]; c[2] += v[1]
+            c[1] += v[1] * 2.0 * B * int(m.group(5)) ** 3 * int(m.group(3)) * int(m.group(4)) * taps
+            continue
+        m = re.match(r"conv_wgrad k(\d) (\d+)x(\d+) @(\d+)", k)
+        if m:
+            c = classes[names[2]]; c[0] += v[0]; c[2] += v[1]
+            c[1] += v[1] * 2.0 * B * int(m.group(4)) ** 3 * int(m.group(2)) * int(m.group(3)) * int(m.group(1)) ** 3
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+    except Exception:
+        traffic = {}
+    def roof_of(name):
+        ms_, fl, n = classes[name]
+        r = {"bound": "tensor", "kernel": name, "launches": n, "avg_launch_us": 1e3 * ms_ / n if n else None,
+             "achieved": fl / (ms_ * 1e-3) / 1e12 if ms_ else None, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
+             "peak_kind": pk_kind + " sustained cuBLAS bf16 (kernel timed inside a long step)",
+             "algorithmic": "sum over launches of 2*M*N*K (linear) / 2*B*S^3*Cin*Cout*taps (conv)", "share_of_step_ms": ms_,
+             "timing": "CUDA events around every launch of one step on the launching stream (b200_prof_*)"}
+        r["frac"] = r["achieved"] / r["peak"] if r["achieved"] else None
+        t = traffic.get(name.split(" ")[0])
+        r["traffic"] = t["dram_bytes_per_launch"] if t else None
+        if t:
+            r["traffic_of"] = t["launch"]
+            r["tensor_pipe_busy"] = t.get("tensor_pipe_busy")
+        return r
+    top_class = max(names, key=lambda nme: classes[nme][0])
+    roof = roof_of(top_class)
+    roof["other_kernels"] = [roof_of(nme) for nme in names if nme != top_class]
     top = max(prof.items(), key=lambda kv: kv[1][0]) if prof else ("none", (0.0, 0))
-    roof = {"bound": "tensor", "kernel": "tc::conv_kernel (tcgen05 implicit-GEMM conv3d, forward + dgrad launches of one step)",
-            "launches": conv_n, "avg_launch_us": 1e3 * conv_ms / conv_n if conv_n else None,
-            "achieved": conv_flop / (conv_ms * 1e-3) / 1e12 if conv_ms else None, "peak": pk["bf16_tflops_sustained"],
-            "unit": "TFLOP/s", "peak_kind": pk_kind + " sustained cuBLAS bf16 (kernel timed inside a long step)", "traffic": None,
-            "algorithmic": "sum over launches of 2*B*D^3*Cin*Cout*k^3", "top_op": top[0], "top_op_ms": top[1][0]}
-    roof["frac"] = roof["achieved"] / roof["peak"] if roof["achieved"] else None
+    roof["top_op"] = top[0]; roof["top_op_ms"] = top[1][0]
     if args.breakdown and rank == 0:
         lib.b200_prof_enable(2)            # phase-level regions only (per-op events have a ~8 us floor each)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
