@@ -62,6 +62,7 @@ SIGNATURES = {
     "b200_test_tc_wgrad": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                    c_void_p, c_void_p]),
     "b200_test_set_debug_buffer": (None, [c_void_p]),
+    "b200_unetr_set_grad_events": (None, [c_void_p, ctypes.POINTER(c_void_p), c_int]),
     "b200_trace_begin": (None, [c_void_p, c_int]),
     "b200_trace_count": (c_int, []),
     "b200_trace_tags": (c_int, [ctypes.c_char_p, c_int]),

@@ -108,6 +108,13 @@ int b200_unetr_backward(void* handle, const float* const* params, float* const* 
   return h->ex->backward(params, grads, x, (char*)workspace, d_enc4, d_logits, flags, (cudaStream_t)stream);
 }
 
+void b200_unetr_set_grad_events(void* handle, void* const* events, int n) {
+  Handle* h = (Handle*)handle;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  for (int i = 0; i < n && i < 4; ++i) ev[i] = (cudaEvent_t)events[i];
+  h->ex->set_grad_events(ev, n);
+}
+
 // ---------------------------------------------------------------- DiceCE
 // scratch: double acc[B*C*3+1] | float coef[B*C*2]
 size_t b200_dicece_scratch_bytes(int B, int C) { return sizeof(double) * ((size_t)B * C * 3 + 2) + sizeof(float) * (size_t)B * C * 2; }

@@ -570,6 +570,8 @@ struct Exec {
     return simt_convT_fwd<T, T>(x, ldx, Ci, sp(in_level), W, out, st);
   }
   const float* const* cur_params = nullptr;
+  cudaEvent_t grad_ev[4]; int n_grad_ev = 0;   // see ExecIface::set_grad_events
+  void mark_grads(int k, cudaStream_t st) { if (n_grad_ev == 4) cudaEventRecord(grad_ev[k], st); }
 
   // softmax(Q K^T * scale) V per (batch, head); scores fp32, probabilities T (kept for backward)
   int attention_fwd(int i, float scale, cudaStream_t st) {
@@ -714,6 +716,7 @@ struct Exec {
       return 0;
 
     // --- ViT backward
+    mark_grads(0, st);
     B200_PROFC_END(st); B200_PROFC_BEGIN("B2 vit+patch", st);
     float scale = 1.0f / sqrtf((float)dh);
     int top = 11;
@@ -753,6 +756,8 @@ struct Exec {
         if (can_split(M, H, 3 * H)) B200_TRY(linear_dgrad_split(w.dqkv, 3 * H, w.wqkv[i], M, 3 * H, H, &ss, st));
         else B200_TRY(linear_dgrad<T>(w.dqkv, 3 * H, bp[B_QKV_W], w.wqkv[i], M, 3 * H, H, ep_plain<T>(w.dln, H), st));
         B200_TRY(launch_layernorm_bwd<T>(w.dln, xin, w.ln1s[i], bp[B_LN1_W], w.dx2, w.dx, w.dxb, bg[B_LN1_W], bg[B_LN1_B], M, H, st, ss.nsplit ? &ss : nullptr)); }
+      if (i == 8) mark_grads(1, st);
+      if (i == 4) mark_grads(2, st);
     }
     // --- patch embedding: dW = dx0^T rows(x), db = colsum, dpos = sum over batch
     if (G[P_PATCH_W]) {
@@ -767,6 +772,7 @@ struct Exec {
     }
     if (G[P_PATCH_B]) B200_TRY(launch_colsum<float>(w.dx, G[P_PATCH_B], M, H, st));
     if (G[P_POS]) { batchsum_kernel<<<cdiv((long)L * H, 256), 256, 0, st>>>(w.dx, G[P_POS], B, (long)L * H); B200_LAUNCH_CHECK(); }
+    mark_grads(3, st);
     B200_PROFC_END(st);
     return 0;
   }

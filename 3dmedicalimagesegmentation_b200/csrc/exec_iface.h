@@ -16,6 +16,9 @@ struct ExecIface {
   virtual int backward(const float* const* P, float* const* G, const float* x, char* ws, const float* d_enc4, const float* d_logits, int flags,
                        cudaStream_t st) = 0;
   virtual const void* peek(const char* name, size_t* bytes) = 0;
+  // optional: events recorded inside backward() when a group of parameter gradients is final (gradient all-reduce overlap):
+  //   [0] convolutional encoders/decoders + head, [1] vit.norm + blocks 8..11, [2] blocks 4..7, [3] blocks 0..3 + patch embedding
+  virtual void set_grad_events(cudaEvent_t* ev, int n) = 0;
 };
 ExecIface* make_exec_f32(const UnetrConfig& c);
 ExecIface* make_exec_bf16(const UnetrConfig& c);

@@ -16,5 +16,6 @@ struct ExecImpl : ExecIface {
     return e.backward(P, G, x, ws, d_enc4, d_logits, flags, st);
   }
   const void* peek(const char* name, size_t* bytes) override { return e.peek(name, bytes); }
+  void set_grad_events(cudaEvent_t* ev, int n) override { e.n_grad_ev = n < 4 ? 0 : 4; for (int i = 0; i < e.n_grad_ev; ++i) e.grad_ev[i] = ev[i]; }
 };
 }  // namespace b200

@@ -60,10 +60,25 @@ class GradientAllReduce:
     buffer is found the whole reduction is a single all-reduce (369.8 MB at 96^3); otherwise gradients are packed
     into `bucket_mb` buckets.  Parameters whose grad is None on every rank are skipped (ranking stages)."""
 
-    def __init__(self, module: torch.nn.Module, world_size: int, bucket_mb: int = 512, group=None):
+    def __init__(self, module: torch.nn.Module, world_size: int, bucket_mb: int = 512, group=None, overlap: bool = True):
         self.params: List[torch.nn.Parameter] = [p for p in module.parameters() if p.requires_grad]
         self.world, self.group = world_size, group
         self.bucket_elems = bucket_mb * 1024 * 1024 // 4
+        self.module = module
+        self.side = None
+        # overlap: the UNETR backward records an event when each of 4 gradient groups is final; their all-reduces run on a side
+        # stream behind those events while the rest of the backward is still executing (the host enqueues far ahead of the GPU)
+        if overlap and world_size > 1 and hasattr(module, "overlap_grad_reduce") and torch.cuda.is_available():
+            module.overlap_grad_reduce = True
+            self.side = torch.cuda.Stream()
+
+    def _avg(self, t):
+        if dist.get_backend(self.group) == "nccl":
+            return dist.all_reduce(t, op=dist.ReduceOp.AVG, group=self.group, async_op=True)
+        w = dist.all_reduce(t, group=self.group, async_op=True)
+        w.wait()
+        t.div_(self.world)
+        return None
 
     def _flat_view(self, grads):
         """All grads contiguous slices of one storage, in order -> return the covering flat tensor."""
@@ -82,11 +97,26 @@ class GradientAllReduce:
     def reduce(self):
         if self.world == 1:
             return
+        ready = getattr(self.module, "_grad_ready", None)
+        if ready is not None and self.side is not None:
+            flat, groups = ready
+            self.module._grad_ready = None
+            works = []
+            with torch.cuda.stream(self.side):
+                for ev, lo, hi in groups:
+                    if hi > lo:
+                        self.side.wait_event(ev)
+                        works.append(self._avg(flat[lo:hi]))
+            for w in works:
+                if w is not None:
+                    w.wait()              # the current stream waits for the reduction
+            return
         grads = [p.grad for p in self.params if p.grad is not None]
         flat = self._flat_view(grads)
         if flat is not None:
-            dist.all_reduce(flat, group=self.group)
-            flat.div_(self.world)
+            w = self._avg(flat)
+            if w is not None:
+                w.wait()
             return
         bucket, size = [], 0
         for g in grads + [None]:

@@ -161,6 +161,25 @@ class _UnetrFunction(torch.autograd.Function):
             d_logits = d_logits.contiguous().float()
         if has_de:
             d_enc4 = d_enc4.contiguous().float()
+        # gradient-ready events (data-parallel overlap, parallel.GradientAllReduce): only the full training backward records all
+        # four groups; they cover contiguous ranges of `flat` because it is laid out in parameter order
+        full = has_dl and enc and all(wanted) and x.is_cuda
+        module._grad_ready = None
+        if full and module.overlap_grad_reduce:
+            evs = module._grad_events
+            if evs is None:
+                evs = [torch.cuda.Event() for _ in range(4)]
+                for e in evs:
+                    e.record()               # forces creation of the underlying cudaEvent_t
+                module._grad_events = evs
+            arr = (ctypes.c_void_p * 4)(*[e.cuda_event for e in evs])
+            lib.b200_unetr_set_grad_events(ctx.handle, arr, 4)
+            nb = _lib.PARAM_COUNT
+            first = lambda i: sum(p.numel() for p in params[:i])
+            b4, b8, conv0 = first(3 + 4 * 11), first(3 + 8 * 11), first(3 + 12 * 11 + 2)
+            module._grad_ready = (flat, [(evs[0], conv0, total), (evs[1], b8, conv0), (evs[2], b4, b8), (evs[3], 0, b4)])
+        else:
+            lib.b200_unetr_set_grad_events(ctx.handle, None, 0)
         _lib.check(lib.b200_unetr_backward(ctx.handle, module._param_table(params), gtab, _lib.ptr(x), _lib.ptr(ws),
                                            _lib.ptr(d_enc4), _lib.ptr(d_logits), flags, _lib.stream_ptr()),
                    "b200_unetr_backward")
@@ -230,6 +249,9 @@ class UNETR(nn.Module):
         self.compute_mode = os.environ.get("B200_UNETR_MODE", "bf16")
         self._handles = {}
         self._infer_ws = {}
+        self._grad_events = None
+        self._grad_ready = None
+        self.overlap_grad_reduce = False   # set by parallel.GradientAllReduce
         self._ordered = None
 
     # ---- plumbing -------------------------------------------------------------------------------

@@ -116,12 +116,25 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
     args.warmup = max(args.warmup, 3)
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO") and not os.environ.get("B200_KEEP_NCCL_DEBUG"):
+        os.environ["NCCL_DEBUG"] = "WARN"     # the NCCL banner goes to stdout; the driver expects ONE JSON line there
 
     pkg = importlib.import_module("3dmedicalimagesegmentation_b200")
     par = importlib.import_module("3dmedicalimagesegmentation_b200.parallel")
-    rank, world, local = par.init_from_env()
-    dev = torch.device("cuda", local)
-    torch.cuda.set_device(dev)
+    # communicator creation prints an "NCCL version" banner on stdout; the driver expects ONE JSON line there
+    sys.stdout.flush()
+    saved_out = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        rank, world, local = par.init_from_env()
+        dev = torch.device("cuda", local)
+        torch.cuda.set_device(dev)
+        par.barrier(world)
+        torch.cuda.synchronize()
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved_out, 1)
+        os.close(saved_out)
     lib = pkg._lib.load()
 
     torch.manual_seed(0)

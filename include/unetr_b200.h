@@ -92,6 +92,12 @@ unsigned long long b200_launch_count(void);
 void b200_prof_enable(int on);
 int b200_prof_report(char* buf, int cap);
 
+/* Optional gradient-ready events for data-parallel overlap: 4 cudaEvent_t handles recorded inside b200_unetr_backward when a
+ * group of parameter gradients is final -- [0] conv encoders/decoders + head, [1] vit.norm + blocks 8..11, [2] blocks 4..7,
+ * [3] blocks 0..3 + patch embedding.  n = 0 switches the recording off.  Only a full backward (logits gradient + trainable
+ * encoder) records all four. */
+void b200_unetr_set_grad_events(void* handle, void* const* events, int n);
+
 /* ---- op-level test hooks (parity tests of single kernels; not part of the reference surface) ---- */
 /* D[M,N] = A[M,K] * B[N,K]^T with bf16 operands on the tcgen05 engine; a_mn/b_mn select MN-major operands
  * (A stored [K,M] / B stored [K,N]).  out fp32. */
