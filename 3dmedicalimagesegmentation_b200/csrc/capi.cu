@@ -125,7 +125,8 @@ int b200_dicece_forward(const float* logits, const float* labels, int B, int C, 
   float* coef = (float*)(acc + (size_t)B * C * 3 + 2);
   B200_CUDA(cudaMemsetAsync(acc, 0, sizeof(double) * ((size_t)B * C * 3 + 2), st));
   dim3 g((unsigned)max(1L, min(148L * 8 / B + 1, (long)((V + 255) / 256))), B);
-  const bool v4 = V % 4 == 0 && C <= 16 && (((uintptr_t)logits | (uintptr_t)labels) & 15) == 0;
+  // measured: the 4-voxel kernels need 184-254 registers and are ~15 % slower than the scalar ones at 14 classes; opt-in only
+  const bool v4 = getenv("B200_DICE_V4") && V % 4 == 0 && C <= 16 && (((uintptr_t)logits | (uintptr_t)labels) & 15) == 0;
   dim3 g4((unsigned)max(1L, min(148L * 4 / B + 1, (long)((V / 4 + 255) / 256))), B);
   if (v4) dicece_fwd4_kernel<16><<<g4, 256, 0, st>>>(logits, labels, C, V, acc, B * C);
   else if (C <= 16) dicece_fwd_kernel<16><<<g, 256, 0, st>>>(logits, labels, C, V, acc, B * C);
@@ -141,7 +142,7 @@ int b200_dicece_backward(const float* logits, const float* labels, int B, int C,
   B200_CHECK(C >= 1 && C <= 32, "DiceCE supports 1..32 classes (got %d)", C);
   const float* coef = (const float*)((const double*)scratch + (size_t)B * C * 3 + 2);
   dim3 g((unsigned)max(1L, min(148L * 8 / B + 1, (long)((V + 255) / 256))), B);
-  const bool v4 = V % 4 == 0 && C <= 16 && (((uintptr_t)logits | (uintptr_t)labels | (uintptr_t)dlogits) & 15) == 0;
+  const bool v4 = getenv("B200_DICE_V4") && V % 4 == 0 && C <= 16 && (((uintptr_t)logits | (uintptr_t)labels | (uintptr_t)dlogits) & 15) == 0;
   dim3 g4((unsigned)max(1L, min(148L * 4 / B + 1, (long)((V / 4 + 255) / 256))), B);
   if (v4) dicece_bwd4_kernel<16><<<g4, 256, 0, st>>>(logits, labels, coef, upstream, B, C, V, dlogits);
   else if (C <= 16) dicece_bwd_kernel<16><<<g, 256, 0, st>>>(logits, labels, coef, upstream, B, C, V, dlogits);

@@ -160,15 +160,15 @@ __global__ void layernorm_fwd_reg_kernel(const float* __restrict__ x, const floa
 #pragma unroll
     for (int i = 0; i < NV4; ++i) {
       const long o = (long)row * H + (i * 32 + lane) * 4;
-      float b4[4], p4[4];
+      float b4[4], p4[4][4];   // <= 4 splits; fixed trip count + predication keeps all loads of the row independent (issued up front)
       load4(ss.resid + o, v[i]); load4(ss.bias + (i * 32 + lane) * 4, b4);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) v[i][j] += b4[j];
-      for (int sp = 0; sp < ss.nsplit; ++sp) {
-        load4(ss.part + sp * ss.stride + o, p4);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) v[i][j] += p4[j];
+      for (int sp = 0; sp < 4; ++sp) {
+        if (sp < ss.nsplit) load4(ss.part + sp * ss.stride + o, p4[sp]);
+        else { p4[sp][0] = p4[sp][1] = p4[sp][2] = p4[sp][3] = 0.f; }
       }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[i][j] += b4[j] + ((p4[0][j] + p4[1][j]) + (p4[2][j] + p4[3][j]));
       store4(ss.xsum + o, v[i]);
     }
   } else {
@@ -211,13 +211,15 @@ __global__ void layernorm_bwd_dx_reg_kernel(const TG* __restrict__ g, const floa
     const long o = (long)row * H + (i * 32 + lane) * 4;
     float gm[4];
     if (ss.nsplit) {
-      float p4[4];
+      float p4[3][4];
       load4(ss.part + o, gg[i]);
-      for (int sp = 1; sp < ss.nsplit; ++sp) {
-        load4(ss.part + sp * ss.stride + o, p4);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) gg[i][j] += p4[j];
+      for (int sp = 1; sp < 4; ++sp) {
+        if (sp < ss.nsplit) load4(ss.part + sp * ss.stride + o, p4[sp - 1]);
+        else { p4[sp - 1][0] = p4[sp - 1][1] = p4[sp - 1][2] = p4[sp - 1][3] = 0.f; }
       }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) gg[i][j] += p4[0][j] + (p4[1][j] + p4[2][j]);
       store4(ss_gout + o, gg[i]);
     } else {
       load4(g + o, gg[i]);
