@@ -6,6 +6,8 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
+#include <utility>
 
 namespace b200 {
 
@@ -75,6 +77,22 @@ __device__ __forceinline__ void trace_start(long long* slot) {
 }
 __device__ __forceinline__ void trace_end(long long* slot) {
   if (slot && threadIdx.x == 0) { long long g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g)); atomicMax(slot + 1, g); }
+}
+
+// ---- programmatic dependent launch (PDL): a kernel launched through launch_pdl may start while its predecessor in the stream is
+// still draining; EVERY such kernel calls pdl_wait() before its first global-memory access (reads AND writes: the predecessor may
+// still be reading a buffer this kernel overwrites).  What precedes pdl_wait() -- barrier init, TMEM allocation, descriptor
+// prefetch, or just the launch latency of a small kernel -- overlaps the predecessor's tail.  B200_NO_PDL=1 turns the attribute off.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+template <class... KArgs, class... Args>
+static cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
+  static const bool off = getenv("B200_NO_PDL") != nullptr;
+  cfg.attrs = at; cfg.numAttrs = off ? 0 : 1;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
 }
 
 // ---- scalar conversions ----

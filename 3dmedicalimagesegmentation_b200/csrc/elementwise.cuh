@@ -59,6 +59,7 @@ static int launch_layout(const float* in, float* out, T* cl, int N, int C, long 
 
 template <class TI, class TO>
 __global__ void cast_kernel(const TI* __restrict__ in, TO* __restrict__ out, long n) {
+  pdl_wait();
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   long stride = (long)gridDim.x * blockDim.x;
   for (; i < n; i += stride) out[i] = from_f<TO>(to_f(in[i]));
@@ -67,7 +68,7 @@ template <class TI, class TO>
 static int launch_cast(const TI* in, TO* out, long n, cudaStream_t st) {
   B200_PROF("cast", st);
   int blocks = (int)min((long)148 * 8, (n + 255) / 256);
-  cast_kernel<TI, TO><<<blocks, 256, 0, st>>>(in, out, n);
+  B200_CUDA(launch_pdl(cast_kernel<TI, TO>, dim3(blocks), dim3(256), 0, st, in, out, n));
   B200_LAUNCH_CHECK();
   return 0;
 }
@@ -115,6 +116,7 @@ static __global__ void multi_pack_kernel(const PackJobs jobs) {
 }
 
 static __global__ void add_kernel(float* __restrict__ dst, const float* __restrict__ src, long n) {
+  pdl_wait();
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   long stride = (long)gridDim.x * blockDim.x;
   for (; i < n; i += stride) dst[i] += src[i];
@@ -122,7 +124,7 @@ static __global__ void add_kernel(float* __restrict__ dst, const float* __restri
 static int launch_add(float* dst, const float* src, long n, cudaStream_t st) {
   B200_PROF("add", st);
   int blocks = (int)min((long)148 * 8, (n + 255) / 256);
-  add_kernel<<<blocks, 256, 0, st>>>(dst, src, n);
+  B200_CUDA(launch_pdl(add_kernel, dim3(blocks), dim3(256), 0, st, dst, src, n));
   B200_LAUNCH_CHECK();
   return 0;
 }
@@ -151,6 +153,7 @@ struct SplitSum { const float* part; int nsplit; long stride; const float* bias;
 template <class TO, int NV4>
 __global__ void layernorm_fwd_reg_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                                          TO* __restrict__ y, float* __restrict__ stats, int M, const SplitSum ss) {
+  pdl_wait();
   constexpr int H = NV4 * 128;
   int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= M) return;
@@ -201,6 +204,7 @@ template <class TG, int NV4>
 __global__ void layernorm_bwd_dx_reg_kernel(const TG* __restrict__ g, const float* __restrict__ x, const float* __restrict__ stats,
                                             const float* __restrict__ gamma, const float* dx_res, float* dx_out, TG* dx_out_cast, int M,
                                             const SplitSum ss, TG* ss_gout) {
+  pdl_wait();
   constexpr int H = NV4 * 128;
   int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= M) return;
@@ -269,7 +273,7 @@ static int launch_layernorm_fwd(const float* x, const float* g, const float* b, 
   B200_PROF("layernorm_fwd", st);
   SplitSum none; memset(&none, 0, sizeof(none));
   B200_CHECK(!ss || H == 768, "fused split-K LayerNorm needs hidden size 768");
-  if (H == 768) layernorm_fwd_reg_kernel<TO, 6><<<cdiv(M, 4), 128, 0, st>>>(x, g, b, y, stats, M, ss ? *ss : none);
+  if (H == 768) B200_CUDA(launch_pdl(layernorm_fwd_reg_kernel<TO, 6>, dim3(cdiv(M, 4)), dim3(128), 0, st, x, g, b, y, stats, M, ss ? *ss : none));
   else layernorm_fwd_kernel<TO><<<cdiv(M, 8), 256, 0, st>>>(x, g, b, y, stats, M, H);
   B200_LAUNCH_CHECK();
   return 0;
@@ -305,6 +309,7 @@ template <class TG>
 __global__ void layernorm_bwd_params_kernel(const TG* __restrict__ g, const float* __restrict__ x,
                                             const float* __restrict__ stats, float* __restrict__ dgamma,
                                             float* __restrict__ dbeta, int M, int H) {
+  pdl_wait();
   __shared__ float sg[32][33], sb[32][33];
   int col = blockIdx.x * 32 + threadIdx.x;
   float a = 0.f, b = 0.f;
@@ -331,11 +336,11 @@ static int launch_layernorm_bwd(const TG* g, const float* x, const float* stats,
   B200_PROF("layernorm_bwd", st);
   SplitSum none; memset(&none, 0, sizeof(none));
   B200_CHECK(!ss || H == 768, "fused split-K LayerNorm needs hidden size 768");
-  if (H == 768) layernorm_bwd_dx_reg_kernel<TG, 6><<<cdiv(M, 4), 128, 0, st>>>(g, x, stats, gamma, dx_res, dx_out, dx_out_cast, M, ss ? *ss : none, const_cast<TG*>(g));
+  if (H == 768) B200_CUDA(launch_pdl(layernorm_bwd_dx_reg_kernel<TG, 6>, dim3(cdiv(M, 4)), dim3(128), 0, st, g, x, stats, gamma, dx_res, dx_out, dx_out_cast, M, ss ? *ss : none, const_cast<TG*>(g)));
   else layernorm_bwd_dx_kernel<TG><<<cdiv(M, 8), 256, 0, st>>>(g, x, stats, gamma, dx_res, dx_out, dx_out_cast, M, H);
   B200_LAUNCH_CHECK();
   if (dgamma) {
-    layernorm_bwd_params_kernel<TG><<<cdiv(H, 32), dim3(32, 32), 0, st>>>(g, x, stats, dgamma, dbeta, M, H);
+    B200_CUDA(launch_pdl(layernorm_bwd_params_kernel<TG>, dim3(cdiv(H, 32)), dim3(dim3(32, 32)), 0, st, g, x, stats, dgamma, dbeta, M, H));
     B200_LAUNCH_CHECK();
   }
   return 0;
@@ -344,6 +349,7 @@ static int launch_layernorm_bwd(const TG* g, const float* x, const float* stats,
 // ------------------------------------------------------------------ column sums (bias gradients)
 template <class TG>
 __global__ void colsum_kernel(const TG* __restrict__ g, float* __restrict__ out, int M, int N) {
+  pdl_wait();
   __shared__ float s[32][33];
   int col = blockIdx.x * 32 + threadIdx.x;
   float a = 0.f;
@@ -362,7 +368,7 @@ __global__ void colsum_kernel(const TG* __restrict__ g, float* __restrict__ out,
 template <class TG>
 static int launch_colsum(const TG* g, float* out, int M, int N, cudaStream_t st) {
   B200_PROF("colsum", st);
-  colsum_kernel<TG><<<cdiv(N, 32), dim3(32, 32), 0, st>>>(g, out, M, N);
+  B200_CUDA(launch_pdl(colsum_kernel<TG>, dim3(cdiv(N, 32)), dim3(dim3(32, 32)), 0, st, g, out, M, N));
   B200_LAUNCH_CHECK();
   return 0;
 }
@@ -389,6 +395,7 @@ static __global__ void rowsum_atomic_kernel(const float* __restrict__ x, float* 
 // U[v_in][tap*Co + co]  (tap = (a*2+b)*2+c of the k2s2 transposed conv).  16-byte moves both ways.
 template <class T>
 __global__ void unshuffle_kernel(const T* __restrict__ y, ClView yv, int Co, int N, int D, int H, int W, T* __restrict__ U) {
+  pdl_wait();
   constexpr int VN = Vec16<T>::N;
   int lanes = Co / VN;
   long total = (long)N * D * H * W * 8 * lanes;
@@ -434,6 +441,7 @@ static __global__ void batchsum_kernel(const float* __restrict__ dx, float* __re
 // S fp32 [rows, ld] (first L columns valid) -> P (type TP) [rows, ld]; one warp per row.
 template <class TP>
 __global__ void softmax_fwd_kernel(const float* __restrict__ S, TP* __restrict__ P, long rows, int L, int ld, float scale) {
+  pdl_wait();
   long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -451,6 +459,7 @@ __global__ void softmax_fwd_kernel(const float* __restrict__ S, TP* __restrict__
 template <class TP>
 __global__ void softmax_bwd_kernel(const TP* __restrict__ P, const float* __restrict__ dP, TP* __restrict__ dS, long rows,
                                    int L, int ld, float scale) {
+  pdl_wait();
   long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -486,6 +495,7 @@ __device__ __forceinline__ void block_reduce_groups(float* vals, int lanes, floa
 
 template <class T>
 __global__ void in_stats_kernel(const typename RawOf<T>::type* __restrict__ x, ClView xv, int C, long V, double* __restrict__ acc) {
+  pdl_wait();
   typedef typename RawOf<T>::type TR;
   constexpr int VN = Vec16<T>::N;
   extern __shared__ float red[];  // [256][2*VN]
@@ -525,6 +535,7 @@ __global__ void in_stats_kernel(const typename RawOf<T>::type* __restrict__ x, C
   }
 }
 static __global__ void in_finalize_kernel(const double* __restrict__ acc, float* __restrict__ mr, int NC, double invV) {
+  pdl_wait();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= NC) return;
   double mean = acc[2 * i] * invV;
@@ -540,6 +551,7 @@ template <class T>
 __global__ void in_apply_kernel(const typename RawOf<T>::type* __restrict__ x, ClView xv, const float* __restrict__ mr,
                                 const typename RawOf<T>::type* __restrict__ x2, ClView x2v, const float* __restrict__ mr2, T* __restrict__ out,
                                 ClView ov, int C, long V, int two) {
+  pdl_wait();
   constexpr int VN = Vec16<T>::N;
   int lanes = C / VN;
   int n = blockIdx.y;
@@ -579,6 +591,7 @@ template <class T, bool TWO>
 __global__ void __launch_bounds__(256, 3) in_bwd_reduce_kernel(const T* __restrict__ dout, ClView dv, const T* __restrict__ act, ClView av,
                                      const typename RawOf<T>::type* __restrict__ ra, ClView rav, const typename RawOf<T>::type* __restrict__ rb, ClView rbv, int C, long V,
                                      double* __restrict__ acc /*[N][C][3]*/) {
+  pdl_wait();
   constexpr int VN = Vec16<T>::N;
   extern __shared__ float red[];  // [warps][lanes][3*VN]
   int lanes = C / VN;
@@ -633,6 +646,7 @@ __global__ void __launch_bounds__(256, 3) in_bwd_reduce_kernel(const T* __restri
 }
 // raw moments -> centred/normalised ones (TWO mode): acc[.][1] = rstd_a*(acc[1] - mean_a*acc[0]), same for [2] with (mean_b, rstd_b)
 static __global__ void in_bwd_fixup_kernel(double* __restrict__ acc, const float* __restrict__ mra, const float* __restrict__ mrb, int NC) {
+  pdl_wait();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= NC) return;
   double sg = acc[3 * i];
@@ -648,6 +662,7 @@ __global__ void __launch_bounds__(256, 3) in_bwd_apply_kernel(const T* __restric
                                     const typename RawOf<T>::type* __restrict__ rb, ClView rbv, const float* __restrict__ mrb, int C, long V,
                                     const double* __restrict__ acc, T* __restrict__ da, ClView dav,
                                     T* __restrict__ db, ClView dbv) {
+  pdl_wait();
   constexpr int VN = Vec16<T>::N;
   extern __shared__ __align__(16) float cst[];   // [6][C]
   int lanes = C / VN;

@@ -265,7 +265,7 @@ struct Exec {
   int in_stats(Cl<const T> x, long Vs, float* mr, cudaStream_t st, bool have_sums = false) {
     B200_PROF("instnorm_stats", st);
     if (have_sums) {  // sums already accumulated by the conv epilogue
-      in_finalize_kernel<<<cdiv(c.B * x.C, 128), 128, 0, st>>>(w.stat_acc, mr, c.B * x.C, 1.0 / (double)Vs);
+      B200_CUDA(launch_pdl(in_finalize_kernel, dim3(cdiv(c.B * x.C, 128)), dim3(128), 0, st, w.stat_acc, mr, c.B * x.C, 1.0 / (double)Vs));
       B200_LAUNCH_CHECK();
       return 0;
     }
@@ -274,17 +274,17 @@ struct Exec {
                "InstanceNorm channel count %d unsupported (need a power of two >= 8)", x.C);
     B200_CUDA(cudaMemsetAsync(w.stat_acc, 0, sizeof(double) * 2 * c.B * x.C, st));
     dim3 g(in_grid_x(Vs, x.C / VN), c.B);
-    in_stats_kernel<T><<<g, 256, 256 * 2 * VN * sizeof(float), st>>>(reinterpret_cast<const TR*>(x.p), ClView{x.pitch, x.coff}, x.C, Vs, w.stat_acc);
+    B200_CUDA(launch_pdl(in_stats_kernel<T>, dim3(g), dim3(256), 256 * 2 * VN * sizeof(float), st, reinterpret_cast<const TR*>(x.p), ClView{x.pitch, x.coff}, x.C, Vs, w.stat_acc));
     B200_LAUNCH_CHECK();
-    in_finalize_kernel<<<cdiv(c.B * x.C, 128), 128, 0, st>>>(w.stat_acc, mr, c.B * x.C, 1.0 / (double)Vs);
+    B200_CUDA(launch_pdl(in_finalize_kernel, dim3(cdiv(c.B * x.C, 128)), dim3(128), 0, st, w.stat_acc, mr, c.B * x.C, 1.0 / (double)Vs));
     B200_LAUNCH_CHECK();
     return 0;
   }
   int in_apply(Cl<const T> x, const float* mr, const T* x2, const float* mr2, Cl<T> out, long Vs, cudaStream_t st) {
     B200_PROF("instnorm_apply", st);
     dim3 g(in_grid_x(Vs, x.C / Vec16<T>::N) * 2, c.B);
-    in_apply_kernel<T><<<g, 256, 0, st>>>(reinterpret_cast<const TR*>(x.p), ClView{x.pitch, x.coff}, mr, reinterpret_cast<const TR*>(x2), ClView{x.C, 0}, mr2, out.p,
-                                          ClView{out.pitch, out.coff}, x.C, Vs, x2 != nullptr);
+    B200_CUDA(launch_pdl(in_apply_kernel<T>, dim3(g), dim3(256), 0, st, reinterpret_cast<const TR*>(x.p), ClView{x.pitch, x.coff}, mr, reinterpret_cast<const TR*>(x2), ClView{x.C, 0}, mr2, out.p,
+                                          ClView{out.pitch, out.coff}, x.C, Vs, x2 != nullptr));
     B200_LAUNCH_CHECK();
     return 0;
   }
@@ -350,8 +350,8 @@ struct Exec {
         else if (Co == 16) conv_in_fwd_kernel<T, 16><<<g, 256, sm, st>>>(raw, W1, W3, c.Cin, s.D, s.H, s.W, (TR*)c1.p, (TR*)c3.p, w.stat_acc, st3);
         else conv_in_fwd_kernel<T, 32><<<g, 256, sm, st>>>(raw, W1, W3, c.Cin, s.D, s.H, s.W, (TR*)c1.p, (TR*)c3.p, w.stat_acc, st3);
         B200_LAUNCH_CHECK();
-        in_finalize_kernel<<<cdiv(c.B * Co, 128), 128, 0, st>>>(w.stat_acc, r.mr1, c.B * Co, 1.0 / (double)Vs); B200_LAUNCH_CHECK();
-        in_finalize_kernel<<<cdiv(c.B * Co, 128), 128, 0, st>>>(st3, r.mr3, c.B * Co, 1.0 / (double)Vs); B200_LAUNCH_CHECK();
+        B200_CUDA(launch_pdl(in_finalize_kernel, dim3(cdiv(c.B * Co, 128)), dim3(128), 0, st, w.stat_acc, r.mr1, c.B * Co, 1.0 / (double)Vs)); B200_LAUNCH_CHECK();
+        B200_CUDA(launch_pdl(in_finalize_kernel, dim3(cdiv(c.B * Co, 128)), dim3(128), 0, st, st3, r.mr3, c.B * Co, 1.0 / (double)Vs)); B200_LAUNCH_CHECK();
       }
       B200_TRY(in_apply(cl<const T>(c1.p, Co, 0, Co), r.mr1, nullptr, nullptr, a1, Vs, st));
       B200_TRY(conv_fwd(cl<const T>(a1.p, Co, 0, Co), s, W2, Co, 3, c2, w.stat_acc, &done, st));
@@ -368,8 +368,8 @@ struct Exec {
         B200_CUDA(cudaMemsetAsync(w.stat_acc, 0, sizeof(double) * 4 * c.B * 8 * c.fs, st));
         tc::HaloFused fu = {1, w.wcf[i3], c3.p, Co, 0, st3, nullptr, 0, 0};
         B200_TRY(tc::conv_halo(x.p, x.pitch, x.coff, x.C, s.N, s.D, s.H, s.W, w.wcf[i1], Co, c1.p, Co, 0, 0, w.stat_acc, st, &fu, 1));
-        in_finalize_kernel<<<cdiv(c.B * Co, 128), 128, 0, st>>>(w.stat_acc, r.mr1, c.B * Co, 1.0 / (double)Vs); B200_LAUNCH_CHECK();
-        in_finalize_kernel<<<cdiv(c.B * Co, 128), 128, 0, st>>>(st3, r.mr3, c.B * Co, 1.0 / (double)Vs); B200_LAUNCH_CHECK();
+        B200_CUDA(launch_pdl(in_finalize_kernel, dim3(cdiv(c.B * Co, 128)), dim3(128), 0, st, w.stat_acc, r.mr1, c.B * Co, 1.0 / (double)Vs)); B200_LAUNCH_CHECK();
+        B200_CUDA(launch_pdl(in_finalize_kernel, dim3(cdiv(c.B * Co, 128)), dim3(128), 0, st, st3, r.mr3, c.B * Co, 1.0 / (double)Vs)); B200_LAUNCH_CHECK();
         fused13 = true;
       }
     }
@@ -408,13 +408,13 @@ struct Exec {
     // final lrelu + two norms
     { B200_PROF("instnorm_bwd", st);
     B200_CUDA(cudaMemsetAsync(w.bwd_acc, 0, sizeof(double) * 3 * B * Co, st));
-    in_bwd_reduce_kernel<T, true><<<gr, 256, red_smem, st>>>(dOut.p, ClView{dOut.pitch, dOut.coff}, out.p, ClView{out.pitch, out.coff},
-                                                      (const TR*)r.c2, pv, (const TR*)r.c3, pv, Co, Vs, w.bwd_acc);
+    B200_CUDA(launch_pdl(in_bwd_reduce_kernel<T, true>, dim3(gr), dim3(256), red_smem, st, dOut.p, ClView{dOut.pitch, dOut.coff}, out.p, ClView{out.pitch, out.coff},
+                                                      (const TR*)r.c2, pv, (const TR*)r.c3, pv, Co, Vs, w.bwd_acc));
     B200_LAUNCH_CHECK();
-    in_bwd_fixup_kernel<<<cdiv(B * Co, 128), 128, 0, st>>>(w.bwd_acc, r.mr2, r.mr3, B * Co);
+    B200_CUDA(launch_pdl(in_bwd_fixup_kernel, dim3(cdiv(B * Co, 128)), dim3(128), 0, st, w.bwd_acc, r.mr2, r.mr3, B * Co));
     B200_LAUNCH_CHECK();
-    in_bwd_apply_kernel<T, true><<<ga, 256, cst_smem, st>>>(dOut.p, ClView{dOut.pitch, dOut.coff}, out.p, ClView{out.pitch, out.coff},
-                                               (const TR*)r.c2, pv, r.mr2, (const TR*)r.c3, pv, r.mr3, Co, Vs, w.bwd_acc, w.dc2, pv, w.dc3, pv);
+    B200_CUDA(launch_pdl(in_bwd_apply_kernel<T, true>, dim3(ga), dim3(256), cst_smem, st, dOut.p, ClView{dOut.pitch, dOut.coff}, out.p, ClView{out.pitch, out.coff},
+                                               (const TR*)r.c2, pv, r.mr2, (const TR*)r.c3, pv, r.mr3, Co, Vs, w.bwd_acc, w.dc2, pv, w.dc3, pv));
     B200_LAUNCH_CHECK(); }
     Cl<const T> dc2 = cl<const T>(w.dc2, Co, 0, Co), dc3 = cl<const T>(w.dc3, Co, 0, Co), a1 = cl<const T>(r.a1, Co, 0, Co);
     // conv2
@@ -423,10 +423,10 @@ struct Exec {
     // lrelu + norm1
     { B200_PROF("instnorm_bwd", st);
     B200_CUDA(cudaMemsetAsync(w.bwd_acc, 0, sizeof(double) * 3 * B * Co, st));
-    in_bwd_reduce_kernel<T, false><<<gr, 256, red_smem, st>>>(w.da1, pv, r.a1, pv, (const TR*)nullptr, pv, (const TR*)nullptr, pv, Co, Vs, w.bwd_acc);
+    B200_CUDA(launch_pdl(in_bwd_reduce_kernel<T, false>, dim3(gr), dim3(256), red_smem, st, w.da1, pv, r.a1, pv, (const TR*)nullptr, pv, (const TR*)nullptr, pv, Co, Vs, w.bwd_acc));
     B200_LAUNCH_CHECK();
-    in_bwd_apply_kernel<T, false><<<ga, 256, cst_smem, st>>>(w.da1, pv, r.a1, pv, (const TR*)nullptr, pv, r.mr1, (const TR*)nullptr, pv, nullptr, Co, Vs, w.bwd_acc,
-                                               w.dc1, pv, nullptr, pv);
+    B200_CUDA(launch_pdl(in_bwd_apply_kernel<T, false>, dim3(ga), dim3(256), cst_smem, st, w.da1, pv, r.a1, pv, (const TR*)nullptr, pv, r.mr1, (const TR*)nullptr, pv, nullptr, Co, Vs, w.bwd_acc,
+                                               w.dc1, pv, nullptr, pv));
     B200_LAUNCH_CHECK(); }
     Cl<const T> dc1 = cl<const T>(w.dc1, Co, 0, Co);
     if (raw) {   // encoder1: both weight gradients from the raw fp32 input in one dedicated kernel
@@ -582,7 +582,7 @@ struct Exec {
     { EpStore<float> ep = ep_plain<float>(w.S, Lp); ep.sb0 = sPb; ep.sb1 = sPh; ep.nb1 = nh;
       if constexpr (kTC) B200_TRY(tc::gemm(tc::operand(qkv, 3 * H, 1, sQb, dh), tc::operand(qkv + H, 3 * H, 1, sQb, dh), ep, L, L, dh, c.B, nh, st));
       else B200_TRY(launch_contract(ld4<T, false>(qkv, 3 * H, 1, sQb, dh, nh), ld4<T, false>(qkv + H, 3 * H, 1, sQb, dh, nh), ep, L, L, dh, BH, 1, st)); }
-    softmax_fwd_kernel<T><<<cdiv((long)BH * L, 8), 256, 0, st>>>(w.S, w.P[i], (long)BH * L, L, Lp, scale);
+    B200_CUDA(launch_pdl(softmax_fwd_kernel<T>, dim3(cdiv((long)BH * L, 8)), dim3(256), 0, st, w.S, w.P[i], (long)BH * L, L, Lp, scale));
     B200_LAUNCH_CHECK();
     { EpStore<T> ep = ep_plain<T>(w.att[i], H); ep.sb0 = (long)L * H; ep.sb1 = dh; ep.nb1 = nh;
       if constexpr (kTC) B200_TRY(tc::gemm(tc::operand(w.P[i], Lp, 1, sPb, sPh), tc::operand(qkv + 2 * H, 1, 3 * H, sQb, dh), ep, L, dh, L, c.B, nh, st));
@@ -603,7 +603,7 @@ struct Exec {
     { EpStore<T> ep = ep_plain<T>(w.dqkv + 2 * H, 3 * H); ep.sb0 = sQb; ep.sb1 = dh; ep.nb1 = nh;
       if constexpr (kTC) B200_TRY(tc::gemm(tc::operand(w.P[i], 1, Lp, sPb, sPh), tc::operand(w.datt, 1, H, sOb, dh), ep, L, dh, L, c.B, nh, st));
       else B200_TRY(launch_contract(ld4<T, true>(w.P[i], 1, Lp, sPb, sPh, nh), ld4<T, true>(w.datt, 1, H, sOb, dh, nh), ep, L, dh, L, BH, 1, st)); }
-    softmax_bwd_kernel<T><<<cdiv((long)BH * L, 8), 256, 0, st>>>(w.P[i], w.dP, w.dS, (long)BH * L, L, Lp, scale);
+    B200_CUDA(launch_pdl(softmax_bwd_kernel<T>, dim3(cdiv((long)BH * L, 8)), dim3(256), 0, st, w.P[i], w.dP, w.dS, (long)BH * L, L, Lp, scale));
     B200_LAUNCH_CHECK();
     // dQ = dS K ; dK = dS^T Q
     { EpStore<T> ep = ep_plain<T>(w.dqkv, 3 * H); ep.sb0 = sQb; ep.sb1 = dh; ep.nb1 = nh;
@@ -802,7 +802,7 @@ struct Exec {
         int Co = dy.C, rows = (int)s.rows(), K8 = 8 * Co;
         { B200_PROFD(st, "convT_unshuffle %d @%d", Co, s.D);
           long tot = (long)rows * 8 * (Co / VN);
-          unshuffle_kernel<T><<<(unsigned)min(148L * 16, (tot + 255) / 256), 256, 0, st>>>(dy.p, ClView{dy.pitch, dy.coff}, Co, s.N, s.D, s.H, s.W, w.unsh);
+          B200_CUDA(launch_pdl(unshuffle_kernel<T>, dim3((unsigned)min(148L * 16, (tot + 255) / 256)), dim3(256), 0, st, dy.p, ClView{dy.pitch, dy.coff}, Co, s.N, s.D, s.H, s.W, w.unsh));
           B200_LAUNCH_CHECK(); }
         if (dW) {   // dW[ci][co*8+tap] = sum_v x[v,ci] U[v, tap*Co+co]   (voxels = reduction, split-K + atomics)
           B200_PROFD(st, "convT_wgrad %dx%d @%d", Ci, Co, s.D);

@@ -105,6 +105,7 @@ conv_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ C
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();   // (resident weights fetched above were packed many launches earlier)
 
   if (warp >= 6) {
     // ---- software A-brick loader (CONV_LOADERS threads)
@@ -367,7 +368,7 @@ static int conv(const bf16* x, int in_pitch, int in_coff, int Ci, int N, int D, 
   static bool attr_done = false;
   if (!attr_done) { B200_CUDA(cudaFuncSetAttribute(conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr_done = true; }
   int grid = (int)(p.total_tiles < num_sms() ? p.total_tiles : num_sms());
-  conv_kernel<<<grid, CONV_THREADS, smem, st>>>(mx, mw, p);
+  B200_CUDA(launch_pdl(conv_kernel, dim3(grid), dim3(CONV_THREADS), smem, st, mx, mw, p));
   B200_LAUNCH_CHECK();
   return 0;
 }

@@ -26,7 +26,8 @@ struct HaloParams {
   int N, D, H, W, Ci, Co;
   int kc, row_bytes, nchunk;     // channels per chunk (<= 64), smem row size, Ci/kc
   int tiles_w, tiles_h, tiles_per_n, total_tiles;
-  int planes;                    // halo planes per pipeline stage: 3 (one box of depth 3) or 1
+  int planes;                    // halo planes per pipeline stage: 3 (one TMA box of depth op+2 serving `op` output planes) or 1
+  int op;                        // output d-planes per tile (planes == 3 only; 1, 2 or 4): (op+2)/op halo planes fetched per output plane
   int plane_bytes;               // HALO_H*HALO_W*row_bytes
   int halo_bytes;                // planes*plane_bytes rounded up to 1024 (weight tiles of a non-resident stage follow)
   int b_bytes;                   // one (tap, chunk) weight tile, rounded to 1024
@@ -59,6 +60,30 @@ __device__ __forceinline__ void issue_plane(uint32_t tmem_d, uint32_t a_pl, uint
         else umma_f16(tmem_d, desc64(a_lo + 2 * k, a_hi), desc64(b_lo + 2 * k, b_hi), idesc, 1u);
       }
     }
+}
+
+// `op` output planes at once: for every (kd, tap, k-step) one MMA per output plane o, so consecutive MMAs target DIFFERENT
+// TMEM accumulators (and share the B descriptor).  a_st: first halo plane of the stage; output o reads plane o + kd.
+template <int KSTEPS>
+__device__ __forceinline__ void issue_planes_interleaved(uint32_t tmem0, uint32_t co, int op, uint32_t a_st, uint32_t plane_units, uint32_t a_hi,
+                                                         uint32_t b_st, uint32_t b_plane, uint32_t b_hi, uint32_t b_tap, uint32_t idesc,
+                                                         uint32_t first, uint32_t tap_on) {
+  constexpr uint32_t ROW_UNITS = 2 * KSTEPS;
+#pragma unroll
+  for (int kd = 0; kd < 3; ++kd)
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw)
+#pragma unroll
+        for (int k = 0; k < KSTEPS; ++k) {
+          const uint32_t a_off = (uint32_t)kd * plane_units + tap_on * (uint32_t)(kh * HALO_W + kw) * ROW_UNITS + 2 * k;
+          const uint32_t b_lo = b_st + (uint32_t)kd * b_plane + (uint32_t)(kh * 3 + kw) * b_tap + 2 * k;
+          const uint32_t accf = (kd == 0 && kh == 0 && kw == 0 && k == 0) ? (first ? 0u : 1u) : 1u;
+#pragma unroll
+          for (int o = 0; o < 4; ++o)
+            if (o < op) umma_f16(tmem0 + (uint32_t)o * co, desc64(a_st + (uint32_t)o * plane_units + a_off, a_hi), desc64(b_lo, b_hi), idesc, accf);
+        }
 }
 
 // KSTEPS = kc/16; CO_T = 16 / 32: output channels known at compile time (register-resident statistics), 0 = generic
@@ -110,16 +135,18 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();   // (the resident weights fetched above were packed many launches earlier)
 
   if (warp == 0) {
     // ---- TMA producer: per (kd group, chunk) one halo box (+ its 9*planes weight tiles when not resident)
     int stage = 0; uint32_t phase = 0;
     const uint32_t ring_u = smem_u32(ring);
-    const uint32_t tx = (uint32_t)(p.planes * p.plane_bytes) + (p.resident ? 0u : 9u * (uint32_t)p.planes * w_tx);
+    const int box_planes = p.planes == 3 ? p.op + 2 : 1;
+    const uint32_t tx = (uint32_t)(box_planes * p.plane_bytes) + (p.resident ? 0u : 9u * (uint32_t)p.planes * w_tx);
     int t = blockIdx.x;
     int n = t / p.tiles_per_n, r = t - n * p.tiles_per_n;
     for (; t < p.total_tiles; t += gridDim.x) {
-      const int tw = r % p.tiles_w, q = r / p.tiles_w, th = q % p.tiles_h, d = q / p.tiles_h;
+      const int tw = r % p.tiles_w, q = r / p.tiles_w, th = q % p.tiles_h, d = (q / p.tiles_h) * p.op;   // first output plane of the tile
       for (int kg = 0; kg < kd_groups; ++kg)
         for (int ch = 0; ch < p.nchunk; ++ch) {
           mbar_wait(empty + stage, phase ^ 1);
@@ -128,7 +155,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
             if (p.dbg_mode & 1) mbar_arrive(full + stage);
             else {
               const bool second = p.mode2 == 2 && (p.planes == 3 || kg == 1);   // the stage that holds the centre plane
-              mbar_expect_tx(full + stage, tx + (second ? (uint32_t)(128 * p.row_bytes) : 0u));
+              mbar_expect_tx(full + stage, tx + (second ? (uint32_t)(p.op * 128 * p.row_bytes) : 0u));
               tma_load_5d(base, &map_x, full + stage, ch * p.kc, tw * HTW - 1, th * HTH - 1, d + kg * p.planes - 1, n);
               if (second) tma_load_5d(base + p.x2_off, &map_x2, full + stage, ch * p.kc, tw * HTW, th * HTH, d, n);
               if (!p.resident)
@@ -147,7 +174,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.Co >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     const uint32_t layout = KSTEPS == 4 ? 2u : (KSTEPS == 2 ? 4u : 6u);
     constexpr uint32_t ROW_BYTES = 32 * KSTEPS;
-    const uint32_t a_hi = desc_hi((uint32_t)(HALO_W * ROW_BYTES), layout);   // next 8-row group = next h line of the halo
+    const uint32_t a_hi = desc_hi((p.dbg_mode & 64) ? 8u * ROW_BYTES : (uint32_t)(HALO_W * ROW_BYTES), layout);   // next 8-row group = next h line of the halo
     const uint32_t b_hi = desc_hi(8 * ROW_BYTES, layout);
     const uint32_t ring_u = smem_u32(ring);
     const uint32_t a_lo0 = desc_lo(ring_u, 16);
@@ -160,7 +187,6 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
       mbar_wait(tempty + acc, acc_phase ^ 1);
       tc_fence_after();
-      const uint32_t tmem_d = tmem_base + (uint32_t)(acc * p.Co);
       int s = 0;
       for (int kg = 0; kg < kd_groups; ++kg)
         for (int ch = 0; ch < p.nchunk; ++ch, ++s) {
@@ -170,24 +196,50 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
           const uint32_t b_st = p.resident ? b_lo0 + (uint32_t)(kg * p.planes) * b_plane + (uint32_t)ch * b_units : b_lo0 + (uint32_t)stage * stage_units;
           if (elect_one()) {
             if (!(p.dbg_mode & 2)) {
-              issue_plane<KSTEPS>(tmem_d, a_st, a_hi, b_st, b_hi, b_tap, idesc, s == 0 ? 1u : 0u);
+              const uint32_t b_k1 = b_lo0 + (uint32_t)(27 * p.nchunk + ch) * b_units;
               if (p.planes == 3) {
-                issue_plane<KSTEPS>(tmem_d, a_st + plane_units, a_hi, b_st + b_plane, b_hi, b_tap, idesc, 0u);
-                issue_plane<KSTEPS>(tmem_d, a_st + 2 * plane_units, a_hi, b_st + 2 * b_plane, b_hi, b_tap, idesc, 0u);
-              }
-              if (p.mode2 && (p.planes == 3 || kg == 1)) {   // fused 1x1x1 conv on the centre plane's stage
-                const uint32_t b_k1 = b_lo0 + (uint32_t)(27 * p.nchunk + ch) * b_units;
-                if (p.mode2 == 1) {       // same input (centre tap view), second accumulator
-                  const uint32_t a_c = a_st + (p.planes == 3 ? plane_units : 0u) + (uint32_t)(HALO_W + 1) * (2 * KSTEPS);
-                  const uint32_t tmem_d2 = tmem_base + (uint32_t)((2 + acc) * p.Co);
+                // `op` output planes share the op+2 halo planes of this stage: output o reads planes o, o+1, o+2
+                const bool inter = p.op > 1 && (p.dbg_mode & 32);   // measured slower than plane-by-plane (92 vs 87 us): opt-in experiment
+                if (inter)
+                  issue_planes_interleaved<KSTEPS>(tmem_base + (uint32_t)(acc * p.op * p.Co), (uint32_t)p.Co, p.op, a_st, plane_units, a_hi, b_st, b_plane,
+                                                   b_hi, b_tap, idesc, s == 0 ? 1u : 0u, (p.dbg_mode & 16) ? 0u : 1u);
+                for (int o = 0; o < p.op; ++o) {
+                  const uint32_t tmem_d = tmem_base + (uint32_t)((acc * p.op + o) * p.Co);
+                  const uint32_t a_o = a_st + (uint32_t)o * plane_units;
+                  if (!inter) {
+                    issue_plane<KSTEPS>(tmem_d, a_o, a_hi, b_st, b_hi, b_tap, idesc, s == 0 ? 1u : 0u);
+                    issue_plane<KSTEPS>(tmem_d, a_o + plane_units, a_hi, b_st + b_plane, b_hi, b_tap, idesc, 0u);
+                    issue_plane<KSTEPS>(tmem_d, a_o + 2 * plane_units, a_hi, b_st + 2 * b_plane, b_hi, b_tap, idesc, 0u);
+                  }
+                  if (p.mode2 == 1) {       // fused 1x1x1 conv: centre tap view of the centre plane, second accumulator set
+                    const uint32_t a_c = a_o + plane_units + (uint32_t)(HALO_W + 1) * (2 * KSTEPS);
+                    const uint32_t tmem_d2 = tmem_base + (uint32_t)(((2 + acc) * p.op + o) * p.Co);
 #pragma unroll
-                  for (int k = 0; k < KSTEPS; ++k)
-                    umma_f16(tmem_d2, desc64(a_c + 2 * k, a_hi), desc64(b_k1 + 2 * k, b_hi), idesc, (ch | k) ? 1u : 0u);
-                } else {                  // second input tile (no halo), same accumulator
-                  const uint32_t a_2 = a_st + ((uint32_t)p.x2_off >> 4);
+                    for (int k = 0; k < KSTEPS; ++k)
+                      umma_f16(tmem_d2, desc64(a_c + 2 * k, a_hi), desc64(b_k1 + 2 * k, b_hi), idesc, (ch | k) ? 1u : 0u);
+                  } else if (p.mode2 == 2) { // fused 1x1x1 dgrad: second input tile (no halo), same accumulator
+                    const uint32_t a_2 = a_st + ((uint32_t)p.x2_off >> 4) + (uint32_t)o * (128u * ROW_BYTES >> 4);
 #pragma unroll
-                  for (int k = 0; k < KSTEPS; ++k)
-                    umma_f16(tmem_d, desc64(a_2 + 2 * k, b_hi), desc64(b_k1 + 2 * k, b_hi), idesc, 1u);
+                    for (int k = 0; k < KSTEPS; ++k)
+                      umma_f16(tmem_d, desc64(a_2 + 2 * k, b_hi), desc64(b_k1 + 2 * k, b_hi), idesc, 1u);
+                  }
+                }
+              } else {
+                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * p.Co);
+                issue_plane<KSTEPS>(tmem_d, a_st, a_hi, b_st, b_hi, b_tap, idesc, s == 0 ? 1u : 0u);
+                if (p.mode2 && kg == 1) {   // the stage that holds the centre plane
+                  if (p.mode2 == 1) {
+                    const uint32_t a_c = a_st + (uint32_t)(HALO_W + 1) * (2 * KSTEPS);
+                    const uint32_t tmem_d2 = tmem_base + (uint32_t)((2 + acc) * p.Co);
+#pragma unroll
+                    for (int k = 0; k < KSTEPS; ++k)
+                      umma_f16(tmem_d2, desc64(a_c + 2 * k, a_hi), desc64(b_k1 + 2 * k, b_hi), idesc, (ch | k) ? 1u : 0u);
+                  } else {
+                    const uint32_t a_2 = a_st + ((uint32_t)p.x2_off >> 4);
+#pragma unroll
+                    for (int k = 0; k < KSTEPS; ++k)
+                      umma_f16(tmem_d, desc64(a_2 + 2 * k, b_hi), desc64(b_k1 + 2 * k, b_hi), idesc, 1u);
+                  }
                 }
               }
             }
@@ -236,19 +288,22 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
       }
     };
     for (; t < p.total_tiles; t += gridDim.x) {
-      const int tw = r % p.tiles_w, qq = r / p.tiles_w, th = qq % p.tiles_h, d = qq / p.tiles_h;
+      const int tw = r % p.tiles_w, qq = r / p.tiles_w, th = qq % p.tiles_h, d0 = (qq / p.tiles_h) * p.op;
       if (n != n_acc) { flush(n_acc); n_acc = n; }
       const int w = tw * HTW + (row & 7), h = th * HTH + (row >> 3);
       const bool valid = (w < p.W) && (h < p.H);
-      const long vox = (((long)n * p.D + d) * p.H + h) * p.W + w;
       mbar_wait(tfull + acc, acc_phase);
       tc_fence_after();
+      for (int o = 0; o < p.op; ++o) {
+      const int d = d0 + o;
+      if (d >= p.D) break;
+      const long vox = (((long)n * p.D + d) * p.H + h) * p.W + w;
 #pragma unroll
       for (int ps = 0; ps < 2; ++ps) {
         if (ps >= npass) continue;
         bf16* dst = ps ? p.out2 + vox * p.pitch2 + p.coff2 : p.out + vox * p.pitch + p.coff;
         double* sp = ps ? p.stats2 : p.stats;
-        const uint32_t trow = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)((2 * ps + acc) * p.Co);
+        const uint32_t trow = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(((2 * ps + acc) * p.op + o) * p.Co);
         if (CO_T) {
 #pragma unroll
           for (int c0 = 0; c0 < NR; c0 += 16) {
@@ -322,6 +377,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
           }
         }
       }
+      }   // o
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty + acc);
@@ -342,8 +398,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
 }
 
 // smem plan shared by the support test and the launcher
-struct HaloPlan { int kc, rb, nchunk, plane_bytes, b_bytes, resident, planes, halo_bytes, stage_bytes, stages; };
-static inline HaloPlan halo_plan(int Ci, int Co, int mode2 = 0) {
+struct HaloPlan { int kc, rb, nchunk, plane_bytes, b_bytes, resident, planes, op, halo_bytes, x2_bytes, stage_bytes, stages; };
+// D, tiles_hw: depth and (h,w) tile count of one sample -- the multi-plane tiling needs enough tiles to balance 148 CTAs
+static inline HaloPlan halo_plan(int Ci, int Co, int mode2 = 0, int D = 0, long tiles_hw_n = 0) {
   HaloPlan h;
   h.kc = Ci % 64 == 0 ? 64 : (Ci % 32 == 0 ? 32 : 16); h.rb = h.kc * 2; h.nchunk = Ci / h.kc;
   h.plane_bytes = HALO_H * HALO_W * h.rb;
@@ -352,14 +409,27 @@ static inline HaloPlan halo_plan(int Ci, int Co, int mode2 = 0) {
   const int wtiles = (27 + (mode2 ? 1 : 0)) * h.nchunk;
   h.resident = ((long)wtiles * h.b_bytes <= 112 * 1024) ? 1 : 0;
   int budget = budget_all - (h.resident ? wtiles * h.b_bytes : 0);
-  const int x2 = mode2 == 2 ? ((128 * h.rb + 1023) / 1024) * 1024 : 0;   // second input tile of the fused 1x1x1 dgrad
-  h.planes = 3;
-  h.halo_bytes = ((3 * h.plane_bytes + 1023) / 1024) * 1024;
-  h.stage_bytes = h.halo_bytes + x2 + (h.resident ? 0 : 27 * h.b_bytes);
+  const int x2_one = mode2 == 2 ? 128 * h.rb : 0;   // second input tile of the fused 1x1x1 dgrad, per output plane
+  const int op_max = getenv("B200_HALO_OP") ? atoi(getenv("B200_HALO_OP")) : 4;
+  const long min_tiles = getenv("B200_HALO_MIN_TILES") ? atol(getenv("B200_HALO_MIN_TILES")) : 148 * 8;   // tests lower it
+  h.planes = 3; h.op = 1;
+  // most output planes per tile that keep >= 3 pipeline stages, fit TMEM (2 buffers x op x Co [x2 outputs]) and leave every CTA
+  // at least ~8 tiles; resident weights and a single channel chunk only
+  for (int op = 4; op >= 1; op >>= 1) {
+    if (op > op_max) continue;
+    if (op > 1 && (!h.resident || h.nchunk != 1 || D <= 0 || D % op != 0 || (long)(D / op) * tiles_hw_n < min_tiles)) continue;
+    if ((mode2 == 1 ? 4 : 2) * op * Co > 512) continue;
+    const int hb = (((op + 2) * h.plane_bytes + 1023) / 1024) * 1024, xb = ((op * x2_one + 1023) / 1024) * 1024;
+    const int st = hb + xb + (h.resident ? 0 : 27 * h.b_bytes);
+    if (budget / st < 3 && op > 1) continue;
+    h.op = op; h.halo_bytes = hb; h.x2_bytes = xb; h.stage_bytes = st;
+    break;
+  }
   if (budget / h.stage_bytes < 3) {   // one plane per stage
-    h.planes = 1;
+    h.planes = 1; h.op = 1;
     h.halo_bytes = ((h.plane_bytes + 1023) / 1024) * 1024;
-    h.stage_bytes = h.halo_bytes + x2 + (h.resident ? 0 : 9 * h.b_bytes);
+    h.x2_bytes = ((x2_one + 1023) / 1024) * 1024;
+    h.stage_bytes = h.halo_bytes + h.x2_bytes + (h.resident ? 0 : 9 * h.b_bytes);
   }
   h.stages = budget / h.stage_bytes; if (h.stages > 8) h.stages = 8;
   return h;
@@ -381,7 +451,7 @@ static int conv_halo_launch(const CUtensorMap& mx, const CUtensorMap& mw, const 
                             size_t smem, cudaStream_t st) {
   static bool attr_done = false;
   if (!attr_done) { B200_CUDA(cudaFuncSetAttribute(conv_halo_kernel<KSTEPS, CO_T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr_done = true; }
-  conv_halo_kernel<KSTEPS, CO_T><<<grid, 192, smem, st>>>(mx, mw, mx2, mw2, p);
+  B200_CUDA(launch_pdl(conv_halo_kernel<KSTEPS, CO_T>, dim3(grid), dim3(192), smem, st, mx, mw, mx2, mw2, p));
   B200_LAUNCH_CHECK();
   return 0;
 }
@@ -398,20 +468,21 @@ static int conv_halo(const bf16* x, int in_pitch, int in_coff, int Ci, int N, in
   EncodeTiledFn enc = get_encode();
   B200_CHECK(enc, "cuTensorMapEncodeTiled not available from the driver");
   const int mode2 = fu ? fu->mode2 : 0;
-  HaloPlan h = halo_plan(Ci, Co, mode2);
+  HaloPlan h = halo_plan(Ci, Co, mode2, D, (long)N * cdiv(H, HTH) * cdiv(W, HTW));
   B200_CHECK(!mode2 || h.resident, "fused 1x1x1 conv needs resident weights (Ci=%d Co=%d)", Ci, Co);
   HaloParams p;
   p.N = N; p.D = D; p.H = H; p.W = W; p.Ci = Ci; p.Co = Co;
   p.kc = h.kc; p.row_bytes = h.rb; p.nchunk = h.nchunk;
   p.tiles_w = cdiv(W, HTW); p.tiles_h = cdiv(H, HTH);
-  p.tiles_per_n = D * p.tiles_h * p.tiles_w;
+  p.op = h.op;
+  p.tiles_per_n = cdiv(D, h.op) * p.tiles_h * p.tiles_w;
   long total = (long)N * p.tiles_per_n;
   B200_CHECK(total < (1L << 30), "halo conv: too many tiles");
   p.total_tiles = (int)total;
   p.planes = h.planes; p.plane_bytes = h.plane_bytes; p.halo_bytes = h.halo_bytes; p.b_bytes = h.b_bytes; p.resident = h.resident;
   p.stage_bytes = h.stage_bytes; p.stages = h.stages;
   B200_CHECK(p.stages >= 2, "halo conv smem budget exceeded (Ci=%d Co=%d)", Ci, Co);
-  uint32_t cols = (mode2 == 1 ? 4 : 2) * Co, pw = 32; while (pw < cols) pw <<= 1; p.tmem_cols = pw;
+  uint32_t cols = (mode2 == 1 ? 4 : 2) * h.op * Co, pw = 32; while (pw < cols) pw <<= 1; p.tmem_cols = pw;
   B200_CHECK(p.tmem_cols <= 512, "halo conv TMEM budget exceeded");
   p.out = out; p.pitch = out_pitch; p.coff = out_coff; p.accumulate = accumulate; p.stats = stats;
   p.out_half = out_half;
@@ -429,7 +500,7 @@ static int conv_halo(const bf16* x, int in_pitch, int in_coff, int Ci, int N, in
     cuuint64_t dims[5] = {(cuuint64_t)Ci, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
     const int pt = fu->x2_pitch;
     cuuint64_t strides[4] = {(cuuint64_t)pt * 2, (cuuint64_t)W * pt * 2, (cuuint64_t)H * W * pt * 2, (cuuint64_t)D * H * W * pt * 2};
-    cuuint32_t box[5] = {(cuuint32_t)p.kc, HTW, HTH, 1, 1};
+    cuuint32_t box[5] = {(cuuint32_t)p.kc, HTW, HTH, (cuuint32_t)h.op, 1};
     cuuint32_t es[5] = {1, 1, 1, 1, 1};
     CUresult r = enc(&mx2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (void*)(fu->x2 + fu->x2_coff), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -447,7 +518,7 @@ static int conv_halo(const bf16* x, int in_pitch, int in_coff, int Ci, int N, in
   {
     cuuint64_t dims[5] = {(cuuint64_t)Ci, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
     cuuint64_t strides[4] = {(cuuint64_t)in_pitch * 2, (cuuint64_t)W * in_pitch * 2, (cuuint64_t)H * W * in_pitch * 2, (cuuint64_t)D * H * W * in_pitch * 2};
-    cuuint32_t box[5] = {(cuuint32_t)p.kc, HALO_W, HALO_H, (cuuint32_t)p.planes, 1};
+    cuuint32_t box[5] = {(cuuint32_t)p.kc, HALO_W, HALO_H, (cuuint32_t)(p.planes == 3 ? h.op + 2 : 1), 1};
     cuuint32_t es[5] = {1, 1, 1, 1, 1};
     CUresult r = enc(&mx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (void*)(x + in_coff), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

@@ -88,20 +88,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// Programmatic dependent launch: the kernel may start while its predecessor in the stream drains; everything before
-// pdl_wait() (barrier init, TMEM allocation, descriptor prefetch) overlaps the predecessor's tail, nothing after it does.
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) { asm volatile("prefetch.tensormap [%0];" ::"l"(m) : "memory"); }
-template <class... KArgs, class... Args>
-static cudaError_t launch_pdl(void (*kern)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, Args&&... args) {
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
-  static const bool off = getenv("B200_NO_PDL") != nullptr;
-  cfg.attrs = at; cfg.numAttrs = off ? 0 : 1;
-  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
-}
 
 // shared-memory matrix descriptor, SWIZZLE_128B (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30),
 // SBO>>4 [32,46), version=1 [46,48), layout_type=2 [61,64))
@@ -389,8 +376,8 @@ static int gemm(const Operand& A, const Operand& B, const EP& ep, int M, int N, 
   long tiles = (long)p.tiles_m * p.tiles_n * p.batches * p.ksplit;
   int grid = (int)(tiles < num_sms() ? tiles : num_sms());
   cudaError_t le;
-  if (p.a_mn) { if (p.b_mn) le = launch_pdl(gemm_kernel<EP, true, true>, grid, 192, smem, st, ma, mb, p, ep); else le = launch_pdl(gemm_kernel<EP, true, false>, grid, 192, smem, st, ma, mb, p, ep); }
-  else { if (p.b_mn) le = launch_pdl(gemm_kernel<EP, false, true>, grid, 192, smem, st, ma, mb, p, ep); else le = launch_pdl(gemm_kernel<EP, false, false>, grid, 192, smem, st, ma, mb, p, ep); }
+  if (p.a_mn) { if (p.b_mn) le = launch_pdl(gemm_kernel<EP, true, true>, dim3(grid), dim3(192), smem, st, ma, mb, p, ep); else le = launch_pdl(gemm_kernel<EP, true, false>, dim3(grid), dim3(192), smem, st, ma, mb, p, ep); }
+  else { if (p.b_mn) le = launch_pdl(gemm_kernel<EP, false, true>, dim3(grid), dim3(192), smem, st, ma, mb, p, ep); else le = launch_pdl(gemm_kernel<EP, false, false>, dim3(grid), dim3(192), smem, st, ma, mb, p, ep); }
   B200_CUDA(le);
   B200_LAUNCH_CHECK();
   return 0;

@@ -72,6 +72,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
 
   if (warp == 0) {
     // ---- TMA producer: warp-uniform loop, one elected lane issues
@@ -222,7 +223,7 @@ static int conv_wgrad(const bf16* x, int x_pitch, int x_coff, int Ci, const bf16
   size_t smem = (size_t)p.stages * a_stage + 2 * (size_t)b_bytes + 1024 + 256;
   static bool attr_done = false;
   if (!attr_done) { B200_CUDA(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr_done = true; }
-  wgrad_kernel<<<p.n_groups * p.vsplit, 192, smem, st>>>(mx, mdy, p);
+  B200_CUDA(launch_pdl(wgrad_kernel, dim3(p.n_groups * p.vsplit), dim3(192), smem, st, mx, mdy, p));
   B200_LAUNCH_CHECK();
   return 0;
 }

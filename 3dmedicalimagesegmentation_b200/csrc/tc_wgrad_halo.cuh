@@ -53,6 +53,7 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
 
   if (warp == 0) {
     // ---- TMA producer
@@ -155,7 +156,7 @@ template <int CI>
 static int wgrad_halo_launch(const CUtensorMap& mx, const CUtensorMap& mdy, const WgradHaloParams& p, int grid, size_t smem, cudaStream_t st) {
   static bool attr_done = false;
   if (!attr_done) { B200_CUDA(cudaFuncSetAttribute(wgrad_halo_kernel<CI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr_done = true; }
-  wgrad_halo_kernel<CI><<<grid, 192, smem, st>>>(mx, mdy, p);
+  B200_CUDA(launch_pdl(wgrad_halo_kernel<CI>, dim3(grid), dim3(192), smem, st, mx, mdy, p));
   B200_LAUNCH_CHECK();
   return 0;
 }

@@ -81,3 +81,33 @@ def test_conv_wgrad(pkg, Ci, Co, ks, dims):
     torch.cuda.synchronize()
     err = ((dW.cpu() - want).abs().max() / want.abs().max()).item()
     assert err <= 1e-3, err
+
+
+@pytest.mark.parametrize("op", [1, 2, 4])
+@pytest.mark.parametrize("Ci,Co", [(16, 16), (32, 16), (16, 32)])
+def test_conv_halo_multi_plane_tiles(pkg, monkeypatch, op, Ci, Co):
+    """The halo kernel computes `op` output d-planes per tile from op+2 halo planes (full-resolution layers use op = 4);
+    forward with statistics and dgrad+accumulate must not depend on op."""
+    monkeypatch.setenv("B200_HALO_MIN_TILES", "1")
+    monkeypatch.setenv("B200_HALO_OP", str(op))
+    g = torch.Generator().manual_seed(op * 100 + Ci + Co)
+    N, dims = 2, (8, 20, 24)
+    x = torch.randn(N, Ci, *dims, generator=g).to(torch.bfloat16)
+    w = torch.randn(Co, Ci, 3, 3, 3, generator=g) / (Ci * 27) ** 0.5
+    want = F.conv3d(x.float(), w.to(torch.bfloat16).float(), padding=1)
+    x_cl = x.permute(0, 2, 3, 4, 1).contiguous().to(DEV)
+    out = torch.zeros(N, *dims, Co, dtype=torch.bfloat16, device=DEV)
+    stats = torch.zeros(N, Co, 2, dtype=torch.float64, device=DEV)
+    run_conv(pkg, x_cl, 0, Ci, w.to(DEV), Co, 3, out, 0, 0, 0, stats)
+    got = out.float().permute(0, 4, 1, 2, 3).cpu()
+    assert ((got - want).abs().max() / want.abs().max()).item() <= 2 ** -7
+    assert torch.allclose(stats.cpu()[..., 1], want.double().square().sum((2, 3, 4)), rtol=1e-3)
+    # dgrad (input has Co channels, output Ci) accumulating onto a base tensor
+    dy = torch.randn(N, Co, *dims, generator=g).to(torch.bfloat16)
+    want_d = F.conv_transpose3d(dy.float(), w.to(torch.bfloat16).float(), padding=1)
+    base = torch.randn(N, *dims, Ci, generator=g).to(torch.bfloat16)
+    dx = base.clone().to(DEV)
+    run_conv(pkg, dy.permute(0, 2, 3, 4, 1).contiguous().to(DEV), 0, Ci, w.to(DEV), Co, 3, dx, 0, 1, 1, None)
+    want_d = want_d + base.float().permute(0, 4, 1, 2, 3)
+    got_d = dx.float().permute(0, 4, 1, 2, 3).cpu()
+    assert ((got_d - want_d).abs().max() / want_d.abs().max()).item() <= 2 ** -7

@@ -35,6 +35,7 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "prof":
         run(int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]), modes=(0,), stamps=False)
     else:
-        run(16, 16, 96, modes=(0,))
-        run(32, 16, 96, modes=(0,))
-        run(64, 32, 48, modes=(0,))
+        os.environ["B200_HALO_OP"] = "4"
+        run(16, 16, 96, modes=(0, 64, 80), stamps=False)
+        run(32, 16, 96, modes=(0, 64), stamps=False)
+        run(64, 32, 48, modes=(0, 64), stamps=False)
