@@ -65,7 +65,8 @@ struct Workspace {
   // decoder
   T *xcl, *c1tmp, *e2a, *e2b, *e3a, *cat5, *cat4, *cat3, *cat2, *d3, *d2, *d1, *d0;
   ResSave<T> rs[5];  // enc1, dec5, dec4, dec3, dec2
-  double* stat_acc;
+  double* stat_acc;      // current (sum, sumsq) accumulator pair: a fresh pre-zeroed slot of stat_pool per use (one memset per forward)
+  double* stat_pool; int stat_next;
   // bf16 mode only: packed bf16 copies of the GEMM weights (refreshed every forward), same layouts as the fp32 masters
   bf16 *wqkv[12], *wproj[12], *wfc1[12], *wfc2[12], *wT[10];
   bf16 *wcf[15], *wcd[15];
@@ -75,13 +76,17 @@ struct Workspace {
   float* part;   // split-K partial tiles [<=4][M][H] (summed by the LayerNorm kernel that consumes the GEMM)
   T *dxb, *dx2b, *unsh;  // unsh: pixel-unshuffled dOut of a transposed conv [rows_in, 8*Co]  // bf16 mode: operand copies of the fp32 residual-stream gradients
   T *dvit, *dh, *dln, *datt, *dqkv, *dS, *gA, *dcat, *dc2, *dc3, *da1, *dc1;
-  double* bwd_acc;
+  double* bwd_acc;       // current backward-norm accumulator: a fresh pre-zeroed slot of bwd_pool per use (one memset per backward)
+  double* bwd_pool; int bwd_next;
   size_t bytes;
 };
 
 template <class T>
 struct Exec {
   typedef typename RawOf<T>::type TR;   // storage type of raw conv outputs (c1, c2, c3 of every residual block)
+  static constexpr int kStatSlots = 20, kBwdSlots = 12;   // >= accumulator uses per forward / backward (5 blocks x 3 / x 2)
+  int next_stat() { if (w.stat_next >= kStatSlots) { set_error("statistics slot pool exhausted"); return 1; } w.stat_acc = w.stat_pool + (size_t)(w.stat_next++) * 4 * c.B * 8 * c.fs; return 0; }
+  int next_bwd() { if (w.bwd_next >= kBwdSlots) { set_error("backward accumulator pool exhausted"); return 1; } w.bwd_acc = w.bwd_pool + (size_t)(w.bwd_next++) * 3 * c.B * 8 * c.fs; return 0; }
   UnetrConfig c;
   int g0, g1, g2, L, Lp, M, H, F, nh, dh;
   long V[5];  // voxels per sample at levels 0 (full) .. 4 (tokens)
@@ -108,6 +113,36 @@ struct Exec {
     if (!cur_params) return -1;
     for (int i = 0; i < 15; ++i) { int p, ci, co, ks; conv_desc(i, p, ci, co, ks); if (cur_params[p] == W) return i; }
     return -1;
+  }
+  // element count of the conv-side parameters (indices P_E1_C1 .. P_OUT_B), 0 for others
+  size_t conv_param_elems(int pidx) const {
+    for (int i = 0; i < 15; ++i) { int p, ci, co, ks; conv_desc(i, p, ci, co, ks); if (p == pidx) return (size_t)ci * co * ks * ks * ks; }
+    for (int i = 0; i < 10; ++i) { int p, ci, co; convT_desc(i, p, ci, co); if (p == pidx) return (size_t)ci * co * 8; }
+    if (pidx == P_OUT_W) return (size_t)c.ncls * c.fs;
+    if (pidx == P_OUT_B) return (size_t)c.ncls;
+    return 0;
+  }
+  // All atomically accumulated weight gradients (convs, transposed convs, head) are zeroed by ONE memset when they are
+  // consecutive slices of one buffer (the Python host hands out views of a flat gradient buffer); otherwise per tensor.
+  bool grads_prezeroed = false;
+  int prezero_conv_grads(float* const* G, cudaStream_t st) {
+    grads_prezeroed = false;
+    float* lo = nullptr; float* expect = nullptr; size_t total = 0;
+    for (int i = P_E1_C1; i < P_COUNT; ++i) {
+      if (!G[i]) continue;
+      size_t n = conv_param_elems(i);
+      if (!lo) { lo = G[i]; expect = lo; }
+      if (G[i] != expect) return 0;          // not contiguous: the per-tensor memsets stay in charge
+      expect = G[i] + n; total += n;
+    }
+    if (!lo) return 0;
+    B200_CUDA(cudaMemsetAsync(lo, 0, sizeof(float) * total, st));
+    grads_prezeroed = true;
+    return 0;
+  }
+  int zero_grad(float* p, size_t n, cudaStream_t st) {
+    if (!grads_prezeroed) B200_CUDA(cudaMemsetAsync(p, 0, sizeof(float) * n, st));
+    return 0;
   }
   size_t convT_elems(int i) const { int p, ci, co; convT_desc(i, p, ci, co); return (size_t)ci * co * 8; }
   const bf16* convT_packed(const float* const* P, const float* W, bool tap_major = false) const {
@@ -151,7 +186,8 @@ struct Exec {
       w.rs[i].a1 = b.take<T>(n); w.rs[i].c2 = b.take<T>(n); w.rs[i].c3 = b.take<T>(n);
       w.rs[i].mr1 = b.take<float>(2 * B * co[i]); w.rs[i].mr2 = b.take<float>(2 * B * co[i]); w.rs[i].mr3 = b.take<float>(2 * B * co[i]);
     }
-    w.stat_acc = b.take<double>((size_t)4 * B * 8 * fs);   // two (sum, sumsq) accumulators
+    w.stat_pool = b.take<double>((size_t)kStatSlots * 4 * B * 8 * fs);   // slots of two (sum, sumsq) accumulators
+    w.stat_acc = w.stat_pool; w.stat_next = 0;
     if (kTC) {
       for (int i = 0; i < 12; ++i) {
         w.wqkv[i] = b.take<bf16>((size_t)3 * H * H); w.wproj[i] = b.take<bf16>((size_t)H * H);
@@ -170,7 +206,8 @@ struct Exec {
       size_t big = (size_t)B * V[0] * fs;
       w.gA = b.take<T>(big); w.dcat = b.take<T>(2 * big); w.dc2 = b.take<T>(big); w.dc3 = b.take<T>(big);
       w.da1 = b.take<T>(big); w.dc1 = b.take<T>(big); w.unsh = b.take<T>(big);
-      w.bwd_acc = b.take<double>((size_t)3 * B * 8 * fs);
+      w.bwd_pool = b.take<double>((size_t)kBwdSlots * 3 * B * 8 * fs);
+      w.bwd_acc = w.bwd_pool; w.bwd_next = 0;
     }
     w.bytes = (b.off + 255) & ~(size_t)255;
   }
@@ -272,7 +309,7 @@ struct Exec {
     constexpr int VN = Vec16<T>::N;
     B200_CHECK(x.C % VN == 0 && 256 % (x.C / VN) == 0 && x.pitch % VN == 0 && x.coff % VN == 0,
                "InstanceNorm channel count %d unsupported (need a power of two >= 8)", x.C);
-    B200_CUDA(cudaMemsetAsync(w.stat_acc, 0, sizeof(double) * 2 * c.B * x.C, st));
+    B200_TRY(next_stat());
     dim3 g(in_grid_x(Vs, x.C / VN), c.B);
     B200_CUDA(launch_pdl(in_stats_kernel<T>, dim3(g), dim3(256), 256 * 2 * VN * sizeof(float), st, reinterpret_cast<const TR*>(x.p), ClView{x.pitch, x.coff}, x.C, Vs, w.stat_acc));
     B200_LAUNCH_CHECK();
@@ -298,7 +335,7 @@ struct Exec {
       int ci = conv_index(W);
       if (ci >= 0 && tc::conv_supported(x.C, Co, x.pitch, x.coff, out.pitch, out.coff)) {
         B200_PROFD(st, "conv_fwd k%d %d->%d @%d", ks, x.C, Co, s.D);
-        if (stats) { B200_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * c.B * Co, st)); if (stats_done) *stats_done = true; }
+        if (stats) { B200_TRY(next_stat()); stats = w.stat_acc; if (stats_done) *stats_done = true; }
         if (ks == 3 && tc::conv_halo_supported(x.C, Co))
           return tc::conv_halo(x.p, x.pitch, x.coff, x.C, s.N, s.D, s.H, s.W, w.wcf[ci], Co, out.p, out.pitch, out.coff, 0, stats, st, nullptr, 1);
         return tc::conv(x.p, x.pitch, x.coff, x.C, s.N, s.D, s.H, s.W, w.wcf[ci], Co, ks, out.p, out.pitch, out.coff, 0, stats, st, 1);
@@ -341,9 +378,9 @@ struct Exec {
     Cl<T> c1 = cl(w.c1tmp, Co, 0, Co), a1 = cl(r.a1, Co, 0, Co), c2 = cl(r.c2, Co, 0, Co), c3 = cl(r.c3, Co, 0, Co);
     bool done = false;
     if (raw) {
+      B200_TRY(next_stat());
       double* st3 = w.stat_acc + (size_t)2 * c.B * 8 * c.fs;
       { B200_PROF("enc1_conv_fwd", st);
-        B200_CUDA(cudaMemsetAsync(w.stat_acc, 0, sizeof(double) * 4 * c.B * 8 * c.fs, st));
         dim3 g((unsigned)min(148L * 4, (Vs + 255) / 256), c.B);
         size_t sm = sizeof(float) * ((size_t)c.Cin * 27 * Co + (size_t)c.Cin * Co);
         if (Co == 8) conv_in_fwd_kernel<T, 8><<<g, 256, sm, st>>>(raw, W1, W3, c.Cin, s.D, s.H, s.W, (TR*)c1.p, (TR*)c3.p, w.stat_acc, st3);
@@ -364,8 +401,8 @@ struct Exec {
       int i1 = conv_index(W1), i3 = conv_index(W3);
       if (i1 >= 0 && i3 >= 0 && tc::conv_supported(x.C, Co, x.pitch, x.coff, Co, 0) && tc::conv_halo_fused_supported(x.C, Co, 1)) {
         B200_PROFD(st, "conv_fwd k3+k1 %d->%d @%d", x.C, Co, s.D);
+        B200_TRY(next_stat());
         double* st3 = w.stat_acc + (size_t)2 * c.B * 8 * c.fs;
-        B200_CUDA(cudaMemsetAsync(w.stat_acc, 0, sizeof(double) * 4 * c.B * 8 * c.fs, st));
         tc::HaloFused fu = {1, w.wcf[i3], c3.p, Co, 0, st3, nullptr, 0, 0};
         B200_TRY(tc::conv_halo(x.p, x.pitch, x.coff, x.C, s.N, s.D, s.H, s.W, w.wcf[i1], Co, c1.p, Co, 0, 0, w.stat_acc, st, &fu, 1));
         B200_CUDA(launch_pdl(in_finalize_kernel, dim3(cdiv(c.B * Co, 128)), dim3(128), 0, st, w.stat_acc, r.mr1, c.B * Co, 1.0 / (double)Vs)); B200_LAUNCH_CHECK();
@@ -407,7 +444,7 @@ struct Exec {
     dim3 gr(in_grid_x(Vs, Co / VN), B), ga(in_grid_x(Vs, Co / VN) * 2, B);
     // final lrelu + two norms
     { B200_PROF("instnorm_bwd", st);
-    B200_CUDA(cudaMemsetAsync(w.bwd_acc, 0, sizeof(double) * 3 * B * Co, st));
+    B200_TRY(next_bwd());
     B200_CUDA(launch_pdl(in_bwd_reduce_kernel<T, true>, dim3(gr), dim3(256), red_smem, st, dOut.p, ClView{dOut.pitch, dOut.coff}, out.p, ClView{out.pitch, out.coff},
                                                       (const TR*)r.c2, pv, (const TR*)r.c3, pv, Co, Vs, w.bwd_acc));
     B200_LAUNCH_CHECK();
@@ -418,11 +455,11 @@ struct Exec {
     B200_LAUNCH_CHECK(); }
     Cl<const T> dc2 = cl<const T>(w.dc2, Co, 0, Co), dc3 = cl<const T>(w.dc3, Co, 0, Co), a1 = cl<const T>(r.a1, Co, 0, Co);
     // conv2
-    if (dW2) { B200_CUDA(cudaMemsetAsync(dW2, 0, sizeof(float) * Co * Co * 27, st)); B200_TRY(conv_wgrad(a1, dc2, s, 3, dW2, st)); }
+    if (dW2) { B200_TRY(zero_grad(dW2, (size_t)Co * Co * 27, st)); B200_TRY(conv_wgrad(a1, dc2, s, 3, dW2, st)); }
     B200_TRY(conv_dgrad(dc2, s, W2, Co, 3, cl(w.da1, Co, 0, Co), 0, st));
     // lrelu + norm1
     { B200_PROF("instnorm_bwd", st);
-    B200_CUDA(cudaMemsetAsync(w.bwd_acc, 0, sizeof(double) * 3 * B * Co, st));
+    B200_TRY(next_bwd());
     B200_CUDA(launch_pdl(in_bwd_reduce_kernel<T, false>, dim3(gr), dim3(256), red_smem, st, w.da1, pv, r.a1, pv, (const TR*)nullptr, pv, (const TR*)nullptr, pv, Co, Vs, w.bwd_acc));
     B200_LAUNCH_CHECK();
     B200_CUDA(launch_pdl(in_bwd_apply_kernel<T, false>, dim3(ga), dim3(256), cst_smem, st, w.da1, pv, r.a1, pv, (const TR*)nullptr, pv, r.mr1, (const TR*)nullptr, pv, nullptr, Co, Vs, w.bwd_acc,
@@ -432,8 +469,8 @@ struct Exec {
     if (raw) {   // encoder1: both weight gradients from the raw fp32 input in one dedicated kernel
       B200_PROF("enc1_conv_wgrad", st);
       B200_CHECK(dW1 && dW3, "encoder1 weight gradients are produced together");
-      B200_CUDA(cudaMemsetAsync(dW1, 0, sizeof(float) * Co * Ci * 27, st));
-      B200_CUDA(cudaMemsetAsync(dW3, 0, sizeof(float) * Co * Ci, st));
+      B200_TRY(zero_grad(dW1, (size_t)Co * Ci * 27, st));
+      B200_TRY(zero_grad(dW3, (size_t)Co * Ci, st));
       long chunk = 4096;
       dim3 g((unsigned)((Vs + chunk - 1) / chunk), B, Ci);
       if (Co == 8) conv_in_wgrad_kernel<T, 8><<<g, 256, 0, st>>>(raw, w.dc1, w.dc3, Ci, s.D, s.H, s.W, chunk, dW1, dW3);
@@ -442,8 +479,8 @@ struct Exec {
       B200_LAUNCH_CHECK();
       return 0;
     }
-    if (dW1) { B200_CUDA(cudaMemsetAsync(dW1, 0, sizeof(float) * Co * Ci * 27, st)); B200_TRY(conv_wgrad(x, dc1, s, 3, dW1, st)); }
-    if (dW3) { B200_CUDA(cudaMemsetAsync(dW3, 0, sizeof(float) * Co * Ci, st)); B200_TRY(conv_wgrad(x, dc3, s, 1, dW3, st)); }
+    if (dW1) { B200_TRY(zero_grad(dW1, (size_t)Co * Ci * 27, st)); B200_TRY(conv_wgrad(x, dc1, s, 3, dW1, st)); }
+    if (dW3) { B200_TRY(zero_grad(dW3, (size_t)Co * Ci, st)); B200_TRY(conv_wgrad(x, dc3, s, 1, dW3, st)); }
     if (dx.p) {
       if constexpr (kTC) {   // dx = dgrad3x3(dc1) + dgrad1x1(dc3) in one kernel (second input tile, same accumulator)
         int i1 = conv_index(W1), i3 = conv_index(W3);
@@ -462,6 +499,7 @@ struct Exec {
   // ------------------------------------------------------------ forward
   int forward(const float* const* P, const float* x_in, char* ws, float* enc4_out, float* logits_out, int flags, cudaStream_t st) {
     layout(ws, false);
+    B200_CUDA(cudaMemsetAsync(w.stat_pool, 0, sizeof(double) * kStatSlots * 4 * c.B * 8 * c.fs, st));
     B200_PROFC_BEGIN("F1 pack+patch", st);
     int B = c.B, fs = c.fs;
     if (!(flags & FLAG_WEIGHTS_PACKED)) B200_TRY(pack_weights(P, st));
@@ -626,7 +664,9 @@ struct Exec {
     bool enc = (flags & FLAG_NEED_ENCODER_GRAD) != 0;
     bool has_denc4 = (flags & FLAG_HAS_DENC4) && d_enc4;
     bool vit_from_top = false;  // does gradient reach blocks 10, 11 and the final LayerNorm?
-    for (int k = 0; k < 3; ++k) B200_CUDA(cudaMemsetAsync(w.dhs[k], 0, sizeof(float) * M * H, st));
+    B200_CUDA(cudaMemsetAsync(w.dhs[0], 0, (size_t)((char*)(w.dhs[2] + (size_t)M * H) - (char*)w.dhs[0]), st));   // dhs[0..2] are consecutive
+    B200_CUDA(cudaMemsetAsync(w.bwd_pool, 0, sizeof(double) * kBwdSlots * 3 * c.B * 8 * c.fs, st));
+    B200_TRY(prezero_conv_grads(G, st));
     B200_PROFC_BEGIN("B1 head+decoders+encoders", st);
 
     if (dec) {
@@ -634,8 +674,8 @@ struct Exec {
       // head: d(d0) = dlogits^T W ; dW = dlogits d0 ; db = sum dlogits
       if (edge_co_ok(fs)) {
         B200_PROF("head_bwd", st);
-        if (G[P_OUT_W]) B200_CUDA(cudaMemsetAsync(G[P_OUT_W], 0, sizeof(float) * c.ncls * fs, st));
-        if (G[P_OUT_B]) B200_CUDA(cudaMemsetAsync(G[P_OUT_B], 0, sizeof(float) * c.ncls, st));
+        if (G[P_OUT_W]) B200_TRY(zero_grad(G[P_OUT_W], (size_t)c.ncls * fs, st));
+        if (G[P_OUT_B]) B200_TRY(zero_grad(G[P_OUT_B], (size_t)c.ncls, st));
         long chunk = 2048;
         dim3 g((unsigned)((V[0] + chunk - 1) / chunk), B);
         size_t sm = head_bwd_smem(c.ncls, fs);
@@ -661,13 +701,13 @@ struct Exec {
       { RowIsOuter<NcdhwGather, true> al; al.g = {d_logits, c.ncls, V[0]};
         B200_TRY(launch_contract(al, ld2<float, true>(P[P_OUT_W], 1, fs), ep_plain<T>(w.gA, fs), rows, fs, c.ncls, 1, 1, st)); }
       if (G[P_OUT_W]) {
-        B200_CUDA(cudaMemsetAsync(G[P_OUT_W], 0, sizeof(float) * c.ncls * fs, st));
+        B200_TRY(zero_grad(G[P_OUT_W], (size_t)c.ncls * fs, st));
         RowIsK<NcdhwGather, false> al; al.g = {d_logits, c.ncls, V[0]};
         EpAtomic ep = {G[P_OUT_W], (long)fs};
         B200_TRY(launch_contract(al, ld2<T, true>(w.d0, 1, fs), ep, c.ncls, fs, rows, 1, pick_splits(rows, 1), st));
       }
       if (G[P_OUT_B]) {
-        B200_CUDA(cudaMemsetAsync(G[P_OUT_B], 0, sizeof(float) * c.ncls, st));
+        B200_TRY(zero_grad(G[P_OUT_B], (size_t)c.ncls, st));
         rowsum_atomic_kernel<<<dim3(32, B * c.ncls), 256, 0, st>>>(d_logits, G[P_OUT_B], V[0], c.ncls);
         B200_LAUNCH_CHECK();
       }
@@ -806,7 +846,7 @@ struct Exec {
           B200_LAUNCH_CHECK(); }
         if (dW) {   // dW[ci][co*8+tap] = sum_v x[v,ci] U[v, tap*Co+co]   (voxels = reduction, split-K + atomics)
           B200_PROFD(st, "convT_wgrad %dx%d @%d", Ci, Co, s.D);
-          B200_CUDA(cudaMemsetAsync(dW, 0, sizeof(float) * Ci * K8, st));
+          B200_TRY(zero_grad(dW, (size_t)Ci * K8, st));
           EpAtomicTapRemap ep = {dW, Co};
           B200_TRY(tc::gemm(tc::operand(x, 1, ldx), tc::operand(w.unsh, 1, K8), ep, Ci, K8, rows, 1, 1, st, true));
         }
@@ -819,7 +859,7 @@ struct Exec {
       }
     }
     if (dW) {
-      B200_CUDA(cudaMemsetAsync(dW, 0, sizeof(float) * Ci * dy.C * 8, st));
+      B200_TRY(zero_grad(dW, (size_t)Ci * dy.C * 8, st));
       B200_TRY((simt_convT_wgrad<T, T>(x, ldx, Ci, dy, s, dW, st)));
     }
     if (dx) B200_TRY((simt_convT_dgrad<T, TO>(dy, s, W, Ci, dx, lddx, accumulate, st)));
