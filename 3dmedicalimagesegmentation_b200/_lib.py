@@ -59,9 +59,14 @@ SIGNATURES = {
     "b200_prof_report": (c_int, [ctypes.c_char_p, c_int]),
     "b200_test_tc_conv": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int,
                                   c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "b200_test_tc_conv_fused": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int,
+                                        c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "b200_test_tc_wgrad": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                    c_void_p, c_void_p]),
     "b200_test_set_debug_buffer": (None, [c_void_p]),
+    "b200_adamw_chunk": (ctypes.c_long, []),
+    "b200_adamw_step": (c_int, [c_void_p, c_void_p, c_int, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float,
+                                c_int, c_void_p]),
     "b200_unetr_set_grad_events": (None, [c_void_p, ctypes.POINTER(c_void_p), c_int]),
     "b200_trace_begin": (None, [c_void_p, c_int]),
     "b200_trace_count": (c_int, []),

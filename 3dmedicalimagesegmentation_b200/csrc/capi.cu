@@ -1,4 +1,5 @@
 // extern "C" surface of libunetr_b200.so (declared in include/unetr_b200.h).
+#include <math.h>
 #include <stdarg.h>
 
 #include <algorithm>
@@ -10,6 +11,7 @@
 #include "../../include/unetr_b200.h"
 #include "exec_iface.h"
 #include "elementwise.cuh"
+#include "adamw.cuh"
 #include "loss.cuh"
 #include "sliding.cuh"
 #include "tc_gemm.cuh"
@@ -113,6 +115,22 @@ void b200_unetr_set_grad_events(void* handle, void* const* events, int n) {
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   for (int i = 0; i < n && i < 4; ++i) ev[i] = (cudaEvent_t)events[i];
   h->ex->set_grad_events(ev, n);
+}
+
+// ---------------------------------------------------------------- fused AdamW
+/* tensors: device array of n_tensors {p, g, m, v, n}; chunks: device array of n_chunks {tensor, pad, start} covering every tensor in
+ * pieces of b200_adamw_chunk() elements; step >= 1 is the 1-based update count (bias correction). */
+long b200_adamw_chunk(void) { return kAdamChunk; }
+int b200_adamw_step(const void* tensors, const void* chunks, int n_chunks, float lr, float beta1, float beta2, float eps, float weight_decay,
+                    int step, void* stream) {
+  B200_CHECK(tensors && chunks && n_chunks > 0 && step >= 1, "b200_adamw_step: bad arguments");
+  AdamHyper h;
+  h.lr = lr; h.beta1 = beta1; h.beta2 = beta2; h.eps = eps; h.weight_decay = weight_decay;
+  h.bc1 = (float)(1.0 - pow((double)beta1, (double)step));
+  h.bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
+  adamw_kernel<<<n_chunks, 256, 0, (cudaStream_t)stream>>>((const AdamTensor*)tensors, (const AdamChunk*)chunks, h);
+  B200_LAUNCH_CHECK();
+  return 0;
 }
 
 // ---------------------------------------------------------------- DiceCE
@@ -278,6 +296,28 @@ int b200_test_tc_conv(const void* x, int in_pitch, int in_coff, int Ci, int N, i
   if (ks == 3 && !getenv("B200_TEST_NO_HALO") && tc::conv_halo_supported(Co, Ci))
     return tc::conv_halo((const bf16*)x, in_pitch, in_coff, Co, N, D, H, W, wd, Ci, (bf16*)out, out_pitch, out_coff, accumulate, stats, st);
   return tc::conv((const bf16*)x, in_pitch, in_coff, Co, N, D, H, W, wd, Ci, ks, (bf16*)out, out_pitch, out_coff, accumulate, stats, st);
+}
+
+/* Fused 3^3 + 1^3 convolution of the residual block (tc_conv_halo.cuh, HaloParams::mode2), dense channels-last bf16 tensors:
+ *  mode 1 (forward):  out = conv3(x; w3), out2 = conv1(x; w1), stats / stats2 = per-(n,c) sum and sum of squares   (x has Ci channels)
+ *  mode 2 (dgrad):    out = dgrad3(x; w3) + dgrad1(x2; w1)                                  (x, x2 have Co channels, out has Ci)
+ * w3 fp32 [Co][Ci][27], w1 fp32 [Co][Ci]; scratch: 2*Co*Ci*28 bf16 */
+int b200_test_tc_conv_fused(const void* x, const void* x2, int Ci, int Co, int N, int D, int H, int W, const float* w3, const float* w1, int mode,
+                            void* out, void* out2, double* stats, double* stats2, void* scratch, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  bf16* w3f = (bf16*)scratch; bf16* w3d = w3f + (size_t)Co * Ci * 27; bf16* w1f = w3d + (size_t)Co * Ci * 27; bf16* w1d = w1f + (size_t)Co * Ci;
+  pack_conv_weights_kernel<<<64, 256, 0, st>>>(w3, w3f, w3d, Co, Ci, 27);
+  B200_LAUNCH_CHECK();
+  pack_conv_weights_kernel<<<64, 256, 0, st>>>(w1, w1f, w1d, Co, Ci, 1);
+  B200_LAUNCH_CHECK();
+  if (mode == 1) {
+    B200_CHECK(tc::conv_halo_fused_supported(Ci, Co, 1), "fused forward unsupported for %d->%d", Ci, Co);
+    tc::HaloFused fu = {1, w1f, (bf16*)out2, Co, 0, stats2, nullptr, 0, 0};
+    return tc::conv_halo((const bf16*)x, Ci, 0, Ci, N, D, H, W, w3f, Co, (bf16*)out, Co, 0, 0, stats, st, &fu);
+  }
+  B200_CHECK(mode == 2 && tc::conv_halo_fused_supported(Co, Ci, 2), "fused dgrad unsupported for %d<-%d", Ci, Co);
+  tc::HaloFused fu = {2, w1d, nullptr, 0, 0, nullptr, (const bf16*)x2, Co, 0};
+  return tc::conv_halo((const bf16*)x, Co, 0, Co, N, D, H, W, w3d, Ci, (bf16*)out, Ci, 0, 0, nullptr, st, &fu);
 }
 
 /* dW fp32 [Co][Ci][ks^3] = sum_v dy[v,co] x[v+tap,ci]; x, dy channels-last bf16 windows */

@@ -109,6 +109,7 @@ def main():
     ap.add_argument("--batch", type=int, default=2, help="crops per GPU")
     ap.add_argument("--mode", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-optimizer", action="store_true")
+    ap.add_argument("--torch-adamw", action="store_true", help="use torch.optim.AdamW(fused=True) instead of the package's FusedAdamW")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--breakdown", action="store_true", help="print the per-op CUDA-event breakdown to stderr")
     ap.add_argument("--no-sliding-window", action="store_true", help="skip the configs[4] whole-CT sliding-window measurement")
@@ -140,7 +141,10 @@ def main():
     torch.manual_seed(0)
     model = pkg.MonaiUNETR(**MODEL_KW).to(dev).set_mode(args.mode)
     loss_fn = pkg.DiceCELoss(to_onehot_y=True, softmax=True)
-    opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=1e-5, fused=True)
+    if args.torch_adamw:
+        opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=1e-5, fused=True)
+    else:
+        opt = pkg.FusedAdamW(model.parameters(), lr=1e-4, weight_decay=1e-5)     # one launch
     ddp = par.GradientAllReduce(model, world) if world > 1 else None
     B = args.batch
     g = torch.Generator().manual_seed(100 + rank)

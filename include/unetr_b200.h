@@ -93,6 +93,14 @@ unsigned long long b200_launch_count(void);
 void b200_prof_enable(int on);
 int b200_prof_report(char* buf, int cap);
 
+/* ---- fused multi-tensor AdamW (stands behind torch.optim.AdamW: unetr_segmentation_3d.py:522,225-226;
+ *      unetr_ranking_pretraining_3d.py:466,214-215).  tensors: device array of {float* p; const float* g; float* m; float* v;
+ *      int64 n}; chunks: device array of {int32 tensor; int32 pad; int64 start}, each covering b200_adamw_chunk() elements.
+ *      Parameters without a gradient are left out of the table (their state does not move).  step is 1-based. */
+long b200_adamw_chunk(void);
+int b200_adamw_step(const void* tensors, const void* chunks, int n_chunks, float lr, float beta1, float beta2, float eps,
+                    float weight_decay, int step, void* stream);
+
 /* Optional gradient-ready events for data-parallel overlap: 4 cudaEvent_t handles recorded inside b200_unetr_backward when a
  * group of parameter gradients is final -- [0] conv encoders/decoders + head, [1] vit.norm + blocks 8..11, [2] blocks 4..7,
  * [3] blocks 0..3 + patch embedding.  n = 0 switches the recording off.  Only a full backward (logits gradient + trainable
@@ -105,6 +113,9 @@ void b200_unetr_set_grad_events(void* handle, void* const* events, int n);
 /* tcgen05 implicit-GEMM conv3d (k=1|3, same padding) on channels-last bf16; see csrc/capi.cu for the argument layout */
 int b200_test_tc_conv(const void* x, int in_pitch, int in_coff, int Ci, int N, int D, int H, int W, const float* w, int Co, int ks,
                       void* out, int out_pitch, int out_coff, int accumulate, int dgrad, double* stats, void* scratch, void* stream);
+/* fused 3^3 + 1^3 conv of the residual block: mode 1 = two outputs of one input (forward), 2 = two inputs of one output (dgrad) */
+int b200_test_tc_conv_fused(const void* x, const void* x2, int Ci, int Co, int N, int D, int H, int W, const float* w3, const float* w1, int mode,
+                            void* out, void* out2, double* stats, double* stats2, void* scratch, void* stream);
 int b200_test_tc_wgrad(const void* x, int x_pitch, int x_coff, int Ci, const void* dy, int dy_pitch, int dy_coff, int Co, int N, int D, int H,
                        int W, int ks, float* dW, void* stream);
 /* tuning aid: 16 x int64 device buffer receiving CTA-0 clock64 phase stamps of the next tcgen05 GEMM launches (NULL = off) */

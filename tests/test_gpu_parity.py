@@ -262,6 +262,34 @@ def test_inference_reuses_packed_weights_until_they_change(pkg):
     assert torch.equal(c, d)
 
 
+def test_fused_adamw_matches_torch(pkg):
+    """one-launch AdamW == torch.optim.AdamW (decoupled decay, bias correction), including parameters without a
+    gradient (state untouched), odd sizes and gradients that are unaligned views of a flat buffer."""
+    g = torch.Generator().manual_seed(0)
+    shapes = [(3, 5, 7), (1031,), (64, 64), (14,), (40000,), (2, 3)]
+    ref = [torch.nn.Parameter(torch.randn(*s, generator=g).to(DEV)) for s in shapes]
+    mine = [torch.nn.Parameter(p.detach().clone()) for p in ref]
+    kw = dict(lr=3e-3, betas=(0.9, 0.99), eps=1e-8, weight_decay=0.05)
+    o_ref, o_mine = torch.optim.AdamW(ref, **kw), pkg.FusedAdamW(mine, **kw)
+    for it in range(5):
+        flat = torch.randn(sum(p.numel() for p in ref) + 1, generator=g).to(DEV)
+        off = 1                                              # odd offset -> 4-byte aligned views only
+        for i, (a, b) in enumerate(zip(ref, mine)):
+            if i == 5 and it < 2:                            # a parameter that wakes up at the third step
+                a.grad = b.grad = None
+            else:
+                a.grad = flat[off:off + a.numel()].view_as(a).clone()
+                b.grad = flat[off:off + a.numel()].view_as(a)
+            off += a.numel()
+        o_ref.step(); o_mine.step()
+    for a, b in zip(ref, mine):
+        assert torch.allclose(a, b, rtol=2e-6, atol=2e-7), (a - b).abs().max()
+    assert o_mine.state[mine[5]]["step"] == 3 and o_mine.state[mine[0]]["step"] == 5
+    v0 = mine[0]._version
+    o_mine.step()
+    assert mine[0]._version > v0          # in-place update is visible to version-keyed caches (UNETR inference workspace)
+
+
 # ------------------------------------------------------------------------------------------- losses
 def test_dicece_matches_oracle_and_closed_form(pkg):
     g = torch.Generator().manual_seed(0)

@@ -111,3 +111,44 @@ def test_conv_halo_multi_plane_tiles(pkg, monkeypatch, op, Ci, Co):
     want_d = want_d + base.float().permute(0, 4, 1, 2, 3)
     got_d = dx.float().permute(0, 4, 1, 2, 3).cpu()
     assert ((got_d - want_d).abs().max() / want_d.abs().max()).item() <= 2 ** -7
+
+
+@pytest.mark.parametrize("op", [1, 4])
+@pytest.mark.parametrize("Ci,Co", [(32, 16), (64, 32), (16, 16)])
+def test_conv_halo_fused_1x1(pkg, monkeypatch, op, Ci, Co):
+    """Residual block fusion: forward conv3(x) and conv1(x) in one launch (two accumulators, two statistic sets); dgrad
+    dgrad3(dc1) + dgrad1(dc3) in one launch (second input tile, one accumulator)."""
+    monkeypatch.setenv("B200_HALO_MIN_TILES", "1")
+    monkeypatch.setenv("B200_HALO_OP", str(op))
+    lib = pkg._lib.load(); L = pkg._lib
+    g = torch.Generator().manual_seed(op + Ci * 3 + Co)
+    N, dims = 2, (8, 20, 24)
+    x = torch.randn(N, Ci, *dims, generator=g).to(torch.bfloat16)
+    w3 = torch.randn(Co, Ci, 3, 3, 3, generator=g) / (Ci * 27) ** 0.5
+    w1 = torch.randn(Co, Ci, 1, 1, 1, generator=g) / Ci ** 0.5
+    scratch = torch.empty(2 * Co * Ci * 28, dtype=torch.bfloat16, device=DEV)
+    w3_d, w1_d = w3.to(DEV), w1.to(DEV)      # keep the device copies alive across the asynchronous launches
+    cl = lambda t: t.permute(0, 2, 3, 4, 1).contiguous().to(DEV)
+    ncdhw = lambda t: t.float().permute(0, 4, 1, 2, 3).cpu()
+    # forward
+    out = torch.zeros(N, *dims, Co, dtype=torch.bfloat16, device=DEV); out2 = torch.zeros_like(out)
+    st1 = torch.zeros(N, Co, 2, dtype=torch.float64, device=DEV); st2 = torch.zeros_like(st1)
+    xc = cl(x)
+    L.check(lib.b200_test_tc_conv_fused(L.ptr(xc), None, Ci, Co, N, *dims, L.ptr(w3_d), L.ptr(w1_d), 1, L.ptr(out), L.ptr(out2),
+                                        L.ptr(st1), L.ptr(st2), L.ptr(scratch), L.stream_ptr()), "fused fwd")
+    torch.cuda.synchronize()
+    want3 = F.conv3d(x.float(), w3.to(torch.bfloat16).float(), padding=1)
+    want1 = F.conv3d(x.float(), w1.to(torch.bfloat16).float())
+    assert ((ncdhw(out) - want3).abs().max() / want3.abs().max()).item() <= 2 ** -7
+    assert ((ncdhw(out2) - want1).abs().max() / want1.abs().max()).item() <= 2 ** -7
+    assert torch.allclose(st1.cpu()[..., 1], want3.double().square().sum((2, 3, 4)), rtol=1e-3)
+    assert torch.allclose(st2.cpu()[..., 0], want1.double().sum((2, 3, 4)), rtol=1e-3, atol=1e-2 * want1.abs().max().item())
+    # dgrad
+    d1 = torch.randn(N, Co, *dims, generator=g).to(torch.bfloat16); d3 = torch.randn(N, Co, *dims, generator=g).to(torch.bfloat16)
+    dx = torch.zeros(N, *dims, Ci, dtype=torch.bfloat16, device=DEV)
+    d1c, d3c = cl(d1), cl(d3)
+    L.check(lib.b200_test_tc_conv_fused(L.ptr(d1c), L.ptr(d3c), Ci, Co, N, *dims, L.ptr(w3_d), L.ptr(w1_d), 2, L.ptr(dx), None,
+                                        None, None, L.ptr(scratch), L.stream_ptr()), "fused dgrad")
+    torch.cuda.synchronize()
+    want = F.conv_transpose3d(d1.float(), w3.to(torch.bfloat16).float(), padding=1) + F.conv_transpose3d(d3.float(), w1.to(torch.bfloat16).float())
+    assert ((ncdhw(dx) - want).abs().max() / want.abs().max()).item() <= 2 ** -7
