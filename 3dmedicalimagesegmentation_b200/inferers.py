@@ -9,6 +9,7 @@ from __future__ import annotations
 
 import ctypes
 import math
+import os
 from typing import Callable, List, Sequence, Tuple
 
 import torch
@@ -77,6 +78,24 @@ def sliding_window_inference(inputs: torch.Tensor, roi_size, sw_batch_size: int,
     sw_batch_size = max(1, min(int(sw_batch_size), 16))
     acc = None
     gout = None
+    # our own UNETR replays its forward as one CUDA graph inside this loop (each prediction is accumulated at once, so the
+    # graph's static output buffers may be overwritten by the next call); B200_NO_GRAPH=1 keeps the eager launches
+    use_graph = hasattr(predictor, "_graph_forward") and not getattr(predictor, "tuple_output", True) and \
+        not torch.is_grad_enabled() and not os.environ.get("B200_NO_GRAPH") and len(mine) >= 4 * sw_batch_size
+    prev_graph = getattr(predictor, "inference_graph", False)
+    if use_graph:
+        predictor.inference_graph = True
+    try:
+        acc, gout = _sw_loop(lib, x, items, mine, sw_batch_size, chan, roi, gin, cval, st, predictor, args, kwargs, batch, size, orig, pad)
+    finally:
+        if use_graph:
+            predictor.inference_graph = prev_graph
+    return _sw_finish(lib, acc, gout, world_size, process_group, batch, orig, per_axis, return_argmax, x, st)
+
+
+def _sw_loop(lib, x, items, mine, sw_batch_size, chan, roi, gin, cval, st, predictor, args, kwargs, batch, size, orig, pad):
+    acc = None
+    gout = None
     for g0 in range(mine.start, mine.stop, sw_batch_size):
         chunk = items[g0:min(g0 + sw_batch_size, mine.stop)]
         n = len(chunk)
@@ -94,6 +113,10 @@ def sliding_window_inference(inputs: torch.Tensor, roi_size, sw_batch_size: int,
         for k, it in enumerate(chunk):   # one launch per window: keeps the reference's summation order
             s4 = (ctypes.c_int32 * 4)(*it)
             _lib.check(lib.b200_sw_accumulate(_lib.ptr(acc), _lib.ptr(pred[k]), ctypes.byref(gout), s4, st), "b200_sw_accumulate")
+    return acc, gout
+
+
+def _sw_finish(lib, acc, gout, world_size, process_group, batch, orig, per_axis, return_argmax, x, st):
     if acc is None:
         raise RuntimeError("this rank owns no windows; use fewer ranks than windows")
     if world_size > 1:

@@ -109,7 +109,10 @@ class _UnetrFunction(torch.autograd.Function):
             ent = module._infer_ws.get(key)
             if ent is None:
                 ent = [torch.empty(lib.b200_unetr_workspace_bytes(handle, 0), dtype=torch.uint8, device=x.device), None]
-                module._infer_ws = {key: ent}      # one cached workspace at a time
+                if len(module._infer_ws) >= 3:     # a few batch sizes at most (sliding window: full chunks + one ragged tail)
+                    module._infer_ws.clear()
+                    module._graphs.clear()         # captured graphs point into the workspaces just dropped
+                module._infer_ws[key] = ent
             ws = ent[0]
             if ent[1] == vkey:
                 packed = _lib.FLAG_WEIGHTS_PACKED
@@ -250,6 +253,8 @@ class UNETR(nn.Module):
         self._handles = {}
         self._infer_ws = {}
         self._grad_events = None
+        self._graphs = {}
+        self.inference_graph = False       # see _graph_forward; switched on by sliding_window_inference for its loop
         self._grad_ready = None
         self.overlap_grad_reduce = False   # set by parallel.GradientAllReduce
         self._ordered = None
@@ -341,8 +346,43 @@ class UNETR(nn.Module):
         params = self._ordered_params()
         # grad mode is off inside Function.forward, so decide here whether the backward workspace is needed
         needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        if self.inference_graph and not needs_grad and x_in.is_cuda:
+            out = self._graph_forward(x_in, params)
+            if out is not None:
+                return out if self.tuple_output else out[1]
         enc4, logits = _UnetrFunction.apply(self, x_in, bool(freeze_encoder), needs_grad, *params)
         return (enc4, logits) if self.tuple_output else logits
+
+    # ---- inference through a captured CUDA graph ---------------------------------------------------------
+    def _graph_forward(self, x_in, params):
+        """Replays the whole forward (about 200 launches, ~2 ms of host work) as ONE graph launch.  Opt-in (`inference_graph`):
+        the returned tensors are the graph's static output buffers and are overwritten by the next call, which is what a
+        sliding-window loop wants (it accumulates each prediction at once) but not what arbitrary callers expect.  The graph is
+        rebuilt when the batch size or any parameter (storage, version) changes."""
+        key = (x_in.shape[0], self.compute_mode, x_in.device)
+        vkey = tuple((p.data_ptr(), p._version) for p in params)
+        ent = self._graphs.get(key)
+        try:
+            if ent is None or ent[0] != vkey:
+                static_x = x_in.detach().contiguous().float().clone()
+                with torch.no_grad():
+                    for _ in range(2):      # eager: allocates the cached workspace, packs the weights, then reuses them
+                        _UnetrFunction.apply(self, static_x, False, False, *params)
+                    torch.cuda.synchronize()
+                    graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(graph):
+                        enc4, logits = _UnetrFunction.apply(self, static_x, False, False, *params)
+                ent = (vkey, graph, static_x, enc4, logits, self._infer_ws[key][0])   # keeps the captured workspace alive
+                self._graphs[key] = ent
+            ent[2].copy_(x_in)
+            ent[1].replay()
+            return ent[3], ent[4]
+        except Exception as exc:      # capture not possible on this driver: fall back to eager launches for good
+            import warnings
+            warnings.warn(f"b200 UNETR: CUDA-graph inference disabled ({exc})")
+            self.inference_graph = False
+            self._graphs = {}
+            return None
 
 
 class MonaiUNETR(UNETR):
