@@ -87,6 +87,105 @@ __global__ void __launch_bounds__(256) conv_in_fwd_kernel(const float* __restric
   }
 }
 
+
+// Same contract as conv_in_fwd_kernel, restructured for occupancy and smem traffic: a thread owns TWO voxels adjacent in w and EIGHT
+// output channels (CO/8 threads per voxel pair), so a weight vector read from smem serves two voxels, accumulators + statistics fit
+// in ~100 registers (2 CTAs/SM instead of 1) and every voxel's channels leave as one 16-byte store per thread.  W must be even.
+template <class T, int CO>
+__global__ void __launch_bounds__(256, 2) conv_in_fwd2_kernel(const float* __restrict__ x, const float* __restrict__ W1, const float* __restrict__ W3,
+                                                              int Cin, int D, int H, int W, typename RawOf<T>::type* __restrict__ c1,
+                                                              typename RawOf<T>::type* __restrict__ c3, double* __restrict__ stats1, double* __restrict__ stats3) {
+  typedef typename RawOf<T>::type TR;
+  static_assert(Vec16<TR>::N == 8 || Vec16<TR>::N == 4, "8 channels per thread = one or two 16-byte stores");
+  constexpr int NCG = CO / 8;                 // channel groups = threads per voxel pair
+  extern __shared__ __align__(16) float sw2[];   // W1 as [ci][tap][CO], then W3 as [ci][CO]
+  __shared__ float red2[8][4 * CO];
+  const long V = (long)D * H * W;
+  const int n = blockIdx.y;
+  for (int i = threadIdx.x; i < Cin * 27 * CO; i += 256) { int co = i % CO, r = i / CO, tap = r % 27, ci = r / 27; sw2[i] = W1[((long)co * Cin + ci) * 27 + tap]; }
+  for (int i = threadIdx.x; i < Cin * CO; i += 256) { int co = i % CO, ci = i / CO; sw2[Cin * 27 * CO + i] = W3[(long)co * Cin + ci]; }
+  __syncthreads();
+  const float* w3 = sw2 + Cin * 27 * CO;
+  const int cg = threadIdx.x % NCG, c0 = cg * 8;
+  const int W2 = W >> 1;
+  const long npairs = V >> 1;
+  float s1[8], q1[8], s3[8], q3[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) s1[c] = q1[c] = s3[c] = q3[c] = 0.f;
+  for (long pi = (long)blockIdx.x * (256 / NCG) + threadIdx.x / NCG; pi < npairs; pi += (long)gridDim.x * (256 / NCG)) {
+    const int pv = (int)pi; const int w = (pv % W2) * 2, t = pv / W2, h = t % H, d = t / H;
+    float a1[2][8], a3[2][8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) a1[0][c] = a1[1][c] = a3[0][c] = a3[1][c] = 0.f;
+    for (int ci = 0; ci < Cin; ++ci) {
+      const float* xc = x + ((long)n * Cin + ci) * V;
+      const float* wc = sw2 + ci * 27 * CO + c0;
+#pragma unroll
+      for (int kd = 0; kd < 3; ++kd) {
+        const int dd = d + kd - 1;
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh) {
+          const int hh = h + kh - 1;
+          const bool ok = (unsigned)dd < (unsigned)D && (unsigned)hh < (unsigned)H;
+          const float* xr = xc + ((long)dd * H + hh) * W + w;       // only dereferenced when ok
+          float xv[4];
+          xv[0] = (ok && w > 0) ? xr[-1] : 0.f;
+          if (ok) { float2 m = *reinterpret_cast<const float2*>(xr); xv[1] = m.x; xv[2] = m.y; } else { xv[1] = xv[2] = 0.f; }
+          xv[3] = (ok && w + 2 < W) ? xr[2] : 0.f;
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw) {
+            const float* wt = wc + ((kd * 3 + kh) * 3 + kw) * CO;
+            const float4 wa = *reinterpret_cast<const float4*>(wt), wb = *reinterpret_cast<const float4*>(wt + 4);
+            const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+            for (int c = 0; c < 8; ++c) { a1[0][c] = fmaf(xv[kw], wv[c], a1[0][c]); a1[1][c] = fmaf(xv[kw + 1], wv[c], a1[1][c]); }
+          }
+          if (kd == 1 && kh == 1) {
+            const float4 wa = *reinterpret_cast<const float4*>(w3 + ci * CO + c0), wb = *reinterpret_cast<const float4*>(w3 + ci * CO + c0 + 4);
+            const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+            for (int c = 0; c < 8; ++c) { a3[0][c] = fmaf(xv[1], wv[c], a3[0][c]); a3[1][c] = fmaf(xv[2], wv[c], a3[1][c]); }
+          }
+        }
+      }
+    }
+    const long v = 2 * pi;
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      TR* o1 = c1 + ((long)n * V + v + e) * CO + c0; TR* o3 = c3 + ((long)n * V + v + e) * CO + c0;
+      constexpr int VN = Vec16<TR>::N;
+#pragma unroll
+      for (int q = 0; q < 8; q += VN) {
+        Vec16<TR> p, r;
+#pragma unroll
+        for (int i = 0; i < VN; ++i) { p.v[i] = a1[e][q + i]; r.v[i] = a3[e][q + i]; }
+        p.store(o1 + q); r.store(o3 + q);
+      }
+#pragma unroll
+      for (int c = 0; c < 8; ++c) { s1[c] += a1[e][c]; q1[c] = fmaf(a1[e][c], a1[e][c], q1[c]); s3[c] += a3[e][c]; q3[c] = fmaf(a3[e][c], a3[e][c], q3[c]); }
+    }
+  }
+  // reduce over the lanes that share a channel group (lane % NCG), then over the 8 warps
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    float a = s1[c], b = q1[c], e = s3[c], f = q3[c];
+    for (int o = NCG; o < 32; o <<= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o);
+      e += __shfl_xor_sync(0xffffffffu, e, o); f += __shfl_xor_sync(0xffffffffu, f, o);
+    }
+    if (lane < NCG) { red2[wp][c0 + c] = a; red2[wp][CO + c0 + c] = b; red2[wp][2 * CO + c0 + c] = e; red2[wp][3 * CO + c0 + c] = f; }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 4 * CO; i += 256) {
+    double tot = 0.0;
+    for (int k = 0; k < 8; ++k) tot += red2[k][i];
+    int which = i / CO, c = i % CO;
+    double* dst = (which < 2 ? stats1 : stats3) + ((long)n * CO + c) * 2 + (which & 1);
+    atomicAdd(dst, tot);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- encoder1 weight gradients
 // dW1[co][ci][tap] += sum_v dc1[v,co] x[ci,v+tap-1] ; dW3[co][ci] += sum_v dc3[v,co] x[ci,v]     (outputs zeroed by the caller)
 // grid (voxel chunks, N, Cin); 8 warps, warp w owns taps {w, w+8, w+16, w+24<27}; warp 7's 4th slot does the 1x1 conv3.

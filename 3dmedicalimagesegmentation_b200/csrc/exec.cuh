@@ -383,6 +383,12 @@ struct Exec {
       { B200_PROF("enc1_conv_fwd", st);
         dim3 g((unsigned)min(148L * 4, (Vs + 255) / 256), c.B);
         size_t sm = sizeof(float) * ((size_t)c.Cin * 27 * Co + (size_t)c.Cin * Co);
+        if (s.W % 2 == 0 && !getenv("B200_ENC1_V1")) {   // two voxels x eight channels per thread
+          dim3 g2((unsigned)min(148L * 8, (Vs / 2 * (Co / 8) + 255) / 256), c.B);
+          if (Co == 8) conv_in_fwd2_kernel<T, 8><<<g2, 256, sm, st>>>(raw, W1, W3, c.Cin, s.D, s.H, s.W, (TR*)c1.p, (TR*)c3.p, w.stat_acc, st3);
+          else if (Co == 16) conv_in_fwd2_kernel<T, 16><<<g2, 256, sm, st>>>(raw, W1, W3, c.Cin, s.D, s.H, s.W, (TR*)c1.p, (TR*)c3.p, w.stat_acc, st3);
+          else conv_in_fwd2_kernel<T, 32><<<g2, 256, sm, st>>>(raw, W1, W3, c.Cin, s.D, s.H, s.W, (TR*)c1.p, (TR*)c3.p, w.stat_acc, st3);
+        } else
         if (Co == 8) conv_in_fwd_kernel<T, 8><<<g, 256, sm, st>>>(raw, W1, W3, c.Cin, s.D, s.H, s.W, (TR*)c1.p, (TR*)c3.p, w.stat_acc, st3);
         else if (Co == 16) conv_in_fwd_kernel<T, 16><<<g, 256, sm, st>>>(raw, W1, W3, c.Cin, s.D, s.H, s.W, (TR*)c1.p, (TR*)c3.p, w.stat_acc, st3);
         else conv_in_fwd_kernel<T, 32><<<g, 256, sm, st>>>(raw, W1, W3, c.Cin, s.D, s.H, s.W, (TR*)c1.p, (TR*)c3.p, w.stat_acc, st3);
