@@ -186,6 +186,51 @@ template <class TO> static inline EpStore<TO> ep_plain(TO* out, long ld) {
   EpStore<TO> e; memset(&e, 0, sizeof(e)); e.out = out; e.ld = ld; e.nb1 = 1; e.alpha = 1.f; return e;
 }
 
+// Row-wise attention epilogues for tc::gemm (see row_op_of in tc_gemm.cuh).  Rows are [batch pair][m][ldw] of TP.
+template <class TP>
+struct EpSoftmaxRow {
+  static constexpr int kRowOp = 1;
+  TP* P; long sb0, sb1; int nb1; int ldw; float scale;
+  __device__ __forceinline__ void store16(int b, int m, int c0, const float* v, int nvalid) const {
+    TP* dst = P + (long)(b / nb1) * sb0 + (long)(b % nb1) * sb1 + (long)m * ldw + c0;
+    constexpr int VN = Vec16<TP>::N;
+    if (nvalid == 16 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+#pragma unroll
+      for (int q = 0; q < 16; q += VN) { Vec16<TP> t; for (int i = 0; i < VN; ++i) t.v[i] = v[q + i]; t.store(dst + q); }
+    } else {
+      for (int j = 0; j < nvalid; ++j) dst[j] = from_f<TP>(v[j]);
+    }
+  }
+  __device__ __forceinline__ void operator()(int, int, int, float) const {}
+};
+template <class TP>
+struct EpSoftmaxBwdRow {
+  static constexpr int kRowOp = 2;
+  const TP* Pin; TP* dS; long sb0, sb1; int nb1; int ldw; float scale;
+  __device__ __forceinline__ void load_p16(int b, int m, int c0, float* pr, int nvalid) const {
+    const TP* src = Pin + (long)(b / nb1) * sb0 + (long)(b % nb1) * sb1 + (long)m * ldw + c0;
+    constexpr int VN = Vec16<TP>::N;
+    if (nvalid == 16 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+#pragma unroll
+      for (int q = 0; q < 16; q += VN) { Vec16<TP> t; t.load(src + q); for (int i = 0; i < VN; ++i) pr[q + i] = t.v[i]; }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) pr[j] = j < nvalid ? to_f(src[j]) : 0.f;
+    }
+  }
+  __device__ __forceinline__ void store16(int b, int m, int c0, const float* v, int nvalid) const {
+    TP* dst = dS + (long)(b / nb1) * sb0 + (long)(b % nb1) * sb1 + (long)m * ldw + c0;
+    constexpr int VN = Vec16<TP>::N;
+    if (nvalid == 16 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+#pragma unroll
+      for (int q = 0; q < 16; q += VN) { Vec16<TP> t; for (int i = 0; i < VN; ++i) t.v[i] = v[q + i]; t.store(dst + q); }
+    } else {
+      for (int j = 0; j < nvalid; ++j) dst[j] = from_f<TP>(v[j]);
+    }
+  }
+  __device__ __forceinline__ void operator()(int, int, int, float) const {}
+};
+
 struct EpPatch {  // tokens = acc + bias + position embedding
   float* out; int H, L; const float* bias; const float* pos;
   __device__ __forceinline__ void operator()(int, int m, int n, float acc) const {

@@ -623,11 +623,23 @@ struct Exec {
     const T* qkv = w.qkv[i];
     long sQb = (long)L * 3 * H, sPb = (long)nh * L * Lp, sPh = (long)L * Lp;
     int BH = c.B * nh;
+    bool fused_sm = false;
+    if constexpr (kTC) {
+      // scores stay in TMEM: softmax in the QK^T epilogue.  Measured SLOWER at L = 216 (0.30 -> 0.38 ms per 12 layers): one 224-wide tile
+      // per (head, row block) leaves 48 CTAs with a serial two-pass epilogue; opt-in experiment only
+      if (L <= 256 && Lp <= 256 && getenv("B200_FUSED_SOFTMAX")) {
+        EpSoftmaxRow<T> ep = {w.P[i], sPb, sPh, nh, Lp, scale};
+        B200_TRY(tc::gemm(tc::operand(qkv, 3 * H, 1, sQb, dh), tc::operand(qkv + H, 3 * H, 1, sQb, dh), ep, L, L, dh, c.B, nh, st));
+        fused_sm = true;
+      }
+    }
+    if (!fused_sm) {
     { EpStore<float> ep = ep_plain<float>(w.S, Lp); ep.sb0 = sPb; ep.sb1 = sPh; ep.nb1 = nh;
       if constexpr (kTC) B200_TRY(tc::gemm(tc::operand(qkv, 3 * H, 1, sQb, dh), tc::operand(qkv + H, 3 * H, 1, sQb, dh), ep, L, L, dh, c.B, nh, st));
       else B200_TRY(launch_contract(ld4<T, false>(qkv, 3 * H, 1, sQb, dh, nh), ld4<T, false>(qkv + H, 3 * H, 1, sQb, dh, nh), ep, L, L, dh, BH, 1, st)); }
     B200_CUDA(launch_pdl(softmax_fwd_kernel<T>, dim3(cdiv((long)BH * L, 8)), dim3(256), 0, st, w.S, w.P[i], (long)BH * L, L, Lp, scale));
     B200_LAUNCH_CHECK();
+    }
     { EpStore<T> ep = ep_plain<T>(w.att[i], H); ep.sb0 = (long)L * H; ep.sb1 = dh; ep.nb1 = nh;
       if constexpr (kTC) B200_TRY(tc::gemm(tc::operand(w.P[i], Lp, 1, sPb, sPh), tc::operand(qkv + 2 * H, 1, 3 * H, sQb, dh), ep, L, dh, L, c.B, nh, st));
       else B200_TRY(launch_contract(ld4<T, false>(w.P[i], Lp, 1, sPb, sPh, nh), ld4<T, true>(qkv + 2 * H, 1, 3 * H, sQb, dh, nh), ep, L, dh, L, BH, 1, st)); }
@@ -639,16 +651,28 @@ struct Exec {
     const T* qkv = w.qkv[i];
     long sQb = (long)L * 3 * H, sPb = (long)nh * L * Lp, sPh = (long)L * Lp, sOb = (long)L * H;
     int BH = c.B * nh;
-    // dP = dO V^T
-    { EpStore<float> ep = ep_plain<float>(w.dP, Lp); ep.sb0 = sPb; ep.sb1 = sPh; ep.nb1 = nh;
+    // dP = dO V^T ; dS = P * (dP - rowsum(dP * P)) * scale  -- in the GEMM epilogue when a row fits one tile
+    bool fused_sm = false;
+    if constexpr (kTC) {
+      if (L <= 256 && Lp <= 256 && getenv("B200_FUSED_SOFTMAX")) {   // see attention_fwd: slower at L = 216, opt-in
+        EpSoftmaxBwdRow<T> ep = {w.P[i], w.dS, sPb, sPh, nh, Lp, scale};
+        B200_TRY(tc::gemm(tc::operand(w.datt, H, 1, sOb, dh), tc::operand(qkv + 2 * H, 3 * H, 1, sQb, dh), ep, L, L, dh, c.B, nh, st));
+        fused_sm = true;
+      }
+    }
+    if (!fused_sm) {
+      EpStore<float> ep = ep_plain<float>(w.dP, Lp); ep.sb0 = sPb; ep.sb1 = sPh; ep.nb1 = nh;
       if constexpr (kTC) B200_TRY(tc::gemm(tc::operand(w.datt, H, 1, sOb, dh), tc::operand(qkv + 2 * H, 3 * H, 1, sQb, dh), ep, L, L, dh, c.B, nh, st));
-      else B200_TRY(launch_contract(ld4<T, false>(w.datt, H, 1, sOb, dh, nh), ld4<T, false>(qkv + 2 * H, 3 * H, 1, sQb, dh, nh), ep, L, L, dh, BH, 1, st)); }
+      else B200_TRY(launch_contract(ld4<T, false>(w.datt, H, 1, sOb, dh, nh), ld4<T, false>(qkv + 2 * H, 3 * H, 1, sQb, dh, nh), ep, L, L, dh, BH, 1, st));
+    }
     // dV = P^T dO
     { EpStore<T> ep = ep_plain<T>(w.dqkv + 2 * H, 3 * H); ep.sb0 = sQb; ep.sb1 = dh; ep.nb1 = nh;
       if constexpr (kTC) B200_TRY(tc::gemm(tc::operand(w.P[i], 1, Lp, sPb, sPh), tc::operand(w.datt, 1, H, sOb, dh), ep, L, dh, L, c.B, nh, st));
       else B200_TRY(launch_contract(ld4<T, true>(w.P[i], 1, Lp, sPb, sPh, nh), ld4<T, true>(w.datt, 1, H, sOb, dh, nh), ep, L, dh, L, BH, 1, st)); }
-    B200_CUDA(launch_pdl(softmax_bwd_kernel<T>, dim3(cdiv((long)BH * L, 8)), dim3(256), 0, st, w.P[i], w.dP, w.dS, (long)BH * L, L, Lp, scale));
-    B200_LAUNCH_CHECK();
+    if (!fused_sm) {
+      B200_CUDA(launch_pdl(softmax_bwd_kernel<T>, dim3(cdiv((long)BH * L, 8)), dim3(256), 0, st, w.P[i], w.dP, w.dS, (long)BH * L, L, Lp, scale));
+      B200_LAUNCH_CHECK();
+    }
     // dQ = dS K ; dK = dS^T Q
     { EpStore<T> ep = ep_plain<T>(w.dqkv, 3 * H); ep.sb0 = sQb; ep.sb1 = dh; ep.nb1 = nh;
       if constexpr (kTC) B200_TRY(tc::gemm(tc::operand(w.dS, Lp, 1, sPb, sPh), tc::operand(qkv + H, 1, 3 * H, sQb, dh), ep, L, dh, L, c.B, nh, st));

@@ -112,6 +112,12 @@ __device__ __forceinline__ void ep_seg16(const EP& ep, int b, int m, int n0, con
   for (int j = 0; j < nvalid; ++j) ep(b, m, n0 + j, v[j]);
 }
 
+// Row-wise epilogues (EP::kRowOp == 1 forward softmax, 2 softmax backward): the CTA's tile holds COMPLETE rows (tiles_n == 1), each
+// epilogue thread owns one row and walks its TMEM columns twice -- attention scores never go to memory as fp32.
+template <class EP> struct row_op_of { template <class U> static constexpr int get(decltype(U::kRowOp)*) { return U::kRowOp; }
+                                       template <class U> static constexpr int get(...) { return 0; }
+                                       static constexpr int value = get<EP>(nullptr); };
+
 struct Params {
   int M, N, K, BN;          // BN in {64,128,256}
   int a_mn, b_mn;           // operand majors
@@ -240,11 +246,55 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
       if (dbg && warp == 2 && lane == 0 && t == blockIdx.x) p.dbg[4] = clock64();   // first accumulator ready
       const int m = tm * BM + q * 32 + lane;
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.BN);
+      if constexpr (row_op_of<EP>::value == 1) {
+        // P = softmax(scale * S) over the N valid columns; two passes over TMEM (running max / sum, then normalise + store)
+        float mx = -INFINITY, sum = 0.f;
+        for (int c0 = 0; c0 < p.N; c0 += 16) {
+          float v[16];
+          tmem_ld16(trow + c0, v);
+          float cm = -INFINITY;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) { v[j] = (c0 + j < p.N) ? v[j] * ep.scale : -INFINITY; cm = fmaxf(cm, v[j]); }
+          const float nm = fmaxf(mx, cm);
+          float cs = 0.f;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) cs += __expf(v[j] - nm);
+          sum = sum * __expf(mx - nm) + cs; mx = nm;
+        }
+        const float inv = 1.f / sum;
+        for (int c0 = 0; c0 < ep.ldw; c0 += 16) {      // ldw >= N: padding columns are written as zeros
+          float v[16];
+          if (c0 < p.N) tmem_ld16(trow + c0, v);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = (c0 + j < p.N) ? __expf(v[j] * ep.scale - mx) * inv : 0.f;
+          if (m < p.M) ep.store16(b, m, c0, v, min(16, ep.ldw - c0));
+        }
+      } else if constexpr (row_op_of<EP>::value == 2) {
+        // dS = P * (dP - sum_j dP_j P_j) * scale, P read back from memory (bf16), dP = this accumulator row
+        float dot = 0.f;
+        const bool rv = m < p.M;               // every lane runs the (warp-aligned) TMEM loads; only valid rows touch memory
+        for (int c0 = 0; c0 < p.N; c0 += 16) {
+          float v[16], pr[16];
+          tmem_ld16(trow + c0, v);
+          ep.load_p16(b, m, c0, pr, rv ? min(16, p.N - c0) : 0);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) dot = fmaf(v[j], pr[j], dot);
+        }
+        for (int c0 = 0; c0 < ep.ldw; c0 += 16) {
+          float v[16], pr[16];
+          if (c0 < p.N) tmem_ld16(trow + c0, v);
+          ep.load_p16(b, m, c0, pr, (rv && c0 < p.N) ? min(16, p.N - c0) : 0);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = (c0 + j < p.N) ? pr[j] * (v[j] - dot) * ep.scale : 0.f;
+          if (rv) ep.store16(b, m, c0, v, min(16, ep.ldw - c0));
+        }
+      } else {
       for (int c0 = 0; c0 < p.BN; c0 += 16) {
         float v[16];
         tmem_ld16(trow + c0, v);
         int n0 = tn * p.BN + c0;
         if (m < p.M && n0 < p.N) ep_seg16(ep, b, m, n0, v, min(16, p.N - n0));
+      }
       }
       tc_fence_before();
       __syncwarp();
@@ -344,6 +394,10 @@ static int gemm(const Operand& A, const Operand& B, const EP& ep, int M, int N, 
       const int kb = ksplit_req > 1 ? cdiv(kbs, ksplit_req) : kbs;
       const double cost = waves * (kb * (128.0 + bn) * 2.2e-3 + 0.6 + bn * 6e-3);
       if (cost < best - 1e-9) { best = cost; p.BN = bn; }
+    }
+    if (row_op_of<EP>::value) {          // complete rows per tile
+      p.BN = (N + 15) & ~15; if (p.BN < 32) p.BN = 32;
+      B200_CHECK(!p.b_mn && p.BN <= 256, "row-wise epilogue needs a K-major B operand and N <= 256 (N=%d)", N);
     }
   }
   p.tiles_m = cdiv(M, BM); p.tiles_n = cdiv(N, p.BN); p.nb1 = nb1; p.batches = nb0 * nb1;
