@@ -248,6 +248,92 @@ __global__ void __launch_bounds__(256) conv_in_wgrad_kernel(const float* __restr
   }
 }
 
+
+// Same contract as conv_in_wgrad_kernel, restructured like conv_in_fwd2: a thread owns TWO voxels adjacent in w, EIGHT output
+// channels and the NINE taps of one kd plane (blockIdx.z = role = (channel octet, kd)), i.e. 72 (+8 for the 1x1x1 conv in the kd = 1
+// role) register accumulators fed by 2 x 16-byte gradient loads and 12 input loads per iteration; one block reduction at the end.
+template <class T, int CO>
+__global__ void __launch_bounds__(256, 2) conv_in_wgrad2_kernel(const float* __restrict__ x, const T* __restrict__ dc1, const T* __restrict__ dc3,
+                                                                int Cin, int D, int H, int W, long pairs_per_block, float* __restrict__ dW1,
+                                                                float* __restrict__ dW3) {
+  constexpr int NCG = CO / 8;
+  __shared__ float red[8][80];
+  const long V = (long)D * H * W;
+  const int n = blockIdx.y;
+  const int role = blockIdx.z % (3 * NCG), ci = blockIdx.z / (3 * NCG);
+  const int cg = role % NCG, kd = role / NCG, c0 = cg * 8;
+  const float* xc = x + ((long)n * Cin + ci) * V;
+  const int W2 = W >> 1;
+  const long npairs = V >> 1;
+  const long p0 = (long)blockIdx.x * pairs_per_block, p1 = min(npairs, p0 + pairs_per_block);
+  float acc[9][8], acc3[8];
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[t][c] = 0.f;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) acc3[c] = 0.f;
+  constexpr int VN = Vec16<T>::N;
+  for (long pi = p0 + threadIdx.x; pi < p1; pi += 256) {
+    const int pv = (int)pi; const int w = (pv % W2) * 2, t = pv / W2, h = t % H, d = t / H;
+    const long v = 2 * pi;
+    float g[2][8];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const T* r1 = dc1 + ((long)n * V + v + e) * CO + c0;
+#pragma unroll
+      for (int q = 0; q < 8; q += VN) { Vec16<T> pk; pk.load(r1 + q);
+#pragma unroll
+        for (int i = 0; i < VN; ++i) g[e][q + i] = pk.v[i]; }
+    }
+    const int dd = d + kd - 1;
+    const bool okd = (unsigned)dd < (unsigned)D;
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      const int hh = h + kh - 1;
+      const bool ok = okd && (unsigned)hh < (unsigned)H;
+      const float* xr = xc + ((long)dd * H + hh) * W + w;       // only dereferenced when ok
+      float xv[4];
+      xv[0] = (ok && w > 0) ? xr[-1] : 0.f;
+      if (ok) { float2 m = *reinterpret_cast<const float2*>(xr); xv[1] = m.x; xv[2] = m.y; } else { xv[1] = xv[2] = 0.f; }
+      xv[3] = (ok && w + 2 < W) ? xr[2] : 0.f;
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[kh * 3 + kw][c] = fmaf(xv[kw], g[0][c], fmaf(xv[kw + 1], g[1][c], acc[kh * 3 + kw][c]));
+      if (kd == 1 && kh == 1) {      // conv3 (1x1x1): centre voxel values xv[1], xv[2] with the dc3 gradients
+        float g3[2][8];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const T* r3 = dc3 + ((long)n * V + v + e) * CO + c0;
+#pragma unroll
+          for (int q = 0; q < 8; q += VN) { Vec16<T> pk; pk.load(r3 + q);
+#pragma unroll
+            for (int i = 0; i < VN; ++i) g3[e][q + i] = pk.v[i]; }
+        }
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc3[c] = fmaf(xv[1], g3[0][c], fmaf(xv[2], g3[1][c], acc3[c]));
+      }
+    }
+  }
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) { float s = warp_sum(acc[t][c]); if (lane == 0) red[wp][t * 8 + c] = s; }
+#pragma unroll
+  for (int c = 0; c < 8; ++c) { float s = warp_sum(acc3[c]); if (lane == 0) red[wp][72 + c] = s; }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 80; i += 256) {
+    float tot = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) tot += red[k][i];
+    const int c = c0 + (i & 7);
+    if (i < 72) atomicAdd(dW1 + ((long)c * Cin + ci) * 27 + kd * 9 + (i >> 3), tot);
+    else if (kd == 1) atomicAdd(dW3 + (long)c * Cin + ci, tot);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- fused last norm pass + head
 // d0[v,c] = lrelu(norm(c2)[v,c] + norm(c3)[v,c]) (stored as T for the backward), logits[n][k][v] = sum_c d0_fp32[c] Wh[k][c] + bh[k]
 template <class T, int CO>

@@ -479,6 +479,13 @@ struct Exec {
       B200_TRY(zero_grad(dW3, (size_t)Co * Ci, st));
       long chunk = 4096;
       dim3 g((unsigned)((Vs + chunk - 1) / chunk), B, Ci);
+      if (s.W % 2 == 0 && !getenv("B200_ENC1_V1")) {   // two voxels x eight channels x nine taps per thread
+        const long ppb = 4096;
+        dim3 g2((unsigned)((Vs / 2 + ppb - 1) / ppb), B, (unsigned)(3 * (Co / 8) * Ci));
+        if (Co == 8) conv_in_wgrad2_kernel<T, 8><<<g2, 256, 0, st>>>(raw, w.dc1, w.dc3, Ci, s.D, s.H, s.W, ppb, dW1, dW3);
+        else if (Co == 16) conv_in_wgrad2_kernel<T, 16><<<g2, 256, 0, st>>>(raw, w.dc1, w.dc3, Ci, s.D, s.H, s.W, ppb, dW1, dW3);
+        else conv_in_wgrad2_kernel<T, 32><<<g2, 256, 0, st>>>(raw, w.dc1, w.dc3, Ci, s.D, s.H, s.W, ppb, dW1, dW3);
+      } else
       if (Co == 8) conv_in_wgrad_kernel<T, 8><<<g, 256, 0, st>>>(raw, w.dc1, w.dc3, Ci, s.D, s.H, s.W, chunk, dW1, dW3);
       else if (Co == 16) conv_in_wgrad_kernel<T, 16><<<g, 256, 0, st>>>(raw, w.dc1, w.dc3, Ci, s.D, s.H, s.W, chunk, dW1, dW3);
       else conv_in_wgrad_kernel<T, 32><<<g, 256, 0, st>>>(raw, w.dc1, w.dc3, Ci, s.D, s.H, s.W, chunk, dW1, dW3);
