@@ -53,6 +53,15 @@ SIGNATURES = {
     "b200_sw_accumulate": (c_int, [c_void_p, c_void_p, POINTER(SwGeom), POINTER(c_int32), c_void_p]),
     "b200_sw_finalize": (c_int, [c_void_p, c_void_p, c_void_p, POINTER(SwGeom), c_int, POINTER(c_int32), c_int,
                                  POINTER(c_int32), c_int, POINTER(c_int32), c_int, c_void_p]),
+    "b200_sw_finalize_metric": (c_int, [c_void_p, c_void_p, c_void_p, POINTER(SwGeom), c_int, POINTER(c_int32), c_int,
+                                        POINTER(c_int32), c_int, POINTER(c_int32), c_int, c_void_p, c_void_p, c_void_p]),
+    "b200_dicece_sigmoid_forward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p]),
+    "b200_dicece_sigmoid_backward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "b200_seg_counts_onehot": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int64, c_void_p, c_void_p]),
+    "b200_seg_counts_labels": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int64, c_void_p, c_void_p]),
+    "b200_seg_metrics": (c_int, [c_void_p, c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p]),
+    "b200_metric_reduce": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "b200_confusion_metric": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "b200_unetr_peek": (c_int, [c_void_p, c_char_p, c_void_p, c_size_t]),
     "b200_launch_count": (ctypes.c_ulonglong, []),
     "b200_prof_enable": (None, [c_int]),

@@ -14,6 +14,7 @@
 #include "adamw.cuh"
 #include "loss.cuh"
 #include "sliding.cuh"
+#include "metrics.cuh"
 #include "tc_gemm.cuh"
 #include "tc_conv_halo.cuh"
 #include "tc_wgrad_halo.cuh"
@@ -169,6 +170,72 @@ int b200_dicece_backward(const float* logits, const float* labels, int B, int C,
   return 0;
 }
 
+// DiceCELoss(to_onehot_y=False, sigmoid=True): target is the float multi-hot tensor [B][C][V] (seg:480); same scratch layout
+int b200_dicece_sigmoid_forward(const float* logits, const float* target, int B, int C, int64_t V, void* scratch, float* out3, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  B200_CHECK(C >= 1 && C <= 16, "sigmoid DiceCE supports 1..16 channels (got %d)", C);
+  double* acc = (double*)scratch;
+  float* coef = (float*)(acc + (size_t)B * C * 3 + 2);
+  B200_CUDA(cudaMemsetAsync(acc, 0, sizeof(double) * ((size_t)B * C * 3 + 2), st));
+  dim3 g((unsigned)max(1L, min(148L * 8 / B + 1, (long)((V + 255) / 256))), B);
+  if (C <= 4) dicece_sig_fwd_kernel<4><<<g, 256, 0, st>>>(logits, target, C, V, acc, B * C);
+  else dicece_sig_fwd_kernel<16><<<g, 256, 0, st>>>(logits, target, C, V, acc, B * C);
+  B200_LAUNCH_CHECK();
+  dicece_finalize_kernel<<<1, 256, 0, st>>>(acc, B, C, V, out3, coef);
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+int b200_dicece_sigmoid_backward(const float* logits, const float* target, int B, int C, int64_t V, const void* scratch,
+                                 const float* upstream, float* dlogits, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  B200_CHECK(C >= 1 && C <= 16, "sigmoid DiceCE supports 1..16 channels (got %d)", C);
+  const float* coef = (const float*)((const double*)scratch + (size_t)B * C * 3 + 2);
+  dim3 g((unsigned)max(1L, min(148L * 8 / B + 1, (long)((V + 255) / 256))), B);
+  if (C <= 4) dicece_sig_bwd_kernel<4><<<g, 256, 0, st>>>(logits, target, coef, upstream, B, C, V, dlogits);
+  else dicece_sig_bwd_kernel<16><<<g, 256, 0, st>>>(logits, target, coef, upstream, B, C, V, dlogits);
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------- validation metrics (DiceMetric / ConfusionMatrixMetric, seg:485-494)
+int b200_seg_counts_onehot(const float* y_pred, const float* y, int B, int C, int64_t V, double* counts, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  B200_CHECK(B >= 1 && C >= 1 && V >= 1, "b200_seg_counts_onehot: bad shape");
+  B200_CUDA(cudaMemsetAsync(counts, 0, sizeof(double) * (size_t)B * C * 3, st));
+  long rows = (long)B * C;
+  dim3 g((unsigned)max(1L, min(148L * 8 / rows + 1, (long)((V / 4 + 255) / 256))), (unsigned)rows);
+  seg_counts_onehot_kernel<<<g, 256, 0, st>>>(y_pred, y, V, counts);
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+int b200_seg_counts_labels(const uint8_t* mask, const float* labels, int B, int C, int64_t V, double* counts, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  B200_CHECK(B >= 1 && C >= 1 && C <= 32 && V >= 1, "b200_seg_counts_labels: 1..32 classes");
+  B200_CUDA(cudaMemsetAsync(counts, 0, sizeof(double) * (size_t)B * C * 3, st));
+  dim3 g((unsigned)max(1L, min(148L * 8 / B + 1, (long)((V + 1023) / 1024))), B);
+  seg_counts_labels_kernel<<<g, 256, 0, st>>>(mask, labels, C, V, counts);
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+int b200_seg_metrics(const double* counts, int N, int C, int64_t V, float* dice, float* confusion, void* stream) {
+  B200_CHECK(N >= 1 && C >= 1, "b200_seg_metrics: bad shape");
+  seg_metrics_kernel<<<cdiv((long)N * C, 256), 256, 0, (cudaStream_t)stream>>>(counts, N * C, (double)V, dice, confusion);
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+int b200_metric_reduce(const float* f, int N, int C, int K, int reduction, float* out, float* not_nans, void* stream) {
+  B200_CHECK(N >= 1 && C >= 1 && K >= 1 && (reduction == 0 || reduction == 1), "b200_metric_reduce: reduction 0 (mean) or 1 (mean_batch)");
+  metric_reduce_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(f, N, C, K, reduction, out, not_nans);
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+int b200_confusion_metric(const float* cm, int rows, int metric, float* out, void* stream) {
+  B200_CHECK(rows >= 1 && (metric == 0 || metric == 1), "b200_confusion_metric: metric 0 (precision) or 1 (sensitivity)");
+  confusion_metric_kernel<<<cdiv(rows, 256), 256, 0, (cudaStream_t)stream>>>(cm, rows, metric, out);
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+
 // ---------------------------------------------------------------- ranking loss
 // scratch: double gram[C*256] | double loss | float coef[C*256]
 size_t b200_ranking_scratch_bytes(int C) { return sizeof(double) * ((size_t)C * 256 + 2) + sizeof(float) * (size_t)C * 256; }
@@ -227,18 +294,26 @@ int b200_sw_accumulate(float* acc, const float* pred, const b200_sw_geom* g, con
   B200_LAUNCH_CHECK();
   return 0;
 }
-int b200_sw_finalize(const float* acc, float* out, uint8_t* mask, const b200_sw_geom* g, int batch, const int32_t* s0, int n0,
-                     const int32_t* s1, int n1, const int32_t* s2, int n2, void* stream) {
+int b200_sw_finalize_metric(const float* acc, float* out, uint8_t* mask, const b200_sw_geom* g, int batch, const int32_t* s0, int n0,
+                            const int32_t* s1, int n1, const int32_t* s2, int n2, const float* labels, double* counts, void* stream) {
   B200_CHECK(n0 <= 64 && n1 <= 64 && n2 <= 64, "more than 64 window starts along one axis");
+  B200_CHECK((labels == nullptr) == (counts == nullptr), "labels and counts go together");
   SwStarts st; st.n0 = n0; st.n1 = n1; st.n2 = n2;
   for (int i = 0; i < n0; ++i) st.s0[i] = s0[i];
   for (int i = 0; i < n1; ++i) st.s1[i] = s1[i];
   for (int i = 0; i < n2; ++i) st.s2[i] = s2[i];
   SwGeom sg = to_sw(g);
-  long total = (long)batch * sg.D * sg.H * sg.W;
-  sw_finalize_kernel<<<(unsigned)min(148L * 16, (total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(acc, out, mask, sg, st, batch);
+  B200_CHECK(!counts || sg.C <= 32, "fused validation counts take at most 32 classes");
+  if (counts) B200_CUDA(cudaMemsetAsync(counts, 0, sizeof(double) * (size_t)batch * sg.C * 3, (cudaStream_t)stream));
+  long vox = (long)sg.D * sg.H * sg.W;
+  dim3 grid((unsigned)max(1L, min(148L * 16 / batch + 1, (vox + 255) / 256)), batch);
+  sw_finalize_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(acc, out, mask, sg, st, labels, counts);
   B200_LAUNCH_CHECK();
   return 0;
+}
+int b200_sw_finalize(const float* acc, float* out, uint8_t* mask, const b200_sw_geom* g, int batch, const int32_t* s0, int n0,
+                     const int32_t* s1, int n1, const int32_t* s2, int n2, void* stream) {
+  return b200_sw_finalize_metric(acc, out, mask, g, batch, s0, n0, s1, n1, s2, n2, nullptr, nullptr, stream);
 }
 
 int b200_unetr_peek(void* handle, const char* name, void* dst, size_t cap) {

@@ -227,6 +227,100 @@ __global__ void __launch_bounds__(256) dicece_bwd4_kernel(const float* __restric
   }
 }
 
+// ------------------------------------------------------------------ DiceCE, multi-label variant
+// MONAI DiceCELoss(to_onehot_y=False, sigmoid=True) as configured at unetr_segmentation_3d.py:480 for the 4-channel
+// multi-hot BraTS target (seg:65-93): Dice on sigmoid probabilities against the float target [B][C][V], plus
+// CrossEntropy(logits, argmax_c target) -- MONAI 0.6.0's `ce` takes the arg-max of a target that has as many channels as
+// the prediction (first maximum wins, as torch.argmax does on CPU and CUDA).  Same accumulator layout and finalize kernel
+// as the softmax variant; fwd reads logits + target once, bwd reads them once and writes dlogits once.
+template <int CMAX>
+__global__ void __launch_bounds__(256) dicece_sig_fwd_kernel(const float* __restrict__ logits, const float* __restrict__ target,
+                                                             int C, long V, double* __restrict__ acc, int nBC) {
+  int b = blockIdx.y;
+  float aI[CMAX], aP[CMAX], aG[CMAX];
+#pragma unroll
+  for (int c = 0; c < CMAX; ++c) aI[c] = aP[c] = aG[c] = 0.f;
+  float ce = 0.f;
+  const float* lg = logits + (long)b * C * V;
+  const float* tg = target + (long)b * C * V;
+  for (long v = (long)blockIdx.x * blockDim.x + threadIdx.x; v < V; v += (long)gridDim.x * blockDim.x) {
+    float l[CMAX], t[CMAX];
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c)
+      if (c < C) { l[c] = lg[(long)c * V + v]; t[c] = tg[(long)c * V + v]; }
+    float mx = -INFINITY, tmax = -INFINITY, ly = 0.f;
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c)
+      if (c < C) {
+        mx = fmaxf(mx, l[c]);
+        if (t[c] > tmax) { tmax = t[c]; ly = l[c]; }
+        float p = 1.f / (1.f + __expf(-l[c]));
+        aI[c] += p * t[c]; aP[c] += p; aG[c] += t[c];
+      }
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c)
+      if (c < C) s += __expf(l[c] - mx);
+    ce += logf(s) - (ly - mx);
+  }
+  __shared__ float red[8][3 * CMAX + 1];
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int c = 0; c < CMAX; ++c) {
+    float x0 = warp_sum(aI[c]), x1 = warp_sum(aP[c]), x2 = warp_sum(aG[c]);
+    if (lane == 0) { red[w][3 * c] = x0; red[w][3 * c + 1] = x1; red[w][3 * c + 2] = x2; }
+  }
+  ce = warp_sum(ce);
+  if (lane == 0) red[w][3 * CMAX] = ce;
+  __syncthreads();
+  for (int i = threadIdx.x; i < 3 * C + 1; i += blockDim.x) {
+    int src = (i < 3 * C) ? i : 3 * CMAX;
+    double t = 0.0;
+    for (int k = 0; k < 8; ++k) t += red[k][src];
+    if (i < 3 * C) atomicAdd(acc + ((long)b * C) * 3 + i, t);
+    else atomicAdd(acc + (long)nBC * 3, t);
+  }
+}
+// dlogits_k = up * [ (a_k t_k + b_k) p_k (1 - p_k) + (softmax_k - [k == argmax t]) / (B V) ]
+template <int CMAX>
+__global__ void __launch_bounds__(256) dicece_sig_bwd_kernel(const float* __restrict__ logits, const float* __restrict__ target,
+                                                             const float* __restrict__ coef, const float* __restrict__ upstream,
+                                                             int B, int C, long V, float* __restrict__ dlogits) {
+  int b = blockIdx.y;
+  float up = upstream ? upstream[0] : 1.f;
+  float invBV = 1.f / ((float)B * (float)V);
+  __shared__ float sc[2 * CMAX];
+  if (threadIdx.x < 2 * C) sc[threadIdx.x] = coef[(long)b * C * 2 + threadIdx.x];
+  __syncthreads();
+  const float* lg = logits + (long)b * C * V;
+  const float* tg = target + (long)b * C * V;
+  float* dl = dlogits + (long)b * C * V;
+  for (long v = (long)blockIdx.x * blockDim.x + threadIdx.x; v < V; v += (long)gridDim.x * blockDim.x) {
+    float l[CMAX], t[CMAX];
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c)
+      if (c < C) { l[c] = lg[(long)c * V + v]; t[c] = tg[(long)c * V + v]; }
+    float mx = -INFINITY, tmax = -INFINITY;
+    int y = 0;
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c)
+      if (c < C) { mx = fmaxf(mx, l[c]); if (t[c] > tmax) { tmax = t[c]; y = c; } }
+    float e[CMAX];
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c)
+      if (c < C) { e[c] = __expf(l[c] - mx); s += e[c]; }
+    float inv = 1.f / s;
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c)
+      if (c < C) {
+        float p = 1.f / (1.f + __expf(-l[c]));
+        float wk = sc[2 * c] * t[c] + sc[2 * c + 1];
+        dl[(long)c * V + v] = up * (wk * p * (1.f - p) + (e[c] * inv - (c == y ? 1.f : 0.f)) * invBV);
+      }
+  }
+}
+
 // ------------------------------------------------------------------ Bradley-Terry ranking loss
 // 16 slices: id = partition*4 + sample (samples ordered batch1[0], batch1[1], batch2[0], batch2[1], rank:80-84).
 // A slice is [C, F0*F1] taken at index idx[partition] along the sliced spatial axis.

@@ -44,13 +44,21 @@ static __global__ void sw_accumulate_kernel(float* __restrict__ acc, const float
   }
 }
 struct SwStarts { int n0, n1, n2; int s0[64], s1[64], s2[64]; };
-// out[b][c][d][h][w] = acc[b][c][d+pd][h+ph][w+pw] / count ; optional argmax over c -> mask[b][d][h][w]
+// out[b][c][d][h][w] = acc[b][c][d+pd][h+ph][w+pw] / count ; optional argmax over c -> mask[b][d][h][w] ;
+// optional validation tail (seg:110-126): with `labels` [B][D][H][W] (integer-valued floats) the argmax is
+// compared with the label in the same pass and counts[b][c][3] += (|y&p|, |p|, |y|) -- the inputs of DiceMetric /
+// ConfusionMatrixMetric -- so whole-volume evaluation never materialises one-hot tensors.
 static __global__ void sw_finalize_kernel(const float* __restrict__ acc, float* __restrict__ out, unsigned char* __restrict__ mask,
-                                   SwGeom g, SwStarts st, int B) {
-  long vox = (long)g.D * g.H * g.W;
-  long total = (long)B * vox;
-  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
-    int b = (int)(e / vox); long r = e % vox;
+                                   SwGeom g, SwStarts st, const float* __restrict__ labels, double* __restrict__ counts) {
+  const long vox = (long)g.D * g.H * g.W;
+  const int b = blockIdx.y;                       // one sample per grid row: the block's histogram belongs to one sample
+  __shared__ unsigned int hist[3 * 32];
+  if (counts) {
+    for (int i = threadIdx.x; i < 3 * 32; i += blockDim.x) hist[i] = 0u;
+    __syncthreads();
+  }
+  for (long r0 = (long)blockIdx.x * blockDim.x + threadIdx.x; r0 < vox; r0 += (long)gridDim.x * blockDim.x) {
+    long r = r0;
     int w = (int)(r % g.W); r /= g.W; int h = (int)(r % g.H); int d = (int)(r / g.H);
     int x = d + g.pd, y = h + g.ph, z = w + g.pw;
     int c0 = 0, c1 = 0, c2 = 0;
@@ -64,7 +72,16 @@ static __global__ void sw_finalize_kernel(const float* __restrict__ acc, float* 
       if (out) out[(((long)b * g.C + c) * g.D + d) * g.H * g.W + (long)h * g.W + w] = v;
       if (v > best) { best = v; arg = c; }
     }
-    if (mask) mask[e] = (unsigned char)arg;
+    if (mask) mask[(long)b * vox + r0] = (unsigned char)arg;
+    if (counts) {
+      int t = (int)labels[(long)b * vox + r0];
+      atomicAdd(&hist[3 * arg + 1], 1u);
+      if ((unsigned)t < (unsigned)g.C) { atomicAdd(&hist[3 * t + 2], 1u); if (t == arg) atomicAdd(&hist[3 * t], 1u); }
+    }
+  }
+  if (counts) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < 3 * g.C; i += blockDim.x) if (hist[i]) atomicAdd(counts + (long)b * g.C * 3 + i, (double)hist[i]);
   }
 }
 

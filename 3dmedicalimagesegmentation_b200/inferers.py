@@ -48,7 +48,12 @@ def sliding_window_inference(inputs: torch.Tensor, roi_size, sw_batch_size: int,
                              overlap: float = 0.25, mode: str = "constant", sigma_scale=0.125,
                              padding_mode: str = "constant", cval: float = 0.0, sw_device=None, device=None,
                              *args, rank: int = 0, world_size: int = 1, process_group=None,
-                             return_argmax: bool = False, **kwargs):
+                             return_argmax: bool = False, labels: torch.Tensor = None, return_logits: bool = True, **kwargs):
+    """Extras beyond MONAI's signature (all keyword-only, defaults reproduce MONAI): `rank`/`world_size`/`process_group`
+    shard the windows; `return_argmax` adds the uint8 class mask; `labels` ([B,1,D,H,W] class ids) fuses the validation
+    tail (seg:110-126) into the normalise pass and adds the [B,C,3] counts DiceMetric/ConfusionMatrixMetric consume
+    (`metric.update_from_counts`); `return_logits=False` skips writing the 3.76 GB normalised logits when only the mask /
+    counts are wanted.  Return: logits | (logits, mask) | (logits, mask, counts), `None` in place of skipped logits."""
     if str(mode).lower() not in ("constant", "blendmode.constant"):
         raise NotImplementedError("only constant blending (the mode both reference call sites use) is implemented")
     if str(padding_mode).lower() not in ("constant", "pytorchpadmode.constant"):
@@ -90,7 +95,7 @@ def sliding_window_inference(inputs: torch.Tensor, roi_size, sw_batch_size: int,
     finally:
         if use_graph:
             predictor.inference_graph = prev_graph
-    return _sw_finish(lib, acc, gout, world_size, process_group, batch, orig, per_axis, return_argmax, x, st)
+    return _sw_finish(lib, acc, gout, world_size, process_group, batch, orig, per_axis, return_argmax, x, st, labels, return_logits)
 
 
 def _sw_loop(lib, x, items, mine, sw_batch_size, chan, roi, gin, cval, st, predictor, args, kwargs, batch, size, orig, pad):
@@ -116,16 +121,31 @@ def _sw_loop(lib, x, items, mine, sw_batch_size, chan, roi, gin, cval, st, predi
     return acc, gout
 
 
-def _sw_finish(lib, acc, gout, world_size, process_group, batch, orig, per_axis, return_argmax, x, st):
+def _sw_finish(lib, acc, gout, world_size, process_group, batch, orig, per_axis, return_argmax, x, st, labels=None,
+               return_logits=True):
     if acc is None:
         raise RuntimeError("this rank owns no windows; use fewer ranks than windows")
     if world_size > 1:
         import torch.distributed as dist
         dist.all_reduce(acc, group=process_group)
     cout = acc.shape[1]
-    out = torch.empty((batch, cout, *orig), dtype=torch.float32, device=x.device)
-    mask = torch.empty((batch, 1, *orig), dtype=torch.uint8, device=x.device) if return_argmax else None
+    want_mask = return_argmax or labels is not None
+    out = torch.empty((batch, cout, *orig), dtype=torch.float32, device=x.device) if return_logits else None
+    mask = torch.empty((batch, 1, *orig), dtype=torch.uint8, device=x.device) if want_mask else None
+    counts = None
+    lab = None
+    if labels is not None:
+        if cout > 32:
+            raise NotImplementedError("fused validation counts take at most 32 classes")
+        lab = labels.to(x.device).float().contiguous()
+        if lab.shape[0] != batch or tuple(lab.shape[-3:]) != tuple(orig) or lab.numel() != batch * orig[0] * orig[1] * orig[2]:
+            raise ValueError(f"labels {tuple(labels.shape)} do not match the volume {(batch, 1, *orig)}")
+        counts = torch.empty((batch, cout, 3), dtype=torch.float64, device=x.device)
     arrs = [(ctypes.c_int32 * len(a))(*a) for a in per_axis]
-    _lib.check(lib.b200_sw_finalize(_lib.ptr(acc), _lib.ptr(out), _lib.ptr(mask), ctypes.byref(gout), batch,
-                                    arrs[0], len(arrs[0]), arrs[1], len(arrs[1]), arrs[2], len(arrs[2]), st), "b200_sw_finalize")
+    _lib.check(lib.b200_sw_finalize_metric(_lib.ptr(acc), _lib.ptr(out), _lib.ptr(mask), ctypes.byref(gout), batch,
+                                           arrs[0], len(arrs[0]), arrs[1], len(arrs[1]), arrs[2], len(arrs[2]),
+                                           _lib.ptr(lab), _lib.ptr(counts), st), "b200_sw_finalize_metric")
+    if counts is not None:
+        counts.voxels = orig[0] * orig[1] * orig[2]
+        return out, mask, counts
     return (out, mask) if return_argmax else out

@@ -1,7 +1,7 @@
 """Loss callables of the hot path, backed by csrc/loss.cuh.
 
 * `DiceCELoss(to_onehot_y=True, softmax=True)`  -- monai.losses.DiceCELoss as configured at
-  unetr_segmentation_3d.py:404 and called at :222.
+  unetr_segmentation_3d.py:404 and called at :222; `DiceCELoss(to_onehot_y=False, sigmoid=True)` as at :480.
 * `extract_triplets_more_partitions` / `BTLoss` -- unetr_ranking_pretraining_3d.py:59-133 and :202-217, same
   call signatures, including BTLoss's side effects (backward, optimizer.step, optimizer.zero_grad, returns float).
 """
@@ -51,23 +51,71 @@ class _DiceCEFunction(torch.autograd.Function):
         return dlogits, None
 
 
+class _DiceCESigmoidFunction(torch.autograd.Function):
+    """DiceCELoss(to_onehot_y=False, sigmoid=True) (seg:480): csrc/loss.cuh dicece_sig_* kernels."""
+
+    @staticmethod
+    def forward(ctx, logits, target):
+        lib = _lib.load()
+        _lib.require_device(logits)
+        logits = logits.float().contiguous()
+        target = target.float().contiguous()
+        b, c = logits.shape[:2]
+        v = logits[0, 0].numel()
+        scratch = torch.empty(lib.b200_dicece_scratch_bytes(b, c), dtype=torch.uint8, device=logits.device)
+        out = torch.empty(3, dtype=torch.float32, device=logits.device)
+        _lib.check(lib.b200_dicece_sigmoid_forward(_lib.ptr(logits), _lib.ptr(target), b, c, v, _lib.ptr(scratch), _lib.ptr(out),
+                                                   _lib.stream_ptr()), "b200_dicece_sigmoid_forward")
+        ctx.save_for_backward(logits, target, scratch)
+        ctx.terms = out
+        return out[0].clone()
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        lib = _lib.load()
+        logits, target, scratch = ctx.saved_tensors
+        b, c = logits.shape[:2]
+        v = logits[0, 0].numel()
+        dlogits = torch.empty_like(logits)
+        up = grad_out.contiguous().float().reshape(1)
+        _lib.check(lib.b200_dicece_sigmoid_backward(_lib.ptr(logits), _lib.ptr(target), b, c, v, _lib.ptr(scratch), _lib.ptr(up),
+                                                    _lib.ptr(dlogits), _lib.stream_ptr()), "b200_dicece_sigmoid_backward")
+        return dlogits, None
+
+
 class DiceCELoss(nn.Module):
-    """Softmax Dice (include_background, smooth 1e-5/1e-5, mean over (b,c)) + mean cross-entropy."""
+    """monai.losses.DiceCELoss in the two configurations the reference uses:
+
+    * `DiceCELoss(to_onehot_y=True, softmax=True)` (seg:404): softmax Dice (include_background, smooth 1e-5/1e-5, mean over
+      (b,c)) + mean cross-entropy against the `[B,1,...]` label map.
+    * `DiceCELoss(to_onehot_y=False, sigmoid=True)` (seg:480): sigmoid Dice against the `[B,C,...]` multi-hot
+      target + cross-entropy against `argmax(target, 1)` (MONAI 0.6.0 `ce` rule for a C-channel target).
+
+    Any other configuration raises NotImplementedError (no fallback)."""
 
     def __init__(self, include_background: bool = True, to_onehot_y: bool = False, sigmoid: bool = False,
                  softmax: bool = False, squared_pred: bool = False, jaccard: bool = False, reduction: str = "mean",
                  smooth_nr: float = 1e-5, smooth_dr: float = 1e-5, batch: bool = False, lambda_dice: float = 1.0,
                  lambda_ce: float = 1.0, **unused) -> None:
         super().__init__()
-        ok = (include_background and to_onehot_y and softmax and not sigmoid and not squared_pred and not jaccard
-              and reduction == "mean" and smooth_nr == 1e-5 and smooth_dr == 1e-5 and not batch
-              and lambda_dice == 1.0 and lambda_ce == 1.0 and not unused)
-        if not ok:
+        common = (include_background and not squared_pred and not jaccard and reduction == "mean" and smooth_nr == 1e-5
+                  and smooth_dr == 1e-5 and not batch and lambda_dice == 1.0 and lambda_ce == 1.0 and not unused)
+        if common and to_onehot_y and softmax and not sigmoid:
+            self.variant = "softmax"
+        elif common and not to_onehot_y and sigmoid and not softmax:
+            self.variant = "sigmoid"
+        else:
             raise NotImplementedError(
-                "b200 DiceCELoss implements DiceCELoss(to_onehot_y=True, softmax=True) with MONAI defaults (seg:404)")
-        self.last_terms = None
+                "b200 DiceCELoss implements DiceCELoss(to_onehot_y=True, softmax=True) (seg:404) and "
+                "DiceCELoss(to_onehot_y=False, sigmoid=True) (seg:480) with MONAI defaults")
 
     def forward(self, input: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+        if self.variant == "sigmoid":
+            if target.shape != input.shape:
+                raise AssertionError(f"ground truth has differing shape ({target.shape}) from input ({input.shape})")
+            if input.shape[1] > 16:
+                raise NotImplementedError("sigmoid DiceCELoss takes at most 16 channels")
+            return _DiceCESigmoidFunction.apply(input, target)
         if target.shape[1] != 1 or target.shape[0] != input.shape[0] or target.shape[2:] != input.shape[2:]:
             raise AssertionError(f"ground truth has differing shape ({target.shape}) from input ({input.shape})")
         return _DiceCEFunction.apply(input, target)

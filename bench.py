@@ -113,6 +113,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--breakdown", action="store_true", help="print the per-op CUDA-event breakdown to stderr")
     ap.add_argument("--no-sliding-window", action="store_true", help="skip the configs[4] whole-CT sliding-window measurement")
+    ap.add_argument("--no-ranking", action="store_true", help="skip the configs[2] ranking pre-training step measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -275,6 +276,43 @@ def main():
         del vol
         model.train()
 
+    # configs[2]: ranking pre-training step (rank:238-274) -- batch 8 x 96^3, "feat" stage: full forward, 576 triplets of enc4
+    # slices along one axis, Bradley-Terry loss, backward through encoder4 + ViT blocks 0-9 + patch embedding, AdamW step
+    rk = None
+    if not args.no_ranking:
+        del model, opt, ddp
+        torch.cuda.empty_cache()
+        rmodel = pkg.UNETR(**MODEL_KW).to(dev).set_mode(args.mode)
+        ropt = pkg.FusedAdamW(rmodel.parameters(), lr=1e-4, weight_decay=1e-5)
+        rddp = par.GradientAllReduce(rmodel, world) if world > 1 else None
+
+        class _Opt:                       # BTLoss(reference, similar, dissimilar, optimizer) steps the optimizer itself (rank:213-215)
+            def step(self):
+                if rddp:
+                    rddp.reduce()
+                ropt.step()
+
+            def zero_grad(self, set_to_none=True):
+                ropt.zero_grad(set_to_none=True)
+        xs = [torch.rand(8, 1, 96, 96, 96, generator=g).to(dev) for _ in range(2)]
+        import numpy as np
+        np.random.seed(rank)
+
+        def rank_step(i):
+            enc4, _ = rmodel(xs[i % 2])
+            f1, f2 = torch.split(enc4, [4, 4], dim=0)
+            ref, sim, dis = pkg.extract_triplets_more_partitions(f1, f2, 2 + i % 3)
+            return pkg.BTLoss(ref, sim, dis, _Opt())
+        for i in range(3):
+            rank_step(i)
+        n_rk = max(6, min(args.steps, 12))
+        ms_rk = timed(rank_step, n_rk) / n_rk
+        rk = {"value": 8 * world / (ms_rk * 1e-3), "unit": "samples/s", "ms_per_step": ms_rk, "batch_per_gpu": 8, "steps": n_rk,
+              "workload": "configs[2]: UNETR.forward -> enc4 -> extract_triplets_more_partitions (576 triplets, slice dims 2,3,4 in turn) "
+                          "-> BTLoss (backward + AdamW inside, loss.item() read back every step)"}
+        del rmodel, ropt, xs
+        torch.cuda.empty_cache()
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         t = cpu_reference_step_time(1, 2, 1)
@@ -291,7 +329,7 @@ def main():
                 "tflops_algorithmic": samples * FLOP_PER_SAMPLE_96 / (ms * 1e-3) / 1e12,
                 "e2e": {"value": samples / (ms_e2e * 1e-3), "unit": "samples/s",
                         "h2d_bytes_per_step": host_x[0].numel() * 4 + host_y[0].numel() * 4, "d2h_bytes_per_step": 4},
-                "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "sliding_window": sw}
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "sliding_window": sw, "ranking_step": rk}
         print(json.dumps(line), flush=True)
     par.shutdown(world)
 

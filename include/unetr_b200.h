@@ -59,6 +59,31 @@ int b200_dicece_forward(const float* logits, const float* labels, int batch, int
 int b200_dicece_backward(const float* logits, const float* labels, int batch, int classes, int64_t voxels,
                          const void* scratch, const float* upstream, float* dlogits, void* stream);
 
+/* ---- monai.losses.DiceCELoss(to_onehot_y=False, sigmoid=True)  (seg:480) ----
+ * target: [B,C,V] fp32 multi-hot (seg:65-93).  Dice on sigmoid(logits); CE against argmax_c(target) (MONAI 0.6.0 rule for a
+ * target with as many channels as the prediction).  Scratch size/layout as b200_dicece_scratch_bytes; C <= 16. */
+int b200_dicece_sigmoid_forward(const float* logits, const float* target, int batch, int channels, int64_t voxels,
+                                void* scratch, float* out3, void* stream);
+int b200_dicece_sigmoid_backward(const float* logits, const float* target, int batch, int channels, int64_t voxels,
+                                 const void* scratch, const float* upstream, float* dlogits, void* stream);
+
+/* ---- validation tail: monai.metrics.DiceMetric / ConfusionMatrixMetric (seg:485-494, used seg:110-126,153-188; 8f N2) ----
+ * counts: [B][C][3] doubles = (|y & p|, |p|, |y|), zeroed by the call.
+ *   _onehot: y_pred, y = [B,C,V] fp32 one-hot tensors as the reference passes them (post_pred / post_label, seg:405-406)
+ *   _labels: mask = [B,V] uint8 argmax (b200_sw_finalize), labels = [B,V] fp32 holding class ids; C <= 32 */
+int b200_seg_counts_onehot(const float* y_pred, const float* y, int batch, int classes, int64_t voxels, double* counts,
+                           void* stream);
+int b200_seg_counts_labels(const uint8_t* mask, const float* labels, int batch, int classes, int64_t voxels,
+                           double* counts, void* stream);
+/* dice[n][c] = 2|y&p|/(|y|+|p|), NaN when |y| == 0; confusion[n][c] = (tp, fp, tn, fn).  Either output may be NULL. */
+int b200_seg_metrics(const double* counts, int rows, int classes, int64_t voxels, float* dice, float* confusion,
+                     void* stream);
+/* MONAI do_metric_reduction over f[N][C][K]: reduction 0 = "mean" -> out[K], 1 = "mean_batch" -> out[C][K]; NaN-aware;
+ * not_nans (same shape as out) may be NULL */
+int b200_metric_reduce(const float* f, int n, int classes, int k, int reduction, float* out, float* not_nans, void* stream);
+/* rows of (tp, fp, tn, fn) -> metric 0 precision, 1 sensitivity; NaN where the denominator is 0 */
+int b200_confusion_metric(const float* confusion, int rows, int metric, float* out, void* stream);
+
 /* ---- extract_triplets_more_partitions + BTLoss  (rank:59-133, rank:202-217) ----
  * 4 samples (batch1[0], batch1[1], batch2[0], batch2[1]), one slice index per partition along the sliced axis. */
 typedef struct {
@@ -84,6 +109,12 @@ int b200_sw_accumulate(float* acc, const float* pred, const b200_sw_geom* g, con
 /* per-axis window starts (n0,n1,n2 <= 64).  out and/or mask (uint8 argmax) may be NULL. */
 int b200_sw_finalize(const float* acc, float* out, uint8_t* mask, const b200_sw_geom* g, int batch, const int32_t* s0,
                      int n0, const int32_t* s1, int n1, const int32_t* s2, int n2, void* stream);
+
+/* same pass with the validation tail fused: labels [B,D,H,W] fp32 class ids, counts [B][C][3] as b200_seg_counts_labels
+ * (zeroed by the call); both NULL = plain b200_sw_finalize */
+int b200_sw_finalize_metric(const float* acc, float* out, uint8_t* mask, const b200_sw_geom* g, int batch,
+                            const int32_t* s0, int n0, const int32_t* s1, int n1, const int32_t* s2, int n2,
+                            const float* labels, double* counts, void* stream);
 
 /* debug: copy a named workspace buffer of the last forward/backward (device to device, synchronous) */
 int b200_unetr_peek(void* handle, const char* name, void* dst, size_t cap);

@@ -335,6 +335,79 @@ def dice_metric(pred_onehot: torch.Tensor, y_onehot: torch.Tensor) -> torch.Tens
     return torch.where(y_o > 0, 2.0 * inter / den, torch.full_like(inter, float("nan")))
 
 
+def dice_ce_loss_sigmoid(logits: torch.Tensor, target: torch.Tensor, smooth_nr=1e-5, smooth_dr=1e-5, return_terms=False):
+    """DiceCELoss(to_onehot_y=False, sigmoid=True) as configured at unetr_segmentation_3d.py:480:
+    Dice on sigmoid(logits) against the float multi-hot target [B,C,...]; CE against argmax(target, 1) because the target has
+    as many channels as the prediction (MONAI 0.6.0 DiceCELoss.ce)."""
+    if target.shape != logits.shape:
+        raise AssertionError(f"ground truth has differing shape ({target.shape}) from input ({logits.shape})")
+    prob = torch.sigmoid(logits)
+    axes = tuple(range(2, logits.dim()))
+    inter = (target * prob).sum(axes)
+    denom = target.sum(axes) + prob.sum(axes)
+    dice = (1.0 - (2.0 * inter + smooth_nr) / (denom + smooth_dr)).mean()
+    ce = F.cross_entropy(logits, torch.argmax(target, dim=1).long(), reduction="mean")
+    if return_terms:
+        return dice + ce, dice, ce
+    return dice + ce
+
+
+def brats_multichannel(label: torch.Tensor) -> torch.Tensor:
+    """ConvertToMultiChannelBasedOnBratsClassesd (unetr_segmentation_3d.py:65-93) on a [B,1,...] or [B,...] label map:
+    channels (background, TC = 2|3, WT = 1|2|3, ET = 3), float32."""
+    if label.dim() == 5:
+        label = label[:, 0]
+    return torch.stack([label == 0, (label == 2) | (label == 3), (label == 1) | (label == 2) | (label == 3), label == 3],
+                       dim=1).float()
+
+
+def metric_reduce(f: torch.Tensor, reduction: str):
+    """monai.metrics.utils.do_metric_reduction (0.6.0, recalled) for "mean" and "mean_batch" on f[N,C,...]: NaN-aware."""
+    f = f.clone()
+    nans = torch.isnan(f)
+    not_nans = (~nans).float()
+    f[nans] = 0
+    zero = torch.zeros(1, dtype=f.dtype)
+    if reduction == "mean":
+        not_nans = not_nans.sum(dim=1)
+        f = torch.where(not_nans > 0, f.sum(dim=1) / not_nans, zero)
+        not_nans = (not_nans > 0).float().sum(dim=0)
+        f = torch.where(not_nans > 0, f.sum(dim=0) / not_nans, zero)
+    elif reduction == "mean_batch":
+        not_nans = not_nans.sum(dim=0)
+        f = torch.where(not_nans > 0, f.sum(dim=0) / not_nans, zero)
+    else:
+        raise ValueError(reduction)
+    return f, not_nans
+
+
+def confusion_matrix(pred_onehot: torch.Tensor, y_onehot: torch.Tensor) -> torch.Tensor:
+    """monai.metrics.get_confusion_matrix (include_background=True): [B,C,4] = (tp, fp, tn, fn)."""
+    b, c = pred_onehot.shape[:2]
+    p = pred_onehot.reshape(b, c, -1).float()
+    y = y_onehot.reshape(b, c, -1).float()
+    tp = ((p + y) == 2).float().sum(2)
+    tn = ((p + y) == 0).float().sum(2)
+    pos = y.sum(2)
+    neg = y.shape[-1] - pos
+    return torch.stack([tp, neg - tn, tn, pos - tp], dim=-1)
+
+
+def confusion_metric(cm: torch.Tensor, metric_name: str) -> torch.Tensor:
+    """compute_confusion_matrix_metric for "precision" (tp/(tp+fp)) and "sensitivity" (tp/(tp+fn)); NaN on a zero denominator."""
+    tp, fp, fn = cm[..., 0], cm[..., 1], cm[..., 3]
+    den = tp + fp if metric_name == "precision" else tp + fn
+    return torch.where(den != 0, tp / den, torch.full_like(den, float("nan")))
+
+
+def confusion_aggregate(cm: torch.Tensor, metric_name: str, reduction: str, compute_sample: bool = False) -> torch.Tensor:
+    """ConfusionMatrixMetric.aggregate (0.6.0, recalled): compute_sample=False (the default the reference uses, seg:487-494)
+    reduces the confusion matrix first and evaluates the metric on the reduced counts."""
+    if compute_sample:
+        return metric_reduce(confusion_metric(cm, metric_name), reduction)[0]
+    return confusion_metric(metric_reduce(cm, reduction)[0], metric_name)
+
+
 # --------------------------------------------------------------------------------------
 # sliding_window_inference   (Appendix B.9; call sites seg:109,143,694)
 # --------------------------------------------------------------------------------------

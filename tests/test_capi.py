@@ -75,8 +75,18 @@ def test_constructor_errors(pkg):
         pkg.UNETR(**{**kw, "norm_name": "batch"})
     with pytest.raises(NotImplementedError):
         pkg.UNETR(**{**kw, "res_block": False})
+    assert pkg.DiceCELoss(to_onehot_y=False, sigmoid=True).variant == "sigmoid"       # seg:480
+    assert pkg.DiceCELoss(to_onehot_y=True, softmax=True).variant == "softmax"         # seg:404
+    for bad in (dict(to_onehot_y=True, sigmoid=True), dict(softmax=True, sigmoid=True, to_onehot_y=True), dict(),
+                dict(to_onehot_y=True, softmax=True, squared_pred=True)):
+        with pytest.raises(NotImplementedError):
+            pkg.DiceCELoss(**bad)
     with pytest.raises(NotImplementedError):
-        pkg.DiceCELoss(to_onehot_y=False, sigmoid=True)
+        pkg.DiceMetric(include_background=False)
+    with pytest.raises(NotImplementedError):
+        pkg.ConfusionMatrixMetric(metric_name="f1 score")
+    with pytest.raises(RuntimeError):           # metrics have no CPU path either
+        pkg.DiceMetric()(y_pred=[torch.zeros(2, 4, 4, 4)], y=[torch.zeros(2, 4, 4, 4)])
 
 
 def test_no_cpu_fallback(pkg):

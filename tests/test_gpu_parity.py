@@ -381,3 +381,111 @@ def test_unetr_as_sliding_window_predictor(pkg):
     with torch.no_grad():
         out = pkg.sliding_window_inference(x, (32, 32, 32), 4, m, overlap=0.5)
     assert out.shape == (1, 5, 48, 32, 40) and torch.isfinite(out).all()
+
+
+# ------------------------------------------------------------------------------------------- sigmoid DiceCE
+@pytest.mark.parametrize("shape,chan", [((24, 20, 16), 4), ((9, 7, 5), 3), ((16, 16, 16), 6)])
+def test_sigmoid_dicece_matches_oracle_and_closed_form(pkg, shape, chan):
+    g = torch.Generator().manual_seed(7)
+    logits = torch.randn(2, chan, *shape, generator=g) * 2
+    if chan == 4:
+        target = O.brats_multichannel(torch.randint(0, 4, (2, 1, *shape), generator=g))     # seg:65-93 multi-hot (ties in argmax)
+    else:
+        target = (torch.rand(2, chan, *shape, generator=g) > 0.6).float()
+    lr = logits.clone().requires_grad_(True)
+    loss_r, dice_r, ce_r = O.dice_ce_loss_sigmoid(lr, target, return_terms=True)
+    (loss_r * 0.6).backward()
+    fn = pkg.DiceCELoss(to_onehot_y=False, sigmoid=True)
+    lg = logits.to(DEV).requires_grad_(True)
+    loss = fn(lg, target.to(DEV))
+    (loss * 0.6).backward()
+    assert abs(loss.item() - loss_r.item()) <= 1e-5                      # bar: 1e-3 (north_star), measured ~1e-6
+    assert relerr(lg.grad, lr.grad) <= 1e-4
+    # T8: zero logits -> Dice term closed form with p = 1/2, CE = ln C
+    z = fn(torch.zeros(2, chan, *shape, device=DEV), target.to(DEV)).item()
+    n = shape[0] * shape[1] * shape[2]
+    gs = target.sum((2, 3, 4)).double()
+    closed = math.log(chan) + (1 - (gs + 1e-5) / (gs + n / 2 + 1e-5)).mean().item()
+    assert abs(z - closed) <= 1e-5
+    with pytest.raises(AssertionError):
+        fn(lg, target.to(DEV)[:, :1])
+    with pytest.raises(NotImplementedError):
+        pkg.DiceCELoss(to_onehot_y=True, sigmoid=True)
+
+
+def test_sigmoid_dicece_task01_size(pkg):
+    """seg:480 configuration at its real size (4 channels, 128^3 crops, batch 2): loss within 1e-3 of the oracle, and the
+    size-independent property d(loss)/d(logits) sums: CE part sums to 0 over channels at every voxel."""
+    g = torch.Generator().manual_seed(8)
+    logits = torch.randn(2, 4, 128, 128, 128, generator=g)
+    target = O.brats_multichannel(torch.randint(0, 4, (2, 1, 128, 128, 128), generator=g))
+    want = O.dice_ce_loss_sigmoid(logits, target).item()
+    lg = logits.to(DEV).requires_grad_(True)
+    loss = pkg.DiceCELoss(to_onehot_y=False, sigmoid=True)(lg, target.to(DEV))
+    loss.backward()
+    assert abs(loss.item() - want) <= 1e-4
+    assert torch.isfinite(lg.grad).all()
+
+
+# ------------------------------------------------------------------------------------------- SURVEY 8f N2: validation metrics
+def _onehot(idx, c):
+    return torch.zeros(idx.shape[0], c, *idx.shape[2:]).scatter_(1, idx.long(), 1.0)
+
+
+def test_dice_and_confusion_metrics_match_oracle(pkg):
+    g = torch.Generator().manual_seed(9)
+    c, shape = 6, (20, 18, 10)
+    lab = torch.randint(0, 4, (3, 1, *shape), generator=g)            # classes 4, 5 never appear in the label -> NaN Dice
+    lab[2] = 0                                                         # sample 2: background only
+    pred = torch.randint(0, c, (3, 1, *shape), generator=g)
+    y, p = _onehot(lab, c), _onehot(pred, c)
+    d_want = O.dice_metric(p, y)
+    cm_want = O.confusion_matrix(p, y)
+    for red in ("mean", "mean_batch"):
+        dm = pkg.DiceMetric(include_background=True, reduction=red, get_not_nans=False)
+        # the reference's call form (seg:112-121): lists of channel-first one-hot tensors, one volume per call, cumulative buffer
+        for i in range(3):
+            rows = dm(y_pred=[p[i].to(DEV)], y=[y[i].to(DEV)])
+            assert torch.allclose(rows.cpu(), d_want[i:i + 1], atol=1e-6, equal_nan=True)
+            agg = dm.aggregate()
+            want, _ = O.metric_reduce(d_want[:i + 1], red)
+            assert agg.shape == want.shape and torch.allclose(agg.cpu(), want, atol=1e-6), (red, i)
+        assert agg.shape == ((1,) if red == "mean" else (c,)) and isinstance(agg.sum().item(), float)
+        dm.reset()
+        with pytest.raises(ValueError):
+            dm.aggregate()
+        for name in ("precision", "sensitivity"):
+            for cs in (False, True):
+                m = pkg.ConfusionMatrixMetric(include_background=True, metric_name=name, reduction=red, compute_sample=cs)
+                rows = m(y_pred=p.to(DEV), y=y.to(DEV))
+                assert torch.equal(rows.cpu(), cm_want)                # integer counts: exact
+                got = m.aggregate()[0]
+                want = O.confusion_aggregate(cm_want, name, red, compute_sample=cs)
+                assert got.shape == want.shape and torch.allclose(got.cpu(), want, atol=1e-6, equal_nan=True), (name, red, cs)
+    # label-map form == one-hot form, bit for bit (integer counts)
+    a = pkg.segmentation_counts(p.to(DEV), y.to(DEV))
+    b = pkg.segmentation_counts_from_label_maps(pred.to(torch.uint8).to(DEV), lab.float().to(DEV), c)
+    assert torch.equal(a, b)
+    assert a[..., 1].sum().item() == 3 * 20 * 18 * 10 and a[..., 2].sum().item() == 3 * 20 * 18 * 10
+
+
+def test_sliding_window_fused_validation_tail(pkg):
+    """seg:103-126 in one call: sliding-window logits -> argmax -> Dice against the label, counts formed inside the normalise
+    pass; equal to the reference's route (one-hot tensors -> DiceMetric) on the same logits."""
+    g = torch.Generator().manual_seed(10)
+    x = torch.rand(2, 1, 40, 33, 50, generator=g)
+    lab = torch.randint(0, 3, (2, 1, 40, 33, 50), generator=g).float()
+    w = torch.randn(5, 1, 3, 3, 3, generator=g)
+    f_gpu = lambda t: torch.nn.functional.conv3d(t, w.to(DEV), padding=1)
+    logits, mask, counts = pkg.sliding_window_inference(x.to(DEV), (16,) * 3, 4, f_gpu, overlap=0.25, labels=lab.to(DEV))
+    plain = pkg.sliding_window_inference(x.to(DEV), (16,) * 3, 4, f_gpu, overlap=0.25)
+    assert torch.equal(logits, plain)
+    assert (mask[:, 0].long() == logits.argmax(1)).all()
+    p, y = _onehot(mask.cpu(), 5), _onehot(lab, 5)
+    dm = pkg.DiceMetric(include_background=True, reduction="mean_batch")
+    dm.update_from_counts(counts)
+    assert torch.allclose(dm.aggregate().cpu(), O.metric_reduce(O.dice_metric(p, y), "mean_batch")[0], atol=1e-6)
+    assert torch.equal(counts, pkg.segmentation_counts(p.to(DEV), y.to(DEV)))
+    none, mask2, counts2 = pkg.sliding_window_inference(x.to(DEV), (16,) * 3, 4, f_gpu, overlap=0.25, labels=lab.to(DEV),
+                                                        return_logits=False)
+    assert none is None and torch.equal(mask2, mask) and torch.equal(counts2, counts)

@@ -166,3 +166,48 @@ def test_freeze_encoder_grad_reach():
     enc4.sum().backward()
     assert m.vit.blocks[9].mlp.linear1.weight.grad is not None
     assert m.vit.blocks[10].mlp.linear1.weight.grad is None and m.decoder5.transp_conv.conv.weight.grad is None
+
+
+# ------------------------------------------------------------------------------- SURVEY 8f N2 / N3 restatements
+def test_T8_sigmoid_dicece_zero_logits_closed_form():
+    """DiceCELoss(to_onehot_y=False, sigmoid=True) (seg:480): zero logits -> p = 1/2 everywhere, CE = ln C."""
+    b, c, s = 2, 4, 8
+    g = torch.Generator().manual_seed(4)
+    lab = torch.randint(0, 4, (b, 1, s, s, s), generator=g)
+    t = O.brats_multichannel(lab)
+    assert t.shape == (b, c, s, s, s)
+    # BraTS channel rule (seg:79-91): label 2 -> TC and WT; label 3 -> TC, WT and ET; label 1 -> WT only
+    assert t[:, 1].sum() == ((lab == 2) | (lab == 3)).sum() and t[:, 2].sum() == (lab > 0).sum() and t[:, 3].sum() == (lab == 3).sum()
+    loss, dice, ce = O.dice_ce_loss_sigmoid(torch.zeros(b, c, s, s, s), t, return_terms=True)
+    n = s ** 3
+    gsum = t.sum((2, 3, 4)).double()
+    closed = (1 - (gsum + 1e-5) / (gsum + n / 2 + 1e-5)).mean().item()
+    assert abs(dice.item() - closed) < 1e-6 and abs(ce.item() - math.log(c)) < 1e-6
+    with pytest.raises(AssertionError):
+        O.dice_ce_loss_sigmoid(torch.zeros(1, 4, 4, 4, 4), torch.zeros(1, 1, 4, 4, 4))
+
+
+def test_T9_dice_metric_nan_rules_and_reductions():
+    """DiceMetric / do_metric_reduction (Appendix B.10): NaN when a class is absent from the label; "mean" averages classes
+    first (ignoring NaN), then samples; "mean_batch" keeps the class axis."""
+    y = torch.zeros(2, 3, 4, 4, 4)
+    p = torch.zeros(2, 3, 4, 4, 4)
+    y[0, 0] = 1; p[0, 0] = 1                                  # sample 0: class 0 perfect, classes 1,2 absent -> NaN
+    y[1, 0, :2] = 1; y[1, 1, 2:] = 1                          # sample 1: class 0 = half the volume, class 1 = other half
+    p[1, 0, :1] = 1; p[1, 1, 1:] = 1                          #           prediction shifts the boundary by one plane
+    d = O.dice_metric(p, y)
+    assert d[0, 0] == 1 and torch.isnan(d[0, 1:]).all() and torch.isnan(d[1, 2])
+    assert abs(d[1, 0].item() - 2 * 16 / (32 + 16)) < 1e-6 and abs(d[1, 1].item() - 2 * 32 / (32 + 48)) < 1e-6
+    mean, nn_ = O.metric_reduce(d, "mean")
+    assert abs(mean.item() - (1.0 + (2 / 3 + 0.8) / 2) / 2) < 1e-6 and nn_.item() == 2
+    mb, nb = O.metric_reduce(d, "mean_batch")
+    assert torch.allclose(mb, torch.tensor([(1 + 2 / 3) / 2, 0.8, 0.0])) and nb.tolist() == [2, 1, 0]
+    cm = O.confusion_matrix(p, y)
+    assert cm[1, 0].tolist() == [16, 0, 32, 16] and cm[1, 1].tolist() == [32, 16, 16, 0]
+    assert cm.sum(-1).eq(64).all()
+    prec = O.confusion_metric(cm, "precision")
+    assert prec[1, 0] == 1 and abs(prec[1, 1].item() - 32 / 48) < 1e-6 and torch.isnan(prec[0, 1])
+    # compute_sample=False: counts are averaged first (micro average), then the metric is formed
+    agg = O.confusion_aggregate(cm, "sensitivity", "mean")
+    red = O.metric_reduce(cm, "mean")[0]
+    assert abs(agg.item() - (red[0] / (red[0] + red[3])).item()) < 1e-7
