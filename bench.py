@@ -186,13 +186,29 @@ def main():
     l0 = lib.b200_launch_count()
     ms = timed(lambda i: step(dev_x[i % 4], dev_y[i % 4]), args.steps)
     launches = lib.b200_launch_count() - l0
-    # end-to-end: pinned host inputs copied in, loss read back, every step
+    # end-to-end: every step's inputs come from pinned host memory and its loss is read back (a blocking .item()).  The copy of
+    # batch i+1 is enqueued on a copy stream while step i computes (what a prefetching loader does; the reference's DataLoader
+    # has pin_memory + 4 workers, seg:587) -- every copy and every read-back is inside the timed region.
+    copy_stream = torch.cuda.Stream()
+    slots = [(torch.empty_like(dev_x[0]), torch.empty_like(dev_y[0]), torch.cuda.Event()) for _ in range(2)]
+
+    def prefetch(i):
+        bx, by, ev = slots[i % 2]
+        with torch.cuda.stream(copy_stream):      # slot i%2 was last read by step i-2, which finished before step i-1's .item()
+            bx.copy_(host_x[i % 4], non_blocking=True)
+            by.copy_(host_y[i % 4], non_blocking=True)
+            ev.record(copy_stream)
+
     def e2e_step(i):
-        x = host_x[i % 4].to(dev, non_blocking=True)
-        y = host_y[i % 4].to(dev, non_blocking=True)
-        return step(x, y).item()
+        bx, by, ev = slots[i % 2]
+        torch.cuda.current_stream().wait_event(ev)
+        loss = step(bx, by)
+        prefetch(i + 1)
+        return loss.item()
+    prefetch(0)
     e2e_step(0)
-    ms_e2e = timed(e2e_step, args.steps)
+    # steps are numbered 1..K here so that the slot primed by the warm-up call is the one step 1 reads
+    ms_e2e = timed(lambda i: e2e_step(i + 1), args.steps)
     clocks = sampler.stop()
 
     # per-op CUDA-event breakdown of one step -> roofline of the dominant kernel class
