@@ -16,6 +16,7 @@
 #include "sliding.cuh"
 #include "metrics.cuh"
 #include "tc_gemm.cuh"
+#include "tc_attention.cuh"
 #include "tc_conv_halo.cuh"
 #include "tc_wgrad_halo.cuh"
 
@@ -420,6 +421,12 @@ void b200_test_set_debug_buffer(void* dev_ptr) { tc::g_dbg = (long long*)dev_ptr
 
 int b200_test_tc_gemm(const void* a, const void* b, float* out, int M, int N, int K, int a_mn, int b_mn, void* stream) {
   return tc_gemm_test((const bf16*)a, (const bf16*)b, out, M, N, K, a_mn, b_mn, (cudaStream_t)stream);
+}
+
+// test hook for the fused attention forward: qkv [B*L][3H] bf16 -> probs [B][nh][L][Lp] bf16 (may be NULL), att [B*L][H] bf16
+int b200_test_tc_attention(const void* qkv, void* probs, void* att, int B, int heads, int L, int Lp, int H, float scale, void* stream) {
+  B200_CHECK(tc::attention_fused_supported(L, Lp, H, heads), "fused attention needs head_dim 64, 16 <= L <= 256, Lp %% 8 == 0");
+  return tc::attention_fused_fwd((const bf16*)qkv, (bf16*)probs, (bf16*)att, B, heads, L, Lp, H, scale, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -13,6 +13,7 @@
 #include "ops.cuh"
 #include "edge_kernels.cuh"
 #include "tc_gemm.cuh"
+#include "tc_attention.cuh"
 #include "tc_conv.cuh"
 #include "tc_conv_halo.cuh"
 #include "tc_wgrad_halo.cuh"
@@ -631,6 +632,10 @@ struct Exec {
     long sQb = (long)L * 3 * H, sPb = (long)nh * L * Lp, sPh = (long)L * Lp;
     int BH = c.B * nh;
     bool fused_sm = false;
+    if constexpr (kTC) {
+      // one kernel per layer: S = Q K^T in TMEM, softmax per TMEM lane, P through shared memory into the P V MMA (tc_attention.cuh)
+      if (tc::attention_fused_supported(L, Lp, H, nh)) return tc::attention_fused_fwd(qkv, w.P[i], w.att[i], c.B, nh, L, Lp, H, scale, st);
+    }
     if constexpr (kTC) {
       // scores stay in TMEM: softmax in the QK^T epilogue.  Measured SLOWER at L = 216 (0.30 -> 0.38 ms per 12 layers): one 224-wide tile
       // per (head, row block) leaves 48 CTAs with a serial two-pass epilogue; opt-in experiment only

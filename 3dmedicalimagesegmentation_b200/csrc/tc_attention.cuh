@@ -1,0 +1,265 @@
+// Fused short-sequence self-attention forward on tcgen05 / TMEM (SABlock.forward; L = 216 tokens at 96^3):
+//
+//   O[b, l, h*64 + d] = sum_j softmax_j(scale * Q[b,h,l,:] . K[b,h,j,:]) * V[b,h,j,d]          head_dim = 64, L <= 256
+//
+// One CTA per (batch, head, 128-row block of queries).  The whole key axis fits one TMEM tile (N = L rounded up to 16 <= 256
+// fp32 columns), so there is no online-softmax rescaling and the scores never leave the SM:
+//   warp 0      TMA: Q block [128 x 64], K [LK x 64] (both K-major, 128B swizzle), V as LK/64 boxes [64 keys x 64] (MN-major B)
+//   warp 1      MMA: S = Q K^T  (4 x tcgen05.mma 128 x LK x 16)  ->  TMEM columns [0, LK)
+//               ... softmax warps publish P (bf16) in shared memory ...
+//               O = P V   (LK/16 x tcgen05.mma 128 x 64 x 16)   ->  TMEM columns [256, 320)
+//   warps 2..9  two threads per query row (TMEM lane; warps 2..5 take the first half of the key columns, 6..9 the second): the
+//               scores are read from TMEM once into registers, (max, sum) are exchanged through shared memory, P is written as
+//               bf16 into the 128B-swizzled K-major A-operand layout the second MMA reads (and to global memory for the
+//               backward pass); finally O -> bf16 -> att[b, l, h*64 ..].
+// Replaces GEMM + softmax kernel + GEMM (3 launches, fp32 scores through L2) of exec.cuh::attention_fwd.
+#pragma once
+#include "tc_gemm.cuh"
+
+namespace b200 {
+namespace tc {
+
+struct AttnParams {
+  int L, LK, Lp, H, nh, tiles_m;     // LK = L rounded up to 16; Lp = row pitch of the stored probabilities
+  float scale;
+  bf16* P;                           // [B][nh][L][Lp] probabilities for the backward pass, or nullptr (inference)
+  bf16* att;                         // [B*L][H]
+  long long* trace;
+  long long* dbg;                    // optional: CTA 0 phase stamps (clock64)
+};
+
+__device__ __forceinline__ float ex2_ftz(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+// 32 consecutive TMEM columns of this thread's lane as two x16 loads behind ONE wait (the second is skipped when `two` is false;
+// its registers are then zero)
+__device__ __forceinline__ void tmem_ld16x2(uint32_t taddr, float* v, bool two) {
+  uint32_t r[32];
+#pragma unroll
+  for (int i = 16; i < 32; ++i) r[i] = 0u;
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr) : "memory");
+  if (two)
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+        : "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr + 16u) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// issue one x16 TMEM load without waiting (the caller runs tcgen05.wait::ld before the first use of v)
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, float* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+      : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]), "=f"(v[8]),
+        "=f"(v[9]), "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15])
+      : "r"(taddr) : "memory");
+}
+
+static constexpr int ATT_Q_BYTES = 128 * 128, ATT_KV_BYTES = 256 * 128, ATT_P_BYTES = 4 * 128 * 128;
+static constexpr int ATT_SMEM = ATT_Q_BYTES + 2 * ATT_KV_BYTES + ATT_P_BYTES + 1024 + 64 + 2 * 128 * 8;
+
+static __global__ void __launch_bounds__(320, 1)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v,
+                const AttnParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + ATT_Q_BYTES;
+  uint8_t* sV = sK + ATT_KV_BYTES;
+  uint8_t* sP = sV + ATT_KV_BYTES;
+  uint64_t* bar_qk = (uint64_t*)(sP + ATT_P_BYTES);
+  uint64_t* bar_v = bar_qk + 1;
+  uint64_t* bar_s = bar_qk + 2;
+  uint64_t* bar_p = bar_qk + 3;
+  uint64_t* bar_o = bar_qk + 4;
+  uint32_t* tmem_slot = (uint32_t*)(bar_qk + 5);
+  float2* xch = (float2*)(bar_qk + 8);           // [2 halves][128 rows] (local max, local sum)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // work item: (batch b, head h, query block tm)
+  int t = blockIdx.x;
+  const int tm = t % p.tiles_m; t /= p.tiles_m;
+  const int h = t % p.nh, b = t / p.nh;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&map_q); prefetch_tmap(&map_k); prefetch_tmap(&map_v);
+    mbar_init(bar_qk, 1); mbar_init(bar_v, 1); mbar_init(bar_s, 1); mbar_init(bar_p, 8); mbar_init(bar_o, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  trace_start(p.trace);
+  const bool dbg = p.dbg && blockIdx.x == 0;
+  if (dbg && threadIdx.x == 0) p.dbg[0] = clock64();
+
+  const int kboxes = (p.LK + 63) >> 6;
+  if (warp == 0) {
+    if (elect_one()) {
+      mbar_expect_tx(bar_qk, (uint32_t)(128 * 128 + p.LK * 128));
+      tma_load_4d(smem_u32(sQ), &map_q, bar_qk, 0, tm * 128, h, b);
+      tma_load_4d(smem_u32(sK), &map_k, bar_qk, 0, 0, h, b);
+      mbar_expect_tx(bar_v, (uint32_t)(kboxes * 64 * 128));
+      for (int c = 0; c < kboxes; ++c) tma_load_4d(smem_u32(sV) + c * (64 * 128), &map_v, bar_v, 0, c * 64, h, b);
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    const uint32_t hi = desc_hi(1024, 2);
+    // S = Q K^T : A = Q (K-major), B = K (K-major), N = LK
+    const uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.LK >> 3) << 17) | ((128u >> 4) << 24);
+    // O = P V   : A = P (K-major, written by the softmax warps), B = V (MN-major), N = 64
+    const uint32_t idesc_o = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+    mbar_wait(bar_qk, 0);
+    tc_fence_after();
+    if (dbg && lane == 0) p.dbg[1] = clock64();
+    if (elect_one()) {
+      const uint32_t q_lo = desc_lo(smem_u32(sQ), 16), k_lo = desc_lo(smem_u32(sK), 16);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) umma_f16(tmem_base, desc64(q_lo + j * 2u, hi), desc64(k_lo + j * 2u, hi), idesc_s, j ? 1u : 0u);
+      umma_commit(bar_s);
+    }
+    __syncwarp();
+    mbar_wait(bar_v, 0);
+    if (dbg && lane == 0) p.dbg[7] = clock64();
+    mbar_wait(bar_p, 0);
+    tc_fence_after();
+    if (elect_one()) {
+      const uint32_t p_lo = desc_lo(smem_u32(sP), 16), v_lo = desc_lo(smem_u32(sV), 64 * BK * 2);
+      const int ksteps = p.LK >> 4;
+      for (int j = 0; j < ksteps; ++j)
+        umma_f16(tmem_base + 256u, desc64(p_lo + (uint32_t)(j >> 2) * (16384u >> 4) + (uint32_t)(j & 3) * 2u, hi),
+                 desc64(v_lo + (uint32_t)j * (2048u >> 4), hi), idesc_o, j ? 1u : 0u);
+      umma_commit(bar_o);
+    }
+    __syncwarp();
+  } else {
+    // ---- softmax + epilogue: warps 2..5 own the first half of the key columns, warps 6..9 the second half; thread = query row.
+    // Each thread reads its <= 128 scores from TMEM ONCE (all loads behind one wait), keeps them in registers, and the two
+    // threads of a row exchange (max, sum) through shared memory.  Branch-free: scores go to the log2 domain once
+    // (s2 = scale * log2 e), every exponential is one MUFU.EX2 (ex2.approx.ftz), masked columns carry -inf (ex2 = 0), and the
+    // normalised probability is e * f with ONE factor f = 2^(local max - row max) / row sum per thread (no second exp pass).
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    const int row = q * 32 + lane;                // TMEM lane = query row inside the block
+    const int m = tm * 128 + row;                 // query index inside the (batch, head)
+    const bool valid = m < p.L;
+    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+    const int nch = p.LK >> 4, nch_a = (nch + 1) >> 1;
+    const int ch0 = half ? nch_a : 0, myn = half ? nch - nch_a : nch_a;      // my 16-column chunks: [ch0, ch0 + myn), myn <= 8
+    const int col0 = ch0 * 16;
+    const float s2 = p.scale * 1.4426950408889634f;
+    mbar_wait(bar_s, 0);
+    tc_fence_after();
+    if (dbg && warp == 2 && lane == 0) p.dbg[2] = clock64();
+    float v[128];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      if (c < myn) tmem_ld16_issue(trow + (uint32_t)(col0 + 16 * c), v + 16 * c);
+      else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[16 * c + j] = -INFINITY;
+      }
+    }
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+    for (int j = 0; j < 128; ++j) { v[j] = (col0 + j < p.L) ? v[j] * s2 : -INFINITY; m4[j & 3] = fmaxf(m4[j & 3], v[j]); }
+    const float mxl = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+    const float mref = mxl == -INFINITY ? 0.f : mxl;       // a half without a valid column (tiny L): all e = 0, no NaN
+    float s4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < 128; ++j) { v[j] = ex2_ftz(v[j] - mref); s4[j & 3] += v[j]; }
+    const float suml = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+    xch[half * 128 + row] = make_float2(mxl, suml);
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    const float2 o = xch[(half ^ 1) * 128 + row];
+    const float mxg = fmaxf(mxl, o.x);                      // finite: the first half always holds column 0
+    const float sumg = suml * ex2_ftz(mxl - mxg) + o.y * ex2_ftz(o.x - mxg);
+    const float f = ex2_ftz(mref - mxg) / sumg;
+    if (dbg && warp == 2 && lane == 0) p.dbg[3] = clock64();
+    bf16* prow = p.P ? p.P + (((long)b * p.nh + h) * p.L + m) * p.Lp : nullptr;
+    uint8_t* srow = sP + row * 128;
+    const int sw = row & 7;
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {                          // 8 columns = one 16-byte chunk per step
+      if (u < 2 * myn) {
+        uint32_t pk[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          __nv_bfloat162 h2 = __floats2bfloat162_rn(v[8 * u + 2 * j] * f, v[8 * u + 2 * j + 1] * f);
+          pk[j] = *reinterpret_cast<uint32_t*>(&h2);
+        }
+        const int c = col0 + 8 * u;
+        // K-major 128B-swizzled A operand: k-block of 64 keys = [128 rows][128 B]; 16-byte chunk ch of row r sits at ch ^ (r & 7)
+        *reinterpret_cast<uint4*>(srow + (c >> 6) * 16384 + ((((c & 63) >> 3) ^ sw) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        if (prow && valid && c + 8 <= p.Lp) *reinterpret_cast<uint4*>(prow + c) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      }
+    }
+    // generic-proxy smem writes -> visible to the tensor core (async proxy), then hand over to the MMA warp
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_p);
+    if (dbg && warp == 2 && lane == 0) p.dbg[4] = clock64();
+    mbar_wait(bar_o, 0);
+    tc_fence_after();
+    if (dbg && warp == 2 && lane == 0) p.dbg[5] = clock64();
+    bf16* orow = p.att + ((long)b * p.L + m) * p.H + h * 64 + half * 32;      // each half stores 32 of the 64 output columns
+    float ov[32];
+    tmem_ld16x2(trow + 256u + (uint32_t)(half * 32), ov, true);
+    if (valid) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        uint32_t pk[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { __nv_bfloat162 h2 = __floats2bfloat162_rn(ov[8 * u + 2 * j], ov[8 * u + 2 * j + 1]); pk[j] = *reinterpret_cast<uint32_t*>(&h2); }
+        *reinterpret_cast<uint4*>(orow + 8 * u) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  trace_end(p.trace);
+  if (dbg && threadIdx.x == 0) p.dbg[6] = clock64();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+static inline bool attention_fused_supported(int L, int Lp, int H, int nh) {
+  static const bool off = getenv("B200_NO_FUSED_ATTENTION") != nullptr;
+  return !off && nh > 0 && H / nh == 64 && H % 8 == 0 && L >= 16 && ((L + 15) & ~15) <= 256 && Lp % 8 == 0 && Lp >= L;
+}
+
+// qkv: [B*L][3H] bf16, columns [Q | K | V], head h at h*64 inside each third.  P (optional): [B][nh][L][Lp].  att: [B*L][H].
+static int attention_fused_fwd(const bf16* qkv, bf16* P, bf16* att, int B, int nh, int L, int Lp, int H, float scale, cudaStream_t st) {
+  const int dh = 64;
+  const long sQb = (long)L * 3 * H;
+  AttnParams p;
+  p.L = L; p.LK = (L + 15) & ~15; p.Lp = Lp; p.H = H; p.nh = nh; p.tiles_m = cdiv(L, 128); p.scale = scale; p.P = P; p.att = att;
+  CUtensorMap mq, mk, mv;
+  B200_TRY(make_map(&mq, operand(qkv, 3 * H, 1, sQb, dh), L, dh, 128, B, nh));
+  B200_TRY(make_map(&mk, operand(qkv + H, 3 * H, 1, sQb, dh), L, dh, p.LK, B, nh));
+  B200_TRY(make_map(&mv, operand(qkv + 2 * H, 1, 3 * H, sQb, dh), dh, L, 64, B, nh));
+  static bool attr_done = false;
+  if (!attr_done) { B200_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM)); attr_done = true; }
+  p.trace = trace_slot(); if (p.trace) trace_tag("attn_fwd L%d b%d", L, B * nh);
+  p.dbg = g_dbg;
+  B200_CUDA(launch_pdl(attn_fwd_kernel, dim3(B * nh * p.tiles_m), dim3(320), (size_t)ATT_SMEM, st, mq, mk, mv, p));
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace tc
+}  // namespace b200

@@ -157,6 +157,10 @@ void b200_trace_begin(void* buf, int cap);
 int b200_trace_count(void);
 int b200_trace_tags(char* out, int cap);
 int b200_test_tc_gemm(const void* a, const void* b, float* out, int M, int N, int K, int a_mn, int b_mn, void* stream);
+/* op-level hook for the fused attention forward (SABlock): qkv [B*L][3H] bf16 with columns [Q|K|V] x head x 64;
+ * probs [B][heads][L][Lp] bf16 (softmax(scale QK^T), may be NULL); att [B*L][H] bf16.  head_dim 64, 16 <= L <= 256. */
+int b200_test_tc_attention(const void* qkv, void* probs, void* att, int batch, int heads, int L, int Lp, int H, float scale,
+                           void* stream);
 
 #ifdef __cplusplus
 }

@@ -27,3 +27,38 @@ def test_tc_gemm_matches_fp32(pkg, a_mn, b_mn, M, N, K):
     torch.cuda.synchronize()
     err = ((out.cpu() - want).abs().max() / want.abs().max()).item()
     assert err <= 1e-3, err
+
+
+@pytest.mark.parametrize("B,heads,L", [(2, 12, 216), (4, 12, 216), (1, 2, 64), (3, 4, 200), (1, 3, 256), (2, 2, 27)])
+def test_fused_attention_matches_fp32(pkg, B, heads, L):
+    """tc_attention.cuh (SABlock) against torch fp32 softmax(scale q k^T) v on the same bf16 q, k, v.
+    Tolerances: probabilities are stored as bf16 (relative rounding 2^-9 -> 4e-3 of max|P|); the output accumulates bf16
+    probabilities in fp32 and is stored as bf16 -> 1e-2 of max|O| (the bf16-mode budget of the north_star)."""
+    lib = pkg._lib.load()
+    H, Lp = heads * 64, (L + 7) & ~7
+    g = torch.Generator().manual_seed(B * 1000 + L)
+    qkv = torch.randn(B * L, 3 * H, generator=g).to(torch.bfloat16)
+    scale = 64 ** -0.5
+    f = qkv.float().view(B, L, 3, heads, 64)
+    q, k, v = (f[:, :, i].permute(0, 2, 1, 3) for i in range(3))          # [B, heads, L, 64]; columns are [Q|K|V] x head x d (a7)
+    p_want = torch.softmax(q @ k.transpose(-1, -2) * scale, dim=-1)
+    o_want = (p_want @ v).permute(0, 2, 1, 3).reshape(B * L, H)
+    qkv_d = qkv.to(DEV)
+    probs = torch.full((B, heads, L, Lp), float("nan"), dtype=torch.bfloat16, device=DEV)
+    att = torch.full((B * L, H), float("nan"), dtype=torch.bfloat16, device=DEV)
+    if L < 16:
+        pytest.skip("fused kernel takes 16 <= L <= 256")
+    pkg._lib.check(lib.b200_test_tc_attention(pkg._lib.ptr(qkv_d), pkg._lib.ptr(probs), pkg._lib.ptr(att), B, heads, L, Lp, H, scale,
+                                               pkg._lib.stream_ptr()), "tc_attention")
+    torch.cuda.synchronize()
+    p_got = probs.float().cpu()
+    assert torch.isfinite(p_got).all() and torch.isfinite(att.float()).all()
+    assert (p_got[..., :L] - p_want).abs().max().item() <= 4e-3 * p_want.max().item()
+    assert (p_got[..., L:] == 0).all()
+    err = ((att.float().cpu() - o_want).abs().max() / o_want.abs().max()).item()
+    assert err <= 1e-2, err
+    # probabilities are optional (inference)
+    att2 = torch.zeros_like(att)
+    pkg._lib.check(lib.b200_test_tc_attention(pkg._lib.ptr(qkv_d), None, pkg._lib.ptr(att2), B, heads, L, Lp, H, scale,
+                                               pkg._lib.stream_ptr()), "tc_attention")
+    assert torch.equal(att2, att)
