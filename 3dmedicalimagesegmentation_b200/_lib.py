@@ -14,6 +14,7 @@ PARAM_COUNT = 164
 FLAG_NEED_ENCODER_GRAD = 1
 FLAG_HAS_DLOGITS = 2
 FLAG_HAS_DENC4 = 4
+FLAG_NO_BACKWARD = 16
 FLAG_WEIGHTS_PACKED = 64
 
 

@@ -40,7 +40,7 @@ enum ParamIdx {
 };
 enum { B_LN1_W = 0, B_LN1_B, B_QKV_W, B_PROJ_W, B_PROJ_B, B_LN2_W, B_LN2_B, B_FC1_W, B_FC1_B, B_FC2_W, B_FC2_B, B_COUNT };
 
-enum { FLAG_NEED_ENCODER_GRAD = 1, FLAG_HAS_DLOGITS = 2, FLAG_HAS_DENC4 = 4, FLAG_SAVE_FOR_BACKWARD = 8,
+enum { FLAG_NEED_ENCODER_GRAD = 1, FLAG_HAS_DLOGITS = 2, FLAG_HAS_DENC4 = 4, FLAG_SAVE_FOR_BACKWARD = 8, FLAG_NO_BACKWARD = 16,   // forward only: no backward call follows (inference)
        FLAG_WEIGHTS_PACKED = 64 };   // the bf16 weight copies in this workspace are current (same workspace, unchanged parameters)
 
 struct Bump {
@@ -513,6 +513,7 @@ struct Exec {
   // ------------------------------------------------------------ forward
   int forward(const float* const* P, const float* x_in, char* ws, float* enc4_out, float* logits_out, int flags, cudaStream_t st) {
     layout(ws, false);
+    no_backward = (flags & FLAG_NO_BACKWARD) != 0;
     B200_CUDA(cudaMemsetAsync(w.stat_pool, 0, sizeof(double) * kStatSlots * 4 * c.B * 8 * c.fs, st));
     B200_PROFC_BEGIN("F1 pack+patch", st);
     int B = c.B, fs = c.fs;
@@ -622,6 +623,7 @@ struct Exec {
     return simt_convT_fwd<T, T>(x, ldx, Ci, sp(in_level), W, out, st);
   }
   const float* const* cur_params = nullptr;
+  bool no_backward = false;     // FLAG_NO_BACKWARD of the current forward: buffers only the backward reads are not written
   cudaEvent_t grad_ev[4]; int n_grad_ev = 0;   // see ExecIface::set_grad_events
   void mark_grads(int k, cudaStream_t st) { if (n_grad_ev == 4) cudaEventRecord(grad_ev[k], st); }
 
@@ -634,7 +636,8 @@ struct Exec {
     bool fused_sm = false;
     if constexpr (kTC) {
       // one kernel per layer: S = Q K^T in TMEM, softmax per TMEM lane, P through shared memory into the P V MMA (tc_attention.cuh)
-      if (tc::attention_fused_supported(L, Lp, H, nh)) return tc::attention_fused_fwd(qkv, w.P[i], w.att[i], c.B, nh, L, Lp, H, scale, st);
+      if (tc::attention_fused_supported(L, Lp, H, nh))
+        return tc::attention_fused_fwd(qkv, no_backward ? nullptr : w.P[i], w.att[i], c.B, nh, L, Lp, H, scale, st);
     }
     if constexpr (kTC) {
       // scores stay in TMEM: softmax in the QK^T epilogue.  Measured SLOWER at L = 216 (0.30 -> 0.38 ms per 12 layers): one 224-wide tile

@@ -171,14 +171,27 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       }
     }
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    // columns >= L exist only in the chunk that straddles L (L is not a multiple of 16): mask that one chunk (warp-uniform branch);
+    // chunks past my range already hold -inf.  max commutes with the positive scale, so the scores stay raw until the one FFMA
+    // that feeds the exponential: FMNMX + FFMA + MUFU + FADD per element.
+    {
+      const int lim = p.L - col0;                // my columns [lim, ...) are padding
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        if (c < myn && 16 * c + 16 > lim) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) if (16 * c + j >= lim) v[16 * c + j] = -INFINITY;
+        }
+    }
     float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-    for (int j = 0; j < 128; ++j) { v[j] = (col0 + j < p.L) ? v[j] * s2 : -INFINITY; m4[j & 3] = fmaxf(m4[j & 3], v[j]); }
-    const float mxl = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
-    const float mref = mxl == -INFINITY ? 0.f : mxl;       // a half without a valid column (tiny L): all e = 0, no NaN
+    for (int j = 0; j < 128; ++j) m4[j & 3] = fmaxf(m4[j & 3], v[j]);
+    const float mraw = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+    const float mxl = mraw * s2;                            // local max in the log2 domain (-inf for a half without valid columns)
+    const float mref = mraw == -INFINITY ? 0.f : mxl;       // ... whose e are then all 0, without NaN
     float s4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int j = 0; j < 128; ++j) { v[j] = ex2_ftz(v[j] - mref); s4[j & 3] += v[j]; }
+    for (int j = 0; j < 128; ++j) { v[j] = ex2_ftz(fmaf(v[j], s2, -mref)); s4[j & 3] += v[j]; }
     const float suml = (s4[0] + s4[1]) + (s4[2] + s4[3]);
     xch[half * 128 + row] = make_float2(mxl, suml);
     asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -187,7 +200,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     const float sumg = suml * ex2_ftz(mxl - mxg) + o.y * ex2_ftz(o.x - mxg);
     const float f = ex2_ftz(mref - mxg) / sumg;
     if (dbg && warp == 2 && lane == 0) p.dbg[3] = clock64();
-    bf16* prow = p.P ? p.P + (((long)b * p.nh + h) * p.L + m) * p.Lp : nullptr;
     uint8_t* srow = sP + row * 128;
     const int sw = row & 7;
 #pragma unroll
@@ -202,7 +214,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         const int c = col0 + 8 * u;
         // K-major 128B-swizzled A operand: k-block of 64 keys = [128 rows][128 B]; 16-byte chunk ch of row r sits at ch ^ (r & 7)
         *reinterpret_cast<uint4*>(srow + (c >> 6) * 16384 + ((((c & 63) >> 3) ^ sw) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-        if (prow && valid && c + 8 <= p.Lp) *reinterpret_cast<uint4*>(prow + c) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
       }
     }
     // generic-proxy smem writes -> visible to the tensor core (async proxy), then hand over to the MMA warp
@@ -211,6 +222,21 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     __syncwarp();
     if (lane == 0) mbar_arrive(bar_p);
     if (dbg && warp == 2 && lane == 0) p.dbg[4] = clock64();
+    if (p.P) {
+      // probabilities for the backward pass: copied out of the swizzled smem tile as whole rows (Lp * 2 contiguous bytes per warp
+      // store; per-thread row stores were 32 sectors per instruction), while the P V MMAs run
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const int wi = warp - 2;
+      bf16* pbase = p.P + (((long)b * p.nh + h) * p.L) * p.Lp;
+      const int nchunk = p.Lp >> 3;                          // 16-byte chunks per stored row (Lp % 8 == 0)
+#pragma unroll 4
+      for (int r = 0; r < 16; ++r) {
+        const int rr = wi * 16 + r, mr = tm * 128 + rr;
+        if (mr < p.L && lane < nchunk)
+          *reinterpret_cast<uint4*>(pbase + (long)mr * p.Lp + lane * 8) =
+              *reinterpret_cast<const uint4*>(sP + (lane >> 3) * 16384 + rr * 128 + (((lane & 7) ^ (rr & 7)) << 4));
+      }
+    }
     mbar_wait(bar_o, 0);
     tc_fence_after();
     if (dbg && warp == 2 && lane == 0) p.dbg[5] = clock64();

@@ -121,7 +121,7 @@ class _UnetrFunction(torch.autograd.Function):
         enc4 = torch.empty((batch, 8 * fs, s[0] // 8, s[1] // 8, s[2] // 8), dtype=torch.float32, device=x.device)
         logits = torch.empty((batch, module.out_channels, *s), dtype=torch.float32, device=x.device)
         table = module._param_table(params)
-        flags = (0 if freeze_encoder else _lib.FLAG_NEED_ENCODER_GRAD) | packed
+        flags = (0 if freeze_encoder else _lib.FLAG_NEED_ENCODER_GRAD) | packed | (0 if needs_grad else _lib.FLAG_NO_BACKWARD)
         _lib.check(lib.b200_unetr_forward(handle, table, _lib.ptr(x), _lib.ptr(ws), _lib.ptr(enc4), _lib.ptr(logits),
                                           flags, _lib.stream_ptr()), "b200_unetr_forward")
         ctx.module, ctx.freeze, ctx.handle = module, bool(freeze_encoder), handle
