@@ -52,6 +52,7 @@ SIGNATURES = {
     "b200_ranking_backward": (c_int, [POINTER(RankGeom), c_void_p, c_void_p, c_void_p]),
     "b200_sw_gather": (c_int, [c_void_p, c_void_p, POINTER(SwGeom), POINTER(c_int32), c_int, c_float, c_void_p]),
     "b200_sw_accumulate": (c_int, [c_void_p, c_void_p, POINTER(SwGeom), POINTER(c_int32), c_void_p]),
+    "b200_sw_accumulate_n": (c_int, [c_void_p, c_void_p, POINTER(SwGeom), POINTER(c_int32), c_int, c_void_p]),
     "b200_sw_finalize": (c_int, [c_void_p, c_void_p, c_void_p, POINTER(SwGeom), c_int, POINTER(c_int32), c_int,
                                  POINTER(c_int32), c_int, POINTER(c_int32), c_int, c_void_p]),
     "b200_sw_finalize_metric": (c_int, [c_void_p, c_void_p, c_void_p, POINTER(SwGeom), c_int, POINTER(c_int32), c_int,

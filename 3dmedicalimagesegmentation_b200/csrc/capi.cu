@@ -295,6 +295,25 @@ int b200_sw_accumulate(float* acc, const float* pred, const b200_sw_geom* g, con
   B200_LAUNCH_CHECK();
   return 0;
 }
+int b200_sw_accumulate_n(float* acc, const float* pred, const b200_sw_geom* g, const int32_t* starts, int n, void* stream) {
+  B200_CHECK(n >= 1 && n <= 16, "sw_accumulate_n takes 1..16 windows per call");
+  SwGeom sg = to_sw(g);
+  SwBatch wb; wb.n = n;
+  SwBox bx; int x1 = 0, y1 = 0, z1 = 0;
+  for (int i = 0; i < n; ++i) {
+    wb.w[i] = SwWindow{starts[4 * i], starts[4 * i + 1], starts[4 * i + 2], starts[4 * i + 3]};
+    B200_CHECK(wb.w[i].b == wb.w[0].b, "sw_accumulate_n: the windows of one call belong to one batch item");
+    const int a = wb.w[i].s0, b = wb.w[i].s1, c = wb.w[i].s2;
+    if (i == 0) { bx.x0 = a; bx.y0 = b; bx.z0 = c; x1 = a; y1 = b; z1 = c; }
+    bx.x0 = std::min(bx.x0, a); bx.y0 = std::min(bx.y0, b); bx.z0 = std::min(bx.z0, c);
+    x1 = std::max(x1, a); y1 = std::max(y1, b); z1 = std::max(z1, c);
+  }
+  bx.nx = x1 - bx.x0 + sg.r0; bx.ny = y1 - bx.y0 + sg.r1; bx.nz = z1 - bx.z0 + sg.r2;
+  long rows = (long)bx.nx * bx.ny * sg.C;         // one warp per (c, x, y) line
+  sw_accumulate_multi_kernel<<<(unsigned)min(148L * 16, (rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(acc, pred, sg, wb, bx);
+  B200_LAUNCH_CHECK();
+  return 0;
+}
 int b200_sw_finalize_metric(const float* acc, float* out, uint8_t* mask, const b200_sw_geom* g, int batch, const int32_t* s0, int n0,
                             const int32_t* s1, int n1, const int32_t* s2, int n2, const float* labels, double* counts, void* stream) {
   B200_CHECK(n0 <= 64 && n1 <= 64 && n2 <= 64, "more than 64 window starts along one axis");

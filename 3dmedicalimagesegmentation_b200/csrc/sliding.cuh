@@ -43,6 +43,40 @@ static __global__ void sw_accumulate_kernel(float* __restrict__ acc, const float
     acc[o] += pred[e];
   }
 }
+// the same overlap-add for n windows of ONE batch item in one launch: a thread owns an accumulator voxel of the windows' bounding
+// box and adds the predictions of the windows that cover it in window order -- the per-voxel sequence of float additions is
+// exactly the one the per-window launches (and MONAI's loop) produce, but a voxel covered twice is read and written once.
+struct SwBox { int x0, y0, z0, nx, ny, nz; };
+static __global__ void __launch_bounds__(256) sw_accumulate_multi_kernel(float* __restrict__ acc, const float* __restrict__ pred, SwGeom g, SwBatch wb, SwBox bx) {
+  // one warp per (channel, x, y) line of the bounding box: the line's window membership along x and y is decided once, the lanes
+  // walk z (coalesced 128-byte accumulator accesses), and only the z test is left per element
+  const long per = (long)g.r0 * g.r1 * g.r2;
+  const long rows = (long)g.C * bx.nx * bx.ny;
+  const int b = wb.w[0].b, lane = threadIdx.x & 31;
+  const long warps = ((long)gridDim.x * blockDim.x) >> 5;
+  for (long row = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < rows; row += warps) {
+    long r = row;
+    const int y = bx.y0 + (int)(r % bx.ny); r /= bx.ny; const int x = bx.x0 + (int)(r % bx.nx); const int c = (int)(r / bx.nx);
+    unsigned live = 0;
+    for (int k = 0; k < wb.n; ++k)
+      if ((unsigned)(x - wb.w[k].s0) < (unsigned)g.r0 && (unsigned)(y - wb.w[k].s1) < (unsigned)g.r1) live |= 1u << k;
+    if (!live) continue;
+    float* arow = acc + ((((long)b * g.C + c) * g.PD + x) * g.PH + y) * g.PW;
+    for (int zi = lane; zi < bx.nz; zi += 32) {
+      const int z = bx.z0 + zi;
+      float a = 0.f; bool any = false;
+#pragma unroll 1
+      for (int k = 0; k < wb.n; ++k) {
+        const int dz = z - wb.w[k].s2;
+        if (((live >> k) & 1u) && (unsigned)dz < (unsigned)g.r2) {
+          if (!any) { a = arow[z]; any = true; }
+          a += pred[((long)k * g.C + c) * per + ((long)(x - wb.w[k].s0) * g.r1 + (y - wb.w[k].s1)) * g.r2 + dz];
+        }
+      }
+      if (any) arow[z] = a;
+    }
+  }
+}
 struct SwStarts { int n0, n1, n2; int s0[64], s1[64], s2[64]; };
 // out[b][c][d][h][w] = acc[b][c][d+pd][h+ph][w+pw] / count ; optional argmax over c -> mask[b][d][h][w] ;
 // optional validation tail (seg:110-126): with `labels` [B][D][H][W] (integer-valued floats) the argmax is

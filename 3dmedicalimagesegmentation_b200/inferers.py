@@ -115,9 +115,17 @@ def _sw_loop(lib, x, items, mine, sw_batch_size, chan, roi, gin, cval, st, predi
             cout = pred.shape[1]
             acc = torch.zeros((batch, cout, *size), dtype=torch.float32, device=x.device)
             gout = _lib.SwGeom(cout, *orig, *pad, *size, *roi)
-        for k, it in enumerate(chunk):   # one launch per window: keeps the reference's summation order
-            s4 = (ctypes.c_int32 * 4)(*it)
-            _lib.check(lib.b200_sw_accumulate(_lib.ptr(acc), _lib.ptr(pred[k]), ctypes.byref(gout), s4, st), "b200_sw_accumulate")
+        # one launch per run of windows of the same batch item; every accumulator voxel adds its windows in window order, so the
+        # sums are bit-identical to the reference's one-window-at-a-time loop
+        k0 = 0
+        while k0 < n:
+            k1 = k0
+            while k1 < n and chunk[k1][0] == chunk[k0][0]:
+                k1 += 1
+            sN = (ctypes.c_int32 * (4 * (k1 - k0)))(*[v for it in chunk[k0:k1] for v in it])
+            _lib.check(lib.b200_sw_accumulate_n(_lib.ptr(acc), _lib.ptr(pred[k0]), ctypes.byref(gout), sN, k1 - k0, st),
+                       "b200_sw_accumulate_n")
+            k0 = k1
     return acc, gout
 
 

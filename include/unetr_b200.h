@@ -107,6 +107,9 @@ typedef struct {
 int b200_sw_gather(const float* volume, float* windows, const b200_sw_geom* g, const int32_t* starts, int n, float cval,
                    void* stream);
 int b200_sw_accumulate(float* acc, const float* pred, const b200_sw_geom* g, const int32_t* start4, void* stream);
+/* the same overlap-add for n <= 16 windows of one batch item in one launch (pred: [n,C,roi]); per-voxel addition order =
+ * window order, so the result is bit-identical to n calls of b200_sw_accumulate */
+int b200_sw_accumulate_n(float* acc, const float* pred, const b200_sw_geom* g, const int32_t* starts, int n, void* stream);
 /* per-axis window starts (n0,n1,n2 <= 64).  out and/or mask (uint8 argmax) may be NULL. */
 int b200_sw_finalize(const float* acc, float* out, uint8_t* mask, const b200_sw_geom* g, int batch, const int32_t* s0,
                      int n0, const int32_t* s1, int n1, const int32_t* s2, int n2, void* stream);

@@ -489,3 +489,27 @@ def test_sliding_window_fused_validation_tail(pkg):
     none, mask2, counts2 = pkg.sliding_window_inference(x.to(DEV), (16,) * 3, 4, f_gpu, overlap=0.25, labels=lab.to(DEV),
                                                         return_logits=False)
     assert none is None and torch.equal(mask2, mask) and torch.equal(counts2, counts)
+
+
+def test_multi_window_accumulate_is_bit_identical_to_window_loop(pkg):
+    """b200_sw_accumulate_n (one launch per predictor call) against the one-window-per-launch loop it replaces: identical bits,
+    because every voxel adds its windows in window order (MONAI's accumulation order, Appendix B.9)."""
+    import ctypes
+    L_ = pkg._lib; lib = L_.load()
+    C, roi, size = 3, (16, 12, 20), (40, 30, 48)
+    g = L_.SwGeom(C, *size, 0, 0, 0, *size, *roi)
+    gen = torch.Generator().manual_seed(11)
+    for starts in ([(0, 0, 0, 0), (0, 0, 0, 10), (0, 0, 0, 20), (0, 0, 0, 28)],          # a run along z, 50 % overlaps
+                   [(0, 8, 18, 28), (0, 16, 0, 0), (0, 16, 0, 10)],                      # wraps to the next row of windows
+                   [(0, 24, 18, 28)], [(0, 0, 0, 0), (0, 0, 0, 0)]):                     # single window; the same window twice
+        n = len(starts)
+        pred = torch.randn(n, C, *roi, generator=gen).to(DEV)
+        base = torch.randn(1, C, *size, generator=gen).to(DEV)
+        a, b = base.clone(), base.clone()
+        for k, it in enumerate(starts):
+            s4 = (ctypes.c_int32 * 4)(*it)
+            L_.check(lib.b200_sw_accumulate(L_.ptr(a), L_.ptr(pred[k]), ctypes.byref(g), s4, L_.stream_ptr()), "acc")
+        sN = (ctypes.c_int32 * (4 * n))(*[v for it in starts for v in it])
+        L_.check(lib.b200_sw_accumulate_n(L_.ptr(b), L_.ptr(pred), ctypes.byref(g), sN, n, L_.stream_ptr()), "acc_n")
+        assert torch.equal(a, b)
+        assert not torch.equal(a, base)
