@@ -448,4 +448,12 @@ int b200_test_tc_attention(const void* qkv, void* probs, void* att, int B, int h
   return tc::attention_fused_fwd((const bf16*)qkv, (bf16*)probs, (bf16*)att, B, heads, L, Lp, H, scale, (cudaStream_t)stream);
 }
 
+// query-row half of the attention backward: probs/datt in, dS [B][heads][L][Lp] and the Q third of dqkv [B*L][3H] out
+int b200_test_tc_attention_bwd(const void* qkv, const void* probs, const void* datt, void* dS, void* dqkv, int B, int heads, int L, int Lp,
+                               int H, float scale, void* stream) {
+  B200_CHECK(tc::attention_fused_supported(L, Lp, H, heads), "fused attention needs head_dim 64, 16 <= L <= 256, Lp %% 8 == 0");
+  return tc::attention_fused_bwd_dq((const bf16*)qkv, (const bf16*)probs, (const bf16*)datt, (bf16*)dS, (bf16*)dqkv, B, heads, L, Lp, H, scale,
+                                    (cudaStream_t)stream);
+}
+
 }  // extern "C"

@@ -666,6 +666,19 @@ struct Exec {
     const T* qkv = w.qkv[i];
     long sQb = (long)L * 3 * H, sPb = (long)nh * L * Lp, sPh = (long)L * Lp, sOb = (long)L * H;
     int BH = c.B * nh;
+    if constexpr (kTC) {
+      // query-row half in one kernel (tc_attention.cuh, BWD = 1): dP = dO V^T in TMEM -> dS (in place of the TMA-loaded P block in
+      // smem) -> dQ = dS K; the key-row half stays two batched GEMMs over P^T and dS^T
+      static const bool off = getenv("B200_NO_FUSED_ATTENTION_BWD") != nullptr;
+      if (!off && tc::attention_fused_supported(L, Lp, H, nh)) {
+        B200_TRY(tc::attention_fused_bwd_dq(qkv, w.P[i], w.datt, w.dS, w.dqkv, c.B, nh, L, Lp, H, scale, st));
+        { EpStore<T> ep = ep_plain<T>(w.dqkv + 2 * H, 3 * H); ep.sb0 = sQb; ep.sb1 = dh; ep.nb1 = nh;      // dV = P^T dO
+          B200_TRY(tc::gemm(tc::operand(w.P[i], 1, Lp, sPb, sPh), tc::operand(w.datt, 1, H, sOb, dh), ep, L, dh, L, c.B, nh, st)); }
+        { EpStore<T> ep = ep_plain<T>(w.dqkv + H, 3 * H); ep.sb0 = sQb; ep.sb1 = dh; ep.nb1 = nh;          // dK = dS^T Q
+          B200_TRY(tc::gemm(tc::operand(w.dS, 1, Lp, sPb, sPh), tc::operand(qkv, 1, 3 * H, sQb, dh), ep, L, dh, L, c.B, nh, st)); }
+        return 0;
+      }
+    }
     // dP = dO V^T ; dS = P * (dP - rowsum(dP * P)) * scale  -- in the GEMM epilogue when a row fits one tile
     bool fused_sm = false;
     if constexpr (kTC) {

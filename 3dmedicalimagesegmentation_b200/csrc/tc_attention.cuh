@@ -22,8 +22,10 @@ namespace tc {
 struct AttnParams {
   int L, LK, Lp, H, nh, tiles_m;     // LK = L rounded up to 16; Lp = row pitch of the stored probabilities
   float scale;
-  bf16* P;                           // [B][nh][L][Lp] probabilities for the backward pass, or nullptr (inference)
-  bf16* att;                         // [B*L][H]
+  bf16* P;                           // [B][nh][L][Lp]: forward = probabilities kept for the backward pass (nullptr in inference);
+                                     // backward = dS (out)
+  bf16* att;                         // forward: att [B*L][H]; backward: the Q third of dqkv [B*L][3H]
+  int out_pitch;                     // row pitch of `att` in elements
   long long* trace;
   long long* dbg;                    // optional: CTA 0 phase stamps (clock64)
 };
@@ -63,9 +65,16 @@ __device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, float* v) {
 static constexpr int ATT_Q_BYTES = 128 * 128, ATT_KV_BYTES = 256 * 128, ATT_P_BYTES = 4 * 128 * 128;
 static constexpr int ATT_SMEM = ATT_Q_BYTES + 2 * ATT_KV_BYTES + ATT_P_BYTES + 1024 + 64 + 2 * 128 * 8;
 
+// BWD = 0: forward as described above.
+// BWD = 1: the query-row half of the backward pass with the same data flow (attention_bwd in exec.cuh):
+//   "Q" = dO block, "K" = V (K-major)  ->  dP = dO V^T in TMEM
+//   row op: dS = P * (dP - sum_j dP_j P_j) * scale, with the P block TMA-loaded into the very smem tile (swizzled K-major A
+//           operand layout) that dS then overwrites in place
+//   "V" = K (MN-major)  ->  dQ = dS K ; dS is also copied out (whole rows) for the dK = dS^T Q product.
+template <int BWD>
 static __global__ void __launch_bounds__(320, 1)
-attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v,
-                const AttnParams p) {
+attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v,
+            const __grid_constant__ CUtensorMap map_p, const AttnParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* sQ = smem;
@@ -77,7 +86,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   uint64_t* bar_s = bar_qk + 2;
   uint64_t* bar_p = bar_qk + 3;
   uint64_t* bar_o = bar_qk + 4;
-  uint32_t* tmem_slot = (uint32_t*)(bar_qk + 5);
+  uint64_t* bar_pld = bar_qk + 5;               // BWD: the P block has landed in sP
+  uint32_t* tmem_slot = (uint32_t*)(bar_qk + 6);
   float2* xch = (float2*)(bar_qk + 8);           // [2 halves][128 rows] (local max, local sum)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -88,6 +98,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&map_q); prefetch_tmap(&map_k); prefetch_tmap(&map_v);
+    if (BWD) prefetch_tmap(&map_p);
+    mbar_init(bar_pld, 1);
     mbar_init(bar_qk, 1); mbar_init(bar_v, 1); mbar_init(bar_s, 1); mbar_init(bar_p, 8); mbar_init(bar_o, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -112,6 +124,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       tma_load_4d(smem_u32(sK), &map_k, bar_qk, 0, 0, h, b);
       mbar_expect_tx(bar_v, (uint32_t)(kboxes * 64 * 128));
       for (int c = 0; c < kboxes; ++c) tma_load_4d(smem_u32(sV) + c * (64 * 128), &map_v, bar_v, 0, c * 64, h, b);
+      if (BWD) {
+        mbar_expect_tx(bar_pld, (uint32_t)(kboxes * 128 * 128));
+        for (int c = 0; c < kboxes; ++c) tma_load_4d(smem_u32(sP) + c * 16384, &map_p, bar_pld, c * 64, tm * 128, h, b);
+      }
     }
     __syncwarp();
   } else if (warp == 1) {
@@ -171,49 +187,89 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       }
     }
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-    // columns >= L exist only in the chunk that straddles L (L is not a multiple of 16): mask that one chunk (warp-uniform branch);
-    // chunks past my range already hold -inf.  max commutes with the positive scale, so the scores stay raw until the one FFMA
-    // that feeds the exponential: FMNMX + FFMA + MUFU + FADD per element.
-    {
-      const int lim = p.L - col0;                // my columns [lim, ...) are padding
-#pragma unroll
-      for (int c = 0; c < 8; ++c)
-        if (c < myn && 16 * c + 16 > lim) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) if (16 * c + j >= lim) v[16 * c + j] = -INFINITY;
-        }
-    }
-    float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-#pragma unroll
-    for (int j = 0; j < 128; ++j) m4[j & 3] = fmaxf(m4[j & 3], v[j]);
-    const float mraw = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
-    const float mxl = mraw * s2;                            // local max in the log2 domain (-inf for a half without valid columns)
-    const float mref = mraw == -INFINITY ? 0.f : mxl;       // ... whose e are then all 0, without NaN
-    float s4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-    for (int j = 0; j < 128; ++j) { v[j] = ex2_ftz(fmaf(v[j], s2, -mref)); s4[j & 3] += v[j]; }
-    const float suml = (s4[0] + s4[1]) + (s4[2] + s4[3]);
-    xch[half * 128 + row] = make_float2(mxl, suml);
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    const float2 o = xch[(half ^ 1) * 128 + row];
-    const float mxg = fmaxf(mxl, o.x);                      // finite: the first half always holds column 0
-    const float sumg = suml * ex2_ftz(mxl - mxg) + o.y * ex2_ftz(o.x - mxg);
-    const float f = ex2_ftz(mref - mxg) / sumg;
-    if (dbg && warp == 2 && lane == 0) p.dbg[3] = clock64();
     uint8_t* srow = sP + row * 128;
     const int sw = row & 7;
+    if constexpr (BWD) {
+      // v = dP (fp32, raw).  P (bf16) is read from the TMA-loaded smem block, chunk by chunk, twice (64 packed registers would not
+      // fit next to v[128] at 320 threads); padding columns of P are zero-filled by the TMA, so dS is zero there.
+      mbar_wait(bar_pld, 0);
+      float d4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int u = 0; u < 16; ++u) {                          // 8 columns = one 16-byte chunk per step
-      if (u < 2 * myn) {
-        uint32_t pk[4];
+      for (int u = 0; u < 16; ++u)
+        if (u < 2 * myn) {
+          const int c = col0 + 8 * u;
+          const uint4 pv = *reinterpret_cast<const uint4*>(srow + (c >> 6) * 16384 + ((((c & 63) >> 3) ^ sw) << 4));
+          const uint32_t pw[4] = {pv.x, pv.y, pv.z, pv.w};
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          __nv_bfloat162 h2 = __floats2bfloat162_rn(v[8 * u + 2 * j] * f, v[8 * u + 2 * j + 1] * f);
-          pk[j] = *reinterpret_cast<uint32_t*>(&h2);
+          for (int j = 0; j < 4; ++j) {
+            const float2 pf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pw[j]));
+            d4[j] = fmaf(v[8 * u + 2 * j], pf.x, d4[j]);
+            d4[j] = fmaf(v[8 * u + 2 * j + 1], pf.y, d4[j]);
+          }
         }
-        const int c = col0 + 8 * u;
-        // K-major 128B-swizzled A operand: k-block of 64 keys = [128 rows][128 B]; 16-byte chunk ch of row r sits at ch ^ (r & 7)
-        *reinterpret_cast<uint4*>(srow + (c >> 6) * 16384 + ((((c & 63) >> 3) ^ sw) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      xch[half * 128 + row] = make_float2((d4[0] + d4[1]) + (d4[2] + d4[3]), 0.f);
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const float dot = xch[row].x + xch[128 + row].x;
+      if (dbg && warp == 2 && lane == 0) p.dbg[3] = clock64();
+#pragma unroll
+      for (int u = 0; u < 16; ++u)
+        if (u < 2 * myn) {
+          const int c = col0 + 8 * u;
+          uint4* slot = reinterpret_cast<uint4*>(srow + (c >> 6) * 16384 + ((((c & 63) >> 3) ^ sw) << 4));
+          const uint4 pv = *slot;
+          const uint32_t pw[4] = {pv.x, pv.y, pv.z, pv.w};
+          uint32_t pk[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 pf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pw[j]));
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(pf.x * (v[8 * u + 2 * j] - dot) * p.scale, pf.y * (v[8 * u + 2 * j + 1] - dot) * p.scale);
+            pk[j] = *reinterpret_cast<uint32_t*>(&h2);
+          }
+          *slot = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+    } else {
+      // columns >= L exist only in the chunk that straddles L (L is not a multiple of 16): mask that one chunk (warp-uniform branch);
+      // chunks past my range already hold -inf.  max commutes with the positive scale, so the scores stay raw until the one FFMA
+      // that feeds the exponential: FMNMX + FFMA + MUFU + FADD per element.
+      {
+        const int lim = p.L - col0;                // my columns [lim, ...) are padding
+  #pragma unroll
+        for (int c = 0; c < 8; ++c)
+          if (c < myn && 16 * c + 16 > lim) {
+  #pragma unroll
+            for (int j = 0; j < 16; ++j) if (16 * c + j >= lim) v[16 * c + j] = -INFINITY;
+          }
+      }
+      float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+  #pragma unroll
+      for (int j = 0; j < 128; ++j) m4[j & 3] = fmaxf(m4[j & 3], v[j]);
+      const float mraw = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+      const float mxl = mraw * s2;                            // local max in the log2 domain (-inf for a half without valid columns)
+      const float mref = mraw == -INFINITY ? 0.f : mxl;       // ... whose e are then all 0, without NaN
+      float s4[4] = {0.f, 0.f, 0.f, 0.f};
+  #pragma unroll
+      for (int j = 0; j < 128; ++j) { v[j] = ex2_ftz(fmaf(v[j], s2, -mref)); s4[j & 3] += v[j]; }
+      const float suml = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+      xch[half * 128 + row] = make_float2(mxl, suml);
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const float2 o = xch[(half ^ 1) * 128 + row];
+      const float mxg = fmaxf(mxl, o.x);                      // finite: the first half always holds column 0
+      const float sumg = suml * ex2_ftz(mxl - mxg) + o.y * ex2_ftz(o.x - mxg);
+      const float f = ex2_ftz(mref - mxg) / sumg;
+      if (dbg && warp == 2 && lane == 0) p.dbg[3] = clock64();
+  #pragma unroll
+      for (int u = 0; u < 16; ++u) {                          // 8 columns = one 16-byte chunk per step
+        if (u < 2 * myn) {
+          uint32_t pk[4];
+  #pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(v[8 * u + 2 * j] * f, v[8 * u + 2 * j + 1] * f);
+            pk[j] = *reinterpret_cast<uint32_t*>(&h2);
+          }
+          const int c = col0 + 8 * u;
+          // K-major 128B-swizzled A operand: k-block of 64 keys = [128 rows][128 B]; 16-byte chunk ch of row r sits at ch ^ (r & 7)
+          *reinterpret_cast<uint4*>(srow + (c >> 6) * 16384 + ((((c & 63) >> 3) ^ sw) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
       }
     }
     // generic-proxy smem writes -> visible to the tensor core (async proxy), then hand over to the MMA warp
@@ -240,7 +296,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     mbar_wait(bar_o, 0);
     tc_fence_after();
     if (dbg && warp == 2 && lane == 0) p.dbg[5] = clock64();
-    bf16* orow = p.att + ((long)b * p.L + m) * p.H + h * 64 + half * 32;      // each half stores 32 of the 64 output columns
+    bf16* orow = p.att + ((long)b * p.L + m) * p.out_pitch + h * 64 + half * 32;      // each half stores 32 of the 64 output columns
     float ov[32];
     tmem_ld16x2(trow + 256u + (uint32_t)(half * 32), ov, true);
     if (valid) {
@@ -273,16 +329,38 @@ static int attention_fused_fwd(const bf16* qkv, bf16* P, bf16* att, int B, int n
   const int dh = 64;
   const long sQb = (long)L * 3 * H;
   AttnParams p;
-  p.L = L; p.LK = (L + 15) & ~15; p.Lp = Lp; p.H = H; p.nh = nh; p.tiles_m = cdiv(L, 128); p.scale = scale; p.P = P; p.att = att;
+  p.L = L; p.LK = (L + 15) & ~15; p.Lp = Lp; p.H = H; p.nh = nh; p.tiles_m = cdiv(L, 128); p.scale = scale; p.P = P; p.att = att; p.out_pitch = H;
   CUtensorMap mq, mk, mv;
   B200_TRY(make_map(&mq, operand(qkv, 3 * H, 1, sQb, dh), L, dh, 128, B, nh));
   B200_TRY(make_map(&mk, operand(qkv + H, 3 * H, 1, sQb, dh), L, dh, p.LK, B, nh));
   B200_TRY(make_map(&mv, operand(qkv + 2 * H, 1, 3 * H, sQb, dh), dh, L, 64, B, nh));
   static bool attr_done = false;
-  if (!attr_done) { B200_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM)); attr_done = true; }
+  if (!attr_done) { B200_CUDA(cudaFuncSetAttribute(attn_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM)); attr_done = true; }
   p.trace = trace_slot(); if (p.trace) trace_tag("attn_fwd L%d b%d", L, B * nh);
   p.dbg = g_dbg;
-  B200_CUDA(launch_pdl(attn_fwd_kernel, dim3(B * nh * p.tiles_m), dim3(320), (size_t)ATT_SMEM, st, mq, mk, mv, p));
+  B200_CUDA(launch_pdl(attn_kernel<0>, dim3(B * nh * p.tiles_m), dim3(320), (size_t)ATT_SMEM, st, mq, mk, mv, mq, p));
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+
+// Backward, query-row half: dS = P * (dO V^T - rowsum(dO V^T * P)) * scale -> dS [B][nh][L][Lp] and dQ = dS K -> dqkv[:, h*64 ..] (Q third
+// of the [B*L][3H] gradient).  datt: [B*L][H] gradient of the attention output; P: probabilities of the forward.
+static int attention_fused_bwd_dq(const bf16* qkv, const bf16* P, const bf16* datt, bf16* dS, bf16* dqkv, int B, int nh, int L, int Lp, int H,
+                                  float scale, cudaStream_t st) {
+  const int dh = 64;
+  const long sQb = (long)L * 3 * H, sOb = (long)L * H, sPb = (long)nh * L * Lp, sPh = (long)L * Lp;
+  AttnParams p;
+  p.L = L; p.LK = (L + 15) & ~15; p.Lp = Lp; p.H = H; p.nh = nh; p.tiles_m = cdiv(L, 128); p.scale = scale; p.P = dS; p.att = dqkv; p.out_pitch = 3 * H;
+  CUtensorMap mq, mk, mv, mp;
+  B200_TRY(make_map(&mq, operand(datt, H, 1, sOb, dh), L, dh, 128, B, nh));                 // "Q" = dO block
+  B200_TRY(make_map(&mk, operand(qkv + 2 * H, 3 * H, 1, sQb, dh), L, dh, p.LK, B, nh));     // "K" = V, K-major
+  B200_TRY(make_map(&mv, operand(qkv + H, 1, 3 * H, sQb, dh), dh, L, 64, B, nh));           // "V" = K, MN-major
+  B200_TRY(make_map(&mp, operand(P, Lp, 1, sPb, sPh), L, L, 128, B, nh));                   // P block: 64-column boxes of 128 rows
+  static bool attr_done = false;
+  if (!attr_done) { B200_CUDA(cudaFuncSetAttribute(attn_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM)); attr_done = true; }
+  p.trace = trace_slot(); if (p.trace) trace_tag("attn_bwd_dq L%d b%d", L, B * nh);
+  p.dbg = g_dbg;
+  B200_CUDA(launch_pdl(attn_kernel<1>, dim3(B * nh * p.tiles_m), dim3(320), (size_t)ATT_SMEM, st, mq, mk, mv, mp, p));
   B200_LAUNCH_CHECK();
   return 0;
 }

@@ -165,6 +165,10 @@ int b200_test_tc_gemm(const void* a, const void* b, float* out, int M, int N, in
  * probs [B][heads][L][Lp] bf16 (softmax(scale QK^T), may be NULL); att [B*L][H] bf16.  head_dim 64, 16 <= L <= 256. */
 int b200_test_tc_attention(const void* qkv, void* probs, void* att, int batch, int heads, int L, int Lp, int H, float scale,
                            void* stream);
+/* query-row half of its backward: dS = probs * (dO V^T - rowsum(dO V^T * probs)) * scale -> dS [B][heads][L][Lp] bf16, and
+ * dQ = dS K -> columns [h*64, h*64+64) of dqkv [B*L][3H] bf16 (the K and V thirds are not touched) */
+int b200_test_tc_attention_bwd(const void* qkv, const void* probs, const void* datt, void* dS, void* dqkv, int batch, int heads,
+                               int L, int Lp, int H, float scale, void* stream);
 
 #ifdef __cplusplus
 }

@@ -62,3 +62,40 @@ def test_fused_attention_matches_fp32(pkg, B, heads, L):
     pkg._lib.check(lib.b200_test_tc_attention(pkg._lib.ptr(qkv_d), None, pkg._lib.ptr(att2), B, heads, L, Lp, H, scale,
                                                pkg._lib.stream_ptr()), "tc_attention")
     assert torch.equal(att2, att)
+
+
+@pytest.mark.parametrize("B,heads,L", [(2, 12, 216), (1, 2, 64), (3, 4, 200), (1, 3, 256), (2, 2, 27)])
+def test_fused_attention_backward_dq_matches_fp32(pkg, B, heads, L):
+    """Query-row half of the attention backward (tc_attention.cuh, BWD = 1) against torch fp32 on the same bf16 inputs:
+    dS = P * (dP - rowsum(dP * P)) * scale with dP = dO V^T, dQ = dS K.  dS and dQ are stored as bf16 and dQ accumulates the
+    bf16 dS: 1e-2 of max|ref| (the bf16-mode budget); the K and V thirds of dqkv must stay untouched."""
+    lib = pkg._lib.load()
+    H, Lp = heads * 64, (L + 7) & ~7
+    g = torch.Generator().manual_seed(B * 77 + L)
+    qkv = torch.randn(B * L, 3 * H, generator=g).to(torch.bfloat16)
+    datt = torch.randn(B * L, H, generator=g).to(torch.bfloat16)
+    scale = 64 ** -0.5
+    f = qkv.float().view(B, L, 3, heads, 64)
+    q, k, v = (f[:, :, i].permute(0, 2, 1, 3) for i in range(3))
+    probs = torch.zeros(B, heads, L, Lp)
+    probs[..., :L] = torch.softmax(q @ k.transpose(-1, -2) * scale, dim=-1)
+    probs = probs.to(torch.bfloat16)
+    pf = probs.float()[..., :L]
+    do = datt.float().view(B, L, heads, 64).permute(0, 2, 1, 3)
+    dp = do @ v.transpose(-1, -2)
+    ds_want = pf * (dp - (dp * pf).sum(-1, keepdim=True)) * scale
+    dq_want = (ds_want @ k).permute(0, 2, 1, 3).reshape(B * L, H)
+    dS = torch.full((B, heads, L, Lp), float("nan"), dtype=torch.bfloat16, device=DEV)
+    dqkv = torch.full((B * L, 3 * H), 7.0, dtype=torch.bfloat16, device=DEV)
+    qkv_d, probs_d, datt_d = qkv.to(DEV), probs.to(DEV), datt.to(DEV)      # named: temporaries would be freed (and aliased) before the launch
+    pkg._lib.check(lib.b200_test_tc_attention_bwd(pkg._lib.ptr(qkv_d), pkg._lib.ptr(probs_d), pkg._lib.ptr(datt_d),
+                                                   pkg._lib.ptr(dS), pkg._lib.ptr(dqkv), B, heads, L, Lp, H, scale, pkg._lib.stream_ptr()),
+                   "tc_attention_bwd")
+    torch.cuda.synchronize()
+    ds_got = dS.float().cpu()
+    assert torch.isfinite(ds_got).all()
+    assert ((ds_got[..., :L] - ds_want).abs().max() / ds_want.abs().max()).item() <= 1e-2
+    assert (ds_got[..., L:] == 0).all()
+    got = dqkv.float().cpu()
+    assert ((got[:, :H] - dq_want).abs().max() / dq_want.abs().max()).item() <= 1e-2
+    assert (got[:, H:] == 7.0).all()
