@@ -221,12 +221,18 @@ def main():
     # kernel classes of the tcgen05 engine, algorithmic FLOPs from the op tags (2*M*N*K; 2*B*S^3*Cin*Cout*taps)
     classes = {"tc::gemm_kernel (ViT linear layers: fwd, dgrad, wgrad)": [0.0, 0.0, 0],
                "tc::conv_halo_kernel (conv3d 3^3 [+fused 1^3] implicit GEMM: fwd, dgrad)": [0.0, 0.0, 0],
-               "tc::wgrad_halo_kernel / tc::wgrad_kernel (conv3d weight gradients)": [0.0, 0.0, 0]}
+               "tc::wgrad_halo_kernel / tc::wgrad_kernel (conv3d weight gradients)": [0.0, 0.0, 0],
+               "tc::attn_kernel (fused attention: fwd; bwd = dS/dQ kernel + dV, dK GEMMs)": [0.0, 0.0, 0]}
     names = list(classes)
     for k, v in prof.items():
         m = re.match(r"linear_(fwd|dgrad|wgrad) (\d+)x(\d+)x(\d+)", k)
         if m:
             c = classes[names[0]]; c[0] += v[0]; c[1] += v[1] * 2.0 * int(m.group(2)) * int(m.group(3)) * int(m.group(4)); c[2] += v[1]
+            continue
+        m = re.match(r"attention_(fwd|bwd)", k)
+        if m:     # L = 216 tokens, 12 heads x 64: 2 (fwd) / 4 (bwd) products of 2*L*L*64 FLOPs per (sample, head)
+            c = classes[names[3]]; c[0] += v[0]; c[2] += v[1]
+            c[1] += v[1] * (2 if m.group(1) == "fwd" else 4) * 2.0 * B * 12 * 216 * 216 * 64
             continue
         m = re.match(r"conv_(fwd|dgrad) k3(\+k1)? (\d+)->(\d+) @(\d+)", k)
         if m:
@@ -247,7 +253,7 @@ def main():
         r = {"bound": "tensor", "kernel": name, "launches": n, "avg_launch_us": 1e3 * ms_ / n if n else None,
              "achieved": fl / (ms_ * 1e-3) / 1e12 if ms_ else None, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
              "peak_kind": pk_kind + " sustained cuBLAS bf16 (kernel timed inside a long step)",
-             "algorithmic": "sum over launches of 2*M*N*K (linear) / 2*B*S^3*Cin*Cout*taps (conv)", "share_of_step_ms": ms_,
+             "algorithmic": "sum over launches of 2*M*N*K (linear) / 2*B*S^3*Cin*Cout*taps (conv) / 2*L*L*64 per product, sample and head (attention)", "share_of_step_ms": ms_,
              "timing": "CUDA events around every launch of one step on the launching stream (b200_prof_*)"}
         r["frac"] = r["achieved"] / r["peak"] if r["achieved"] else None
         t = traffic.get(name.split(" ")[0])
