@@ -35,16 +35,20 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe).  The sampler is started before the
+    warm-up (nvidia-smi needs ~1 s to come up, longer with 8 ranks starting one each) and every row is stamped on arrival; `stop`
+    reports the rows that fall inside [mark_begin, mark_end] -- the timed region -- and, if the region was shorter than the
+    sampling period, the rows of the whole loaded run (warm-up included), saying which."""
 
     def __init__(self, index):
         self.rows, self.proc, self.index = [], None, index
+        self.t0 = self.t1 = None
 
     def start(self):
         q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
@@ -52,16 +56,27 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def stop(self):
         if self.proc:
             self.proc.terminate()
-        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
-        mx = max([int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()] or [0])
+        inside = [r for t, r in self.rows if self.t0 is not None and self.t1 is not None and self.t0 <= t <= self.t1 + 0.05]
+        window = "timed region"
+        if not inside:
+            inside = [r for t, r in self.rows if self.t0 is None or t >= self.t0 - 2.0]
+            window = "loaded run (warm-up + timed region): the timed region was shorter than one sampling period"
+        sm = sorted(int(r[0]) for r in inside if r and r[0].isdigit())
+        mx = max([int(r[1]) for r in inside if len(r) > 1 and r[1].isdigit()] or [0])
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": reasons, "samples": len(sm)}
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in inside)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": reasons, "samples": len(sm), "window": window}
 
 
 def cpu_reference_step_time(batch, steps, warmup):
@@ -178,11 +193,12 @@ def main():
         par.barrier(world)
         return par.max_over_ranks(e0.elapsed_time(e1), world, dev)
 
+    sampler = ClockSampler(local)
+    sampler.start()
     for i in range(args.warmup):
         step(dev_x[i % 4], dev_y[i % 4])
     torch.cuda.synchronize()
-    sampler = ClockSampler(local)
-    sampler.start()
+    sampler.mark_begin()
     l0 = lib.b200_launch_count()
     ms = timed(lambda i: step(dev_x[i % 4], dev_y[i % 4]), args.steps)
     launches = lib.b200_launch_count() - l0
@@ -209,6 +225,7 @@ def main():
     e2e_step(0)
     # steps are numbered 1..K here so that the slot primed by the warm-up call is the one step 1 reads
     ms_e2e = timed(lambda i: e2e_step(i + 1), args.steps)
+    sampler.mark_end()
     clocks = sampler.stop()
 
     # per-op CUDA-event breakdown of one step -> roofline of the dominant kernel class
