@@ -122,6 +122,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--batch", type=int, default=2, help="crops per GPU")
+    ap.add_argument("--img", type=int, default=96, choices=[96, 128],
+                    help="crop edge; 128 with --batch 4 is configs[3] (a parity-test configuration, measured on request; the metric line is configs[1])")
     ap.add_argument("--mode", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-optimizer", action="store_true")
     ap.add_argument("--torch-adamw", action="store_true", help="use torch.optim.AdamW(fused=True) instead of the package's FusedAdamW")
@@ -155,7 +157,11 @@ def main():
     lib = pkg._lib.load()
 
     torch.manual_seed(0)
-    model = pkg.MonaiUNETR(**MODEL_KW).to(dev).set_mode(args.mode)
+    S = args.img
+    model_kw = dict(MODEL_KW, img_size=(S, S, S))
+    flop_per_sample = FLOP_PER_SAMPLE_96 if S == 96 else 916.84e9      # 3 x 305.61 GFLOP at 128^3
+    n_tok = (S // 16) ** 3
+    model = pkg.MonaiUNETR(**model_kw).to(dev).set_mode(args.mode)
     loss_fn = pkg.DiceCELoss(to_onehot_y=True, softmax=True)
     if args.torch_adamw:
         opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=1e-5, fused=True)
@@ -165,8 +171,8 @@ def main():
     B = args.batch
     g = torch.Generator().manual_seed(100 + rank)
     # 8 distinct host batches (pinned) cycled through: per-step inputs exceed nothing cached on the device side
-    host_x = [torch.rand(B, 1, 96, 96, 96, generator=g).pin_memory() for _ in range(4)]
-    host_y = [torch.randint(0, 14, (B, 1, 96, 96, 96), generator=g).float().pin_memory() for _ in range(4)]
+    host_x = [torch.rand(B, 1, S, S, S, generator=g).pin_memory() for _ in range(4)]
+    host_y = [torch.randint(0, 14, (B, 1, S, S, S), generator=g).float().pin_memory() for _ in range(4)]
     dev_x = [t.to(dev) for t in host_x]
     dev_y = [t.to(dev) for t in host_y]
 
@@ -249,7 +255,7 @@ def main():
         m = re.match(r"attention_(fwd|bwd)", k)
         if m:     # L = 216 tokens, 12 heads x 64: 2 (fwd) / 4 (bwd) products of 2*L*L*64 FLOPs per (sample, head)
             c = classes[names[3]]; c[0] += v[0]; c[2] += v[1]
-            c[1] += v[1] * (2 if m.group(1) == "fwd" else 4) * 2.0 * B * 12 * 216 * 216 * 64
+            c[1] += v[1] * (2 if m.group(1) == "fwd" else 4) * 2.0 * B * 12 * n_tok * n_tok * 64
             continue
         m = re.match(r"conv_(fwd|dgrad) k3(\+k1)? (\d+)->(\d+) @(\d+)", k)
         if m:
@@ -299,7 +305,7 @@ def main():
 
     # second half of the metric: sliding-window inference on a synthetic 512x512x256 CT (configs[4]), windows sharded over ranks
     sw = None
-    if not args.no_sliding_window:
+    if not args.no_sliding_window and S == 96:
         model.eval()
         vol = torch.rand(1, 1, 512, 512, 256, generator=torch.Generator().manual_seed(5)).to(dev)
         with torch.no_grad():
@@ -318,7 +324,7 @@ def main():
     # configs[2]: ranking pre-training step (rank:238-274) -- batch 8 x 96^3, "feat" stage: full forward, 576 triplets of enc4
     # slices along one axis, Bradley-Terry loss, backward through encoder4 + ViT blocks 0-9 + patch embedding, AdamW step
     rk = None
-    if not args.no_ranking:
+    if not args.no_ranking and S == 96:
         del model, opt, ddp
         torch.cuda.empty_cache()
         rmodel = pkg.UNETR(**MODEL_KW).to(dev).set_mode(args.mode)
@@ -359,13 +365,13 @@ def main():
                "sample": "2 timed steps x 1 crop of 96^3 (fwd+DiceCE+bwd), oracle restatement of the MONAI 0.6.0 path on the host CPU"}
     if rank == 0:
         samples = B * world * args.steps
-        line = {"metric": "UNETR 96^3 fwd+bwd samples/s", "value": samples / (ms * 1e-3), "unit": "samples/s", "n_gpus": world,
+        line = {"metric": f"UNETR {S}^3 fwd+bwd samples/s", "value": samples / (ms * 1e-3), "unit": "samples/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": args.mode, "data": "synthetic",
-                "config": {"workload": "configs[1]: UNETR(1->14,96^3,fs16,ViT-B) segmentation training step (fwd+DiceCE+bwd" +
+                "config": {"workload": ("configs[1]" if S == 96 else "configs[3]") + f": UNETR(1->14,{S}^3,fs16,ViT-B) segmentation training step (fwd+DiceCE+bwd" +
                            ("" if args.no_optimizer else "+AdamW") + f"), batch {B}/GPU", "global_batch": B * world,
                            "parallelism": f"dp{world}", "l2": "4 rotating input batches; activations per step (~1 GB) exceed the 126 MB L2"},
-                "tflops_algorithmic": samples * FLOP_PER_SAMPLE_96 / (ms * 1e-3) / 1e12,
+                "tflops_algorithmic": samples * flop_per_sample / (ms * 1e-3) / 1e12,
                 "e2e": {"value": samples / (ms_e2e * 1e-3), "unit": "samples/s",
                         "h2d_bytes_per_step": host_x[0].numel() * 4 + host_y[0].numel() * 4, "d2h_bytes_per_step": 4},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "sliding_window": sw, "ranking_step": rk}

@@ -191,6 +191,40 @@ def test_config1_full_size_forward_and_dice(pkg, mode, tol):
         assert assert_argmax_parity(logits, logits_r) <= 8
 
 
+@pytest.mark.parametrize("mode,tol", [("fp32", 1e-4), ("bf16", 1e-2)])
+def test_config4_128_cube_forward_and_training_step(pkg, mode, tol):
+    """BASELINE.json configs[3] geometry: 128^3 crops (L = 512 tokens: the attention runs as batched GEMMs + softmax, the decoder
+    stages are 8..128 voxels wide).  Forward of one crop against the fp32 oracle at the north_star tolerances; then the per-GPU
+    batch of the configuration (4 crops) runs a full training step in bf16 mode: finite loss and gradients, loss of the first crop's
+    logits consistent with the batch-1 forward (samples are independent: InstanceNorm is per sample)."""
+    ref = O.make_model(img=128)
+    mine = pkg.UNETR(1, 14, (128,) * 3, 16, 768, 3072, 12, "perceptron", "instance", res_block=True)
+    mine.load_state_dict(ref.state_dict())
+    mine = mine.to(DEV).set_mode(mode)
+    x, y = O.make_inputs(img=128)
+    with torch.no_grad():
+        enc4_r, logits_r = ref(x)
+        loss_r = O.dice_ce_loss(logits_r, y)
+        enc4, logits = mine.eval()(x.to(DEV))
+        loss = pkg.DiceCELoss(to_onehot_y=True, softmax=True)(logits, y.to(DEV))
+    e = relerr(logits, logits_r)
+    print(f"[config4 {mode}] 128^3 logits rel-err {e:.3e}  enc4 rel-err {relerr(enc4, enc4_r):.3e}  loss {loss.item():.6f} vs {loss_r.item():.6f}")
+    assert enc4.shape == (1, 128, 16, 16, 16) and logits.shape == (1, 14, 128, 128, 128)
+    assert e <= tol and abs(loss.item() - loss_r.item()) <= 1e-3
+    if mode == "bf16":
+        x4, y4 = O.make_inputs(batch=4, img=128, seed=7)
+        x4[0], y4[0] = x[0], y[0]
+        mine.train()
+        _, lg4 = mine(x4.to(DEV))
+        l4 = pkg.DiceCELoss(to_onehot_y=True, softmax=True)(lg4, y4.to(DEV))
+        l4.backward()
+        torch.cuda.synchronize()
+        assert torch.isfinite(l4).item() and all(torch.isfinite(p.grad).all().item() for p in mine.parameters() if p.grad is not None)
+        assert all(p.grad is not None for n, p in mine.named_parameters() if "cls_token" not in n)
+        # a batch of 4 is 4 independent crops; tile shapes / split-K depend on the batch, so bf16 roundings differ: same budget
+        assert relerr(lg4[:1], logits) <= 1e-2
+
+
 @pytest.mark.parametrize("mode,cos_min,cos_med", [("fp32", 0.9995, 0.99999), ("bf16", 0.97, 0.985)])
 def test_config2_training_step_gradients(pkg, mode, cos_min, cos_med):
     """BASELINE.json configs[1]: batch 2, 96^3 -- fwd + DiceCE + bwd; per-tensor gradient cosine against the fp32 oracle.
