@@ -547,3 +547,28 @@ def test_multi_window_accumulate_is_bit_identical_to_window_loop(pkg):
         L_.check(lib.b200_sw_accumulate_n(L_.ptr(b), L_.ptr(pred), ctypes.byref(g), sN, n, L_.stream_ptr()), "acc_n")
         assert torch.equal(a, b)
         assert not torch.equal(a, base)
+
+
+@pytest.mark.parametrize("mode,tol", [("fp32", 1e-4), ("bf16", 1e-2)])
+def test_task01_configuration_four_channel_128_cube_sigmoid_loss(pkg, mode, tol):
+    """The second dataset configuration the segmentation script runs (seg:408-482, 501-513): 4 MR channels in,
+    4 multi-hot BraTS channels out, 128^3 crops -- perceptron patch embedding with K = 4 * 4096, encoder1 on 4 input channels,
+    DiceCELoss(to_onehot_y=False, sigmoid=True).  Logits and loss against the oracle at the north_star tolerances; one backward."""
+    ref = O.make_model(img=128, in_channels=4, out_channels=4)
+    mine = pkg.UNETR(4, 4, (128,) * 3, 16, 768, 3072, 12, "perceptron", "instance", res_block=True)
+    mine.load_state_dict(ref.state_dict())
+    mine = mine.to(DEV).set_mode(mode)
+    g = torch.Generator().manual_seed(21)
+    x = torch.randn(1, 4, 128, 128, 128, generator=g)                       # NormalizeIntensityd output: zero mean, unit variance (seg:476)
+    target = O.brats_multichannel(torch.randint(0, 4, (1, 1, 128, 128, 128), generator=g))
+    with torch.no_grad():
+        _, logits_r = ref(x)
+        loss_r = O.dice_ce_loss_sigmoid(logits_r, target)
+    _, logits = mine(x.to(DEV))
+    loss = pkg.DiceCELoss(to_onehot_y=False, sigmoid=True)(logits, target.to(DEV))
+    e = relerr(logits, logits_r)
+    print(f"[task01 {mode}] logits rel-err {e:.3e}  sigmoid DiceCE {loss.item():.6f} vs {loss_r.item():.6f}")
+    assert e <= tol and abs(loss.item() - loss_r.item()) <= 1e-3
+    loss.backward()
+    torch.cuda.synchronize()
+    assert all(torch.isfinite(p.grad).all().item() for n, p in mine.named_parameters() if "cls_token" not in n)
