@@ -99,6 +99,30 @@ struct ConvWeightB {
 // ------------------------------------------------------------------ epilogues:  void operator()(b, m, n, acc)
 enum { ACT_NONE = 0, ACT_GELU = 1, ACT_GELU_BWD = 2 };
 
+// 4 consecutive elements <-> floats (16-byte fp32 / 8-byte 16-bit accesses): the coalesced tcgen05 epilogue hands every lane 4 columns
+__device__ __forceinline__ void ep_ld4(const float* p, float* o) { float4 t = *reinterpret_cast<const float4*>(p); o[0] = t.x; o[1] = t.y; o[2] = t.z; o[3] = t.w; }
+__device__ __forceinline__ void ep_ld4(const bf16* p, float* o) {
+  uint2 t = *reinterpret_cast<const uint2*>(p);
+  float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.x)), b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.y));
+  o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y;
+}
+__device__ __forceinline__ void ep_ld4(const __half* p, float* o) {
+  uint2 t = *reinterpret_cast<const uint2*>(p);
+  float2 a = __half22float2(*reinterpret_cast<const __half2*>(&t.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&t.y));
+  o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y;
+}
+__device__ __forceinline__ void ep_st4(float* p, const float* v) { *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]); }
+__device__ __forceinline__ void ep_st4(bf16* p, const float* v) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+  uint2 t; t.x = *reinterpret_cast<uint32_t*>(&a); t.y = *reinterpret_cast<uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(p) = t;
+}
+__device__ __forceinline__ void ep_st4(__half* p, const float* v) {
+  __half2 a = __floats2half2_rn(v[0], v[1]), b = __floats2half2_rn(v[2], v[3]);
+  uint2 t; t.x = *reinterpret_cast<uint32_t*>(&a); t.y = *reinterpret_cast<uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(p) = t;
+}
+
 template <class TO>
 struct EpStore {
   TO* out; long ld, sb0, sb1; int nb1;
@@ -180,6 +204,89 @@ struct EpStore {
     }
 #pragma unroll
     for (int j = 0; j < 16; j += VN) { Vec16<TO> t; for (int i = 0; i < VN; ++i) t.v[i] = v[j + i]; t.store(out + o + j); }
+  }
+  // 4 consecutive columns of row m (coalesced tcgen05 epilogue: 8 lanes cover 32 consecutive columns of one row)
+  __device__ __forceinline__ void seg4(int b, int m, int n0, const float* acc, int nvalid) const {
+    constexpr uintptr_t AO = 4 * sizeof(TO) - 1;
+    if (splitk_nbat) {
+      if (split_stride && nvalid == 4) {
+        const int sp = b / splitk_nbat; const int bb = b - sp * splitk_nbat;
+        float* dst = reinterpret_cast<float*>(out) + sp * split_stride + (long)(bb / nb1) * sb0 + (long)(bb % nb1) * sb1 + (long)m * ld + n0;
+        if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+          *reinterpret_cast<float4*>(dst) = make_float4(acc[0] * alpha, acc[1] * alpha, acc[2] * alpha, acc[3] * alpha);
+          return;
+        }
+      }
+      split_store(b, m, n0, acc, nvalid);
+      return;
+    }
+    long o = (long)(b / nb1) * sb0 + (long)(b % nb1) * sb1 + (long)m * ld + n0;
+    bool fast = nvalid == 4 && ((reinterpret_cast<uintptr_t>(out + o) & AO) == 0) && (!preact || (reinterpret_cast<uintptr_t>(preact + o) & AO) == 0) &&
+                (!usrc || (reinterpret_cast<uintptr_t>(usrc + o) & AO) == 0) && (!resid || (reinterpret_cast<uintptr_t>(resid + (long)m * ldr + n0) & 15) == 0) &&
+                (!bias || (reinterpret_cast<uintptr_t>(bias + n0) & 15) == 0);
+    if (!fast) {
+#pragma unroll 1
+      for (int j = 0; j < nvalid; ++j) (*this)(b, m, n0 + j, acc[j]);
+      return;
+    }
+    float v[4] = {acc[0] * alpha, acc[1] * alpha, acc[2] * alpha, acc[3] * alpha};
+    if (bias) { float4 t = *reinterpret_cast<const float4*>(bias + n0); v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w; }
+    if (preact) ep_st4(preact + o, v);
+    if (act == ACT_GELU) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = gelu_erf(v[j]);
+    } else if (act == ACT_GELU_BWD) {
+      float u[4]; ep_ld4(usrc + o, u);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] *= gelu_erf_grad(u[j]);
+    }
+    if (resid) { float4 t = *reinterpret_cast<const float4*>(resid + (long)m * ldr + n0); v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w; }
+    if (accumulate) { float u[4]; ep_ld4(out + o, u); v[0] += u[0]; v[1] += u[1]; v[2] += u[2]; v[3] += u[3]; }
+    ep_st4(out + o, v);
+  }
+  // Per-tile context of the coalesced epilogue: the batch offset (two integer divisions) and every alignment test are done once per
+  // output tile instead of once per 4 columns (the epilogue warps are one per SM sub-partition: issue-bound).
+  struct Tile { long ob; int fast; int sp; };
+  __device__ __forceinline__ Tile tile(int b) const {
+    constexpr uintptr_t AO = 4 * sizeof(TO) - 1;
+    Tile t; t.sp = 0;
+    int bb = b;
+    if (splitk_nbat) { t.sp = b / splitk_nbat; bb = b - t.sp * splitk_nbat; }
+    t.ob = (long)(bb / nb1) * sb0 + (long)(bb % nb1) * sb1;
+    bool f;
+    if (splitk_nbat) {
+      f = split_stride != 0 && ((reinterpret_cast<uintptr_t>(reinterpret_cast<float*>(out) + t.sp * split_stride + t.ob) & 15) == 0) && (ld & 3) == 0;
+    } else {
+      f = ((reinterpret_cast<uintptr_t>(out + t.ob) & AO) == 0) && (ld & 3) == 0;
+      if (preact) f = f && ((reinterpret_cast<uintptr_t>(preact + t.ob) & AO) == 0);
+      if (usrc) f = f && ((reinterpret_cast<uintptr_t>(usrc + t.ob) & AO) == 0);
+      if (resid) f = f && ((reinterpret_cast<uintptr_t>(resid) & 15) == 0) && (ldr & 3) == 0;
+      if (bias) f = f && ((reinterpret_cast<uintptr_t>(bias) & 15) == 0);
+    }
+    t.fast = f;
+    return t;
+  }
+  __device__ __forceinline__ void seg4t(const Tile& t, int b, int m, int n0, const float* acc, int nvalid) const {
+    if (!t.fast || nvalid != 4 || (n0 & 3)) { seg4(b, m, n0, acc, nvalid); return; }
+    const long o = t.ob + (long)m * ld + n0;
+    if (splitk_nbat) {
+      *reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + t.sp * split_stride + o) = make_float4(acc[0] * alpha, acc[1] * alpha, acc[2] * alpha, acc[3] * alpha);
+      return;
+    }
+    float v[4] = {acc[0] * alpha, acc[1] * alpha, acc[2] * alpha, acc[3] * alpha};
+    if (bias) { float4 q = *reinterpret_cast<const float4*>(bias + n0); v[0] += q.x; v[1] += q.y; v[2] += q.z; v[3] += q.w; }
+    if (preact) ep_st4(preact + o, v);
+    if (act == ACT_GELU) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = gelu_erf(v[j]);
+    } else if (act == ACT_GELU_BWD) {
+      float u[4]; ep_ld4(usrc + o, u);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] *= gelu_erf_grad(u[j]);
+    }
+    if (resid) { float4 q = *reinterpret_cast<const float4*>(resid + (long)m * ldr + n0); v[0] += q.x; v[1] += q.y; v[2] += q.z; v[3] += q.w; }
+    if (accumulate) { float u[4]; ep_ld4(out + o, u); v[0] += u[0]; v[1] += u[1]; v[2] += u[2]; v[3] += u[3]; }
+    ep_st4(out + o, v);
   }
 };
 template <class TO> static inline EpStore<TO> ep_plain(TO* out, long ld) {

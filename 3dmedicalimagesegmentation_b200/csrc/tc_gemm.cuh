@@ -23,6 +23,7 @@ namespace b200 {
 namespace tc {
 
 static constexpr int BM = 128, BK = 64;
+static constexpr int EPI_STG_BYTES = 4 * 32 * 36 * 4;   // coalesced-epilogue staging: 4 warps x 32 rows x (32 + 4 pad) floats
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -88,6 +89,28 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// 32 consecutive TMEM columns of this thread's lane as two x16 loads behind ONE wait (the second is skipped when `two` is false;
+// its registers are then zero)
+__device__ __forceinline__ void tmem_ld16x2(uint32_t taddr, float* v, bool two) {
+  uint32_t r[32];
+#pragma unroll
+  for (int i = 16; i < 32; ++i) r[i] = 0u;
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr) : "memory");
+  if (two)
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+        : "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr + 16u) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) { asm volatile("prefetch.tensormap [%0];" ::"l"(m) : "memory"); }
 
 // shared-memory matrix descriptor, SWIZZLE_128B (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30),
@@ -112,6 +135,24 @@ __device__ __forceinline__ void ep_seg16(const EP& ep, int b, int m, int n0, con
   for (int j = 0; j < nvalid; ++j) ep(b, m, n0 + j, v[j]);
 }
 
+// 4 consecutive output columns of one row (coalesced epilogue): functors with `seg4` use it, others get the scalar call
+template <class EP>
+__device__ __forceinline__ auto ep_seg4(const EP& ep, int b, int m, int n0, const float* v, int nvalid) -> decltype(ep.seg4(b, m, n0, v, nvalid), void()) {
+  ep.seg4(b, m, n0, v, nvalid);
+}
+template <class EP, class... Dummy>
+__device__ __forceinline__ void ep_seg4(const EP& ep, int b, int m, int n0, const float* v, int nvalid, Dummy...) {
+#pragma unroll 1
+  for (int j = 0; j < nvalid; ++j) ep(b, m, n0 + j, v[j]);
+}
+
+// functors that provide seg4 take the coalesced epilogue; the others (atomic / scatter epilogues) keep one row per lane
+template <class EP> struct has_seg4 {
+  template <class U> static constexpr auto test(int) -> decltype(std::declval<const U&>().seg4(0, 0, 0, (const float*)nullptr, 0), true) { return true; }
+  template <class U> static constexpr bool test(...) { return false; }
+  static constexpr bool value = test<EP>(0);
+};
+
 // Row-wise epilogues (EP::kRowOp == 1 forward softmax, 2 softmax backward): the CTA's tile holds COMPLETE rows (tiles_n == 1), each
 // epilogue thread owns one row and walks its TMEM columns twice -- attention scores never go to memory as fp32.
 template <class EP> struct row_op_of { template <class U> static constexpr int get(decltype(U::kRowOp)*) { return U::kRowOp; }
@@ -125,6 +166,7 @@ struct Params {
   int stages;
   uint32_t tmem_cols;       // 2*BN rounded to a power of two
   int ksplit, kb_per_split; // split-K: work item = (tile, split); epilogue functor must accumulate atomically
+  int coalesce;             // epilogue stores through a per-warp smem transpose (8 lanes x 16 B per row) instead of one row per lane
   long long* dbg;           // optional: CTA 0 phase timestamps (clock64) for tuning
   long long* trace;         // optional in-situ (start, end) slot
 };
@@ -140,6 +182,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
   uint64_t* tfull = empty + p.stages;   // [2]
   uint64_t* tempty = tfull + 2;         // [2]
   uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
+  float* stg_all = (float*)(smem + (size_t)p.stages * stage_bytes + 256);   // 4 epilogue warps x 32 rows x 36 floats (EPI_STG_BYTES)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool dbg = p.dbg && blockIdx.x == 0;
@@ -289,12 +332,52 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
           if (rv) ep.store16(b, m, c0, v, min(16, ep.ldw - c0));
         }
       } else {
-      for (int c0 = 0; c0 < p.BN; c0 += 16) {
-        float v[16];
-        tmem_ld16(trow + c0, v);
-        int n0 = tn * p.BN + c0;
-        if (m < p.M && n0 < p.N) ep_seg16(ep, b, m, n0, v, min(16, p.N - n0));
-      }
+        bool done = false;
+#ifdef B200_COALESCED_EPILOGUE
+        // EXPERIMENT, compiled out (make EXTRA=-DB200_COALESCED_EPILOGUE): measured SLOWER on B200 -- 7.44 vs 6.73 ms/step; in situ the
+        // single-tile GEMMs grow by ~5 us each (432x3072x768: 14.1 -> 19.8 us, with the GELU-backward epilogue 19.9 -> 34.9 us).  The
+        // row-per-lane stores are not what bounds the epilogue: the 16 smem operations + 8 address computations per 32 columns on a
+        // warp that is alone on its SM sub-partition cost more than the sector savings return.
+        if constexpr (has_seg4<EP>::value) {
+          if (p.coalesce) {
+            // One row per lane is what tcgen05.ld delivers, and stored that way every warp store touches 32 rows (32 sectors per
+            // instruction, ~32 LSU cycles each).  32 columns at a time go through a per-warp smem transpose (row pitch 36 floats:
+            // conflict-free both ways) so that 8 lanes cover 32 consecutive columns of one row.
+            float* stg = stg_all + (warp - 2) * (32 * 36);
+            const auto tl = ep.tile(b);
+            const int ch = lane & 7, rsub = lane >> 3;
+            for (int c0 = 0; c0 < p.BN; c0 += 32) {
+              float v[32];
+              tmem_ld16x2(trow + c0, v, c0 + 16 < p.BN);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) *reinterpret_cast<float4*>(stg + lane * 36 + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+              __syncwarp();
+              const int cc = c0 + 4 * ch;
+              const int n0 = tn * p.BN + cc;
+              const int nv = min(4, p.N - n0);
+              if (cc < p.BN && nv > 0) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const int r = i * 4 + rsub;
+                  const float4 t = *reinterpret_cast<const float4*>(stg + r * 36 + 4 * ch);
+                  const int mm = tm * BM + q * 32 + r;
+                  if (mm < p.M) ep.seg4t(tl, b, mm, n0, reinterpret_cast<const float*>(&t), nv);
+                }
+              }
+              __syncwarp();
+            }
+            done = true;
+          }
+        }
+#endif
+        if (!done) {
+          for (int c0 = 0; c0 < p.BN; c0 += 16) {
+            float v[16];
+            tmem_ld16(trow + c0, v);
+            int n0 = tn * p.BN + c0;
+            if (m < p.M && n0 < p.N) ep_seg16(ep, b, m, n0, v, min(16, p.N - n0));
+          }
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -426,7 +509,14 @@ static int gemm(const Operand& A, const Operand& B, const EP& ep, int M, int N, 
     long want = num_sms() / base_tiles; if (want > kbs / 4) want = kbs / 4; if (want < 1) want = 1;
     p.kb_per_split = cdiv(kbs, (int)want); p.ksplit = cdiv(kbs, p.kb_per_split);
   }
+#ifdef B200_COALESCED_EPILOGUE
+  static const bool no_coalesce = getenv("B200_NO_COALESCED_EPILOGUE") != nullptr;
+  p.coalesce = no_coalesce ? 0 : 1;
+  size_t smem = (size_t)p.stages * stage_bytes + 1024 + 256 + EPI_STG_BYTES;
+#else
+  p.coalesce = 0;
   size_t smem = (size_t)p.stages * stage_bytes + 1024 + 256;
+#endif
   long tiles = (long)p.tiles_m * p.tiles_n * p.batches * p.ksplit;
   int grid = (int)(tiles < num_sms() ? tiles : num_sms());
   cudaError_t le;
