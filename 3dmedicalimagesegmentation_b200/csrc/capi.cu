@@ -456,4 +456,12 @@ int b200_test_tc_attention_bwd(const void* qkv, const void* probs, const void* d
                                     (cudaStream_t)stream);
 }
 
+// key-row half: dV = probs^T dO -> V third of dqkv, dK = dS^T Q -> K third (the Q third is not touched)
+int b200_test_tc_attention_bwd_kv(const void* qkv, const void* probs, const void* dS, const void* datt, void* dqkv, int B, int heads, int L,
+                                  int Lp, int H, void* stream) {
+  B200_CHECK(tc::attention_fused_supported(L, Lp, H, heads), "fused attention needs head_dim 64, 16 <= L <= 256, Lp %% 8 == 0");
+  return tc::attention_fused_bwd_kv((const bf16*)qkv, (const bf16*)probs, (const bf16*)dS, (const bf16*)datt, (bf16*)dqkv, B, heads, L, Lp, H,
+                                    (cudaStream_t)stream);
+}
+
 }  // extern "C"

@@ -674,6 +674,8 @@ struct Exec {
       static const bool off = getenv("B200_NO_FUSED_ATTENTION_BWD") != nullptr;
       if (!off && tc::attention_fused_supported(L, Lp, H, nh)) {
         B200_TRY(tc::attention_fused_bwd_dq(qkv, w.P[i], w.datt, w.dS, w.dqkv, c.B, nh, L, Lp, H, scale, st));
+        static const bool kv_off = getenv("B200_NO_FUSED_ATTENTION_KV") != nullptr;
+        if (!kv_off) return tc::attention_fused_bwd_kv(qkv, w.P[i], w.dS, w.datt, w.dqkv, c.B, nh, L, Lp, H, st);   // dV, dK in one launch
         { EpStore<T> ep = ep_plain<T>(w.dqkv + 2 * H, 3 * H); ep.sb0 = sQb; ep.sb1 = dh; ep.nb1 = nh;      // dV = P^T dO
           B200_TRY(tc::gemm(tc::operand(w.P[i], 1, Lp, sPb, sPh), tc::operand(w.datt, 1, H, sOb, dh), ep, L, dh, L, c.B, nh, st)); }
         { EpStore<T> ep = ep_plain<T>(w.dqkv + H, 3 * H); ep.sb0 = sQb; ep.sb1 = dh; ep.nb1 = nh;          // dK = dS^T Q

@@ -297,6 +297,123 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
   }
 }
 
+// Key-row half of the attention backward in one launch (was two batched GEMM launches):
+//   dV[keys, d] = P^T dO      dK[keys, d] = dS^T Q        per (sample, head, 128-key block), reduction over the <= 256 queries
+// Both products read their A operand transposed out of a [queries][keys] row-major matrix (MN-major A: 64-key x 64-query TMA boxes)
+// and their B operand as [queries][64] (MN-major B); two fp32 accumulators of 64 columns sit side by side in TMEM.
+struct AttnKvParams {
+  int L, LK, H, nh, tiles_k;
+  bf16* dqkv;                        // [B*L][3H]: dK goes to the K third, dV to the V third
+  long long* trace;
+};
+static constexpr int ATT_KV_SMEM = 2 * 4 * 16384 + 2 * 4 * 8192 + 1024 + 256;
+
+static __global__ void __launch_bounds__(192, 1)
+attn_bwd_kv_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_constant__ CUtensorMap map_do, const __grid_constant__ CUtensorMap map_ds,
+                   const __grid_constant__ CUtensorMap map_q, const AttnKvParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA1 = smem;                 // P^T  : 4 query blocks x (2 boxes of [64 queries][64 keys])
+  uint8_t* sA2 = sA1 + 4 * 16384;      // dS^T
+  uint8_t* sB1 = sA2 + 4 * 16384;      // dO   : 4 query blocks x [64 queries][64]
+  uint8_t* sB2 = sB1 + 4 * 8192;       // Q
+  uint64_t* bar1 = (uint64_t*)(sB2 + 4 * 8192);
+  uint64_t* bar2 = bar1 + 1;
+  uint64_t* bar_done = bar1 + 2;
+  uint32_t* tmem_slot = (uint32_t*)(bar1 + 3);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int t = blockIdx.x;
+  const int tk = t % p.tiles_k; t /= p.tiles_k;
+  const int h = t % p.nh, b = t / p.nh;
+  const int m0 = tk * 128;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&map_p); prefetch_tmap(&map_do); prefetch_tmap(&map_ds); prefetch_tmap(&map_q);
+    mbar_init(bar1, 1); mbar_init(bar2, 1); mbar_init(bar_done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(128u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  trace_start(p.trace);
+  const int kblocks = (p.LK + 63) >> 6;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      mbar_expect_tx(bar1, (uint32_t)(kblocks * (16384 + 8192)));
+      for (int kb = 0; kb < kblocks; ++kb) {
+        tma_load_4d(smem_u32(sA1) + kb * 16384, &map_p, bar1, m0, kb * 64, h, b);
+        tma_load_4d(smem_u32(sA1) + kb * 16384 + 8192, &map_p, bar1, m0 + 64, kb * 64, h, b);
+        tma_load_4d(smem_u32(sB1) + kb * 8192, &map_do, bar1, 0, kb * 64, h, b);
+      }
+      mbar_expect_tx(bar2, (uint32_t)(kblocks * (16384 + 8192)));
+      for (int kb = 0; kb < kblocks; ++kb) {
+        tma_load_4d(smem_u32(sA2) + kb * 16384, &map_ds, bar2, m0, kb * 64, h, b);
+        tma_load_4d(smem_u32(sA2) + kb * 16384 + 8192, &map_ds, bar2, m0 + 64, kb * 64, h, b);
+        tma_load_4d(smem_u32(sB2) + kb * 8192, &map_q, bar2, 0, kb * 64, h, b);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // both operands MN-major (bits 15, 16), N = 64, M = 128; A: 64-wide M atoms 8192 B apart (LBO), 8-k-row groups 1024 B apart (SBO),
+    // +2048 B per 16-wide K step; B likewise with a single 64-wide N atom
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t hi = desc_hi(1024, 2);
+    const int ksteps = p.LK >> 4;
+    for (int prod = 0; prod < 2; ++prod) {
+      mbar_wait(prod ? bar2 : bar1, 0);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t a_lo = desc_lo(smem_u32(prod ? sA2 : sA1), 8192), b_lo = desc_lo(smem_u32(prod ? sB2 : sB1), 8192);
+        for (int j = 0; j < ksteps; ++j)
+          umma_f16(tmem_base + (uint32_t)(prod * 64),
+                   desc64(a_lo + (uint32_t)(j >> 2) * (16384u >> 4) + (uint32_t)(j & 3) * (2048u >> 4), hi),
+                   desc64(b_lo + (uint32_t)(j >> 2) * (8192u >> 4) + (uint32_t)(j & 3) * (2048u >> 4), hi), idesc, j ? 1u : 0u);
+        if (prod) umma_commit(bar_done);
+      }
+      __syncwarp();
+    }
+  } else {
+    const int q = warp & 3;
+    const int key = m0 + q * 32 + lane;
+    mbar_wait(bar_done, 0);
+    tc_fence_after();
+    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+#pragma unroll
+    for (int prod = 0; prod < 2; ++prod) {
+      // prod 0 = dV -> V third (column offset 2H), prod 1 = dK -> K third (offset H)
+      bf16* orow = p.dqkv + ((long)b * p.L + key) * (3 * p.H) + (prod ? p.H : 2 * p.H) + h * 64;
+#pragma unroll
+      for (int c0 = 0; c0 < 64; c0 += 32) {
+        float v[32];
+        tmem_ld16x2(trow + (uint32_t)(prod * 64 + c0), v, true);
+        if (key < p.L) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            uint32_t pk[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { __nv_bfloat162 h2 = __floats2bfloat162_rn(v[8 * u + 2 * j], v[8 * u + 2 * j + 1]); pk[j] = *reinterpret_cast<uint32_t*>(&h2); }
+            *reinterpret_cast<uint4*>(orow + c0 + 8 * u) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  trace_end(p.trace);
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128u) : "memory");
+  }
+}
+
 static inline bool attention_fused_supported(int L, int Lp, int H, int nh) {
   static const bool off = getenv("B200_NO_FUSED_ATTENTION") != nullptr;
   return !off && nh > 0 && H / nh == 64 && H % 8 == 0 && L >= 16 && ((L + 15) & ~15) <= 256 && Lp % 8 == 0 && Lp >= L;
@@ -339,6 +456,26 @@ static int attention_fused_bwd_dq(const bf16* qkv, const bf16* P, const bf16* da
   p.trace = trace_slot(); if (p.trace) trace_tag("attn_bwd_dq L%d b%d", L, B * nh);
   p.dbg = g_dbg;
   B200_CUDA(launch_pdl(attn_kernel<1>, dim3(B * nh * p.tiles_m), dim3(320), (size_t)ATT_SMEM, st, mq, mk, mv, mp, p));
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+
+// Backward, key-row half: dV = P^T dO -> V third of dqkv, dK = dS^T Q -> K third.
+static int attention_fused_bwd_kv(const bf16* qkv, const bf16* P, const bf16* dS, const bf16* datt, bf16* dqkv, int B, int nh, int L, int Lp, int H,
+                                  cudaStream_t st) {
+  const int dh = 64;
+  const long sQb = (long)L * 3 * H, sOb = (long)L * H, sPb = (long)nh * L * Lp, sPh = (long)L * Lp;
+  AttnKvParams p;
+  p.L = L; p.LK = (L + 15) & ~15; p.H = H; p.nh = nh; p.tiles_k = cdiv(L, 128); p.dqkv = dqkv;
+  CUtensorMap mp, mdo, mds, mq;
+  B200_TRY(make_map(&mp, operand(P, 1, Lp, sPb, sPh), L, L, 128, B, nh));             // A = P^T   (MN-major: keys contiguous)
+  B200_TRY(make_map(&mdo, operand(datt, 1, H, sOb, dh), dh, L, 64, B, nh));           // B = dO    (MN-major: d contiguous)
+  B200_TRY(make_map(&mds, operand(dS, 1, Lp, sPb, sPh), L, L, 128, B, nh));           // A = dS^T
+  B200_TRY(make_map(&mq, operand(qkv, 1, 3 * H, sQb, dh), dh, L, 64, B, nh));         // B = Q
+  static bool attr_done = false;
+  if (!attr_done) { B200_CUDA(cudaFuncSetAttribute(attn_bwd_kv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_KV_SMEM)); attr_done = true; }
+  p.trace = trace_slot(); if (p.trace) trace_tag("attn_bwd_kv L%d b%d", L, B * nh);
+  B200_CUDA(launch_pdl(attn_bwd_kv_kernel, dim3(B * nh * p.tiles_k), dim3(192), (size_t)ATT_KV_SMEM, st, mp, mdo, mds, mq, p));
   B200_LAUNCH_CHECK();
   return 0;
 }

@@ -169,6 +169,9 @@ int b200_test_tc_attention(const void* qkv, void* probs, void* att, int batch, i
  * dQ = dS K -> columns [h*64, h*64+64) of dqkv [B*L][3H] bf16 (the K and V thirds are not touched) */
 int b200_test_tc_attention_bwd(const void* qkv, const void* probs, const void* datt, void* dS, void* dqkv, int batch, int heads,
                                int L, int Lp, int H, float scale, void* stream);
+/* key-row half: dV = probs^T dO -> columns [2H + h*64, +64) of dqkv, dK = dS^T Q -> columns [H + h*64, +64) */
+int b200_test_tc_attention_bwd_kv(const void* qkv, const void* probs, const void* dS, const void* datt, void* dqkv, int batch,
+                                  int heads, int L, int Lp, int H, void* stream);
 
 #ifdef __cplusplus
 }

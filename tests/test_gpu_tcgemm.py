@@ -99,3 +99,32 @@ def test_fused_attention_backward_dq_matches_fp32(pkg, B, heads, L):
     got = dqkv.float().cpu()
     assert ((got[:, :H] - dq_want).abs().max() / dq_want.abs().max()).item() <= 1e-2
     assert (got[:, H:] == 7.0).all()
+
+
+@pytest.mark.parametrize("B,heads,L", [(2, 12, 216), (1, 2, 64), (3, 4, 200), (1, 3, 256), (2, 2, 27)])
+def test_fused_attention_backward_kv_matches_fp32(pkg, B, heads, L):
+    """Key-row half of the attention backward (attn_bwd_kv_kernel): dV = P^T dO and dK = dS^T Q against torch fp32 on the same
+    bf16 operands; 1e-2 of max|ref| (bf16 outputs); the Q third of dqkv must stay untouched."""
+    lib = pkg._lib.load()
+    H, Lp = heads * 64, (L + 7) & ~7
+    g = torch.Generator().manual_seed(B * 131 + L)
+    qkv = torch.randn(B * L, 3 * H, generator=g).to(torch.bfloat16)
+    datt = torch.randn(B * L, H, generator=g).to(torch.bfloat16)
+    probs = torch.zeros(B, heads, L, Lp)
+    probs[..., :L] = torch.softmax(torch.randn(B, heads, L, L, generator=g), dim=-1)
+    dS = torch.zeros(B, heads, L, Lp)
+    dS[..., :L] = torch.randn(B, heads, L, L, generator=g) * 0.05
+    probs, dS = probs.to(torch.bfloat16), dS.to(torch.bfloat16)
+    q = qkv.float().view(B, L, 3, heads, 64)[:, :, 0].permute(0, 2, 1, 3)
+    do = datt.float().view(B, L, heads, 64).permute(0, 2, 1, 3)
+    dv_want = (probs.float()[..., :L].transpose(-1, -2) @ do).permute(0, 2, 1, 3).reshape(B * L, H)
+    dk_want = (dS.float()[..., :L].transpose(-1, -2) @ q).permute(0, 2, 1, 3).reshape(B * L, H)
+    qkv_d, probs_d, ds_d, datt_d = qkv.to(DEV), probs.to(DEV), dS.to(DEV), datt.to(DEV)
+    dqkv = torch.full((B * L, 3 * H), 7.0, dtype=torch.bfloat16, device=DEV)
+    pkg._lib.check(lib.b200_test_tc_attention_bwd_kv(pkg._lib.ptr(qkv_d), pkg._lib.ptr(probs_d), pkg._lib.ptr(ds_d), pkg._lib.ptr(datt_d),
+                                                      pkg._lib.ptr(dqkv), B, heads, L, Lp, H, pkg._lib.stream_ptr()), "tc_attention_bwd_kv")
+    torch.cuda.synchronize()
+    got = dqkv.float().cpu()
+    assert (got[:, :H] == 7.0).all()
+    assert ((got[:, H:2 * H] - dk_want).abs().max() / dk_want.abs().max()).item() <= 1e-2
+    assert ((got[:, 2 * H:] - dv_want).abs().max() / dv_want.abs().max()).item() <= 1e-2
