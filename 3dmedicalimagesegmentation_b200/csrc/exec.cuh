@@ -495,8 +495,24 @@ struct Exec {
       B200_LAUNCH_CHECK();
       return 0;
     }
-    if (dW1) { B200_TRY(zero_grad(dW1, (size_t)Co * Ci * 27, st)); B200_TRY(conv_wgrad(x, dc1, s, 3, dW1, st)); }
-    if (dW3) { B200_TRY(zero_grad(dW3, (size_t)Co * Ci, st)); B200_TRY(conv_wgrad(x, dc3, s, 1, dW3, st)); }
+    bool wg_fused = false;
+    if constexpr (kTC) {
+      // conv1 (3^3) and conv3 (1^3) read the same x: one halo weight-gradient launch with a tenth accumulator for the 1^3 tap
+      static const bool off = getenv("B200_NO_FUSED_WGRAD_1X1") != nullptr;
+      if (!off && dW1 && dW3 && tc::wgrad_supported(x.C, dc1.C, x.pitch, x.coff, dc1.pitch, dc1.coff) && tc::wgrad_halo_supported(x.C, dc1.C, 3) &&
+          dc3.C == dc1.C && (dc3.pitch * 2) % 16 == 0 && (dc3.coff * 2) % 16 == 0) {
+        B200_TRY(zero_grad(dW1, (size_t)Co * Ci * 27, st));
+        B200_TRY(zero_grad(dW3, (size_t)Co * Ci, st));
+        B200_PROFD(st, "conv_wgrad k3+k1 %dx%d @%d", x.C, dc1.C, s.D);
+        B200_TRY(tc::conv_wgrad_halo(x.p, x.pitch, x.coff, x.C, dc1.p, dc1.pitch, dc1.coff, dc1.C, s.N, s.D, s.H, s.W, dW1, st,
+                                     dc3.p, dc3.pitch, dc3.coff, dW3));
+        wg_fused = true;
+      }
+    }
+    if (!wg_fused) {
+      if (dW1) { B200_TRY(zero_grad(dW1, (size_t)Co * Ci * 27, st)); B200_TRY(conv_wgrad(x, dc1, s, 3, dW1, st)); }
+      if (dW3) { B200_TRY(zero_grad(dW3, (size_t)Co * Ci, st)); B200_TRY(conv_wgrad(x, dc3, s, 1, dW3, st)); }
+    }
     if (dx.p) {
       if constexpr (kTC) {   // dx = dgrad3x3(dc1) + dgrad1x1(dc3) in one kernel (second input tile, same accumulator)
         int i1 = conv_index(W1), i3 = conv_index(W3);

@@ -24,12 +24,15 @@ struct WgradHaloParams {
   int tiles_w, tiles_h, tiles_per_n, total_tiles;
   int plane_bytes, x_bytes, dy_bytes, stage_bytes, stages; uint32_t tmem_cols;
   float* dW;
+  float* dW3;               // optional: weight gradient [Co][Ci] of the residual block's 1x1x1 convolution on the same x (fused: a tenth
+                            // accumulator fed by the centre tap and a second dy tile); nullptr = plain 3x3x3 weight gradient
   long long* trace;
 };
 
 template <int CI>   // 16 or 32
 __global__ void __launch_bounds__(192, 1)
-wgrad_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_dy, const WgradHaloParams p) {
+wgrad_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_dy3,
+                  const WgradHaloParams p) {
   constexpr uint32_t ROW_BYTES = CI * 2, ROW_UNITS = ROW_BYTES / 16;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -59,7 +62,7 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     // ---- TMA producer
     int stage = 0; uint32_t phase = 0;
     const uint32_t smem_u = smem_u32(smem);
-    const uint32_t tx = (uint32_t)(3 * p.plane_bytes) + (uint32_t)(128 * p.Co * 2);
+    const uint32_t tx = (uint32_t)(3 * p.plane_bytes) + (uint32_t)(128 * p.Co * 2) * (p.dW3 ? 2u : 1u);
     int t = blockIdx.x;
     int n = t / p.tiles_per_n, r = t - n * p.tiles_per_n;
     for (; t < p.total_tiles; t += gridDim.x) {
@@ -70,6 +73,7 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
         mbar_expect_tx(full + stage, tx);
         tma_load_5d(base, &map_x, full + stage, 0, tw * HTW - 1, th * HTH - 1, d - 1, n);
         tma_load_5d(base + p.x_bytes, &map_dy, full + stage, 0, tw * HTW, th * HTH, d, n);
+        if (p.dW3) tma_load_5d(base + p.x_bytes + p.dy_bytes, &map_dy3, full + stage, 0, tw * HTW, th * HTH, d, n);
       }
       __syncwarp();
       if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -109,6 +113,14 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
             for (int j = 0; j < 8; ++j)
               umma_f16(tmem_d, desc64(a_t + (uint32_t)j * A_KSTEP, a_hi), desc64(b_st + (uint32_t)j * b_kstep, b_hi), idesc, j == 0 ? accum : 1u);
           }
+        if (p.dW3) {   // 1x1x1: centre (kd, kh) = (1, 1) view of x against the second dy tile; the kw = 1 atom is the result
+          const uint32_t a_t = a_st + plane_units + (uint32_t)HALO_W * ROW_UNITS;
+          const uint32_t b3 = b_st + ((uint32_t)p.dy_bytes >> 4);
+          const uint32_t tmem_d = tmem_base + 9u * co;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            umma_f16(tmem_d, desc64(a_t + (uint32_t)j * A_KSTEP, a_hi), desc64(b3 + (uint32_t)j * b_kstep, b_hi), idesc, j == 0 ? accum : 1u);
+        }
         umma_commit(empty + stage);
       }
       __syncwarp();
@@ -137,6 +149,17 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
           }
         }
       }
+      if (p.dW3) {
+        const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(9 * p.Co);
+        for (int c0 = 0; c0 < p.Co; c0 += 16) {
+          float v[16];
+          tmem_ld16(trow + c0, v);
+          if (kw == 1) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) atomicAdd(p.dW3 + (long)(c0 + j) * p.Ci + ci, v[j]);
+          }
+        }
+      }
     }
   }
   tc_fence_before();
@@ -153,17 +176,19 @@ static inline bool wgrad_halo_supported(int Ci, int Co, int ks) {
 }
 
 template <int CI>
-static int wgrad_halo_launch(const CUtensorMap& mx, const CUtensorMap& mdy, const WgradHaloParams& p, int grid, size_t smem, cudaStream_t st) {
+static int wgrad_halo_launch(const CUtensorMap& mx, const CUtensorMap& mdy, const CUtensorMap& mdy3, const WgradHaloParams& p, int grid, size_t smem,
+                             cudaStream_t st) {
   static bool attr_done = false;
   if (!attr_done) { B200_CUDA(cudaFuncSetAttribute(wgrad_halo_kernel<CI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr_done = true; }
-  B200_CUDA(launch_pdl(wgrad_halo_kernel<CI>, dim3(grid), dim3(192), smem, st, mx, mdy, p));
+  B200_CUDA(launch_pdl(wgrad_halo_kernel<CI>, dim3(grid), dim3(192), smem, st, mx, mdy, mdy3, p));
   B200_LAUNCH_CHECK();
   return 0;
 }
 
-// dW (fp32 [Co][Ci][27]) must be zero on entry.
+// dW (fp32 [Co][Ci][27]) must be zero on entry.  dy3 / dW3 (optional, dW3 fp32 [Co][Ci] zero on entry): the 1x1x1 convolution of the
+// residual block reads the same x, so its weight gradient rides along as a tenth accumulator (one more TMA box, 8 more MMAs per tile).
 static int conv_wgrad_halo(const bf16* x, int x_pitch, int x_coff, int Ci, const bf16* dy, int dy_pitch, int dy_coff, int Co, int N, int D, int H, int W,
-                           float* dW, cudaStream_t st) {
+                           float* dW, cudaStream_t st, const bf16* dy3 = nullptr, int dy3_pitch = 0, int dy3_coff = 0, float* dW3 = nullptr) {
   EncodeTiledFn enc = get_encode();
   B200_CHECK(enc, "cuTensorMapEncodeTiled not available from the driver");
   WgradHaloParams p;
@@ -177,13 +202,14 @@ static int conv_wgrad_halo(const bf16* x, int x_pitch, int x_coff, int Ci, const
   // the junk atoms of the last k-step read up to (128/Ci - 3) voxel rows past the third plane: keep them inside the stage
   p.x_bytes = ((3 * p.plane_bytes + (128 / Ci) * rb + 1023) / 1024) * 1024;
   p.dy_bytes = ((128 * Co * 2 + 1023) / 1024) * 1024;
-  p.stage_bytes = p.x_bytes + p.dy_bytes;
+  p.dW3 = (dy3 && dW3) ? dW3 : nullptr;
+  p.stage_bytes = p.x_bytes + p.dy_bytes * (p.dW3 ? 2 : 1);
   p.stages = (200 * 1024) / p.stage_bytes; if (p.stages > 8) p.stages = 8;
   B200_CHECK(p.stages >= 2, "wgrad halo smem budget exceeded");
-  uint32_t cols = 9 * Co, pw = 32; while (pw < cols) pw <<= 1; p.tmem_cols = pw;
+  uint32_t cols = (p.dW3 ? 10 : 9) * Co, pw = 32; while (pw < cols) pw <<= 1; p.tmem_cols = pw;
   B200_CHECK(p.tmem_cols <= 512, "wgrad halo TMEM budget exceeded");
   p.dW = dW;
-  p.trace = trace_slot(); if (p.trace) trace_tag("wgrad_halo %dx%d @%d", Ci, Co, D);
+  p.trace = trace_slot(); if (p.trace) trace_tag("wgrad_halo %dx%d @%d%s", Ci, Co, D, p.dW3 ? " +1x1" : "");
   CUtensorMap mx, mdy;
   {
     CUtensorMapSwizzle sw = rb == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
@@ -205,10 +231,21 @@ static int conv_wgrad_halo(const bf16* x, int x_pitch, int x_coff, int Ci, const
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     B200_CHECK(r == CUDA_SUCCESS, "wgrad halo dy tensor map failed (%d)", (int)r);
   }
+  CUtensorMap mdy3 = mdy;
+  if (p.dW3) {
+    CUtensorMapSwizzle sw = Co * 2 == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+    cuuint64_t dims[5] = {(cuuint64_t)Co, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
+    cuuint64_t strides[4] = {(cuuint64_t)dy3_pitch * 2, (cuuint64_t)W * dy3_pitch * 2, (cuuint64_t)H * W * dy3_pitch * 2, (cuuint64_t)D * H * W * dy3_pitch * 2};
+    cuuint32_t box[5] = {(cuuint32_t)Co, HTW, HTH, 1, 1};
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(&mdy3, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (void*)(dy3 + dy3_coff), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    B200_CHECK(r == CUDA_SUCCESS, "wgrad halo dy3 tensor map failed (%d)", (int)r);
+  }
   size_t smem = (size_t)p.stages * p.stage_bytes + 1024 + 256;
   int grid = (int)(p.total_tiles < num_sms() ? p.total_tiles : num_sms());
-  if (Ci == 16) return wgrad_halo_launch<16>(mx, mdy, p, grid, smem, st);
-  return wgrad_halo_launch<32>(mx, mdy, p, grid, smem, st);
+  if (Ci == 16) return wgrad_halo_launch<16>(mx, mdy, mdy3, p, grid, smem, st);
+  return wgrad_halo_launch<32>(mx, mdy, mdy3, p, grid, smem, st);
 }
 
 }  // namespace tc

@@ -572,3 +572,26 @@ def test_task01_configuration_four_channel_128_cube_sigmoid_loss(pkg, mode, tol)
     loss.backward()
     torch.cuda.synchronize()
     assert all(torch.isfinite(p.grad).all().item() for n, p in mine.named_parameters() if "cls_token" not in n)
+
+
+def test_fused_1x1_weight_gradient_rides_on_the_halo_kernel(pkg):
+    """decoder2's residual block: the 1^3 convolution's weight gradient is formed by the 3^3 halo weight-gradient launch (tenth TMEM
+    accumulator, centre tap).  bf16-mode gradients of both convolutions against the fp32-mode kernels of the same network: the
+    layers sit next to the loss, where bf16 gradients agree to cosine > 0.995; with the fusion switched off the same numbers come out."""
+    cfg = dict(in_channels=1, out_channels=5, img_size=(48, 48, 48), feature_size=16, hidden_size=128, mlp_dim=256, num_heads=2,
+               pos_embed="perceptron", norm_name="instance", res_block=True)
+    torch.manual_seed(3)
+    base = pkg.UNETR(**cfg)
+    x, y = O.make_inputs(batch=2, img=48, n_classes=5, seed=5)
+    grads = {}
+    for mode in ("fp32", "bf16"):
+        net = pkg.UNETR(**cfg)
+        net.load_state_dict(base.state_dict())
+        net = net.to(DEV).set_mode(mode)
+        _, logits = net(x.to(DEV))
+        pkg.DiceCELoss(to_onehot_y=True, softmax=True)(logits, y.to(DEV)).backward()
+        grads[mode] = {k: p.grad.detach().clone() for k, p in net.named_parameters() if p.grad is not None}
+    for k in ("decoder2.conv_block.conv1.conv.weight", "decoder2.conv_block.conv3.conv.weight", "decoder2.conv_block.conv2.conv.weight"):
+        c = cosine(grads["bf16"][k], grads["fp32"][k])
+        n = (grads["bf16"][k].norm() / grads["fp32"][k].norm()).item()
+        assert c >= 0.995 and 0.95 <= n <= 1.05, (k, c, n)
