@@ -263,10 +263,10 @@ def main():
             c = classes[names[1]]; c[0] += v[0]; c[2] += v[1]
             c[1] += v[1] * 2.0 * B * int(m.group(5)) ** 3 * int(m.group(3)) * int(m.group(4)) * taps
             continue
-        m = re.match(r"conv_wgrad k(\d) (\d+)x(\d+) @(\d+)", k)
-        if m:
+        m = re.match(r"conv_wgrad k(\d)(\+k1)? (\d+)x(\d+) @(\d+)", k)
+        if m:     # "k3+k1": the residual block's 1^3 weight gradient formed by the same halo launch (one more tap)
             c = classes[names[2]]; c[0] += v[0]; c[2] += v[1]
-            c[1] += v[1] * 2.0 * B * int(m.group(4)) ** 3 * int(m.group(2)) * int(m.group(3)) * int(m.group(1)) ** 3
+            c[1] += v[1] * 2.0 * B * int(m.group(5)) ** 3 * int(m.group(3)) * int(m.group(4)) * (int(m.group(1)) ** 3 + (1 if m.group(2) else 0))
     try:
         traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
     except Exception:
