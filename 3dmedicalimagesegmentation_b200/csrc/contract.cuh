@@ -97,7 +97,14 @@ struct ConvWeightB {
 };
 
 // ------------------------------------------------------------------ epilogues:  void operator()(b, m, n, acc)
-enum { ACT_NONE = 0, ACT_GELU = 1, ACT_GELU_BWD = 2 };
+// ACT_GELU_SAVE (forward of a layer that will be differentiated): out = gelu(v) and `preact` receives gelu'(v) instead of v -- the erf is
+// shared, and the backward epilogue (ACT_MUL_SAVED: v *= usrc) is one multiply instead of erf + exp per element
+enum { ACT_NONE = 0, ACT_GELU = 1, ACT_GELU_BWD = 2, ACT_GELU_SAVE = 3, ACT_MUL_SAVED = 4 };
+__device__ __forceinline__ void gelu_and_grad(float x, float& y, float& dy) {
+  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
+  y = x * cdf;
+  dy = cdf + x * 0.3989422804014327f * __expf(-0.5f * x * x);
+}
 
 // 4 consecutive elements <-> floats (16-byte fp32 / 8-byte 16-bit accesses): the coalesced tcgen05 epilogue hands every lane 4 columns
 __device__ __forceinline__ void ep_ld4(const float* p, float* o) { float4 t = *reinterpret_cast<const float4*>(p); o[0] = t.x; o[1] = t.y; o[2] = t.z; o[3] = t.w; }
@@ -155,9 +162,13 @@ struct EpStore {
     long o = (long)(b / nb1) * sb0 + (long)(b % nb1) * sb1 + (long)m * ld + n;
     float v = acc * alpha;
     if (bias) v += bias[n];
-    if (preact) preact[o] = from_f<TO>(v);
-    if (act == ACT_GELU) v = gelu_erf(v);
-    else if (act == ACT_GELU_BWD) v *= gelu_erf_grad(to_f(usrc[o]));
+    if (act == ACT_GELU_SAVE) { float y, d; gelu_and_grad(v, y, d); preact[o] = from_f<TO>(d); v = y; }
+    else {
+      if (preact) preact[o] = from_f<TO>(v);
+      if (act == ACT_GELU) v = gelu_erf(v);
+      else if (act == ACT_GELU_BWD) v *= gelu_erf_grad(to_f(usrc[o]));
+      else if (act == ACT_MUL_SAVED) v *= to_f(usrc[o]);
+    }
     if (resid) v += resid[(long)m * ldr + n];
     if (accumulate) v += to_f(out[o]);
     out[o] = from_f<TO>(v);
@@ -182,7 +193,13 @@ struct EpStore {
 #pragma unroll
       for (int j = 0; j < 16; j += 4) { float4 t = *reinterpret_cast<const float4*>(bias + n0 + j); v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w; }
     }
-    if (preact) {
+    if (act == ACT_GELU_SAVE) {
+      float d[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) { float y; gelu_and_grad(v[j], y, d[j]); v[j] = y; }
+#pragma unroll
+      for (int j = 0; j < 16; j += VN) { Vec16<TO> t; for (int i = 0; i < VN; ++i) t.v[i] = d[j + i]; t.store(preact + o + j); }
+    } else if (preact) {
 #pragma unroll
       for (int j = 0; j < 16; j += VN) { Vec16<TO> t; for (int i = 0; i < VN; ++i) t.v[i] = v[j + i]; t.store(preact + o + j); }
     }
@@ -192,6 +209,9 @@ struct EpStore {
     } else if (act == ACT_GELU_BWD) {
 #pragma unroll
       for (int j = 0; j < 16; j += VN) { Vec16<TO> t; t.load(usrc + o + j); for (int i = 0; i < VN; ++i) v[j + i] *= gelu_erf_grad(t.v[i]); }
+    } else if (act == ACT_MUL_SAVED) {
+#pragma unroll
+      for (int j = 0; j < 16; j += VN) { Vec16<TO> t; t.load(usrc + o + j); for (int i = 0; i < VN; ++i) v[j + i] *= t.v[i]; }
     }
     if (resid) {
       const float* r = resid + (long)m * ldr + n0;
@@ -231,7 +251,12 @@ struct EpStore {
     }
     float v[4] = {acc[0] * alpha, acc[1] * alpha, acc[2] * alpha, acc[3] * alpha};
     if (bias) { float4 t = *reinterpret_cast<const float4*>(bias + n0); v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w; }
-    if (preact) ep_st4(preact + o, v);
+    if (act == ACT_GELU_SAVE) {
+      float d[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { float y; gelu_and_grad(v[j], y, d[j]); v[j] = y; }
+      ep_st4(preact + o, d);
+    } else if (preact) ep_st4(preact + o, v);
     if (act == ACT_GELU) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) v[j] = gelu_erf(v[j]);
@@ -239,6 +264,10 @@ struct EpStore {
       float u[4]; ep_ld4(usrc + o, u);
 #pragma unroll
       for (int j = 0; j < 4; ++j) v[j] *= gelu_erf_grad(u[j]);
+    } else if (act == ACT_MUL_SAVED) {
+      float u[4]; ep_ld4(usrc + o, u);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] *= u[j];
     }
     if (resid) { float4 t = *reinterpret_cast<const float4*>(resid + (long)m * ldr + n0); v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w; }
     if (accumulate) { float u[4]; ep_ld4(out + o, u); v[0] += u[0]; v[1] += u[1]; v[2] += u[2]; v[3] += u[3]; }
@@ -275,7 +304,12 @@ struct EpStore {
     }
     float v[4] = {acc[0] * alpha, acc[1] * alpha, acc[2] * alpha, acc[3] * alpha};
     if (bias) { float4 q = *reinterpret_cast<const float4*>(bias + n0); v[0] += q.x; v[1] += q.y; v[2] += q.z; v[3] += q.w; }
-    if (preact) ep_st4(preact + o, v);
+    if (act == ACT_GELU_SAVE) {
+      float d[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { float y; gelu_and_grad(v[j], y, d[j]); v[j] = y; }
+      ep_st4(preact + o, d);
+    } else if (preact) ep_st4(preact + o, v);
     if (act == ACT_GELU) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) v[j] = gelu_erf(v[j]);
@@ -283,6 +317,10 @@ struct EpStore {
       float u[4]; ep_ld4(usrc + o, u);
 #pragma unroll
       for (int j = 0; j < 4; ++j) v[j] *= gelu_erf_grad(u[j]);
+    } else if (act == ACT_MUL_SAVED) {
+      float u[4]; ep_ld4(usrc + o, u);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] *= u[j];
     }
     if (resid) { float4 q = *reinterpret_cast<const float4*>(resid + (long)m * ldr + n0); v[0] += q.x; v[1] += q.y; v[2] += q.z; v[3] += q.w; }
     if (accumulate) { float u[4]; ep_ld4(out + o, u); v[0] += u[0]; v[1] += u[1]; v[2] += u[2]; v[3] += u[3]; }

@@ -570,7 +570,9 @@ struct Exec {
       }
       B200_TRY(launch_layernorm_fwd<T>(w.x1[i], bp[B_LN2_W], bp[B_LN2_B], w.ln2[i], w.ln2s[i], M, H, st, pend.nsplit ? &pend : nullptr));
       pend.nsplit = 0;
-      { EpStore<T> ep = ep_plain<T>(w.h[i], F); ep.bias = bp[B_FC1_B]; ep.act = ACT_GELU; ep.preact = w.u[i];
+      { EpStore<T> ep = ep_plain<T>(w.h[i], F); ep.bias = bp[B_FC1_B];
+        // training: u[i] receives gelu'(pre-activation) (all the backward needs of it); inference: nothing is kept
+        if (no_backward) { ep.act = ACT_GELU; ep.preact = nullptr; } else { ep.act = ACT_GELU_SAVE; ep.preact = w.u[i]; }
         B200_TRY(linear_fwd<T>(w.ln2[i], H, bp[B_FC1_W], w.wfc1[i], M, F, H, ep, st)); }
       if (can_split(M, H, F)) {
         B200_TRY(linear_fwd_split(w.h[i], F, w.wfc2[i], M, H, F, bp[B_FC2_B], w.x1[i], w.hs[i], &pend, st));
@@ -856,7 +858,7 @@ struct Exec {
       // hs = x1 + fc2(h) + b2
       if (bg[B_FC2_W]) B200_TRY(linear_wgrad(w.dxb, H, w.h[i], F, M, H, F, bg[B_FC2_W], st));
       if (bg[B_FC2_B]) B200_TRY(launch_colsum<float>(w.dx, bg[B_FC2_B], M, H, st));
-      { EpStore<T> ep = ep_plain<T>(w.dh, F); ep.act = ACT_GELU_BWD; ep.usrc = w.u[i];   // du = (dx W2) * gelu'(u)
+      { EpStore<T> ep = ep_plain<T>(w.dh, F); ep.act = ACT_MUL_SAVED; ep.usrc = w.u[i];   // du = (dx W2) * gelu'(u), gelu'(u) saved by the forward epilogue
         B200_TRY(linear_dgrad<T>(w.dxb, H, bp[B_FC2_W], w.wfc2[i], M, H, F, ep, st)); }
       if (bg[B_FC1_W]) B200_TRY(linear_wgrad(w.dh, F, w.ln2[i], H, M, F, H, bg[B_FC1_W], st));
       if (bg[B_FC1_B]) B200_TRY(launch_colsum<T>(w.dh, bg[B_FC1_B], M, F, st));
