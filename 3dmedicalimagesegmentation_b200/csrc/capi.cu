@@ -16,6 +16,7 @@
 #include "sliding.cuh"
 #include "metrics.cuh"
 #include "tc_gemm.cuh"
+#include "tc_gemm_grouped.cuh"
 #include "tc_attention.cuh"
 #include "tc_conv_halo.cuh"
 #include "tc_wgrad_halo.cuh"
@@ -440,6 +441,11 @@ void b200_test_set_debug_buffer(void* dev_ptr) { tc::g_dbg = (long long*)dev_ptr
 
 int b200_test_tc_gemm(const void* a, const void* b, float* out, int M, int N, int K, int a_mn, int b_mn, void* stream) {
   return tc_gemm_test((const bf16*)a, (const bf16*)b, out, M, N, K, a_mn, b_mn, (cudaStream_t)stream);
+}
+
+int b200_test_tc_gemm_grouped(const void* const* a, const void* const* b, float* const* out, const int* M, const int* N, const int* K, int n, int mn,
+                              void* stream) {
+  return tc_gemm_grouped_test((const bf16* const*)a, (const bf16* const*)b, out, M, N, K, n, mn, (cudaStream_t)stream);
 }
 
 // test hook for the fused attention forward: qkv [B*L][3H] bf16 -> probs [B][nh][L][Lp] bf16 (may be NULL), att [B*L][H] bf16

@@ -13,6 +13,7 @@
 #include "ops.cuh"
 #include "edge_kernels.cuh"
 #include "tc_gemm.cuh"
+#include "tc_gemm_grouped.cuh"
 #include "tc_attention.cuh"
 #include "tc_conv.cuh"
 #include "tc_conv_halo.cuh"
@@ -75,8 +76,12 @@ struct Workspace {
   // backward scratch
   float *dx, *dx2, *dhs[3], *dP;
   float* part;   // split-K partial tiles [<=4][M][H] (summed by the LayerNorm kernel that consumes the GEMM)
-  T *dxb, *dx2b, *unsh;  // unsh: pixel-unshuffled dOut of a transposed conv [rows_in, 8*Co]  // bf16 mode: operand copies of the fp32 residual-stream gradients
-  T *dvit, *dh, *dln, *datt, *dqkv, *dS, *gA, *dcat, *dc2, *dc3, *da1, *dc1;
+  T *unsh;  // unsh: pixel-unshuffled dOut of a transposed conv [rows_in, 8*Co]  // bf16 mode: operand copies of the fp32 residual-stream gradients
+  T *dvit, *datt, *dS, *gA, *dcat, *dc2, *dc3, *da1, *dc1;
+  // per-block operands of the DEFERRED parameter gradients (weight / bias / LayerNorm-parameter sums are issued per group of blocks,
+  // see vit_param_grads): dyo[i+1] = d(hs[i]) and dyo[0] = d(x0) as T, dh[i] = d(fc1 pre-activation), dy1[i] = d(x1[i]) as T,
+  // dqkv[i], dln2[i] / dln1[i] = gradients wrt the two LayerNorm outputs
+  T *dyo[13], *dh[12], *dy1[12], *dqkv[12], *dln2[12], *dln1[12];
   double* bwd_acc;       // current backward-norm accumulator: a fresh pre-zeroed slot of bwd_pool per use (one memset per backward)
   double* bwd_pool; int bwd_next;
   size_t bytes;
@@ -200,10 +205,14 @@ struct Exec {
     }
     if (with_backward) {
       w.dx = b.take<float>(MH); w.dx2 = b.take<float>(MH);
-      w.dxb = b.take<T>(MH); w.dx2b = b.take<T>(MH);
       for (int i = 0; i < 3; ++i) w.dhs[i] = b.take<float>(MH);
       w.dP = b.take<float>(PP); w.dS = b.take<T>(PP);
-      w.dvit = b.take<T>(MH); w.dh = b.take<T>(MF); w.dln = b.take<T>(MH); w.datt = b.take<T>(MH); w.dqkv = b.take<T>(3 * MH);
+      w.dvit = b.take<T>(MH); w.datt = b.take<T>(MH);
+      for (int i = 0; i < 13; ++i) w.dyo[i] = b.take<T>(MH);
+      for (int i = 0; i < 12; ++i) {
+        w.dh[i] = b.take<T>(MF); w.dy1[i] = b.take<T>(MH); w.dqkv[i] = b.take<T>(3 * MH);
+        w.dln2[i] = b.take<T>(MH); w.dln1[i] = b.take<T>(MH);
+      }
       size_t big = (size_t)B * V[0] * fs;
       w.gA = b.take<T>(big); w.dcat = b.take<T>(2 * big); w.dc2 = b.take<T>(big); w.dc3 = b.take<T>(big);
       w.da1 = b.take<T>(big); w.dc1 = b.take<T>(big); w.unsh = b.take<T>(big);
@@ -691,12 +700,12 @@ struct Exec {
       // smem) -> dQ = dS K; the key-row half stays two batched GEMMs over P^T and dS^T
       static const bool off = getenv("B200_NO_FUSED_ATTENTION_BWD") != nullptr;
       if (!off && tc::attention_fused_supported(L, Lp, H, nh)) {
-        B200_TRY(tc::attention_fused_bwd_dq(qkv, w.P[i], w.datt, w.dS, w.dqkv, c.B, nh, L, Lp, H, scale, st));
+        B200_TRY(tc::attention_fused_bwd_dq(qkv, w.P[i], w.datt, w.dS, w.dqkv[i], c.B, nh, L, Lp, H, scale, st));
         static const bool kv_off = getenv("B200_NO_FUSED_ATTENTION_KV") != nullptr;
-        if (!kv_off) return tc::attention_fused_bwd_kv(qkv, w.P[i], w.dS, w.datt, w.dqkv, c.B, nh, L, Lp, H, st);   // dV, dK in one launch
-        { EpStore<T> ep = ep_plain<T>(w.dqkv + 2 * H, 3 * H); ep.sb0 = sQb; ep.sb1 = dh; ep.nb1 = nh;      // dV = P^T dO
+        if (!kv_off) return tc::attention_fused_bwd_kv(qkv, w.P[i], w.dS, w.datt, w.dqkv[i], c.B, nh, L, Lp, H, st);   // dV, dK in one launch
+        { EpStore<T> ep = ep_plain<T>(w.dqkv[i] + 2 * H, 3 * H); ep.sb0 = sQb; ep.sb1 = dh; ep.nb1 = nh;      // dV = P^T dO
           B200_TRY(tc::gemm(tc::operand(w.P[i], 1, Lp, sPb, sPh), tc::operand(w.datt, 1, H, sOb, dh), ep, L, dh, L, c.B, nh, st)); }
-        { EpStore<T> ep = ep_plain<T>(w.dqkv + H, 3 * H); ep.sb0 = sQb; ep.sb1 = dh; ep.nb1 = nh;          // dK = dS^T Q
+        { EpStore<T> ep = ep_plain<T>(w.dqkv[i] + H, 3 * H); ep.sb0 = sQb; ep.sb1 = dh; ep.nb1 = nh;          // dK = dS^T Q
           B200_TRY(tc::gemm(tc::operand(w.dS, 1, Lp, sPb, sPh), tc::operand(qkv, 1, 3 * H, sQb, dh), ep, L, dh, L, c.B, nh, st)); }
         return 0;
       }
@@ -716,7 +725,7 @@ struct Exec {
       else B200_TRY(launch_contract(ld4<T, false>(w.datt, H, 1, sOb, dh, nh), ld4<T, false>(qkv + 2 * H, 3 * H, 1, sQb, dh, nh), ep, L, L, dh, BH, 1, st));
     }
     // dV = P^T dO
-    { EpStore<T> ep = ep_plain<T>(w.dqkv + 2 * H, 3 * H); ep.sb0 = sQb; ep.sb1 = dh; ep.nb1 = nh;
+    { EpStore<T> ep = ep_plain<T>(w.dqkv[i] + 2 * H, 3 * H); ep.sb0 = sQb; ep.sb1 = dh; ep.nb1 = nh;
       if constexpr (kTC) B200_TRY(tc::gemm(tc::operand(w.P[i], 1, Lp, sPb, sPh), tc::operand(w.datt, 1, H, sOb, dh), ep, L, dh, L, c.B, nh, st));
       else B200_TRY(launch_contract(ld4<T, true>(w.P[i], 1, Lp, sPb, sPh, nh), ld4<T, true>(w.datt, 1, H, sOb, dh, nh), ep, L, dh, L, BH, 1, st)); }
     if (!fused_sm) {
@@ -724,12 +733,53 @@ struct Exec {
       B200_LAUNCH_CHECK();
     }
     // dQ = dS K ; dK = dS^T Q
-    { EpStore<T> ep = ep_plain<T>(w.dqkv, 3 * H); ep.sb0 = sQb; ep.sb1 = dh; ep.nb1 = nh;
+    { EpStore<T> ep = ep_plain<T>(w.dqkv[i], 3 * H); ep.sb0 = sQb; ep.sb1 = dh; ep.nb1 = nh;
       if constexpr (kTC) B200_TRY(tc::gemm(tc::operand(w.dS, Lp, 1, sPb, sPh), tc::operand(qkv + H, 1, 3 * H, sQb, dh), ep, L, dh, L, c.B, nh, st));
       else B200_TRY(launch_contract(ld4<T, false>(w.dS, Lp, 1, sPb, sPh, nh), ld4<T, true>(qkv + H, 1, 3 * H, sQb, dh, nh), ep, L, dh, L, BH, 1, st)); }
-    { EpStore<T> ep = ep_plain<T>(w.dqkv + H, 3 * H); ep.sb0 = sQb; ep.sb1 = dh; ep.nb1 = nh;
+    { EpStore<T> ep = ep_plain<T>(w.dqkv[i] + H, 3 * H); ep.sb0 = sQb; ep.sb1 = dh; ep.nb1 = nh;
       if constexpr (kTC) B200_TRY(tc::gemm(tc::operand(w.dS, 1, Lp, sPb, sPh), tc::operand(qkv, 1, 3 * H, sQb, dh), ep, L, dh, L, c.B, nh, st));
       else B200_TRY(launch_contract(ld4<T, true>(w.dS, 1, Lp, sPb, sPh, nh), ld4<T, true>(qkv, 1, 3 * H, sQb, dh, nh), ep, L, dh, L, BH, 1, st)); }
+    return 0;
+  }
+
+  // Parameter gradients of transformer blocks lo..hi from the per-block operands the critical path left behind:
+  //   weights   dW = dY^T X for {fc2, fc1, out_proj, qkv}: ONE grouped tcgen05 launch (tc_gemm_grouped.cuh) in bf16 mode
+  //   biases    column sums of dY: one launch;   LayerNorm weight / bias: one launch.
+  int vit_param_grads(float* const* G, int lo, int hi, cudaStream_t st) {
+    if (hi < lo) return 0;
+    tc::GroupItem items[4 * 12]; int ni = 0; double flops = 0;
+    ColsumJobs cs; cs.count = 0;
+    LnParamJobs ln; ln.count = 0; ln.M = M; ln.H = H;
+    for (int i = hi; i >= lo; --i) {
+      float* const* bg = G + P_BLK0 + i * B_COUNT;
+      const float* xin = i ? w.hs[i - 1] : w.x0;
+      struct { float* dW; const T* dY; int N; const T* X; int K; } wg[4] = {
+          {bg[B_FC2_W], w.dyo[i + 1], H, w.h[i], F}, {bg[B_FC1_W], w.dh[i], F, w.ln2[i], H},
+          {bg[B_PROJ_W], w.dy1[i], H, w.att[i], H}, {bg[B_QKV_W], w.dqkv[i], 3 * H, w.ln1[i], H}};
+      for (auto& g : wg) {
+        if (!g.dW) continue;
+        if constexpr (kTC) {
+          tc::GroupItem& it = items[ni++];
+          it.A = tc::operand(g.dY, 1, g.N); it.B = tc::operand(g.X, 1, g.K); it.out = g.dW; it.ldo = g.K; it.M = g.N; it.N = g.K; it.K = M;
+          flops += 2.0 * g.N * g.K * M;
+        } else {
+          B200_TRY(linear_wgrad(g.dY, g.N, g.X, g.K, M, g.N, g.K, g.dW, st));
+        }
+      }
+      if (bg[B_FC2_B]) cs.j[cs.count++] = ColsumJob{w.dyo[i + 1], bg[B_FC2_B], M, H};
+      if (bg[B_FC1_B]) cs.j[cs.count++] = ColsumJob{w.dh[i], bg[B_FC1_B], M, F};
+      if (bg[B_PROJ_B]) cs.j[cs.count++] = ColsumJob{w.dy1[i], bg[B_PROJ_B], M, H};
+      if (bg[B_LN2_W] || bg[B_LN2_B]) ln.j[ln.count++] = LnParamJob{w.dln2[i], w.x1[i], w.ln2s[i], bg[B_LN2_W], bg[B_LN2_B]};
+      if (bg[B_LN1_W] || bg[B_LN1_B]) ln.j[ln.count++] = LnParamJob{w.dln1[i], xin, w.ln1s[i], bg[B_LN1_W], bg[B_LN1_B]};
+    }
+    if constexpr (kTC) {
+      if (ni) {
+        B200_PROFD(st, "linear_wgrad grouped x%d mflop=%.0f", ni, flops * 1e-6);
+        B200_TRY(tc::gemm_grouped(items, ni, st));
+      }
+    }
+    B200_TRY(launch_colsum_multi<T>(cs, st));
+    B200_TRY(launch_layernorm_bwd_params_multi<T>(ln, st));
     return 0;
   }
 
@@ -808,7 +858,6 @@ struct Exec {
         B200_TRY(convT_bwd(w.e2a, 2 * fs, 2 * fs, 3, P[P_E2_T1], cl<const T>(w.dc2, 2 * fs, 0, 2 * fs), G[P_E2_T1], w.dc3, 2 * fs, 0, st));
         B200_TRY(convT_bwd(w.hsT[0], H, H, 4, P[P_E2_T0], cl<const T>(w.dc3, 2 * fs, 0, 2 * fs), G[P_E2_T0], w.dhs[0], H, 0, st));
       }
-      if (flags & 16) return 0;  // debug: stop right after the decoder3 block (b200_unetr_peek then reads its scratch)
       B200_TRY(convT_bwd(w.d2, 4 * fs, 4 * fs, 2, P[P_D3_T], cl<const T>(w.dcat, 4 * fs, 0, 2 * fs), G[P_D3_T], w.gA, 4 * fs, 0, st));
       // decoder4
       B200_TRY(res_bwd(cl<const T>(w.cat4, 8 * fs, 0, 8 * fs), 2, P[P_D4_C1], P[P_D4_C2], P[P_D4_C3], w.rs[2], cl<const T>(w.d2, 4 * fs, 0, 4 * fs),
@@ -841,50 +890,52 @@ struct Exec {
     float scale = 1.0f / sqrtf((float)dh);
     int top = 11;
     if (vit_from_top) {
-      B200_TRY(launch_layernorm_bwd<T>(w.dvit, w.hs[11], w.lnfs, P[P_NORM_W], nullptr, w.dx, w.dxb, G[P_NORM_W], G[P_NORM_B], M, H, st));
+      B200_TRY(launch_layernorm_bwd<T>(w.dvit, w.hs[11], w.lnfs, P[P_NORM_W], nullptr, w.dx, w.dyo[12], G[P_NORM_W], G[P_NORM_B], M, H, st));
     } else {
       top = 9;  // blocks 10, 11 and vit.norm are unreachable from enc4: their grads stay None
       B200_CUDA(cudaMemsetAsync(w.dx, 0, sizeof(float) * M * H, st));
-      B200_CUDA(cudaMemsetAsync(w.dxb, 0, sizeof(T) * M * H, st));
+      B200_CUDA(cudaMemsetAsync(w.dyo[10], 0, sizeof(T) * M * H, st));
     }
+    // The loop below is the CRITICAL PATH only: dgrad GEMMs, attention backward and the LayerNorm input gradients.  Everything that
+    // only feeds the optimizer (4 weight gradients, 3 bias sums and 2 LayerNorm parameter sums per block) reads per-block copies of
+    // the output gradients and is issued by vit_param_grads() once per gradient group (blocks 8..11 / 4..7 / 0..3): 3 launches per
+    // group instead of 36.
+    int group_hi = top;
     for (int i = top; i >= 0; --i) {
       const float* const* bp = P + P_BLK0 + i * B_COUNT;
-      float* const* bg = G + P_BLK0 + i * B_COUNT;
       const float* xin = i ? w.hs[i - 1] : w.x0;
+      T* dyo = w.dyo[i + 1];      // d(hs[i]) as T (the fp32 original is w.dx)
       if (i == 9 || i == 6 || i == 3) {
         B200_TRY(launch_add(w.dx, w.dhs[(i - 3) / 3], (long)M * H, st));
-        B200_TRY(launch_cast<float, T>(w.dx, w.dxb, (long)M * H, st));
+        B200_TRY(launch_cast<float, T>(w.dx, dyo, (long)M * H, st));
       }
       // hs = x1 + fc2(h) + b2
-      if (bg[B_FC2_W]) B200_TRY(linear_wgrad(w.dxb, H, w.h[i], F, M, H, F, bg[B_FC2_W], st));
-      if (bg[B_FC2_B]) B200_TRY(launch_colsum<float>(w.dx, bg[B_FC2_B], M, H, st));
-      { EpStore<T> ep = ep_plain<T>(w.dh, F); ep.act = ACT_MUL_SAVED; ep.usrc = w.u[i];   // du = (dx W2) * gelu'(u), gelu'(u) saved by the forward epilogue
-        B200_TRY(linear_dgrad<T>(w.dxb, H, bp[B_FC2_W], w.wfc2[i], M, H, F, ep, st)); }
-      if (bg[B_FC1_W]) B200_TRY(linear_wgrad(w.dh, F, w.ln2[i], H, M, F, H, bg[B_FC1_W], st));
-      if (bg[B_FC1_B]) B200_TRY(launch_colsum<T>(w.dh, bg[B_FC1_B], M, F, st));
+      { EpStore<T> ep = ep_plain<T>(w.dh[i], F); ep.act = ACT_MUL_SAVED; ep.usrc = w.u[i];   // du = (dx W2) * gelu'(u), gelu'(u) saved by the forward epilogue
+        B200_TRY(linear_dgrad<T>(dyo, H, bp[B_FC2_W], w.wfc2[i], M, H, F, ep, st)); }
       { SplitSum ss; memset(&ss, 0, sizeof(ss));
-        if (can_split(M, H, F)) B200_TRY(linear_dgrad_split(w.dh, F, w.wfc1[i], M, F, H, &ss, st));
-        else B200_TRY(linear_dgrad<T>(w.dh, F, bp[B_FC1_W], w.wfc1[i], M, F, H, ep_plain<T>(w.dln, H), st));
-        B200_TRY(launch_layernorm_bwd<T>(w.dln, w.x1[i], w.ln2s[i], bp[B_LN2_W], w.dx, w.dx2, w.dx2b, bg[B_LN2_W], bg[B_LN2_B], M, H, st, ss.nsplit ? &ss : nullptr)); }
+        if (can_split(M, H, F)) B200_TRY(linear_dgrad_split(w.dh[i], F, w.wfc1[i], M, F, H, &ss, st));
+        else B200_TRY(linear_dgrad<T>(w.dh[i], F, bp[B_FC1_W], w.wfc1[i], M, F, H, ep_plain<T>(w.dln2[i], H), st));
+        B200_TRY(launch_layernorm_bwd<T>(w.dln2[i], w.x1[i], w.ln2s[i], bp[B_LN2_W], w.dx, w.dx2, w.dy1[i], nullptr, nullptr, M, H, st, ss.nsplit ? &ss : nullptr)); }
       // x1 = xin + proj(att) + bp
-      if (bg[B_PROJ_W]) B200_TRY(linear_wgrad(w.dx2b, H, w.att[i], H, M, H, H, bg[B_PROJ_W], st));
-      if (bg[B_PROJ_B]) B200_TRY(launch_colsum<float>(w.dx2, bg[B_PROJ_B], M, H, st));
-      B200_TRY(linear_dgrad<T>(w.dx2b, H, bp[B_PROJ_W], w.wproj[i], M, H, H, ep_plain<T>(w.datt, H), st));
+      B200_TRY(linear_dgrad<T>(w.dy1[i], H, bp[B_PROJ_W], w.wproj[i], M, H, H, ep_plain<T>(w.datt, H), st));
       B200_TRY(attention_bwd(i, scale, st));
-      if (bg[B_QKV_W]) B200_TRY(linear_wgrad(w.dqkv, 3 * H, w.ln1[i], H, M, 3 * H, H, bg[B_QKV_W], st));
       { SplitSum ss; memset(&ss, 0, sizeof(ss));
-        if (can_split(M, H, 3 * H)) B200_TRY(linear_dgrad_split(w.dqkv, 3 * H, w.wqkv[i], M, 3 * H, H, &ss, st));
-        else B200_TRY(linear_dgrad<T>(w.dqkv, 3 * H, bp[B_QKV_W], w.wqkv[i], M, 3 * H, H, ep_plain<T>(w.dln, H), st));
-        B200_TRY(launch_layernorm_bwd<T>(w.dln, xin, w.ln1s[i], bp[B_LN1_W], w.dx2, w.dx, w.dxb, bg[B_LN1_W], bg[B_LN1_B], M, H, st, ss.nsplit ? &ss : nullptr)); }
-      if (i == 8) mark_grads(1, st);
-      if (i == 4) mark_grads(2, st);
+        if (can_split(M, H, 3 * H)) B200_TRY(linear_dgrad_split(w.dqkv[i], 3 * H, w.wqkv[i], M, 3 * H, H, &ss, st));
+        else B200_TRY(linear_dgrad<T>(w.dqkv[i], 3 * H, bp[B_QKV_W], w.wqkv[i], M, 3 * H, H, ep_plain<T>(w.dln1[i], H), st));
+        B200_TRY(launch_layernorm_bwd<T>(w.dln1[i], xin, w.ln1s[i], bp[B_LN1_W], w.dx2, w.dx, w.dyo[i], nullptr, nullptr, M, H, st, ss.nsplit ? &ss : nullptr)); }
+      if (i == 8 || i == 4 || i == 0) {
+        B200_TRY(vit_param_grads(G, i, group_hi, st));
+        group_hi = i - 1;
+        if (i == 8) mark_grads(1, st);
+        if (i == 4) mark_grads(2, st);
+      }
     }
     // --- patch embedding: dW = dx0^T rows(x), db = colsum, dpos = sum over batch
     if (G[P_PATCH_W]) {
       B200_PROF("patch_wgrad", st);
       int Kp = 4096 * c.Cin;
       if constexpr (kTC) {
-        B200_TRY(tc::gemm(tc::operand(w.dxb, 1, H), tc::operand(w.apatch, 1, Kp), ep_plain<float>(G[P_PATCH_W], Kp), H, Kp, M, 1, 1, st));
+        B200_TRY(tc::gemm(tc::operand(w.dyo[0], 1, H), tc::operand(w.apatch, 1, Kp), ep_plain<float>(G[P_PATCH_W], Kp), H, Kp, M, 1, 1, st));
       } else {
         RowIsK<PatchGather, true> bl; bl.g = {x_in, c.Cin, c.S0, c.S1, c.S2, g0, g1, g2, c.conv_patch};
         B200_TRY(launch_contract(ld2<float, true>(w.dx, 1, H), bl, ep_plain<float>(G[P_PATCH_W], Kp), H, Kp, M, 1, 1, st));

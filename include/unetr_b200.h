@@ -161,6 +161,12 @@ void b200_trace_begin(void* buf, int cap);
 int b200_trace_count(void);
 int b200_trace_tags(char* out, int cap);
 int b200_test_tc_gemm(const void* a, const void* b, float* out, int M, int N, int K, int a_mn, int b_mn, void* stream);
+/* op-level hook for the grouped tcgen05 GEMM that forms the deferred ViT weight gradients (dW = dY^T X of
+ * /root/reference/unetr.py:69-76's 12 x {qkv, out_proj, linear1, linear2}) in one persistent launch: n independent problems
+ * out_i [M_i, N_i] fp32 = A_i B_i^T; mn != 0: a_i is [K_i, M_i] and b_i is [K_i, N_i] bf16 (MN-major, the weight-gradient form),
+ * mn == 0: a_i [M_i, K_i], b_i [N_i, K_i].  a / b / out are HOST arrays of n device pointers, M / N / K host arrays of n ints. */
+int b200_test_tc_gemm_grouped(const void* const* a, const void* const* b, float* const* out, const int* M, const int* N, const int* K,
+                              int n, int mn, void* stream);
 /* op-level hook for the fused attention forward (SABlock): qkv [B*L][3H] bf16 with columns [Q|K|V] x head x 64;
  * probs [B][heads][L][Lp] bf16 (softmax(scale QK^T), may be NULL); att [B*L][H] bf16.  head_dim 64, 16 <= L <= 256. */
 int b200_test_tc_attention(const void* qkv, void* probs, void* att, int batch, int heads, int L, int Lp, int H, float scale,

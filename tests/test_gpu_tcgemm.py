@@ -128,3 +128,35 @@ def test_fused_attention_backward_kv_matches_fp32(pkg, B, heads, L):
     assert (got[:, :H] == 7.0).all()
     assert ((got[:, H:2 * H] - dk_want).abs().max() / dk_want.abs().max()).item() <= 1e-2
     assert ((got[:, 2 * H:] - dv_want).abs().max() / dv_want.abs().max()).item() <= 1e-2
+
+
+@pytest.mark.parametrize("mn", [1, 0])
+@pytest.mark.parametrize("tokens,layers", [(432, 4), (2048, 1), (216, 2), (104, 1)])
+def test_grouped_gemm_matches_fp32(pkg, mn, tokens, layers):
+    """tc_gemm_grouped.cuh: the deferred ViT weight gradients dW = dY^T X of `layers` transformer blocks (4 problems each: fc2, fc1,
+    out_proj, qkv at ViT-B sizes, reduction over `tokens` rows with a ragged last k-block) in ONE launch, against torch fp32 on the
+    same bf16 operands.  Tolerance 1e-3 of max|ref| (fp32 accumulation of exact bf16 products; only the order differs)."""
+    import ctypes
+    lib = pkg._lib.load()
+    H, F = 768, 3072
+    shapes = [(H, F), (F, H), (H, H), (3 * H, H)] * layers          # (out features = GEMM M, in features = GEMM N)
+    if tokens == 104:
+        shapes = [(136, 200), (64, 72), (520, 264)]                   # ragged M / N edges
+    g = torch.Generator().manual_seed(tokens + layers)
+    A, Bm, O, want = [], [], [], []
+    for (m, n) in shapes:
+        dy = torch.randn(tokens, m, generator=g).to(torch.bfloat16)     # [K, M]
+        x = torch.randn(tokens, n, generator=g).to(torch.bfloat16)      # [K, N]
+        want.append(dy.float().t() @ x.float())
+        A.append((dy if mn else dy.t().contiguous()).to(DEV))
+        Bm.append((x if mn else x.t().contiguous()).to(DEV))
+        O.append(torch.full((m, n), float("nan"), device=DEV))
+    n = len(shapes)
+    arr = lambda ts: (ctypes.c_void_p * n)(*[t.data_ptr() for t in ts])
+    ints = lambda vs: (ctypes.c_int * n)(*vs)
+    pkg._lib.check(lib.b200_test_tc_gemm_grouped(arr(A), arr(Bm), arr(O), ints([s[0] for s in shapes]), ints([s[1] for s in shapes]),
+                                                  ints([tokens] * n), n, mn, pkg._lib.stream_ptr()), "tc_gemm_grouped")
+    torch.cuda.synchronize()
+    for o, w in zip(O, want):
+        err = ((o.cpu() - w).abs().max() / w.abs().max()).item()
+        assert err <= 1e-3, err
