@@ -78,6 +78,12 @@ SIGNATURES = {
     "b200_adamw_chunk": (ctypes.c_long, []),
     "b200_adamw_step": (c_int, [c_void_p, c_void_p, c_int, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float,
                                 c_int, c_void_p]),
+    "b200_adamw_step_capturable": (c_int, [c_void_p, c_void_p, c_int, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float,
+                                           ctypes.c_float, c_int, c_void_p, c_void_p]),
+    "b200_unetr_packed_bytes": (c_size_t, [c_void_p]),
+    "b200_unetr_set_packed_weights": (None, [c_void_p, c_void_p]),
+    "b200_unetr_packed_cast_offset": (c_int64, [c_void_p, c_int]),
+    "b200_unetr_pack_convs": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "b200_unetr_set_grad_events": (None, [c_void_p, ctypes.POINTER(c_void_p), c_int]),
     "b200_trace_begin": (None, [c_void_p, c_int]),
     "b200_trace_count": (c_int, []),
@@ -122,16 +128,25 @@ def check(rc: int, what: str):
 
 
 def require_device(tensor):
-    """All entry points take CUDA tensors on an sm_100 device."""
+    """All entry points take CUDA tensors on an sm_100 device.  One device per process (the multi-GPU design is one process per
+    GPU, parallel.py): the library caches per-device launch attributes and the SM count for the first device it sees, and every
+    call launches on the current stream of the current device, so a tensor on another device is refused rather than silently
+    launched into the wrong context."""
     import torch
 
     if not tensor.is_cuda:
         raise RuntimeError("b200 UNETR kernels need CUDA tensors on a B200 (sm_100a); there is no CPU path")
     dev = tensor.device.index if tensor.device.index is not None else torch.cuda.current_device()
     if dev not in _device_ok:
+        if _device_ok:
+            raise RuntimeError(f"libunetr_b200 is bound to cuda:{next(iter(_device_ok))} in this process; got a tensor on cuda:{dev} "
+                               "(run one process per GPU: torchrun / parallel.init_from_env)")
         with torch.cuda.device(dev):
             check(load().b200_device_check(), "b200_device_check")
         _device_ok.add(dev)
+    if dev != torch.cuda.current_device():
+        raise RuntimeError(f"tensor on cuda:{dev} but the current device is cuda:{torch.cuda.current_device()}: call "
+                           "torch.cuda.set_device first (kernels launch on the current device's stream)")
     return dev
 
 

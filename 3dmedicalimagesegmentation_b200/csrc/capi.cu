@@ -51,6 +51,7 @@ void prof_begin(const char* tag, cudaStream_t st) {
 }
 void prof_end(cudaStream_t st) { cudaEventRecord(g_prof.back().b, st); }
 
+static constexpr int P_COUNT_PUBLIC = 164;   // parameters in the C-ABI table (enum ParamIdx in exec.cuh; _lib.PARAM_COUNT)
 struct Handle {
   UnetrConfig cfg;
   ExecIface* ex;
@@ -120,17 +121,38 @@ void b200_unetr_set_grad_events(void* handle, void* const* events, int n) {
   h->ex->set_grad_events(ev, n);
 }
 
+size_t b200_unetr_packed_bytes(void* handle) { return ((Handle*)handle)->ex->packed_bytes(); }
+void b200_unetr_set_packed_weights(void* handle, void* buf) { ((Handle*)handle)->ex->set_packed((char*)buf); }
+int64_t b200_unetr_packed_cast_offset(void* handle, int param_index) {
+  Handle* h = (Handle*)handle;
+  if (!h || param_index < 0 || param_index >= P_COUNT_PUBLIC) return -1;
+  return h->ex->packed_cast_offset(param_index);
+}
+int b200_unetr_pack_convs(void* handle, const float* const* params, void* packed, void* stream) {
+  Handle* h = (Handle*)handle;
+  B200_CHECK(h && params, "b200_unetr_pack_convs: null argument");
+  return h->ex->pack_convs(params, (char*)packed, (cudaStream_t)stream);
+}
+
 // ---------------------------------------------------------------- fused AdamW
-/* tensors: device array of n_tensors {p, g, m, v, n}; chunks: device array of n_chunks {tensor, pad, start} covering every tensor in
+/* tensors: device array of n_tensors {p, g, m, v, n, s0} (six 8-byte fields, adamw.cuh); chunks: device array of n_chunks {tensor, pad, start} covering every tensor in
  * pieces of b200_adamw_chunk() elements; step >= 1 is the 1-based update count (bias correction). */
 long b200_adamw_chunk(void) { return kAdamChunk; }
 int b200_adamw_step(const void* tensors, const void* chunks, int n_chunks, float lr, float beta1, float beta2, float eps, float weight_decay,
                     int step, void* stream) {
-  B200_CHECK(tensors && chunks && n_chunks > 0 && step >= 1, "b200_adamw_step: bad arguments");
+  return b200_adamw_step_capturable(tensors, chunks, n_chunks, lr, beta1, beta2, eps, weight_decay, step, nullptr, stream);
+}
+/* dev_step != NULL: the update count is the device int *dev_step, advanced by one before the update (host `step` is ignored): the
+ * launch sequence is then identical every step and can be replayed from a CUDA graph. */
+int b200_adamw_step_capturable(const void* tensors, const void* chunks, int n_chunks, float lr, float beta1, float beta2, float eps,
+                               float weight_decay, int step, int* dev_step, void* stream) {
+  B200_CHECK(tensors && chunks && n_chunks > 0 && (step >= 1 || dev_step), "b200_adamw_step: bad arguments");
   AdamHyper h;
   h.lr = lr; h.beta1 = beta1; h.beta2 = beta2; h.eps = eps; h.weight_decay = weight_decay;
   h.bc1 = (float)(1.0 - pow((double)beta1, (double)step));
   h.bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
+  h.dev_step = dev_step;
+  if (dev_step) { adam_step_inc_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(dev_step); B200_LAUNCH_CHECK(); }
   adamw_kernel<<<n_chunks, 256, 0, (cudaStream_t)stream>>>((const AdamTensor*)tensors, (const AdamChunk*)chunks, h);
   B200_LAUNCH_CHECK();
   return 0;

@@ -194,15 +194,7 @@ struct Exec {
     }
     w.stat_pool = b.take<double>((size_t)kStatSlots * 4 * B * 8 * fs);   // slots of two (sum, sumsq) accumulators
     w.stat_acc = w.stat_pool; w.stat_next = 0;
-    if (kTC) {
-      for (int i = 0; i < 12; ++i) {
-        w.wqkv[i] = b.take<bf16>((size_t)3 * H * H); w.wproj[i] = b.take<bf16>((size_t)H * H);
-        w.wfc1[i] = b.take<bf16>((size_t)F * H); w.wfc2[i] = b.take<bf16>((size_t)H * F);
-      }
-      for (int i = 0; i < 10; ++i) { w.wT[i] = b.take<bf16>(convT_elems(i)); w.wTt[i] = b.take<bf16>(convT_elems(i)); }
-      w.wpatch = b.take<bf16>((size_t)H * 4096 * c.Cin); w.apatch = b.take<bf16>((size_t)M * 4096 * c.Cin);
-      for (int i = 0; i < 15; ++i) { int p, ci, co, ks; conv_desc(i, p, ci, co, ks); size_t n = (size_t)ci * co * ks * ks * ks; w.wcf[i] = b.take<bf16>(n); w.wcd[i] = b.take<bf16>(n); }
-    }
+    if (kTC) w.apatch = b.take<bf16>((size_t)M * 4096 * c.Cin);
     if (with_backward) {
       w.dx = b.take<float>(MH); w.dx2 = b.take<float>(MH);
       for (int i = 0; i < 3; ++i) w.dhs[i] = b.take<float>(MH);
@@ -220,6 +212,41 @@ struct Exec {
       w.bwd_acc = w.bwd_pool; w.bwd_next = 0;
     }
     w.bytes = (b.off + 255) & ~(size_t)255;
+  }
+
+  // bf16 mode: the packed bf16 copies of the GEMM / conv weights live in ONE caller-owned buffer that outlives the workspaces (it does
+  // not depend on the batch size): the forward refreshes it (pack_weights) unless the caller says it is current
+  // (FLAG_WEIGHTS_PACKED) -- FusedAdamW writes the copies itself while it updates the fp32 masters (adamw.cuh), so a training
+  // step has no cast / re-layout launch at all.  Returns the byte size; base == nullptr only measures.
+  char* packed_base = nullptr;
+  size_t layout_packed(char* base) {
+    Bump b{base, 0};
+    if (kTC) {
+      for (int i = 0; i < 12; ++i) {
+        w.wqkv[i] = b.take<bf16>((size_t)3 * H * H); w.wproj[i] = b.take<bf16>((size_t)H * H);
+        w.wfc1[i] = b.take<bf16>((size_t)F * H); w.wfc2[i] = b.take<bf16>((size_t)H * F);
+      }
+      for (int i = 0; i < 10; ++i) { w.wT[i] = b.take<bf16>(convT_elems(i)); w.wTt[i] = b.take<bf16>(convT_elems(i)); }
+      w.wpatch = b.take<bf16>((size_t)H * 4096 * c.Cin);
+      for (int i = 0; i < 15; ++i) { int p, ci, co, ks; conv_desc(i, p, ci, co, ks); size_t n = (size_t)ci * co * ks * ks * ks; w.wcf[i] = b.take<bf16>(n); w.wcd[i] = b.take<bf16>(n); }
+    }
+    return (b.off + 255) & ~(size_t)255;
+  }
+  // Byte offset of the PLAIN bf16 cast of parameter `pidx` in the packed buffer, or -1 when the parameter has none (biases, norms,
+  // position embedding, and the conv weights, which only exist re-laid-out).  These are the copies FusedAdamW writes itself.
+  long long packed_cast_offset(int pidx) {
+    if (!kTC) return -1;
+    char* const fake = reinterpret_cast<char*>(uintptr_t(1) << 20);      // offsets only: nothing is dereferenced; forward()/backward() re-bind
+    layout_packed(fake);
+    auto off = [fake](const void* q) { return (long long)(reinterpret_cast<const char*>(q) - fake); };
+    if (pidx == P_PATCH_W) return off(w.wpatch);
+    if (pidx >= P_BLK0 && pidx < P_NORM_W) {
+      const int i = (pidx - P_BLK0) / B_COUNT, k = (pidx - P_BLK0) % B_COUNT;
+      const bf16* q = k == B_QKV_W ? w.wqkv[i] : k == B_PROJ_W ? w.wproj[i] : k == B_FC1_W ? w.wfc1[i] : k == B_FC2_W ? w.wfc2[i] : nullptr;
+      return q ? off(q) : -1;
+    }
+    for (int i = 0; i < 10; ++i) { int pp, ci, co; convT_desc(i, pp, ci, co); if (pp == pidx) return off(w.wT[i]); }
+    return -1;
   }
 
   // ------------------------------------------------------------ engine dispatch (CUDA-core engine; see exec.cu for tcgen05)
@@ -276,9 +303,11 @@ struct Exec {
     }
   }
   // bf16 mode: refresh the packed weight copies (one launch for all ViT + transposed-conv weights)
-  int pack_weights(const float* const* P, cudaStream_t st) {
+  // casts = false: only the re-laid-out conv / transposed-conv copies (the plain casts are kept current by FusedAdamW)
+  int pack_weights(const float* const* P, cudaStream_t st, bool casts = true) {
     if constexpr (kTC) {
       B200_PROF("pack_weights", st);
+      if (casts) {
       CastJobs jobs; int n = 0;
       auto add = [&](const float* src, bf16* dst, size_t cnt) { jobs.j[n].src = src; jobs.j[n].dst = dst; jobs.j[n].n = (long)cnt; ++n; };
       for (int i = 0; i < 12; ++i) {
@@ -291,6 +320,7 @@ struct Exec {
       jobs.count = n;
       multi_cast_kernel<<<dim3(64, n), 256, 0, st>>>(jobs);
       B200_LAUNCH_CHECK();
+      }
       PackJobs pj; int m = 0;
       for (int i = 0; i < 10; ++i) {
         int p, ci, co; convT_desc(i, p, ci, co);
@@ -540,6 +570,7 @@ struct Exec {
   // ------------------------------------------------------------ forward
   int forward(const float* const* P, const float* x_in, char* ws, float* enc4_out, float* logits_out, int flags, cudaStream_t st) {
     layout(ws, false);
+    if (kTC) { B200_CHECK(packed_base, "bf16 mode needs the packed-weight buffer (b200_unetr_set_packed_weights)"); layout_packed(packed_base); }
     no_backward = (flags & FLAG_NO_BACKWARD) != 0;
     B200_CUDA(cudaMemsetAsync(w.stat_pool, 0, sizeof(double) * kStatSlots * 4 * c.B * 8 * c.fs, st));
     B200_PROFC_BEGIN("F1 pack+patch", st);
@@ -788,6 +819,7 @@ struct Exec {
   int backward(const float* const* P, float* const* G, const float* x_in, char* ws, const float* d_enc4, const float* d_logits,
                int flags, cudaStream_t st) {
     layout(ws, true);
+    if (kTC) { B200_CHECK(packed_base, "bf16 mode needs the packed-weight buffer (b200_unetr_set_packed_weights)"); layout_packed(packed_base); }
     cur_params = P;
     int B = c.B, fs = c.fs;
     bool dec = (flags & FLAG_HAS_DLOGITS) && d_logits;

@@ -19,6 +19,11 @@ struct ExecIface {
   // optional: events recorded inside backward() when a group of parameter gradients is final (gradient all-reduce overlap):
   //   [0] convolutional encoders/decoders + head, [1] vit.norm + blocks 8..11, [2] blocks 4..7, [3] blocks 0..3 + patch embedding
   virtual void set_grad_events(cudaEvent_t* ev, int n) = 0;
+  // bf16 mode: caller-owned buffer of packed_bytes() bytes holding the packed bf16 weight copies (see Exec::layout_packed)
+  virtual size_t packed_bytes() = 0;
+  virtual void set_packed(char* buf) = 0;
+  virtual long long packed_cast_offset(int pidx) = 0;
+  virtual int pack_convs(const float* const* P, char* packed, cudaStream_t st) = 0;
 };
 ExecIface* make_exec_f32(const UnetrConfig& c);
 ExecIface* make_exec_bf16(const UnetrConfig& c);

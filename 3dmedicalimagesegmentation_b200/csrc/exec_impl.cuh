@@ -16,6 +16,15 @@ struct ExecImpl : ExecIface {
     return e.backward(P, G, x, ws, d_enc4, d_logits, flags, st);
   }
   const void* peek(const char* name, size_t* bytes) override { return e.peek(name, bytes); }
+  size_t packed_bytes() override { return e.layout_packed(nullptr); }
+  void set_packed(char* buf) override { e.packed_base = buf; }
+  long long packed_cast_offset(int pidx) override { return e.packed_cast_offset(pidx); }
+  int pack_convs(const float* const* P, char* packed, cudaStream_t st) override {
+    if (!Exec<T>::kTC) return 0;
+    if (!packed) { set_error("b200_unetr_pack_convs: no packed-weight buffer"); return 1; }
+    e.layout_packed(packed);
+    return e.pack_weights(P, st, false);
+  }
   void set_grad_events(cudaEvent_t* ev, int n) override { e.n_grad_ev = n < 4 ? 0 : 4; for (int i = 0; i < e.n_grad_ev; ++i) e.grad_ev[i] = ev[i]; }
 };
 }  // namespace b200

@@ -15,21 +15,41 @@ __all__ = ["FusedAdamW"]
 
 
 class FusedAdamW(torch.optim.Optimizer):
-    def __init__(self, params, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 1e-2):
+    def __init__(self, params, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 1e-2, mirror=None,
+                 capturable: bool = False):
+        """`mirror`: a b200 UNETR module whose parameters this optimizer updates.  In bf16 mode the same launch then also writes the
+        module's packed bf16 weight copies (the operands of the tcgen05 engine), so the next forward skips its cast / re-layout
+        launches.  Without it nothing changes: the forward re-packs whenever a parameter's version counter moved."""
         if lr < 0 or eps < 0 or not 0 <= betas[0] < 1 or not 0 <= betas[1] < 1 or weight_decay < 0:
             raise ValueError("invalid AdamW hyper-parameters")
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
         self._tables = {}          # group index -> (key, tensors_dev, chunks_dev, n_chunks)
+        self._mirror = mirror
+        # capturable: the update count is read from device memory (advanced by a one-thread kernel before each update), so the launch
+        # sequence of a step does not change from step to step and can be replayed from a CUDA graph (graph.GraphedTrainStep).  The
+        # host-side `state[p]["step"]` is advanced by every Python-driven step; replays advance it through `advance_host_steps`.
+        self.capturable = bool(capturable)
+        self._dev_steps = {}       # (group, cohort) -> int32 device counter
+        self._last_cohorts = []
+
+    def _mirror_rows(self, device):
+        """id(parameter) -> device address of its plain bf16 mirror (parameters that have one), or {}."""
+        m = self._mirror
+        if m is None or getattr(m, "compute_mode", None) != "bf16" or not getattr(self, "_mirror_was_ok", False):
+            return {}
+        rows = m.packed_mirrors(device)
+        return {id(p): r for p, r in zip(m._ordered_params(), rows) if r}
 
     def _build(self, gi, plist):
         chunk = _lib.load().b200_adamw_chunk()
         rows, chunks = [], []
+        mirrors = self._mirror_rows(plist[0].device)
         for ti, p in enumerate(plist):
             st = self.state[p]
-            rows.append((p.data_ptr(), p.grad.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(), p.numel()))
+            rows.append((p.data_ptr(), p.grad.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(), p.numel(), mirrors.get(id(p), 0)))
             for s in range(0, p.numel(), chunk):
                 chunks.append((ti, s))
-        tens = np.array(rows, dtype=np.int64)                                   # {p, g, m, v, n}: five 8-byte fields
+        tens = np.array(rows, dtype=np.int64)                                   # {p, g, m, v, n, s0}: six 8-byte fields
         ch = np.zeros(len(chunks), dtype=[("t", "<i4"), ("pad", "<i4"), ("s", "<i8")])
         ch["t"] = [c[0] for c in chunks]; ch["s"] = [c[1] for c in chunks]
         dev = plist[0].device
@@ -44,6 +64,18 @@ class FusedAdamW(torch.optim.Optimizer):
             with torch.enable_grad():
                 loss = closure()
         lib = _lib.load()
+        self._last_cohorts = []
+        # the packed mirrors stay current through this step only if they were current before it (every parameter unchanged since
+        # the forward that packed or verified them)
+        m = self._mirror
+        mirror_dev, mirror_ok = None, False
+        if m is not None and getattr(m, "compute_mode", None) == "bf16":
+            mp = m._ordered_params()
+            mirror_dev = mp[0].device
+            mirror_ok = m._packed_key.get(mirror_dev) == m._version_key(mp)
+            if mirror_ok != getattr(self, "_mirror_was_ok", None):
+                self._tables = {}          # tables carry (or omit) the mirror pointers
+                self._mirror_was_ok = mirror_ok
         for gi, group in enumerate(self.param_groups):
             plist = [p for p in group["params"] if p.grad is not None]
             if not plist:
@@ -66,11 +98,29 @@ class FusedAdamW(torch.optim.Optimizer):
                     ent = (key,) + self._build(gi, sub)
                     self._tables[(gi, si)] = ent
                 b1, b2 = group["betas"]
-                _lib.check(lib.b200_adamw_step(_lib.ptr(ent[1]), _lib.ptr(ent[2]), ent[3], float(group["lr"]), float(b1), float(b2),
-                                               float(group["eps"]), float(group["weight_decay"]), s0 + 1, _lib.stream_ptr()), "b200_adamw_step")
+                dev_step = None
+                if self.capturable:
+                    dev_step = self._dev_steps.get((gi, si))
+                    if dev_step is None or dev_step[1] != key:
+                        dev_step = (torch.full((1,), s0, dtype=torch.int32, device=sub[0].device), key)
+                        self._dev_steps[(gi, si)] = dev_step
+                    self._last_cohorts.append(sub)
+                _lib.check(lib.b200_adamw_step_capturable(_lib.ptr(ent[1]), _lib.ptr(ent[2]), ent[3], float(group["lr"]), float(b1), float(b2),
+                                                          float(group["eps"]), float(group["weight_decay"]), s0 + 1,
+                                                          _lib.ptr(dev_step[0]) if dev_step else None, _lib.stream_ptr()), "b200_adamw_step")
                 for p in sub:
                     self.state[p]["step"] = s0 + 1
                 # the kernel wrote through raw pointers: bump the autograd version counters so that everything keyed on them (the
                 # UNETR inference cache of packed bf16 weights, saved-tensor checks) sees the in-place update
                 torch.autograd.graph.increment_version(sub)
+        if mirror_ok:
+            m.repack_convs(mirror_dev)       # the re-laid-out conv copies (one launch); the plain casts were written by the update itself
+            m._packed_key[mirror_dev] = m._version_key(m._ordered_params())
         return loss
+
+    def advance_host_steps(self, n: int = 1):
+        """After `n` replays of a captured step: bring the host-side step counts of the parameters the captured step updated in line
+        with the device counters (which the replays advanced)."""
+        for sub in self._last_cohorts:
+            for p in sub:
+                self.state[p]["step"] += n

@@ -101,6 +101,13 @@ class GradientAllReduce:
         if ready is not None and self.side is not None:
             flat, groups = ready
             self.module._grad_ready = None
+            # the events cover ranges of the autograd node's flat buffer: the averages only reach the parameters if every p.grad
+            # IS a view of it, in order (true when AccumulateGrad stole the views; false under gradient accumulation,
+            # zero_grad(set_to_none=False) or a cloned gradient) -- otherwise take the generic path below
+            view = self._flat_view([p.grad for p in self.params if p.grad is not None])
+            if view is None or view.data_ptr() != flat.data_ptr() or view.numel() != flat.numel():
+                ready = None
+        if ready is not None and self.side is not None:
             works = []
             with torch.cuda.stream(self.side):
                 for ev, lo, hi in groups:

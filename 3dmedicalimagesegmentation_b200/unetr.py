@@ -97,26 +97,23 @@ class _UnetrFunction(torch.autograd.Function):
         _lib.require_device(x)
         x = x.contiguous().float()
         batch = x.shape[0]
-        handle = module._handle(batch)
-        packed = 0
+        handle = module._handle(batch, x.device)
+        # the packed bf16 weight copies live in one persistent buffer per device (bf16 mode); they are current when every parameter
+        # still has the storage and version counter they were packed from (FusedAdamW keeps them current itself)
+        vkey = module._version_key(params)
+        packed = _lib.FLAG_WEIGHTS_PACKED if module._packed_key.get(x.device) == vkey else 0
         if needs_grad:
             ws = torch.empty(lib.b200_unetr_workspace_bytes(handle, 1), dtype=torch.uint8, device=x.device)
         else:
-            # inference (sliding window: hundreds of calls on fixed weights): keep one workspace per batch size and skip the
-            # fp32 -> bf16 weight re-pack while every parameter still has the same storage and version counter
+            # inference (sliding window: hundreds of calls on fixed weights): keep one workspace per batch size
             key = (batch, module.compute_mode, x.device)
-            vkey = tuple((p.data_ptr(), p._version) for p in params)
-            ent = module._infer_ws.get(key)
-            if ent is None:
-                ent = [torch.empty(lib.b200_unetr_workspace_bytes(handle, 0), dtype=torch.uint8, device=x.device), None]
+            ws = module._infer_ws.get(key)
+            if ws is None:
+                ws = torch.empty(lib.b200_unetr_workspace_bytes(handle, 0), dtype=torch.uint8, device=x.device)
                 if len(module._infer_ws) >= 3:     # a few batch sizes at most (sliding window: full chunks + one ragged tail)
                     module._infer_ws.clear()
                     module._graphs.clear()         # captured graphs point into the workspaces just dropped
-                module._infer_ws[key] = ent
-            ws = ent[0]
-            if ent[1] == vkey:
-                packed = _lib.FLAG_WEIGHTS_PACKED
-            ent[1] = vkey
+                module._infer_ws[key] = ws
         fs, s = module.feature_size, module.img_size
         enc4 = torch.empty((batch, 8 * fs, s[0] // 8, s[1] // 8, s[2] // 8), dtype=torch.float32, device=x.device)
         logits = torch.empty((batch, module.out_channels, *s), dtype=torch.float32, device=x.device)
@@ -124,6 +121,7 @@ class _UnetrFunction(torch.autograd.Function):
         flags = (0 if freeze_encoder else _lib.FLAG_NEED_ENCODER_GRAD) | packed | (0 if needs_grad else _lib.FLAG_NO_BACKWARD)
         _lib.check(lib.b200_unetr_forward(handle, table, _lib.ptr(x), _lib.ptr(ws), _lib.ptr(enc4), _lib.ptr(logits),
                                           flags, _lib.stream_ptr()), "b200_unetr_forward")
+        module._packed_key[x.device] = vkey
         ctx.module, ctx.freeze, ctx.handle = module, bool(freeze_encoder), handle
         ctx.save_for_backward(x, ws, *params)
         ctx.set_materialize_grads(False)
@@ -148,7 +146,15 @@ class _UnetrFunction(torch.autograd.Function):
         reach = module._grad_reach(has_dl, enc, has_dl or has_de)
         wanted = [reach[i] and params[i].requires_grad for i in range(n)]
         total = sum(p.numel() for p, wnt in zip(params, wanted) if wnt)
-        flat = torch.empty(total, dtype=torch.float32, device=x.device)
+        # All parameter gradients are views of ONE flat buffer (a single all-reduce / one AdamW table).  The buffer is kept across
+        # steps -- stable gradient addresses mean the optimizer's pointer tables and a captured CUDA graph stay valid -- unless a
+        # parameter still holds a gradient (accumulation: autograd adds the new views to it, so they must not share storage).
+        fkey = (x.device, tuple(wanted))
+        flat = module._flat_grads.get(fkey)
+        if flat is None or flat.numel() != total or any(w and p.grad is not None for p, w in zip(params, wanted)):
+            flat = torch.empty(total, dtype=torch.float32, device=x.device)
+            if all(p.grad is None for p, w in zip(params, wanted) if w):
+                module._flat_grads = {fkey: flat}
         grads, off = [], 0
         gtab = (ctypes.c_void_p * n)()
         for i, (p, wnt) in enumerate(zip(params, wanted)):
@@ -250,14 +256,44 @@ class UNETR(nn.Module):
         self.out.conv = _conv(fs, out_channels, 1, 1, bias=True)
         # "bf16" (throughput, default) or "fp32" (parity: logits within 1e-4 of the fp32 reference)
         self.compute_mode = os.environ.get("B200_UNETR_MODE", "bf16")
+        self.inference_graph = False       # see _graph_forward; switched on by sliding_window_inference for its loop
+        self.overlap_grad_reduce = False   # set by parallel.GradientAllReduce
+        self._init_runtime()
+
+    _RUNTIME = ("_handles", "_infer_ws", "_grad_events", "_graphs", "_grad_ready", "_ordered", "_packed", "_packed_key", "_flat_grads")
+
+    def _init_runtime(self):
+        """Per-process state that must never be copied: C handles, workspaces, CUDA graphs / events, the packed bf16 weights."""
         self._handles = {}
         self._infer_ws = {}
         self._grad_events = None
         self._graphs = {}
-        self.inference_graph = False       # see _graph_forward; switched on by sliding_window_inference for its loop
         self._grad_ready = None
-        self.overlap_grad_reduce = False   # set by parallel.GradientAllReduce
         self._ordered = None
+        self._packed = {}                  # device -> uint8 buffer of packed bf16 weight copies
+        self._packed_key = {}              # device -> parameter (storage, version) key the buffer was packed from
+        self._flat_grads = {}
+
+    def __getstate__(self):
+        # copy.deepcopy / pickle / torch.save(model): the raw C handles (freed in __del__), CUDA events and graphs belong to THIS
+        # object; the copy rebuilds its own lazily
+        state = dict(super().__getstate__()) if hasattr(super(), "__getstate__") else dict(self.__dict__)
+        for k in self._RUNTIME:
+            state.pop(k, None)
+        return state
+
+    def __setstate__(self, state):
+        super().__setstate__(state)
+        self._init_runtime()
+
+    def _apply(self, fn, *a, **k):
+        # .to() / .cuda() / .float(): parameters get new storage; cached tables, packed copies and graphs are rebuilt lazily
+        out = super()._apply(fn, *a, **k)
+        self._ordered = None
+        self._packed_key = {}
+        self._graphs = {}
+        self._flat_grads = {}
+        return out
 
     # ---- plumbing -------------------------------------------------------------------------------
     def set_mode(self, mode: str) -> "UNETR":
@@ -317,8 +353,39 @@ class UNETR(nn.Module):
             tab[i] = p.data_ptr()
         return tab
 
-    def _handle(self, batch: int):
-        key = (batch, self.compute_mode)
+    @staticmethod
+    def _version_key(params):
+        return tuple((p.data_ptr(), p._version) for p in params)
+
+    def _norm_device(self, device):
+        device = torch.device(device)
+        if device.type == "cuda" and device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        return device
+
+    def packed_mirrors(self, device):
+        """Per parameter of `_ordered_params()`: device address of its plain bf16 mirror in the packed-weight buffer, or 0 (C ABI:
+        b200_unetr_packed_cast_offset).  FusedAdamW writes these while it updates the parameter.  None in fp32 mode."""
+        if self.compute_mode != "bf16":
+            return None
+        lib = _lib.load()
+        device = self._norm_device(device)
+        h = self._handle(1, device)
+        base = self._packed[device].data_ptr()
+        offs = [lib.b200_unetr_packed_cast_offset(h, i) for i in range(_lib.PARAM_COUNT)]
+        return [base + o if o >= 0 else 0 for o in offs]
+
+    def repack_convs(self, device):
+        """Refresh the re-laid-out conv / transposed-conv copies of the packed-weight buffer from the fp32 parameters (one launch)."""
+        lib = _lib.load()
+        device = self._norm_device(device)
+        h = self._handle(1, device)
+        _lib.check(lib.b200_unetr_pack_convs(h, self._param_table(self._ordered_params()), _lib.ptr(self._packed[device]), _lib.stream_ptr()),
+                   "b200_unetr_pack_convs")
+
+    def _handle(self, batch: int, device=None):
+        device = self._norm_device(self._ordered_params()[0].device if device is None else device)
+        key = (batch, self.compute_mode, device)
         h = self._handles.get(key)
         if h is None:
             lib = _lib.load()
@@ -328,13 +395,20 @@ class UNETR(nn.Module):
             h = lib.b200_unetr_create(ctypes.byref(cfg))
             if not h:
                 raise RuntimeError("b200_unetr_create: " + _lib.last_error())
+            if self.compute_mode == "bf16":
+                buf = self._packed.get(device)
+                if buf is None:
+                    buf = torch.empty(lib.b200_unetr_packed_bytes(h), dtype=torch.uint8, device=device)
+                    self._packed[device] = buf
+                lib.b200_unetr_set_packed_weights(h, _lib.ptr(buf))
             self._handles[key] = h
         return h
 
     def __del__(self):
         try:
             lib = _lib.load()
-            for h in self._handles.values():
+            handles, self._handles = list(self._handles.values()), {}
+            for h in handles:
                 lib.b200_unetr_destroy(h)
         except Exception:
             pass
@@ -372,7 +446,7 @@ class UNETR(nn.Module):
                     graph = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(graph):
                         enc4, logits = _UnetrFunction.apply(self, static_x, False, False, *params)
-                ent = (vkey, graph, static_x, enc4, logits, self._infer_ws[key][0])   # keeps the captured workspace alive
+                ent = (vkey, graph, static_x, enc4, logits, self._infer_ws[key])   # keeps the captured workspace alive
                 self._graphs[key] = ent
             ent[2].copy_(x_in)
             ent[1].replay()

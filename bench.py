@@ -128,6 +128,7 @@ def main():
     ap.add_argument("--no-optimizer", action="store_true")
     ap.add_argument("--torch-adamw", action="store_true", help="use torch.optim.AdamW(fused=True) instead of the package's FusedAdamW")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="issue every step's launches from the host instead of replaying the captured CUDA graph")
     ap.add_argument("--breakdown", action="store_true", help="print the per-op CUDA-event breakdown to stderr")
     ap.add_argument("--no-sliding-window", action="store_true", help="skip the configs[4] whole-CT sliding-window measurement")
     ap.add_argument("--no-ranking", action="store_true", help="skip the configs[2] ranking pre-training step measurement")
@@ -161,7 +162,8 @@ def main():
     if args.torch_adamw:
         opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=1e-5, fused=True)
     else:
-        opt = pkg.FusedAdamW(model.parameters(), lr=1e-4, weight_decay=1e-5)     # one launch
+        # one launch; keeps the packed bf16 weights current; update count on the device (graph replay)
+        opt = pkg.FusedAdamW(model.parameters(), lr=1e-4, weight_decay=1e-5, mirror=model, capturable=True)
     ddp = par.GradientAllReduce(model, world) if world > 1 else None
     B = args.batch
     g = torch.Generator().manual_seed(100 + rank)
@@ -171,7 +173,7 @@ def main():
     dev_x = [t.to(dev) for t in host_x]
     dev_y = [t.to(dev) for t in host_y]
 
-    def step(x, y):
+    def eager_step(x, y):
         logits = model(x)
         loss = loss_fn(logits, y)
         loss.backward()
@@ -181,6 +183,23 @@ def main():
             opt.step()
         opt.zero_grad(set_to_none=True)
         return loss
+
+    gstep, graph_note = None, "off (--no-graph)"
+    if args.torch_adamw or args.no_optimizer:
+        graph_note = "off (needs the capturable FusedAdamW)"
+    elif not args.no_graph:
+        try:
+            # the whole step (forward, DiceCE, backward, gradient all-reduce, AdamW) captured once and replayed: graph.py
+            gstep = pkg.GraphedTrainStep(model, loss_fn, opt, dev_x[0], dev_y[0], reducer=ddp, warmup=2)
+            graph_note = "whole step replayed as one CUDA graph"
+        except Exception as exc:      # capture refused (driver / NCCL): same kernels, launched from the host
+            print(f"[bench] CUDA-graph capture of the step failed, running eager launches: {exc}", file=sys.stderr)
+            torch.cuda.synchronize()
+            opt.zero_grad(set_to_none=True)
+            graph_note = f"off (capture failed: {type(exc).__name__})"
+
+    def step(x, y):
+        return gstep(x, y) if gstep is not None else eager_step(x, y)
 
     def timed(fn, steps):
         par.barrier(world)
@@ -203,6 +222,8 @@ def main():
     l0 = lib.b200_launch_count()
     ms = timed(lambda i: step(dev_x[i % 4], dev_y[i % 4]), args.steps)
     launches = lib.b200_launch_count() - l0
+    if gstep is not None:
+        launches = gstep.launches_per_step * args.steps      # kernel nodes of the replayed graph (counted while it was captured)
     # end-to-end: every step's inputs come from pinned host memory and its loss is read back (a blocking .item()).  The copy of
     # batch i+1 is enqueued on a copy stream while step i computes (what a prefetching loader does; the reference's DataLoader
     # has pin_memory + 4 workers, seg:587) -- every copy and every read-back is inside the timed region.
@@ -231,7 +252,7 @@ def main():
 
     # per-op CUDA-event breakdown of one step -> roofline of the dominant kernel class
     lib.b200_prof_enable(1)
-    step(dev_x[0], dev_y[0])
+    eager_step(dev_x[0], dev_y[0])
     prof = pkg._lib.prof_report()
     lib.b200_prof_enable(0)
     pk, pk_kind = peaks()
@@ -292,7 +313,7 @@ def main():
     if args.breakdown and rank == 0:
         lib.b200_prof_enable(2)            # phase-level regions only (per-op events have a ~8 us floor each)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); step(dev_x[1], dev_y[1]); e1.record()
+        e0.record(); eager_step(dev_x[1], dev_y[1]); e1.record()
         phases = pkg._lib.prof_report()
         lib.b200_prof_enable(0)
         print(f"  phases of one step ({e0.elapsed_time(e1):.3f} ms incl. loss + AdamW): " +
@@ -324,10 +345,11 @@ def main():
     # slices along one axis, Bradley-Terry loss, backward through encoder4 + ViT blocks 0-9 + patch embedding, AdamW step
     rk = None
     if not args.no_ranking and S == 96:
+        gstep = None
         del model, opt, ddp
         torch.cuda.empty_cache()
         rmodel = pkg.UNETR(**MODEL_KW).to(dev).set_mode(args.mode)
-        ropt = pkg.FusedAdamW(rmodel.parameters(), lr=1e-4, weight_decay=1e-5)
+        ropt = pkg.FusedAdamW(rmodel.parameters(), lr=1e-4, weight_decay=1e-5, mirror=rmodel)
         rddp = par.GradientAllReduce(rmodel, world) if world > 1 else None
 
         class _Opt:                       # BTLoss(reference, similar, dissimilar, optimizer) steps the optimizer itself (rank:213-215)
@@ -369,7 +391,7 @@ def main():
                 "scaling": "weak", "vs_baseline": None, "dtype": args.mode, "data": "synthetic",
                 "config": {"workload": ("configs[1]" if S == 96 else "configs[3]") + f": UNETR(1->14,{S}^3,fs16,ViT-B) segmentation training step (fwd+DiceCE+bwd" +
                            ("" if args.no_optimizer else "+AdamW") + f"), batch {B}/GPU", "global_batch": B * world,
-                           "parallelism": f"dp{world}", "l2": "4 rotating input batches; activations per step (~1 GB) exceed the 126 MB L2"},
+                           "parallelism": f"dp{world}", "launch": graph_note, "l2": "4 rotating input batches; activations per step (~1 GB) exceed the 126 MB L2"},
                 "tflops_algorithmic": samples * flop_per_sample / (ms * 1e-3) / 1e12,
                 "e2e": {"value": samples / (ms_e2e * 1e-3), "unit": "samples/s",
                         "h2d_bytes_per_step": host_x[0].numel() * 4 + host_y[0].numel() * 4, "d2h_bytes_per_step": 4},

@@ -27,7 +27,7 @@ extern "C" {
 #define B200_HAS_DLOGITS 2
 #define B200_HAS_DENC4 4
 #define B200_NO_BACKWARD 16 /* forward only: no backward call follows (inference); buffers only the backward reads may be left unwritten */
-#define B200_WEIGHTS_PACKED 64 /* forward only: the bf16 weight copies in this workspace are current (same workspace, unchanged parameters) */
+#define B200_WEIGHTS_PACKED 64 /* forward only: the bf16 weight copies in the packed buffer are current (b200_unetr_set_packed_weights) */
 
 typedef struct {
   int32_t batch, in_channels, out_channels; /* unetr.py:29-30 */
@@ -128,13 +128,29 @@ unsigned long long b200_launch_count(void);
 void b200_prof_enable(int on);
 int b200_prof_report(char* buf, int cap);
 
+/* ---- packed bf16 weight copies (bf16 mode).  The tcgen05 engine reads bf16 copies of the GEMM / convolution weights in its own
+ *      layouts from ONE caller-owned device buffer of b200_unetr_packed_bytes() bytes (independent of the batch size; handles of the
+ *      same network may share it).  b200_unetr_forward refreshes every copy from the fp32 parameters unless B200_WEIGHTS_PACKED says
+ *      they are current.  An optimizer can keep them current instead: b200_adamw_step writes the PLAIN casts (byte offset from
+ *      b200_unetr_packed_cast_offset, -1 = the parameter has none) while it updates the parameters, and b200_unetr_pack_convs
+ *      refreshes the re-laid-out convolution / transposed-convolution copies (one launch, 7 M parameters at configs[1]). */
+size_t b200_unetr_packed_bytes(void* handle);
+void b200_unetr_set_packed_weights(void* handle, void* buffer);
+int64_t b200_unetr_packed_cast_offset(void* handle, int param_index);
+int b200_unetr_pack_convs(void* handle, const float* const* params, void* packed, void* stream);
+
 /* ---- fused multi-tensor AdamW (stands behind torch.optim.AdamW: unetr_segmentation_3d.py:522,225-226;
  *      unetr_ranking_pretraining_3d.py:466,214-215).  tensors: device array of {float* p; const float* g; float* m; float* v;
- *      int64 n}; chunks: device array of {int32 tensor; int32 pad; int64 start}, each covering b200_adamw_chunk() elements.
+ *      int64 n; bf16* s0} -- s0 (nullable) is the plain bf16 mirror of the parameter in the packed-weight buffer
+ *      (b200_unetr_packed_cast_offset), which the same launch keeps current; chunks: device array of {int32 tensor; int32 pad; int64 start}, each covering b200_adamw_chunk() elements.
  *      Parameters without a gradient are left out of the table (their state does not move).  step is 1-based. */
 long b200_adamw_chunk(void);
 int b200_adamw_step(const void* tensors, const void* chunks, int n_chunks, float lr, float beta1, float beta2, float eps,
                     float weight_decay, int step, void* stream);
+/* dev_step != NULL: the 1-based update count is the device int *dev_step, advanced by one on the stream before the update (the
+ * host `step` is ignored) -- every step is then the same launch sequence and can be replayed from a CUDA graph. */
+int b200_adamw_step_capturable(const void* tensors, const void* chunks, int n_chunks, float lr, float beta1, float beta2, float eps,
+                               float weight_decay, int step, int* dev_step, void* stream);
 
 /* Optional gradient-ready events for data-parallel overlap: 4 cudaEvent_t handles recorded inside b200_unetr_backward when a
  * group of parameter gradients is final -- [0] conv encoders/decoders + head, [1] vit.norm + blocks 8..11, [2] blocks 4..7,
