@@ -159,6 +159,24 @@ int b200_adamw_step_capturable(const void* tensors, const void* chunks, int n_ch
 }
 
 // ---------------------------------------------------------------- DiceCE
+// staged kernels (loss.cuh): whole tiles of kDiceTile voxels, 16-byte aligned planes; B200_DICE_DIRECT=1 keeps the register kernels
+static bool dice_staged_ok(const float* logits, const float* labels, const float* dlogits, int C, int64_t V) {
+  static const bool off = getenv("B200_DICE_DIRECT") != nullptr;
+  return !off && C <= 16 && V % kDiceTile == 0 && (((uintptr_t)logits | (uintptr_t)labels | (uintptr_t)dlogits) & 15) == 0;
+}
+static dim3 dice_staged_grid(int B, int64_t V) {
+  const long tiles = V / kDiceTile;
+  return dim3((unsigned)std::max(1L, std::min(tiles, (long)(2 * tc::num_sms() / B))), B);
+}
+static int dice_staged_attr() {
+  static bool done = false;
+  if (!done) {
+    B200_CUDA(cudaFuncSetAttribute(dicece_staged_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dice_staged_smem(16)));
+    B200_CUDA(cudaFuncSetAttribute(dicece_staged_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dice_staged_smem(16)));
+    done = true;
+  }
+  return 0;
+}
 // scratch: double acc[B*C*3+1] | float coef[B*C*2]
 size_t b200_dicece_scratch_bytes(int B, int C) { return sizeof(double) * ((size_t)B * C * 3 + 2) + sizeof(float) * (size_t)B * C * 2; }
 int b200_dicece_forward(const float* logits, const float* labels, int B, int C, int64_t V, void* scratch, float* out3, void* stream) {
@@ -171,7 +189,11 @@ int b200_dicece_forward(const float* logits, const float* labels, int B, int C, 
   // measured: the 4-voxel kernels need 184-254 registers and are ~15 % slower than the scalar ones at 14 classes; opt-in only
   const bool v4 = getenv("B200_DICE_V4") && V % 4 == 0 && C <= 16 && (((uintptr_t)logits | (uintptr_t)labels) & 15) == 0;
   dim3 g4((unsigned)max(1L, min(148L * 4 / B + 1, (long)((V / 4 + 255) / 256))), B);
-  if (v4) dicece_fwd4_kernel<16><<<g4, 256, 0, st>>>(logits, labels, C, V, acc, B * C);
+  if (dice_staged_ok(logits, labels, nullptr, C, V)) {
+    B200_TRY(dice_staged_attr());
+    dicece_staged_kernel<16, false><<<dice_staged_grid(B, V), 256, dice_staged_smem(C), st>>>(logits, labels, C, V, acc, B * C, nullptr, nullptr, B, nullptr);
+  }
+  else if (v4) dicece_fwd4_kernel<16><<<g4, 256, 0, st>>>(logits, labels, C, V, acc, B * C);
   else if (C <= 16) dicece_fwd_kernel<16><<<g, 256, 0, st>>>(logits, labels, C, V, acc, B * C);
   else dicece_fwd_kernel<32><<<g, 256, 0, st>>>(logits, labels, C, V, acc, B * C);
   B200_LAUNCH_CHECK();
@@ -187,7 +209,11 @@ int b200_dicece_backward(const float* logits, const float* labels, int B, int C,
   dim3 g((unsigned)max(1L, min(148L * 8 / B + 1, (long)((V + 255) / 256))), B);
   const bool v4 = getenv("B200_DICE_V4") && V % 4 == 0 && C <= 16 && (((uintptr_t)logits | (uintptr_t)labels | (uintptr_t)dlogits) & 15) == 0;
   dim3 g4((unsigned)max(1L, min(148L * 4 / B + 1, (long)((V / 4 + 255) / 256))), B);
-  if (v4) dicece_bwd4_kernel<16><<<g4, 256, 0, st>>>(logits, labels, coef, upstream, B, C, V, dlogits);
+  if (dice_staged_ok(logits, labels, dlogits, C, V)) {
+    B200_TRY(dice_staged_attr());
+    dicece_staged_kernel<16, true><<<dice_staged_grid(B, V), 256, dice_staged_smem(C), st>>>(logits, labels, C, V, nullptr, B * C, coef, upstream, B, dlogits);
+  }
+  else if (v4) dicece_bwd4_kernel<16><<<g4, 256, 0, st>>>(logits, labels, coef, upstream, B, C, V, dlogits);
   else if (C <= 16) dicece_bwd_kernel<16><<<g, 256, 0, st>>>(logits, labels, coef, upstream, B, C, V, dlogits);
   else dicece_bwd_kernel<32><<<g, 256, 0, st>>>(logits, labels, coef, upstream, B, C, V, dlogits);
   B200_LAUNCH_CHECK();

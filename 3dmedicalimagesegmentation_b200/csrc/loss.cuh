@@ -4,6 +4,7 @@
 // for the forward, one read + one write for the backward.
 #pragma once
 #include "common.cuh"
+#include "tc_gemm.cuh"
 
 namespace b200 {
 
@@ -224,6 +225,144 @@ __global__ void __launch_bounds__(256) dicece_bwd4_kernel(const float* __restric
 #pragma unroll
     for (int c = 0; c < CMAX; ++c)
       if (c < C) *reinterpret_cast<float4*>(dl + (long)c * V + 4 * q) = l[c];
+  }
+}
+
+// ------------------------------------------------------------------ DiceCE, staged through shared memory by bulk copies
+// The kernels above read 14 class planes straight into registers: every thread has 14 dependent-latency loads per voxel and only
+// ~6 voxels of work, and they reach 17 % (forward) / 23 % (backward) of the HBM roofline (round 1, ncu).  Here a CTA walks tiles of
+// kDiceTile voxels: ONE thread issues C + 1 `cp.async.bulk` copies per tile (a class plane row or the label row, 2 KB each) into a
+// 3-stage smem ring guarded by mbarriers, so 3 x 30 KB per CTA are in flight with no registers tied up, and the 256 threads compute
+// two voxels each from conflict-free smem rows.  The backward overwrites the stage in place with dlogits and hands the rows back
+// to the copy engine (`cp.async.bulk.global.shared::cta`), so its global stores are 2 KB bursts as well.
+static constexpr int kDiceTile = 512, kDiceStages = 3;
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(tc::smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+static inline size_t dice_staged_smem(int C) { return (size_t)kDiceStages * (C + 1) * kDiceTile * sizeof(float) + 64; }
+
+// tiles of one sample are dealt round-robin to the CTAs of that sample's grid row; V % kDiceTile == 0
+template <int CMAX, bool BWD>
+__global__ void __launch_bounds__(256) dicece_staged_kernel(const float* __restrict__ logits, const float* __restrict__ labels, int C, long V,
+                                                            double* __restrict__ acc, int nBC, const float* __restrict__ coef,
+                                                            const float* __restrict__ upstream, int B, float* __restrict__ dlogits) {
+  extern __shared__ __align__(128) uint8_t dsm[];
+  const int b = blockIdx.y;
+  const uint32_t stage_floats = (uint32_t)(C + 1) * kDiceTile, stage_bytes = stage_floats * 4;
+  float* ring = reinterpret_cast<float*>(dsm);
+  uint64_t* full = reinterpret_cast<uint64_t*>(dsm + (size_t)kDiceStages * stage_bytes);
+  __shared__ float sc[2 * CMAX];
+  __shared__ float red[8][3 * CMAX + 1];
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    for (int s = 0; s < kDiceStages; ++s) tc::mbar_init(full + s, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (BWD && tid < 2 * C) sc[tid] = coef[(long)b * C * 2 + tid];
+  __syncthreads();
+  const long tiles = V / kDiceTile;
+  const float* lg = logits + (long)b * C * V;
+  const float* lb = labels + (long)b * V;
+  float* dl = BWD ? dlogits + (long)b * C * V : nullptr;
+  auto issue = [&](long tile, int s) {       // thread 0 only
+    const uint32_t base = tc::smem_u32(ring + (size_t)s * stage_floats);
+    tc::mbar_expect_tx(full + s, stage_bytes);
+    for (int c = 0; c < C; ++c) bulk_g2s(base + (uint32_t)c * kDiceTile * 4, lg + (long)c * V + tile * kDiceTile, kDiceTile * 4, full + s);
+    bulk_g2s(base + (uint32_t)C * kDiceTile * 4, lb + tile * kDiceTile, kDiceTile * 4, full + s);
+  };
+  if (tid == 0)
+    for (int s = 0; s < kDiceStages; ++s) { const long t = blockIdx.x + (long)s * gridDim.x; if (t < tiles) issue(t, s); }
+  float aI[CMAX], aP[CMAX], aG[CMAX];
+#pragma unroll
+  for (int c = 0; c < CMAX; ++c) aI[c] = aP[c] = aG[c] = 0.f;
+  float ce = 0.f;
+  const float up = BWD ? (upstream ? upstream[0] : 1.f) : 0.f;
+  const float invBV = 1.f / ((float)B * (float)V);
+  int it = 0;
+  for (long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+    const int s = it % kDiceStages;
+    tc::mbar_wait(full + s, (uint32_t)(it / kDiceStages) & 1u);
+    float* st = ring + (size_t)s * stage_floats;
+#pragma unroll
+    for (int e = 0; e < kDiceTile / 256; ++e) {
+      const int v = e * 256 + tid;
+      float l[CMAX];
+      float mx = -INFINITY, ly = 0.f;
+      const int y = (int)st[C * kDiceTile + v];
+#pragma unroll
+      for (int c = 0; c < CMAX; ++c)
+        if (c < C) { l[c] = st[c * kDiceTile + v]; mx = fmaxf(mx, l[c]); if (c == y) ly = l[c]; }
+      float sum = 0.f;
+#pragma unroll
+      for (int c = 0; c < CMAX; ++c)
+        if (c < C) { l[c] = __expf(l[c] - mx); sum += l[c]; }
+      const float inv = 1.f / sum;
+      if (!BWD) {
+        ce += logf(sum) - (ly - mx);
+#pragma unroll
+        for (int c = 0; c < CMAX; ++c)
+          if (c < C) {
+            const float p = l[c] * inv;
+            aP[c] += p;
+            if (c == y) { aI[c] += p; aG[c] += 1.f; }
+          }
+      } else {
+        float dot = 0.f;
+#pragma unroll
+        for (int c = 0; c < CMAX; ++c)
+          if (c < C) { l[c] *= inv; dot += l[c] * (sc[2 * c] * (c == y ? 1.f : 0.f) + sc[2 * c + 1]); }
+#pragma unroll
+        for (int c = 0; c < CMAX; ++c)
+          if (c < C) {
+            const float t = (c == y) ? 1.f : 0.f;
+            const float wk = sc[2 * c] * t + sc[2 * c + 1];
+            st[c * kDiceTile + v] = up * (l[c] * (wk - dot) + (l[c] - t) * invBV);     // in place: only this thread touches column v
+          }
+      }
+    }
+    if (BWD) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();                                   // every thread is done with stage s
+    if (tid == 0) {
+      const long nxt = tile + (long)kDiceStages * gridDim.x;
+      if (BWD) {
+        const uint32_t base = tc::smem_u32(st);
+        for (int c = 0; c < C; ++c) bulk_s2g(dl + (long)c * V + tile * kDiceTile, base + (uint32_t)c * kDiceTile * 4, kDiceTile * 4);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        // stage s is refilled one iteration later (when its stores have read it): refill the PREVIOUS stage now
+        asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        const long prev_nxt = nxt - gridDim.x;
+        if (it >= 1 && prev_nxt < tiles) issue(prev_nxt, (it - 1) % kDiceStages);
+      } else if (nxt < tiles) {
+        issue(nxt, s);
+      }
+    }
+  }
+  if (BWD) {
+    if (tid == 0) {
+      // the last stage written has not been refilled (nothing left to load for it unless tiles remain: handled above for it-1 only)
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
+    return;
+  }
+  const int lane = tid & 31, w = tid >> 5;
+#pragma unroll
+  for (int c = 0; c < CMAX; ++c) {
+    float x0 = warp_sum(aI[c]), x1 = warp_sum(aP[c]), x2 = warp_sum(aG[c]);
+    if (lane == 0) { red[w][3 * c] = x0; red[w][3 * c + 1] = x1; red[w][3 * c + 2] = x2; }
+  }
+  ce = warp_sum(ce);
+  if (lane == 0) red[w][3 * CMAX] = ce;
+  __syncthreads();
+  for (int i = tid; i < 3 * C + 1; i += blockDim.x) {
+    const int src = (i < 3 * C) ? i : 3 * CMAX;
+    double t = 0.0;
+    for (int k = 0; k < 8; ++k) t += red[k][src];
+    if (i < 3 * C) atomicAdd(acc + ((long)b * C) * 3 + i, t);
+    else atomicAdd(acc + (long)nBC * 3, t);
   }
 }
 
