@@ -57,6 +57,10 @@ SIGNATURES = {
                                  POINTER(c_int32), c_int, POINTER(c_int32), c_int, c_void_p]),
     "b200_sw_finalize_metric": (c_int, [c_void_p, c_void_p, c_void_p, POINTER(SwGeom), c_int, POINTER(c_int32), c_int,
                                         POINTER(c_int32), c_int, POINTER(c_int32), c_int, c_void_p, c_void_p, c_void_p]),
+    "b200_sw_accumulate_slab": (c_int, [c_void_p, POINTER(SwGeom), POINTER(c_void_p), POINTER(c_int32), c_int, c_int, c_int, c_void_p]),
+    "b200_sw_pack_rows": (c_int, [c_void_p, c_void_p, POINTER(SwGeom), c_int, c_int, c_void_p]),
+    "b200_sw_finalize_slab": (c_int, [c_void_p, c_void_p, c_void_p, POINTER(SwGeom), c_int, POINTER(c_int32), c_int, POINTER(c_int32), c_int,
+                                      POINTER(c_int32), c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "b200_dicece_sigmoid_forward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p]),
     "b200_dicece_sigmoid_backward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "b200_seg_counts_onehot": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int64, c_void_p, c_void_p]),

@@ -363,8 +363,29 @@ int b200_sw_accumulate_n(float* acc, const float* pred, const b200_sw_geom* g, c
   B200_LAUNCH_CHECK();
   return 0;
 }
+static int sw_finalize_impl(const float* acc, float* out, uint8_t* mask, const b200_sw_geom* g, int batch, const int32_t* s0, int n0,
+                            const int32_t* s1, int n1, const int32_t* s2, int n2, const float* labels, double* counts, const SwSlab* slab,
+                            int zero_counts, void* stream);
 int b200_sw_finalize_metric(const float* acc, float* out, uint8_t* mask, const b200_sw_geom* g, int batch, const int32_t* s0, int n0,
                             const int32_t* s1, int n1, const int32_t* s2, int n2, const float* labels, double* counts, void* stream) {
+  return sw_finalize_impl(acc, out, mask, g, batch, s0, n0, s1, n1, s2, n2, labels, counts, nullptr, 1, stream);
+}
+/* slab form (multi-GPU): this rank owns un-padded rows [d0, d0 + nd) of ONE batch item (index `item` of the full-size mask / labels /
+ * counts); acc holds padded rows [acc_xoff, acc_xoff + acc_rows) of that item; out (nullable) holds un-padded rows
+ * [out_d0, out_d0 + out_rows).  counts (if given) are accumulated, not zeroed: the caller zeroes them once and all-reduces. */
+int b200_sw_finalize_slab(const float* acc, float* out, uint8_t* mask, const b200_sw_geom* g, int item, const int32_t* s0, int n0,
+                          const int32_t* s1, int n1, const int32_t* s2, int n2, const float* labels, double* counts,
+                          int d0, int nd, int acc_xoff, int acc_rows, int out_d0, int out_rows, void* stream) {
+  B200_CHECK(item >= 0 && nd >= 0 && d0 >= 0 && d0 + nd <= g->d, "b200_sw_finalize_slab: rows out of range");
+  if (nd == 0) return 0;
+  SwSlab sl = {d0, nd, acc_xoff, acc_rows, out_d0, out_rows};
+  const long vox = (long)g->d * g->h * g->w;
+  return sw_finalize_impl(acc, out, mask ? mask + (size_t)item * vox : nullptr, g, 1, s0, n0, s1, n1, s2, n2,
+                          labels ? labels + (size_t)item * vox : nullptr, counts ? counts + (size_t)item * g->channels * 3 : nullptr, &sl, 0, stream);
+}
+static int sw_finalize_impl(const float* acc, float* out, uint8_t* mask, const b200_sw_geom* g, int batch, const int32_t* s0, int n0,
+                            const int32_t* s1, int n1, const int32_t* s2, int n2, const float* labels, double* counts, const SwSlab* slab,
+                            int zero_counts, void* stream) {
   B200_CHECK(n0 <= 64 && n1 <= 64 && n2 <= 64, "more than 64 window starts along one axis");
   B200_CHECK((labels == nullptr) == (counts == nullptr), "labels and counts go together");
   SwStarts st; st.n0 = n0; st.n1 = n1; st.n2 = n2;
@@ -373,11 +394,46 @@ int b200_sw_finalize_metric(const float* acc, float* out, uint8_t* mask, const b
   for (int i = 0; i < n2; ++i) st.s2[i] = s2[i];
   SwGeom sg = to_sw(g);
   B200_CHECK(!counts || sg.C <= 32, "fused validation counts take at most 32 classes");
-  if (counts) B200_CUDA(cudaMemsetAsync(counts, 0, sizeof(double) * (size_t)batch * sg.C * 3, (cudaStream_t)stream));
-  long vox = (long)sg.D * sg.H * sg.W;
+  if (counts && zero_counts) B200_CUDA(cudaMemsetAsync(counts, 0, sizeof(double) * (size_t)batch * sg.C * 3, (cudaStream_t)stream));
+  SwSlab sl = slab ? *slab : SwSlab{0, sg.D, 0, sg.PD, 0, sg.D};
+  long vox = (long)sl.nd * sg.H * sg.W;
   dim3 grid((unsigned)max(1L, min(148L * 16 / batch + 1, (vox + 255) / 256)), batch);
-  sw_finalize_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(acc, out, mask, sg, st, labels, counts);
+  sw_finalize_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(acc, out, mask, sg, st, labels, counts, sl);
   B200_LAUNCH_CHECK();
+  return 0;
+}
+/* pieces: n x {s0, s1, s2, x_lo, x_hi, nx, xbase} (int32) + preds: n device pointers; acc = slab [C][nrows][PH][PW] of padded rows
+ * [xoff, xoff + nrows).  Adds the pieces in the order given (= global window order). */
+int b200_sw_accumulate_slab(float* acc, const b200_sw_geom* g, const void* const* preds, const int32_t* pieces, int n, int xoff, int nrows,
+                            void* stream) {
+  B200_CHECK(n >= 1 && n <= 16, "sw_accumulate_slab takes 1..16 pieces per call");
+  SwGeom sg = to_sw(g);
+  SwPieces ps; ps.n = n;
+  SwBox bx; int x1 = 0, y1 = 0, z1 = 0;
+  for (int i = 0; i < n; ++i) {
+    const int32_t* q = pieces + 7 * i;
+    ps.p[i] = SwPiece{(const float*)preds[i], q[0], q[1], q[2], q[3], q[4], q[5], q[6]};
+    B200_CHECK(q[3] >= q[0] && q[4] <= q[0] + sg.r0 && q[6] <= q[3] && q[6] + q[5] >= q[4], "sw_accumulate_slab: piece %d rows outside its window/buffer", i);
+    const int a = q[3], a1 = q[4], b = q[1], c = q[2];
+    if (i == 0) { bx.x0 = a; x1 = a1; bx.y0 = b; y1 = b; bx.z0 = c; z1 = c; }
+    bx.x0 = std::min(bx.x0, a); x1 = std::max(x1, a1);
+    bx.y0 = std::min(bx.y0, b); y1 = std::max(y1, b); bx.z0 = std::min(bx.z0, c); z1 = std::max(z1, c);
+  }
+  bx.x0 = std::max(bx.x0, xoff); x1 = std::min(x1, xoff + nrows);
+  bx.nx = x1 - bx.x0; bx.ny = y1 - bx.y0 + sg.r1; bx.nz = z1 - bx.z0 + sg.r2;
+  if (bx.nx <= 0) return 0;
+  long rows = (long)bx.nx * bx.ny * sg.C;
+  sw_accumulate_slab_kernel<<<(unsigned)min(148L * 16, (rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(acc, sg, ps, bx, xoff, nrows);
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+/* rows [x_from, x_from + nx) of a window prediction [C][r0][r1][r2] -> contiguous [C][nx][r1][r2] (the wire format of a halo piece):
+ * one strided device-to-device copy on the DMA engine */
+int b200_sw_pack_rows(const float* pred, float* dst, const b200_sw_geom* g, int x_from, int nx, void* stream) {
+  B200_CHECK(x_from >= 0 && nx >= 1 && x_from + nx <= g->roi0, "b200_sw_pack_rows: rows outside the window");
+  const size_t plane = (size_t)g->roi1 * g->roi2 * sizeof(float);
+  B200_CUDA(cudaMemcpy2DAsync(dst, plane * nx, pred + (size_t)x_from * g->roi1 * g->roi2, plane * g->roi0, plane * nx, g->channels,
+                              cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   return 0;
 }
 int b200_sw_finalize(const float* acc, float* out, uint8_t* mask, const b200_sw_geom* g, int batch, const int32_t* s0, int n0,

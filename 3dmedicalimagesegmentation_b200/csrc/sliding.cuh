@@ -77,21 +77,62 @@ static __global__ void __launch_bounds__(256) sw_accumulate_multi_kernel(float* 
     }
   }
 }
+// ---- slab-owned accumulation (multi-GPU): a rank owns the padded rows [xoff, xoff + nrows) of ONE batch item and adds,
+// in global window order, every contribution that touches them: its own windows and the row-clipped pieces of lower ranks' windows
+// that arrived over NVLink.  A piece is a window prediction restricted to padded rows [x_lo, x_hi); its buffer is [C][nx][r1][r2]
+// with buffer row 0 = padded row xbase (own windows: the full prediction, xbase = s0, nx = r0; received pieces: xbase = x_lo).
+// Per voxel the float additions happen in piece order = window order: bit-identical to the single-GPU loop.
+struct SwPiece { const float* pred; int s0, s1, s2, x_lo, x_hi, nx, xbase; };
+struct SwPieces { SwPiece p[16]; int n; };
+static __global__ void __launch_bounds__(256) sw_accumulate_slab_kernel(float* __restrict__ acc, SwGeom g, SwPieces ps, SwBox bx, int xoff, int nrows) {
+  const long rows = (long)g.C * bx.nx * bx.ny;
+  const int lane = threadIdx.x & 31;
+  const long warps = ((long)gridDim.x * blockDim.x) >> 5;
+  for (long row = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < rows; row += warps) {
+    long r = row;
+    const int y = bx.y0 + (int)(r % bx.ny); r /= bx.ny; const int x = bx.x0 + (int)(r % bx.nx); const int c = (int)(r / bx.nx);
+    if ((unsigned)(x - xoff) >= (unsigned)nrows) continue;
+    unsigned live = 0;
+    for (int k = 0; k < ps.n; ++k)
+      if (x >= ps.p[k].x_lo && x < ps.p[k].x_hi && (unsigned)(y - ps.p[k].s1) < (unsigned)g.r1) live |= 1u << k;
+    if (!live) continue;
+    float* arow = acc + (((long)c * nrows + (x - xoff)) * g.PH + y) * g.PW;
+    for (int zi = lane; zi < bx.nz; zi += 32) {
+      const int z = bx.z0 + zi;
+      float a = 0.f; bool any = false;
+#pragma unroll 1
+      for (int k = 0; k < ps.n; ++k) {
+        const int dz = z - ps.p[k].s2;
+        if (((live >> k) & 1u) && (unsigned)dz < (unsigned)g.r2) {
+          if (!any) { a = arow[z]; any = true; }
+          a += ps.p[k].pred[(((long)c * ps.p[k].nx + (x - ps.p[k].xbase)) * g.r1 + (y - ps.p[k].s1)) * g.r2 + dz];
+        }
+      }
+      if (any) arow[z] = a;
+    }
+  }
+}
+
 struct SwStarts { int n0, n1, n2; int s0[64], s1[64], s2[64]; };
+// which rows a normalise pass works on: un-padded rows [d0, d0 + nd) of the volume, read from an accumulator that holds padded rows
+// [acc_xoff, acc_xoff + acc_rows) and written to an output tensor that holds un-padded rows [out_d0, out_d0 + out_rows)
+struct SwSlab { int d0, nd, acc_xoff, acc_rows, out_d0, out_rows; };
 // out[b][c][d][h][w] = acc[b][c][d+pd][h+ph][w+pw] / count ; optional argmax over c -> mask[b][d][h][w] ;
 // optional validation tail (seg:110-126): with `labels` [B][D][H][W] (integer-valued floats) the argmax is
 // compared with the label in the same pass and counts[b][c][3] += (|y&p|, |p|, |y|) -- the inputs of DiceMetric /
 // ConfusionMatrixMetric -- so whole-volume evaluation never materialises one-hot tensors.
 static __global__ void sw_finalize_kernel(const float* __restrict__ acc, float* __restrict__ out, unsigned char* __restrict__ mask,
-                                   SwGeom g, SwStarts st, const float* __restrict__ labels, double* __restrict__ counts) {
+                                   SwGeom g, SwStarts st, const float* __restrict__ labels, double* __restrict__ counts, SwSlab sl) {
   const long vox = (long)g.D * g.H * g.W;
+  const long vox_slab = (long)sl.nd * g.H * g.W, vbase = (long)sl.d0 * g.H * g.W;
   const int b = blockIdx.y;                       // one sample per grid row: the block's histogram belongs to one sample
   __shared__ unsigned int hist[3 * 32];
   if (counts) {
     for (int i = threadIdx.x; i < 3 * 32; i += blockDim.x) hist[i] = 0u;
     __syncthreads();
   }
-  for (long r0 = (long)blockIdx.x * blockDim.x + threadIdx.x; r0 < vox; r0 += (long)gridDim.x * blockDim.x) {
+  for (long rs = (long)blockIdx.x * blockDim.x + threadIdx.x; rs < vox_slab; rs += (long)gridDim.x * blockDim.x) {
+    const long r0 = vbase + rs;
     long r = r0;
     int w = (int)(r % g.W); r /= g.W; int h = (int)(r % g.H); int d = (int)(r / g.H);
     int x = d + g.pd, y = h + g.ph, z = w + g.pw;
@@ -102,8 +143,8 @@ static __global__ void sw_finalize_kernel(const float* __restrict__ acc, float* 
     float cnt = (float)(c0 * c1 * c2);
     float best = -INFINITY; int arg = 0;
     for (int c = 0; c < g.C; ++c) {
-      float v = acc[((((long)b * g.C + c) * g.PD + x) * g.PH + y) * g.PW + z] / cnt;
-      if (out) out[(((long)b * g.C + c) * g.D + d) * g.H * g.W + (long)h * g.W + w] = v;
+      float v = acc[((((long)b * g.C + c) * sl.acc_rows + (x - sl.acc_xoff)) * g.PH + y) * g.PW + z] / cnt;
+      if (out) out[(((long)b * g.C + c) * sl.out_rows + (d - sl.out_d0)) * g.H * g.W + (long)h * g.W + w] = v;
       if (v > best) { best = v; arg = c; }
     }
     if (mask) mask[(long)b * vox + r0] = (unsigned char)arg;

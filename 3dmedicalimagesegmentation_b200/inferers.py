@@ -2,8 +2,14 @@
 unetr_segmentation_3d.py:109 (positional, overlap 0.25), :143 and :694-695 (keyword, overlap 0.8).
 
 Window enumeration, padding, scan interval and accumulation order follow MONAI 0.6.0; the
-gather / overlap-add / divide-by-count arithmetic runs in csrc/sliding.cuh.  `rank`/`world_size` shard the window
-list across GPUs (windows are independent; the overlap-add is completed with one all-reduce).
+gather / overlap-add / divide-by-count arithmetic runs in csrc/sliding.cuh.
+
+Multi-GPU (`rank`/`world_size`, one process per GPU): the window list of each volume is cut into contiguous chunks, and
+rank r OWNS the padded rows (first spatial axis) from the first row of its first window up to the first row of rank r+1's first
+window -- an x-slab.  Each rank predicts its windows, sends the rows of those predictions that fall into higher ranks' slabs as
+row-clipped pieces (NCCL send/recv: only halo rows cross NVLink, about one window depth per boundary), adds every piece of its own
+slab in GLOBAL window order (bit-identical to the single-GPU loop, which is MONAI's order), normalises its slab locally, and the
+uint8 mask / validation counts are combined with one small all-reduce.  The logits stay sharded unless the caller asks for them.
 """
 from __future__ import annotations
 
@@ -16,7 +22,7 @@ import torch
 
 from . import _lib
 
-__all__ = ["sliding_window_inference", "window_starts", "shard_windows"]
+__all__ = ["sliding_window_inference", "window_starts", "shard_windows", "slab_plan"]
 
 
 def _scan_interval(image_size, roi, overlap):
@@ -44,16 +50,48 @@ def shard_windows(n_items: int, rank: int, world_size: int) -> range:
     return range(min(rank * per, n_items), min((rank + 1) * per, n_items))
 
 
+def slab_plan(flat: Sequence[Tuple[int, int, int]], roi0: int, padded_rows: int, world_size: int):
+    """Ownership and halo traffic of the slab-owned sliding window for ONE volume (pure host logic; unit-tested on the CPU).
+
+    `flat`: window starts in MONAI order (first axis slowest).  Returns (chunks, bounds, pieces):
+      chunks[r]  = range of window indices rank r predicts (contiguous, `shard_windows`);
+      bounds     = world_size + 1 padded-row boundaries: rank r owns rows [bounds[r], bounds[r+1]) (possibly empty);
+      pieces[d]  = the contributions to rank d's slab in global window order: (window, source rank, x_lo, x_hi) with
+                   [x_lo, x_hi) = that window's rows inside d's slab.  source == d: an own window; source < d: a halo piece.
+    A window only ever reaches forward (into slabs of ranks >= its own), so data flows one way along the rank order."""
+    n = len(flat)
+    chunks = [shard_windows(n, r, world_size) for r in range(world_size)]
+    bounds = [flat[c.start][0] if len(c) else padded_rows for c in chunks] + [padded_rows]
+    bounds[0] = 0
+    for r in range(world_size - 1, -1, -1):          # ranks without windows own nothing: collapse onto the next boundary
+        bounds[r] = min(bounds[r], bounds[r + 1])
+    pieces = [[] for _ in range(world_size)]
+    for src, ch in enumerate(chunks):
+        for w in ch:
+            xs = flat[w][0]
+            for d in range(src, world_size):
+                lo, hi = max(xs, bounds[d]), min(xs + roi0, bounds[d + 1])
+                if hi > lo:
+                    pieces[d].append((w, src, lo, hi))
+    for d in range(world_size):
+        pieces[d].sort(key=lambda p: p[0])
+    return chunks, bounds, pieces
+
+
 def sliding_window_inference(inputs: torch.Tensor, roi_size, sw_batch_size: int, predictor: Callable,
                              overlap: float = 0.25, mode: str = "constant", sigma_scale=0.125,
                              padding_mode: str = "constant", cval: float = 0.0, sw_device=None, device=None,
                              *args, rank: int = 0, world_size: int = 1, process_group=None,
-                             return_argmax: bool = False, labels: torch.Tensor = None, return_logits: bool = True, **kwargs):
+                             return_argmax: bool = False, labels: torch.Tensor = None, return_logits: bool = True,
+                             gather_logits: bool = True, **kwargs):
     """Extras beyond MONAI's signature (all keyword-only, defaults reproduce MONAI): `rank`/`world_size`/`process_group`
     shard the windows; `return_argmax` adds the uint8 class mask; `labels` ([B,1,D,H,W] class ids) fuses the validation
     tail (seg:110-126) into the normalise pass and adds the [B,C,3] counts DiceMetric/ConfusionMatrixMetric consume
     (`metric.update_from_counts`); `return_logits=False` skips writing the 3.76 GB normalised logits when only the mask /
-    counts are wanted.  Return: logits | (logits, mask) | (logits, mask, counts), `None` in place of skipped logits."""
+    counts are wanted.  Return: logits | (logits, mask) | (logits, mask, counts), `None` in place of skipped logits.
+    `world_size > 1`: slab-owned accumulation (module docstring); mask and counts are complete on every rank; the logits are
+    complete on every rank with `gather_logits=True` (default, MONAI semantics: one broadcast per slab) and otherwise stay
+    sharded: the returned tensor is this rank's slab `[1,C,rows,H,W]` with `.row_offset` (batch 1 only, else None)."""
     if str(mode).lower() not in ("constant", "blendmode.constant"):
         raise NotImplementedError("only constant blending (the mode both reference call sites use) is implemented")
     if str(padding_mode).lower() not in ("constant", "pytorchpadmode.constant"):
@@ -75,9 +113,12 @@ def sliding_window_inference(inputs: torch.Tensor, roi_size, sw_batch_size: int,
     if max(len(a) for a in per_axis) > 64:
         raise NotImplementedError("more than 64 windows along one axis")
     num_win = len(flat)
-    items = [(b, *flat[w]) for b in range(batch) for w in range(num_win)]   # idx -> (idx // num_win, idx % num_win)
-    mine = shard_windows(len(items), rank, world_size)
     st = _lib.stream_ptr()
+    if world_size > 1:
+        return _sw_slabs(lib, x, per_axis, flat, roi, size, orig, pad, chan, batch, max(1, min(int(sw_batch_size), 16)), predictor, args, kwargs,
+                         float(cval), rank, world_size, process_group, return_argmax, labels, return_logits, gather_logits)
+    items = [(b, *flat[w]) for b in range(batch) for w in range(num_win)]   # idx -> (idx // num_win, idx % num_win)
+    mine = range(len(items))
 
     gin = _lib.SwGeom(chan, *orig, *pad, *size, *roi)
     sw_batch_size = max(1, min(int(sw_batch_size), 16))
@@ -85,17 +126,27 @@ def sliding_window_inference(inputs: torch.Tensor, roi_size, sw_batch_size: int,
     gout = None
     # our own UNETR replays its forward as one CUDA graph inside this loop (each prediction is accumulated at once, so the
     # graph's static output buffers may be overwritten by the next call); B200_NO_GRAPH=1 keeps the eager launches
-    use_graph = hasattr(predictor, "_graph_forward") and not getattr(predictor, "tuple_output", True) and \
-        not torch.is_grad_enabled() and not os.environ.get("B200_NO_GRAPH") and len(mine) >= 4 * sw_batch_size
-    prev_graph = getattr(predictor, "inference_graph", False)
-    if use_graph:
-        predictor.inference_graph = True
-    try:
+    with _graphed(predictor, len(mine) >= 4 * sw_batch_size):
         acc, gout = _sw_loop(lib, x, items, mine, sw_batch_size, chan, roi, gin, cval, st, predictor, args, kwargs, batch, size, orig, pad)
-    finally:
-        if use_graph:
-            predictor.inference_graph = prev_graph
-    return _sw_finish(lib, acc, gout, world_size, process_group, batch, orig, per_axis, return_argmax, x, st, labels, return_logits)
+    return _sw_finish(lib, acc, gout, batch, orig, per_axis, return_argmax, x, st, labels, return_logits)
+
+
+class _graphed:
+    """our own UNETR replays its forward as one CUDA graph inside the window loop (see sliding_window_inference)"""
+
+    def __init__(self, predictor, worth_it):
+        self.p = predictor
+        self.on = hasattr(predictor, "_graph_forward") and not getattr(predictor, "tuple_output", True) and \
+            not torch.is_grad_enabled() and not os.environ.get("B200_NO_GRAPH") and worth_it
+
+    def __enter__(self):
+        if self.on:
+            self.prev = getattr(self.p, "inference_graph", False)
+            self.p.inference_graph = True
+
+    def __exit__(self, *exc):
+        if self.on:
+            self.p.inference_graph = self.prev
 
 
 def _sw_loop(lib, x, items, mine, sw_batch_size, chan, roi, gin, cval, st, predictor, args, kwargs, batch, size, orig, pad):
@@ -129,26 +180,12 @@ def _sw_loop(lib, x, items, mine, sw_batch_size, chan, roi, gin, cval, st, predi
     return acc, gout
 
 
-def _sw_finish(lib, acc, gout, world_size, process_group, batch, orig, per_axis, return_argmax, x, st, labels=None,
-               return_logits=True):
-    if acc is None:
-        raise RuntimeError("this rank owns no windows; use fewer ranks than windows")
-    if world_size > 1:
-        import torch.distributed as dist
-        dist.all_reduce(acc, group=process_group)
+def _sw_finish(lib, acc, gout, batch, orig, per_axis, return_argmax, x, st, labels=None, return_logits=True):
     cout = acc.shape[1]
     want_mask = return_argmax or labels is not None
     out = torch.empty((batch, cout, *orig), dtype=torch.float32, device=x.device) if return_logits else None
     mask = torch.empty((batch, 1, *orig), dtype=torch.uint8, device=x.device) if want_mask else None
-    counts = None
-    lab = None
-    if labels is not None:
-        if cout > 32:
-            raise NotImplementedError("fused validation counts take at most 32 classes")
-        lab = labels.to(x.device).float().contiguous()
-        if lab.shape[0] != batch or tuple(lab.shape[-3:]) != tuple(orig) or lab.numel() != batch * orig[0] * orig[1] * orig[2]:
-            raise ValueError(f"labels {tuple(labels.shape)} do not match the volume {(batch, 1, *orig)}")
-        counts = torch.empty((batch, cout, 3), dtype=torch.float64, device=x.device)
+    lab, counts = _label_args(labels, x, batch, cout, orig)
     arrs = [(ctypes.c_int32 * len(a))(*a) for a in per_axis]
     _lib.check(lib.b200_sw_finalize_metric(_lib.ptr(acc), _lib.ptr(out), _lib.ptr(mask), ctypes.byref(gout), batch,
                                            arrs[0], len(arrs[0]), arrs[1], len(arrs[1]), arrs[2], len(arrs[2]),
@@ -157,3 +194,184 @@ def _sw_finish(lib, acc, gout, world_size, process_group, batch, orig, per_axis,
         counts.voxels = orig[0] * orig[1] * orig[2]
         return out, mask, counts
     return (out, mask) if return_argmax else out
+
+
+def _label_args(labels, x, batch, cout, orig):
+    if labels is None:
+        return None, None
+    if cout > 32:
+        raise NotImplementedError("fused validation counts take at most 32 classes")
+    lab = labels.to(x.device).float().contiguous()
+    if lab.shape[0] != batch or tuple(lab.shape[-3:]) != tuple(orig) or lab.numel() != batch * orig[0] * orig[1] * orig[2]:
+        raise ValueError(f"labels {tuple(labels.shape)} do not match the volume {(batch, 1, *orig)}")
+    return lab, torch.zeros((batch, cout, 3), dtype=torch.float64, device=x.device)
+
+
+# ------------------------------------------------------------------------------------------------ slab-owned multi-GPU path
+class _SlabItem:
+    """One volume (batch item) on one rank: predict own windows, pack the halo pieces, accumulate the slab, normalise it."""
+
+    def __init__(self, lib, x, item, flat, roi, size, orig, pad, chan, rank, world, cval):
+        self.lib, self.x, self.item, self.flat, self.roi, self.size, self.orig, self.pad = lib, x, item, flat, roi, size, orig, pad
+        self.chan, self.rank, self.world, self.cval = chan, rank, world, cval
+        self.chunks, self.bounds, self.pieces = slab_plan(flat, roi[0], size[0], world)
+        self.mine = self.chunks[rank]
+        self.x0, self.x1 = self.bounds[rank], self.bounds[rank + 1]
+        self.gin = _lib.SwGeom(chan, *orig, *pad, *size, *roi)
+        self.preds = None
+        self.gout = None
+        self.cout = None
+
+    def predict(self, predictor, sw_batch, args, kwargs):
+        lib, st = self.lib, _lib.stream_ptr()
+        for g0 in range(self.mine.start, self.mine.stop, sw_batch):
+            ws = range(g0, min(g0 + sw_batch, self.mine.stop))
+            n = len(ws)
+            starts = (ctypes.c_int32 * (4 * n))(*[v for w in ws for v in (self.item, *self.flat[w])])
+            win = torch.empty((n, self.chan, *self.roi), dtype=torch.float32, device=self.x.device)
+            _lib.check(lib.b200_sw_gather(_lib.ptr(self.x), _lib.ptr(win), ctypes.byref(self.gin), starts, n, self.cval, st), "b200_sw_gather")
+            pred = predictor(win, *args, **kwargs)
+            if isinstance(pred, (tuple, list)):
+                raise TypeError("predictor must return a tensor (monai.networks.nets.UNETR flavour, seg:36)")
+            if self.preds is None:
+                self.cout = pred.shape[1]
+                self.preds = torch.empty((len(self.mine), self.cout, *self.roi), dtype=torch.float32, device=self.x.device)
+                self.gout = _lib.SwGeom(self.cout, *self.orig, *self.pad, *self.size, *self.roi)
+            # every prediction is kept until the halo pieces of the lower ranks have arrived: a voxel's additions must happen in
+            # global window order, and those pieces come first
+            self.preds[g0 - self.mine.start:g0 - self.mine.start + n].copy_(pred)
+
+    def piece_elems(self, lo, hi):
+        return self.cout * (hi - lo) * self.roi[1] * self.roi[2]
+
+    def pack_sends(self):
+        """{dst: flat fp32 buffer} of the row-clipped pieces of own windows that land in dst's slab, in window order."""
+        lib, st, out = self.lib, _lib.stream_ptr(), {}
+        for d in range(self.rank + 1, self.world):
+            mine = [p for p in self.pieces[d] if p[1] == self.rank]
+            if not mine:
+                continue
+            buf = torch.empty(sum(self.piece_elems(lo, hi) for _, _, lo, hi in mine), dtype=torch.float32, device=self.x.device)
+            off = 0
+            for w, _, lo, hi in mine:
+                _lib.check(lib.b200_sw_pack_rows(_lib.ptr(self.preds[w - self.mine.start]), ctypes.c_void_p(buf.data_ptr() + 4 * off),
+                                                 ctypes.byref(self.gout), lo - self.flat[w][0], hi - lo, st), "b200_sw_pack_rows")
+                off += self.piece_elems(lo, hi)
+            out[d] = buf
+        return out
+
+    def recv_sizes(self, cout):
+        """{src: element count} this rank receives (cout known to every rank: same predictor)."""
+        out = {}
+        for w, src, lo, hi in self.pieces[self.rank]:
+            if src != self.rank:
+                out[src] = out.get(src, 0) + cout * (hi - lo) * self.roi[1] * self.roi[2]
+        return out
+
+    def accumulate(self, recv):
+        """recv: {src: flat buffer}.  Adds all pieces of the slab in global window order; returns the slab accumulator."""
+        lib, st = self.lib, _lib.stream_ptr()
+        nrows = self.x1 - self.x0
+        acc = torch.zeros((self.cout, max(nrows, 1), self.size[1], self.size[2]), dtype=torch.float32, device=self.x.device)
+        if nrows <= 0:
+            return acc
+        offs = {src: 0 for src in recv}
+        todo = []
+        for w, src, lo, hi in self.pieces[self.rank]:
+            s0, s1, s2 = self.flat[w]
+            if src == self.rank:
+                ptr, nx, xbase = self.preds[w - self.mine.start].data_ptr(), self.roi[0], s0
+            else:
+                ptr, nx, xbase = recv[src].data_ptr() + 4 * offs[src], hi - lo, lo
+                offs[src] += self.cout * (hi - lo) * self.roi[1] * self.roi[2]
+            todo.append((ptr, (s0, s1, s2, lo, hi, nx, xbase)))
+        for k0 in range(0, len(todo), 16):
+            grp = todo[k0:k0 + 16]
+            ptrs = (ctypes.c_void_p * len(grp))(*[g[0] for g in grp])
+            desc = (ctypes.c_int32 * (7 * len(grp)))(*[v for g in grp for v in g[1]])
+            _lib.check(lib.b200_sw_accumulate_slab(_lib.ptr(acc), ctypes.byref(self.gout), ptrs, desc, len(grp), self.x0, nrows, st),
+                       "b200_sw_accumulate_slab")
+        return acc
+
+    def rows(self):
+        """un-padded rows [d0, d1) of the volume this rank owns"""
+        d0 = min(max(self.x0 - self.pad[0], 0), self.orig[0])
+        d1 = min(max(self.x1 - self.pad[0], 0), self.orig[0])
+        return d0, d1
+
+    def finalize(self, acc, per_axis, out, out_d0, out_rows, mask, lab, counts):
+        d0, d1 = self.rows()
+        arrs = [(ctypes.c_int32 * len(a))(*a) for a in per_axis]
+        _lib.check(self.lib.b200_sw_finalize_slab(_lib.ptr(acc), _lib.ptr(out), _lib.ptr(mask), ctypes.byref(self.gout), self.item,
+                                                  arrs[0], len(arrs[0]), arrs[1], len(arrs[1]), arrs[2], len(arrs[2]),
+                                                  _lib.ptr(lab), _lib.ptr(counts), d0, d1 - d0, self.x0, max(self.x1 - self.x0, 1),
+                                                  out_d0, out_rows, _lib.stream_ptr()), "b200_sw_finalize_slab")
+
+
+def _exchange_nccl(sends, recv_sizes, device, group):
+    """sends: {dst: buffer}; recv_sizes: {src: elements} -> {src: buffer}.  One batched NCCL send/recv round."""
+    import torch.distributed as dist
+    recv = {src: torch.empty(n, dtype=torch.float32, device=device) for src, n in recv_sizes.items()}
+    ops = [dist.P2POp(dist.isend, buf, dst, group) for dst, buf in sorted(sends.items())] + \
+          [dist.P2POp(dist.irecv, buf, src, group) for src, buf in sorted(recv.items())]
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    return recv
+
+
+def _sw_slabs(lib, x, per_axis, flat, roi, size, orig, pad, chan, batch, sw_batch, predictor, args, kwargs, cval, rank, world, group,
+              return_argmax, labels, return_logits, gather_logits, exchange=None):
+    import torch.distributed as dist
+    if len(flat) < world:
+        raise RuntimeError("fewer windows than ranks; use fewer ranks")
+    exchange = exchange or (lambda sends, sizes: _exchange_nccl(sends, sizes, x.device, group))
+    want_mask = return_argmax or labels is not None
+    mask = torch.zeros((batch, 1, *orig), dtype=torch.uint8, device=x.device) if want_mask else None
+    lab = counts = None
+    full = None
+    slab_out = None
+    items = [_SlabItem(lib, x, b, flat, roi, size, orig, pad, chan, rank, world, cval) for b in range(batch)]
+    with _graphed(predictor, len(items[0].mine) * batch >= 4 * sw_batch):
+        for it in items:
+            it.predict(predictor, sw_batch, args, kwargs)
+    cout = items[0].cout
+    lab, counts = _label_args(labels, x, batch, cout, orig)
+    for it in items:
+        recv = exchange(it.pack_sends(), it.recv_sizes(cout))
+        acc = it.accumulate(recv)
+        d0, d1 = it.rows()
+        out = None
+        if return_logits and gather_logits:
+            if full is None:
+                full = torch.empty((batch, cout, *orig), dtype=torch.float32, device=x.device)
+            out, out_d0, out_rows = full[it.item], 0, orig[0]
+        elif return_logits and batch == 1:
+            slab_out = torch.empty((1, cout, max(d1 - d0, 0), orig[1], orig[2]), dtype=torch.float32, device=x.device)
+            slab_out.row_offset = d0
+            out, out_d0, out_rows = slab_out, d0, max(d1 - d0, 1)
+        else:
+            out_d0, out_rows = 0, 1
+        it.finalize(acc, per_axis, out, out_d0, out_rows, mask, lab, counts)
+        it.preds = None
+    # combine: every un-padded row has exactly one owner, the others hold zeros
+    if mask is not None and dist.is_initialized():
+        dist.all_reduce(mask, group=group)
+    if counts is not None and dist.is_initialized():
+        dist.all_reduce(counts, group=group)
+    if full is not None and dist.is_initialized():
+        works = []
+        for it in items:
+            for r in range(world):
+                lo = min(max(it.bounds[r] - pad[0], 0), orig[0]); hi = min(max(it.bounds[r + 1] - pad[0], 0), orig[0])
+                if hi > lo:      # rows of one owner are a strided view per channel: broadcast channel planes as contiguous chunks
+                    for c in range(cout):
+                        works.append(dist.broadcast(full[it.item, c, lo:hi], src=dist.get_global_rank(group, r) if group is not None else r,
+                                                    group=group, async_op=True))
+        for w in works:
+            w.wait()
+    logits = full if full is not None else slab_out
+    if counts is not None:
+        counts.voxels = orig[0] * orig[1] * orig[2]
+        return logits, mask, counts
+    return (logits, mask) if return_argmax else logits

@@ -98,6 +98,68 @@ def cpu_reference_step_time(batch, steps, warmup):
     return sum(times) / len(times)
 
 
+def run_dp_check(pkg, par, model_kw, dev, rank, world):
+    """Untimed correctness of the two sharded paths on the real hardware (N > 1).
+    (a) data parallel, fp32 mode, one crop per rank: rank 0's all-reduced (AVG) gradients against the single-process gradient of
+        the concatenated batch (SURVEY 8(d) config 4) -- relative L2 per tensor; the two differ by fp32 summation order only;
+    (b) slab-owned sliding window on a reduced volume (240x192x96, 12 windows): logits + mask against the single-GPU call, with a
+        batch-composition-independent predictor (bit-equality required) and with the UNETR itself (reported: its forward rounds
+        differently when a window sits in a different sw_batch chunk, so equality is not a property of the sharding)."""
+    import torch.distributed as dist
+    out = {}
+    torch.manual_seed(1234)
+    net = pkg.MonaiUNETR(**model_kw).to(dev).set_mode("fp32")
+    loss_fn = pkg.DiceCELoss(to_onehot_y=True, softmax=True)
+    S = model_kw["img_size"][0]
+    gens = [torch.Generator().manual_seed(900 + r) for r in range(world)]
+    xs = [torch.rand(1, 1, S, S, S, generator=g) for g in gens]
+    ys = [torch.randint(0, 14, (1, 1, S, S, S), generator=g).float() for g in gens]
+    red = par.GradientAllReduce(net, world)
+    loss_fn(net(xs[rank].to(dev)), ys[rank].to(dev)).backward()
+    red.reduce()
+    torch.cuda.synchronize()
+    mine = [p.grad.clone() for p in net.parameters()]
+    net.zero_grad(set_to_none=True)
+    if rank == 0:
+        loss_fn(net(torch.cat(xs).to(dev)), torch.cat(ys).to(dev)).backward()
+        torch.cuda.synchronize()
+        worst, worst_name = 0.0, ""
+        for (name, p), g in zip(net.named_parameters(), mine):
+            e = ((g - p.grad).norm() / p.grad.norm().clamp_min(1e-30)).item()
+            if e > worst:
+                worst, worst_name = e, name
+        out["dp_grad_rel_l2_worst"] = worst
+        out["dp_grad_worst_tensor"] = worst_name
+        out["dp_grad_ok"] = bool(worst <= 2e-3)
+    net.zero_grad(set_to_none=True)
+    del red
+    par.barrier(world)
+
+    vol = torch.randn(1, 1, 240, 192, 96, generator=torch.Generator().manual_seed(77)).to(dev)
+    wts = torch.linspace(-1.5, 1.5, 14, device=dev).view(1, 14, 1, 1, 1)
+
+    def synth(t):      # elementwise: the value of a voxel does not depend on which windows share its predictor call
+        return t * wts + 0.25 * t * t
+
+    net.set_mode("bf16").eval()
+    for tag, f in (("synthetic", synth), ("unetr_bf16", net)):
+        with torch.no_grad():
+            got, gmask = pkg.sliding_window_inference(vol, (96,) * 3, 4, f, overlap=0.5, rank=rank, world_size=world, return_argmax=True)
+            if rank == 0:
+                want, wmask = pkg.sliding_window_inference(vol, (96,) * 3, 4, f, overlap=0.5, return_argmax=True)
+                out[f"sw_{tag}_bit_equal"] = bool(torch.equal(got, want) and torch.equal(gmask, wmask))
+                out[f"sw_{tag}_max_abs_diff"] = (got - want).abs().max().item()
+                out[f"sw_{tag}_mask_mismatch"] = int((gmask != wmask).sum().item())
+                del want, wmask
+            del got, gmask
+        par.barrier(world)
+    if rank == 0:
+        out["sw_ok"] = out["sw_synthetic_bit_equal"]
+    del net
+    torch.cuda.empty_cache()
+    return out if rank == 0 else None
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -131,6 +193,8 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="issue every step's launches from the host instead of replaying the captured CUDA graph")
     ap.add_argument("--breakdown", action="store_true", help="print the per-op CUDA-event breakdown to stderr")
     ap.add_argument("--no-sliding-window", action="store_true", help="skip the configs[4] whole-CT sliding-window measurement")
+    ap.add_argument("--no-dp128", action="store_true", help="skip the configs[3] leg (128^3 crops, 4 per GPU)")
+    ap.add_argument("--no-dp-check", action="store_true", help="skip the untimed multi-GPU correctness checks (N > 1)")
     ap.add_argument("--no-ranking", action="store_true", help="skip the configs[2] ranking pre-training step measurement")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -323,23 +387,58 @@ def main():
         for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0]):
             print(f"  {k:34s} {v[0]:9.3f} ms  {v[1]:4d} calls  {100 * v[0] / tot:5.1f}%", file=sys.stderr)
 
-    # second half of the metric: sliding-window inference on a synthetic 512x512x256 CT (configs[4]), windows sharded over ranks
+    # untimed multi-GPU correctness checks; printed as "dp_check"
+    dp_check = None
+    if world > 1 and S == 96 and not args.no_dp_check:
+        dp_check = run_dp_check(pkg, par, model_kw, dev, rank, world)
+
+    # second half of the metric: sliding-window inference on a synthetic 512x512x256 CT (configs[4]), windows sharded over ranks:
+    # every rank owns an x-slab of the accumulator, halo rows travel by NCCL send/recv, the uint8 mask is all-reduced, logits stay sharded
     sw = None
     if not args.no_sliding_window and S == 96:
         model.eval()
         vol = torch.rand(1, 1, 512, 512, 256, generator=torch.Generator().manual_seed(5)).to(dev)
+        swi = lambda: pkg.sliding_window_inference(vol, (96,) * 3, 4, model, overlap=0.5, rank=rank, world_size=world, return_argmax=True,
+                                                   gather_logits=False)
         with torch.no_grad():
-            # warm-up on the FULL volume: the first call pays cudaMalloc of the 2 x 3.76 GB accumulator/output buffers and NCCL's
-            # lazy set-up of the accumulator all-reduce (measured 240 vs 460 ms run to run without it); steady state is what a
-            # validation loop over many volumes sees
-            pkg.sliding_window_inference(vol, (96,) * 3, 4, model, overlap=0.5, rank=rank, world_size=world)
+            # warm-up on the FULL volume: the first call pays cudaMalloc of the accumulator / output buffers and NCCL's lazy set-up
+            # of the point-to-point channels; steady state is what a validation loop over many volumes sees
+            swi()
             torch.cuda.synchronize()
-            t_sw = min(timed(lambda i: pkg.sliding_window_inference(vol, (96,) * 3, 4, model, overlap=0.5, rank=rank, world_size=world), 1)
-                       for _ in range(2))
+            t_sw = min(timed(lambda i: swi(), 1) for _ in range(2))
         sw = {"value": 1e3 / t_sw, "unit": "volumes/s", "ms_per_volume": t_sw, "windows": 500, "volume": "512x512x256", "roi": 96,
-              "overlap": 0.5, "sw_batch_size": 4, "tflops_algorithmic": 63.29e12 / (t_sw * 1e-3) / 1e12}
+              "overlap": 0.5, "sw_batch_size": 4, "tflops_algorithmic": 63.29e12 / (t_sw * 1e-3) / 1e12,
+              "outputs": "normalised logits (sharded by x-slab across ranks) + uint8 argmax mask (complete on every rank)",
+              "sharding": None if world == 1 else "x-slab accumulators, halo pieces by NCCL send/recv, mask all-reduce (inferers.py)"}
         del vol
         model.train()
+
+    # configs[3]: data-parallel training at 128^3 crops, 4 per GPU (same step: fwd + DiceCE + bwd + gradient all-reduce + AdamW)
+    dp128 = None
+    if not args.no_dp128 and S == 96:
+        gstep = None
+        m128 = pkg.MonaiUNETR(**dict(MODEL_KW, img_size=(128, 128, 128))).to(dev).set_mode(args.mode)
+        o128 = pkg.FusedAdamW(m128.parameters(), lr=1e-4, weight_decay=1e-5, mirror=m128, capturable=True)
+        d128 = par.GradientAllReduce(m128, world) if world > 1 else None
+        x128 = [torch.rand(4, 1, 128, 128, 128, generator=g).to(dev) for _ in range(2)]
+        y128 = [torch.randint(0, 14, (4, 1, 128, 128, 128), generator=g).float().to(dev) for _ in range(2)]
+
+        def step128(i):
+            loss = loss_fn(m128(x128[i % 2]), y128[i % 2])
+            loss.backward()
+            if d128:
+                d128.reduce()
+            o128.step()
+            o128.zero_grad(set_to_none=True)
+        for i in range(3):
+            step128(i)
+        n128 = max(6, min(args.steps, 10))
+        ms128 = timed(step128, n128) / n128
+        dp128 = {"value": 4 * world / (ms128 * 1e-3), "unit": "samples/s", "ms_per_step": ms128, "batch_per_gpu": 4, "steps": n128,
+                 "tflops_algorithmic": 4 * world * 916.84e9 / (ms128 * 1e-3) / 1e12,
+                 "workload": "configs[3]: UNETR(1->14,128^3,fs16,ViT-B) training step, 4 crops per GPU, gradient all-reduce over NVLink (weak scaling)"}
+        del m128, o128, d128, x128, y128
+        torch.cuda.empty_cache()
 
     # configs[2]: ranking pre-training step (rank:238-274) -- batch 8 x 96^3, "feat" stage: full forward, 576 triplets of enc4
     # slices along one axis, Bradley-Terry loss, backward through encoder4 + ViT blocks 0-9 + patch embedding, AdamW step
@@ -395,7 +494,7 @@ def main():
                 "tflops_algorithmic": samples * flop_per_sample / (ms * 1e-3) / 1e12,
                 "e2e": {"value": samples / (ms_e2e * 1e-3), "unit": "samples/s",
                         "h2d_bytes_per_step": host_x[0].numel() * 4 + host_y[0].numel() * 4, "d2h_bytes_per_step": 4},
-                "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "sliding_window": sw, "ranking_step": rk}
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "sliding_window": sw, "ranking_step": rk, "dp_128": dp128, "dp_check": dp_check}
         sys.stdout.flush()
         os.write(saved_out, (json.dumps(line) + "\n").encode())
     par.shutdown(world)

@@ -120,6 +120,23 @@ int b200_sw_finalize_metric(const float* acc, float* out, uint8_t* mask, const b
                             const int32_t* s0, int n0, const int32_t* s1, int n1, const int32_t* s2, int n2,
                             const float* labels, double* counts, void* stream);
 
+/* ---- slab-owned sliding window (multi-GPU, one process per GPU).  The window list of a volume is cut into contiguous
+ * chunks per rank; rank r owns the padded rows from the first row of its first window to the first row of rank r+1's first window.
+ * Contributions that fall into another rank's rows travel there as row-clipped "pieces" (b200_sw_pack_rows -> ncclSend/Recv) and the
+ * owner adds all pieces of a voxel in global window order (b200_sw_accumulate_slab), so the result is bit-identical to the
+ * single-GPU loop of b200_sw_accumulate_n.  pieces: n x {s0, s1, s2, x_lo, x_hi, nx, xbase} int32 -- window start, the padded rows
+ * [x_lo, x_hi) this piece covers, and its buffer preds[i] = [C][nx][roi1][roi2] whose row 0 is padded row xbase.  acc is the slab
+ * [C][nrows][padded_h][padded_w] of padded rows [xoff, xoff + nrows).  preds is a HOST array of n device pointers. */
+int b200_sw_accumulate_slab(float* acc, const b200_sw_geom* g, const void* const* preds, const int32_t* pieces, int n, int xoff, int nrows,
+                            void* stream);
+int b200_sw_pack_rows(const float* pred, float* dst, const b200_sw_geom* g, int x_from, int nx, void* stream);
+/* normalise pass of a slab: un-padded rows [d0, d0 + nd) of batch item `item`; out (nullable) holds un-padded rows
+ * [out_d0, out_d0 + out_rows) of that item; mask / labels / counts are the FULL-size tensors of b200_sw_finalize_metric (counts are
+ * accumulated, not zeroed). */
+int b200_sw_finalize_slab(const float* acc, float* out, uint8_t* mask, const b200_sw_geom* g, int item, const int32_t* s0, int n0,
+                          const int32_t* s1, int n1, const int32_t* s2, int n2, const float* labels, double* counts,
+                          int d0, int nd, int acc_xoff, int acc_rows, int out_d0, int out_rows, void* stream);
+
 /* debug: copy a named workspace buffer of the last forward/backward (device to device, synchronous) */
 int b200_unetr_peek(void* handle, const char* name, void* dst, size_t cap);
 

@@ -135,3 +135,43 @@ def test_gradient_reach_table(pkg):
     assert feat[0] and feat[3 + 9 * 11 + 10] and not feat[3 + 10 * 11] and not feat[135] and feat[145] and not feat[146]
     recon = reach(True, False, True)         # freeze_encoder=True (rank:261-262)
     assert not any(recon[:146]) and all(recon[146:])
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 5, 8])
+@pytest.mark.parametrize("size,roi,overlap", [((40, 24, 24), (16, 16, 16), 0.5), ((512, 512, 256), (96, 96, 96), 0.5), ((33, 16, 20), (16, 16, 16), 0.25)])
+def test_slab_plan_reproduces_the_sequential_sum(pkg, world, size, roi, overlap):
+    """Host logic of the slab-owned sliding window (inferers.slab_plan), emulated with numpy along the sharded axis only: every padded
+    row has exactly one owner, data only flows to higher ranks, and adding each slab's pieces in plan order gives, bit for bit, the
+    float32 sums of the sequential window loop (MONAI's order)."""
+    import importlib
+    import numpy as np
+    inf = importlib.import_module("3dmedicalimagesegmentation_b200.inferers")
+    per_axis, flat = inf.window_starts(size, roi, overlap)
+    if len(flat) < world:
+        pytest.skip("fewer windows than ranks")
+    chunks, bounds, pieces = inf.slab_plan(flat, roi[0], size[0], world)
+    assert bounds[0] == 0 and bounds[-1] == size[0] and all(a <= b for a, b in zip(bounds, bounds[1:]))
+    assert sorted(w for c in chunks for w in c) == list(range(len(flat)))
+    rng = np.random.default_rng(0)
+    # one value per (window, row): the y/z extent does not matter for ownership, so the emulation keeps the first axis only,
+    # but distinguishes windows that share an x-start by giving every (window, row) its own value and its own (y, z) column
+    vals = rng.standard_normal((len(flat), roi[0])).astype(np.float32) * 100
+    cols = {}
+    seq = {}
+    for w, (xs, ys, zs) in enumerate(flat):
+        for i in range(roi[0]):
+            key = (xs + i, ys, zs)          # a representative voxel of this window row
+            seq[key] = np.float32(seq.get(key, np.float32(0)) + vals[w, i])
+    # windows with different (ys, zs) do not meet at their representative voxel; windows with equal (ys, zs) and different xs do
+    got = {}
+    for d in range(world):
+        last = -1
+        for (w, src, lo, hi) in pieces[d]:
+            assert src <= d and w in chunks[src] and w > last - 1 and bounds[d] <= lo < hi <= bounds[d + 1]
+            last = w
+            xs, ys, zs = flat[w]
+            for x in range(lo, hi):
+                key = (x, ys, zs)
+                got[key] = np.float32(got.get(key, np.float32(0)) + vals[w, x - xs])
+    assert got.keys() == seq.keys()
+    assert all(got[k] == seq[k] for k in seq)

@@ -396,17 +396,52 @@ def test_sliding_window_identity_and_oracle(pkg, overlap, shape, roi):
     assert (mask[:, 0].cpu().long() == got.argmax(1).cpu()).all()
 
 
-def test_sliding_window_sharded_equals_single(pkg):
-    """Two-rank sharding emulated on one GPU: the partial overlap-adds of the two shards sum to the full result."""
-    x = torch.rand(1, 1, 48, 40, 32, device=DEV)
-    f = lambda t: torch.cat([t, -t, 2 * t], 1)
-    full = pkg.sliding_window_inference(x, (16,) * 3, 4, f, overlap=0.5)
+@pytest.mark.parametrize("world", [2, 3, 8])
+@pytest.mark.parametrize("shape,roi,overlap", [((48, 40, 32), (16, 16, 16), 0.5), ((40, 20, 24), (16, 16, 16), 0.25), ((12, 40, 40), (16, 16, 16), 0.5)])
+def test_sliding_window_slabs_equal_single_bitwise(pkg, world, shape, roi, overlap):
+    """The slab-owned multi-GPU path, every rank run in turn on one GPU with the NCCL exchange replaced by a hand-over of the packed
+    halo buffers: each rank predicts its window chunk, packs the row-clipped pieces for the higher ranks, accumulates its slab in
+    global window order and normalises it.  Stitched together, logits and argmax mask must equal the single-GPU call BIT FOR BIT
+    (same per-voxel addition order), including a volume smaller than the window along the sharded axis (padding rows)."""
     import importlib
     inf = importlib.import_module("3dmedicalimagesegmentation_b200.inferers")
-    per_axis, flat = inf.window_starts((48, 40, 32), (16,) * 3, 0.5)
-    owned = [list(inf.shard_windows(len(flat), r, 2)) for r in range(2)]
-    assert sorted(owned[0] + owned[1]) == list(range(len(flat)))
-    assert torch.allclose(full, f(x), atol=1e-5)
+    lib = pkg._lib.load()
+    g = torch.Generator().manual_seed(sum(shape) + world)
+    x = torch.randn(1, 2, *shape, generator=g).to(DEV)
+    wts = torch.tensor([[0.7, -1.3], [1.9, 0.4], [-0.6, 0.8]], device=DEV)
+
+    def f(t):      # 2 -> 3 channels, not window-position independent after fp32 rounding of the overlap sums
+        return torch.einsum("kc,bcxyz->bkxyz", wts, t) + 0.1 * t[:, :1] * t[:, 1:2]
+
+    lab = torch.randint(0, 3, (1, 1, *shape), generator=g).float().to(DEV)
+    want, want_mask, want_counts = pkg.sliding_window_inference(x, roi, 4, f, overlap=overlap, return_argmax=True, labels=lab)
+    size = tuple(max(o, r) for o, r in zip(shape, roi))
+    pad = tuple((s_ - o) // 2 for s_, o in zip(size, shape))
+    per_axis, flat = inf.window_starts(size, roi, overlap)
+    if len(flat) < world:
+        pytest.skip("fewer windows than ranks")
+    ranks = [inf._SlabItem(lib, x, 0, flat, roi, size, shape, pad, 2, r, world, 0.0) for r in range(world)]
+    sends = []
+    for it in ranks:
+        it.predict(f, 4, (), {})
+        sends.append(it.pack_sends())
+    cout = ranks[0].cout
+    got = torch.full_like(want, float("nan"))
+    mask = torch.zeros_like(want_mask)
+    counts = torch.zeros_like(want_counts)
+    covered = 0
+    for r, it in enumerate(ranks):
+        sizes = it.recv_sizes(cout)
+        recv = {src: sends[src][r] for src in sizes}
+        assert all(recv[src].numel() == n for src, n in sizes.items())
+        acc = it.accumulate(recv)
+        d0, d1 = it.rows()
+        covered += d1 - d0
+        it.finalize(acc, per_axis, got[0], 0, shape[0], mask, lab, counts)
+    torch.cuda.synchronize()
+    assert covered == shape[0]
+    assert torch.equal(got, want), (got - want).abs().max().item()
+    assert torch.equal(mask, want_mask) and torch.equal(counts, want_counts)
 
 
 def test_unetr_as_sliding_window_predictor(pkg):

@@ -58,3 +58,47 @@ def test_gradient_allreduce_two_ranks_gloo(tmp_path):
     for p, a, b in zip(net.parameters(), got["bucket"], got["fast"]):
         assert torch.allclose(p.grad, a, atol=1e-6) and torch.allclose(p.grad, b, atol=1e-6)
     assert got["max"] == 2.0
+
+
+def _slab_worker(rank, world, port, out):
+    """Halo exchange of the slab-owned sliding window over gloo: every rank fills its send buffers with (window, row) codes laid out as
+    the plan says and checks that what arrives is exactly the list of pieces the plan promises, in window order."""
+    sys.path.insert(0, ROOT)
+    par = importlib.import_module("3dmedicalimagesegmentation_b200.parallel")
+    inf = importlib.import_module("3dmedicalimagesegmentation_b200.inferers")
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    par.init_from_env("gloo")
+    size, roi = (64, 32, 16), (16, 16, 16)
+    _, flat = inf.window_starts(size, roi, 0.5)
+    chunks, bounds, pieces = inf.slab_plan(flat, roi[0], size[0], world)
+    code = lambda w, x: float(w * 1000 + x)                  # one value per (window, padded row); a piece row carries it `per` times
+    per = 3
+    sends = {}
+    for d in range(rank + 1, world):
+        mine = [p for p in pieces[d] if p[1] == rank]
+        if mine:
+            sends[d] = torch.tensor([code(w, x) for (w, _, lo, hi) in mine for x in range(lo, hi) for _ in range(per)])
+    sizes = {}
+    for (w, src, lo, hi) in pieces[rank]:
+        if src != rank:
+            sizes[src] = sizes.get(src, 0) + (hi - lo) * per
+    recv = inf._exchange_nccl(sends, sizes, "cpu", None)
+    ok = True
+    for src in sizes:
+        want = [code(w, x) for (w, s, lo, hi) in pieces[rank] if s == src for x in range(lo, hi) for _ in range(per)]
+        ok = ok and recv[src].tolist() == want
+    flags = [None] * world
+    dist.all_gather_object(flags, (ok, len(sizes)))
+    if rank == 0:
+        torch.save(flags, out)
+    par.barrier(world)
+    par.shutdown(world)
+
+
+def test_slab_halo_exchange_three_ranks_gloo(tmp_path):
+    out = str(tmp_path / "slab.pt")
+    port = 31000 + os.getpid() % 2000
+    mp.start_processes(_slab_worker, args=(3, port, out), nprocs=3, join=True, start_method="spawn")
+    flags = torch.load(out)
+    assert all(f[0] for f in flags)
+    assert flags[0][1] == 0 and flags[1][1] >= 1 and flags[2][1] >= 1          # data only flows to higher ranks
