@@ -45,9 +45,11 @@ def window_starts(image_size, roi, overlap):
 
 
 def shard_windows(n_items: int, rank: int, world_size: int) -> range:
-    """Contiguous chunk of the ij-ordered window list owned by `rank` (x-slabs)."""
-    per = (n_items + world_size - 1) // world_size
-    return range(min(rank * per, n_items), min((rank + 1) * per, n_items))
+    """Contiguous chunk of the ij-ordered window list owned by `rank` (x-slabs), balanced to within one window: the
+    first `n_items % world_size` ranks take one more.  Every rank gets at least one window when n_items >= world_size."""
+    base, extra = divmod(n_items, world_size)
+    start = rank * base + min(rank, extra)
+    return range(start, start + base + (1 if rank < extra else 0))
 
 
 def slab_plan(flat: Sequence[Tuple[int, int, int]], roi0: int, padded_rows: int, world_size: int):
