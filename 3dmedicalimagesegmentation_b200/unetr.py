@@ -101,7 +101,8 @@ class _UnetrFunction(torch.autograd.Function):
         # the packed bf16 weight copies live in one persistent buffer per device (bf16 mode); they are current when every parameter
         # still has the storage and version counter they were packed from (FusedAdamW keeps them current itself)
         vkey = module._version_key(params)
-        packed = _lib.FLAG_WEIGHTS_PACKED if module._packed_key.get(x.device) == vkey else 0
+        bf16 = module.compute_mode == "bf16"
+        packed = _lib.FLAG_WEIGHTS_PACKED if bf16 and module._packed_key.get(x.device) == vkey else 0
         if needs_grad:
             ws = torch.empty(lib.b200_unetr_workspace_bytes(handle, 1), dtype=torch.uint8, device=x.device)
         else:
@@ -121,7 +122,8 @@ class _UnetrFunction(torch.autograd.Function):
         flags = (0 if freeze_encoder else _lib.FLAG_NEED_ENCODER_GRAD) | packed | (0 if needs_grad else _lib.FLAG_NO_BACKWARD)
         _lib.check(lib.b200_unetr_forward(handle, table, _lib.ptr(x), _lib.ptr(ws), _lib.ptr(enc4), _lib.ptr(logits),
                                           flags, _lib.stream_ptr()), "b200_unetr_forward")
-        module._packed_key[x.device] = vkey
+        if bf16:
+            module._packed_key[x.device] = vkey
         ctx.module, ctx.freeze, ctx.handle = module, bool(freeze_encoder), handle
         ctx.save_for_backward(x, ws, *params)
         ctx.set_materialize_grads(False)
@@ -400,6 +402,7 @@ class UNETR(nn.Module):
                 if buf is None:
                     buf = torch.empty(lib.b200_unetr_packed_bytes(h), dtype=torch.uint8, device=device)
                     self._packed[device] = buf
+                    self._packed_key.pop(device, None)      # a fresh buffer holds nothing yet
                 lib.b200_unetr_set_packed_weights(h, _lib.ptr(buf))
             self._handles[key] = h
         return h

@@ -118,14 +118,16 @@ def run_dp_check(pkg, par, model_kw, dev, rank, world):
     loss_fn(net(xs[rank].to(dev)), ys[rank].to(dev)).backward()
     red.reduce()
     torch.cuda.synchronize()
-    mine = [p.grad.clone() for p in net.parameters()]
+    mine = {n: p.grad.clone() for n, p in net.named_parameters() if p.grad is not None}
     net.zero_grad(set_to_none=True)
     if rank == 0:
         loss_fn(net(torch.cat(xs).to(dev)), torch.cat(ys).to(dev)).backward()
         torch.cuda.synchronize()
         worst, worst_name = 0.0, ""
-        for (name, p), g in zip(net.named_parameters(), mine):
-            e = ((g - p.grad).norm() / p.grad.norm().clamp_min(1e-30)).item()
+        for name, p in net.named_parameters():
+            if p.grad is None:
+                continue
+            e = ((mine[name] - p.grad).norm() / p.grad.norm().clamp_min(1e-30)).item()
             if e > worst:
                 worst, worst_name = e, name
         out["dp_grad_rel_l2_worst"] = worst

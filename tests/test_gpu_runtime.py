@@ -176,3 +176,19 @@ def test_graphed_train_step_matches_eager(pkg):
     with torch.no_grad():
         _, ref = fresh(batches[0][0])
     assert torch.equal(out, ref)
+
+
+def test_mode_switch_repacks(pkg):
+    """fp32-mode calls must not mark the (not yet existing) packed bf16 weights as current: a module that ran in fp32 mode and is then
+    switched to bf16 has to pack on its first bf16 forward."""
+    model = make(pkg, mode="fp32")
+    x, _ = data()
+    with torch.no_grad():
+        model(x)
+        model.set_mode("bf16")
+        _, got = model(x)
+    fresh = make(pkg, seed=11)
+    fresh.load_state_dict(model.state_dict())
+    with torch.no_grad():
+        _, want = fresh(x)
+    assert torch.isfinite(got).all() and torch.equal(got, want)
