@@ -116,8 +116,8 @@ int b200_unetr_backward(void* handle, const float* const* params, float* const* 
 
 void b200_unetr_set_grad_events(void* handle, void* const* events, int n) {
   Handle* h = (Handle*)handle;
-  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-  for (int i = 0; i < n && i < 4; ++i) ev[i] = (cudaEvent_t)events[i];
+  cudaEvent_t ev[13] = {};
+  for (int i = 0; i < n && i < 13; ++i) ev[i] = (cudaEvent_t)events[i];
   h->ex->set_grad_events(ev, n);
 }
 
@@ -142,17 +142,19 @@ int b200_adamw_step(const void* tensors, const void* chunks, int n_chunks, float
                     int step, void* stream) {
   return b200_adamw_step_capturable(tensors, chunks, n_chunks, lr, beta1, beta2, eps, weight_decay, step, nullptr, stream);
 }
-/* dev_step != NULL: the update count is the device int *dev_step, advanced by one before the update (host `step` is ignored): the
- * launch sequence is then identical every step and can be replayed from a CUDA graph. */
+/* dev_step != NULL: the update count is the device int *dev_step, advanced by one before the update when step > 0 (step == 0: a
+ * further launch of the same update, e.g. a later gradient range -- the count is read, not advanced): the launch sequence is then
+ * identical every step and can be replayed from a CUDA graph. */
 int b200_adamw_step_capturable(const void* tensors, const void* chunks, int n_chunks, float lr, float beta1, float beta2, float eps,
                                float weight_decay, int step, int* dev_step, void* stream) {
   B200_CHECK(tensors && chunks && n_chunks > 0 && (step >= 1 || dev_step), "b200_adamw_step: bad arguments");
+  const bool advance = dev_step && step > 0;     // step == 0 with dev_step: a further launch of the same update (a later gradient range)
   AdamHyper h;
   h.lr = lr; h.beta1 = beta1; h.beta2 = beta2; h.eps = eps; h.weight_decay = weight_decay;
   h.bc1 = (float)(1.0 - pow((double)beta1, (double)step));
   h.bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
   h.dev_step = dev_step;
-  if (dev_step) { adam_step_inc_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(dev_step); B200_LAUNCH_CHECK(); }
+  if (advance) { adam_step_inc_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(dev_step); B200_LAUNCH_CHECK(); }
   adamw_kernel<<<n_chunks, 256, 0, (cudaStream_t)stream>>>((const AdamTensor*)tensors, (const AdamChunk*)chunks, h);
   B200_LAUNCH_CHECK();
   return 0;

@@ -684,8 +684,12 @@ struct Exec {
   }
   const float* const* cur_params = nullptr;
   bool no_backward = false;     // FLAG_NO_BACKWARD of the current forward: buffers only the backward reads are not written
-  cudaEvent_t grad_ev[4]; int n_grad_ev = 0;   // see ExecIface::set_grad_events
-  void mark_grads(int k, cudaStream_t st) { if (n_grad_ev == 4) cudaEventRecord(grad_ev[k], st); }
+  // Gradient-ready events (ExecIface::set_grad_events): event 0 = conv stacks + head, event k >= 1 = the k-th group of transformer
+  // blocks from the top (the first also covers vit.norm, the last also the patch embedding).  4 / 7 / 13 events = groups of 4 / 2 / 1
+  // blocks; the deferred parameter-gradient launches (vit_param_grads) use the same grouping.
+  cudaEvent_t grad_ev[13]; int n_grad_ev = 0;
+  int vit_group() const { return n_grad_ev == 13 ? 1 : n_grad_ev == 7 ? 2 : 4; }
+  void mark_grads(int k, cudaStream_t st) { if (k < n_grad_ev) cudaEventRecord(grad_ev[k], st); }
 
   // softmax(Q K^T * scale) V per (batch, head); scores fp32, probabilities T (kept for backward)
   int attention_fwd(int i, float scale, cudaStream_t st) {
@@ -933,6 +937,7 @@ struct Exec {
     // the output gradients and is issued by vit_param_grads() once per gradient group (blocks 8..11 / 4..7 / 0..3): 3 launches per
     // group instead of 36.
     int group_hi = top;
+    const int gs = vit_group();
     for (int i = top; i >= 0; --i) {
       const float* const* bp = P + P_BLK0 + i * B_COUNT;
       const float* xin = i ? w.hs[i - 1] : w.x0;
@@ -955,11 +960,10 @@ struct Exec {
         if (can_split(M, H, 3 * H)) B200_TRY(linear_dgrad_split(w.dqkv[i], 3 * H, w.wqkv[i], M, 3 * H, H, &ss, st));
         else B200_TRY(linear_dgrad<T>(w.dqkv[i], 3 * H, bp[B_QKV_W], w.wqkv[i], M, 3 * H, H, ep_plain<T>(w.dln1[i], H), st));
         B200_TRY(launch_layernorm_bwd<T>(w.dln1[i], xin, w.ln1s[i], bp[B_LN1_W], w.dx2, w.dx, w.dyo[i], nullptr, nullptr, M, H, st, ss.nsplit ? &ss : nullptr)); }
-      if (i == 8 || i == 4 || i == 0) {
+      if (i % gs == 0) {
         B200_TRY(vit_param_grads(G, i, group_hi, st));
         group_hi = i - 1;
-        if (i == 8) mark_grads(1, st);
-        if (i == 4) mark_grads(2, st);
+        if (i) mark_grads((12 - i) / gs, st);      // the last group's event waits for the patch embedding below
       }
     }
     // --- patch embedding: dW = dx0^T rows(x), db = colsum, dpos = sum over batch
@@ -975,7 +979,7 @@ struct Exec {
     }
     if (G[P_PATCH_B]) B200_TRY(launch_colsum<float>(w.dx, G[P_PATCH_B], M, H, st));
     if (G[P_POS]) { batchsum_kernel<<<cdiv((long)L * H, 256), 256, 0, st>>>(w.dx, G[P_POS], B, (long)L * H); B200_LAUNCH_CHECK(); }
-    mark_grads(3, st);
+    mark_grads(12 / gs, st);
     B200_PROFC_END(st);
     return 0;
   }

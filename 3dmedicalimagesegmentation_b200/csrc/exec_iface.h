@@ -17,7 +17,8 @@ struct ExecIface {
                        cudaStream_t st) = 0;
   virtual const void* peek(const char* name, size_t* bytes) = 0;
   // optional: events recorded inside backward() when a group of parameter gradients is final (gradient all-reduce overlap):
-  //   [0] convolutional encoders/decoders + head, [1] vit.norm + blocks 8..11, [2] blocks 4..7, [3] blocks 0..3 + patch embedding
+  //   [0] convolutional encoders/decoders + head, then groups of transformer blocks from the top: n = 4 -> [1] vit.norm + blocks 8..11,
+  //   [2] blocks 4..7, [3] blocks 0..3 + patch embedding; n = 7 -> groups of two blocks; n = 13 -> one block per event
   virtual void set_grad_events(cudaEvent_t* ev, int n) = 0;
   // bf16 mode: caller-owned buffer of packed_bytes() bytes holding the packed bf16 weight copies (see Exec::layout_packed)
   virtual size_t packed_bytes() = 0;

@@ -25,6 +25,6 @@ struct ExecImpl : ExecIface {
     e.layout_packed(packed);
     return e.pack_weights(P, st, false);
   }
-  void set_grad_events(cudaEvent_t* ev, int n) override { e.n_grad_ev = n < 4 ? 0 : 4; for (int i = 0; i < e.n_grad_ev; ++i) e.grad_ev[i] = ev[i]; }
+  void set_grad_events(cudaEvent_t* ev, int n) override { e.n_grad_ev = (n == 4 || n == 7 || n == 13) ? n : 0; for (int i = 0; i < e.n_grad_ev; ++i) e.grad_ev[i] = ev[i]; }
 };
 }  // namespace b200

@@ -6,6 +6,8 @@ Same arithmetic and the same skip rule as torch.optim.AdamW (parameters whose `.
 rely on it), but ONE kernel launch over all parameters instead of torch's multi_tensor_apply passes."""
 from __future__ import annotations
 
+import ctypes
+
 import numpy as np
 import torch
 
@@ -42,23 +44,29 @@ class FusedAdamW(torch.optim.Optimizer):
 
     def _build(self, gi, plist):
         chunk = _lib.load().b200_adamw_chunk()
-        rows, chunks = [], []
+        rows, chunks, gaddr = [], [], []
         mirrors = self._mirror_rows(plist[0].device)
+        # table in gradient-address order: a range of one flat gradient buffer is then a contiguous range of chunks (step(grad_ranges=))
+        plist = sorted(plist, key=lambda q: q.grad.data_ptr())
         for ti, p in enumerate(plist):
             st = self.state[p]
             rows.append((p.data_ptr(), p.grad.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(), p.numel(), mirrors.get(id(p), 0)))
             for s in range(0, p.numel(), chunk):
                 chunks.append((ti, s))
+                gaddr.append(p.grad.data_ptr() + 4 * s)
         tens = np.array(rows, dtype=np.int64)                                   # {p, g, m, v, n, s0}: six 8-byte fields
         ch = np.zeros(len(chunks), dtype=[("t", "<i4"), ("pad", "<i4"), ("s", "<i8")])
         ch["t"] = [c[0] for c in chunks]; ch["s"] = [c[1] for c in chunks]
         dev = plist[0].device
         tens_d = torch.from_numpy(tens.view(np.uint8).reshape(-1)).to(dev)
         ch_d = torch.from_numpy(ch.view(np.uint8).reshape(-1)).to(dev)
-        return tens_d, ch_d, len(chunks)
+        return tens_d, ch_d, len(chunks), np.array(gaddr, dtype=np.int64)
 
     @torch.no_grad()
-    def step(self, closure=None):
+    def step(self, closure=None, grad_ranges=None):
+        """`grad_ranges` (parallel.GradientAllReduce.reduce_and_step): [(work, lo_addr, hi_addr)] -- gradient address ranges in the order
+        their all-reduces were issued.  The update is then launched range by range, each behind its own reduction, so the update of
+        the early groups runs while the last all-reduce is still on the wire."""
         loss = None
         if closure is not None:
             with torch.enable_grad():
@@ -105,9 +113,26 @@ class FusedAdamW(torch.optim.Optimizer):
                         dev_step = (torch.full((1,), s0, dtype=torch.int32, device=sub[0].device), key)
                         self._dev_steps[(gi, si)] = dev_step
                     self._last_cohorts.append(sub)
-                _lib.check(lib.b200_adamw_step_capturable(_lib.ptr(ent[1]), _lib.ptr(ent[2]), ent[3], float(group["lr"]), float(b1), float(b2),
-                                                          float(group["eps"]), float(group["weight_decay"]), s0 + 1,
-                                                          _lib.ptr(dev_step[0]) if dev_step else None, _lib.stream_ptr()), "b200_adamw_step")
+                hyper = (float(group["lr"]), float(b1), float(b2), float(group["eps"]), float(group["weight_decay"]))
+                dptr = _lib.ptr(dev_step[0]) if dev_step else None
+                if grad_ranges:
+                    # chunks outside every range (none in practice) would be skipped: require full cover
+                    done, first = 0, True
+                    for work, lo, hi in grad_ranges:
+                        c0, c1 = int(np.searchsorted(ent[4], lo, "left")), int(np.searchsorted(ent[4], hi, "left"))
+                        if work is not None:
+                            work.wait()
+                        if c1 > c0:
+                            # the device-side update count advances once per step: the first launch advances it (step > 0), the others read it
+                            _lib.check(lib.b200_adamw_step_capturable(_lib.ptr(ent[1]), ctypes.c_void_p(ent[2].data_ptr() + 16 * c0), c1 - c0, *hyper,
+                                                                      s0 + 1 if (first or not dev_step) else 0, dptr, _lib.stream_ptr()), "b200_adamw_step")
+                            first = False
+                            done += c1 - c0
+                    if done != ent[3]:
+                        raise RuntimeError("FusedAdamW.step(grad_ranges=): the ranges do not cover every gradient exactly once")
+                else:
+                    _lib.check(lib.b200_adamw_step_capturable(_lib.ptr(ent[1]), _lib.ptr(ent[2]), ent[3], *hyper, s0 + 1, dptr, _lib.stream_ptr()),
+                               "b200_adamw_step")
                 for p in sub:
                     self.state[p]["step"] = s0 + 1
                 # the kernel wrote through raw pointers: bump the autograd version counters so that everything keyed on them (the

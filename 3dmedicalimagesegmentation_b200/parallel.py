@@ -94,18 +94,39 @@ class GradientAllReduce:
         n = (off - start) // 4
         return torch.as_strided(grads[0], (n,), (1,))
 
+    def reduce_and_step(self, optimizer):
+        """`reduce(); optimizer.step()` with the optimizer update of every gradient group launched behind that group's own all-reduce
+        (optim.FusedAdamW.step(grad_ranges=)): the update of the early groups overlaps the all-reduce of the last one, which has no
+        backward left to hide behind.  Any other optimizer, or a backward that did not record group events: plain reduce + step."""
+        ready = getattr(self.module, "_grad_ready", None)
+        ok = self.world > 1 and ready is not None and self.side is not None and hasattr(optimizer, "advance_host_steps")
+        if ok:
+            flat, groups, views = ready
+            ok = not any(p.grad is None or p.grad.data_ptr() != ptr for p, ptr in views)
+        if not ok:
+            self.reduce()
+            return optimizer.step()
+        self.module._grad_ready = None
+        ranges = []
+        base = flat.data_ptr()
+        with torch.cuda.stream(self.side):
+            for ev, lo, hi in groups:
+                if hi > lo:
+                    self.side.wait_event(ev)
+                    ranges.append((self._avg(flat[lo:hi]), base + 4 * lo, base + 4 * hi))
+        return optimizer.step(grad_ranges=ranges)
+
     def reduce(self):
         if self.world == 1:
             return
         ready = getattr(self.module, "_grad_ready", None)
         if ready is not None and self.side is not None:
-            flat, groups = ready
+            flat, groups, views = ready
             self.module._grad_ready = None
             # the events cover ranges of the autograd node's flat buffer: the averages only reach the parameters if every p.grad
-            # IS a view of it, in order (true when AccumulateGrad stole the views; false under gradient accumulation,
-            # zero_grad(set_to_none=False) or a cloned gradient) -- otherwise take the generic path below
-            view = self._flat_view([p.grad for p in self.params if p.grad is not None])
-            if view is None or view.data_ptr() != flat.data_ptr() or view.numel() != flat.numel():
+            # IS the view of it that the backward handed out (true when AccumulateGrad stole the views; false under gradient
+            # accumulation, zero_grad(set_to_none=False) or a cloned gradient) -- otherwise take the generic path below
+            if any(p.grad is None or p.grad.data_ptr() != ptr for p, ptr in views):
                 ready = None
         if ready is not None and self.side is not None:
             works = []
@@ -118,7 +139,7 @@ class GradientAllReduce:
                 if w is not None:
                     w.wait()              # the current stream waits for the reduction
             return
-        grads = [p.grad for p in self.params if p.grad is not None]
+        grads = sorted((p.grad for p in self.params if p.grad is not None), key=lambda g: g.data_ptr())
         flat = self._flat_view(grads)
         if flat is not None:
             w = self._avg(flat)

@@ -172,23 +172,33 @@ class _UnetrFunction(torch.autograd.Function):
             d_logits = d_logits.contiguous().float()
         if has_de:
             d_enc4 = d_enc4.contiguous().float()
-        # gradient-ready events (data-parallel overlap, parallel.GradientAllReduce): only the full training backward records all
-        # four groups; they cover contiguous ranges of `flat` because it is laid out in parameter order
-        full = has_dl and enc and all(wanted) and x.is_cuda
+        # gradient-ready events (data-parallel overlap, parallel.GradientAllReduce): backward passes through the encoder whose
+        # reachable parameters are all trainable -- the segmentation step and the ranking stages alike -- record one event per
+        # gradient group; the groups cover contiguous ranges of `flat` because it is laid out in parameter order
+        full = enc and x.is_cuda and wanted == list(reach)
         module._grad_ready = None
         if full and module.overlap_grad_reduce:
+            ng = int(module.grad_groups)
+            if ng not in (4, 7, 13):
+                raise ValueError("grad_groups must be 4, 7 or 13 (transformer blocks per gradient group: 4, 2, 1)")
             evs = module._grad_events
-            if evs is None:
-                evs = [torch.cuda.Event() for _ in range(4)]
+            if evs is None or len(evs) != ng:
+                evs = [torch.cuda.Event() for _ in range(ng)]
                 for e in evs:
                     e.record()               # forces creation of the underlying cudaEvent_t
                 module._grad_events = evs
-            arr = (ctypes.c_void_p * 4)(*[e.cuda_event for e in evs])
-            lib.b200_unetr_set_grad_events(ctx.handle, arr, 4)
-            nb = _lib.PARAM_COUNT
-            first = lambda i: sum(p.numel() for p in params[:i])
-            b4, b8, conv0 = first(3 + 4 * 11), first(3 + 8 * 11), first(3 + 12 * 11 + 2)
-            module._grad_ready = (flat, [(evs[0], conv0, total), (evs[1], b8, conv0), (evs[2], b4, b8), (evs[3], 0, b4)])
+            arr = (ctypes.c_void_p * ng)(*[e.cuda_event for e in evs])
+            lib.b200_unetr_set_grad_events(ctx.handle, arr, ng)
+            first = lambda i: sum(p.numel() for p, wnt in zip(params[:i], wanted) if wnt)
+            gs = 12 // (ng - 1)
+            conv0 = first(3 + 12 * 11 + 2)
+            ranges = [(evs[0], conv0, total)]
+            hi = conv0                        # vit.norm rides with the top group
+            for k in range(1, ng):
+                lo = first(3 + (12 - k * gs) * 11) if k < ng - 1 else 0
+                ranges.append((evs[k], lo, hi))
+                hi = lo
+            module._grad_ready = (flat, ranges, [(p, g.data_ptr()) for p, g in zip(params, grads) if g is not None])
         else:
             lib.b200_unetr_set_grad_events(ctx.handle, None, 0)
         _lib.check(lib.b200_unetr_backward(ctx.handle, module._param_table(params), gtab, _lib.ptr(x), _lib.ptr(ws),
@@ -260,6 +270,7 @@ class UNETR(nn.Module):
         self.compute_mode = os.environ.get("B200_UNETR_MODE", "bf16")
         self.inference_graph = False       # see _graph_forward; switched on by sliding_window_inference for its loop
         self.overlap_grad_reduce = False   # set by parallel.GradientAllReduce
+        self.grad_groups = 7               # gradient-ready events per backward when overlapping: conv stack + 6 groups of 2 blocks
         self._init_runtime()
 
     _RUNTIME = ("_handles", "_infer_ws", "_grad_events", "_graphs", "_grad_ready", "_ordered", "_packed", "_packed_key", "_flat_grads")

@@ -244,10 +244,13 @@ def main():
         logits = model(x)
         loss = loss_fn(logits, y)
         loss.backward()
-        if ddp:
-            ddp.reduce()
-        if not args.no_optimizer:
-            opt.step()
+        if ddp and not args.no_optimizer and not args.torch_adamw:
+            ddp.reduce_and_step(opt)      # AdamW of each gradient group behind that group's all-reduce
+        else:
+            if ddp:
+                ddp.reduce()
+            if not args.no_optimizer:
+                opt.step()
         opt.zero_grad(set_to_none=True)
         return loss
 
@@ -434,8 +437,9 @@ def main():
             loss = loss_fn(m128(x128[i % 2]), y128[i % 2])
             loss.backward()
             if d128:
-                d128.reduce()
-            o128.step()
+                d128.reduce_and_step(o128)
+            else:
+                o128.step()
             o128.zero_grad(set_to_none=True)
         for i in range(3):
             step128(i)
@@ -461,8 +465,9 @@ def main():
         class _Opt:                       # BTLoss(reference, similar, dissimilar, optimizer) steps the optimizer itself (rank:213-215)
             def step(self):
                 if rddp:
-                    rddp.reduce()
-                ropt.step()
+                    rddp.reduce_and_step(ropt)
+                else:
+                    ropt.step()
 
             def zero_grad(self, set_to_none=True):
                 ropt.zero_grad(set_to_none=True)

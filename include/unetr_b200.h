@@ -164,15 +164,17 @@ int b200_unetr_pack_convs(void* handle, const float* const* params, void* packed
 long b200_adamw_chunk(void);
 int b200_adamw_step(const void* tensors, const void* chunks, int n_chunks, float lr, float beta1, float beta2, float eps,
                     float weight_decay, int step, void* stream);
-/* dev_step != NULL: the 1-based update count is the device int *dev_step, advanced by one on the stream before the update (the
- * host `step` is ignored) -- every step is then the same launch sequence and can be replayed from a CUDA graph. */
+/* dev_step != NULL: the 1-based update count is the device int *dev_step, advanced by one on the stream before the update when
+ * step > 0 (step == 0: a further launch of the same update over other chunks; the count is read, not advanced) -- every step is
+ * then the same launch sequence and can be replayed from a CUDA graph. */
 int b200_adamw_step_capturable(const void* tensors, const void* chunks, int n_chunks, float lr, float beta1, float beta2, float eps,
                                float weight_decay, int step, int* dev_step, void* stream);
 
-/* Optional gradient-ready events for data-parallel overlap: 4 cudaEvent_t handles recorded inside b200_unetr_backward when a
- * group of parameter gradients is final -- [0] conv encoders/decoders + head, [1] vit.norm + blocks 8..11, [2] blocks 4..7,
- * [3] blocks 0..3 + patch embedding.  n = 0 switches the recording off.  Only a full backward (logits gradient + trainable
- * encoder) records all four. */
+/* Optional gradient-ready events for data-parallel overlap: cudaEvent_t handles recorded inside b200_unetr_backward when a group
+ * of parameter gradients is final -- [0] conv encoders/decoders + head, then groups of transformer blocks from the top; the first
+ * of those also covers vit.norm, the last also the patch embedding.  n = 4: groups of 4 blocks ([1] 8..11, [2] 4..7, [3] 0..3);
+ * n = 7: groups of 2 blocks; n = 13: one block per event.  The deferred weight-gradient launches use the same grouping.  n = 0
+ * switches the recording off.  Only a full backward (logits gradient + trainable encoder) records all of them. */
 void b200_unetr_set_grad_events(void* handle, void* const* events, int n);
 
 /* ---- op-level test hooks (parity tests of single kernels; not part of the reference surface) ---- */
