@@ -30,6 +30,10 @@ class RankGeom(ctypes.Structure):
                 ("channels", c_int32), ("f0", c_int32), ("f1", c_int32), ("idx", c_int32 * 4), ("temperature", c_float)]
 
 
+class AugMap(ctypes.Structure):
+    _fields_ = [("perm", c_int32 * 3), ("flip", c_int32 * 3), ("shift", c_float)]
+
+
 class SwGeom(ctypes.Structure):
     _fields_ = [(n, c_int32) for n in (
         "channels", "d", "h", "w", "pad_d", "pad_h", "pad_w", "padded_d", "padded_h", "padded_w", "roi0", "roi1", "roi2")]
@@ -61,6 +65,12 @@ SIGNATURES = {
     "b200_sw_pack_rows": (c_int, [c_void_p, c_void_p, POINTER(SwGeom), c_int, c_int, c_void_p]),
     "b200_sw_finalize_slab": (c_int, [c_void_p, c_void_p, c_void_p, POINTER(SwGeom), c_int, POINTER(c_int32), c_int, POINTER(c_int32), c_int,
                                       POINTER(c_int32), c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "b200_aug_blocks": (c_int, [c_int64]),
+    "b200_aug_index": (c_int, [c_void_p, c_int, c_void_p, c_int, c_float, c_int64, c_void_p, c_void_p, c_void_p]),
+    "b200_aug_pick_centers": (c_int, [c_void_p, c_int, c_void_p, c_int, c_float, c_int, c_int, c_int, c_void_p, POINTER(c_int64), c_int,
+                                      c_int, c_int, c_int, c_void_p, c_void_p]),
+    "b200_aug_crop": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, POINTER(AugMap), c_int, c_int, c_int, c_int,
+                              c_int, c_void_p, c_void_p, c_void_p]),
     "b200_dicece_sigmoid_forward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p]),
     "b200_dicece_sigmoid_backward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "b200_seg_counts_onehot": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int64, c_void_p, c_void_p]),

@@ -15,6 +15,7 @@
 #include "loss.cuh"
 #include "sliding.cuh"
 #include "metrics.cuh"
+#include "augment.cuh"
 #include "tc_gemm.cuh"
 #include "tc_gemm_grouped.cuh"
 #include "tc_attention.cuh"
@@ -441,6 +442,55 @@ int b200_sw_pack_rows(const float* pred, float* dst, const b200_sw_geom* g, int 
 int b200_sw_finalize(const float* acc, float* out, uint8_t* mask, const b200_sw_geom* g, int batch, const int32_t* s0, int n0,
                      const int32_t* s1, int n1, const int32_t* s2, int n2, void* stream) {
   return b200_sw_finalize_metric(acc, out, mask, g, batch, s0, n0, s1, n1, s2, n2, nullptr, nullptr, stream);
+}
+
+// ---------------------------------------------------------------- GPU-side crop sampling / augmentation
+int b200_aug_blocks(int64_t voxels) { return (int)((voxels + kAugBlock - 1) / kAugBlock); }
+/* prefix: int32[2][b200_aug_blocks(V)] (out: exclusive prefix of the per-block foreground / background counts); totals: int64[2] (device) */
+int b200_aug_index(const float* label, int label_channels, const float* image, int image_channels, float image_threshold, int64_t voxels,
+                   int32_t* prefix, int64_t* totals, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  B200_CHECK(label && label_channels >= 1 && voxels >= 1 && voxels < (1LL << 31) && prefix && totals, "b200_aug_index: bad arguments");
+  const int nblk = b200_aug_blocks(voxels);
+  aug_fgbg_counts_kernel<<<nblk, 256, 0, st>>>(label, label_channels, image, image ? image_channels : 0, image_threshold, voxels, nblk, prefix);
+  B200_LAUNCH_CHECK();
+  aug_prefix_kernel<<<2, 1024, 0, st>>>(prefix, nblk, (long long*)totals);
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+/* picks: n x {use_fg, k} (int64, host); starts: device int32[n][3] receives the crop start of each pick (RandCropByPosNegLabeld) */
+int b200_aug_pick_centers(const float* label, int label_channels, const float* image, int image_channels, float image_threshold, int d, int h,
+                          int w, const int32_t* prefix, const int64_t* picks, int n, int roi0, int roi1, int roi2, int32_t* starts, void* stream) {
+  B200_CHECK(n >= 1 && n <= 16, "b200_aug_pick_centers takes 1..16 picks per call");
+  B200_CHECK(roi0 <= d && roi1 <= h && roi2 <= w, "The size of the proposed random crop ROI is larger than the image size.");
+  AugPicks pk; pk.n = n;
+  for (int i = 0; i < n; ++i) { pk.p[i].use_fg = (int)picks[2 * i]; pk.p[i].k = picks[2 * i + 1]; }
+  AugDims g = {d, h, w, roi0, roi1, roi2};
+  aug_pick_kernel<<<n, 256, 0, (cudaStream_t)stream>>>(label, label_channels, image, image ? image_channels : 0, image_threshold, prefix,
+                                                        b200_aug_blocks((int64_t)d * h * w), pk, g, starts);
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+/* starts: device int32[n][3]; maps: n x {perm[3], flip[3], shift} (host, 7 x 4 bytes each); out_image / out_label may be NULL */
+int b200_aug_crop(const float* image, int image_channels, const float* label, int label_channels, int d, int h, int w, const int32_t* starts,
+                  const b200_aug_map* maps, int n, int roi0, int roi1, int roi2, int brats, float* out_image, float* out_label, void* stream) {
+  B200_CHECK(n >= 1 && n <= 16, "b200_aug_crop takes 1..16 samples per call");
+  B200_CHECK(!brats || label_channels == 1, "the BraTS conversion takes a single-channel label map");
+  AugMaps mp; mp.n = n;
+  for (int i = 0; i < n; ++i) {
+    int seen = 0;
+    for (int a = 0; a < 3; ++a) { mp.m[i].perm[a] = maps[i].perm[a]; mp.m[i].flip[a] = maps[i].flip[a]; if (maps[i].perm[a] >= 0 && maps[i].perm[a] < 3) seen |= 1 << maps[i].perm[a]; }
+    B200_CHECK(seen == 7, "b200_aug_crop: perm of sample %d is not a permutation of the three axes", i);
+    const int ext[3] = {roi0, roi1, roi2};
+    for (int a = 0; a < 3; ++a) B200_CHECK(ext[a] == ext[maps[i].perm[a]], "b200_aug_crop: rot90 of a non-square crop plane changes the crop shape");
+    mp.m[i].shift = maps[i].shift;
+  }
+  AugDims g = {d, h, w, roi0, roi1, roi2};
+  const long per = (long)roi0 * roi1 * roi2;
+  dim3 grid((unsigned)std::max(1L, std::min(148L * 8 / n + 1, (per + 255) / 256)), n);
+  aug_crop_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(image, image_channels, label, label_channels, g, starts, mp, brats, out_image, out_label);
+  B200_LAUNCH_CHECK();
+  return 0;
 }
 
 int b200_unetr_peek(void* handle, const char* name, void* dst, size_t cap) {

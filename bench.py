@@ -102,7 +102,8 @@ def run_dp_check(pkg, par, model_kw, dev, rank, world):
     """Untimed correctness of the two sharded paths on the real hardware (N > 1).
     (a) data parallel, fp32 mode, one crop per rank: rank 0's all-reduced (AVG) gradients against the single-process gradient of
         the concatenated batch (SURVEY 8(d) config 4) -- relative L2 per tensor; the two differ by fp32 summation order only;
-    (b) slab-owned sliding window on a reduced volume (240x192x96, 12 windows): logits + mask against the single-GPU call, with a
+    (b) slab-owned sliding window on a reduced volume (240x240x144: 32 windows, whole sw_batch chunks on 2/4/8 ranks): logits + mask
+        against the single-GPU call, with a
         batch-composition-independent predictor (bit-equality required) and with the UNETR itself (reported: its forward rounds
         differently when a window sits in a different sw_batch chunk, so equality is not a property of the sharding)."""
     import torch.distributed as dist
@@ -137,7 +138,7 @@ def run_dp_check(pkg, par, model_kw, dev, rank, world):
     del red
     par.barrier(world)
 
-    vol = torch.randn(1, 1, 240, 192, 96, generator=torch.Generator().manual_seed(77)).to(dev)
+    vol = torch.randn(1, 1, 240, 240, 144, generator=torch.Generator().manual_seed(77)).to(dev)
     wts = torch.linspace(-1.5, 1.5, 14, device=dev).view(1, 14, 1, 1, 1)
 
     def synth(t):      # elementwise: the value of a voxel does not depend on which windows share its predictor call
@@ -196,6 +197,7 @@ def main():
     ap.add_argument("--breakdown", action="store_true", help="print the per-op CUDA-event breakdown to stderr")
     ap.add_argument("--no-sliding-window", action="store_true", help="skip the configs[4] whole-CT sliding-window measurement")
     ap.add_argument("--graph-dp", action="store_true", help="N > 1: capture the step including the NCCL all-reduces as a CUDA graph")
+    ap.add_argument("--no-augment", action="store_true", help="skip the leg that feeds the step from the GPU-side crop sampler (SURVEY 8f N4)")
     ap.add_argument("--no-dp128", action="store_true", help="skip the configs[3] leg (128^3 crops, 4 per GPU)")
     ap.add_argument("--no-dp-check", action="store_true", help="skip the untimed multi-GPU correctness checks (N > 1)")
     ap.add_argument("--no-ranking", action="store_true", help="skip the configs[2] ranking pre-training step measurement")
@@ -397,6 +399,35 @@ def main():
         for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0]):
             print(f"  {k:34s} {v[0]:9.3f} ms  {v[1]:4d} calls  {100 * v[0] / tot:5.1f}%", file=sys.stderr)
 
+    # the same step fed from a device-resident CT volume by the GPU-side crop sampler + augmentation (seg:341-375):
+    # RandCropByPosNegLabeld (one crop pair per step) + 3 flips + rot90 + intensity shift as one fused gather, then the training step
+    aug = None
+    if not args.no_augment and S == 96:
+        Tm = pkg.transforms
+        gv = torch.Generator().manual_seed(11 + rank)
+        vol_i = torch.rand(1, 320, 320, 192, generator=gv).to(dev)
+        vol_l = (torch.rand(1, 320, 320, 192, generator=gv) < 0.02).float().to(dev) * torch.randint(1, 14, (1, 320, 320, 192), generator=gv).float().to(dev)
+        pipe = Tm.Compose([
+            Tm.RandCropByPosNegLabeld(keys=["image", "label"], label_key="label", spatial_size=(96, 96, 96), pos=1, neg=1, num_samples=B,
+                                      image_key="image", image_threshold=0),
+            Tm.RandFlipd(keys=["image", "label"], spatial_axis=[0], prob=0.10), Tm.RandFlipd(keys=["image", "label"], spatial_axis=[1], prob=0.10),
+            Tm.RandFlipd(keys=["image", "label"], spatial_axis=[2], prob=0.10), Tm.RandRotate90d(keys=["image", "label"], prob=0.10, max_k=3),
+            Tm.RandShiftIntensityd(keys=["image"], offsets=0.10, prob=0.50)]).set_random_state(seed=rank)
+        sample = {"image": vol_i, "label": vol_l}
+
+        def aug_step(i):
+            crops = pipe(sample)
+            return step(torch.stack([c["image"] for c in crops]), torch.stack([c["label"] for c in crops]))
+        for i in range(3):
+            aug_step(i)
+        l0 = lib.b200_launch_count()
+        ms_aug = timed(aug_step, args.steps) / args.steps
+        aug = {"value": B * world / (ms_aug * 1e-3), "unit": "samples/s", "ms_per_step": ms_aug, "steps": args.steps,
+               "sampler_launches_per_step": (lib.b200_launch_count() - l0) // args.steps if gstep is not None else None,
+               "workload": "configs[1] step fed by transforms.Compose([RandCropByPosNegLabeld(num_samples=batch), RandFlipd x3, RandRotate90d, "
+                           "RandShiftIntensityd]) from a device-resident 320x320x192 volume (foreground/background index built once)"}
+        del vol_i, vol_l, pipe, sample
+
     # untimed multi-GPU correctness checks; printed as "dp_check"
     dp_check = None
     if world > 1 and S == 96 and not args.no_dp_check:
@@ -506,7 +537,7 @@ def main():
                 "tflops_algorithmic": samples * flop_per_sample / (ms * 1e-3) / 1e12,
                 "e2e": {"value": samples / (ms_e2e * 1e-3), "unit": "samples/s",
                         "h2d_bytes_per_step": host_x[0].numel() * 4 + host_y[0].numel() * 4, "d2h_bytes_per_step": 4},
-                "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "sliding_window": sw, "ranking_step": rk, "dp_128": dp128, "dp_check": dp_check}
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "sliding_window": sw, "ranking_step": rk, "dp_128": dp128, "augmented_step": aug, "dp_check": dp_check}
         sys.stdout.flush()
         os.write(saved_out, (json.dumps(line) + "\n").encode())
     par.shutdown(world)

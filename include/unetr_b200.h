@@ -137,6 +137,28 @@ int b200_sw_finalize_slab(const float* acc, float* out, uint8_t* mask, const b20
                           const int32_t* s1, int n1, const int32_t* s2, int n2, const float* labels, double* counts,
                           int d0, int nd, int acc_xoff, int acc_rows, int out_d0, int out_rows, void* stream);
 
+/* ---- GPU-side crop sampling and augmentation on a volume resident in device memory: the per-iteration tail of the
+ *      reference's training transforms -- RandCropByPosNegLabeld (seg:341-350), RandFlipd x3 / RandRotate90d / RandShiftIntensityd
+ *      (seg:351-375), RandSpatialCropSamplesd (rank:365-369), ConvertToMultiChannelBasedOnBratsClassesd (seg:65-93).  The random
+ *      draws are made on the host (numpy RandomState streams, as MONAI's Randomizable does); the kernels do everything that touches
+ *      voxels.  image [Ci][D][H][W], label [Cl][D][H][W] fp32.
+ *   b200_aug_index        once per volume: per-block counts + exclusive prefix of the foreground (any label channel != 0) and
+ *                         background (not foreground, and any image channel > threshold; image NULL: not foreground) voxel sets of
+ *                         monai.transforms.utils.map_binary_to_indices -- never materialised as index lists; totals = their sizes
+ *   b200_aug_pick_centers picks[i] = {use_fg, k}: crop start of "the k-th voxel of that set in raster order" (= fg_indices[k]) after
+ *                         correct_crop_centers, written to device memory (no host round trip before the crop)
+ *   b200_aug_crop         n crops in one gather launch; maps[i]: output axis a reads crop axis perm[a], reversed when flip[a] (the
+ *                         composition of the flips and rot90 the host drew), image + shift; brats != 0: label map -> 4 multi-hot
+ *                         channels (background, TC, WT, ET) */
+typedef struct { int32_t perm[3]; int32_t flip[3]; float shift; } b200_aug_map;
+int b200_aug_blocks(int64_t voxels);
+int b200_aug_index(const float* label, int label_channels, const float* image, int image_channels, float image_threshold, int64_t voxels,
+                   int32_t* prefix, int64_t* totals, void* stream);
+int b200_aug_pick_centers(const float* label, int label_channels, const float* image, int image_channels, float image_threshold, int d, int h,
+                          int w, const int32_t* prefix, const int64_t* picks, int n, int roi0, int roi1, int roi2, int32_t* starts, void* stream);
+int b200_aug_crop(const float* image, int image_channels, const float* label, int label_channels, int d, int h, int w, const int32_t* starts,
+                  const b200_aug_map* maps, int n, int roi0, int roi1, int roi2, int brats, float* out_image, float* out_label, void* stream);
+
 /* debug: copy a named workspace buffer of the last forward/backward (device to device, synchronous) */
 int b200_unetr_peek(void* handle, const char* name, void* dst, size_t cap);
 
