@@ -139,8 +139,11 @@ class GradientAllReduce:
                 if w is not None:
                     w.wait()              # the current stream waits for the reduction
             return
-        grads = sorted((p.grad for p in self.params if p.grad is not None), key=lambda g: g.data_ptr())
-        flat = self._flat_view(grads)
+        grads = [p.grad for p in self.params if p.grad is not None]
+        # one covering view if the gradients are consecutive slices of one buffer in ADDRESS order (the UNETR node lays them out in
+        # its own parameter-table order, which is the same on every rank); the bucket path below must keep the rank-independent
+        # parameter order
+        flat = self._flat_view(sorted(grads, key=lambda g: g.data_ptr()))
         if flat is not None:
             w = self._avg(flat)
             if w is not None:
