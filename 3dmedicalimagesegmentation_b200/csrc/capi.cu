@@ -11,6 +11,7 @@
 #include "../../include/unetr_b200.h"
 #include "exec_iface.h"
 #include "elementwise.cuh"
+#include "edge_kernels.cuh"
 #include "adamw.cuh"
 #include "loss.cuh"
 #include "sliding.cuh"
@@ -591,6 +592,86 @@ int b200_trace_tags(char* out, int cap) {
   for (auto& t : g_trace_tags) { int n = snprintf(out + off, cap - off, "%s\n", t.c_str()); if (n < 0 || off + n >= cap) break; off += n; }
   if (cap > 0) out[off < cap ? off : cap - 1] = 0;
   return 0;
+}
+
+// ---------------------------------------------------------------- op-level hooks for the backward element-wise kernels
+// (each kernel of the backward pinned on its own against fp32 torch with an injected upstream gradient: tests/test_gpu_ops_bwd.py)
+}  // extern "C"
+template <class T>
+static int test_layernorm_bwd_t(const void* g, const float* x, const float* stats, const float* gamma, const float* dx_res, float* dx_out,
+                                void* dx_cast, float* dgamma, float* dbeta, int M, int H, cudaStream_t st) {
+  return launch_layernorm_bwd<T>((const T*)g, x, stats, gamma, dx_res, dx_out, (T*)dx_cast, dgamma, dbeta, M, H, st);
+}
+extern "C" {
+/* LayerNorm backward (exec.cuh transformer blocks): g [M,H] (bf16 when bf16 != 0, else fp32), x fp32 [M,H], stats fp32 [M][2] = (mean,
+ * rstd), gamma [H]; dx_out fp32 = dx_res (nullable) + d/dx; dx_cast = the same as T; dgamma / dbeta [H] */
+int b200_test_layernorm_bwd(const void* g, const float* x, const float* stats, const float* gamma, const float* dx_res, float* dx_out,
+                            void* dx_cast, float* dgamma, float* dbeta, int M, int H, int bf16_mode, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  return bf16_mode ? test_layernorm_bwd_t<bf16>(g, x, stats, gamma, dx_res, dx_out, dx_cast, dgamma, dbeta, M, H, st)
+                   : test_layernorm_bwd_t<float>(g, x, stats, gamma, dx_res, dx_out, dx_cast, dgamma, dbeta, M, H, st);
+}
+}  // extern "C"
+template <class T>
+static int test_instnorm_bwd_t(int two, const void* dout, const void* act, const void* ra, const float* mra, const void* rb, const float* mrb,
+                               int N, int C, long V, double* acc, void* da, void* db, cudaStream_t st) {
+  typedef typename RawOf<T>::type TR;
+  constexpr int VN = Vec16<T>::N;
+  B200_CHECK(C % VN == 0 && 256 % (C / VN) == 0, "InstanceNorm channel count %d unsupported", C);
+  ClView pv{C, 0};
+  const size_t red_smem = 256 * 3 * VN * sizeof(float), cst_smem = 6 * (size_t)C * sizeof(float);
+  dim3 gr(in_grid_x(V, C / VN), N), ga(in_grid_x(V, C / VN) * 2, N);
+  B200_CUDA(cudaMemsetAsync(acc, 0, sizeof(double) * 3 * N * C, st));
+  if (two) {
+    B200_CUDA(launch_pdl(in_bwd_reduce_kernel<T, true>, gr, dim3(256), red_smem, st, (const T*)dout, pv, (const T*)act, pv, (const TR*)ra, pv, (const TR*)rb, pv, C, V, acc));
+    B200_LAUNCH_CHECK();
+    B200_CUDA(launch_pdl(in_bwd_fixup_kernel, dim3(cdiv(N * C, 128)), dim3(128), 0, st, acc, mra, mrb, N * C));
+    B200_LAUNCH_CHECK();
+    B200_CUDA(launch_pdl(in_bwd_apply_kernel<T, true>, ga, dim3(256), cst_smem, st, (const T*)dout, pv, (const T*)act, pv, (const TR*)ra, pv, mra, (const TR*)rb, pv, mrb,
+                         C, V, (const double*)acc, (T*)da, pv, (T*)db, pv));
+    B200_LAUNCH_CHECK();
+  } else {
+    B200_CUDA(launch_pdl(in_bwd_reduce_kernel<T, false>, gr, dim3(256), red_smem, st, (const T*)dout, pv, (const T*)act, pv, (const TR*)nullptr, pv, (const TR*)nullptr, pv, C, V, acc));
+    B200_LAUNCH_CHECK();
+    B200_CUDA(launch_pdl(in_bwd_apply_kernel<T, false>, ga, dim3(256), cst_smem, st, (const T*)dout, pv, (const T*)act, pv, (const TR*)nullptr, pv, mra, (const TR*)nullptr, pv,
+                         (const float*)nullptr, C, V, (const double*)acc, (T*)da, pv, (T*)nullptr, pv));
+    B200_LAUNCH_CHECK();
+  }
+  return 0;
+}
+extern "C" {
+/* InstanceNorm(+LeakyReLU) backward of the residual conv block (exec.cuh res_bwd), channels-last [N,V,C]:
+ *  two != 0: out = lrelu(norm(c2) + norm(c3)): dout, act = out (T), ra = c2, rb = c3 (raw conv outputs: fp16 in bf16 mode), mra / mrb
+ *            = (mean, rstd) [N][C][2] -> da = d c2, db = d c3;
+ *  two == 0: act = lrelu(norm(c1)) (T; the normalised value is recovered from it), mra = (mean, rstd) of c1 -> da = d c1.
+ * acc: double [N][C][3] scratch */
+int b200_test_instnorm_bwd(int two, const void* dout, const void* act, const void* ra, const float* mra, const void* rb, const float* mrb,
+                           int N, int C, int64_t V, double* acc, void* da, void* db, int bf16_mode, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  return bf16_mode ? test_instnorm_bwd_t<bf16>(two, dout, act, ra, mra, rb, mrb, N, C, V, acc, da, db, st)
+                   : test_instnorm_bwd_t<float>(two, dout, act, ra, mra, rb, mrb, N, C, V, acc, da, db, st);
+}
+}  // extern "C"
+template <class T, int CO>
+static int test_head_bwd_t(const float* dlogits, const void* d0, const float* Wh, int ncls, int N, long V, void* g, float* dWh, float* dbh, cudaStream_t st) {
+  const long chunk = 2048;
+  dim3 grid((unsigned)((V + chunk - 1) / chunk), N);
+  B200_CUDA(cudaFuncSetAttribute(head_bwd2_kernel<T, CO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+  B200_CUDA(cudaMemsetAsync(dWh, 0, sizeof(float) * ncls * CO, st));
+  B200_CUDA(cudaMemsetAsync(dbh, 0, sizeof(float) * ncls, st));
+  head_bwd2_kernel<T, CO><<<grid, 256, head_bwd2_smem(CO), st>>>(dlogits, (const T*)d0, Wh, ncls, V, chunk, (T*)g, dWh, dbh);
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" {
+/* 1x1x1 head backward (UnetOutBlock, unetr.py:175): dlogits fp32 [N][ncls][V], d0 [N,V,fs] (T) -> g = d(d0) [N,V,fs] (T), dWh [ncls][fs],
+ * dbh [ncls]; fs in {8,16,32}, ncls <= 16 */
+int b200_test_head_bwd(const float* dlogits, const void* d0, const float* Wh, int ncls, int fs, int N, int64_t V, void* g, float* dWh,
+                       float* dbh, int bf16_mode, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  B200_CHECK((fs == 8 || fs == 16 || fs == 32) && ncls >= 1 && ncls <= 16, "b200_test_head_bwd: fs in {8,16,32}, ncls <= 16");
+  if (bf16_mode) return fs == 8 ? test_head_bwd_t<bf16, 8>(dlogits, d0, Wh, ncls, N, V, g, dWh, dbh, st) : fs == 16 ? test_head_bwd_t<bf16, 16>(dlogits, d0, Wh, ncls, N, V, g, dWh, dbh, st) : test_head_bwd_t<bf16, 32>(dlogits, d0, Wh, ncls, N, V, g, dWh, dbh, st);
+  return fs == 8 ? test_head_bwd_t<float, 8>(dlogits, d0, Wh, ncls, N, V, g, dWh, dbh, st) : fs == 16 ? test_head_bwd_t<float, 16>(dlogits, d0, Wh, ncls, N, V, g, dWh, dbh, st) : test_head_bwd_t<float, 32>(dlogits, d0, Wh, ncls, N, V, g, dWh, dbh, st);
 }
 
 void b200_test_set_debug_buffer(void* dev_ptr) { tc::g_dbg = (long long*)dev_ptr; }

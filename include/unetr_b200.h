@@ -210,6 +210,19 @@ int b200_test_tc_conv_fused(const void* x, const void* x2, int Ci, int Co, int N
                             void* out, void* out2, double* stats, double* stats2, void* scratch, void* stream);
 int b200_test_tc_wgrad(const void* x, int x_pitch, int x_coff, int Ci, const void* dy, int dy_pitch, int dy_coff, int Co, int N, int D, int H,
                        int W, int ks, float* dW, void* stream);
+/* op-level hooks for the element-wise kernels of the backward, each pinned on its own against fp32 torch with an injected upstream
+ * gradient (tests/test_gpu_ops_bwd.py).  bf16_mode != 0: activations / gradients are bf16 (raw conv outputs fp16), else fp32.
+ *  layernorm_bwd: g [M,H], x fp32 [M,H], stats fp32 [M][2] = (mean, rstd), gamma [H]; dx_out fp32 = dx_res (nullable) + dL/dx,
+ *                 dx_cast = the same in the activation type, dgamma / dbeta [H]                       (transformer blocks, unetr.py:69-76)
+ *  instnorm_bwd:  channels-last [N,V,C]; two != 0: out = lrelu(norm(c2) + norm(c3)) with ra = c2, rb = c3 -> da = d c2, db = d c3;
+ *                 two == 0: act = lrelu(norm(c1)) -> da = d c1; mra / mrb = (mean, rstd) [N][C][2]; acc: double [N][C][3] scratch
+ *  head_bwd:      dlogits fp32 [N][ncls][V], d0 [N,V,fs] -> g = d(d0), dWh [ncls][fs], dbh [ncls]      (UnetOutBlock, unetr.py:175) */
+int b200_test_layernorm_bwd(const void* g, const float* x, const float* stats, const float* gamma, const float* dx_res, float* dx_out,
+                            void* dx_cast, float* dgamma, float* dbeta, int M, int H, int bf16_mode, void* stream);
+int b200_test_instnorm_bwd(int two, const void* dout, const void* act, const void* ra, const float* mra, const void* rb, const float* mrb,
+                           int N, int C, int64_t V, double* acc, void* da, void* db, int bf16_mode, void* stream);
+int b200_test_head_bwd(const float* dlogits, const void* d0, const float* Wh, int ncls, int fs, int N, int64_t V, void* g, float* dWh,
+                       float* dbh, int bf16_mode, void* stream);
 /* tuning aid: 16 x int64 device buffer receiving CTA-0 clock64 phase stamps of the next tcgen05 GEMM launches (NULL = off) */
 void b200_test_set_debug_buffer(void* dev_ptr);
 /* in-situ trace of the tcgen05 launches of the following calls: buf = device int64[2*cap] pre-filled with (INT64_MAX, 0)
