@@ -16,6 +16,7 @@
 // warp reduction per sample instead of 2*Co shuffled reductions per tile.
 #pragma once
 #include "tc_conv.cuh"
+#include "tc_conv_halo48.cuh"
 
 namespace b200 {
 namespace tc {
@@ -468,6 +469,13 @@ static int conv_halo(const bf16* x, int in_pitch, int in_coff, int Ci, int N, in
   EncodeTiledFn enc = get_encode();
   B200_CHECK(enc, "cuTensorMapEncodeTiled not available from the driver");
   const int mode2 = fu ? fu->mode2 : 0;
+  {  // 16 / 32 output channels: kw taps stacked along N (tc_conv_halo48.cuh), 9 instead of 27 MMAs per k-step
+    Halo48Plan h48 = halo48_plan(Ci, Co, mode2, D, (long)N * cdiv(H, S48_TH) * cdiv(W, S48_TW));
+    if (h48.ok)
+      return conv_halo48(h48, x, in_pitch, in_coff, Ci, N, D, H, W, wp, Co, out, out_pitch, out_coff, accumulate, stats, st, mode2, fu ? fu->wp2 : nullptr,
+                         fu ? fu->out2 : nullptr, fu ? fu->pitch2 : 0, fu ? fu->coff2 : 0, fu ? fu->stats2 : nullptr, fu ? fu->x2 : nullptr,
+                         fu ? fu->x2_pitch : 0, fu ? fu->x2_coff : 0, out_half);
+  }
   HaloPlan h = halo_plan(Ci, Co, mode2, D, (long)N * cdiv(H, HTH) * cdiv(W, HTW));
   B200_CHECK(!mode2 || h.resident, "fused 1x1x1 conv needs resident weights (Ci=%d Co=%d)", Ci, Co);
   HaloParams p;
