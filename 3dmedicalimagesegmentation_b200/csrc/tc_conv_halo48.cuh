@@ -18,7 +18,9 @@
 // output planes per tile) and the same fused 1x1x1 convolution of the residual block:
 //   mode2 == 1 (forward):  second output = centre-tap view (one line + one column in) x W3, N = Co, own accumulator columns
 //   mode2 == 2 (dgrad):    second input tile (16 x 8 voxels, columns 6, 7 unused) x W3^T into the kw = 0 columns
-// Used when Ci in {16, 32, 64} (one channel chunk) and Co in {16, 32}; everything else stays on tc_conv_halo.cuh.
+// Used when Ci in {16, 32, 64} (one channel chunk) and Co = 16 (the full-resolution layers); everything else stays on tc_conv_halo.cuh.
+// Measured on B200, configs[1] (in-situ trace, us per launch): 16 -> 16 @96^3 77.6 -> 61.3, 32 -> 16 @96^3 with the fused 1x1x1 154 -> 88.
+// ncu (profiles/r02_summary.md): the tensor sub-pipe is busy 87 % of the kernel, 96 cycles per 128 x 48 x 16 MMA.
 #pragma once
 #include "tc_conv.cuh"
 
@@ -255,7 +257,11 @@ conv_halo48_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
 struct Halo48Plan { int rb, plane_bytes, halo_bytes, x2_bytes, stage_bytes, stages, w_bytes, op, acc_cols; uint32_t tmem_cols; bool ok; };
 static inline Halo48Plan halo48_plan(int Ci, int Co, int mode2, int D, long tiles_hw_n) {
   Halo48Plan h; memset(&h, 0, sizeof(h));
-  if (!((Ci == 16 || Ci == 32 || Ci == 64) && (Co == 16 || Co == 32))) return h;
+  // Co = 32 (N = 96) was measured no faster than the per-tap kernel (16 -> 32 @96^3 dgrad: 106 vs 87 us): ncu shows the tensor pipe busy
+  // ~42 + 1.1 * N cycles per 128-row MMA at these 32..64-byte operand rows (smem operand fetch), so stacking only pays while N is small.
+  // B200_HALO48_CO32=1 switches it on for experiments.
+  static const bool co32 = getenv("B200_HALO48_CO32") != nullptr;
+  if (!((Ci == 16 || Ci == 32 || Ci == 64) && (Co == 16 || (Co == 32 && co32)))) return h;
   static const bool off = getenv("B200_NO_HALO48") != nullptr;
   if (off) return h;
   h.rb = Ci * 2; h.plane_bytes = S48_HH * S48_HW * h.rb;
