@@ -150,6 +150,7 @@ int b200_adamw_step(const void* tensors, const void* chunks, int n_chunks, float
 int b200_adamw_step_capturable(const void* tensors, const void* chunks, int n_chunks, float lr, float beta1, float beta2, float eps,
                                float weight_decay, int step, int* dev_step, void* stream) {
   B200_CHECK(tensors && chunks && n_chunks > 0 && (step >= 1 || dev_step), "b200_adamw_step: bad arguments");
+  B200_PROF("adamw", (cudaStream_t)stream);
   const bool advance = dev_step && step > 0;     // step == 0 with dev_step: a further launch of the same update (a later gradient range)
   AdamHyper h;
   h.lr = lr; h.beta1 = beta1; h.beta2 = beta2; h.eps = eps; h.weight_decay = weight_decay;
@@ -188,6 +189,7 @@ int b200_dicece_forward(const float* logits, const float* labels, int B, int C, 
   B200_CHECK(C >= 1 && C <= 32, "DiceCE supports 1..32 classes (got %d)", C);
   double* acc = (double*)scratch;
   float* coef = (float*)(acc + (size_t)B * C * 3 + 2);
+  B200_PROF("dicece_fwd", st);
   B200_CUDA(cudaMemsetAsync(acc, 0, sizeof(double) * ((size_t)B * C * 3 + 2), st));
   dim3 g((unsigned)max(1L, min(148L * 8 / B + 1, (long)((V + 255) / 256))), B);
   // measured: the 4-voxel kernels need 184-254 registers and are ~15 % slower than the scalar ones at 14 classes; opt-in only
@@ -210,6 +212,7 @@ int b200_dicece_backward(const float* logits, const float* labels, int B, int C,
   cudaStream_t st = (cudaStream_t)stream;
   B200_CHECK(C >= 1 && C <= 32, "DiceCE supports 1..32 classes (got %d)", C);
   const float* coef = (const float*)((const double*)scratch + (size_t)B * C * 3 + 2);
+  B200_PROF("dicece_bwd", st);
   dim3 g((unsigned)max(1L, min(148L * 8 / B + 1, (long)((V + 255) / 256))), B);
   const bool v4 = getenv("B200_DICE_V4") && V % 4 == 0 && C <= 16 && (((uintptr_t)logits | (uintptr_t)labels | (uintptr_t)dlogits) & 15) == 0;
   dim3 g4((unsigned)max(1L, min(148L * 4 / B + 1, (long)((V / 4 + 255) / 256))), B);

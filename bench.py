@@ -167,15 +167,17 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    batch = 1
+    batch = args.batch          # the GPU arm's per-step batch (configs[1]: 2 crops)
     t = cpu_reference_step_time(batch, args.steps, max(1, min(args.warmup, 1)))
     val = batch / t
     line = {"impl": "reference", "metric": "UNETR 96^3 fwd+bwd samples/s", "value": val, "unit": "samples/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "UNETR(1->14,96^3,fs16,ViT-B) fwd+DiceCE+bwd, CPU fp32, batch 1 per step (bounded sample of configs[1])"},
+            "config": {"workload": f"configs[1]: UNETR(1->14,96^3,fs16,ViT-B) segmentation training step (fwd+DiceCE+bwd), batch {batch}, CPU fp32 "
+                                   "(oracle restatement of the MONAI 0.6.0 path on the host cores; the optimizer step is left out of this arm)",
+                       "global_batch": batch},
             "cpu_baseline": {"value": val, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port",
-                             "sample": f"{args.steps} steps x 1 crop of 96^3, oracle restatement of the MONAI 0.6.0 path, torch {torch.__version__} CPU"},
+                             "sample": f"{args.steps} steps x {batch} crops of 96^3, oracle restatement of the MONAI 0.6.0 path, torch {torch.__version__} CPU"},
             "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -363,10 +365,13 @@ def main():
         if m:     # "k3+k1": the residual block's 1^3 weight gradient formed by the same halo launch (one more tap)
             c = classes[names[2]]; c[0] += v[0]; c[2] += v[1]
             c[1] += v[1] * 2.0 * B * int(m.group(5)) ** 3 * int(m.group(3)) * int(m.group(4)) * (int(m.group(1)) ** 3 + (1 if m.group(2) else 0))
+    # DRAM bytes per launch of the hot kernels: `ncu --set full` captures of tools/prof_kernels.py, summarised by tools/ncu_traffic.py
+    # into profiles/r02_traffic.json together with the git revision of the build that was profiled
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
     except Exception:
         traffic = {}
+    traffic_rev = traffic.get("_git_sha")
     def roof_of(name):
         ms_, fl, n = classes[name]
         r = {"bound": "tensor", "kernel": name, "launches": n, "avg_launch_us": 1e3 * ms_ / n if n else None,
@@ -380,10 +385,31 @@ def main():
         if t:
             r["traffic_of"] = t["launch"]
             r["tensor_pipe_busy"] = t.get("tensor_pipe_busy")
+            r["traffic_build"] = traffic_rev
         return r
     top_class = max(names, key=lambda nme: classes[nme][0])
     roof = roof_of(top_class)
     roof["other_kernels"] = [roof_of(nme) for nme in names if nme != top_class]
+    # HBM-bound kernel classes: algorithmic bytes / CUDA-event time of the same profiled step
+    V0 = float(S) ** 3
+    act = 2 if args.mode == "bf16" else 4
+    n_par = sum(p.numel() for p in model.parameters() if p.requires_grad)
+    n_mir = sum(p.numel() for p in model.parameters() if p.dim() >= 2 and p.numel() >= 768 * 768) if args.mode == "bf16" else 0
+    # InstanceNorm backward of the 5 residual blocks: final norm pair (4 reads + 4 reads + 2 writes) + first norm (2 + 2 + 1) = 15 passes
+    in_bytes = B * 15 * act * sum(v * c for v, c in ((V0, 16), (V0, 16), (V0 / 8, 32), (V0 / 64, 64), (V0 / 512, 128)))
+    hbm_classes = {
+        "adamw_kernel (FusedAdamW: g,p,m,v read; p,m,v written; bf16 mirror of the GEMM weights written)": ("adamw", 28.0 * n_par + 2.0 * n_mir),
+        "dicece_staged_kernel<fwd> (logits + labels read once)": ("dicece_fwd", B * V0 * (4 * 14 + 4)),
+        "dicece_staged_kernel<bwd> (logits + labels read, dlogits written)": ("dicece_bwd", B * V0 * (8 * 14 + 4)),
+        "in_bwd_reduce / in_bwd_apply (InstanceNorm + LeakyReLU backward, 5 residual blocks)": ("instnorm_bwd", in_bytes)}
+    hbm = []
+    for name, (tag, nbytes) in hbm_classes.items():
+        if tag in prof and prof[tag][0] > 0:
+            ms_ = prof[tag][0]
+            hbm.append({"bound": "hbm", "kernel": name, "launches": prof[tag][1], "share_of_step_ms": ms_, "algorithmic_bytes": nbytes,
+                        "achieved": nbytes / (ms_ * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": nbytes / (ms_ * 1e-3) / 1e9 / pk["hbm_gbs"],
+                        "peak_kind": pk_kind + " STREAM-style copy", "timing": "CUDA events around the launches of one step (includes ~4 us of event overhead per launch)"})
+    roof["hbm_kernels"] = hbm
     top = max(prof.items(), key=lambda kv: kv[1][0]) if prof else ("none", (0.0, 0))
     roof["top_op"] = top[0]; roof["top_op_ms"] = top[1][0]
     if args.breakdown and rank == 0:
@@ -523,9 +549,9 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        t = cpu_reference_step_time(1, 2, 1)
+        t = cpu_reference_step_time(1, 5, 1)
         cpu = {"value": 1 / t, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port",
-               "sample": "2 timed steps x 1 crop of 96^3 (fwd+DiceCE+bwd), oracle restatement of the MONAI 0.6.0 path on the host CPU"}
+               "sample": "5 timed steps x 1 crop of 96^3 (fwd+DiceCE+bwd), oracle restatement of the MONAI 0.6.0 path on the host CPU"}
     if rank == 0:
         samples = B * world * args.steps
         line = {"metric": f"UNETR {S}^3 fwd+bwd samples/s", "value": samples / (ms * 1e-3), "unit": "samples/s", "n_gpus": world,
