@@ -12,6 +12,14 @@
 //   D         : nine fp32 accumulators [128 x Co] in TMEM, one per (kd,kh), resident across ALL tiles of the CTA; one
 //               atomic epilogue at the end.
 // Per 128 voxels: 1 + 1 TMA boxes and 72 MMAs (9 (kd,kh) x 8 k-steps of 16 voxels), issued from a fully unrolled loop.
+//
+// kh stacked along N (`stack`, default): these N = 16 MMAs are bound by their fixed issue cost (ncu: tensor pipe 96 % busy at 72 MMAs
+// of 64 x 16 x 16 per tile), so the kh shift is moved from x to dy --
+//       dW[kd,kh,kw] = sum_b x[b + (kd-1, 0, kw-1)] * dy[b - (0, kh-1, 0)]        (b = v + the kh shift; out-of-volume terms are zero)
+// -- and becomes the N-atom index of the B operand exactly as kw is the M-atom index of A: the dy tile is fetched with one halo line
+// above and below (18 x 8 voxels), N-atom i starts i lines further down (LBO = SBO = one line) and holds kh = 2 - i.  x then needs its
+// halo in w and d only (16 x 10 voxels per plane).  One MMA is M x 3*Co x 16 and a tile takes 24 of them instead of 72; the three
+// accumulators (one per kd) are [M x 3*Co].
 #pragma once
 #include "tc_conv_halo.cuh"
 #include "tc_wgrad.cuh"
@@ -24,6 +32,7 @@ struct WgradHaloParams {
   int tiles_w, tiles_h, tiles_per_n, total_tiles;
   int plane_bytes, x_bytes, dy_bytes, stage_bytes, stages; uint32_t tmem_cols;
   float* dW;
+  int stack;                // kh stacked along N (see the header)
   float* dW3;               // optional: weight gradient [Co][Ci] of the residual block's 1x1x1 convolution on the same x (fused: a tenth
                             // accumulator fed by the centre tap and a second dy tile); nullptr = plain 3x3x3 weight gradient
   long long* trace;
@@ -62,7 +71,7 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     // ---- TMA producer
     int stage = 0; uint32_t phase = 0;
     const uint32_t smem_u = smem_u32(smem);
-    const uint32_t tx = (uint32_t)(3 * p.plane_bytes) + (uint32_t)(128 * p.Co * 2) * (p.dW3 ? 2u : 1u);
+    const uint32_t tx = (uint32_t)(3 * p.plane_bytes) + (uint32_t)((p.stack ? 144 : 128) * p.Co * 2) + (p.dW3 ? (uint32_t)(128 * p.Co * 2) : 0u);
     int t = blockIdx.x;
     int n = t / p.tiles_per_n, r = t - n * p.tiles_per_n;
     for (; t < p.total_tiles; t += gridDim.x) {
@@ -71,8 +80,8 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
       if (elect_one()) {
         const uint32_t base = smem_u + (uint32_t)stage * p.stage_bytes;
         mbar_expect_tx(full + stage, tx);
-        tma_load_5d(base, &map_x, full + stage, 0, tw * HTW - 1, th * HTH - 1, d - 1, n);
-        tma_load_5d(base + p.x_bytes, &map_dy, full + stage, 0, tw * HTW, th * HTH, d, n);
+        tma_load_5d(base, &map_x, full + stage, 0, tw * HTW - 1, th * HTH - (p.stack ? 0 : 1), d - 1, n);
+        tma_load_5d(base + p.x_bytes, &map_dy, full + stage, 0, tw * HTW, th * HTH - (p.stack ? 1 : 0), d, n);
         if (p.dW3) tma_load_5d(base + p.x_bytes + p.dy_bytes, &map_dy3, full + stage, 0, tw * HTW, th * HTH, d, n);
       }
       __syncwarp();
@@ -102,7 +111,30 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
       mbar_wait(full + stage, phase);
       tc_fence_after();
       const uint32_t a_st = a_lo0 + (uint32_t)stage * stage_units, b_st = b_lo0 + (uint32_t)stage * stage_units;
-      if (elect_one()) {
+      if (p.stack) {
+        if (elect_one()) {
+          // B: three kh atoms of Co channels, one dy line apart (LBO = SBO = 8 rows)
+          const uint32_t idesc3 = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)((3 * p.Co) >> 3) << 17) | ((MROWS >> 4) << 24);
+          const uint32_t b_st3 = desc_lo(smem_u + (uint32_t)p.x_bytes + (uint32_t)stage * (uint32_t)p.stage_bytes, 8 * b_row_bytes);
+#pragma unroll
+          for (int kd = 0; kd < 3; ++kd) {
+            const uint32_t a_t = a_st + (uint32_t)kd * plane_units;
+            const uint32_t tmem_d = tmem_base + (uint32_t)kd * 3u * co;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              umma_f16(tmem_d, desc64(a_t + (uint32_t)j * A_KSTEP, a_hi), desc64(b_st3 + (uint32_t)j * b_kstep, b_hi), idesc3, j == 0 ? accum : 1u);
+          }
+          if (p.dW3) {   // 1x1x1: centre plane of x against the second dy tile (no halo); the kw = 1 atom is the result
+            const uint32_t a_t = a_st + plane_units;
+            const uint32_t b3 = b_st + ((uint32_t)p.dy_bytes >> 4);
+            const uint32_t tmem_d = tmem_base + 9u * co;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              umma_f16(tmem_d, desc64(a_t + (uint32_t)j * A_KSTEP, a_hi), desc64(b3 + (uint32_t)j * b_kstep, b_hi), idesc, j == 0 ? accum : 1u);
+          }
+          umma_commit(empty + stage);
+        }
+      } else if (elect_one()) {
 #pragma unroll
         for (int kd = 0; kd < 3; ++kd)
 #pragma unroll
@@ -144,8 +176,9 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
           float v[16];
           tmem_ld16(trow + c0, v);
           if (kw < 3) {
+            const int tap3 = p.stack ? (a / 3) * 3 + (2 - a % 3) : a;      // (kd, kh) of this accumulator block
 #pragma unroll
-            for (int j = 0; j < 16; ++j) atomicAdd(p.dW + ((long)(c0 + j) * p.Ci + ci) * 27 + a * 3 + kw, v[j]);
+            for (int j = 0; j < 16; ++j) atomicAdd(p.dW + ((long)(c0 + j) * p.Ci + ci) * 27 + tap3 * 3 + kw, v[j]);
           }
         }
       }
@@ -198,12 +231,14 @@ static int conv_wgrad_halo(const bf16* x, int x_pitch, int x_coff, int Ci, const
   B200_CHECK(total < (1L << 30), "wgrad halo: too many tiles");
   p.total_tiles = (int)total;
   const int rb = Ci * 2;
-  p.plane_bytes = HALO_H * HALO_W * rb;
+  static const bool old_form = getenv("B200_WGRAD_HALO_OLD") != nullptr;
+  p.stack = old_form ? 0 : 1;
+  p.plane_bytes = (p.stack ? HTH : HALO_H) * HALO_W * rb;
   // the junk atoms of the last k-step read up to (128/Ci - 3) voxel rows past the third plane: keep them inside the stage
   p.x_bytes = ((3 * p.plane_bytes + (128 / Ci) * rb + 1023) / 1024) * 1024;
-  p.dy_bytes = ((128 * Co * 2 + 1023) / 1024) * 1024;
+  p.dy_bytes = (((p.stack ? 144 : 128) * Co * 2 + 1023) / 1024) * 1024;      // stack: 18 lines of 8 voxels (one halo line above and below)
   p.dW3 = (dy3 && dW3) ? dW3 : nullptr;
-  p.stage_bytes = p.x_bytes + p.dy_bytes * (p.dW3 ? 2 : 1);
+  p.stage_bytes = p.x_bytes + p.dy_bytes + (p.dW3 ? ((128 * Co * 2 + 1023) / 1024) * 1024 : 0);
   p.stages = (200 * 1024) / p.stage_bytes; if (p.stages > 8) p.stages = 8;
   B200_CHECK(p.stages >= 2, "wgrad halo smem budget exceeded");
   uint32_t cols = (p.dW3 ? 10 : 9) * Co, pw = 32; while (pw < cols) pw <<= 1; p.tmem_cols = pw;
@@ -215,7 +250,7 @@ static int conv_wgrad_halo(const bf16* x, int x_pitch, int x_coff, int Ci, const
     CUtensorMapSwizzle sw = rb == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
     cuuint64_t dims[5] = {(cuuint64_t)Ci, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
     cuuint64_t strides[4] = {(cuuint64_t)x_pitch * 2, (cuuint64_t)W * x_pitch * 2, (cuuint64_t)H * W * x_pitch * 2, (cuuint64_t)D * H * W * x_pitch * 2};
-    cuuint32_t box[5] = {(cuuint32_t)Ci, HALO_W, HALO_H, 3, 1};
+    cuuint32_t box[5] = {(cuuint32_t)Ci, HALO_W, (cuuint32_t)(p.stack ? HTH : HALO_H), 3, 1};
     cuuint32_t es[5] = {1, 1, 1, 1, 1};
     CUresult r = enc(&mx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (void*)(x + x_coff), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -225,7 +260,7 @@ static int conv_wgrad_halo(const bf16* x, int x_pitch, int x_coff, int Ci, const
     CUtensorMapSwizzle sw = Co * 2 == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
     cuuint64_t dims[5] = {(cuuint64_t)Co, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
     cuuint64_t strides[4] = {(cuuint64_t)dy_pitch * 2, (cuuint64_t)W * dy_pitch * 2, (cuuint64_t)H * W * dy_pitch * 2, (cuuint64_t)D * H * W * dy_pitch * 2};
-    cuuint32_t box[5] = {(cuuint32_t)Co, HTW, HTH, 1, 1};
+    cuuint32_t box[5] = {(cuuint32_t)Co, HTW, (cuuint32_t)(p.stack ? HALO_H : HTH), 1, 1};
     cuuint32_t es[5] = {1, 1, 1, 1, 1};
     CUresult r = enc(&mdy, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (void*)(dy + dy_coff), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
