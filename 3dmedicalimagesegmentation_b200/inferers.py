@@ -334,14 +334,28 @@ def _sw_slabs(lib, x, per_axis, flat, roi, size, orig, pad, chan, batch, sw_batc
     full = None
     slab_out = None
     items = [_SlabItem(lib, x, b, flat, roi, size, orig, pad, chan, rank, world, cval) for b in range(batch)]
+    timing = os.environ.get("B200_SW_TIMING")          # tuning aid: CUDA-event time of each phase, printed by every rank to stderr
+    marks = []
+
+    def mark(tag):
+        if timing:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            marks.append((tag, e))
+    mark("start")
     with _graphed(predictor, len(items[0].mine) * batch >= 4 * sw_batch):
         for it in items:
             it.predict(predictor, sw_batch, args, kwargs)
+    mark("predict")
     cout = items[0].cout
     lab, counts = _label_args(labels, x, batch, cout, orig)
     for it in items:
-        recv = exchange(it.pack_sends(), it.recv_sizes(cout))
+        sends = it.pack_sends()
+        mark("pack")
+        recv = exchange(sends, it.recv_sizes(cout))
+        mark("exchange")
         acc = it.accumulate(recv)
+        mark("accumulate")
         d0, d1 = it.rows()
         out = None
         if return_logits and gather_logits:
@@ -372,6 +386,12 @@ def _sw_slabs(lib, x, per_axis, flat, roi, size, orig, pad, chan, batch, sw_batc
                                                     group=group, async_op=True))
         for w in works:
             w.wait()
+    mark("finalize+combine")
+    if timing:
+        import sys
+        torch.cuda.synchronize()
+        print(f"[sliding window rank {rank}] " + "  ".join(f"{b[0]} {a[1].elapsed_time(b[1]):.2f} ms" for a, b in zip(marks, marks[1:])) +
+              f"  (windows {len(items[0].mine)}, slab rows {items[0].x1 - items[0].x0})", file=sys.stderr, flush=True)
     logits = full if full is not None else slab_out
     if counts is not None:
         counts.voxels = orig[0] * orig[1] * orig[2]

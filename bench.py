@@ -236,6 +236,8 @@ def main():
         # one launch; keeps the packed bf16 weights current; update count on the device (graph replay)
         opt = pkg.FusedAdamW(model.parameters(), lr=1e-4, weight_decay=1e-5, mirror=model, capturable=True)
     ddp = par.GradientAllReduce(model, world) if world > 1 else None
+    if os.environ.get("B200_GRAD_GROUPS"):
+        model.grad_groups = int(os.environ["B200_GRAD_GROUPS"])       # tuning aid: 4 / 7 / 13 gradient-ready events per backward
     B = args.batch
     g = torch.Generator().manual_seed(100 + rank)
     # 8 distinct host batches (pinned) cycled through: per-step inputs exceed nothing cached on the device side
