@@ -5,9 +5,8 @@ Window enumeration, padding, scan interval and accumulation order follow MONAI 0
 gather / overlap-add / divide-by-count arithmetic runs in csrc/sliding.cuh.
 
 Multi-GPU (`rank`/`world_size`, one process per GPU): the window list of each volume is cut into contiguous chunks, and
-rank r OWNS the padded rows (first spatial axis) from the first row of its first window up to the first row of rank r+1's first
-window -- an x-slab.  Each rank predicts its windows, sends the rows of those predictions that fall into higher ranks' slabs as
-row-clipped pieces (NCCL send/recv: only halo rows cross NVLink, about one window depth per boundary), adds every piece of its own
+rank r OWNS an equal share of the padded rows (first spatial axis) -- an x-slab.  Each rank predicts its windows, sends the rows of
+those predictions that fall into other ranks' slabs as row-clipped pieces (NCCL send/recv: only halo rows cross NVLink, about one window depth per boundary), adds every piece of its own
 slab in GLOBAL window order (bit-identical to the single-GPU loop, which is MONAI's order), normalises its slab locally, and the
 uint8 mask / validation counts are combined with one small all-reduce.  The logits stay sharded unless the caller asks for them.
 """
@@ -56,22 +55,21 @@ def slab_plan(flat: Sequence[Tuple[int, int, int]], roi0: int, padded_rows: int,
     """Ownership and halo traffic of the slab-owned sliding window for ONE volume (pure host logic; unit-tested on the CPU).
 
     `flat`: window starts in MONAI order (first axis slowest).  Returns (chunks, bounds, pieces):
-      chunks[r]  = range of window indices rank r predicts (contiguous, `shard_windows`);
-      bounds     = world_size + 1 padded-row boundaries: rank r owns rows [bounds[r], bounds[r+1]) (possibly empty);
+      chunks[r]  = range of window indices rank r predicts (contiguous, balanced: `shard_windows`);
+      bounds     = world_size + 1 padded-row boundaries: rank r owns rows [bounds[r], bounds[r+1]) -- EQUAL slabs, so that every
+                   rank accumulates and normalises the same number of rows (cutting at the first window of each chunk instead
+                   leaves 48..128-row slabs at 8 ranks on 512 rows, and the widest one sets the time);
       pieces[d]  = the contributions to rank d's slab in global window order: (window, source rank, x_lo, x_hi) with
-                   [x_lo, x_hi) = that window's rows inside d's slab.  source == d: an own window; source < d: a halo piece.
-    A window only ever reaches forward (into slabs of ranks >= its own), so data flows one way along the rank order."""
+                   [x_lo, x_hi) = that window's rows inside d's slab.  source == d: an own window, otherwise a halo piece.
+    A window reaches at most roi0 rows, i.e. into the slabs next to its own chunk's; traffic flows both ways."""
     n = len(flat)
     chunks = [shard_windows(n, r, world_size) for r in range(world_size)]
-    bounds = [flat[c.start][0] if len(c) else padded_rows for c in chunks] + [padded_rows]
-    bounds[0] = 0
-    for r in range(world_size - 1, -1, -1):          # ranks without windows own nothing: collapse onto the next boundary
-        bounds[r] = min(bounds[r], bounds[r + 1])
+    bounds = [(padded_rows * r) // world_size for r in range(world_size)] + [padded_rows]
     pieces = [[] for _ in range(world_size)]
     for src, ch in enumerate(chunks):
         for w in ch:
             xs = flat[w][0]
-            for d in range(src, world_size):
+            for d in range(world_size):
                 lo, hi = max(xs, bounds[d]), min(xs + roi0, bounds[d + 1])
                 if hi > lo:
                     pieces[d].append((w, src, lo, hi))
@@ -249,7 +247,9 @@ class _SlabItem:
     def pack_sends(self):
         """{dst: flat fp32 buffer} of the row-clipped pieces of own windows that land in dst's slab, in window order."""
         lib, st, out = self.lib, _lib.stream_ptr(), {}
-        for d in range(self.rank + 1, self.world):
+        for d in range(self.world):
+            if d == self.rank:
+                continue
             mine = [p for p in self.pieces[d] if p[1] == self.rank]
             if not mine:
                 continue

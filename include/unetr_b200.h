@@ -121,7 +121,7 @@ int b200_sw_finalize_metric(const float* acc, float* out, uint8_t* mask, const b
                             const float* labels, double* counts, void* stream);
 
 /* ---- slab-owned sliding window (multi-GPU, one process per GPU).  The window list of a volume is cut into contiguous
- * chunks per rank; rank r owns the padded rows from the first row of its first window to the first row of rank r+1's first window.
+ * chunks per rank; rank r owns an equal slab of the padded rows.
  * Contributions that fall into another rank's rows travel there as row-clipped "pieces" (b200_sw_pack_rows -> ncclSend/Recv) and the
  * owner adds all pieces of a voxel in global window order (b200_sw_accumulate_slab), so the result is bit-identical to the
  * single-GPU loop of b200_sw_accumulate_n.  pieces: n x {s0, s1, s2, x_lo, x_hi, nx, xbase} int32 -- window start, the padded rows

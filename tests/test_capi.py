@@ -141,7 +141,7 @@ def test_gradient_reach_table(pkg):
 @pytest.mark.parametrize("size,roi,overlap", [((40, 24, 24), (16, 16, 16), 0.5), ((512, 512, 256), (96, 96, 96), 0.5), ((33, 16, 20), (16, 16, 16), 0.25)])
 def test_slab_plan_reproduces_the_sequential_sum(pkg, world, size, roi, overlap):
     """Host logic of the slab-owned sliding window (inferers.slab_plan), emulated with numpy along the sharded axis only: every padded
-    row has exactly one owner, data only flows to higher ranks, and adding each slab's pieces in plan order gives, bit for bit, the
+    row has exactly one owner, and adding each slab's pieces in plan order gives, bit for bit, the
     float32 sums of the sequential window loop (MONAI's order)."""
     import importlib
     import numpy as np
@@ -167,7 +167,7 @@ def test_slab_plan_reproduces_the_sequential_sum(pkg, world, size, roi, overlap)
     for d in range(world):
         last = -1
         for (w, src, lo, hi) in pieces[d]:
-            assert src <= d and w in chunks[src] and w > last - 1 and bounds[d] <= lo < hi <= bounds[d + 1]
+            assert w in chunks[src] and w > last - 1 and bounds[d] <= lo < hi <= bounds[d + 1]
             last = w
             xs, ys, zs = flat[w]
             for x in range(lo, hi):

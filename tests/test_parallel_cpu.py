@@ -74,7 +74,9 @@ def _slab_worker(rank, world, port, out):
     code = lambda w, x: float(w * 1000 + x)                  # one value per (window, padded row); a piece row carries it `per` times
     per = 3
     sends = {}
-    for d in range(rank + 1, world):
+    for d in range(world):
+        if d == rank:
+            continue
         mine = [p for p in pieces[d] if p[1] == rank]
         if mine:
             sends[d] = torch.tensor([code(w, x) for (w, _, lo, hi) in mine for x in range(lo, hi) for _ in range(per)])
@@ -101,4 +103,4 @@ def test_slab_halo_exchange_three_ranks_gloo(tmp_path):
     mp.start_processes(_slab_worker, args=(3, port, out), nprocs=3, join=True, start_method="spawn")
     flags = torch.load(out)
     assert all(f[0] for f in flags)
-    assert flags[0][1] == 0 and flags[1][1] >= 1 and flags[2][1] >= 1          # data only flows to higher ranks
+    assert all(f[1] >= 1 for f in flags)                                       # every rank receives halo pieces
