@@ -225,6 +225,56 @@ struct EpStore {
 #pragma unroll
     for (int j = 0; j < 16; j += VN) { Vec16<TO> t; for (int i = 0; i < VN; ++i) t.v[i] = v[j + i]; t.store(out + o + j); }
   }
+  // TMA-store epilogue of tc::gemm (tc_gemm.cuh): the final values of 16 consecutive columns of row m -- and, for ACT_GELU_SAVE / preact,
+  // the second output -- are RETURNED instead of stored; the kernel parks them in swizzled smem boxes and the copy engine writes them.
+  // Plain dense outputs only: one batch, no accumulate (the host side of tc::gemm checks).  Split-K launches with partial tiles
+  // (split_stride > 0) return the raw partial sums.  `live` = row m exists (m < M): rows past the edge are clipped by the tensor map.
+  __device__ __forceinline__ void values16(bool live, int m, int n0, const float* acc, float* v, float* pv) const {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = acc[j] * alpha;
+    if (splitk_nbat) return;
+    constexpr int VN = Vec16<TO>::N;
+    const long o = (long)m * ld + n0;
+    if (bias) {
+#pragma unroll
+      for (int j = 0; j < 16; j += 4) { float4 t = *reinterpret_cast<const float4*>(bias + n0 + j); v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w; }
+    }
+    if (act == ACT_GELU_SAVE) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) { float y; gelu_and_grad(v[j], y, pv[j]); v[j] = y; }
+    } else if (preact) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) pv[j] = v[j];
+    }
+    if (act == ACT_GELU) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = gelu_erf(v[j]);
+    } else if (act == ACT_GELU_BWD) {
+      if (live) {
+#pragma unroll
+        for (int j = 0; j < 16; j += VN) { Vec16<TO> t; t.load(usrc + o + j); for (int i = 0; i < VN; ++i) v[j + i] *= gelu_erf_grad(t.v[i]); }
+      }
+    } else if (act == ACT_MUL_SAVED) {
+      if (live) {
+#pragma unroll
+        for (int j = 0; j < 16; j += VN) { Vec16<TO> t; t.load(usrc + o + j); for (int i = 0; i < VN; ++i) v[j + i] *= t.v[i]; }
+      }
+    }
+    if (resid && live) {
+      const float* r = resid + (long)m * ldr + n0;
+#pragma unroll
+      for (int j = 0; j < 16; j += 4) { float4 t = *reinterpret_cast<const float4*>(r + j); v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w; }
+    }
+  }
+  // is this launch a plain dense store the TMA epilogue can take?  (16-byte aligned operands, no batch offsets, no accumulate)
+  bool tma_store_ok(int nbatch) const {
+    auto al = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+    if (nbatch != 1 || accumulate || (splitk_nbat && !split_stride) || (splitk_nbat && splitk_nbat != 1)) return false;
+    if (!al(out) || (ld * sizeof(TO)) % 16 || (preact && !al(preact)) || (usrc && !al(usrc)) || (bias && !al(bias))) return false;
+    if (resid && (!al(resid) || (ldr * 4) % 16)) return false;
+    if (splitk_nbat && (split_stride * 4) % 16) return false;
+    return true;
+  }
   // 4 consecutive columns of row m (coalesced tcgen05 epilogue: 8 lanes cover 32 consecutive columns of one row)
   __device__ __forceinline__ void seg4(int b, int m, int n0, const float* acc, int nvalid) const {
     constexpr uintptr_t AO = 4 * sizeof(TO) - 1;

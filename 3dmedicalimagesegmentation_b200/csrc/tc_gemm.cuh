@@ -113,6 +113,39 @@ __device__ __forceinline__ void tmem_ld16x2(uint32_t taddr, float* v, bool two) 
 
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) { asm volatile("prefetch.tensormap [%0];" ::"l"(m) : "memory"); }
 
+// ---- TMA-store epilogue helpers (bulk tensor stores global <- shared::cta, tracked by bulk async-groups of the issuing thread)
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+// one accumulator row of 32 columns into a [32 rows][32 cols] smem box in the layout the tensor map expects: fp32 rows are 128 B
+// (SWIZZLE_128B: 16-byte chunk ^ (row & 7)), bf16 rows 64 B (SWIZZLE_64B: chunk ^ ((row >> 1) & 3)); both conflict-free per quarter-warp
+__device__ __forceinline__ void stage_row32(uint8_t* box, int row, const float* v, float) {
+  uint8_t* rp = box + row * 128;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) *reinterpret_cast<float4*>(rp + ((j ^ (row & 7)) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+}
+__device__ __forceinline__ void stage_row32(uint8_t* box, int row, const float* v, bf16) {
+  uint8_t* rp = box + row * 64;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    uint4 t;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&t);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[8 * j + 2 * i], v[8 * j + 2 * i + 1]);
+    *reinterpret_cast<uint4*>(rp + ((j ^ ((row >> 1) & 3)) << 4)) = t;
+  }
+}
+// epilogue functors that can hand their values to the TMA-store path (EpStore<TO>, contract.cuh)
+template <class EP> struct ep_tma { static constexpr bool ok = false; typedef float out_t; };
+template <class TO> struct ep_tma<EpStore<TO>> { static constexpr bool ok = true; typedef TO out_t; };
+
 // shared-memory matrix descriptor, SWIZZLE_128B (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30),
 // SBO>>4 [32,46), version=1 [46,48), layout_type=2 [61,64))
 __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -167,22 +200,28 @@ struct Params {
   uint32_t tmem_cols;       // 2*BN rounded to a power of two
   int ksplit, kb_per_split; // split-K: work item = (tile, split); epilogue functor must accumulate atomically
   int coalesce;             // epilogue stores through a per-warp smem transpose (8 lanes x 16 B per row) instead of one row per lane
+  int tma_store;            // epilogue through swizzled smem boxes + cp.async.bulk.tensor stores (plain dense EpStore outputs); 2 = with second output
+  uint32_t stg_bytes;       // staging area of the TMA-store epilogue (between the stage ring and the barriers)
   long long* dbg;           // optional: CTA 0 phase timestamps (clock64) for tuning
   long long* trace;         // optional in-situ (start, end) slot
 };
 
 template <class EP, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(192, 1)
-gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const Params p, const EP ep) {
+gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_o,
+            const __grid_constant__ CUtensorMap map_o2, const Params p, const EP ep) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const uint32_t a_bytes = BM * BK * 2, b_bytes = (uint32_t)p.BN * BK * 2, stage_bytes = a_bytes + b_bytes;
-  uint64_t* full = (uint64_t*)(smem + (size_t)p.stages * stage_bytes);
+  uint8_t* stg_base = smem + (size_t)p.stages * stage_bytes;                 // TMA-store boxes (1024-byte aligned), p.stg_bytes
+  uint64_t* full = (uint64_t*)(stg_base + p.stg_bytes);
   uint64_t* empty = full + p.stages;
   uint64_t* tfull = empty + p.stages;   // [2]
   uint64_t* tempty = tfull + 2;         // [2]
   uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
-  float* stg_all = (float*)(smem + (size_t)p.stages * stage_bytes + 256);   // 4 epilogue warps x 32 rows x 36 floats (EPI_STG_BYTES)
+#ifdef B200_COALESCED_EPILOGUE
+  float* stg_all = (float*)(stg_base + p.stg_bytes + 256);   // 4 epilogue warps x 32 rows x 36 floats (EPI_STG_BYTES)
+#endif
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool dbg = p.dbg && blockIdx.x == 0;
@@ -279,7 +318,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
   } else {
     // ------------------------------------------------ epilogue warps (TMEM lane quarter = warp % 4)
     const int q = warp & 3;
-    int acc = 0; uint32_t acc_phase = 0;
+    int acc = 0; uint32_t acc_phase = 0; int tsb = 0;
     for (long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       long r = t / p.ksplit;
       int tm = (int)(r % p.tiles_m); r /= p.tiles_m; int tn = (int)(r % p.tiles_n); int b = (int)(r / p.tiles_n);
@@ -333,6 +372,43 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         }
       } else {
         bool done = false;
+        if constexpr (ep_tma<EP>::ok) {
+          if (p.tma_store) {
+            // Row-per-lane st.global is what bounds the epilogue of these single-tile GEMMs (measured: 432x3072x768, 128 CTAs: MMAs
+            // done at cycle 9.5 k, kernel end at 17.3 k -- 4 us of scattered 16-byte stores).  Values go through swizzled smem boxes
+            // of 32 rows x 32 columns instead and ONE lane hands each box to the copy engine; two boxes per output alternate.
+            typedef typename ep_tma<EP>::out_t TO;
+            constexpr uint32_t BOX = 32 * 32 * sizeof(TO);
+            const bool two = p.tma_store == 2;
+            uint8_t* wstg = stg_base + (uint32_t)(warp - 2) * (two ? 4u : 2u) * BOX;
+            const int mrow0 = tm * BM + q * 32;
+            const int z = p.ksplit > 1 ? (int)(t % p.ksplit) : 0;
+            for (int c0 = 0; c0 < p.BN; c0 += 32) {
+              float a32[32];
+              tmem_ld16x2(trow + c0, a32, true);
+              const int n0 = tn * p.BN + c0;
+              if (mrow0 < p.M && n0 < p.N) {                 // warp-uniform
+                float v[32], pv[32];
+                ep.values16(m < p.M, m, n0, a32, v, pv);
+                ep.values16(m < p.M, m, n0 + 16, a32 + 16, v + 16, pv + 16);
+                uint8_t* box = wstg + (uint32_t)tsb * BOX;
+                if (lane == 0) bulk_wait_read<1>();           // the group that last read these boxes (two chunks ago) is done
+                __syncwarp();
+                stage_row32(box, lane, v, TO());
+                if (two) stage_row32(box + 2 * BOX, lane, pv, TO());
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                  tma_store_3d(&map_o, smem_u32(box), n0, mrow0, z);
+                  if (two) tma_store_3d(&map_o2, smem_u32(box + 2 * BOX), n0, mrow0, 0);
+                  bulk_commit();
+                }
+                tsb ^= 1;
+              }
+            }
+            done = true;
+          }
+        }
 #ifdef B200_COALESCED_EPILOGUE
         // EXPERIMENT, compiled out (make EXTRA=-DB200_COALESCED_EPILOGUE): measured SLOWER on B200 -- 7.44 vs 6.73 ms/step; in situ the
         // single-tile GEMMs grow by ~5 us each (432x3072x768: 14.1 -> 19.8 us, with the GELU-backward epilogue 19.9 -> 34.9 us).  The
@@ -384,6 +460,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
       if (lane == 0) mbar_arrive(tempty + acc);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (p.tma_store && lane == 0) bulk_wait_read<0>();      // the staging boxes must outlive the bulk stores that read them
   }
   tc_fence_before();
   __syncthreads();
@@ -435,6 +512,31 @@ static int make_map(CUtensorMap* map, const Operand& op, long extent_o, long ext
   return 0;
 }
 
+// row-major [Z][M][N] output of element size `esz` (4: fp32, 2: bf16) as a 3-D tensor map with 32 x 32 boxes for the TMA-store epilogue
+static int make_store_map(CUtensorMap* map, void* out, long M, long N, long ld, long Z, long zstride, int esz) {
+  EncodeTiledFn enc = get_encode();
+  B200_CHECK(enc, "cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t dims[3] = {(cuuint64_t)N, (cuuint64_t)M, (cuuint64_t)(Z > 1 ? Z : 1)};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * esz, (cuuint64_t)(Z > 1 ? zstride : ld * M) * esz};
+  cuuint32_t box[3] = {32u, 32u, 1u};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, esz == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, out, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, esz == 4 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  B200_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (store map) failed with code %d (dims %ld x %ld x %ld, ld %ld)", (int)r, N, M, Z, ld);
+  return 0;
+}
+template <class EP> static inline bool ep_tma_ok(const EP&, int) { return false; }
+template <class TO> static inline bool ep_tma_ok(const EpStore<TO>& ep, int nbatch) { return ep.tma_store_ok(nbatch); }
+template <class EP> static inline int ep_make_store_maps(const EP&, CUtensorMap*, CUtensorMap*, int, int, int) { return 0; }
+template <class TO> static inline int ep_make_store_maps(const EpStore<TO>& ep, CUtensorMap* mo, CUtensorMap* mo2, int M, int N, int ksplit) {
+  B200_TRY(make_store_map(mo, (void*)ep.out, M, N, ep.ld, ep.splitk_nbat ? ksplit : 1, ep.split_stride, (int)sizeof(TO)));
+  if (ep.preact) B200_TRY(make_store_map(mo2, (void*)ep.preact, M, N, ep.ld, 1, 0, (int)sizeof(TO)));
+  return 0;
+}
+template <class EP> static inline bool ep_has_second(const EP&) { return false; }
+template <class TO> static inline bool ep_has_second(const EpStore<TO>& ep) { return ep.preact != nullptr; }
+
 static long long* g_dbg = nullptr;   // set by b200_test_set_debug_buffer
 static int g_num_sms = 0;
 static inline int num_sms() {
@@ -464,9 +566,13 @@ static int gemm(const Operand& A, const Operand& B, const EP& ep, int M, int N, 
   p.a_mn = A.mn_major(); p.b_mn = B.mn_major();
   // N-tile: minimise (waves) x (per-tile cost); per-tile cost ~ k-blocks x rows fetched (L2->SM bound, measured ~2.2 ns per
   // row of 128 B per k-block in situ) + a fixed pipeline fill + the epilogue.  MN-major B is fetched in 64-column boxes.
+  // TMA-store epilogue: plain dense EpStore outputs (one batch, no accumulate, no atomic split-K), 32-column boxes
+  static const bool tma_off = getenv("B200_NO_TMA_STORE") != nullptr;
+  const bool tma_ok = ep_tma<EP>::ok && !tma_off && !allow_splitk && N % 32 == 0 && ep_tma_ok(ep, nb0 * nb1);
   {
     static const int cand_k[] = {32, 48, 64, 80, 96, 112, 128, 160, 192, 224, 256}, cand_mn[] = {64, 128, 192, 256};
-    const int* cand = p.b_mn ? cand_mn : cand_k; const int nc = p.b_mn ? 4 : 11;
+    static const int cand_k32[] = {32, 64, 96, 128, 160, 192, 224, 256};
+    const int* cand = p.b_mn ? cand_mn : (tma_ok ? cand_k32 : cand_k); const int nc = p.b_mn ? 4 : (tma_ok ? 8 : 11);
     const long tm = cdiv(M, BM), nb = (long)nb0 * nb1; const int kbs = cdiv(K, BK);
     double best = 1e30; p.BN = 64;
     for (int i = 0; i < nc; ++i) {
@@ -485,7 +591,10 @@ static int gemm(const Operand& A, const Operand& B, const EP& ep, int M, int N, 
   }
   p.tiles_m = cdiv(M, BM); p.tiles_n = cdiv(N, p.BN); p.nb1 = nb1; p.batches = nb0 * nb1;
   uint32_t stage_bytes = BM * BK * 2 + p.BN * BK * 2;
-  p.stages = (int)((200 * 1024) / stage_bytes); if (p.stages > 8) p.stages = 8;
+  p.tma_store = tma_ok ? (ep_has_second(ep) ? 2 : 1) : 0;
+  p.stg_bytes = tma_ok ? 4u * (p.tma_store == 2 ? 4u : 2u) * 32u * 32u * (uint32_t)sizeof(typename ep_tma<EP>::out_t) : 0u;
+  { const uint32_t avail = 227u * 1024 - 1280 - p.stg_bytes, budget = avail < 200u * 1024 ? avail : 200u * 1024;
+    p.stages = (int)(budget / stage_bytes); if (p.stages > 8) p.stages = 8; }
   { uint32_t c = 32; while (c < (uint32_t)p.BN * 2) c <<= 1; p.tmem_cols = c; }
   CUtensorMap ma, mb;
   B200_TRY(make_map(&ma, A, M, K, BM, nb0, nb1));
@@ -512,16 +621,20 @@ static int gemm(const Operand& A, const Operand& B, const EP& ep, int M, int N, 
 #ifdef B200_COALESCED_EPILOGUE
   static const bool no_coalesce = getenv("B200_NO_COALESCED_EPILOGUE") != nullptr;
   p.coalesce = no_coalesce ? 0 : 1;
-  size_t smem = (size_t)p.stages * stage_bytes + 1024 + 256 + EPI_STG_BYTES;
+  size_t smem = (size_t)p.stages * stage_bytes + p.stg_bytes + 1024 + 256 + EPI_STG_BYTES;
 #else
   p.coalesce = 0;
-  size_t smem = (size_t)p.stages * stage_bytes + 1024 + 256;
+  size_t smem = (size_t)p.stages * stage_bytes + p.stg_bytes + 1024 + 256;
 #endif
+  B200_CHECK(smem <= 227 * 1024, "tcgen05 GEMM smem budget exceeded (%zu)", smem);
+  CUtensorMap mo, mo2;
+  memset(&mo, 0, sizeof(mo)); memset(&mo2, 0, sizeof(mo2));
+  if (p.tma_store) B200_TRY(ep_make_store_maps(ep, &mo, &mo2, M, N, p.ksplit));
   long tiles = (long)p.tiles_m * p.tiles_n * p.batches * p.ksplit;
   int grid = (int)(tiles < num_sms() ? tiles : num_sms());
   cudaError_t le;
-  if (p.a_mn) { if (p.b_mn) le = launch_pdl(gemm_kernel<EP, true, true>, dim3(grid), dim3(192), smem, st, ma, mb, p, ep); else le = launch_pdl(gemm_kernel<EP, true, false>, dim3(grid), dim3(192), smem, st, ma, mb, p, ep); }
-  else { if (p.b_mn) le = launch_pdl(gemm_kernel<EP, false, true>, dim3(grid), dim3(192), smem, st, ma, mb, p, ep); else le = launch_pdl(gemm_kernel<EP, false, false>, dim3(grid), dim3(192), smem, st, ma, mb, p, ep); }
+  if (p.a_mn) { if (p.b_mn) le = launch_pdl(gemm_kernel<EP, true, true>, dim3(grid), dim3(192), smem, st, ma, mb, mo, mo2, p, ep); else le = launch_pdl(gemm_kernel<EP, true, false>, dim3(grid), dim3(192), smem, st, ma, mb, mo, mo2, p, ep); }
+  else { if (p.b_mn) le = launch_pdl(gemm_kernel<EP, false, true>, dim3(grid), dim3(192), smem, st, ma, mb, mo, mo2, p, ep); else le = launch_pdl(gemm_kernel<EP, false, false>, dim3(grid), dim3(192), smem, st, ma, mb, mo, mo2, p, ep); }
   B200_CUDA(le);
   B200_LAUNCH_CHECK();
   return 0;
