@@ -584,7 +584,15 @@ int b200_test_tc_wgrad(const void* x, int x_pitch, int x_coff, int Ci, const voi
   B200_CUDA(cudaMemsetAsync(dW, 0, sizeof(float) * Co * Ci * ks * ks * ks, st));
   if (tc::wgrad_halo_supported(Ci, Co, ks))
     return tc::conv_wgrad_halo((const bf16*)x, x_pitch, x_coff, Ci, (const bf16*)dy, dy_pitch, dy_coff, Co, N, D, H, W, dW, st);
-  return tc::conv_wgrad((const bf16*)x, x_pitch, x_coff, Ci, (const bf16*)dy, dy_pitch, dy_coff, Co, N, D, H, W, ks, dW, st);
+  // the deterministic epilogue needs a scratch buffer for the partial tiles: the hook keeps one (grown on demand, never freed)
+  static float* scratch = nullptr; static size_t scratch_bytes = 0;
+  const size_t need = tc::wgrad_scratch_bytes(Ci, Co, ks, N, D, H, W);
+  if (need > scratch_bytes) {
+    B200_CUDA(cudaStreamSynchronize(st));
+    if (scratch) B200_CUDA(cudaFree(scratch));
+    B200_CUDA(cudaMalloc(&scratch, need)); scratch_bytes = need;
+  }
+  return tc::conv_wgrad((const bf16*)x, x_pitch, x_coff, Ci, (const bf16*)dy, dy_pitch, dy_coff, Co, N, D, H, W, ks, dW, st, scratch, scratch_bytes);
 }
 
 /* in-situ trace of the tcgen05 launches: buf = device int64[2*cap] pre-filled with (INT64_MAX, 0) pairs; null stops tracing */

@@ -76,6 +76,7 @@ struct Workspace {
   // backward scratch
   float *dx, *dx2, *dhs[3], *dP;
   float* part;   // split-K partial tiles [<=4][M][H] (summed by the LayerNorm kernel that consumes the GEMM)
+  float* wg_scratch; size_t wg_scratch_bytes;   // partial tiles of the deterministic weight-gradient epilogue (tc_wgrad.cuh)
   T *unsh;  // unsh: pixel-unshuffled dOut of a transposed conv [rows_in, 8*Co]  // bf16 mode: operand copies of the fp32 residual-stream gradients
   T *dvit, *datt, *dS, *gA, *dcat, *dc2, *dc3, *da1, *dc1;
   // per-block operands of the DEFERRED parameter gradients (weight / bias / LayerNorm-parameter sums are issued per group of blocks,
@@ -208,6 +209,18 @@ struct Exec {
       size_t big = (size_t)B * V[0] * fs;
       w.gA = b.take<T>(big); w.dcat = b.take<T>(2 * big); w.dc2 = b.take<T>(big); w.dc3 = b.take<T>(big);
       w.da1 = b.take<T>(big); w.dc1 = b.take<T>(big); w.unsh = b.take<T>(big);
+      w.wg_scratch_bytes = 0;
+      if constexpr (kTC) {
+        const int lvl_of_blk[5] = {0, 3, 2, 1, 0};
+        for (int i = 0; i < 15; ++i) {
+          int pp, ci, co, ks; conv_desc(i, pp, ci, co, ks);
+          if (!tc::wgrad_supported(ci, co, 8, 0, 8, 0) || tc::wgrad_halo_supported(ci, co, ks)) continue;
+          Sp s = sp(lvl_of_blk[i / 3]);
+          size_t need = tc::wgrad_scratch_bytes(ci, co, ks, s.N, s.D, s.H, s.W);
+          if (need > w.wg_scratch_bytes) w.wg_scratch_bytes = need;
+        }
+      }
+      w.wg_scratch = b.take<float>(w.wg_scratch_bytes / sizeof(float));
       w.bwd_pool = b.take<double>((size_t)kBwdSlots * 3 * B * 8 * fs);
       w.bwd_acc = w.bwd_pool; w.bwd_next = 0;
     }
@@ -403,7 +416,7 @@ struct Exec {
         B200_PROFD(st, "conv_wgrad k%d %dx%d @%d", ks, x.C, dy.C, s.D);
         if (tc::wgrad_halo_supported(x.C, dy.C, ks))
           return tc::conv_wgrad_halo(x.p, x.pitch, x.coff, x.C, dy.p, dy.pitch, dy.coff, dy.C, s.N, s.D, s.H, s.W, dW, st);
-        return tc::conv_wgrad(x.p, x.pitch, x.coff, x.C, dy.p, dy.pitch, dy.coff, dy.C, s.N, s.D, s.H, s.W, ks, dW, st);
+        return tc::conv_wgrad(x.p, x.pitch, x.coff, x.C, dy.p, dy.pitch, dy.coff, dy.C, s.N, s.D, s.H, s.W, ks, dW, st, w.wg_scratch, w.wg_scratch_bytes);
       }
     }
     return simt_conv_wgrad<T>(x, dy, s, ks, dW, st);
