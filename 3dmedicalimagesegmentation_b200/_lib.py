@@ -91,6 +91,8 @@ SIGNATURES = {
     "b200_test_layernorm_bwd": (c_int, [c_void_p] * 9 + [c_int, c_int, c_int, c_void_p]),
     "b200_test_instnorm_bwd": (c_int, [c_int] + [c_void_p] * 6 + [c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "b200_test_head_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "b200_test_tc_conv_dgrad_normbwd": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                                POINTER(c_int), c_void_p, c_void_p]),
     "b200_test_set_debug_buffer": (None, [c_void_p]),
     "b200_adamw_chunk": (ctypes.c_long, []),
     "b200_adamw_step": (c_int, [c_void_p, c_void_p, c_int, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float,

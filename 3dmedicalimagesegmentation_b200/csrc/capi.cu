@@ -554,6 +554,25 @@ int b200_test_tc_conv(const void* x, int in_pitch, int in_coff, int Ci, int N, i
   return tc::conv((const bf16*)x, in_pitch, in_coff, Co, N, D, H, W, wd, Ci, ks, (bf16*)out, out_pitch, out_coff, accumulate, stats, st);
 }
 
+/* dgrad of a 3^3 convolution (dy: [N,D,H,W,Co] bf16 dense, w fp32 [Co][Ci][27] -> out = dx [N,D,H,W,Ci] bf16) with the first pass of the
+ * InstanceNorm + LeakyReLU backward folded into the epilogue: act = lrelu(norm(.)) saved by the forward ([N,D,H,W,Ci] bf16), acc double
+ * [N][Ci][3] receives (sum g, sum g*n, untouched), g = dx * lrelu'(act), n recovered from act.  Returns 0 and *folded = 1 when the kernel
+ * that ran supports the fold (tc_conv_halo48.cuh), *folded = 0 otherwise (acc untouched).  scratch: 2*Co*Ci*27 bf16 */
+int b200_test_tc_conv_dgrad_normbwd(const void* dy, int Co, int Ci, int N, int D, int H, int W, const float* w, const void* act, void* out, double* acc,
+                                    int* folded, void* scratch, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  bf16* wf = (bf16*)scratch; bf16* wd = wf + (size_t)Co * Ci * 27;
+  pack_conv_weights_kernel<<<64, 256, 0, st>>>(w, wf, wd, Co, Ci, 27);
+  B200_LAUNCH_CHECK();
+  B200_CUDA(cudaMemsetAsync(acc, 0, sizeof(double) * 3 * N * Ci, st));
+  bool done = false;
+  tc::HaloNormBwd nb = {(const bf16*)act, Ci, 0, acc, &done};
+  B200_CHECK(tc::conv_halo_supported(Co, Ci), "shape unsupported by the halo conv");
+  B200_TRY(tc::conv_halo((const bf16*)dy, Co, 0, Co, N, D, H, W, wd, Ci, (bf16*)out, Ci, 0, 0, nullptr, st, nullptr, 0, &nb));
+  *folded = done ? 1 : 0;
+  return 0;
+}
+
 /* Fused 3^3 + 1^3 convolution of the residual block (tc_conv_halo.cuh, HaloParams::mode2), dense channels-last bf16 tensors:
  *  mode 1 (forward):  out = conv3(x; w3), out2 = conv1(x; w1), stats / stats2 = per-(n,c) sum and sum of squares   (x has Ci channels)
  *  mode 2 (dgrad):    out = dgrad3(x; w3) + dgrad1(x2; w1)                                  (x, x2 have Co channels, out has Ci)

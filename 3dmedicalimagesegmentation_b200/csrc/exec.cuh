@@ -398,13 +398,15 @@ struct Exec {
     }
     return simt_conv_fwd<T>(x, s, W, Co, ks, out, st);
   }
-  int conv_dgrad(Cl<const T> dy, Sp s, const float* W, int Ci, int ks, Cl<T> dx, int acc, cudaStream_t st) {
+  // nb (bf16 engine only): fold the first pass of the backward of the norm that produced this conv's input into the epilogue
+  int conv_dgrad(Cl<const T> dy, Sp s, const float* W, int Ci, int ks, Cl<T> dx, int acc, cudaStream_t st, const tc::HaloNormBwd* nb = nullptr) {
+    if (nb && nb->done) *nb->done = false;
     if constexpr (kTC) {
       int ci = conv_index(W);
       if (ci >= 0 && tc::conv_supported(dy.C, Ci, dy.pitch, dy.coff, dx.pitch, dx.coff)) {
         B200_PROFD(st, "conv_dgrad k%d %d->%d @%d", ks, dy.C, Ci, s.D);
         if (ks == 3 && tc::conv_halo_supported(dy.C, Ci))
-          return tc::conv_halo(dy.p, dy.pitch, dy.coff, dy.C, s.N, s.D, s.H, s.W, w.wcd[ci], Ci, dx.p, dx.pitch, dx.coff, acc, nullptr, st);
+          return tc::conv_halo(dy.p, dy.pitch, dy.coff, dy.C, s.N, s.D, s.H, s.W, w.wcd[ci], Ci, dx.p, dx.pitch, dx.coff, acc, nullptr, st, nullptr, 0, nb);
         return tc::conv(dy.p, dy.pitch, dy.coff, dy.C, s.N, s.D, s.H, s.W, w.wcd[ci], Ci, ks, dx.p, dx.pitch, dx.coff, acc, nullptr, st);
       }
     }
@@ -517,12 +519,24 @@ struct Exec {
     Cl<const T> dc2 = cl<const T>(w.dc2, Co, 0, Co), dc3 = cl<const T>(w.dc3, Co, 0, Co), a1 = cl<const T>(r.a1, Co, 0, Co);
     // conv2
     if (dW2) { B200_TRY(zero_grad(dW2, (size_t)Co * Co * 27, st)); B200_TRY(conv_wgrad(a1, dc2, s, 3, dW2, st)); }
-    B200_TRY(conv_dgrad(dc2, s, W2, Co, 3, cl(w.da1, Co, 0, Co), 0, st));
-    // lrelu + norm1
-    { B200_PROF("instnorm_bwd", st);
+    // lrelu + norm1: the reduction pass (sum g, sum g*n) rides on the dgrad epilogue where the kernel supports it (tc_conv_halo48.cuh)
     B200_TRY(next_bwd());
+    bool folded = false;
+    if constexpr (kTC) {
+      // MEASURED SLOWER on B200 (configs[1]: 5.34 ms/step folded vs 5.21 ms with the separate reduction pass): the dgrad kernel is tensor-bound
+      // with its epilogue hidden behind the next tile's MMAs, and the extra 32-byte global load per row in the epilogue un-hides it (the
+      // saved 2 x 30 us of in_bwd_reduce cost 2 x 95 us in the convolution).  Kept as an opt-in experiment (B200_NORM_FOLD=1) with its
+      // op-level test (tests/test_gpu_tcconv.py).
+      static const bool fold = getenv("B200_NORM_FOLD") != nullptr;
+      tc::HaloNormBwd nb = {reinterpret_cast<const bf16*>(r.a1), Co, 0, w.bwd_acc, &folded};
+      B200_TRY(conv_dgrad(dc2, s, W2, Co, 3, cl(w.da1, Co, 0, Co), 0, st, fold ? &nb : nullptr));
+    } else {
+      B200_TRY(conv_dgrad(dc2, s, W2, Co, 3, cl(w.da1, Co, 0, Co), 0, st));
+    }
+    { B200_PROF("instnorm_bwd", st);
+    if (!folded) {
     B200_CUDA(launch_pdl(in_bwd_reduce_kernel<T, false>, dim3(gr), dim3(256), red_smem, st, w.da1, pv, r.a1, pv, (const TR*)nullptr, pv, (const TR*)nullptr, pv, Co, Vs, w.bwd_acc));
-    B200_LAUNCH_CHECK();
+    B200_LAUNCH_CHECK(); }
     B200_CUDA(launch_pdl(in_bwd_apply_kernel<T, false>, dim3(ga), dim3(256), cst_smem, st, w.da1, pv, r.a1, pv, (const TR*)nullptr, pv, r.mr1, (const TR*)nullptr, pv, nullptr, Co, Vs, w.bwd_acc,
                                                w.dc1, pv, nullptr, pv));
     B200_LAUNCH_CHECK(); }

@@ -458,6 +458,9 @@ static int conv_halo_launch(const CUtensorMap& mx, const CUtensorMap& mw, const 
 }
 
 // 3x3x3 only.  wp: packed bf16 [27][Co][Ci] (same packing as tc::conv).
+// optional (dgrad of a conv whose input was a = lrelu(norm(c))): the first pass of that norm's backward rides on the epilogue -- `acc`
+// ([N][C][3] doubles, zeroed) receives (sum g, sum g*n); *done tells the caller whether the kernel that ran supports it
+struct HaloNormBwd { const bf16* act; int pitch, coff; double* acc; bool* done; };
 struct HaloFused {   // optional fused 1x1x1 conv (see HaloParams::mode2); wp2: packed bf16 [Co][Ci]
   int mode2; const bf16* wp2;
   bf16* out2; int pitch2, coff2; double* stats2;          // mode2 == 1
@@ -465,16 +468,21 @@ struct HaloFused {   // optional fused 1x1x1 conv (see HaloParams::mode2); wp2: 
 };
 static int conv_halo(const bf16* x, int in_pitch, int in_coff, int Ci, int N, int D, int H, int W, const bf16* wp, int Co,
                      bf16* out, int out_pitch, int out_coff, int accumulate, double* stats, cudaStream_t st, const HaloFused* fu = nullptr,
-                     int out_half = 0) {
+                     int out_half = 0, const HaloNormBwd* nb = nullptr) {
+  if (nb && nb->done) *nb->done = false;
   EncodeTiledFn enc = get_encode();
   B200_CHECK(enc, "cuTensorMapEncodeTiled not available from the driver");
   const int mode2 = fu ? fu->mode2 : 0;
   {  // 16 / 32 output channels: kw taps stacked along N (tc_conv_halo48.cuh), 9 instead of 27 MMAs per k-step
     Halo48Plan h48 = halo48_plan(Ci, Co, mode2, D, (long)N * cdiv(H, S48_TH) * cdiv(W, S48_TW));
-    if (h48.ok)
-      return conv_halo48(h48, x, in_pitch, in_coff, Ci, N, D, H, W, wp, Co, out, out_pitch, out_coff, accumulate, stats, st, mode2, fu ? fu->wp2 : nullptr,
-                         fu ? fu->out2 : nullptr, fu ? fu->pitch2 : 0, fu ? fu->coff2 : 0, fu ? fu->stats2 : nullptr, fu ? fu->x2 : nullptr,
-                         fu ? fu->x2_pitch : 0, fu ? fu->x2_coff : 0, out_half);
+    if (h48.ok) {
+      const bool fold = nb && !stats && !mode2 && !accumulate && (nb->pitch % 8 == 0) && (nb->coff % 8 == 0);
+      if (fold && nb->done) *nb->done = true;
+      return conv_halo48(h48, x, in_pitch, in_coff, Ci, N, D, H, W, wp, Co, out, out_pitch, out_coff, accumulate, fold ? nb->acc : stats, st, mode2,
+                         fu ? fu->wp2 : nullptr, fu ? fu->out2 : nullptr, fu ? fu->pitch2 : 0, fu ? fu->coff2 : 0, fu ? fu->stats2 : nullptr,
+                         fu ? fu->x2 : nullptr, fu ? fu->x2_pitch : 0, fu ? fu->x2_coff : 0, out_half, fold ? nb->act : nullptr, fold ? nb->pitch : 0,
+                         fold ? nb->coff : 0);
+    }
   }
   HaloPlan h = halo_plan(Ci, Co, mode2, D, (long)N * cdiv(H, HTH) * cdiv(W, HTW));
   B200_CHECK(!mode2 || h.resident, "fused 1x1x1 conv needs resident weights (Ci=%d Co=%d)", Ci, Co);

@@ -36,6 +36,10 @@ struct Halo48Params {
   int acc_cols; uint32_t tmem_cols;
   bf16* out; int pitch, coff, accumulate; double* stats; int out_half;
   int mode2; bf16* out2; int pitch2, coff2; double* stats2;
+  // Backward-norm sums in the dgrad epilogue (stats != null, gact != null): the output IS the gradient wrt a = lrelu(norm(c)); with the
+  // saved activation row the epilogue accumulates Sg = sum g and Sgn = sum g*n (g = out * lrelu'(a), n recovered from a) instead of
+  // sum x / sum x^2 -- the first pass of the InstanceNorm backward (in_bwd_reduce_kernel<false>) without reading the tensor again.
+  const bf16* gact; int gact_pitch, gact_coff; int stats_stride;
   long long* trace;
 };
 
@@ -177,7 +181,7 @@ conv_halo48_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         if (e < 2 * CO_T) {
           float tot = red[e] + red[2 * CO_T + e] + red[4 * CO_T + e] + red[6 * CO_T + e];
           int c = e % CO_T, which = e / CO_T;
-          atomicAdd(sp + ((long)nn * CO_T + c) * 2 + which, (double)tot);
+          atomicAdd(sp + ((long)nn * CO_T + c) * p.stats_stride + which, (double)tot);
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");
       }
@@ -213,8 +217,20 @@ conv_halo48_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
             }
             if (valid) {
               if (sp) {
+                if (p.gact && ps == 0) {
+                  Vec16<bf16> a0, a1;
+                  const bf16* ar = p.gact + vox * p.gact_pitch + p.gact_coff + c0;
+                  a0.load(ar); a1.load(ar + 8);
 #pragma unroll
-                for (int j = 0; j < 16; ++j) { rs1[ps][c0 + j] += v[j]; rs2[ps][c0 + j] = fmaf(v[j], v[j], rs2[ps][c0 + j]); }
+                  for (int j = 0; j < 16; ++j) {
+                    const float a = j < 8 ? a0.v[j] : a1.v[j - 8];
+                    const float g = v[j] * (a > 0.f ? 1.f : 0.01f), nn = a > 0.f ? a : a * 100.f;
+                    rs1[ps][c0 + j] += g; rs2[ps][c0 + j] = fmaf(g, nn, rs2[ps][c0 + j]);
+                  }
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) { rs1[ps][c0 + j] += v[j]; rs2[ps][c0 + j] = fmaf(v[j], v[j], rs2[ps][c0 + j]); }
+                }
               }
               if (p.accumulate && ps == 0) {
                 Vec16<bf16> a, b; a.load(dst + c0); b.load(dst + c0 + 8);
@@ -298,7 +314,8 @@ static int conv_halo48_launch(const CUtensorMap& mx, const CUtensorMap& mw, cons
 // same contract as tc::conv_halo (tc_conv_halo.cuh); mode2 / wp2 / out2 / x2 describe the fused 1x1x1 convolution
 static int conv_halo48(const Halo48Plan& h, const bf16* x, int in_pitch, int in_coff, int Ci, int N, int D, int H, int W, const bf16* wp, int Co,
                        bf16* out, int out_pitch, int out_coff, int accumulate, double* stats, cudaStream_t st, int mode2, const bf16* wp2,
-                       bf16* out2, int pitch2, int coff2, double* stats2, const bf16* x2, int x2_pitch, int x2_coff, int out_half) {
+                       bf16* out2, int pitch2, int coff2, double* stats2, const bf16* x2, int x2_pitch, int x2_coff, int out_half,
+                       const bf16* gact = nullptr, int gact_pitch = 0, int gact_coff = 0) {
   EncodeTiledFn enc = get_encode();
   B200_CHECK(enc, "cuTensorMapEncodeTiled not available from the driver");
   Halo48Params p; memset(&p, 0, sizeof(p));
@@ -312,6 +329,7 @@ static int conv_halo48(const Halo48Plan& h, const bf16* x, int in_pitch, int in_
   p.total_tiles = (int)total;
   p.out = out; p.pitch = out_pitch; p.coff = out_coff; p.accumulate = accumulate; p.stats = stats; p.out_half = out_half;
   p.mode2 = mode2; p.out2 = out2; p.pitch2 = pitch2; p.coff2 = coff2; p.stats2 = stats2;
+  p.gact = gact; p.gact_pitch = gact_pitch; p.gact_coff = gact_coff; p.stats_stride = gact ? 3 : 2;
   p.trace = trace_slot(); if (p.trace) trace_tag("conv_halo48 %d->%d @%d mode2=%d", Ci, Co, D, mode2);
   const CUtensorMapSwizzle sw = h.rb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (h.rb == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
   CUtensorMap mx, mw, mx2, mw2;

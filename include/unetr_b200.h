@@ -223,6 +223,11 @@ int b200_test_instnorm_bwd(int two, const void* dout, const void* act, const voi
                            int N, int C, int64_t V, double* acc, void* da, void* db, int bf16_mode, void* stream);
 int b200_test_head_bwd(const float* dlogits, const void* d0, const float* Wh, int ncls, int fs, int N, int64_t V, void* g, float* dWh,
                        float* dbh, int bf16_mode, void* stream);
+/* dgrad of a 3^3 convolution with the first pass of the InstanceNorm + LeakyReLU backward folded into its epilogue (res_bwd, exec.cuh):
+ * dy [N,D,H,W,Co] bf16, w fp32 [Co][Ci][27], act = the saved activation lrelu(norm(.)) [N,D,H,W,Ci] bf16 -> out = dx bf16, acc double
+ * [N][Ci][3] = (sum g, sum g*n, -); *folded = 0 when the kernel that ran does not fold (acc untouched).  scratch: 2*Co*Ci*27 bf16 */
+int b200_test_tc_conv_dgrad_normbwd(const void* dy, int Co, int Ci, int N, int D, int H, int W, const float* w, const void* act, void* out,
+                                    double* acc, int* folded, void* scratch, void* stream);
 /* tuning aid: 16 x int64 device buffer receiving CTA-0 clock64 phase stamps of the next tcgen05 GEMM launches (NULL = off) */
 void b200_test_set_debug_buffer(void* dev_ptr);
 /* in-situ trace of the tcgen05 launches of the following calls: buf = device int64[2*cap] pre-filled with (INT64_MAX, 0)

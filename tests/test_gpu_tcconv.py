@@ -152,3 +152,41 @@ def test_conv_halo_fused_1x1(pkg, monkeypatch, op, Ci, Co):
     torch.cuda.synchronize()
     want = F.conv_transpose3d(d1.float(), w3.to(torch.bfloat16).float(), padding=1) + F.conv_transpose3d(d3.float(), w1.to(torch.bfloat16).float())
     assert ((ncdhw(dx) - want).abs().max() / want.abs().max()).item() <= 2 ** -7
+
+
+@pytest.mark.parametrize("Ci,Co,dims", [(16, 16, (12, 16, 12)), (16, 32, (8, 16, 18)), (32, 16, (8, 16, 18)), (16, 16, (8, 20, 24))])
+def test_conv_dgrad_with_folded_norm_backward_sums(pkg, Ci, Co, dims):
+    """The dgrad of a 3^3 convolution whose input was a = lrelu(norm(c)) accumulates the first pass of that norm's backward in its
+    epilogue (tc_conv_halo48.cuh): sum g and sum g*n per (sample, channel), g = dx * lrelu'(a), n recovered from a.  Against torch fp64 on
+    the same bf16 operands: the sums are formed from the fp32 accumulators (before the bf16 rounding of dx): 2e-3 relative to the sum of |terms|."""
+    import ctypes
+    lib = pkg._lib.load()
+    g = torch.Generator().manual_seed(Ci + Co + dims[0])
+    N = 2
+    dy = torch.randn(N, Co, *dims, generator=g).to(torch.bfloat16)
+    w = torch.randn(Co, Ci, 3, 3, 3, generator=g) / (Co * 27) ** 0.5
+    act = torch.nn.functional.leaky_relu(torch.randn(N, Ci, *dims, generator=g), 0.01).to(torch.bfloat16)
+    dx = F.conv_transpose3d(dy.double(), w.to(torch.bfloat16).double(), padding=1)
+    a = act.double()
+    gg = dx * torch.where(a > 0, 1.0, 0.01)
+    nn_ = torch.where(a > 0, a, a * 100.0)
+    want = torch.stack([gg.sum((2, 3, 4)), (gg * nn_).sum((2, 3, 4))], -1)
+    scale = torch.stack([gg.abs().sum((2, 3, 4)), (gg * nn_).abs().sum((2, 3, 4))], -1)
+    cl = lambda t: t.permute(0, 2, 3, 4, 1).contiguous().to(DEV)
+    dy_cl, act_cl = cl(dy), cl(act)
+    out = torch.empty(N, *dims, Ci, dtype=torch.bfloat16, device=DEV)
+    acc = torch.full((N, Ci, 3), 7.0, dtype=torch.float64, device=DEV)
+    scratch = torch.empty(2 * w.numel(), dtype=torch.bfloat16, device=DEV)
+    folded = ctypes.c_int(-1)
+    pkg._lib.check(lib.b200_test_tc_conv_dgrad_normbwd(pkg._lib.ptr(dy_cl), Co, Ci, N, *dims, pkg._lib.ptr(w.to(DEV)), pkg._lib.ptr(act_cl), pkg._lib.ptr(out),
+                                                        pkg._lib.ptr(acc), ctypes.byref(folded), pkg._lib.ptr(scratch), pkg._lib.stream_ptr()), "dgrad_normbwd")
+    torch.cuda.synchronize()
+    got_dx = out.float().permute(0, 4, 1, 2, 3).cpu()
+    assert ((got_dx - dx.float()).abs().max() / dx.abs().max()).item() <= 2 ** -7
+    if Ci == 16:                      # the output-channel count the stacked kernel takes
+        assert folded.value == 1
+        err = ((acc[..., :2].cpu() - want).abs() / scale).max().item()
+        assert err <= 2e-3, err
+        assert (acc[..., 2] == 0).all()
+    else:
+        assert folded.value == 0 and (acc == 0).all()
