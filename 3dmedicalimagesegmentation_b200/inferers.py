@@ -222,7 +222,20 @@ class _SlabItem:
         self.gout = None
         self.cout = None
 
-    def predict(self, predictor, sw_batch, args, kwargs):
+    # The halo exchange is cut into ROUNDS so that it overlaps the prediction loop: the pieces of the windows in the j-th part of a
+    # rank's chunk travel as soon as that part is predicted (NCCL runs them on its own stream); only the last round is exposed.
+    ROUNDS = 4
+
+    def round_of(self, w, src):
+        ch = self.chunks[src]
+        return min(self.ROUNDS - 1, (w - ch.start) * self.ROUNDS // max(len(ch), 1))
+
+    def round_end(self, j):
+        """number of own windows that must be predicted before round j can be sent"""
+        n = len(self.mine)
+        return n if j >= self.ROUNDS - 1 else max(i for i in range(n + 1) if i == 0 or self.round_of(self.mine.start + i - 1, self.rank) <= j)
+
+    def predict(self, predictor, sw_batch, args, kwargs, after_call=None):
         lib, st = self.lib, _lib.stream_ptr()
         for g0 in range(self.mine.start, self.mine.stop, sw_batch):
             ws = range(g0, min(g0 + sw_batch, self.mine.stop))
@@ -240,17 +253,20 @@ class _SlabItem:
             # every prediction is kept until the halo pieces of the lower ranks have arrived: a voxel's additions must happen in
             # global window order, and those pieces come first
             self.preds[g0 - self.mine.start:g0 - self.mine.start + n].copy_(pred)
+            if after_call is not None:
+                after_call(self, g0 - self.mine.start + n)
 
     def piece_elems(self, lo, hi):
         return self.cout * (hi - lo) * self.roi[1] * self.roi[2]
 
-    def pack_sends(self):
-        """{dst: flat fp32 buffer} of the row-clipped pieces of own windows that land in dst's slab, in window order."""
+    def pack_sends(self, rnd=None):
+        """{dst: flat fp32 buffer} of the row-clipped pieces of own windows (of exchange round `rnd`; None = all) that land in dst's
+        slab, in window order."""
         lib, st, out = self.lib, _lib.stream_ptr(), {}
         for d in range(self.world):
             if d == self.rank:
                 continue
-            mine = [p for p in self.pieces[d] if p[1] == self.rank]
+            mine = [p for p in self.pieces[d] if p[1] == self.rank and (rnd is None or self.round_of(p[0], self.rank) == rnd)]
             if not mine:
                 continue
             buf = torch.empty(sum(self.piece_elems(lo, hi) for _, _, lo, hi in mine), dtype=torch.float32, device=self.x.device)
@@ -262,16 +278,17 @@ class _SlabItem:
             out[d] = buf
         return out
 
-    def recv_sizes(self, cout):
-        """{src: element count} this rank receives (cout known to every rank: same predictor)."""
+    def recv_sizes(self, cout, rnd=None):
+        """{src: element count} this rank receives (in exchange round `rnd`; None = all); cout is known to every rank: same predictor"""
         out = {}
         for w, src, lo, hi in self.pieces[self.rank]:
-            if src != self.rank:
+            if src != self.rank and (rnd is None or self.round_of(w, src) == rnd):
                 out[src] = out.get(src, 0) + cout * (hi - lo) * self.roi[1] * self.roi[2]
         return out
 
     def accumulate(self, recv):
-        """recv: {src: flat buffer}.  Adds all pieces of the slab in global window order; returns the slab accumulator."""
+        """recv: {src: flat buffer} (one exchange) or {(src, round): flat buffer}.  Adds all pieces of the slab in global window order;
+        returns the slab accumulator."""
         lib, st = self.lib, _lib.stream_ptr()
         nrows = self.x1 - self.x0
         acc = torch.zeros((self.cout, max(nrows, 1), self.size[1], self.size[2]), dtype=torch.float32, device=self.x.device)
@@ -284,8 +301,9 @@ class _SlabItem:
             if src == self.rank:
                 ptr, nx, xbase = self.preds[w - self.mine.start].data_ptr(), self.roi[0], s0
             else:
-                ptr, nx, xbase = recv[src].data_ptr() + 4 * offs[src], hi - lo, lo
-                offs[src] += self.cout * (hi - lo) * self.roi[1] * self.roi[2]
+                key = (src, self.round_of(w, src)) if (src, self.round_of(w, src)) in recv else src
+                ptr, nx, xbase = recv[key].data_ptr() + 4 * offs[key], hi - lo, lo
+                offs[key] += self.cout * (hi - lo) * self.roi[1] * self.roi[2]
             todo.append((ptr, (s0, s1, s2, lo, hi, nx, xbase)))
         for k0 in range(0, len(todo), 16):
             grp = todo[k0:k0 + 16]
@@ -310,15 +328,18 @@ class _SlabItem:
                                                   out_d0, out_rows, _lib.stream_ptr()), "b200_sw_finalize_slab")
 
 
-def _exchange_nccl(sends, recv_sizes, device, group):
-    """sends: {dst: buffer}; recv_sizes: {src: elements} -> {src: buffer}.  One batched NCCL send/recv round."""
+def _exchange_nccl(sends, recv_sizes, device, group, wait=True):
+    """sends: {dst: buffer}; recv_sizes: {src: elements} -> {src: buffer}.  One batched NCCL send/recv round.  wait=False returns
+    (recv, works): the caller waits on the works before it reads the buffers (and keeps `sends` alive until then)."""
     import torch.distributed as dist
     recv = {src: torch.empty(n, dtype=torch.float32, device=device) for src, n in recv_sizes.items()}
     ops = [dist.P2POp(dist.isend, buf, dst, group) for dst, buf in sorted(sends.items())] + \
           [dist.P2POp(dist.irecv, buf, src, group) for src, buf in sorted(recv.items())]
-    if ops:
-        for w in dist.batch_isend_irecv(ops):
-            w.wait()
+    works = dist.batch_isend_irecv(ops) if ops else []
+    if not wait:
+        return recv, works
+    for w in works:
+        w.wait()
     return recv
 
 
@@ -327,7 +348,6 @@ def _sw_slabs(lib, x, per_axis, flat, roi, size, orig, pad, chan, batch, sw_batc
     import torch.distributed as dist
     if len(flat) < world:
         raise RuntimeError("fewer windows than ranks; use fewer ranks")
-    exchange = exchange or (lambda sends, sizes: _exchange_nccl(sends, sizes, x.device, group))
     want_mask = return_argmax or labels is not None
     mask = torch.zeros((batch, 1, *orig), dtype=torch.uint8, device=x.device) if want_mask else None
     lab = counts = None
@@ -343,17 +363,36 @@ def _sw_slabs(lib, x, per_axis, flat, roi, size, orig, pad, chan, batch, sw_batc
             e.record()
             marks.append((tag, e))
     mark("start")
+    # halo pieces leave in rounds while the prediction loop is still running (NCCL on its own stream); `exchange` (tests) = one blocking round
+    inflight = {id(it): {"recv": {}, "works": [], "keep": [], "next": 0} for it in items}
+
+    def after_call(it, done_local):
+        if exchange is not None:
+            return
+        fl = inflight[id(it)]
+        while fl["next"] < it.ROUNDS and done_local >= it.round_end(fl["next"]):
+            j = fl["next"]
+            sends = it.pack_sends(j)
+            recv, works = _exchange_nccl(sends, it.recv_sizes(it.cout, j), x.device, group, wait=False)
+            fl["recv"].update({(src, j): buf for src, buf in recv.items()})
+            fl["works"] += works
+            fl["keep"].append(sends)
+            fl["next"] = j + 1
     with _graphed(predictor, len(items[0].mine) * batch >= 4 * sw_batch):
         for it in items:
-            it.predict(predictor, sw_batch, args, kwargs)
-    mark("predict")
+            it.predict(predictor, sw_batch, args, kwargs, after_call)
+    mark("predict+pack+send")
     cout = items[0].cout
     lab, counts = _label_args(labels, x, batch, cout, orig)
     for it in items:
-        sends = it.pack_sends()
-        mark("pack")
-        recv = exchange(sends, it.recv_sizes(cout))
-        mark("exchange")
+        if exchange is not None:
+            recv = exchange(it.pack_sends(), it.recv_sizes(cout))
+        else:
+            fl = inflight[id(it)]
+            for wk in fl["works"]:
+                wk.wait()
+            recv = fl["recv"]
+        mark("exchange tail")
         acc = it.accumulate(recv)
         mark("accumulate")
         d0, d1 = it.rows()

@@ -412,9 +412,10 @@ def test_sliding_window_identity_and_oracle(pkg, overlap, shape, roi):
     assert (mask[:, 0].cpu().long() == got.argmax(1).cpu()).all()
 
 
+@pytest.mark.parametrize("rounds", [False, True])
 @pytest.mark.parametrize("world", [2, 3, 8])
 @pytest.mark.parametrize("shape,roi,overlap", [((48, 40, 32), (16, 16, 16), 0.5), ((40, 20, 24), (16, 16, 16), 0.25), ((12, 40, 40), (16, 16, 16), 0.5)])
-def test_sliding_window_slabs_equal_single_bitwise(pkg, world, shape, roi, overlap):
+def test_sliding_window_slabs_equal_single_bitwise(pkg, world, shape, roi, overlap, rounds):
     """The slab-owned multi-GPU path, every rank run in turn on one GPU with the NCCL exchange replaced by a hand-over of the packed
     halo buffers: each rank predicts its window chunk, packs the row-clipped pieces for the higher ranks, accumulates its slab in
     global window order and normalises it.  Stitched together, logits and argmax mask must equal the single-GPU call BIT FOR BIT
@@ -440,16 +441,24 @@ def test_sliding_window_slabs_equal_single_bitwise(pkg, world, shape, roi, overl
     sends = []
     for it in ranks:
         it.predict(f, 4, (), {})
-        sends.append(it.pack_sends())
+        # rounds: the pipelined form of the exchange (pieces leave in ROUNDS parts while the prediction loop runs)
+        sends.append([it.pack_sends(j) for j in range(it.ROUNDS)] if rounds else it.pack_sends())
     cout = ranks[0].cout
     got = torch.full_like(want, float("nan"))
     mask = torch.zeros_like(want_mask)
     counts = torch.zeros_like(want_counts)
     covered = 0
     for r, it in enumerate(ranks):
-        sizes = it.recv_sizes(cout)
-        recv = {src: sends[src][r] for src in sizes}
-        assert all(recv[src].numel() == n for src, n in sizes.items())
+        if rounds:
+            recv = {}
+            for j in range(it.ROUNDS):
+                for src, n in it.recv_sizes(cout, j).items():
+                    recv[(src, j)] = sends[src][j][r]
+                    assert recv[(src, j)].numel() == n
+        else:
+            sizes = it.recv_sizes(cout)
+            recv = {src: sends[src][r] for src in sizes}
+            assert all(recv[src].numel() == n for src, n in sizes.items())
         acc = it.accumulate(recv)
         d0, d1 = it.rows()
         covered += d1 - d0
