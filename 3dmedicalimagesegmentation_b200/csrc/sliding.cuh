@@ -99,16 +99,26 @@ static __global__ void __launch_bounds__(256) sw_accumulate_slab_kernel(float* _
     float* arow = acc + (((long)c * nrows + (x - xoff)) * g.PH + y) * g.PW;
     for (int zi = lane; zi < bx.nz; zi += 32) {
       const int z = bx.z0 + zi;
-      float a = 0.f; bool any = false;
-#pragma unroll 1
-      for (int k = 0; k < ps.n; ++k) {
-        const int dz = z - ps.p[k].s2;
-        if (((live >> k) & 1u) && (unsigned)dz < (unsigned)g.r2) {
-          if (!any) { a = arow[z]; any = true; }
-          a += ps.p[k].pred[(((long)c * ps.p[k].nx + (x - ps.p[k].xbase)) * g.r1 + (y - ps.p[k].s1)) * g.r2 + dz];
+      // all loads of the voxel first (independent, up to 16 in flight), then the additions in piece order: the order of the float
+      // additions is what makes the result bit-identical to the sequential loop, the order of the loads is free
+      float vals[16]; unsigned has = 0;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        vals[k] = 0.f;
+        if (k < ps.n) {
+          const int dz = z - ps.p[k].s2;
+          if (((live >> k) & 1u) && (unsigned)dz < (unsigned)g.r2) {
+            vals[k] = ps.p[k].pred[(((long)c * ps.p[k].nx + (x - ps.p[k].xbase)) * g.r1 + (y - ps.p[k].s1)) * g.r2 + dz];
+            has |= 1u << k;
+          }
         }
       }
-      if (any) arow[z] = a;
+      if (has) {
+        float a = arow[z];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) if ((has >> k) & 1u) a += vals[k];
+        arow[z] = a;
+      }
     }
   }
 }

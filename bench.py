@@ -198,6 +198,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="issue every step's launches from the host instead of replaying the captured CUDA graph")
     ap.add_argument("--breakdown", action="store_true", help="print the per-op CUDA-event breakdown to stderr")
     ap.add_argument("--no-sliding-window", action="store_true", help="skip the configs[4] whole-CT sliding-window measurement")
+    ap.add_argument("--fp32-allreduce", action="store_true", help="N > 1: all-reduce the gradients in fp32 (default in bf16 mode: bf16 on the wire)")
     ap.add_argument("--graph-dp", action="store_true", help="N > 1: capture the step including the NCCL all-reduces as a CUDA graph")
     ap.add_argument("--no-augment", action="store_true", help="skip the leg that feeds the step from the GPU-side crop sampler (SURVEY 8f N4)")
     ap.add_argument("--no-dp128", action="store_true", help="skip the configs[3] leg (128^3 crops, 4 per GPU)")
@@ -235,7 +236,9 @@ def main():
     else:
         # one launch; keeps the packed bf16 weights current; update count on the device (graph replay)
         opt = pkg.FusedAdamW(model.parameters(), lr=1e-4, weight_decay=1e-5, mirror=model, capturable=True)
-    ddp = par.GradientAllReduce(model, world) if world > 1 else None
+    # bf16 mode: gradients cross NVLink as bf16 (parallel.GradientAllReduce(compress="bf16")); --fp32-allreduce keeps fp32 on the wire
+    compress = "bf16" if (args.mode == "bf16" and not args.fp32_allreduce) else None
+    ddp = par.GradientAllReduce(model, world, compress=compress) if world > 1 else None
     if os.environ.get("B200_GRAD_GROUPS"):
         model.grad_groups = int(os.environ["B200_GRAD_GROUPS"])       # tuning aid: 4 / 7 / 13 gradient-ready events per backward
     B = args.batch
@@ -488,7 +491,7 @@ def main():
         gstep = None
         m128 = pkg.MonaiUNETR(**dict(MODEL_KW, img_size=(128, 128, 128))).to(dev).set_mode(args.mode)
         o128 = pkg.FusedAdamW(m128.parameters(), lr=1e-4, weight_decay=1e-5, mirror=m128, capturable=True)
-        d128 = par.GradientAllReduce(m128, world) if world > 1 else None
+        d128 = par.GradientAllReduce(m128, world, compress=compress) if world > 1 else None
         x128 = [torch.rand(4, 1, 128, 128, 128, generator=g).to(dev) for _ in range(2)]
         y128 = [torch.randint(0, 14, (4, 1, 128, 128, 128), generator=g).float().to(dev) for _ in range(2)]
 
@@ -519,7 +522,7 @@ def main():
         torch.cuda.empty_cache()
         rmodel = pkg.UNETR(**MODEL_KW).to(dev).set_mode(args.mode)
         ropt = pkg.FusedAdamW(rmodel.parameters(), lr=1e-4, weight_decay=1e-5, mirror=rmodel)
-        rddp = par.GradientAllReduce(rmodel, world) if world > 1 else None
+        rddp = par.GradientAllReduce(rmodel, world, compress=compress) if world > 1 else None
 
         class _Opt:                       # BTLoss(reference, similar, dissimilar, optimizer) steps the optimizer itself (rank:213-215)
             def step(self):
@@ -561,7 +564,7 @@ def main():
                 "scaling": "weak", "vs_baseline": None, "dtype": args.mode, "data": "synthetic",
                 "config": {"workload": ("configs[1]" if S == 96 else "configs[3]") + f": UNETR(1->14,{S}^3,fs16,ViT-B) segmentation training step (fwd+DiceCE+bwd" +
                            ("" if args.no_optimizer else "+AdamW") + f"), batch {B}/GPU", "global_batch": B * world,
-                           "parallelism": f"dp{world}", "launch": graph_note, "l2": "4 rotating input batches; activations per step (~1 GB) exceed the 126 MB L2"},
+                           "parallelism": f"dp{world}", "gradient_allreduce": (None if world == 1 else (compress or "fp32")), "launch": graph_note, "l2": "4 rotating input batches; activations per step (~1 GB) exceed the 126 MB L2"},
                 "tflops_algorithmic": samples * flop_per_sample / (ms * 1e-3) / 1e12,
                 "e2e": {"value": samples / (ms_e2e * 1e-3), "unit": "samples/s",
                         "h2d_bytes_per_step": host_x[0].numel() * 4 + host_y[0].numel() * 4, "d2h_bytes_per_step": 4},
