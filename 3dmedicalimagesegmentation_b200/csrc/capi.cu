@@ -366,7 +366,10 @@ int b200_sw_accumulate_n(float* acc, const float* pred, const b200_sw_geom* g, c
   }
   bx.nx = x1 - bx.x0 + sg.r0; bx.ny = y1 - bx.y0 + sg.r1; bx.nz = z1 - bx.z0 + sg.r2;
   long rows = (long)bx.nx * bx.ny * sg.C;         // one warp per (c, x, y) line
-  sw_accumulate_multi_kernel<<<(unsigned)min(148L * 16, (rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(acc, pred, sg, wb, bx);
+  bool v4 = sg.r2 % 4 == 0 && sg.PW % 4 == 0 && bx.z0 % 4 == 0 && bx.nz % 4 == 0 && (((uintptr_t)acc | (uintptr_t)pred) & 15) == 0;
+  for (int i = 0; i < n; ++i) v4 = v4 && wb.w[i].s2 % 4 == 0;
+  if (v4) sw_accumulate_multi_kernel<4><<<(unsigned)min(148L * 16, (rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(acc, pred, sg, wb, bx);
+  else sw_accumulate_multi_kernel<1><<<(unsigned)min(148L * 16, (rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(acc, pred, sg, wb, bx);
   B200_LAUNCH_CHECK();
   return 0;
 }
@@ -430,7 +433,10 @@ int b200_sw_accumulate_slab(float* acc, const b200_sw_geom* g, const void* const
   bx.nx = x1 - bx.x0; bx.ny = y1 - bx.y0 + sg.r1; bx.nz = z1 - bx.z0 + sg.r2;
   if (bx.nx <= 0) return 0;
   long rows = (long)bx.nx * bx.ny * sg.C;
-  sw_accumulate_slab_kernel<<<(unsigned)min(148L * 16, (rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(acc, sg, ps, bx, xoff, nrows);
+  bool v4 = sg.r2 % 4 == 0 && sg.PW % 4 == 0 && bx.z0 % 4 == 0 && bx.nz % 4 == 0 && ((uintptr_t)acc & 15) == 0;
+  for (int i = 0; i < n; ++i) v4 = v4 && ps.p[i].s2 % 4 == 0 && ((uintptr_t)ps.p[i].pred & 15) == 0;
+  if (v4) sw_accumulate_slab_kernel<4><<<(unsigned)min(148L * 16, (rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(acc, sg, ps, bx, xoff, nrows);
+  else sw_accumulate_slab_kernel<1><<<(unsigned)min(148L * 16, (rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(acc, sg, ps, bx, xoff, nrows);
   B200_LAUNCH_CHECK();
   return 0;
 }

@@ -47,9 +47,11 @@ static __global__ void sw_accumulate_kernel(float* __restrict__ acc, const float
 // box and adds the predictions of the windows that cover it in window order -- the per-voxel sequence of float additions is
 // exactly the one the per-window launches (and MONAI's loop) produce, but a voxel covered twice is read and written once.
 struct SwBox { int x0, y0, z0, nx, ny, nz; };
+template <int VEC>   // VEC = 4: four consecutive z per lane (16-byte accesses; window z-starts, roi and the padded width are multiples of 4)
 static __global__ void __launch_bounds__(256) sw_accumulate_multi_kernel(float* __restrict__ acc, const float* __restrict__ pred, SwGeom g, SwBatch wb, SwBox bx) {
   // one warp per (channel, x, y) line of the bounding box: the line's window membership along x and y is decided once, the lanes
-  // walk z (coalesced 128-byte accumulator accesses), and only the z test is left per element
+  // walk z (coalesced accumulator accesses), and only the z test is left per element.  All loads of a voxel are issued before the
+  // additions; the additions happen in window order (bit-identical to the one-window-at-a-time loop).
   const long per = (long)g.r0 * g.r1 * g.r2;
   const long rows = (long)g.C * bx.nx * bx.ny;
   const int b = wb.w[0].b, lane = threadIdx.x & 31;
@@ -62,18 +64,34 @@ static __global__ void __launch_bounds__(256) sw_accumulate_multi_kernel(float* 
       if ((unsigned)(x - wb.w[k].s0) < (unsigned)g.r0 && (unsigned)(y - wb.w[k].s1) < (unsigned)g.r1) live |= 1u << k;
     if (!live) continue;
     float* arow = acc + ((((long)b * g.C + c) * g.PD + x) * g.PH + y) * g.PW;
-    for (int zi = lane; zi < bx.nz; zi += 32) {
+    for (int zi = lane * VEC; zi < bx.nz; zi += 32 * VEC) {
       const int z = bx.z0 + zi;
-      float a = 0.f; bool any = false;
-#pragma unroll 1
-      for (int k = 0; k < wb.n; ++k) {
-        const int dz = z - wb.w[k].s2;
-        if (((live >> k) & 1u) && (unsigned)dz < (unsigned)g.r2) {
-          if (!any) { a = arow[z]; any = true; }
-          a += pred[((long)k * g.C + c) * per + ((long)(x - wb.w[k].s0) * g.r1 + (y - wb.w[k].s1)) * g.r2 + dz];
+      float vals[16][VEC]; unsigned has = 0;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        if (k < wb.n && ((live >> k) & 1u)) {
+          const int dz = z - wb.w[k].s2;
+          if ((unsigned)dz < (unsigned)g.r2) {
+            const float* src = pred + ((long)k * g.C + c) * per + ((long)(x - wb.w[k].s0) * g.r1 + (y - wb.w[k].s1)) * g.r2 + dz;
+            if (VEC == 4) { const float4 t = *reinterpret_cast<const float4*>(src); vals[k][0] = t.x; vals[k][1] = t.y; vals[k][VEC > 1 ? 2 : 0] = t.z; vals[k][VEC > 1 ? 3 : 0] = t.w; }
+            else vals[k][0] = *src;
+            has |= 1u << k;
+          }
         }
       }
-      if (any) arow[z] = a;
+      if (has) {
+        float a[VEC];
+        if (VEC == 4) { const float4 t = *reinterpret_cast<const float4*>(arow + z); a[0] = t.x; a[1] = t.y; a[VEC > 1 ? 2 : 0] = t.z; a[VEC > 1 ? 3 : 0] = t.w; }
+        else a[0] = arow[z];
+#pragma unroll
+        for (int k = 0; k < 16; ++k)
+          if ((has >> k) & 1u) {
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) a[i] += vals[k][i];
+          }
+        if (VEC == 4) *reinterpret_cast<float4*>(arow + z) = make_float4(a[0], a[1], a[VEC > 1 ? 2 : 0], a[VEC > 1 ? 3 : 0]);
+        else arow[z] = a[0];
+      }
     }
   }
 }
@@ -84,6 +102,7 @@ static __global__ void __launch_bounds__(256) sw_accumulate_multi_kernel(float* 
 // Per voxel the float additions happen in piece order = window order: bit-identical to the single-GPU loop.
 struct SwPiece { const float* pred; int s0, s1, s2, x_lo, x_hi, nx, xbase; };
 struct SwPieces { SwPiece p[16]; int n; };
+template <int VEC>
 static __global__ void __launch_bounds__(256) sw_accumulate_slab_kernel(float* __restrict__ acc, SwGeom g, SwPieces ps, SwBox bx, int xoff, int nrows) {
   const long rows = (long)g.C * bx.nx * bx.ny;
   const int lane = threadIdx.x & 31;
@@ -97,27 +116,35 @@ static __global__ void __launch_bounds__(256) sw_accumulate_slab_kernel(float* _
       if (x >= ps.p[k].x_lo && x < ps.p[k].x_hi && (unsigned)(y - ps.p[k].s1) < (unsigned)g.r1) live |= 1u << k;
     if (!live) continue;
     float* arow = acc + (((long)c * nrows + (x - xoff)) * g.PH + y) * g.PW;
-    for (int zi = lane; zi < bx.nz; zi += 32) {
+    for (int zi = lane * VEC; zi < bx.nz; zi += 32 * VEC) {
       const int z = bx.z0 + zi;
-      // all loads of the voxel first (independent, up to 16 in flight), then the additions in piece order: the order of the float
+      // all loads of the voxel(s) first (independent, up to 16 in flight), then the additions in piece order: the order of the float
       // additions is what makes the result bit-identical to the sequential loop, the order of the loads is free
-      float vals[16]; unsigned has = 0;
+      float vals[16][VEC]; unsigned has = 0;
 #pragma unroll
       for (int k = 0; k < 16; ++k) {
-        vals[k] = 0.f;
-        if (k < ps.n) {
+        if (k < ps.n && ((live >> k) & 1u)) {
           const int dz = z - ps.p[k].s2;
-          if (((live >> k) & 1u) && (unsigned)dz < (unsigned)g.r2) {
-            vals[k] = ps.p[k].pred[(((long)c * ps.p[k].nx + (x - ps.p[k].xbase)) * g.r1 + (y - ps.p[k].s1)) * g.r2 + dz];
+          if ((unsigned)dz < (unsigned)g.r2) {
+            const float* src = ps.p[k].pred + (((long)c * ps.p[k].nx + (x - ps.p[k].xbase)) * g.r1 + (y - ps.p[k].s1)) * g.r2 + dz;
+            if (VEC == 4) { const float4 t = *reinterpret_cast<const float4*>(src); vals[k][0] = t.x; vals[k][1] = t.y; vals[k][VEC > 1 ? 2 : 0] = t.z; vals[k][VEC > 1 ? 3 : 0] = t.w; }
+            else vals[k][0] = *src;
             has |= 1u << k;
           }
         }
       }
       if (has) {
-        float a = arow[z];
+        float a[VEC];
+        if (VEC == 4) { const float4 t = *reinterpret_cast<const float4*>(arow + z); a[0] = t.x; a[1] = t.y; a[VEC > 1 ? 2 : 0] = t.z; a[VEC > 1 ? 3 : 0] = t.w; }
+        else a[0] = arow[z];
 #pragma unroll
-        for (int k = 0; k < 16; ++k) if ((has >> k) & 1u) a += vals[k];
-        arow[z] = a;
+        for (int k = 0; k < 16; ++k)
+          if ((has >> k) & 1u) {
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) a[i] += vals[k][i];
+          }
+        if (VEC == 4) *reinterpret_cast<float4*>(arow + z) = make_float4(a[0], a[1], a[VEC > 1 ? 2 : 0], a[VEC > 1 ? 3 : 0]);
+        else arow[z] = a[0];
       }
     }
   }
