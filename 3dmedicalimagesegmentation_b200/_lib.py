@@ -15,6 +15,7 @@ FLAG_NEED_ENCODER_GRAD = 1
 FLAG_HAS_DLOGITS = 2
 FLAG_HAS_DENC4 = 4
 FLAG_NO_BACKWARD = 16
+FLAG_INPLACE_WGRADS = 32
 FLAG_WEIGHTS_PACKED = 64
 
 

@@ -655,19 +655,25 @@ static int test_instnorm_bwd_t(int two, const void* dout, const void* act, const
   constexpr int VN = Vec16<T>::N;
   B200_CHECK(C % VN == 0 && 256 % (C / VN) == 0, "InstanceNorm channel count %d unsupported", C);
   ClView pv{C, 0};
-  const size_t red_smem = 256 * 3 * VN * sizeof(float), cst_smem = 6 * (size_t)C * sizeof(float);
+  const size_t red_smem = 256 * 3 * VN * sizeof(float), cst_smem = 7 * (size_t)C * sizeof(float);
   dim3 gr(in_grid_x(V, C / VN), N), ga(in_grid_x(V, C / VN) * 2, N);
   B200_CUDA(cudaMemsetAsync(acc, 0, sizeof(double) * 3 * N * C, st));
   if (two) {
-    B200_CUDA(launch_pdl(in_bwd_reduce_kernel<T, true>, gr, dim3(256), red_smem, st, (const T*)dout, pv, (const T*)act, pv, (const TR*)ra, pv, (const TR*)rb, pv, C, V, acc));
-    B200_LAUNCH_CHECK();
-    B200_CUDA(launch_pdl(in_bwd_fixup_kernel, dim3(cdiv(N * C, 128)), dim3(128), 0, st, acc, mra, mrb, N * C));
-    B200_LAUNCH_CHECK();
-    B200_CUDA(launch_pdl(in_bwd_apply_kernel<T, true>, ga, dim3(256), cst_smem, st, (const T*)dout, pv, (const T*)act, pv, (const TR*)ra, pv, mra, (const TR*)rb, pv, mrb,
-                         C, V, (const double*)acc, (T*)da, pv, (T*)db, pv));
-    B200_LAUNCH_CHECK();
+    if (act) {
+      B200_CUDA(launch_pdl(in_bwd_reduce_kernel<T, true, false>, gr, dim3(256), red_smem, st, (const T*)dout, pv, (const T*)act, pv, (const TR*)ra, pv, (const TR*)rb, pv, C, V, acc, mra, mrb));
+      B200_LAUNCH_CHECK();
+      B200_CUDA(launch_pdl(in_bwd_apply_kernel<T, true, false>, ga, dim3(256), cst_smem, st, (const T*)dout, pv, (const T*)act, pv, (const TR*)ra, pv, mra, (const TR*)rb, pv, mrb,
+                           C, V, (const double*)acc, (T*)da, pv, (T*)db, pv));
+      B200_LAUNCH_CHECK();
+    } else {   // the engine's default: the sign is recomputed from the raw conv outputs
+      B200_CUDA(launch_pdl(in_bwd_reduce_kernel<T, true, true>, gr, dim3(256), red_smem, st, (const T*)dout, pv, (const T*)act, pv, (const TR*)ra, pv, (const TR*)rb, pv, C, V, acc, mra, mrb));
+      B200_LAUNCH_CHECK();
+      B200_CUDA(launch_pdl(in_bwd_apply_kernel<T, true, true>, ga, dim3(256), cst_smem, st, (const T*)dout, pv, (const T*)act, pv, (const TR*)ra, pv, mra, (const TR*)rb, pv, mrb,
+                           C, V, (const double*)acc, (T*)da, pv, (T*)db, pv));
+      B200_LAUNCH_CHECK();
+    }
   } else {
-    B200_CUDA(launch_pdl(in_bwd_reduce_kernel<T, false>, gr, dim3(256), red_smem, st, (const T*)dout, pv, (const T*)act, pv, (const TR*)nullptr, pv, (const TR*)nullptr, pv, C, V, acc));
+    B200_CUDA(launch_pdl(in_bwd_reduce_kernel<T, false>, gr, dim3(256), red_smem, st, (const T*)dout, pv, (const T*)act, pv, (const TR*)nullptr, pv, (const TR*)nullptr, pv, C, V, acc, (const float*)nullptr, (const float*)nullptr));
     B200_LAUNCH_CHECK();
     B200_CUDA(launch_pdl(in_bwd_apply_kernel<T, false>, ga, dim3(256), cst_smem, st, (const T*)dout, pv, (const T*)act, pv, (const TR*)nullptr, pv, mra, (const TR*)nullptr, pv,
                          (const float*)nullptr, C, V, (const double*)acc, (T*)da, pv, (T*)nullptr, pv));
@@ -677,7 +683,7 @@ static int test_instnorm_bwd_t(int two, const void* dout, const void* act, const
 }
 extern "C" {
 /* InstanceNorm(+LeakyReLU) backward of the residual conv block (exec.cuh res_bwd), channels-last [N,V,C]:
- *  two != 0: out = lrelu(norm(c2) + norm(c3)): dout, act = out (T), ra = c2, rb = c3 (raw conv outputs: fp16 in bf16 mode), mra / mrb
+ *  two != 0: out = lrelu(norm(c2) + norm(c3)): dout, act = out (T; NULL: the sign is recomputed from c2, c3), ra = c2, rb = c3 (raw conv outputs: fp16 in bf16 mode), mra / mrb
  *            = (mean, rstd) [N][C][2] -> da = d c2, db = d c3;
  *  two == 0: act = lrelu(norm(c1)) (T; the normalised value is recovered from it), mra = (mean, rstd) of c1 -> da = d c1.
  * acc: double [N][C][3] scratch */

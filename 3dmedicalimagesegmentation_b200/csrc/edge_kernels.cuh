@@ -337,14 +337,23 @@ __global__ void __launch_bounds__(256, 2) conv_in_wgrad2_kernel(const float* __r
 // ---------------------------------------------------------------------------------------------- fused last norm pass + head
 // d0[v,c] = lrelu(norm(c2)[v,c] + norm(c3)[v,c]) (stored as T for the backward), logits[n][k][v] = sum_c d0_fp32[c] Wh[k][c] + bh[k]
 template <class T, int CO>
-__global__ void __launch_bounds__(256) in_apply_head_kernel(const typename RawOf<T>::type* __restrict__ c2, const float* __restrict__ mr2, const typename RawOf<T>::type* __restrict__ c3,
-                                                            const float* __restrict__ mr3, T* __restrict__ d0, const float* __restrict__ Wh,
-                                                            const float* __restrict__ bh, int ncls, long V, float* __restrict__ logits) {
+__global__ void __launch_bounds__(256) in_apply_head_kernel(const typename RawOf<T>::type* __restrict__ c2, float* __restrict__ mr2, const typename RawOf<T>::type* __restrict__ c3,
+                                                            float* __restrict__ mr3, T* __restrict__ d0, const float* __restrict__ Wh,
+                                                            const float* __restrict__ bh, int ncls, long V, float* __restrict__ logits,
+                                                            const double* __restrict__ acc2, const double* __restrict__ acc3, double invV) {
   __shared__ float sW[32 * CO], sb[32], sm[4 * CO];
   const int n = blockIdx.y;
   for (int i = threadIdx.x; i < ncls * CO; i += 256) sW[i] = Wh[i];
   if (threadIdx.x < ncls) sb[threadIdx.x] = bh[threadIdx.x];
-  for (int i = threadIdx.x; i < 2 * CO; i += 256) { sm[i] = mr2[(long)n * CO * 2 + i]; sm[2 * CO + i] = mr3[(long)n * CO * 2 + i]; }
+  // (mean, rstd) of both inputs: from the (sum, sumsq) accumulators when given (in_moments; block 0 stores them for the backward)
+  for (int i = threadIdx.x; i < 2 * CO; i += 256) {
+    const int which = i / CO, c = i % CO;
+    const double* acc = which ? acc3 : acc2; float* mr = which ? mr3 : mr2;
+    float m, r;
+    if (acc) { in_moments(acc + 2 * ((long)n * CO + c), invV, m, r); if (blockIdx.x == 0) { mr[((long)n * CO + c) * 2] = m; mr[((long)n * CO + c) * 2 + 1] = r; } }
+    else { m = mr[((long)n * CO + c) * 2]; r = mr[((long)n * CO + c) * 2 + 1]; }
+    sm[which * 2 * CO + 2 * c] = m; sm[which * 2 * CO + 2 * c + 1] = r;
+  }
   __syncthreads();
   constexpr int VN = Vec16<T>::N;
   for (long v = (long)blockIdx.x * 256 + threadIdx.x; v < V; v += (long)gridDim.x * 256) {

@@ -121,6 +121,22 @@ static __global__ void add_kernel(float* __restrict__ dst, const float* __restri
   long stride = (long)gridDim.x * blockDim.x;
   for (; i < n; i += stride) dst[i] += src[i];
 }
+// dst += src; cast = T(dst)   (ViT backward: the encoder's gradient joins the residual stream at hidden states 3 / 6 / 9)
+template <class T>
+static __global__ void add_cast_kernel(float* __restrict__ dst, const float* __restrict__ src, T* __restrict__ cast, long n) {
+  pdl_wait();
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  long stride = (long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) { const float v = dst[i] + src[i]; dst[i] = v; cast[i] = from_f<T>(v); }
+}
+template <class T>
+static int launch_add_cast(float* dst, const float* src, T* cast, long n, cudaStream_t st) {
+  B200_PROF("add", st);
+  int blocks = (int)min((long)148 * 8, (n + 255) / 256);
+  B200_CUDA(launch_pdl(add_cast_kernel<T>, dim3(blocks), dim3(256), 0, st, dst, src, cast, n));
+  B200_LAUNCH_CHECK();
+  return 0;
+}
 static int launch_add(float* dst, const float* src, long n, cudaStream_t st) {
   B200_PROF("add", st);
   int blocks = (int)min((long)148 * 8, (n + 255) / 256);
@@ -149,7 +165,8 @@ __device__ __forceinline__ void store4(bf16* p, const float* v) {
 // use, one pass over memory (the generic kernels below are latency-bound: 2-3 dependent passes of 24 scalar loads).
 // Split-K producer fused into its consumer: x[row] = resid[row] + bias + sum_s part[s][row] is formed here (and written to xsum,
 // the fp32 residual stream) instead of by atomics in the GEMM epilogue.
-struct SplitSum { const float* part; int nsplit; long stride; const float* bias; const float* resid; float* xsum; };
+struct SplitSum { const float* part; int nsplit; long stride; const float* bias; const float* resid; float* xsum;
+                  void* xsum_cast; };   // xsum_cast (nullable): a second copy of the summed row in the kernel's output type (the hidden states the encoders read)
 template <class TO, int NV4>
 __global__ void layernorm_fwd_reg_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                                          TO* __restrict__ y, float* __restrict__ stats, int M, const SplitSum ss) {
@@ -173,6 +190,7 @@ __global__ void layernorm_fwd_reg_kernel(const float* __restrict__ x, const floa
 #pragma unroll
       for (int j = 0; j < 4; ++j) v[i][j] += b4[j] + ((p4[0][j] + p4[1][j]) + (p4[2][j] + p4[3][j]));
       store4(ss.xsum + o, v[i]);
+      if (ss.xsum_cast) store4(reinterpret_cast<TO*>(ss.xsum_cast) + o, v[i]);
     }
   } else {
 #pragma unroll
@@ -610,23 +628,23 @@ __global__ void in_stats_kernel(const typename RawOf<T>::type* __restrict__ x, C
     }
   }
 }
-static __global__ void in_finalize_kernel(const double* __restrict__ acc, float* __restrict__ mr, int NC, double invV) {
-  pdl_wait();
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= NC) return;
-  double mean = acc[2 * i] * invV;
-  double var = acc[2 * i + 1] * invV - mean * mean;
+// (mean, rstd) of one (n, c) from the double (sum, sumsq) pair that the conv epilogues / in_stats_kernel accumulate.  There is no separate
+// finalize launch: every block of the consuming normalise pass derives the constants of its own channels from the sums, and block 0 of
+// each sample also stores them as (mean, rstd) for the backward (17 launches of one CTA each per forward otherwise).
+__device__ __forceinline__ void in_moments(const double* __restrict__ acc2, double invV, float& mean, float& rstd) {
+  double m = acc2[0] * invV, var = acc2[1] * invV - m * m;
   if (var < 0) var = 0;
-  mr[2 * i] = (float)mean;
-  mr[2 * i + 1] = (float)(1.0 / sqrt(var + 1e-5));
+  mean = (float)m; rstd = 1.0f / sqrtf((float)var + 1e-5f);
 }
 
 // out = lrelu(norm(x))                            (two==0)
 // out = lrelu(norm_a(x) + norm_b(x2))             (two==1)
+// acc1 / acc2 (nullable): the (sum, sumsq) accumulators of x / x2 -- the constants come from them (in_moments) and are stored to mr / mr2
+// by block 0; null: mr / mr2 already hold (mean, rstd)
 template <class T>
-__global__ void in_apply_kernel(const typename RawOf<T>::type* __restrict__ x, ClView xv, const float* __restrict__ mr,
-                                const typename RawOf<T>::type* __restrict__ x2, ClView x2v, const float* __restrict__ mr2, T* __restrict__ out,
-                                ClView ov, int C, long V, int two) {
+__global__ void in_apply_kernel(const typename RawOf<T>::type* __restrict__ x, ClView xv, float* __restrict__ mr,
+                                const typename RawOf<T>::type* __restrict__ x2, ClView x2v, float* __restrict__ mr2, T* __restrict__ out,
+                                ClView ov, int C, long V, int two, const double* __restrict__ acc1, const double* __restrict__ acc2, double invV) {
   pdl_wait();
   constexpr int VN = Vec16<T>::N;
   int lanes = C / VN;
@@ -636,12 +654,25 @@ __global__ void in_apply_kernel(const typename RawOf<T>::type* __restrict__ x, C
   const long e0 = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const int lgl = 31 - __clz(lanes);   // lanes is a power of two
   const int lv = (int)(e0 & (lanes - 1)), c0 = lv * VN;
+  // one channel per thread: (mean, rstd) from the sums (or from memory) into shared memory; block 0 keeps them for the backward
+  __shared__ __align__(16) float smr[4][256];   // mean1, rstd1, mean2, rstd2 per channel (C <= 256)
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const long ch = (long)n * C + c;
+    float m, r;
+    if (acc1) { in_moments(acc1 + 2 * ch, invV, m, r); if (blockIdx.x == 0) { mr[2 * ch] = m; mr[2 * ch + 1] = r; } }
+    else { m = mr[2 * ch]; r = mr[2 * ch + 1]; }
+    smr[0][c] = m; smr[1][c] = r;
+    m = 0.f; r = 0.f;
+    if (two) {
+      if (acc2) { in_moments(acc2 + 2 * ch, invV, m, r); if (blockIdx.x == 0) { mr2[2 * ch] = m; mr2[2 * ch + 1] = r; } }
+      else { m = mr2[2 * ch]; r = mr2[2 * ch + 1]; }
+    }
+    smr[2][c] = m; smr[3][c] = r;
+  }
+  __syncthreads();
   float m1[VN], r1[VN], m2[VN], r2[VN];
 #pragma unroll
-  for (int i = 0; i < VN; ++i) {
-    m1[i] = mr[((long)n * C + c0 + i) * 2]; r1[i] = mr[((long)n * C + c0 + i) * 2 + 1];
-    m2[i] = two ? mr2[((long)n * C + c0 + i) * 2] : 0.f; r2[i] = two ? mr2[((long)n * C + c0 + i) * 2 + 1] : 0.f;
-  }
+  for (int i = 0; i < VN; ++i) { m1[i] = smr[0][c0 + i]; r1[i] = smr[1][c0 + i]; m2[i] = smr[2][c0 + i]; r2[i] = smr[3][c0 + i]; }
 #pragma unroll 4
   for (long e = e0; e < total; e += (long)gridDim.x * blockDim.x) {
     long v = e >> lgl;
@@ -662,11 +693,11 @@ __global__ void in_apply_kernel(const typename RawOf<T>::type* __restrict__ x, C
 // Backward, pass 1: per-(n,c) sums.  g = dOut * lrelu'(act).
 //  TWO == false: act = lrelu(n1) is the saved activation; n1 recovered from it.   sums: [Sg, Sg*n1]
 //  TWO == true : act = lrelu(n2+n3); RAW moments [Sg, S g*c2, S g*c3] of the raw conv outputs are accumulated (no per-channel
-//                constants in the loop) and converted to [Sg, Sg*n2, Sg*n3] by in_bwd_fixup_kernel: Sg*n = rstd*(S g*c - mean*Sg)
-template <class T, bool TWO>
+//                constants in the loop) and converted to [Sg, Sg*n2, Sg*n3] in the prologue of in_bwd_apply_kernel: Sg*n = rstd*(S g*c - mean*Sg)
+template <class T, bool TWO, bool RESIGN = false>
 __global__ void __launch_bounds__(256, 3) in_bwd_reduce_kernel(const T* __restrict__ dout, ClView dv, const T* __restrict__ act, ClView av,
                                      const typename RawOf<T>::type* __restrict__ ra, ClView rav, const typename RawOf<T>::type* __restrict__ rb, ClView rbv, int C, long V,
-                                     double* __restrict__ acc /*[N][C][3]*/) {
+                                     double* __restrict__ acc /*[N][C][3]*/, const float* __restrict__ mra, const float* __restrict__ mrb) {
   pdl_wait();
   constexpr int VN = Vec16<T>::N;
   extern __shared__ float red[];  // [warps][lanes][3*VN]
@@ -678,16 +709,38 @@ __global__ void __launch_bounds__(256, 3) in_bwd_reduce_kernel(const T* __restri
   float s0[VN], s1[VN], s2[VN];
 #pragma unroll
   for (int i = 0; i < VN; ++i) s0[i] = s1[i] = s2[i] = 0.f;
+  // RESIGN (TWO only; act is not read): the sign of the block output n2 + n3 = c2*r2 + c3*r3 - (m2*r2 + m3*r3) is recomputed from the raw conv outputs
+  // instead of reading the stored activation (one tensor pass less); the three constants per channel sit in shared memory
+  constexpr bool resign = TWO && RESIGN;
+  __shared__ __align__(16) float kc[TWO ? 3 * 256 : 4];
+  if (resign) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      const long ch = (long)n * C + c;
+      const float qa = mra[2 * ch + 1], qb = mrb[2 * ch + 1];
+      kc[c] = qa; kc[C + c] = qb; kc[2 * C + c] = -(mra[2 * ch] * qa + mrb[2 * ch] * qb);
+    }
+    __syncthreads();
+  }
 #pragma unroll 4
   for (long v = v0 + sub; v < v1; v += nsub) {
     long base = (long)n * V + v;
-    Vec16<T> d, a; d.load(dout + base * dv.pitch + dv.coff + c0); a.load(act + base * av.pitch + av.coff + c0);
+    Vec16<T> d, a; d.load(dout + base * dv.pitch + dv.coff + c0);
+    if (!resign) a.load(act + base * av.pitch + av.coff + c0);
     if (TWO) {
       Vec16<typename RawOf<T>::type> xa, xb; xa.load(ra + base * rav.pitch + rav.coff + c0); xb.load(rb + base * rbv.pitch + rbv.coff + c0);
 #pragma unroll
-      for (int i = 0; i < VN; ++i) {
-        float g = d.v[i] * (a.v[i] > 0.f ? 1.f : 0.01f);
-        s0[i] += g; s1[i] = fmaf(g, xa.v[i], s1[i]); s2[i] = fmaf(g, xb.v[i], s2[i]);
+      for (int i = 0; i < VN; i += 4) {
+        float qa[4] = {0.f, 0.f, 0.f, 0.f}, qb[4] = {0.f, 0.f, 0.f, 0.f}, kk[4] = {0.f, 0.f, 0.f, 0.f};
+        if (resign) {
+          const float4 A = *reinterpret_cast<const float4*>(kc + c0 + i), B = *reinterpret_cast<const float4*>(kc + C + c0 + i), K = *reinterpret_cast<const float4*>(kc + 2 * C + c0 + i);
+          qa[0] = A.x; qa[1] = A.y; qa[2] = A.z; qa[3] = A.w; qb[0] = B.x; qb[1] = B.y; qb[2] = B.z; qb[3] = B.w; kk[0] = K.x; kk[1] = K.y; kk[2] = K.z; kk[3] = K.w;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float pre = resign ? fmaf(xa.v[i + q], qa[q], fmaf(xb.v[i + q], qb[q], kk[q])) : a.v[i + q];
+          float g = d.v[i + q] * (pre > 0.f ? 1.f : 0.01f);
+          s0[i + q] += g; s1[i + q] = fmaf(g, xa.v[i + q], s1[i + q]); s2[i + q] = fmaf(g, xb.v[i + q], s2[i + q]);
+        }
       }
     } else {
 #pragma unroll
@@ -720,19 +773,10 @@ __global__ void __launch_bounds__(256, 3) in_bwd_reduce_kernel(const T* __restri
     }
   }
 }
-// raw moments -> centred/normalised ones (TWO mode): acc[.][1] = rstd_a*(acc[1] - mean_a*acc[0]), same for [2] with (mean_b, rstd_b)
-static __global__ void in_bwd_fixup_kernel(double* __restrict__ acc, const float* __restrict__ mra, const float* __restrict__ mrb, int NC) {
-  pdl_wait();
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= NC) return;
-  double sg = acc[3 * i];
-  acc[3 * i + 1] = (double)mra[2 * i + 1] * (acc[3 * i + 1] - (double)mra[2 * i] * sg);
-  acc[3 * i + 2] = (double)mrb[2 * i + 1] * (acc[3 * i + 2] - (double)mrb[2 * i] * sg);
-}
 // Backward, pass 2:  d(raw) = rstd * (g - mean(g) - n * mean(g*n))  =  A1*g + A2*raw + A3  with per-(n,c) constants staged in smem
 //   A1 = rstd, A2 = -rstd^2 * mean(g n), A3 = rstd^2 * mean(g n) * mean - rstd * mean(g)      (TWO: one triple per raw input)
 //   !TWO: n is recovered from the saved activation: d = rstd * (g - mg - n*mgn)
-template <class T, bool TWO>
+template <class T, bool TWO, bool RESIGN = false>
 __global__ void __launch_bounds__(256, 3) in_bwd_apply_kernel(const T* __restrict__ dout, ClView dv, const T* __restrict__ act, ClView av,
                                     const typename RawOf<T>::type* __restrict__ ra, ClView rav, const float* __restrict__ mra,
                                     const typename RawOf<T>::type* __restrict__ rb, ClView rbv, const float* __restrict__ mrb, int C, long V,
@@ -740,20 +784,23 @@ __global__ void __launch_bounds__(256, 3) in_bwd_apply_kernel(const T* __restric
                                     T* __restrict__ db, ClView dbv) {
   pdl_wait();
   constexpr int VN = Vec16<T>::N;
-  extern __shared__ __align__(16) float cst[];   // [6][C]
+  extern __shared__ __align__(16) float cst[];   // [7][C]: 6 affine constants + the sign constant (RESIGN, see in_bwd_reduce_kernel)
   int lanes = C / VN;
   int n = blockIdx.y;
   long total = V * lanes;
   float invV = 1.f / (float)V;
+  constexpr bool resign = TWO && RESIGN;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const double* a3 = acc + ((long)n * C + c) * 3;
     float mg = (float)a3[0] * invV, mga = (float)a3[1] * invV;
     float m = mra[((long)n * C + c) * 2], r = mra[((long)n * C + c) * 2 + 1];
-    if (TWO) {
-      float mgb = (float)a3[2] * invV;
+    if (TWO) {   // acc holds RAW moments here (in_bwd_reduce_kernel<TWO>): centre / normalise them first, in double like the sums
       float m2 = mrb[((long)n * C + c) * 2], r2 = mrb[((long)n * C + c) * 2 + 1];
+      mga = (float)((double)r * (a3[1] - (double)m * a3[0])) * invV;
+      float mgb = (float)((double)r2 * (a3[2] - (double)m2 * a3[0])) * invV;
       cst[c] = r; cst[C + c] = -r * r * mga; cst[2 * C + c] = r * r * mga * m - r * mg;
       cst[3 * C + c] = r2; cst[4 * C + c] = -r2 * r2 * mgb; cst[5 * C + c] = r2 * r2 * mgb * m2 - r2 * mg;
+      cst[6 * C + c] = -(m * r + m2 * r2);
     } else {
       cst[c] = r; cst[C + c] = -r * mga; cst[2 * C + c] = -r * mg;   // d = r*g + (-r*mga)*n + (-r*mg)
     }
@@ -766,7 +813,8 @@ __global__ void __launch_bounds__(256, 3) in_bwd_apply_kernel(const T* __restric
   for (long e = e0; e < total; e += (long)gridDim.x * blockDim.x) {
     long v = e >> lgl;
     long base = (long)n * V + v;
-    Vec16<T> d, a; d.load(dout + base * dv.pitch + dv.coff + c0); a.load(act + base * av.pitch + av.coff + c0);
+    Vec16<T> d, a; d.load(dout + base * dv.pitch + dv.coff + c0);
+    if (!resign) a.load(act + base * av.pitch + av.coff + c0);
     Vec16<T> oa, ob;
     if (TWO) {
       Vec16<typename RawOf<T>::type> xa, xb; xa.load(ra + base * rav.pitch + rav.coff + c0); xb.load(rb + base * rbv.pitch + rbv.coff + c0);
@@ -776,9 +824,12 @@ __global__ void __launch_bounds__(256, 3) in_bwd_apply_kernel(const T* __restric
         float4 B1 = *reinterpret_cast<const float4*>(cst + 3 * C + c0 + i), B2 = *reinterpret_cast<const float4*>(cst + 4 * C + c0 + i), B3 = *reinterpret_cast<const float4*>(cst + 5 * C + c0 + i);
         const float a1[4] = {A1.x, A1.y, A1.z, A1.w}, a2[4] = {A2.x, A2.y, A2.z, A2.w}, a3c[4] = {A3.x, A3.y, A3.z, A3.w};
         const float b1[4] = {B1.x, B1.y, B1.z, B1.w}, b2[4] = {B2.x, B2.y, B2.z, B2.w}, b3[4] = {B3.x, B3.y, B3.z, B3.w};
+        float kk[4] = {0.f, 0.f, 0.f, 0.f};   // -(m2*r2 + m3*r3): n2 + n3 = c2*r2 + c3*r3 + kk (resign only; r2 = a1, r3 = b1)
+        if (resign) { const float4 K = *reinterpret_cast<const float4*>(cst + 6 * C + c0 + i); kk[0] = K.x; kk[1] = K.y; kk[2] = K.z; kk[3] = K.w; }
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          float g = d.v[i + q] * (a.v[i + q] > 0.f ? 1.f : 0.01f);
+          const float pre = resign ? fmaf(xa.v[i + q], a1[q], fmaf(xb.v[i + q], b1[q], kk[q])) : a.v[i + q];
+          float g = d.v[i + q] * (pre > 0.f ? 1.f : 0.01f);
           oa.v[i + q] = fmaf(a1[q], g, fmaf(a2[q], xa.v[i + q], a3c[q]));
           ob.v[i + q] = fmaf(b1[q], g, fmaf(b2[q], xb.v[i + q], b3[q]));
         }

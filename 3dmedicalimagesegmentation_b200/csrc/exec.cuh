@@ -9,6 +9,8 @@
 // Caller owns all memory: parameters / gradients are PyTorch-layout fp32 pointers, the workspace is one buffer.
 #pragma once
 #include <type_traits>
+#include <functional>
+#include <vector>
 
 #include "ops.cuh"
 #include "edge_kernels.cuh"
@@ -42,6 +44,7 @@ enum ParamIdx {
 enum { B_LN1_W = 0, B_LN1_B, B_QKV_W, B_PROJ_W, B_PROJ_B, B_LN2_W, B_LN2_B, B_FC1_W, B_FC1_B, B_FC2_W, B_FC2_B, B_COUNT };
 
 enum { FLAG_NEED_ENCODER_GRAD = 1, FLAG_HAS_DLOGITS = 2, FLAG_HAS_DENC4 = 4, FLAG_SAVE_FOR_BACKWARD = 8, FLAG_NO_BACKWARD = 16,   // forward only: no backward call follows (inference)
+       FLAG_INPLACE_WGRADS = 32,   // backward with gradient events: keep the conv-stack weight gradients in place (default: deferred behind the ViT backward)
        FLAG_WEIGHTS_PACKED = 64 };   // the bf16 weight copies in this workspace are current (same workspace, unchanged parameters)
 
 struct Bump {
@@ -79,6 +82,7 @@ struct Workspace {
   float* wg_scratch; size_t wg_scratch_bytes;   // partial tiles of the deterministic weight-gradient epilogue (tc_wgrad.cuh)
   T *unsh;  // unsh: pixel-unshuffled dOut of a transposed conv [rows_in, 8*Co]  // bf16 mode: operand copies of the fp32 residual-stream gradients
   T *dvit, *datt, *dS, *gA, *dcat, *dc2, *dc3, *da1, *dc1;
+  T* dcs[5][3];          // per residual block (indexed like rs): dc1, dc2, dc3 kept until the deferred weight-gradient launches (Exec::defer_wg)
   // per-block operands of the DEFERRED parameter gradients (weight / bias / LayerNorm-parameter sums are issued per group of blocks,
   // see vit_param_grads): dyo[i+1] = d(hs[i]) and dyo[0] = d(x0) as T, dh[i] = d(fc1 pre-activation), dy1[i] = d(x1[i]) as T,
   // dqkv[i], dln2[i] / dln1[i] = gradients wrt the two LayerNorm outputs
@@ -209,6 +213,8 @@ struct Exec {
       size_t big = (size_t)B * V[0] * fs;
       w.gA = b.take<T>(big); w.dcat = b.take<T>(2 * big); w.dc2 = b.take<T>(big); w.dc3 = b.take<T>(big);
       w.da1 = b.take<T>(big); w.dc1 = b.take<T>(big); w.unsh = b.take<T>(big);
+      { const int lvl[5] = {0, 3, 2, 1, 0};
+        for (int k = 0; k < 5; ++k) for (int j = 0; j < 3; ++j) w.dcs[k][j] = b.take<T>((size_t)B * V[lvl[k]] * (fs << lvl[k])); }
       w.wg_scratch_bytes = 0;
       if constexpr (kTC) {
         const int lvl_of_blk[5] = {0, 3, 2, 1, 0};
@@ -283,7 +289,7 @@ struct Exec {
       const int ks = tc::plan_splitk(Mr, N, K, 1);
       EpStore<float> e = ep_plain<float>(w.part, N); e.splitk_nbat = 1; e.split_stride = (long)Mr * N;
       B200_TRY(tc::gemm(tc::operand(A, lda, 1), tc::operand(Wb, K, 1), e, Mr, N, K, 1, 1, st, false, ks));
-      *ss = SplitSum{w.part, ks, (long)Mr * N, bias, resid, xsum};
+      *ss = SplitSum{w.part, ks, (long)Mr * N, bias, resid, xsum, nullptr};
     }
     return 0;
   }
@@ -354,13 +360,20 @@ struct Exec {
   }
 
   // ------------------------------------------------------------ InstanceNorm helpers
+  // (sum, sumsq) accumulators whose (mean, rstd) have not been derived yet: the normalise pass that consumes `mr` does it in its
+  // prologue (elementwise.cuh: in_moments) instead of a finalize launch per statistic
+  struct PendStat { const float* mr; const double* acc; } pend_stat[4] = {};
+  void set_pending(const float* mr, const double* acc) {
+    for (auto& p : pend_stat) if (!p.mr || p.mr == mr) { p.mr = mr; p.acc = acc; return; }
+    pend_stat[0].mr = mr; pend_stat[0].acc = acc;   // unreachable: at most three statistics are in flight per residual block
+  }
+  const double* take_pending(const float* mr) {
+    if (mr) for (auto& p : pend_stat) if (p.mr == mr) { p.mr = nullptr; return p.acc; }
+    return nullptr;
+  }
   int in_stats(Cl<const T> x, long Vs, float* mr, cudaStream_t st, bool have_sums = false) {
+    if (have_sums) { set_pending(mr, w.stat_acc); return 0; }   // sums already accumulated by the conv epilogue
     B200_PROF("instnorm_stats", st);
-    if (have_sums) {  // sums already accumulated by the conv epilogue
-      B200_CUDA(launch_pdl(in_finalize_kernel, dim3(cdiv(c.B * x.C, 128)), dim3(128), 0, st, w.stat_acc, mr, c.B * x.C, 1.0 / (double)Vs));
-      B200_LAUNCH_CHECK();
-      return 0;
-    }
     constexpr int VN = Vec16<T>::N;
     B200_CHECK(x.C % VN == 0 && 256 % (x.C / VN) == 0 && x.pitch % VN == 0 && x.coff % VN == 0,
                "InstanceNorm channel count %d unsupported (need a power of two >= 8)", x.C);
@@ -368,15 +381,16 @@ struct Exec {
     dim3 g(in_grid_x(Vs, x.C / VN), c.B);
     B200_CUDA(launch_pdl(in_stats_kernel<T>, dim3(g), dim3(256), 256 * 2 * VN * sizeof(float), st, reinterpret_cast<const TR*>(x.p), ClView{x.pitch, x.coff}, x.C, Vs, w.stat_acc));
     B200_LAUNCH_CHECK();
-    B200_CUDA(launch_pdl(in_finalize_kernel, dim3(cdiv(c.B * x.C, 128)), dim3(128), 0, st, w.stat_acc, mr, c.B * x.C, 1.0 / (double)Vs));
-    B200_LAUNCH_CHECK();
+    set_pending(mr, w.stat_acc);
     return 0;
   }
-  int in_apply(Cl<const T> x, const float* mr, const T* x2, const float* mr2, Cl<T> out, long Vs, cudaStream_t st) {
+  int in_apply(Cl<const T> x, float* mr, const T* x2, float* mr2, Cl<T> out, long Vs, cudaStream_t st) {
     B200_PROF("instnorm_apply", st);
+    B200_CHECK(x.C <= 256, "InstanceNorm over %d channels unsupported (<= 256)", x.C);
     dim3 g(in_grid_x(Vs, x.C / Vec16<T>::N) * 2, c.B);
+    const double* a1 = take_pending(mr); const double* a2 = take_pending(mr2);
     B200_CUDA(launch_pdl(in_apply_kernel<T>, dim3(g), dim3(256), 0, st, reinterpret_cast<const TR*>(x.p), ClView{x.pitch, x.coff}, mr, reinterpret_cast<const TR*>(x2), ClView{x.C, 0}, mr2, out.p,
-                                          ClView{out.pitch, out.coff}, x.C, Vs, x2 != nullptr));
+                                          ClView{out.pitch, out.coff}, x.C, Vs, (int)(x2 != nullptr), a1, a2, 1.0 / (double)Vs));
     B200_LAUNCH_CHECK();
     return 0;
   }
@@ -450,8 +464,7 @@ struct Exec {
         else if (Co == 16) conv_in_fwd_kernel<T, 16><<<g, 256, sm, st>>>(raw, W1, W3, c.Cin, s.D, s.H, s.W, (TR*)c1.p, (TR*)c3.p, w.stat_acc, st3);
         else conv_in_fwd_kernel<T, 32><<<g, 256, sm, st>>>(raw, W1, W3, c.Cin, s.D, s.H, s.W, (TR*)c1.p, (TR*)c3.p, w.stat_acc, st3);
         B200_LAUNCH_CHECK();
-        B200_CUDA(launch_pdl(in_finalize_kernel, dim3(cdiv(c.B * Co, 128)), dim3(128), 0, st, w.stat_acc, r.mr1, c.B * Co, 1.0 / (double)Vs)); B200_LAUNCH_CHECK();
-        B200_CUDA(launch_pdl(in_finalize_kernel, dim3(cdiv(c.B * Co, 128)), dim3(128), 0, st, st3, r.mr3, c.B * Co, 1.0 / (double)Vs)); B200_LAUNCH_CHECK();
+        set_pending(r.mr1, w.stat_acc); set_pending(r.mr3, st3);
       }
       B200_TRY(in_apply(cl<const T>(c1.p, Co, 0, Co), r.mr1, nullptr, nullptr, a1, Vs, st));
       B200_TRY(conv_fwd(cl<const T>(a1.p, Co, 0, Co), s, W2, Co, 3, c2, w.stat_acc, &done, st));
@@ -468,8 +481,7 @@ struct Exec {
         double* st3 = w.stat_acc + (size_t)2 * c.B * 8 * c.fs;
         tc::HaloFused fu = {1, w.wcf[i3], c3.p, Co, 0, st3, nullptr, 0, 0};
         B200_TRY(tc::conv_halo(x.p, x.pitch, x.coff, x.C, s.N, s.D, s.H, s.W, w.wcf[i1], Co, c1.p, Co, 0, 0, w.stat_acc, st, &fu, 1));
-        B200_CUDA(launch_pdl(in_finalize_kernel, dim3(cdiv(c.B * Co, 128)), dim3(128), 0, st, w.stat_acc, r.mr1, c.B * Co, 1.0 / (double)Vs)); B200_LAUNCH_CHECK();
-        B200_CUDA(launch_pdl(in_finalize_kernel, dim3(cdiv(c.B * Co, 128)), dim3(128), 0, st, st3, r.mr3, c.B * Co, 1.0 / (double)Vs)); B200_LAUNCH_CHECK();
+        set_pending(r.mr1, w.stat_acc); set_pending(r.mr3, st3);
         fused13 = true;
       }
     }
@@ -487,9 +499,10 @@ struct Exec {
     if (head && out.pitch == Co && out.coff == 0) {
       B200_PROF("norm_head_fwd", st);
       dim3 g((unsigned)min(148L * 4, (Vs + 255) / 256), c.B);
-      if (Co == 8) in_apply_head_kernel<T, 8><<<g, 256, 0, st>>>((const TR*)c2.p, r.mr2, (const TR*)c3.p, r.mr3, out.p, head->Wh, head->bh, c.ncls, Vs, head->logits);
-      else if (Co == 16) in_apply_head_kernel<T, 16><<<g, 256, 0, st>>>((const TR*)c2.p, r.mr2, (const TR*)c3.p, r.mr3, out.p, head->Wh, head->bh, c.ncls, Vs, head->logits);
-      else in_apply_head_kernel<T, 32><<<g, 256, 0, st>>>((const TR*)c2.p, r.mr2, (const TR*)c3.p, r.mr3, out.p, head->Wh, head->bh, c.ncls, Vs, head->logits);
+      const double* a2 = take_pending(r.mr2); const double* a3 = take_pending(r.mr3); const double invV = 1.0 / (double)Vs;
+      if (Co == 8) in_apply_head_kernel<T, 8><<<g, 256, 0, st>>>((const TR*)c2.p, r.mr2, (const TR*)c3.p, r.mr3, out.p, head->Wh, head->bh, c.ncls, Vs, head->logits, a2, a3, invV);
+      else if (Co == 16) in_apply_head_kernel<T, 16><<<g, 256, 0, st>>>((const TR*)c2.p, r.mr2, (const TR*)c3.p, r.mr3, out.p, head->Wh, head->bh, c.ncls, Vs, head->logits, a2, a3, invV);
+      else in_apply_head_kernel<T, 32><<<g, 256, 0, st>>>((const TR*)c2.p, r.mr2, (const TR*)c3.p, r.mr3, out.p, head->Wh, head->bh, c.ncls, Vs, head->logits, a2, a3, invV);
       B200_LAUNCH_CHECK();
       return 0;
     }
@@ -503,22 +516,36 @@ struct Exec {
     constexpr int VN = Vec16<T>::N;
     Sp s = sp(level); long Vs = V[level]; int Co = out.C, Ci = x.C; int B = c.B;
     ClView pv{Co, 0};
-    size_t red_smem = 256 * 3 * VN * sizeof(float), cst_smem = 6 * (size_t)Co * sizeof(float);
-    dim3 gr(in_grid_x(Vs, Co / VN), B), ga(in_grid_x(Vs, Co / VN) * 2, B);
+    // data-parallel overlap: the weight gradients of the conv stacks are issued AFTER the ViT backward (flush_deferred), so that the
+    // 340 MB of ViT gradients are reduced behind them; their inputs dc1..3 then live in per-block buffers instead of the shared ones
+    const int blk = (int)(&r - w.rs);
+    T* const pdc1 = defer_wg ? w.dcs[blk][0] : w.dc1; T* const pdc2 = defer_wg ? w.dcs[blk][1] : w.dc2; T* const pdc3 = defer_wg ? w.dcs[blk][2] : w.dc3;
+    size_t red_smem = 256 * 3 * VN * sizeof(float), cst_smem = 7 * (size_t)Co * sizeof(float);
+    // the sign of the block output is recomputed from c2, c3 instead of reading `out` again (B200_INBWD_ACT=1 reads it)
+    static const bool read_act = getenv("B200_INBWD_ACT") != nullptr;
+    const T* actp = read_act ? out.p : (const T*)nullptr;
+    static const int grmul = getenv("B200_INBWD_GRID") ? atoi(getenv("B200_INBWD_GRID")) : 1;
+    dim3 gr(in_grid_x(Vs, Co / VN) * grmul, B), ga(in_grid_x(Vs, Co / VN) * 2, B);
     // final lrelu + two norms
     { B200_PROF("instnorm_bwd", st);
     B200_TRY(next_bwd());
-    B200_CUDA(launch_pdl(in_bwd_reduce_kernel<T, true>, dim3(gr), dim3(256), red_smem, st, dOut.p, ClView{dOut.pitch, dOut.coff}, out.p, ClView{out.pitch, out.coff},
-                                                      (const TR*)r.c2, pv, (const TR*)r.c3, pv, Co, Vs, w.bwd_acc));
-    B200_LAUNCH_CHECK();
-    B200_CUDA(launch_pdl(in_bwd_fixup_kernel, dim3(cdiv(B * Co, 128)), dim3(128), 0, st, w.bwd_acc, r.mr2, r.mr3, B * Co));
-    B200_LAUNCH_CHECK();
-    B200_CUDA(launch_pdl(in_bwd_apply_kernel<T, true>, dim3(ga), dim3(256), cst_smem, st, dOut.p, ClView{dOut.pitch, dOut.coff}, out.p, ClView{out.pitch, out.coff},
-                                               (const TR*)r.c2, pv, r.mr2, (const TR*)r.c3, pv, r.mr3, Co, Vs, w.bwd_acc, w.dc2, pv, w.dc3, pv));
+    if (read_act) {
+      B200_CUDA(launch_pdl(in_bwd_reduce_kernel<T, true, false>, dim3(gr), dim3(256), red_smem, st, dOut.p, ClView{dOut.pitch, dOut.coff}, actp, ClView{out.pitch, out.coff},
+                                                        (const TR*)r.c2, pv, (const TR*)r.c3, pv, Co, Vs, w.bwd_acc, (const float*)r.mr2, (const float*)r.mr3));
+      B200_LAUNCH_CHECK();
+      B200_CUDA(launch_pdl(in_bwd_apply_kernel<T, true, false>, dim3(ga), dim3(256), cst_smem, st, dOut.p, ClView{dOut.pitch, dOut.coff}, actp, ClView{out.pitch, out.coff},
+                                                 (const TR*)r.c2, pv, r.mr2, (const TR*)r.c3, pv, r.mr3, Co, Vs, w.bwd_acc, pdc2, pv, pdc3, pv));
+    } else {
+      B200_CUDA(launch_pdl(in_bwd_reduce_kernel<T, true, true>, dim3(gr), dim3(256), red_smem, st, dOut.p, ClView{dOut.pitch, dOut.coff}, actp, ClView{out.pitch, out.coff},
+                                                        (const TR*)r.c2, pv, (const TR*)r.c3, pv, Co, Vs, w.bwd_acc, (const float*)r.mr2, (const float*)r.mr3));
+      B200_LAUNCH_CHECK();
+      B200_CUDA(launch_pdl(in_bwd_apply_kernel<T, true, true>, dim3(ga), dim3(256), cst_smem, st, dOut.p, ClView{dOut.pitch, dOut.coff}, actp, ClView{out.pitch, out.coff},
+                                                 (const TR*)r.c2, pv, r.mr2, (const TR*)r.c3, pv, r.mr3, Co, Vs, w.bwd_acc, pdc2, pv, pdc3, pv));
+    }
     B200_LAUNCH_CHECK(); }
-    Cl<const T> dc2 = cl<const T>(w.dc2, Co, 0, Co), dc3 = cl<const T>(w.dc3, Co, 0, Co), a1 = cl<const T>(r.a1, Co, 0, Co);
+    Cl<const T> dc2 = cl<const T>(pdc2, Co, 0, Co), dc3 = cl<const T>(pdc3, Co, 0, Co), a1 = cl<const T>(r.a1, Co, 0, Co);
     // conv2
-    if (dW2) { B200_TRY(zero_grad(dW2, (size_t)Co * Co * 27, st)); B200_TRY(conv_wgrad(a1, dc2, s, 3, dW2, st)); }
+    if (dW2) B200_TRY(run_or_defer([=](cudaStream_t st) -> int { B200_TRY(zero_grad(dW2, (size_t)Co * Co * 27, st)); return conv_wgrad(a1, dc2, s, 3, dW2, st); }, st));
     // lrelu + norm1: the reduction pass (sum g, sum g*n) rides on the dgrad epilogue where the kernel supports it (tc_conv_halo48.cuh)
     B200_TRY(next_bwd());
     bool folded = false;
@@ -535,15 +562,16 @@ struct Exec {
     }
     { B200_PROF("instnorm_bwd", st);
     if (!folded) {
-    B200_CUDA(launch_pdl(in_bwd_reduce_kernel<T, false>, dim3(gr), dim3(256), red_smem, st, w.da1, pv, r.a1, pv, (const TR*)nullptr, pv, (const TR*)nullptr, pv, Co, Vs, w.bwd_acc));
+    B200_CUDA(launch_pdl(in_bwd_reduce_kernel<T, false>, dim3(gr), dim3(256), red_smem, st, w.da1, pv, r.a1, pv, (const TR*)nullptr, pv, (const TR*)nullptr, pv, Co, Vs, w.bwd_acc, (const float*)nullptr, (const float*)nullptr));
     B200_LAUNCH_CHECK(); }
     B200_CUDA(launch_pdl(in_bwd_apply_kernel<T, false>, dim3(ga), dim3(256), cst_smem, st, w.da1, pv, r.a1, pv, (const TR*)nullptr, pv, r.mr1, (const TR*)nullptr, pv, nullptr, Co, Vs, w.bwd_acc,
-                                               w.dc1, pv, nullptr, pv));
+                                               pdc1, pv, nullptr, pv));
     B200_LAUNCH_CHECK(); }
-    Cl<const T> dc1 = cl<const T>(w.dc1, Co, 0, Co);
+    Cl<const T> dc1 = cl<const T>(pdc1, Co, 0, Co);
     if (raw) {   // encoder1: both weight gradients from the raw fp32 input in one dedicated kernel
-      B200_PROF("enc1_conv_wgrad", st);
       B200_CHECK(dW1 && dW3, "encoder1 weight gradients are produced together");
+      return run_or_defer([=](cudaStream_t st) -> int {
+      B200_PROF("enc1_conv_wgrad", st);
       B200_TRY(zero_grad(dW1, (size_t)Co * Ci * 27, st));
       B200_TRY(zero_grad(dW3, (size_t)Co * Ci, st));
       long chunk = 4096;
@@ -551,16 +579,17 @@ struct Exec {
       if (s.W % 2 == 0 && !getenv("B200_ENC1_V1")) {   // two voxels x eight channels x nine taps per thread
         const long ppb = 4096;
         dim3 g2((unsigned)((Vs / 2 + ppb - 1) / ppb), B, (unsigned)(3 * (Co / 8) * Ci));
-        if (Co == 8) conv_in_wgrad2_kernel<T, 8><<<g2, 256, 0, st>>>(raw, w.dc1, w.dc3, Ci, s.D, s.H, s.W, ppb, dW1, dW3);
-        else if (Co == 16) conv_in_wgrad2_kernel<T, 16><<<g2, 256, 0, st>>>(raw, w.dc1, w.dc3, Ci, s.D, s.H, s.W, ppb, dW1, dW3);
-        else conv_in_wgrad2_kernel<T, 32><<<g2, 256, 0, st>>>(raw, w.dc1, w.dc3, Ci, s.D, s.H, s.W, ppb, dW1, dW3);
+        if (Co == 8) conv_in_wgrad2_kernel<T, 8><<<g2, 256, 0, st>>>(raw, pdc1, pdc3, Ci, s.D, s.H, s.W, ppb, dW1, dW3);
+        else if (Co == 16) conv_in_wgrad2_kernel<T, 16><<<g2, 256, 0, st>>>(raw, pdc1, pdc3, Ci, s.D, s.H, s.W, ppb, dW1, dW3);
+        else conv_in_wgrad2_kernel<T, 32><<<g2, 256, 0, st>>>(raw, pdc1, pdc3, Ci, s.D, s.H, s.W, ppb, dW1, dW3);
       } else
-      if (Co == 8) conv_in_wgrad_kernel<T, 8><<<g, 256, 0, st>>>(raw, w.dc1, w.dc3, Ci, s.D, s.H, s.W, chunk, dW1, dW3);
-      else if (Co == 16) conv_in_wgrad_kernel<T, 16><<<g, 256, 0, st>>>(raw, w.dc1, w.dc3, Ci, s.D, s.H, s.W, chunk, dW1, dW3);
-      else conv_in_wgrad_kernel<T, 32><<<g, 256, 0, st>>>(raw, w.dc1, w.dc3, Ci, s.D, s.H, s.W, chunk, dW1, dW3);
+      if (Co == 8) conv_in_wgrad_kernel<T, 8><<<g, 256, 0, st>>>(raw, pdc1, pdc3, Ci, s.D, s.H, s.W, chunk, dW1, dW3);
+      else if (Co == 16) conv_in_wgrad_kernel<T, 16><<<g, 256, 0, st>>>(raw, pdc1, pdc3, Ci, s.D, s.H, s.W, chunk, dW1, dW3);
+      else conv_in_wgrad_kernel<T, 32><<<g, 256, 0, st>>>(raw, pdc1, pdc3, Ci, s.D, s.H, s.W, chunk, dW1, dW3);
       B200_LAUNCH_CHECK();
-      return 0;
+      return 0; }, st);
     }
+    B200_TRY(run_or_defer([=](cudaStream_t st) -> int {
     bool wg_fused = false;
     if constexpr (kTC) {
       // conv1 (3^3) and conv3 (1^3) read the same x: one halo weight-gradient launch with a tenth accumulator for the 1^3 tap
@@ -579,6 +608,7 @@ struct Exec {
       if (dW1) { B200_TRY(zero_grad(dW1, (size_t)Co * Ci * 27, st)); B200_TRY(conv_wgrad(x, dc1, s, 3, dW1, st)); }
       if (dW3) { B200_TRY(zero_grad(dW3, (size_t)Co * Ci, st)); B200_TRY(conv_wgrad(x, dc3, s, 1, dW3, st)); }
     }
+    return 0; }, st));
     if (dx.p) {
       if constexpr (kTC) {   // dx = dgrad3x3(dc1) + dgrad1x1(dc3) in one kernel (second input tile, same accumulator)
         int i1 = conv_index(W1), i3 = conv_index(W3);
@@ -622,11 +652,15 @@ struct Exec {
     // --- transformer blocks (a6-a8)
     float scale = 1.0f / sqrtf((float)dh);
     SplitSum pend; memset(&pend, 0, sizeof(pend));   // split-K partials of the previous N = hidden GEMM, consumed by the next LayerNorm
+    int hsT_done = 0;
     for (int i = 0; i < 12; ++i) {
       const float* const* bp = P + P_BLK0 + i * B_COUNT;
       const float* xin = i ? w.hs[i - 1] : w.x0;
+      // hidden states 3 / 6 / 9 (= hs[i - 1] here) feed the encoders as T: the LayerNorm that forms them from the split-K partials
+      // stores that copy too
+      if (pend.nsplit && (i == 4 || i == 7 || i == 10)) { pend.xsum_cast = w.hsT[(i - 4) / 3]; hsT_done |= 1 << ((i - 4) / 3); }
       B200_TRY(launch_layernorm_fwd<T>(xin, bp[B_LN1_W], bp[B_LN1_B], w.ln1[i], w.ln1s[i], M, H, st, pend.nsplit ? &pend : nullptr));
-      pend.nsplit = 0;
+      pend.nsplit = 0; pend.xsum_cast = nullptr;
       B200_TRY(linear_fwd<T>(w.ln1[i], H, bp[B_QKV_W], w.wqkv[i], M, 3 * H, H, ep_plain<T>(w.qkv[i], 3 * H), st));
       B200_TRY(attention_fwd(i, scale, st));
       if (can_split(M, H, H)) {
@@ -649,7 +683,7 @@ struct Exec {
       }
     }
     B200_TRY(launch_layernorm_fwd<T>(w.hs[11], P[P_NORM_W], P[P_NORM_B], w.vit_out, w.lnfs, M, H, st, pend.nsplit ? &pend : nullptr));
-    for (int k = 0; k < 3; ++k) B200_TRY(launch_cast<float, T>(w.hs[3 + 3 * k], w.hsT[k], (long)M * H, st));
+    for (int k = 0; k < 3; ++k) if (!(hsT_done >> k & 1)) B200_TRY(launch_cast<float, T>(w.hs[3 + 3 * k], w.hsT[k], (long)M * H, st));
 
     B200_PROFC_END(st); B200_PROFC_BEGIN("F3 encoders", st);
     // --- encoder1 on the input volume (a9) -> upper half of concat2
@@ -715,6 +749,22 @@ struct Exec {
   // blocks from the top (the first also covers vit.norm, the last also the patch embedding).  4 / 7 / 13 events = groups of 4 / 2 / 1
   // blocks; the deferred parameter-gradient launches (vit_param_grads) use the same grouping.
   cudaEvent_t grad_ev[13]; int n_grad_ev = 0;
+  // With gradient events set (data-parallel overlap) the conv-stack weight gradients only feed the optimizer, like the ViT parameter
+  // gradients: they are queued here and launched after the ViT backward, and event 0 is recorded LAST (the host side reduces the
+  // conv range last: unetr.py).  FLAG_INPLACE_WGRADS keeps the in-place order.
+  bool defer_wg = false;
+  std::vector<std::function<int(cudaStream_t)>> deferred;
+  template <class F> int run_or_defer(F&& job, cudaStream_t st) {
+    if (!defer_wg) return job(st);
+    deferred.emplace_back(std::forward<F>(job));
+    return 0;
+  }
+  int flush_deferred(cudaStream_t st) {
+    int rc = 0;
+    for (auto& j : deferred) { rc = j(st); if (rc) break; }
+    deferred.clear();
+    return rc;
+  }
   int vit_group() const { return n_grad_ev == 13 ? 1 : n_grad_ev == 7 ? 2 : 4; }
   void mark_grads(int k, cudaStream_t st) { if (k < n_grad_ev) cudaEventRecord(grad_ev[k], st); }
 
@@ -849,6 +899,18 @@ struct Exec {
   // G: gradient pointers indexed like P (null = not wanted).  Workspace must be the one the forward filled.
   int backward(const float* const* P, float* const* G, const float* x_in, char* ws, const float* d_enc4, const float* d_logits,
                int flags, cudaStream_t st) {
+    defer_wg = n_grad_ev > 0 && !(flags & FLAG_INPLACE_WGRADS);
+    deferred.clear();
+    int rc = backward_impl(P, G, x_in, ws, d_enc4, d_logits, flags, st);
+    if (defer_wg) {
+      if (!rc) { B200_PROFC_BEGIN("B3 deferred conv wgrads", st); rc = flush_deferred(st); B200_PROFC_END(st); }
+      deferred.clear();
+      if (!rc) mark_grads(0, st);
+    }
+    return rc;
+  }
+  int backward_impl(const float* const* P, float* const* G, const float* x_in, char* ws, const float* d_enc4, const float* d_logits,
+                    int flags, cudaStream_t st) {
     layout(ws, true);
     if (kTC) { B200_CHECK(packed_base, "bf16 mode needs the packed-weight buffer (b200_unetr_set_packed_weights)"); layout_packed(packed_base); }
     cur_params = P;
@@ -948,7 +1010,7 @@ struct Exec {
       return 0;
 
     // --- ViT backward
-    mark_grads(0, st);
+    if (!defer_wg) mark_grads(0, st);
     B200_PROFC_END(st); B200_PROFC_BEGIN("B2 vit+patch", st);
     float scale = 1.0f / sqrtf((float)dh);
     int top = 11;
@@ -970,8 +1032,7 @@ struct Exec {
       const float* xin = i ? w.hs[i - 1] : w.x0;
       T* dyo = w.dyo[i + 1];      // d(hs[i]) as T (the fp32 original is w.dx)
       if (i == 9 || i == 6 || i == 3) {
-        B200_TRY(launch_add(w.dx, w.dhs[(i - 3) / 3], (long)M * H, st));
-        B200_TRY(launch_cast<float, T>(w.dx, dyo, (long)M * H, st));
+        B200_TRY(launch_add_cast<T>(w.dx, w.dhs[(i - 3) / 3], dyo, (long)M * H, st));
       }
       // hs = x1 + fc2(h) + b2
       { EpStore<T> ep = ep_plain<T>(w.dh[i], F); ep.act = ACT_MUL_SAVED; ep.usrc = w.u[i];   // du = (dx W2) * gelu'(u), gelu'(u) saved by the forward epilogue

@@ -198,6 +198,12 @@ class _UnetrFunction(torch.autograd.Function):
                 lo = first(3 + (12 - k * gs) * 11) if k < ng - 1 else 0
                 ranges.append((evs[k], lo, hi))
                 hi = lo
+            # with events set the engine launches the conv-stack weight gradients AFTER the ViT backward and records event 0 last
+            # (exec.cuh: defer_wg), so the 340 MB of ViT gradients cross NVLink behind them: reduce the conv range last
+            if module.defer_conv_wgrads:
+                ranges = ranges[1:] + ranges[:1]
+            else:
+                flags |= _lib.FLAG_INPLACE_WGRADS
             module._grad_ready = (flat, ranges, [(p, g.data_ptr()) for p, g in zip(params, grads) if g is not None])
         else:
             lib.b200_unetr_set_grad_events(ctx.handle, None, 0)
@@ -270,6 +276,8 @@ class UNETR(nn.Module):
         self.compute_mode = os.environ.get("B200_UNETR_MODE", "bf16")
         self.inference_graph = False       # see _graph_forward; switched on by sliding_window_inference for its loop
         self.overlap_grad_reduce = False   # set by parallel.GradientAllReduce
+        # with overlap_grad_reduce: launch the conv-stack weight gradients after the ViT backward and reduce the conv range last
+        self.defer_conv_wgrads = not os.environ.get("B200_NO_DEFER_WGRAD")
         self.grad_groups = 7               # gradient-ready events per backward when overlapping: conv stack + 6 groups of 2 blocks
         self._init_runtime()
 

@@ -26,6 +26,7 @@ extern "C" {
 #define B200_NEED_ENCODER_GRAD 1 /* 0 == forward(x, freeze_encoder=True), unetr.py:183-192 */
 #define B200_HAS_DLOGITS 2
 #define B200_HAS_DENC4 4
+#define B200_INPLACE_WGRADS 32 /* backward with gradient events set: launch the conv-stack weight gradients in place (default: after the ViT backward, event 0 last) */
 #define B200_NO_BACKWARD 16 /* forward only: no backward call follows (inference); buffers only the backward reads may be left unwritten */
 #define B200_WEIGHTS_PACKED 64 /* forward only: the bf16 weight copies in the packed buffer are current (b200_unetr_set_packed_weights) */
 
@@ -214,7 +215,7 @@ int b200_test_tc_wgrad(const void* x, int x_pitch, int x_coff, int Ci, const voi
  * gradient (tests/test_gpu_ops_bwd.py).  bf16_mode != 0: activations / gradients are bf16 (raw conv outputs fp16), else fp32.
  *  layernorm_bwd: g [M,H], x fp32 [M,H], stats fp32 [M][2] = (mean, rstd), gamma [H]; dx_out fp32 = dx_res (nullable) + dL/dx,
  *                 dx_cast = the same in the activation type, dgamma / dbeta [H]                       (transformer blocks, unetr.py:69-76)
- *  instnorm_bwd:  channels-last [N,V,C]; two != 0: out = lrelu(norm(c2) + norm(c3)) with ra = c2, rb = c3 -> da = d c2, db = d c3;
+ *  instnorm_bwd:  channels-last [N,V,C]; two != 0: out = lrelu(norm(c2) + norm(c3)) with ra = c2, rb = c3 -> da = d c2, db = d c3 (act NULL: sign recomputed from c2, c3);
  *                 two == 0: act = lrelu(norm(c1)) -> da = d c1; mra / mrb = (mean, rstd) [N][C][2]; acc: double [N][C][3] scratch
  *  head_bwd:      dlogits fp32 [N][ncls][V], d0 [N,V,fs] -> g = d(d0), dWh [ncls][fs], dbh [ncls]      (UnetOutBlock, unetr.py:175) */
 int b200_test_layernorm_bwd(const void* g, const float* x, const float* stats, const float* gamma, const float* dx_res, float* dx_out,

@@ -77,6 +77,12 @@ def test_instnorm_lrelu_backward(pkg, bf16, N, V, C):
     L.check(lib.b200_test_instnorm_bwd(1, *[L.ptr(t) for t in args], N, C, V, L.ptr(acc), L.ptr(da), L.ptr(db), bf16, L.stream_ptr()), "in_bwd two")
     torch.cuda.synchronize()
     check("dc2", da.float().cpu(), a2.grad, bf16); check("dc3", db.float().cpu(), a3.grad, bf16)
+    # the engine's default: no saved activation -- the sign of n2 + n3 is recomputed from c2, c3 and their (mean, rstd)
+    da.zero_(); db.zero_()
+    args[1] = None
+    L.check(lib.b200_test_instnorm_bwd(1, *[L.ptr(t) for t in args], N, C, V, L.ptr(acc), L.ptr(da), L.ptr(db), bf16, L.stream_ptr()), "in_bwd two, sign recomputed")
+    torch.cuda.synchronize()
+    check("dc2 (sign recomputed)", da.float().cpu(), a2.grad, bf16); check("dc3 (sign recomputed)", db.float().cpu(), a3.grad, bf16)
     # ---- one input, normalised value recovered from the saved activation
     a1 = c2.float().clone().requires_grad_(True)
     n1, m1, r1 = _instnorm(a1)

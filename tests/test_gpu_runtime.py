@@ -192,3 +192,38 @@ def test_mode_switch_repacks(pkg):
     with torch.no_grad():
         _, want = fresh(x)
     assert torch.isfinite(got).all() and torch.equal(got, want)
+
+
+@pytest.mark.parametrize("mode", ["bf16", "fp32"])
+def test_deferred_conv_weight_gradients_match_the_in_place_order(pkg, mode):
+    """With gradient-ready events set (data-parallel overlap) the conv-stack weight gradients are launched after the ViT backward from
+    per-block copies of their output gradients (exec.cuh: defer_wg) and the conv range is handed to the reducer last: same gradients
+    as the in-place order (fp32 atomics: order-of-summation noise only), ranges still a partition of the flat buffer."""
+    model = make(pkg, mode=mode)
+    loss_fn = pkg.DiceCELoss(to_onehot_y=True, softmax=True)
+    x, y = data()
+
+    def grads():
+        model.zero_grad(set_to_none=True)
+        _, logits = model(x)
+        loss_fn(logits, y).backward()
+        torch.cuda.synchronize()
+        return {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None}
+
+    want = grads()
+    model.overlap_grad_reduce = True
+    got = grads()
+    ready = model._grad_ready
+    assert ready is not None
+    flat, ranges, views = ready
+    assert ranges[-1][2] == flat.numel() and ranges[-1][1] > 0, "the conv range is reduced last"
+    covered = sorted((lo, hi) for _, lo, hi in ranges)
+    assert covered[0][0] == 0 and all(a[1] == b[0] for a, b in zip(covered, covered[1:])) and covered[-1][1] == flat.numel()
+    assert all(ev.query() for ev, _, _ in ranges)
+    assert got.keys() == want.keys()
+    for n in want:
+        torch.testing.assert_close(got[n], want[n], rtol=1e-3, atol=1e-5 * float(want[n].abs().max()) + 1e-12, msg=lambda m: f"{n}: {m}")
+    model.overlap_grad_reduce = False
+    again = grads()
+    for n in want:
+        torch.testing.assert_close(again[n], want[n], rtol=1e-3, atol=1e-5 * float(want[n].abs().max()) + 1e-12, msg=lambda m: f"{n}: {m}")
