@@ -44,7 +44,7 @@ enum ParamIdx {
 enum { B_LN1_W = 0, B_LN1_B, B_QKV_W, B_PROJ_W, B_PROJ_B, B_LN2_W, B_LN2_B, B_FC1_W, B_FC1_B, B_FC2_W, B_FC2_B, B_COUNT };
 
 enum { FLAG_NEED_ENCODER_GRAD = 1, FLAG_HAS_DLOGITS = 2, FLAG_HAS_DENC4 = 4, FLAG_SAVE_FOR_BACKWARD = 8, FLAG_NO_BACKWARD = 16,   // forward only: no backward call follows (inference)
-       FLAG_INPLACE_WGRADS = 32,   // backward with gradient events: keep the conv-stack weight gradients in place (default: deferred behind the ViT backward)
+       FLAG_INPLACE_WGRADS = 32,   // backward with gradient events: keep the conv-stack weight gradients in place (otherwise: deferred behind the ViT backward)
        FLAG_WEIGHTS_PACKED = 64 };   // the bf16 weight copies in this workspace are current (same workspace, unchanged parameters)
 
 struct Bump {

@@ -198,8 +198,8 @@ class _UnetrFunction(torch.autograd.Function):
                 lo = first(3 + (12 - k * gs) * 11) if k < ng - 1 else 0
                 ranges.append((evs[k], lo, hi))
                 hi = lo
-            # with events set the engine launches the conv-stack weight gradients AFTER the ViT backward and records event 0 last
-            # (exec.cuh: defer_wg), so the 340 MB of ViT gradients cross NVLink behind them: reduce the conv range last
+            # defer_conv_wgrads: the engine launches the conv-stack weight gradients AFTER the ViT backward and records event 0 last
+            # (exec.cuh: defer_wg): reduce the conv range last
             if module.defer_conv_wgrads:
                 ranges = ranges[1:] + ranges[:1]
             else:
@@ -276,8 +276,11 @@ class UNETR(nn.Module):
         self.compute_mode = os.environ.get("B200_UNETR_MODE", "bf16")
         self.inference_graph = False       # see _graph_forward; switched on by sliding_window_inference for its loop
         self.overlap_grad_reduce = False   # set by parallel.GradientAllReduce
-        # with overlap_grad_reduce: launch the conv-stack weight gradients after the ViT backward and reduce the conv range last
-        self.defer_conv_wgrads = not os.environ.get("B200_NO_DEFER_WGRAD")
+        # with overlap_grad_reduce: launch the conv-stack weight gradients after the ViT backward and reduce the conv range last, so
+        # that the 340 MB of ViT gradients cross NVLink behind them.  Measured equal to the in-place order within run-to-run noise
+        # (N = 8: 5.83 / 5.94 ms deferred vs 5.86 / 5.90 in place; N = 2: 5.70 vs 5.66, profiles/r02_dp_sweep_n*.json) -- the
+        # all-reduce tail is not what limits data parallel -- so the in-place order stays the default.  B200_DEFER_WGRAD=1 turns it on.
+        self.defer_conv_wgrads = bool(os.environ.get("B200_DEFER_WGRAD"))
         self.grad_groups = 7               # gradient-ready events per backward when overlapping: conv stack + 6 groups of 2 blocks
         self._init_runtime()
 

@@ -26,7 +26,7 @@ extern "C" {
 #define B200_NEED_ENCODER_GRAD 1 /* 0 == forward(x, freeze_encoder=True), unetr.py:183-192 */
 #define B200_HAS_DLOGITS 2
 #define B200_HAS_DENC4 4
-#define B200_INPLACE_WGRADS 32 /* backward with gradient events set: launch the conv-stack weight gradients in place (default: after the ViT backward, event 0 last) */
+#define B200_INPLACE_WGRADS 32 /* backward with gradient events set: launch the conv-stack weight gradients in place (otherwise: after the ViT backward, event 0 last) */
 #define B200_NO_BACKWARD 16 /* forward only: no backward call follows (inference); buffers only the backward reads may be left unwritten */
 #define B200_WEIGHTS_PACKED 64 /* forward only: the bf16 weight copies in the packed buffer are current (b200_unetr_set_packed_weights) */
 

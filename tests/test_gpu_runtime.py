@@ -212,6 +212,7 @@ def test_deferred_conv_weight_gradients_match_the_in_place_order(pkg, mode):
 
     want = grads()
     model.overlap_grad_reduce = True
+    model.defer_conv_wgrads = True
     got = grads()
     ready = model._grad_ready
     assert ready is not None
@@ -223,6 +224,12 @@ def test_deferred_conv_weight_gradients_match_the_in_place_order(pkg, mode):
     assert got.keys() == want.keys()
     for n in want:
         torch.testing.assert_close(got[n], want[n], rtol=1e-3, atol=1e-5 * float(want[n].abs().max()) + 1e-12, msg=lambda m: f"{n}: {m}")
+    # events set, in-place order (the default): conv range first
+    model.defer_conv_wgrads = False
+    inplace = grads()
+    assert model._grad_ready[1][0][2] == flat.numel(), "in-place order: the conv range is reduced first"
+    for n in want:
+        torch.testing.assert_close(inplace[n], want[n], rtol=1e-3, atol=1e-5 * float(want[n].abs().max()) + 1e-12, msg=lambda m: f"{n}: {m}")
     model.overlap_grad_reduce = False
     again = grads()
     for n in want:

@@ -4,6 +4,4 @@ import json,sys
 d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('$tag', round(d['ms_per_step'],4), round(d['value'],1))"; }
 run default A=1
 run read_act B200_INBWD_ACT=1
-run grid2 B200_INBWD_GRID=2
 run default2 A=1
-run read_act2 B200_INBWD_ACT=1
