@@ -30,7 +30,10 @@ for path in sys.argv[1:]:
             if pat in name:
                 out[key] = {"launch": desc, "kernel": name[:100], "dram_bytes_per_launch": int(val(r, "dram__bytes_read.sum") + val(r, "dram__bytes_write.sum")),
                             "duration_us_under_ncu": round(val(r, "gpu__time_duration.sum") * 1e6, 1),
-                            "tensor_pipe_busy": round(val(r, "sm__pipe_tensor_subpipe_hmma_cycles_active_realtime.avg") / val(r, "sm__cycles_elapsed.max"), 3)}
+                            # the metric /opt/skills/guides/B200_PROFILING.md names: tensor pipe active cycles as a fraction of the launch
+                            # (rounds before r02's final summary divided sm__pipe_tensor_subpipe_hmma_cycles_active_realtime by
+                            # sm__cycles_elapsed, which is not a fraction -- it exceeds 1 -- and overstated the pipe occupancy)
+                            "tensor_pipe_busy": round(val(r, "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed") / 100, 3)}
                 if out[key]["tensor_pipe_busy"] != out[key]["tensor_pipe_busy"]:      # metric not collected in this pass
                     out[key]["tensor_pipe_busy"] = prev.get(key, {}).get("tensor_pipe_busy")
                 prev[key] = dict(out[key])
