@@ -629,6 +629,7 @@ struct Exec {
     layout(ws, false);
     if (kTC) { B200_CHECK(packed_base, "bf16 mode needs the packed-weight buffer (b200_unetr_set_packed_weights)"); layout_packed(packed_base); }
     no_backward = (flags & FLAG_NO_BACKWARD) != 0;
+    for (auto& p : pend_stat) p = PendStat{nullptr, nullptr};   // nothing carries over from a forward that ended early
     B200_CUDA(cudaMemsetAsync(w.stat_pool, 0, sizeof(double) * kStatSlots * 4 * c.B * 8 * c.fs, st));
     B200_PROFC_BEGIN("F1 pack+patch", st);
     int B = c.B, fs = c.fs;
