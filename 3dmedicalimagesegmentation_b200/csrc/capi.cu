@@ -365,11 +365,13 @@ int b200_sw_accumulate_n(float* acc, const float* pred, const b200_sw_geom* g, c
     x1 = std::max(x1, a); y1 = std::max(y1, b); z1 = std::max(z1, c);
   }
   bx.nx = x1 - bx.x0 + sg.r0; bx.ny = y1 - bx.y0 + sg.r1; bx.nz = z1 - bx.z0 + sg.r2;
-  long rows = (long)bx.nx * bx.ny * sg.C;         // one warp per (c, x, y) line
   bool v4 = sg.r2 % 4 == 0 && sg.PW % 4 == 0 && bx.z0 % 4 == 0 && bx.nz % 4 == 0 && (((uintptr_t)acc | (uintptr_t)pred) & 15) == 0;
   for (int i = 0; i < n; ++i) v4 = v4 && wb.w[i].s2 % 4 == 0;
-  if (v4) sw_accumulate_multi_kernel<4><<<(unsigned)min(148L * 16, (rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(acc, pred, sg, wb, bx);
-  else sw_accumulate_multi_kernel<1><<<(unsigned)min(148L * 16, (rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(acc, pred, sg, wb, bx);
+  B200_CHECK(sg.C <= 65535, "sw_accumulate_n: at most 65535 channels");
+  const dim3 grid((unsigned)bx.nx, (unsigned)sg.C);      // one block per (row, channel) plane of the bounding box
+  if (v4 && n <= 4) sw_accumulate_multi_kernel<4, 4><<<grid, 256, 0, (cudaStream_t)stream>>>(acc, pred, sg, wb, bx);
+  else if (v4) sw_accumulate_multi_kernel<4, 16><<<grid, 256, 0, (cudaStream_t)stream>>>(acc, pred, sg, wb, bx);
+  else sw_accumulate_multi_kernel<1, 16><<<grid, 256, 0, (cudaStream_t)stream>>>(acc, pred, sg, wb, bx);
   B200_LAUNCH_CHECK();
   return 0;
 }
@@ -432,11 +434,13 @@ int b200_sw_accumulate_slab(float* acc, const b200_sw_geom* g, const void* const
   bx.x0 = std::max(bx.x0, xoff); x1 = std::min(x1, xoff + nrows);
   bx.nx = x1 - bx.x0; bx.ny = y1 - bx.y0 + sg.r1; bx.nz = z1 - bx.z0 + sg.r2;
   if (bx.nx <= 0) return 0;
-  long rows = (long)bx.nx * bx.ny * sg.C;
   bool v4 = sg.r2 % 4 == 0 && sg.PW % 4 == 0 && bx.z0 % 4 == 0 && bx.nz % 4 == 0 && ((uintptr_t)acc & 15) == 0;
   for (int i = 0; i < n; ++i) v4 = v4 && ps.p[i].s2 % 4 == 0 && ((uintptr_t)ps.p[i].pred & 15) == 0;
-  if (v4) sw_accumulate_slab_kernel<4><<<(unsigned)min(148L * 16, (rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(acc, sg, ps, bx, xoff, nrows);
-  else sw_accumulate_slab_kernel<1><<<(unsigned)min(148L * 16, (rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(acc, sg, ps, bx, xoff, nrows);
+  B200_CHECK(sg.C <= 65535, "sw_accumulate_slab: at most 65535 channels");
+  const dim3 grid((unsigned)bx.nx, (unsigned)sg.C);      // one block per (row, channel) plane of the bounding box
+  if (v4 && n <= 4) sw_accumulate_slab_kernel<4, 4><<<grid, 256, 0, (cudaStream_t)stream>>>(acc, sg, ps, bx, xoff, nrows);
+  else if (v4) sw_accumulate_slab_kernel<4, 16><<<grid, 256, 0, (cudaStream_t)stream>>>(acc, sg, ps, bx, xoff, nrows);
+  else sw_accumulate_slab_kernel<1, 16><<<grid, 256, 0, (cudaStream_t)stream>>>(acc, sg, ps, bx, xoff, nrows);
   B200_LAUNCH_CHECK();
   return 0;
 }

@@ -28,3 +28,17 @@ with torch.no_grad():
     pkg.sliding_window_inference(vol, (96,) * 3, 4, model, overlap=0.5)
     e1.record(); t1 = time.perf_counter(); torch.cuda.synchronize()
     print(f"sliding window: GPU {e0.elapsed_time(e1):.1f} ms, host enqueue {1e3 * (t1 - t0):.1f} ms")
+    # the loop's own kernels without the predictor: a predictor that returns a fixed tensor leaves gather + accumulate + finalize
+    fixed = torch.randn(4, 14, 96, 96, 96, device=dev)
+    fake = lambda w: fixed[:w.shape[0]]
+    for _ in range(2):
+        pkg.sliding_window_inference(vol, (96,) * 3, 4, fake, overlap=0.5)
+    torch.cuda.synchronize()
+    e0.record()
+    pkg.sliding_window_inference(vol, (96,) * 3, 4, fake, overlap=0.5)
+    e1.record(); torch.cuda.synchronize()
+    print(f"sliding window with a constant predictor (gather + accumulate + normalise only): {e0.elapsed_time(e1):.1f} ms")
+    e0.record()
+    pkg.sliding_window_inference(vol, (96,) * 3, 4, fake, overlap=0.5, return_argmax=True)
+    e1.record(); torch.cuda.synchronize()
+    print(f"  ... with the argmax mask: {e0.elapsed_time(e1):.1f} ms")
