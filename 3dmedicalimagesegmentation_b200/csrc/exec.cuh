@@ -351,9 +351,10 @@ struct Exec {
         pj.j[m++] = PackJob{P[p], w.wcf[i], w.wcd[i], co, ci, ks * ks * ks, 1};
       }
       pj.count = m;
-      // grid.x sized for the largest job (256 -> 128 channels, 27 taps = 885 k elements): 32 blocks per job left it at 108 serial
-      // scattered stores per thread (117 us for 33 MB); small jobs' surplus blocks exit at once
-      multi_pack_kernel<<<dim3(296, m), 256, 0, st>>>(pj);
+      for (int i = 0; i < m; ++i)
+        B200_CHECK(pj.j[i].kind == 0 ? pj.j[i].b * 8 <= kPackTile : pj.j[i].taps <= 27, "weight re-layout: tile does not fit (job %d)", i);
+      // grid.x = tiles of the largest job (256 -> 128 channels: 8 x 16 tiles of 16 co x 16 ci x 27 taps); smaller jobs' surplus blocks exit at once
+      multi_pack_kernel<<<dim3(128, m), 256, 0, st>>>(pj);
       B200_LAUNCH_CHECK();
     }
     return 0;
@@ -641,7 +642,11 @@ struct Exec {
       EpPatch ep = {w.x0, H, L, P[P_PATCH_B], P[P_POS]};
       if constexpr (kTC) {
         long tot = (long)M * 4096 * c.Cin;
-        patch_gather_kernel<<<(unsigned)min(148L * 8, (tot + 255) / 256), 256, 0, st>>>(x_in, w.apatch, c.Cin, c.S0, c.S1, c.S2, g0, g1, g2, c.conv_patch, tot);
+        // S2 % 16 == 0 (img_size is a multiple of the patch size), so 8-voxel groups of a patch line are 32-byte aligned in an fp32 volume
+        if ((c.conv_patch || c.Cin == 1) && tot / 8 < (1L << 31) && ((uintptr_t)x_in & 15) == 0)
+          patch_gather8_kernel<<<(unsigned)min(148L * 8, (tot / 8 + 255) / 256), 256, 0, st>>>(x_in, w.apatch, c.Cin, c.S0, c.S1, c.S2, g0, g1, g2, (int)(tot / 8));
+        else
+          patch_gather_kernel<<<(unsigned)min(148L * 8, (tot + 255) / 256), 256, 0, st>>>(x_in, w.apatch, c.Cin, c.S0, c.S1, c.S2, g0, g1, g2, c.conv_patch, tot);
         B200_LAUNCH_CHECK();
         B200_TRY(tc::gemm(tc::operand(w.apatch, 4096L * c.Cin, 1), tc::operand(w.wpatch, 4096L * c.Cin, 1), ep, M, H, 4096 * c.Cin, 1, 1, st));
       } else {

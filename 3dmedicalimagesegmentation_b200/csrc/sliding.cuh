@@ -174,34 +174,44 @@ struct SwSlab { int d0, nd, acc_xoff, acc_rows, out_d0, out_rows; };
 static __global__ void sw_finalize_kernel(const float* __restrict__ acc, float* __restrict__ out, unsigned char* __restrict__ mask,
                                    SwGeom g, SwStarts st, const float* __restrict__ labels, double* __restrict__ counts, SwSlab sl) {
   const long vox = (long)g.D * g.H * g.W;
-  const long vox_slab = (long)sl.nd * g.H * g.W, vbase = (long)sl.d0 * g.H * g.W;
   const int b = blockIdx.y;                       // one sample per grid row: the block's histogram belongs to one sample
   __shared__ unsigned int hist[3 * 32];
   if (counts) {
     for (int i = threadIdx.x; i < 3 * 32; i += blockDim.x) hist[i] = 0u;
     __syncthreads();
   }
-  for (long rs = (long)blockIdx.x * blockDim.x + threadIdx.x; rs < vox_slab; rs += (long)gridDim.x * blockDim.x) {
-    const long r0 = vbase + rs;
-    long r = r0;
-    int w = (int)(r % g.W); r /= g.W; int h = (int)(r % g.H); int d = (int)(r / g.H);
-    int x = d + g.pd, y = h + g.ph, z = w + g.pw;
-    int c0 = 0, c1 = 0, c2 = 0;
+  // a block walks (d, h) lines, its threads the w of a line: one division per line and block instead of two 64-bit div/mod per voxel;
+  // the window counts along x and y are per line, only the z count is per voxel
+  const long lines = (long)sl.nd * g.H;
+  for (long line = blockIdx.x; line < lines; line += gridDim.x) {
+    const int dd = (int)(line / g.H), h = (int)(line - (long)dd * g.H), d = sl.d0 + dd;
+    const int x = d + g.pd, y = h + g.ph;
+    int c0 = 0, c1 = 0;
     for (int i = 0; i < st.n0; ++i) c0 += (x >= st.s0[i] && x < st.s0[i] + g.r0);
     for (int i = 0; i < st.n1; ++i) c1 += (y >= st.s1[i] && y < st.s1[i] + g.r1);
-    for (int i = 0; i < st.n2; ++i) c2 += (z >= st.s2[i] && z < st.s2[i] + g.r2);
-    float cnt = (float)(c0 * c1 * c2);
-    float best = -INFINITY; int arg = 0;
-    for (int c = 0; c < g.C; ++c) {
-      float v = acc[((((long)b * g.C + c) * sl.acc_rows + (x - sl.acc_xoff)) * g.PH + y) * g.PW + z] / cnt;
-      if (out) out[(((long)b * g.C + c) * sl.out_rows + (d - sl.out_d0)) * g.H * g.W + (long)h * g.W + w] = v;
-      if (v > best) { best = v; arg = c; }
-    }
-    if (mask) mask[(long)b * vox + r0] = (unsigned char)arg;
-    if (counts) {
-      int t = (int)labels[(long)b * vox + r0];
-      atomicAdd(&hist[3 * arg + 1], 1u);
-      if ((unsigned)t < (unsigned)g.C) { atomicAdd(&hist[3 * t + 2], 1u); if (t == arg) atomicAdd(&hist[3 * t], 1u); }
+    const float* aline = acc + ((((long)b * g.C) * sl.acc_rows + (x - sl.acc_xoff)) * g.PH + y) * g.PW + g.pw;
+    const long cstride_a = (long)sl.acc_rows * g.PH * g.PW;
+    float* oline = out ? out + (((long)b * g.C) * sl.out_rows + (d - sl.out_d0)) * g.H * g.W + (long)h * g.W : nullptr;
+    const long cstride_o = (long)sl.out_rows * g.H * g.W;
+    const long r_line = ((long)d * g.H + h) * g.W;
+    for (int w = threadIdx.x; w < g.W; w += blockDim.x) {
+      const int z = w + g.pw;
+      int c2 = 0;
+      for (int i = 0; i < st.n2; ++i) c2 += (z >= st.s2[i] && z < st.s2[i] + g.r2);
+      const float cnt = (float)(c0 * c1 * c2);
+      float best = -INFINITY; int arg = 0;
+      for (int c = 0; c < g.C; ++c) {
+        const float v = aline[c * cstride_a + w] / cnt;
+        if (oline) oline[c * cstride_o + w] = v;
+        if (v > best) { best = v; arg = c; }
+      }
+      const long r0 = r_line + w;
+      if (mask) mask[(long)b * vox + r0] = (unsigned char)arg;
+      if (counts) {
+        int t = (int)labels[(long)b * vox + r0];
+        atomicAdd(&hist[3 * arg + 1], 1u);
+        if ((unsigned)t < (unsigned)g.C) { atomicAdd(&hist[3 * t + 2], 1u); if (t == arg) atomicAdd(&hist[3 * t], 1u); }
+      }
     }
   }
   if (counts) {
