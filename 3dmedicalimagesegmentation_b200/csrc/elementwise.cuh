@@ -507,18 +507,21 @@ static __global__ void rowsum_atomic_kernel(const float* __restrict__ x, float* 
 
 // Pixel-unshuffle of the 2x up-sampled channels-last tensor y (window coff..coff+Co of pitch) into the GEMM operand
 // U[v_in][tap*Co + co]  (tap = (a*2+b)*2+c of the k2s2 transposed conv).  16-byte moves both ways.
-template <class T>
+// IDX = unsigned when the element count fits 32 bits (every shape of the benchmark): eight div/mod per 16-byte move are then 32-bit.
+template <class T, class IDX>
 __global__ void unshuffle_kernel(const T* __restrict__ y, ClView yv, int Co, int N, int D, int H, int W, T* __restrict__ U) {
   pdl_wait();
   constexpr int VN = Vec16<T>::N;
-  int lanes = Co / VN;
-  long total = (long)N * D * H * W * 8 * lanes;
-  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
-    int lv = (int)(e % lanes); long r = e / lanes; int tap = (int)(r & 7); long v = r >> 3;
-    int w = (int)(v % W); long t = v / W; int h = (int)(t % H); t /= H; int d = (int)(t % D); long n = t / D;
-    long pos = ((n * 2 * D + 2 * d + (tap >> 2)) * 2 * H + 2 * h + ((tap >> 1) & 1)) * 2 * W + 2 * w + (tap & 1);
+  const IDX lanes = (IDX)(Co / VN);
+  const IDX total = (IDX)N * D * H * W * 8 * lanes;
+  for (IDX e = (IDX)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (IDX)gridDim.x * blockDim.x) {
+    const IDX r = e / lanes; const int lv = (int)(e - r * lanes); const int tap = (int)(r & 7); const IDX v = r >> 3;
+    IDX t = v / (IDX)W; const int w = (int)(v - t * (IDX)W);
+    IDX t2 = t / (IDX)H; const int h = (int)(t - t2 * (IDX)H);
+    const IDX n = t2 / (IDX)D; const int d = (int)(t2 - n * (IDX)D);
+    long pos = (((long)n * 2 * D + 2 * d + (tap >> 2)) * 2 * H + 2 * h + ((tap >> 1) & 1)) * 2 * W + 2 * w + (tap & 1);
     Vec16<T> a; a.load(y + pos * yv.pitch + yv.coff + lv * VN);
-    a.store(U + v * 8 * Co + tap * Co + lv * VN);
+    a.store(U + (long)v * 8 * Co + tap * Co + lv * VN);
   }
 }
 // fp32 [Ci][Co][8] -> bf16 [Ci][8][Co]  (tap-major copy of a transposed-conv weight)

@@ -1103,7 +1103,11 @@ struct Exec {
         int Co = dy.C, rows = (int)s.rows(), K8 = 8 * Co;
         { B200_PROFD(st, "convT_unshuffle %d @%d", Co, s.D);
           long tot = (long)rows * 8 * (Co / VN);
-          B200_CUDA(launch_pdl(unshuffle_kernel<T>, dim3((unsigned)min(148L * 16, (tot + 255) / 256)), dim3(256), 0, st, dy.p, ClView{dy.pitch, dy.coff}, Co, s.N, s.D, s.H, s.W, w.unsh));
+          const dim3 ug((unsigned)min(148L * 16, (tot + 255) / 256));
+          if (tot + (long)ug.x * 256 < (1L << 32))
+            B200_CUDA(launch_pdl(unshuffle_kernel<T, unsigned>, ug, dim3(256), 0, st, dy.p, ClView{dy.pitch, dy.coff}, Co, s.N, s.D, s.H, s.W, w.unsh));
+          else
+            B200_CUDA(launch_pdl(unshuffle_kernel<T, long>, ug, dim3(256), 0, st, dy.p, ClView{dy.pitch, dy.coff}, Co, s.N, s.D, s.H, s.W, w.unsh));
           B200_LAUNCH_CHECK(); }
         if (dW) {   // dW[ci][co*8+tap] = sum_v x[v,ci] U[v, tap*Co+co]   (voxels = reduction, split-K + atomics)
           B200_PROFD(st, "convT_wgrad %dx%d @%d", Ci, Co, s.D);
