@@ -334,24 +334,6 @@ def main():
     sampler.mark_end()
     clocks = sampler.stop()
 
-    # N > 1: the same step with the conv-stack weight gradients left in place (gradient group 0 reduced first) instead of deferred
-    # behind the ViT backward (group 0 reduced last): both orders measured in this process, the headline uses the module's default
-    wgrad_order = None
-    if ddp is not None and gstep is None and getattr(model, "overlap_grad_reduce", False):
-        default = model.defer_conv_wgrads
-        model.defer_conv_wgrads = not default
-        for i in range(3):
-            step(dev_x[i % 4], dev_y[i % 4])
-        ms_other = timed(lambda i: step(dev_x[i % 4], dev_y[i % 4]), args.steps)
-        model.defer_conv_wgrads = default
-        for i in range(2):
-            step(dev_x[i % 4], dev_y[i % 4])
-        ms_again = timed(lambda i: step(dev_x[i % 4], dev_y[i % 4]), args.steps)
-        wgrad_order = {"default": "deferred" if default else "in_place",
-                       "deferred_ms_per_step": (ms_again if default else ms_other) / args.steps,
-                       "in_place_ms_per_step": (ms_other if default else ms_again) / args.steps,
-                       "note": "measured after the headline region in the same process; 'default' repeats the headline configuration"}
-
     # per-op CUDA-event breakdown of one step -> roofline of the dominant kernel class
     lib.b200_prof_enable(1)
     eager_step(dev_x[0], dev_y[0])
@@ -587,7 +569,7 @@ def main():
                 "tflops_algorithmic": samples * flop_per_sample / (ms * 1e-3) / 1e12,
                 "e2e": {"value": samples / (ms_e2e * 1e-3), "unit": "samples/s",
                         "h2d_bytes_per_step": host_x[0].numel() * 4 + host_y[0].numel() * 4, "d2h_bytes_per_step": 4},
-                "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "sliding_window": sw, "ranking_step": rk, "dp_128": dp128, "augmented_step": aug, "dp_check": dp_check, "dp_wgrad_order": wgrad_order}
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "sliding_window": sw, "ranking_step": rk, "dp_128": dp128, "augmented_step": aug, "dp_check": dp_check}
         sys.stdout.flush()
         os.write(saved_out, (json.dumps(line) + "\n").encode())
     par.shutdown(world)
