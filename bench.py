@@ -79,6 +79,22 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": reasons, "samples": len(sm), "window": window}
 
 
+def cpu_sliding_window_ms_per_window():
+    """The reference's whole-volume inference (oracle restatement of MONAI 0.6.0 `sliding_window_inference` around the oracle UNETR) on
+    all host cores, on a BOUNDED sample: a 144x144x96 volume = 4 windows of 96^3 at overlap 0.5 = one predictor call of sw_batch_size 4.
+    Returns milliseconds per window (the full 512x512x256 volume is 500 windows of the same cost)."""
+    from oracle import unetr_oracle as O
+    torch.set_num_threads(os.cpu_count())
+    model = O.make_model(tuple_output=False).eval()
+    vol = torch.rand(1, 1, 144, 144, 96, generator=torch.Generator().manual_seed(5))
+    with torch.no_grad():
+        O.sliding_window_inference(vol, (96,) * 3, 4, model, overlap=0.5)
+        t0 = time.perf_counter()
+        O.sliding_window_inference(vol, (96,) * 3, 4, model, overlap=0.5)
+        t = time.perf_counter() - t0
+    return 1e3 * t / 4
+
+
 def cpu_reference_step_time(batch, steps, warmup):
     """The reference's arithmetic (oracle restatement of MONAI 0.6.0 UNETR + DiceCELoss; MONAI itself cannot be
     installed here) on all host cores: forward + DiceCE + backward on `batch` 96^3 crops."""
@@ -554,6 +570,11 @@ def main():
         torch.cuda.empty_cache()
 
     cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and sw is not None:
+        # the sliding-window half of the metric on the host cores (bounded sample, extrapolated by window count: every window costs the same)
+        mspw = cpu_sliding_window_ms_per_window()
+        sw["cpu_baseline"] = {"value": 1e3 / (mspw * 500), "unit": "volumes/s", "ms_per_window": mspw, "cores": os.cpu_count(), "kind": "port",
+                              "sample": "oracle sliding_window_inference on a 144x144x96 volume (4 windows of 96^3 = one predictor call), per-window time x 500 windows"}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         t = cpu_reference_step_time(1, 5, 1)
         cpu = {"value": 1 / t, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port",
