@@ -572,9 +572,12 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline and sw is not None:
         # the sliding-window half of the metric on the host cores (bounded sample, extrapolated by window count: every window costs the same)
-        mspw = cpu_sliding_window_ms_per_window()
-        sw["cpu_baseline"] = {"value": 1e3 / (mspw * 500), "unit": "volumes/s", "ms_per_window": mspw, "cores": os.cpu_count(), "kind": "port",
-                              "sample": "oracle sliding_window_inference on a 144x144x96 volume (4 windows of 96^3 = one predictor call), per-window time x 500 windows"}
+        try:
+            mspw = cpu_sliding_window_ms_per_window()
+            sw["cpu_baseline"] = {"value": 1e3 / (mspw * 500), "unit": "volumes/s", "ms_per_window": mspw, "cores": os.cpu_count(), "kind": "port",
+                                  "sample": "oracle sliding_window_inference on a 144x144x96 volume (4 windows of 96^3 = one predictor call), per-window time x 500 windows"}
+        except Exception as exc:      # never lose the bench line to its side measurement
+            sw["cpu_baseline"] = {"error": f"{type(exc).__name__}: {exc}"[:200]}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         t = cpu_reference_step_time(1, 5, 1)
         cpu = {"value": 1 / t, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port",
