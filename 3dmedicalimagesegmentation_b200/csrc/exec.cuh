@@ -643,7 +643,7 @@ struct Exec {
       if constexpr (kTC) {
         long tot = (long)M * 4096 * c.Cin;
         // S2 % 16 == 0 (img_size is a multiple of the patch size), so 8-voxel groups of a patch line are 32-byte aligned in an fp32 volume
-        if ((c.conv_patch || c.Cin == 1) && tot / 8 < (1L << 31) && ((uintptr_t)x_in & 15) == 0)
+        if ((c.conv_patch || c.Cin == 1) && tot / 8 < (1L << 30) && ((uintptr_t)x_in & 15) == 0)
           patch_gather8_kernel<<<(unsigned)min(148L * 8, (tot / 8 + 255) / 256), 256, 0, st>>>(x_in, w.apatch, c.Cin, c.S0, c.S1, c.S2, g0, g1, g2, (int)(tot / 8));
         else
           patch_gather_kernel<<<(unsigned)min(148L * 8, (tot + 255) / 256), 256, 0, st>>>(x_in, w.apatch, c.Cin, c.S0, c.S1, c.S2, g0, g1, g2, c.conv_patch, tot);
