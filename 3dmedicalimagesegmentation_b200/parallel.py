@@ -76,7 +76,7 @@ class GradientAllReduce:
         self.compress = compress
         self._stage16 = None
         self.post = None
-        # overlap: the UNETR backward records an event when each of 4 gradient groups is final; their all-reduces run on a side
+        # overlap: the UNETR backward records an event when each of its gradient groups (UNETR.grad_groups: 7 by default) is final; their all-reduces run on a side
         # stream behind those events while the rest of the backward is still executing (the host enqueues far ahead of the GPU)
         if overlap and world_size > 1 and hasattr(module, "overlap_grad_reduce") and torch.cuda.is_available():
             module.overlap_grad_reduce = True
