@@ -95,6 +95,29 @@ def cpu_sliding_window_ms_per_window():
     return 1e3 * t / 4
 
 
+def cpu_ranking_step_time(batch=8):
+    """configs[2] on the host cores: oracle UNETR forward on `batch` crops of 96^3 -> enc4 -> the reference's 576-triplet Bradley-Terry loss
+    in its own per-triplet form (oracle.bt_ranking_loss, rank:202-212) -> backward.  One untimed and one timed step."""
+    import numpy as np
+    from oracle import unetr_oracle as O
+    torch.set_num_threads(os.cpu_count())
+    model = O.make_model(tuple_output=True)
+    x = torch.rand(batch, 1, 96, 96, 96, generator=torch.Generator().manual_seed(3))
+    np.random.seed(0)
+    t = None
+    for i in range(2):
+        t0 = time.perf_counter()
+        model.zero_grad(set_to_none=True)
+        enc4, _ = model(x)
+        f1, f2 = torch.split(enc4, [batch // 2, batch // 2], dim=0)
+        sd = 2 + i % 3
+        loss = O.bt_ranking_loss(f1, f2, sd, O.slice_indices(f1.shape[sd]), 0.1)
+        loss.backward()
+        float(loss.detach())
+        t = time.perf_counter() - t0
+    return t
+
+
 def cpu_reference_step_time(batch, steps, warmup):
     """The reference's arithmetic (oracle restatement of MONAI 0.6.0 UNETR + DiceCELoss; MONAI itself cannot be
     installed here) on all host cores: forward + DiceCE + backward on `batch` 96^3 crops."""
@@ -108,7 +131,7 @@ def cpu_reference_step_time(batch, steps, warmup):
         model.zero_grad(set_to_none=True)
         loss = O.dice_ce_loss(model(x), y)
         loss.backward()
-        float(loss)
+        float(loss.detach())
         if i >= warmup:
             times.append(time.perf_counter() - t0)
     return sum(times) / len(times)
@@ -578,6 +601,13 @@ def main():
                                   "sample": "oracle sliding_window_inference on a 144x144x96 volume (4 windows of 96^3 = one predictor call), per-window time x 500 windows"}
         except Exception as exc:      # never lose the bench line to its side measurement
             sw["cpu_baseline"] = {"error": f"{type(exc).__name__}: {exc}"[:200]}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and rk is not None:
+        try:
+            t_rk = cpu_ranking_step_time(8)
+            rk["cpu_baseline"] = {"value": 8 / t_rk, "unit": "samples/s", "s_per_step": t_rk, "cores": os.cpu_count(), "kind": "port",
+                                  "sample": "1 timed step (after 1 untimed) of batch 8: oracle UNETR forward -> enc4 -> per-triplet BTLoss form of the reference -> backward, no optimizer step"}
+        except Exception as exc:
+            rk["cpu_baseline"] = {"error": f"{type(exc).__name__}: {exc}"[:200]}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         t = cpu_reference_step_time(1, 5, 1)
         cpu = {"value": 1 / t, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port",
