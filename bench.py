@@ -95,7 +95,7 @@ def cpu_sliding_window_ms_per_window():
     return 1e3 * t / 4
 
 
-def cpu_ranking_step_time(batch=8):
+def cpu_ranking_step_time(batch=4):
     """configs[2] on the host cores: oracle UNETR forward on `batch` crops of 96^3 -> enc4 -> the reference's 576-triplet Bradley-Terry loss
     in its own per-triplet form (oracle.bt_ranking_loss, rank:202-212) -> backward.  One untimed and one timed step."""
     import numpy as np
@@ -603,9 +603,9 @@ def main():
             sw["cpu_baseline"] = {"error": f"{type(exc).__name__}: {exc}"[:200]}
     if rank == 0 and world == 1 and not args.no_cpu_baseline and rk is not None:
         try:
-            t_rk = cpu_ranking_step_time(8)
-            rk["cpu_baseline"] = {"value": 8 / t_rk, "unit": "samples/s", "s_per_step": t_rk, "cores": os.cpu_count(), "kind": "port",
-                                  "sample": "1 timed step (after 1 untimed) of batch 8: oracle UNETR forward -> enc4 -> per-triplet BTLoss form of the reference -> backward, no optimizer step"}
+            t_rk = cpu_ranking_step_time(4)
+            rk["cpu_baseline"] = {"value": 4 / t_rk, "unit": "samples/s", "s_per_step": t_rk, "cores": os.cpu_count(), "kind": "port",
+                                  "sample": "1 timed step (after 1 untimed) of batch 4 (the reference's own batch, rank:251): oracle UNETR forward -> enc4 -> per-triplet BTLoss form of the reference -> backward, no optimizer step"}
         except Exception as exc:
             rk["cpu_baseline"] = {"error": f"{type(exc).__name__}: {exc}"[:200]}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
